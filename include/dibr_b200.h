@@ -1,0 +1,142 @@
+/*
+ * dibr_b200.h -- C ABI of libdibr_b200.so, the B200 (sm_100a) implementation of the DIB-R
+ * differentiable rasterizer on Self6D++'s render-and-compare path.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference):
+ *
+ *   dibr_setup_faces      lib/dr_utils/dib_renderer_x/rasterizer/rasterizer.py:36-70  (prepare_tfpoints:
+ *                         x multiplier, per-face bbox, expanded bbox) at the linear_rasterizer seam.
+ *   dibr_setup_meshes     renderer/vertex_shaders/perpsective.py:71-111 (view transform, 4x4 projection,
+ *                         divide, per-face gather, face normal) + renderer/vcrender_batch.py:49-88
+ *                         (per-sample Python loop, attribute gather + ones channel) + prepare_tfpoints,
+ *                         for a whole ragged batch in one launch.
+ *   dibr_forward          kaolin.graphics.dib_renderer.cuda.rasterizer.forward as called at
+ *                         rasterizer.py:152-172 (kernels dr_cuda_forward_render_batch and
+ *                         dr_cuda_forward_prob_batch of the un-vendored kaolin v0.1).
+ *   dibr_backward_faces   kaolin...rasterizer.backward as called at rasterizer.py:249-269
+ *                         (dr_cuda_backward_color_batch + dr_cuda_backward_prob_batch), returning
+ *                         dldp2 + dldp2_prob and dldc exactly like rasterizer.py:278-291 -- but as a
+ *                         deterministic per-face gather instead of fp32 global atomics.
+ *   dibr_backward_meshes  the torch autograd tail the reference runs after the extension returns:
+ *                         index_select/cat backward (scatter-add to vertices), division and matmul
+ *                         backward down to cam_view_R / cam_view_pos (renderer/base.py:169-170).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says host; fp32 contiguous; the library never
+ *     allocates, frees or retains caller memory (the reference's Python owns every buffer too,
+ *     rasterizer.py:124-148,198-211) and never synchronises the device.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - return 0 on success, non-zero on error; dibr_last_error() gives a thread-local message.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ *
+ * Image/face layout
+ *   images b = 0..batch-1; image b owns faces [face_offsets[b], face_offsets[b+1]) of one global
+ *   face array (total_faces entries).  If face_offsets is NULL every image owns faces_per_image
+ *   faces (the reference's dense b x f layout).  Face index buffers store the face number LOCAL to
+ *   the image plus one (0 = no face), like the reference's imidx (rasterizer.py:124).
+ */
+#ifndef DIBR_B200_H
+#define DIBR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIBR_ABI_VERSION 1
+#define DIBR_MAX_ATTR 12 /* interpolated channels per pixel (the reference uses 4: rgb/xyz/normal + ones) */
+
+typedef struct DibrPass {
+    /* ---- problem size ------------------------------------------------------------------ */
+    int32_t batch;           /* images */
+    int32_t height, width;   /* pixels */
+    int32_t num_attr;        /* D: channels per vertex in face_attr (3*D floats per face) */
+    int32_t knum;            /* soft-silhouette cap K (reference default 30) */
+    int32_t multiplier;      /* reference default 1000 (passed as a C int, rasterizer.py:170) */
+    int32_t delta;           /* reference default 7000 ("sigmainv") */
+    float expand;            /* reference default 0.02 */
+    int32_t total_faces;     /* faces over all images */
+    int32_t faces_per_image; /* used when face_offsets == NULL */
+    const int32_t *face_offsets; /* [batch+1] or NULL */
+
+    /* ---- operator-seam inputs (dibr_setup_faces) ------------------------------------------ */
+    const float *points3d;   /* [total_faces, 9] view-space xyz of the 3 corners (only z is read) */
+    const float *points2d;   /* [total_faces, 6] NDC xy of the 3 corners, NOT yet multiplied */
+    const float *normalz;    /* [total_faces]    z of the face normal; < 0 = back face */
+
+    /* ---- fused inputs (dibr_setup_meshes / dibr_backward_meshes) ---------------------------- */
+    int32_t num_instances;          /* objects with a pose; the batch modes have one per image */
+    const int32_t *inst_desc;       /* [num_instances, 12]: vert_base, num_verts, mesh_face_base, num_faces,
+                                       out_face_base (ascending), cam_index, proj_index, attr_base,
+                                       gvert_base (row of this instance in grad_verts / grad_vert_attr),
+                                       image index, 2 reserved */
+    const float *verts;             /* [sum verts, 3] object-space vertices (packed meshes) */
+    const int32_t *mesh_faces;      /* [sum mesh faces, 3] vertex ids local to the mesh */
+    const float *vert_attr;         /* [sum verts(attr space), vert_attr_dim] per-vertex attributes */
+    int32_t vert_attr_dim;          /* channels read per vertex */
+    int32_t attr_flags;             /* bit0: append a ones channel (vcrender_batch.py:87-88);
+                                       bit1: append view depth -z_view (= z of R v + t,
+                                       renderer_dibr.py:296-301) as one more channel */
+    const float *cam_rot;           /* [ncam, 9]  cam_view_R = diag(1,-1,-1) R   (base.py:169) */
+    const float *cam_pos;           /* [ncam, 3]  cam_view_pos = -(R^T t)        (base.py:170) */
+    const float *cam_proj;          /* [nproj, 16] row-major 4x4 used as [p,1] @ proj (perspective.py:122-129) */
+
+    /* ---- workspace written by set-up, read by forward/backward (sizes: dibr_workspace_bytes) - */
+    void *workspace;
+    size_t workspace_bytes;
+    float *face_attr;        /* [total_faces, 3, D] per-face corner attributes.  Seam mode: the caller's
+                                vertex_attr_bxfx3d (read-only).  Fused mode: written by set-up. */
+    float *face_normal;      /* optional [total_faces, 3]: normalised face normal (vcrender_batch.py:79) */
+
+    /* ---- forward outputs ----------------------------------------------------------------- */
+    float *im;               /* [batch, H, W, D] interpolated attributes (0 where uncovered) */
+    float *improb;           /* [batch, H, W]    soft silhouette probability */
+    int32_t *imidx;          /* [batch, H, W]    >0: local face id + 1 of the covering face;
+                                                 0: uncovered, every near face counted;
+                                                 <0: uncovered, only faces with id+1 <= -value counted
+                                                 (the K-th accepted face: first-K-in-index-order rule) */
+    float *imcomp;           /* [batch, H, W]    prod_k (1 - p_k) over the accepted faces of an uncovered pixel
+                                                 (= 1 - improb, kept separately at full relative precision;
+                                                 saved for the backward, 0 where covered) */
+
+    /* ---- backward inputs / outputs --------------------------------------------------------- */
+    const float *grad_im;     /* [batch, H, W, D] or NULL */
+    const float *grad_improb; /* [batch, H, W]    or NULL */
+    float *grad_points2d;     /* [total_faces, 6]  dL/d points2d (un-multiplied NDC), colour + soft parts */
+    float *grad_face_attr;    /* [total_faces, 3, D] */
+    float *grad_verts;        /* optional [sum over instances of num_verts, 3] (fused), row gvert_base + v */
+    float *grad_vert_attr;    /* optional [sum over instances of num_verts, vert_attr_dim] (fused) */
+    float *grad_cam_rot;      /* [num_instances, 9] (fused): dL/d cam_view_R of the instance's camera */
+    float *grad_cam_pos;      /* [num_instances, 3] (fused) */
+    const int32_t *vert_face_ptr;  /* CSR vertex -> incident (face,corner) list, per packed mesh vertex: [sum verts + 1] */
+    const int32_t *vert_face_idx;  /* [3 * sum mesh faces] entries face*3+corner, ascending */
+    int32_t num_cams;
+    int32_t reserved0;
+} DibrPass;
+
+int dibr_abi_version(void);
+/* sizeof(DibrPass) as compiled, so a binding can verify its struct mirror */
+int dibr_sizeof_pass(void);
+const char *dibr_last_error(void);
+
+/* number of CUDA devices visible to the library (0 when there is no driver/GPU) */
+int dibr_device_count(void);
+
+/* bytes of workspace needed for a pass of this size (host-side arithmetic only) */
+int dibr_workspace_bytes(const DibrPass *pass, size_t *bytes);
+
+int dibr_setup_faces(const DibrPass *pass, void *stream);
+int dibr_setup_meshes(const DibrPass *pass, void *stream);
+int dibr_forward(const DibrPass *pass, void *stream);
+int dibr_backward_faces(const DibrPass *pass, void *stream);
+int dibr_backward_meshes(const DibrPass *pass, void *stream);
+
+/* how many kernels the library has launched on this thread since the last reset (bench evidence) */
+long long dibr_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIBR_B200_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of libdibr_b200.so (C ABI declared in include/dibr_b200.h).
+
+The library is built in-tree by ``self6dpp_b200/csrc/Makefile`` (``__graft_entry__.build()`` runs
+it).  There is deliberately no fallback of any kind: if the shared object is missing, or the
+process has no CUDA device, the compute entry points raise.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdibr_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dibr_b200.h")
+
+_c_f32p = ctypes.c_void_p
+_c_i32p = ctypes.c_void_p
+
+
+class DibrPass(ctypes.Structure):
+    """Mirror of ``struct DibrPass`` -- field order and types must match include/dibr_b200.h."""
+
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+        ("num_attr", ctypes.c_int32), ("knum", ctypes.c_int32), ("multiplier", ctypes.c_int32),
+        ("delta", ctypes.c_int32), ("expand", ctypes.c_float), ("total_faces", ctypes.c_int32),
+        ("faces_per_image", ctypes.c_int32), ("face_offsets", _c_i32p),
+        ("points3d", _c_f32p), ("points2d", _c_f32p), ("normalz", _c_f32p),
+        ("num_instances", ctypes.c_int32), ("inst_desc", _c_i32p), ("verts", _c_f32p),
+        ("mesh_faces", _c_i32p), ("vert_attr", _c_f32p), ("vert_attr_dim", ctypes.c_int32),
+        ("attr_flags", ctypes.c_int32), ("cam_rot", _c_f32p), ("cam_pos", _c_f32p), ("cam_proj", _c_f32p),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("face_attr", _c_f32p), ("face_normal", _c_f32p),
+        ("im", _c_f32p), ("improb", _c_f32p), ("imidx", _c_i32p), ("imcomp", _c_f32p),
+        ("grad_im", _c_f32p), ("grad_improb", _c_f32p), ("grad_points2d", _c_f32p),
+        ("grad_face_attr", _c_f32p), ("grad_verts", _c_f32p), ("grad_vert_attr", _c_f32p),
+        ("grad_cam_rot", _c_f32p), ("grad_cam_pos", _c_f32p),
+        ("vert_face_ptr", _c_i32p), ("vert_face_idx", _c_i32p),
+        ("num_cams", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+    ]
+
+
+EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_device_count", "dibr_workspace_bytes",
+           "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
+           "dibr_backward_meshes", "dibr_launch_count"]
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libdibr_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("building libdibr_b200.so failed")
+    return LIB_PATH
+
+
+def load():
+    """Load the shared library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(self6dpp_b200 has no CPU or PyTorch fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.dibr_abi_version.restype = ctypes.c_int
+    lib.dibr_last_error.restype = ctypes.c_char_p
+    lib.dibr_device_count.restype = ctypes.c_int
+    lib.dibr_launch_count.restype = ctypes.c_longlong
+    lib.dibr_launch_count.argtypes = [ctypes.c_int]
+    lib.dibr_workspace_bytes.argtypes = [ctypes.POINTER(DibrPass), ctypes.POINTER(ctypes.c_size_t)]
+    for name in ("dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces", "dibr_backward_meshes"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrPass), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    if lib.dibr_abi_version() != 1:
+        raise RuntimeError("libdibr_b200.so ABI version mismatch")
+    if lib.dibr_sizeof_pass() != ctypes.sizeof(DibrPass):
+        raise RuntimeError("DibrPass mirror out of date: C sizeof %d != ctypes %d"
+                           % (lib.dibr_sizeof_pass(), ctypes.sizeof(DibrPass)))
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        raise RuntimeError(f"{what} failed: {load().dibr_last_error().decode()}")
+
+
+def workspace_bytes(p):
+    n = ctypes.c_size_t(0)
+    check(load().dibr_workspace_bytes(ctypes.byref(p), ctypes.byref(n)), "dibr_workspace_bytes")
+    return n.value
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,184 @@
+// extern "C" boundary of libdibr_b200.so (see include/dibr_b200.h): argument validation, workspace
+// carving and launch of the kernels.  No torch types, no allocation, no device synchronisation.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/dibr_b200.h"
+#include "dibr_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local long long g_launches = 0;
+
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+int cuda_fail(const char* what, int code) {
+    if (code == 0) return 0;
+    return fail("%s: CUDA error %d (%s)", what, code, cudaGetErrorString((cudaError_t)code));
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+dibr::Workspace carve(const DibrPass* p, void* base) {
+    dibr::Workspace w;
+    size_t off = 0;
+    char* b = (char*)base;
+    auto take = [&](size_t bytes) { void* r = b ? (void*)(b + off) : nullptr; off += align_up(bytes, 256); return r; };
+    w.recs = (dibr::FaceRec*)take(sizeof(dibr::FaceRec) * (size_t)p->total_faces);
+    w.bbox = (float4*)take(sizeof(float4) * (size_t)p->total_faces);
+    w.imgbox = (uint4*)take(sizeof(uint4) * (size_t)p->batch);
+    w.xs = (float*)take(sizeof(float) * (size_t)p->width);
+    w.ys = (float*)take(sizeof(float) * (size_t)p->height);
+    w.pose_part = (float*)take(sizeof(float) * 12 * dibr::POSE_BLOCKS * (size_t)(p->num_instances > 0 ? p->num_instances : 0));
+    w.bytes = off;
+    return w;
+}
+
+int check_common(const DibrPass* p, bool need_ws) {
+    if (!p) return fail("null DibrPass");
+    if (p->batch <= 0 || p->height <= 0 || p->width <= 0) return fail("bad image size b=%d h=%d w=%d", p->batch, p->height, p->width);
+    if (p->num_attr <= 0 || p->num_attr > DIBR_MAX_ATTR) return fail("num_attr=%d outside [1,%d]", p->num_attr, DIBR_MAX_ATTR);
+    if (p->knum < 0 || p->knum > 250) return fail("knum=%d outside [0,250]", p->knum);
+    if (p->multiplier <= 0 || p->delta < 0) return fail("bad multiplier/delta");
+    if (p->total_faces < 0) return fail("total_faces < 0");
+    if (!p->face_offsets && (long long)p->faces_per_image * p->batch != (long long)p->total_faces)
+        return fail("faces_per_image*batch != total_faces and no face_offsets given");
+    if ((long long)p->batch * p->height * p->width >= (1ll << 31)) return fail("image batch too large for 32-bit pixel ids");
+    if (need_ws) {
+        if (!p->workspace) return fail("workspace is null");
+        if (((uintptr_t)p->workspace & 255u) != 0) return fail("workspace must be 256-byte aligned");
+        const dibr::Workspace w = carve(p, nullptr);
+        if (p->workspace_bytes < w.bytes) return fail("workspace too small: %zu < %zu", p->workspace_bytes, w.bytes);
+    }
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    return 0;
+}
+
+dibr::SetupParams setup_params(const DibrPass* p) {
+    dibr::SetupParams s;
+    memset(&s, 0, sizeof(s));
+    s.batch = p->batch; s.height = p->height; s.width = p->width; s.multiplier = p->multiplier;
+    s.total_faces = p->total_faces; s.faces_per_image = p->faces_per_image; s.face_offsets = p->face_offsets;
+    s.points3d = p->points3d; s.points2d = p->points2d; s.normalz = p->normalz;
+    s.num_instances = p->num_instances; s.inst_desc = p->inst_desc; s.verts = p->verts; s.mesh_faces = p->mesh_faces;
+    s.vert_attr = p->vert_attr; s.vert_attr_dim = p->vert_attr_dim; s.attr_flags = p->attr_flags; s.num_attr = p->num_attr;
+    s.cam_rot = p->cam_rot; s.cam_pos = p->cam_pos; s.cam_proj = p->cam_proj;
+    s.face_attr = p->face_attr; s.face_normal = p->face_normal;
+    s.ws = carve(p, p->workspace);
+    return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dibr_abi_version(void) { return DIBR_ABI_VERSION; }
+
+int dibr_sizeof_pass(void) { return (int)sizeof(DibrPass); }
+
+const char* dibr_last_error(void) { return g_err; }
+
+int dibr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+long long dibr_launch_count(int reset) {
+    const long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int dibr_workspace_bytes(const DibrPass* p, size_t* bytes) {
+    if (!p || !bytes) return fail("null argument");
+    if (p->batch <= 0 || p->height <= 0 || p->width <= 0 || p->total_faces < 0) return fail("bad sizes");
+    *bytes = carve(p, nullptr).bytes;
+    return 0;
+}
+
+int dibr_setup_faces(const DibrPass* p, void* stream) {
+    if (int e = check_common(p, true)) return e;
+    if (!p->points3d || !p->points2d || !p->normalz) return fail("setup_faces: points3d/points2d/normalz required");
+    const dibr::SetupParams s = setup_params(p);
+    g_launches += 1;
+    return cuda_fail("dibr_setup_faces", dibr::launch_setup_faces(s, (cudaStream_t)stream));
+}
+
+int dibr_setup_meshes(const DibrPass* p, void* stream) {
+    if (int e = check_common(p, true)) return e;
+    if (p->num_instances <= 0 || !p->inst_desc || !p->verts || !p->mesh_faces || !p->cam_rot || !p->cam_pos || !p->cam_proj)
+        return fail("setup_meshes: instances, verts, mesh_faces and cameras required");
+    if (!p->face_attr) return fail("setup_meshes: face_attr output required");
+    const int d = p->vert_attr_dim + ((p->attr_flags & 1) ? 1 : 0) + ((p->attr_flags & 2) ? 1 : 0);
+    if (d != p->num_attr) return fail("setup_meshes: vert_attr_dim + flags = %d but num_attr = %d", d, p->num_attr);
+    if (p->vert_attr_dim > 0 && !p->vert_attr) return fail("setup_meshes: vert_attr is null");
+    const dibr::SetupParams s = setup_params(p);
+    g_launches += 1;
+    return cuda_fail("dibr_setup_meshes", dibr::launch_setup_meshes(s, (cudaStream_t)stream));
+}
+
+int dibr_forward(const DibrPass* p, void* stream) {
+    if (int e = check_common(p, true)) return e;
+    if (!p->face_attr || !p->im || !p->improb || !p->imidx || !p->imcomp) return fail("forward: face_attr/im/improb/imidx/imcomp required");
+    const dibr::Workspace w = carve(p, p->workspace);
+    dibr::FwdParams f;
+    memset(&f, 0, sizeof(f));
+    f.batch = p->batch; f.height = p->height; f.width = p->width; f.num_attr = p->num_attr; f.knum = p->knum;
+    f.multiplier = p->multiplier; f.delta = p->delta;
+    f.expand_mul = (float)((double)p->expand * (double)p->multiplier);
+    f.faces_per_image = p->faces_per_image; f.face_offsets = p->face_offsets;
+    f.recs = w.recs; f.bbox = w.bbox; f.imgbox = w.imgbox; f.face_attr = p->face_attr;
+    f.im = p->im; f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
+    g_launches += 1;
+    return cuda_fail("dibr_forward", dibr::launch_forward(f, (cudaStream_t)stream));
+}
+
+int dibr_backward_faces(const DibrPass* p, void* stream) {
+    if (int e = check_common(p, true)) return e;
+    if (!p->face_attr || !p->improb || !p->imidx || !p->imcomp) return fail("backward_faces: saved forward buffers required");
+    if (!p->grad_points2d || !p->grad_face_attr) return fail("backward_faces: grad outputs required");
+    const dibr::Workspace w = carve(p, p->workspace);
+    dibr::BwdParams b;
+    memset(&b, 0, sizeof(b));
+    b.batch = p->batch; b.height = p->height; b.width = p->width; b.num_attr = p->num_attr; b.knum = p->knum;
+    b.multiplier = p->multiplier; b.delta = p->delta;
+    b.expand_mul = (float)((double)p->expand * (double)p->multiplier);
+    b.total_faces = p->total_faces; b.faces_per_image = p->faces_per_image; b.face_offsets = p->face_offsets;
+    b.recs = w.recs; b.xs = w.xs; b.ys = w.ys; b.face_attr = p->face_attr;
+    b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx;
+    b.grad_im = p->grad_im; b.grad_improb = p->grad_improb;
+    b.grad_points2d = p->grad_points2d; b.grad_face_attr = p->grad_face_attr;
+    g_launches += 1;
+    return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream));
+}
+
+int dibr_backward_meshes(const DibrPass* p, void* stream) {
+    if (int e = check_common(p, true)) return e;
+    if (p->num_instances <= 0 || !p->inst_desc || !p->verts || !p->cam_rot || !p->cam_pos || !p->cam_proj)
+        return fail("backward_meshes: instances, verts and cameras required");
+    if (!p->grad_points2d || !p->grad_face_attr || !p->vert_face_ptr || !p->vert_face_idx) return fail("backward_meshes: face grads and vertex adjacency required");
+    if (!p->grad_cam_rot || !p->grad_cam_pos) return fail("backward_meshes: grad_cam_rot/grad_cam_pos required");
+    const dibr::Workspace w = carve(p, p->workspace);
+    dibr::MeshBwdParams m;
+    memset(&m, 0, sizeof(m));
+    m.num_instances = p->num_instances; m.inst_desc = p->inst_desc; m.verts = p->verts;
+    m.cam_rot = p->cam_rot; m.cam_pos = p->cam_pos; m.cam_proj = p->cam_proj;
+    m.vert_attr_dim = p->vert_attr_dim; m.attr_flags = p->attr_flags; m.num_attr = p->num_attr;
+    m.grad_points2d = p->grad_points2d; m.grad_face_attr = p->grad_face_attr;
+    m.vert_face_ptr = p->vert_face_ptr; m.vert_face_idx = p->vert_face_idx;
+    m.grad_verts = p->grad_verts; m.grad_vert_attr = p->grad_vert_attr;
+    m.grad_cam_rot = p->grad_cam_rot; m.grad_cam_pos = p->grad_cam_pos; m.pose_part = w.pose_part;
+    g_launches += 2;
+    return cuda_fail("dibr_backward_meshes", dibr::launch_backward_meshes(m, (cudaStream_t)stream));
+}
+
+}  // extern "C"

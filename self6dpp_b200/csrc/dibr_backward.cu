@@ -1,0 +1,349 @@
+// Backward pass of the B200 DIB-R rasterizer -- deterministic, no global atomics.
+//
+// The reference (kaolin v0.1 dr_cuda_backward_color_batch / dr_cuda_backward_prob_batch, called at
+// /root/reference/lib/dr_utils/dib_renderer_x/rasterizer/rasterizer.py:249-269) runs one thread per
+// PIXEL and scatters into its face with fp32 atomicAdd (9*D + up to 4*K atomics per pixel, order
+// undefined).  Here the loop is turned inside out: 8 lanes own one FACE, walk the pixel centres
+// inside its bbox (colour part) and expanded bbox (soft part), pick up the pixels that belong to
+// it (imidx == face+1, or uncovered with the face among the first K), accumulate in registers in a
+// fixed order and reduce with a fixed shuffle tree.  Every output element is written exactly once.
+//
+// Algebra used (see DESIGN.md "Backward"): with acc[i][d] = sum_pix w_i * dL/dI_d (which IS
+// dL/dattr, rasterizer.py:278-291 'dldc'),  A_i = sum_d (c1-c0)_d acc[i][d],
+// B_i = sum_d (c2-c0)_d acc[i][d], the reference's per-pixel coordinate gradient sums to
+//   dL/dP_i = multiplier / k3 * ( -q A_i + p B_i ,  n A_i - m B_i ),
+// so the colour part needs no per-pixel coordinate work at all.
+#include "dibr_internal.h"
+
+namespace dibr {
+
+// first column c in [0,W] with xs[c] >= x  (xs ascending)
+__device__ __forceinline__ int col_lower(const float* __restrict__ xs, int W, float x, float scale) {
+    const float e = ceilf((x * scale + (float)(W - 1)) * 0.5f);
+    int c = (int)fminf(fmaxf(e, 0.f), (float)W);
+    while (c > 0 && xs[c - 1] >= x) c--;
+    while (c < W && xs[c] < x) c++;
+    return c;
+}
+// first row r in [0,H] with ys[r] < y  (ys descending)
+__device__ __forceinline__ int row_lower(const float* __restrict__ ys, int H, float y, float scale) {
+    const float e = floorf(((float)(H - 1) - y * scale) * 0.5f) + 1.0f;
+    int r = (int)fminf(fmaxf(e, 0.f), (float)H);
+    while (r > 0 && ys[r - 1] < y) r--;
+    while (r < H && ys[r] >= y) r++;
+    return r;
+}
+
+__device__ __forceinline__ int image_of_face_b(int g, int batch, int faces_per_image, const int32_t* __restrict__ off) {
+    if (!off) return g / faces_per_image;
+    int lo = 0, hi = batch;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+
+constexpr int GRP = 8;     // lanes per face
+
+template <int DMAX>
+__global__ void __launch_bounds__(256) backward_faces_kernel(BwdParams P)
+{
+    const int tid = threadIdx.x;
+    const int gl = tid & (GRP - 1);
+    const int g = blockIdx.x * (256 / GRP) + (tid / GRP);
+    const bool active = g < P.total_faces;
+    const int D = P.num_attr;
+    const int W = P.width, H = P.height;
+
+    float acc[3 * DMAX];
+#pragma unroll
+    for (int i = 0; i < 3 * DMAX; i++) acc[i] = 0.f;
+    float gp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    bool any_c = false, any_p = false;
+    FaceRec rec;
+    int b = 0, f = 0;
+
+    if (active) {
+        rec = P.recs[g];
+        b = image_of_face_b(g, P.batch, P.faces_per_image, P.face_offsets);
+        f = g - (P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image);
+        const size_t img = (size_t)b * H * W;
+        const int32_t* __restrict__ idx = P.imidx + img;
+        const float sx = (float)W / (float)P.multiplier, sy = (float)H / (float)P.multiplier;
+
+        // ---- colour part: pixels this face won -------------------------------------------------
+        if (P.grad_im && rec.nz >= 0.0f) {
+            const int c0 = col_lower(P.xs, W, rec.xmin, sx), c1 = col_lower(P.xs, W, rec.xmax, sx);
+            const int r0 = row_lower(P.ys, H, rec.ymax, sy), r1 = row_lower(P.ys, H, rec.ymin, sy);
+            const int nc = c1 - c0, npx = nc * (r1 - r0);
+            if (nc > 0 && npx > 0) {
+                const FaceK fk = make_facek(rec);
+                const float* __restrict__ gim = P.grad_im + img * D;
+                for (int i = gl; i < npx; i += GRP) {
+                    const int r = r0 + i / nc, c = c0 + i % nc;
+                    const size_t pix = (size_t)r * W + c;
+                    if (idx[pix] != f + 1) continue;
+                    float w0, w1, w2;
+                    bary(fk, P.xs[c], P.ys[r], w0, w1, w2);
+                    any_c = true;
+#pragma unroll
+                    for (int d = 0; d < DMAX; d++) {
+                        if (d < D) {
+                            const float gv = __ldg(gim + pix * D + d);
+                            acc[0 * DMAX + d] = fmaf(gv, w0, acc[0 * DMAX + d]);
+                            acc[1 * DMAX + d] = fmaf(gv, w1, acc[1 * DMAX + d]);
+                            acc[2 * DMAX + d] = fmaf(gv, w2, acc[2 * DMAX + d]);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- soft part: uncovered pixels that counted this face ---------------------------------
+        if (P.grad_improb && P.knum > 0) {
+            const float ex = P.expand_mul;
+            const float xmin = rec.xmin - ex, xmax = rec.xmax + ex, ymin = rec.ymin - ex, ymax = rec.ymax + ex;
+            const int c0 = col_lower(P.xs, W, xmin, sx), c1 = col_lower(P.xs, W, xmax, sx);
+            const int r0 = row_lower(P.ys, H, ymax, sy), r1 = row_lower(P.ys, H, ymin, sy);
+            const int nc = c1 - c0, npx = nc * (r1 - r0);
+            if (nc > 0 && npx > 0) {
+                const float mult = (float)P.multiplier;
+                const float zscale = (float)P.delta / (mult * mult);
+                const float sentinel = 4.0f * mult * mult;
+                const float* __restrict__ gpr = P.grad_improb + img;
+                const float* __restrict__ comp = P.imcomp + img;
+                const float px[3] = {rec.ax, rec.bx, rec.cx}, py[3] = {rec.ay, rec.by, rec.cy};
+                for (int i = gl; i < npx; i += GRP) {
+                    const int r = r0 + i / nc, c = c0 + i % nc;
+                    const size_t pix = (size_t)r * W + c;
+                    const int v = idx[pix];
+                    if (v > 0 || (v < 0 && f + 1 > -v)) continue;      // covered, or beyond the K-th face
+                    const float x0 = P.xs[c], y0 = P.ys[r];
+                    const SoftHit h = soft_distance(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, x0, y0, sentinel);
+                    float p, om;
+                    soft_prob(h.d2 * zscale, p, om);
+                    // d improb / d p_k = prod_{j != k}(1 - p_j) = comp / (1 - p_k);  dp/dz = -p;
+                    // z = zscale * d2;  gradient w.r.t. UN-multiplied coordinates carries one more 'mult'
+                    const float coef = -__ldg(gpr + pix) * __ldg(comp + pix) / (om + 1e-15f) * p * zscale * mult;
+                    if (coef == 0.0f) continue;
+                    any_p = true;
+                    if (h.kase >= 3) {
+                        const int k = h.kase - 3;
+                        const float vx = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
+                        const float vy = (k == 0) ? py[0] : ((k == 1) ? py[1] : py[2]);
+                        const float gx = coef * 2.0f * (vx - x0), gy = coef * 2.0f * (vy - y0);
+                        if (k == 0) { gp[0] += gx; gp[1] += gy; }
+                        else if (k == 1) { gp[2] += gx; gp[3] += gy; }
+                        else { gp[4] += gx; gp[5] += gy; }
+                    } else {
+                        const int k = h.kase, k2 = (k + 1) % 3;
+                        const float x1 = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
+                        const float y1 = (k == 0) ? py[0] : ((k == 1) ? py[1] : py[2]);
+                        const float x2 = (k2 == 0) ? px[0] : ((k2 == 1) ? px[1] : px[2]);
+                        const float y2 = (k2 == 0) ? py[0] : ((k2 == 1) ? py[1] : py[2]);
+                        const float exx = x2 - x1, eyy = y2 - y1;
+                        const float s2 = 2.0f * coef / h.len2;
+                        const float gx1 = s2 * ((y0 - y2) * h.cr + h.d2 * exx);
+                        const float gy1 = s2 * (-(x0 - x2) * h.cr + h.d2 * eyy);
+                        const float gx2 = s2 * (-(y0 - y1) * h.cr - h.d2 * exx);
+                        const float gy2 = s2 * ((x0 - x1) * h.cr - h.d2 * eyy);
+                        if (k == 0) { gp[0] += gx1; gp[1] += gy1; gp[2] += gx2; gp[3] += gy2; }
+                        else if (k == 1) { gp[2] += gx1; gp[3] += gy1; gp[4] += gx2; gp[5] += gy2; }
+                        else { gp[4] += gx1; gp[5] += gy1; gp[0] += gx2; gp[1] += gy2; }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- fixed-tree reduction over the 8 lanes of the face ------------------------------------------
+    const unsigned full = 0xffffffffu;
+    const unsigned gmask = 0xffu << ((tid & 31) & ~(GRP - 1));
+    const bool grp_c = (__ballot_sync(full, any_c) & gmask) != 0u;
+    const bool grp_p = (__ballot_sync(full, any_p) & gmask) != 0u;
+    // the shuffles below are warp-wide collectives: every lane of the warp must execute the same
+    // sequence, so the "skip if nothing accumulated" test is made warp-uniform
+    const bool warp_c = __any_sync(full, any_c), warp_p = __any_sync(full, any_p);
+    if (warp_c) {
+#pragma unroll
+        for (int i = 0; i < 3 * DMAX; i++) {
+            float v = acc[i];
+            v += __shfl_xor_sync(full, v, 4);
+            v += __shfl_xor_sync(full, v, 2);
+            v += __shfl_xor_sync(full, v, 1);
+            acc[i] = v;
+        }
+    }
+    if (warp_p) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            float v = gp[i];
+            v += __shfl_xor_sync(full, v, 4);
+            v += __shfl_xor_sync(full, v, 2);
+            v += __shfl_xor_sync(full, v, 1);
+            gp[i] = v;
+        }
+    }
+    if (!active || gl != 0) return;
+
+    float* __restrict__ gpo = P.grad_points2d + (size_t)g * 6;
+    float* __restrict__ gao = P.grad_face_attr + (size_t)g * 3 * D;
+    float out[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) out[i] = grp_p ? gp[i] : 0.f;
+    if (grp_c) {
+        const FaceK fk = make_facek(rec);
+        const float* __restrict__ a = P.face_attr + (size_t)g * 3 * D;
+        float A[3] = {0.f, 0.f, 0.f}, Bv[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int d = 0; d < DMAX; d++) {
+            if (d < D) {
+                const float c0 = a[d], e1 = a[D + d] - c0, e2 = a[2 * D + d] - c0;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    A[i] = fmaf(e1, acc[i * DMAX + d], A[i]);
+                    Bv[i] = fmaf(e2, acc[i * DMAX + d], Bv[i]);
+                }
+            }
+        }
+        // multiplier * k3 / (k3^2 + eps): the reference's multiplier * g / (k3*k3 + eps) times the k3 the
+        // un-normalised dw terms carry
+        const float inv = (float)P.multiplier * fk.k3 / (fk.k3 * fk.k3 + 1e-15f);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            out[2 * i + 0] += inv * (-fk.q * A[i] + fk.p * Bv[i]);
+            out[2 * i + 1] += inv * (fk.n * A[i] - fk.m * Bv[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) gpo[i] = out[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int d = 0; d < DMAX; d++)
+            if (d < D) gao[i * D + d] = grp_c ? acc[i * DMAX + d] : 0.f;
+}
+
+int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
+{
+    if (P.total_faces <= 0) return 0;
+    const int grid = (P.total_faces + (256 / GRP) - 1) / (256 / GRP);
+    if (P.num_attr <= 4) backward_faces_kernel<4><<<grid, 256, 0, stream>>>(P);
+    else if (P.num_attr <= 8) backward_faces_kernel<8><<<grid, 256, 0, stream>>>(P);
+    else backward_faces_kernel<12><<<grid, 256, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------------
+// Fused-mode tail: per-face gradients -> per-vertex (fixed-order gather over the vertex's incident
+// (face,corner) list) -> through divide / projection / view transform -> dL/d cam_view_R, dL/d cam_view_pos
+// (and optionally dL/d vertices, dL/d vertex attributes).  Replaces the torch autograd graph the
+// reference keeps for index_select, cat, division and matmul (perpsective.py:80-101, vcrender_batch.py:84-88).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mesh_vertex_grad_kernel(MeshBwdParams P)
+{
+    const int inst = blockIdx.y;
+    const int32_t* de = P.inst_desc + inst * INST_STRIDE;
+    const int nv = de[I_NUM_VERTS], vbase = de[I_VERT_BASE], fbase = de[I_OUT_FACE_BASE], gvbase = de[I_GVERT_BASE];
+    const float* R = P.cam_rot + (size_t)de[I_CAM] * 9;
+    const float* T = P.cam_pos + (size_t)de[I_CAM] * 3;
+    const float* Pm = P.cam_proj + (size_t)de[I_PROJ] * 16;
+    const int A = P.vert_attr_dim, D = P.num_attr;
+    const int depth_ch = (P.attr_flags & 2) ? (A + ((P.attr_flags & 1) ? 1 : 0)) : -1;
+
+    float s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0.f;
+
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+        const int e0 = P.vert_face_ptr[vbase + v], e1 = P.vert_face_ptr[vbase + v + 1];
+        float g2x = 0.f, g2y = 0.f, gdep = 0.f;
+        float ga[DIBR_MAX_ATTR_INTERNAL];
+#pragma unroll
+        for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) ga[d] = 0.f;
+        for (int e = e0; e < e1; e++) {
+            const int fc = P.vert_face_idx[e];
+            const int gf = fbase + fc / 3, c = fc % 3;
+            g2x += P.grad_points2d[(size_t)gf * 6 + c * 2 + 0];
+            g2y += P.grad_points2d[(size_t)gf * 6 + c * 2 + 1];
+            const float* gfa = P.grad_face_attr + ((size_t)gf * 3 + c) * D;
+            if (P.grad_vert_attr) {
+#pragma unroll
+                for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) if (d < A) ga[d] += gfa[d];
+            }
+            if (depth_ch >= 0) gdep += gfa[depth_ch];
+        }
+        if (P.grad_vert_attr) {
+            float* o = P.grad_vert_attr + (size_t)(gvbase + v) * A;
+#pragma unroll
+            for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) if (d < A) o[d] = ga[d];
+        }
+        // forward recomputation (cheap) for the chain rule
+        const float* vp = P.verts + (size_t)(vbase + v) * 3;
+        const float d0 = vp[0] - T[0], d1 = vp[1] - T[1], d2 = vp[2] - T[2];
+        float pc[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) pc[j] = fmaf(R[j * 3 + 2], d2, fmaf(R[j * 3 + 1], d1, R[j * 3 + 0] * d0));
+        const float cxv = fmaf(pc[2], Pm[8 + 0], fmaf(pc[1], Pm[4 + 0], pc[0] * Pm[0])) + Pm[12 + 0];
+        const float cyv = fmaf(pc[2], Pm[8 + 1], fmaf(pc[1], Pm[4 + 1], pc[0] * Pm[1])) + Pm[12 + 1];
+        const float cwv = fmaf(pc[2], Pm[8 + 3], fmaf(pc[1], Pm[4 + 3], pc[0] * Pm[3])) + Pm[12 + 3];
+        const float iw = 1.0f / cwv;
+        const float gcx = g2x * iw, gcy = g2y * iw;
+        const float gcw = -(g2x * cxv + g2y * cyv) * iw * iw;
+        float gpc[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) gpc[r] = Pm[r * 4 + 0] * gcx + Pm[r * 4 + 1] * gcy + Pm[r * 4 + 3] * gcw;
+        gpc[2] -= gdep;                                  // depth attribute = -z_view
+        float gd[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) gd[k] = R[0 * 3 + k] * gpc[0] + R[1 * 3 + k] * gpc[1] + R[2 * 3 + k] * gpc[2];
+        if (P.grad_verts) {
+            float* o = P.grad_verts + (size_t)(gvbase + v) * 3;
+            o[0] = gd[0]; o[1] = gd[1]; o[2] = gd[2];
+        }
+        const float dd[3] = {d0, d1, d2};
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) s[j * 3 + k] += gpc[j] * dd[k];
+        s[9] -= gd[0]; s[10] -= gd[1]; s[11] -= gd[2];
+    }
+    // fixed-tree block reduction of the 12 pose sums
+    __shared__ float red[8][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        float v = s[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) v += red[w][threadIdx.x];
+        P.pose_part[((size_t)inst * gridDim.x + blockIdx.x) * 12 + threadIdx.x] = v;
+    }
+}
+
+__global__ void pose_finalize_kernel(MeshBwdParams P, int nblocks)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.num_instances * 12) return;
+    const int inst = t / 12, i = t % 12;
+    float v = 0.f;
+    for (int b = 0; b < nblocks; b++) v += P.pose_part[((size_t)inst * nblocks + b) * 12 + i];
+    if (i < 9) P.grad_cam_rot[(size_t)inst * 9 + i] = v;
+    else P.grad_cam_pos[(size_t)inst * 3 + (i - 9)] = v;
+}
+
+int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream)
+{
+    if (P.num_instances <= 0) return 0;
+    dim3 grid(POSE_BLOCKS, P.num_instances);
+    mesh_vertex_grad_kernel<<<grid, 256, 0, stream>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    pose_finalize_kernel<<<(P.num_instances * 12 + 127) / 128, 128, 0, stream>>>(P, POSE_BLOCKS);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dibr

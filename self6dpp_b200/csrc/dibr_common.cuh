@@ -1,0 +1,180 @@
+// Shared device helpers for the B200 DIB-R kernels.  Every arithmetic step that decides
+// coverage (and therefore the bit-exact face-index buffer) is written with explicit
+// round-to-nearest intrinsics so nvcc can neither contract nor reorder it; the order is the one
+// frozen in oracle/dibr_oracle_body.h (which restates kaolin v0.1's dr_cuda_forward_render_batch,
+// reached from /root/reference/lib/dr_utils/dib_renderer_x/rasterizer/rasterizer.py:152).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dibr {
+
+constexpr int TILE = 64;            // forward CTA tile (pixels per side)
+constexpr int FWD_THREADS = 256;
+constexpr int LCAP = 2048;          // faces per in-shared-memory batch of a tile
+constexpr int SUB = 16;             // sub-tile side for the soft-silhouette lists
+constexpr int NSUB = (TILE / SUB) * (TILE / SUB);
+constexpr int SUBCAP = 384;         // entries per sub-tile list
+constexpr int BIGCAP = 128;         // deferred large faces per batch
+constexpr int BIG_AREA = 96;        // pixels of a face inside the tile above which the CTA cooperates
+constexpr int SCAN_CHUNK = 256;     // faces per TMA-staged bbox chunk
+
+// 64 B face record, written by the set-up kernels.
+struct __align__(16) FaceRec {
+    float ax, ay, bx, by;           // 2D corners, already x multiplier
+    float cx, cy, az, bz;           // third corner, view-space z of a and b
+    float cz, nz, pad0, pad1;       // view-space z of c, z of the face normal (< 0: back face)
+    float xmin, ymin, xmax, ymax;   // bbox of the 2D corners (rasterizer.py:49-52)
+};
+
+// float -> unsigned with the same ordering
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// (float)((double)num / ((double)den + 1e-15)), bit-exact.  For |den| >= 32 the double sum
+// den + 1e-15 rounds back to den (half an ulp of a double in [32,64) is 3.6e-15) and a double
+// quotient rounded to float equals the correctly rounded float quotient (53 >= 2*24+2), so the
+// fast path is the IEEE fp32 division.
+__device__ __forceinline__ float div_eps(float num, float den) {
+    if (fabsf(den) >= 32.0f) return __fdiv_rn(num, den);
+    return (float)((double)num / ((double)den + 1e-15));
+}
+
+// per-face constants of the barycentric solve
+struct FaceK {
+    float ax, ay, m, p, n, q, k3;
+    float az, bz, cz;
+};
+
+__device__ __forceinline__ FaceK make_facek(const FaceRec& r) {
+    FaceK k;
+    k.ax = r.ax; k.ay = r.ay;
+    k.m = __fsub_rn(r.bx, r.ax); k.p = __fsub_rn(r.by, r.ay);
+    k.n = __fsub_rn(r.cx, r.ax); k.q = __fsub_rn(r.cy, r.ay);
+    k.k3 = __fmaf_rn(k.m, k.q, -__fmul_rn(k.n, k.p));
+    k.az = r.az; k.bz = r.bz; k.cz = r.cz;
+    return k;
+}
+
+// barycentric weights of pixel centre (x0,y0); returns false when outside (any weight < 0)
+__device__ __forceinline__ bool bary(const FaceK& k, float x0, float y0, float& w0, float& w1, float& w2) {
+    const float s = __fsub_rn(x0, k.ax), t = __fsub_rn(y0, k.ay);
+    const float k1 = __fmaf_rn(s, k.q, -__fmul_rn(k.n, t));
+    const float k2 = __fmaf_rn(k.m, t, -__fmul_rn(s, k.p));
+    w1 = div_eps(k1, k.k3);
+    w2 = div_eps(k2, k.k3);
+    w0 = __fsub_rn(__fsub_rn(1.0f, w1), w2);
+    return !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
+}
+
+__device__ __forceinline__ float blend(float w0, float w1, float w2, float r0, float r1, float r2) {
+    return __fmaf_rn(w2, r2, __fmaf_rn(w0, r0, __fmul_rn(w1, r1)));
+}
+
+// pixel-centre coordinates: "1.0 * multiplier / width * (2*w + 1 - width)" in double, rounded once
+__device__ __forceinline__ float pix_x(int w, int width, int multiplier) {
+    return (float)(1.0 * multiplier / width * (2 * w + 1 - width));
+}
+__device__ __forceinline__ float pix_y(int h, int height, int multiplier) {
+    return (float)(1.0 * multiplier / height * (height - 2 * h - 1));
+}
+
+// Soft-silhouette distance of a pixel to a face: min over the 3 edges (perpendicular distance when
+// the foot lies on the segment, else the sentinel 4 m^2) and the 3 corners, first minimum wins
+// (edge0, edge1, edge2, corner0, corner1, corner2).  Written in local differences, which is better
+// conditioned than the reference's A x + B y + C form; compared with the fp64 oracle at 1e-5.
+struct SoftHit {
+    float d2;       // squared distance, multiplier units
+    int kase;       // 0..5
+    float cr, len2; // edge cases: cross product and squared edge length
+};
+
+__device__ __forceinline__ SoftHit soft_distance(float x1, float y1, float x2, float y2, float x3, float y3,
+                                                 float x0, float y0, float sentinel) {
+    const float dx1 = x0 - x1, dy1 = y0 - y1;
+    const float dx2 = x0 - x2, dy2 = y0 - y2;
+    const float dx3 = x0 - x3, dy3 = y0 - y3;
+    SoftHit h;
+    h.d2 = sentinel; h.kase = 0; h.cr = 0.f; h.len2 = 1.f;
+    float best = 3.0e38f;
+    // edges i -> i+1
+#define DIBR_EDGE(I, DX, DY, XA, YA, XB, YB)                                   \
+    {                                                                            \
+        const float ex = (XB) - (XA), ey = (YB) - (YA);                          \
+        const float len2 = fmaf(ex, ex, ey * ey);                                \
+        const float dot = fmaf((DX), ex, (DY) * ey);                             \
+        const float cr = fmaf((DX), ey, -((DY) * ex));                           \
+        const bool on = (dot >= 0.0f) && (dot <= len2) && (len2 > 0.0f);         \
+        const float d = on ? __fdividef(cr * cr, len2) : sentinel;               \
+        if (best > d) { best = d; h.kase = (I); h.cr = cr; h.len2 = len2; }      \
+    }
+    DIBR_EDGE(0, dx1, dy1, x1, y1, x2, y2)
+    DIBR_EDGE(1, dx2, dy2, x2, y2, x3, y3)
+    DIBR_EDGE(2, dx3, dy3, x3, y3, x1, y1)
+#undef DIBR_EDGE
+    const float v1 = fmaf(dx1, dx1, dy1 * dy1);
+    const float v2 = fmaf(dx2, dx2, dy2 * dy2);
+    const float v3 = fmaf(dx3, dx3, dy3 * dy3);
+    if (best > v1) { best = v1; h.kase = 3; }
+    if (best > v2) { best = v2; h.kase = 4; }
+    if (best > v3) { best = v3; h.kase = 5; }
+    h.d2 = best;
+    return h;
+}
+
+// prob = exp(-z) and om = 1 - prob, both with full relative accuracy
+__device__ __forceinline__ void soft_prob(float z, float& p, float& om) {
+    p = expf(-z);
+    om = (z < 0.25f) ? -expm1f(-z) : (1.0f - p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA (1-D bulk async copy) + mbarrier helpers (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();   // never hang the box on a lost transaction
+    }
+}
+// global -> shared bulk copy; bytes multiple of 16, both addresses 16 B aligned
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace dibr

@@ -1,0 +1,111 @@
+// Internal launch-parameter structs shared by the kernels and the C-ABI translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dibr_common.cuh"
+
+namespace dibr {
+
+// workspace carved out of DibrPass::workspace by dibr_abi.cu
+struct Workspace {
+    FaceRec* recs;      // [total_faces]
+    float4* bbox;       // [total_faces]
+    uint4* imgbox;      // [batch]  ordered maxima of (-xmin,-ymin,xmax,ymax); 0 = empty
+    float* xs;          // [width]  pixel-centre x
+    float* ys;          // [height] pixel-centre y
+    float* pose_part;   // [num_instances * POSE_BLOCKS * 12] partial pose-gradient sums
+    size_t bytes;
+};
+
+#define DIBR_MAX_ATTR_INTERNAL 12
+constexpr int POSE_BLOCKS = 16;   // vertex blocks per instance in the pose-gradient reduction
+
+struct SetupParams {
+    int batch, height, width, multiplier;
+    int total_faces, faces_per_image;
+    const int32_t* face_offsets;
+    // seam mode
+    const float* points3d;
+    const float* points2d;
+    const float* normalz;
+    // fused mode
+    int num_instances;
+    const int32_t* inst_desc;
+    const float* verts;
+    const int32_t* mesh_faces;
+    const float* vert_attr;
+    int vert_attr_dim, attr_flags, num_attr;
+    const float* cam_rot;
+    const float* cam_pos;
+    const float* cam_proj;
+    float* face_attr;
+    float* face_normal;
+    float* points2d_out;     // optional [total_faces,6] un-multiplied NDC (fused mode, for the backward)
+    Workspace ws;
+};
+
+struct FwdParams {
+    int batch, height, width, num_attr, knum, multiplier, delta;
+    float expand_mul;
+    int faces_per_image;
+    const int32_t* face_offsets;
+    const FaceRec* recs;
+    const float4* bbox;
+    const uint4* imgbox;
+    const float* face_attr;
+    float* im;
+    float* improb;
+    float* imcomp;
+    int32_t* imidx;
+};
+
+struct BwdParams {
+    int batch, height, width, num_attr, knum, multiplier, delta;
+    float expand_mul;
+    int total_faces, faces_per_image;
+    const int32_t* face_offsets;
+    const FaceRec* recs;
+    const float* xs;
+    const float* ys;
+    const float* face_attr;
+    const float* improb;
+    const float* imcomp;
+    const int32_t* imidx;
+    const float* grad_im;
+    const float* grad_improb;
+    float* grad_points2d;
+    float* grad_face_attr;
+};
+
+struct MeshBwdParams {
+    int num_instances;
+    const int32_t* inst_desc;
+    const float* verts;
+    const float* cam_rot;
+    const float* cam_pos;
+    const float* cam_proj;
+    int vert_attr_dim, attr_flags, num_attr;
+    const float* grad_points2d;
+    const float* grad_face_attr;
+    const int32_t* vert_face_ptr;
+    const int32_t* vert_face_idx;
+    float* grad_verts;
+    float* grad_vert_attr;
+    float* grad_cam_rot;
+    float* grad_cam_pos;
+    float* pose_part;
+};
+
+constexpr int INST_STRIDE = 12;
+// inst_desc columns
+enum { I_VERT_BASE = 0, I_NUM_VERTS, I_MESH_FACE_BASE, I_NUM_FACES, I_OUT_FACE_BASE, I_CAM, I_PROJ, I_ATTR_BASE,
+       I_GVERT_BASE, I_IMAGE, I_ADJ_BASE, I_RESERVED };
+
+int launch_setup_faces(const SetupParams& P, cudaStream_t stream);
+int launch_setup_meshes(const SetupParams& P, cudaStream_t stream);
+int launch_forward(const FwdParams& P, cudaStream_t stream);
+int launch_backward_faces(const BwdParams& P, cudaStream_t stream);
+int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream);
+
+}  // namespace dibr

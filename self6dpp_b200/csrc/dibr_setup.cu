@@ -1,0 +1,173 @@
+// Face set-up kernels: build the 64 B face records + bbox array the forward/backward kernels read.
+//
+//   setup_faces_kernel   operator-seam mode: inputs are the reference's points3d_bxfx9 /
+//                        points2d_bxfx6 / normalz_bxfx1; replaces prepare_tfpoints
+//                        (/root/reference/lib/dr_utils/dib_renderer_x/rasterizer/rasterizer.py:36-70).
+//   setup_meshes_kernel  fused mode: object-space vertices + per-instance camera; replaces the
+//                        per-sample Python loop of renderer/vcrender_batch.py:49-102 and
+//                        renderer/vertex_shaders/perpsective.py:71-111 (view transform, 4x4
+//                        projection, divide, per-face gather, face normal, attribute gather with
+//                        the ones channel) for the whole ragged batch in ONE launch.  The fp32
+//                        operation order is the one frozen in oracle dibr_oracle_project.
+#include "dibr_internal.h"
+
+namespace dibr {
+
+__device__ __forceinline__ int image_of_face(int g, int batch, int faces_per_image, const int32_t* __restrict__ off) {
+    if (!off) return g / faces_per_image;
+    int lo = 0, hi = batch;              // last b with off[b] <= g
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// union of the faces' bboxes per image, as ordered maxima of (-xmin,-ymin,xmax,ymax)
+__device__ __forceinline__ void image_box_update(uint4* imgbox, int b, bool ok, float xmin, float ymin, float xmax, float ymax) {
+    uint32_t v0 = ok ? f2ord(-xmin) : 0u, v1 = ok ? f2ord(-ymin) : 0u, v2 = ok ? f2ord(xmax) : 0u, v3 = ok ? f2ord(ymax) : 0u;
+    const unsigned full = 0xffffffffu;
+    const int b0 = __shfl_sync(full, b, 0);
+    if (__all_sync(full, b == b0)) {
+        v0 = __reduce_max_sync(full, v0); v1 = __reduce_max_sync(full, v1);
+        v2 = __reduce_max_sync(full, v2); v3 = __reduce_max_sync(full, v3);
+        if ((threadIdx.x & 31) == 0 && b0 >= 0 && v2 != 0u) {
+            atomicMax(&imgbox[b0].x, v0); atomicMax(&imgbox[b0].y, v1);
+            atomicMax(&imgbox[b0].z, v2); atomicMax(&imgbox[b0].w, v3);
+        }
+    } else if (ok && b >= 0) {
+        atomicMax(&imgbox[b].x, v0); atomicMax(&imgbox[b].y, v1);
+        atomicMax(&imgbox[b].z, v2); atomicMax(&imgbox[b].w, v3);
+    }
+}
+
+__device__ __forceinline__ void write_tables(const SetupParams& P, int gtid) {
+    if (gtid < P.width) P.ws.xs[gtid] = pix_x(gtid, P.width, P.multiplier);
+    else if (gtid < P.width + P.height) P.ws.ys[gtid - P.width] = pix_y(gtid - P.width, P.height, P.multiplier);
+}
+
+__device__ __forceinline__ void store_face(const SetupParams& P, int g, int b, float ax, float ay, float bx, float by,
+                                           float cx, float cy, float az, float bz, float cz, float nz, bool active)
+{
+    float xmin = 0.f, ymin = 0.f, xmax = 0.f, ymax = 0.f;
+    bool ok = false;
+    if (active) {
+        xmin = fminf(ax, fminf(bx, cx)); xmax = fmaxf(ax, fmaxf(bx, cx));
+        ymin = fminf(ay, fminf(by, cy)); ymax = fmaxf(ay, fmaxf(by, cy));
+        // non-finite corners make the face invisible (torch.min/max would propagate the NaN)
+        ok = isfinite(ax) && isfinite(ay) && isfinite(bx) && isfinite(by) && isfinite(cx) && isfinite(cy);
+        if (!ok) { xmin = ymin = 3.0e38f; xmax = ymax = -3.0e38f; }
+        FaceRec r;
+        r.ax = ax; r.ay = ay; r.bx = bx; r.by = by; r.cx = cx; r.cy = cy;
+        r.az = az; r.bz = bz; r.cz = cz; r.nz = nz; r.pad0 = 0.f; r.pad1 = 0.f;
+        r.xmin = xmin; r.ymin = ymin; r.xmax = xmax; r.ymax = ymax;
+        P.ws.recs[g] = r;
+        P.ws.bbox[g] = make_float4(xmin, ymin, xmax, ymax);
+    }
+    image_box_update(P.ws.imgbox, active ? b : -1, ok, xmin, ymin, xmax, ymax);
+}
+
+__global__ void __launch_bounds__(256) setup_faces_kernel(SetupParams P)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    write_tables(P, g);
+    const bool active = g < P.total_faces;
+    float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0, az = 0, bz = 0, cz = 0, nz = 0;
+    int b = -1;
+    if (active) {
+        const float m = (float)P.multiplier;
+        const float* p2 = P.points2d + (size_t)g * 6;
+        ax = __fmul_rn(m, p2[0]); ay = __fmul_rn(m, p2[1]);      // rasterizer.py:46
+        bx = __fmul_rn(m, p2[2]); by = __fmul_rn(m, p2[3]);
+        cx = __fmul_rn(m, p2[4]); cy = __fmul_rn(m, p2[5]);
+        const float* p3 = P.points3d + (size_t)g * 9;
+        az = p3[2]; bz = p3[5]; cz = p3[8];
+        nz = P.normalz[g];
+        b = image_of_face(g, P.batch, P.faces_per_image, P.face_offsets);
+    }
+    store_face(P, g, b, ax, ay, bx, by, cx, cy, az, bz, cz, nz, active);
+}
+
+__device__ __forceinline__ int instance_of_face(int g, int n, const int32_t* __restrict__ desc) {
+    int lo = 0, hi = n;                  // last i with out_face_base[i] <= g
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (desc[mid * INST_STRIDE + I_OUT_FACE_BASE] <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) setup_meshes_kernel(SetupParams P)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    write_tables(P, g);
+    const bool active = g < P.total_faces;
+    float x2[3] = {0, 0, 0}, y2[3] = {0, 0, 0}, zc[3] = {0, 0, 0};
+    float nz = 0.f;
+    int b = -1;
+    if (active) {
+        const int inst = instance_of_face(g, P.num_instances, P.inst_desc);
+        const int32_t* de = P.inst_desc + inst * INST_STRIDE;
+        const int lf = g - de[I_OUT_FACE_BASE];
+        b = de[I_IMAGE];
+        const int32_t* fv = P.mesh_faces + (size_t)(de[I_MESH_FACE_BASE] + lf) * 3;
+        const float* R = P.cam_rot + (size_t)de[I_CAM] * 9;
+        const float* T = P.cam_pos + (size_t)de[I_CAM] * 3;
+        const float* Pm = P.cam_proj + (size_t)de[I_PROJ] * 16;
+        const float m = (float)P.multiplier;
+        const int A = P.vert_attr_dim, D = P.num_attr;
+        float pc[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int vid = fv[c];
+            const float* v = P.verts + (size_t)(de[I_VERT_BASE] + vid) * 3;
+            const float d0 = __fsub_rn(v[0], T[0]), d1 = __fsub_rn(v[1], T[1]), d2 = __fsub_rn(v[2], T[2]);
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                pc[c][j] = __fmaf_rn(R[j * 3 + 2], d2, __fmaf_rn(R[j * 3 + 1], d1, __fmul_rn(R[j * 3 + 0], d0)));
+            float clip[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                clip[k] = __fadd_rn(__fmaf_rn(pc[c][2], Pm[8 + k], __fmaf_rn(pc[c][1], Pm[4 + k], __fmul_rn(pc[c][0], Pm[k]))), Pm[12 + k]);
+            const float xn = __fdiv_rn(clip[0], clip[3]), yn = __fdiv_rn(clip[1], clip[3]);
+            x2[c] = __fmul_rn(m, xn); y2[c] = __fmul_rn(m, yn);
+            zc[c] = pc[c][2];
+            // per-face corner attributes: [vertex attrs | ones | view depth]
+            float* fa = P.face_attr + ((size_t)g * 3 + c) * D;
+            const float* va = P.vert_attr + (size_t)(de[I_ATTR_BASE] + vid) * A;
+            for (int d = 0; d < A; d++) fa[d] = va[d];
+            int d = A;
+            if (P.attr_flags & 1) fa[d++] = 1.0f;
+            if (P.attr_flags & 2) fa[d++] = -pc[c][2];
+        }
+        const float e1x = __fsub_rn(pc[1][0], pc[0][0]), e1y = __fsub_rn(pc[1][1], pc[0][1]), e1z = __fsub_rn(pc[1][2], pc[0][2]);
+        const float e2x = __fsub_rn(pc[2][0], pc[0][0]), e2y = __fsub_rn(pc[2][1], pc[0][1]), e2z = __fsub_rn(pc[2][2], pc[0][2]);
+        const float nx = __fmaf_rn(e1y, e2z, -__fmul_rn(e1z, e2y));
+        const float ny = __fmaf_rn(e1z, e2x, -__fmul_rn(e1x, e2z));
+        nz = __fmaf_rn(e1x, e2y, -__fmul_rn(e1y, e2x));
+        if (P.face_normal) {
+            const float len = sqrtf(nx * nx + ny * ny + nz * nz) + 1e-15f;   // utils/utils.py:27-33
+            P.face_normal[(size_t)g * 3 + 0] = nx / len;
+            P.face_normal[(size_t)g * 3 + 1] = ny / len;
+            P.face_normal[(size_t)g * 3 + 2] = nz / len;
+        }
+    }
+    store_face(P, g, b, x2[0], y2[0], x2[1], y2[1], x2[2], y2[2], zc[0], zc[1], zc[2], nz, active);
+}
+
+static inline int setup_grid(const SetupParams& P) {
+    const int n = max(P.total_faces, P.width + P.height);
+    return (n + 255) / 256;
+}
+
+int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(P.ws.imgbox, 0, sizeof(uint4) * (size_t)P.batch, stream);
+    if (e != cudaSuccess) return (int)e;
+    setup_faces_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(P.ws.imgbox, 0, sizeof(uint4) * (size_t)P.batch, stream);
+    if (e != cudaSuccess) return (int)e;
+    setup_meshes_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dibr
