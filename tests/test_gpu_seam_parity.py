@@ -11,7 +11,7 @@ from tests import helpers as Hh
 pytestmark = pytest.mark.gpu
 
 
-def run_case(p3, p2, nz, at, H, W, knum=30, expand=0.02, seed=0, check_grad=True):
+def run_case(p3, p2, nz, at, H, W, knum=30, expand=0.02, seed=0, check_grad=True, min_same=0.999):
     from self6dpp_b200 import rasterizer as Rz
     dev = torch.device("cuda:0")
     fw32 = O.rasterize(W, H, p3, p2, nz, at, expand=expand, knum=knum)
@@ -21,7 +21,7 @@ def run_case(p3, p2, nz, at, H, W, knum=30, expand=0.02, seed=0, check_grad=True
     assert torch.equal(dbg["imidx"].cpu(), fw32["imidx"]), \
         f"imidx mismatch at {int((dbg['imidx'].cpu() != fw32['imidx']).sum())} pixels"
     same = (fw32["imidx"].double() == fw64["imidx"])                  # pixels where fp32 and fp64 agree on the face
-    assert same.float().mean() > 0.999
+    assert same.float().mean() > min_same
     # 2. attributes and soft mask vs float64
     e_im = Hh.assert_close("im", dbg["im"], fw64["im"], mask=same.expand_as(fw64["im"]))
     e_pr = Hh.assert_close("improb", dbg["improb"], fw64["improb"], mask=same)
@@ -80,7 +80,8 @@ def test_big_triangles_and_ties():
     nz = torch.tensor([[[1.0], [1.0], [1.0], [-1.0]]])
     g = torch.Generator().manual_seed(0)
     at = torch.rand(1, 4, 12, generator=g)
-    print(run_case(p3, p2, nz, at, H, W, seed=7))
+    # pixel centres lie exactly on the shared hypotenuse, where fp32 and fp64 may disagree on w0 >= 0
+    print(run_case(p3, p2, nz, at, H, W, seed=7, min_same=0.99))
 
 
 def test_empty_and_offscreen():
