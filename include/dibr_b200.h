@@ -47,6 +47,7 @@ extern "C" {
 
 #define DIBR_ABI_VERSION 1
 #define DIBR_MAX_ATTR 12 /* interpolated channels per pixel (the reference uses 4: rgb/xyz/normal + ones) */
+#define DIBR_MAX_OUTPUTS 6
 
 typedef struct DibrPass {
     /* ---- problem size ------------------------------------------------------------------ */
@@ -71,7 +72,7 @@ typedef struct DibrPass {
     const int32_t *inst_desc;       /* [num_instances, 12]: vert_base, num_verts, mesh_face_base, num_faces,
                                        out_face_base (ascending), cam_index, proj_index, attr_base,
                                        gvert_base (row of this instance in grad_verts / grad_vert_attr),
-                                       image index, 2 reserved */
+                                       image index, adj_base (row of the mesh's vertex 0 in vert_face_ptr), 1 reserved */
     const float *verts;             /* [sum verts, 3] object-space vertices (packed meshes) */
     const int32_t *mesh_faces;      /* [sum mesh faces, 3] vertex ids local to the mesh */
     const float *vert_attr;         /* [sum verts(attr space), vert_attr_dim] per-vertex attributes */
@@ -110,6 +111,14 @@ typedef struct DibrPass {
     float *grad_vert_attr;    /* optional [sum over instances of num_verts, vert_attr_dim] (fused) */
     float *grad_cam_rot;      /* [num_instances, 9] (fused): dL/d cam_view_R of the instance's camera */
     float *grad_cam_pos;      /* [num_instances, 3] (fused) */
+    /* ---- optional split of the D channels over several output tensors --------------------- */
+    int32_t num_outputs;                       /* 0: one tensor `im` / `grad_im` with D channels (operator seam).
+                                                  n>0: channel groups out_channels[0..n) (sum = D) go to separate
+                                                  tensors out[g] of shape [batch,H,W,out_channels[g]]; grad_out[g]
+                                                  may be NULL (= no gradient for that group). */
+    int32_t out_channels[DIBR_MAX_OUTPUTS];
+    float *out[DIBR_MAX_OUTPUTS];
+    const float *grad_out[DIBR_MAX_OUTPUTS];
     const int32_t *vert_face_ptr;  /* CSR vertex -> incident (face,corner) list, per packed mesh vertex: [sum verts + 1] */
     const int32_t *vert_face_idx;  /* [3 * sum mesh faces] entries face*3+corner, ascending */
     int32_t num_cams;

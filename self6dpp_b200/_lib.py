@@ -34,6 +34,8 @@ class DibrPass(ctypes.Structure):
         ("grad_im", _c_f32p), ("grad_improb", _c_f32p), ("grad_points2d", _c_f32p),
         ("grad_face_attr", _c_f32p), ("grad_verts", _c_f32p), ("grad_vert_attr", _c_f32p),
         ("grad_cam_rot", _c_f32p), ("grad_cam_pos", _c_f32p),
+        ("num_outputs", ctypes.c_int32), ("out_channels", ctypes.c_int32 * 6),
+        ("out", ctypes.c_void_p * 6), ("grad_out", ctypes.c_void_p * 6),
         ("vert_face_ptr", _c_i32p), ("vert_face_idx", _c_i32p),
         ("num_cams", ctypes.c_int32), ("reserved0", ctypes.c_int32),
     ]

@@ -62,6 +62,17 @@ int check_common(const DibrPass* p, bool need_ws) {
     return 0;
 }
 
+int check_outputs(const DibrPass* p) {
+    if (p->num_outputs < 0 || p->num_outputs > DIBR_MAX_OUTPUTS) return fail("num_outputs=%d outside [0,%d]", p->num_outputs, DIBR_MAX_OUTPUTS);
+    if (p->num_outputs == 0) return p->im ? 0 : fail("forward: im is null");
+    int d = 0;
+    for (int g = 0; g < p->num_outputs; g++) {
+        if (p->out_channels[g] <= 0 || !p->out[g]) return fail("forward: output group %d is empty or null", g);
+        d += p->out_channels[g];
+    }
+    return d == p->num_attr ? 0 : fail("out_channels sum %d != num_attr %d", d, p->num_attr);
+}
+
 dibr::SetupParams setup_params(const DibrPass* p) {
     dibr::SetupParams s;
     memset(&s, 0, sizeof(s));
@@ -128,7 +139,8 @@ int dibr_setup_meshes(const DibrPass* p, void* stream) {
 
 int dibr_forward(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
-    if (!p->face_attr || !p->im || !p->improb || !p->imidx || !p->imcomp) return fail("forward: face_attr/im/improb/imidx/imcomp required");
+    if (!p->face_attr || !p->improb || !p->imidx || !p->imcomp) return fail("forward: face_attr/improb/imidx/imcomp required");
+    if (int e = check_outputs(p)) return e;
     const dibr::Workspace w = carve(p, p->workspace);
     dibr::FwdParams f;
     memset(&f, 0, sizeof(f));
@@ -137,7 +149,9 @@ int dibr_forward(const DibrPass* p, void* stream) {
     f.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     f.faces_per_image = p->faces_per_image; f.face_offsets = p->face_offsets;
     f.recs = w.recs; f.bbox = w.bbox; f.imgbox = w.imgbox; f.face_attr = p->face_attr;
-    f.im = p->im; f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
+    if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
+    else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }
+    f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
     g_launches += 1;
     return cuda_fail("dibr_forward", dibr::launch_forward(f, (cudaStream_t)stream));
 }
@@ -155,7 +169,24 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     b.total_faces = p->total_faces; b.faces_per_image = p->faces_per_image; b.face_offsets = p->face_offsets;
     b.recs = w.recs; b.xs = w.xs; b.ys = w.ys; b.face_attr = p->face_attr;
     b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx;
-    b.grad_im = p->grad_im; b.grad_improb = p->grad_improb;
+    if (p->num_outputs < 0 || p->num_outputs > DIBR_MAX_OUTPUTS) return fail("num_outputs=%d outside [0,%d]", p->num_outputs, DIBR_MAX_OUTPUTS);
+    b.any_grad_im = 0;
+    if (p->num_outputs == 0) {
+        for (int d = 0; d < p->num_attr; d++) { b.chan_grad[d] = p->grad_im ? p->grad_im + d : nullptr; b.chan_stride[d] = p->num_attr; }
+        b.any_grad_im = p->grad_im != nullptr;
+    } else {
+        int d = 0;
+        for (int g = 0; g < p->num_outputs; g++) {
+            for (int c = 0; c < p->out_channels[g]; c++, d++) {
+                if (d >= p->num_attr) return fail("out_channels sum exceeds num_attr");
+                b.chan_grad[d] = p->grad_out[g] ? p->grad_out[g] + c : nullptr;
+                b.chan_stride[d] = p->out_channels[g];
+            }
+            if (p->grad_out[g]) b.any_grad_im = 1;
+        }
+        if (d != p->num_attr) return fail("out_channels sum %d != num_attr %d", d, p->num_attr);
+    }
+    b.grad_improb = p->grad_improb;
     b.grad_points2d = p->grad_points2d; b.grad_face_attr = p->grad_face_attr;
     g_launches += 1;
     return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream));

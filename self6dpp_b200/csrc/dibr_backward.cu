@@ -70,13 +70,13 @@ __global__ void __launch_bounds__(256) backward_faces_kernel(BwdParams P)
         const float sx = (float)W / (float)P.multiplier, sy = (float)H / (float)P.multiplier;
 
         // ---- colour part: pixels this face won -------------------------------------------------
-        if (P.grad_im && rec.nz >= 0.0f) {
+        if (P.any_grad_im && rec.nz >= 0.0f) {
             const int c0 = col_lower(P.xs, W, rec.xmin, sx), c1 = col_lower(P.xs, W, rec.xmax, sx);
             const int r0 = row_lower(P.ys, H, rec.ymax, sy), r1 = row_lower(P.ys, H, rec.ymin, sy);
             const int nc = c1 - c0, npx = nc * (r1 - r0);
             if (nc > 0 && npx > 0) {
                 const FaceK fk = make_facek(rec);
-                const float* __restrict__ gim = P.grad_im + img * D;
+                const size_t img_px = img;
                 for (int i = gl; i < npx; i += GRP) {
                     const int r = r0 + i / nc, c = c0 + i % nc;
                     const size_t pix = (size_t)r * W + c;
@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(256) backward_faces_kernel(BwdParams P)
                     any_c = true;
 #pragma unroll
                     for (int d = 0; d < DMAX; d++) {
-                        if (d < D) {
-                            const float gv = __ldg(gim + pix * D + d);
+                        if (d < D && P.chan_grad[d]) {
+                            const float gv = __ldg(P.chan_grad[d] + (img_px + pix) * (size_t)P.chan_stride[d]);
                             acc[0 * DMAX + d] = fmaf(gv, w0, acc[0 * DMAX + d]);
                             acc[1 * DMAX + d] = fmaf(gv, w1, acc[1 * DMAX + d]);
                             acc[2 * DMAX + d] = fmaf(gv, w2, acc[2 * DMAX + d]);
@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(256) mesh_vertex_grad_kernel(MeshBwdParams P)
     const int inst = blockIdx.y;
     const int32_t* de = P.inst_desc + inst * INST_STRIDE;
     const int nv = de[I_NUM_VERTS], vbase = de[I_VERT_BASE], fbase = de[I_OUT_FACE_BASE], gvbase = de[I_GVERT_BASE];
+    const int abase = de[I_ADJ_BASE];      // row of this mesh's vertex 0 in the CSR pointer array
     const float* R = P.cam_rot + (size_t)de[I_CAM] * 9;
     const float* T = P.cam_pos + (size_t)de[I_CAM] * 3;
     const float* Pm = P.cam_proj + (size_t)de[I_PROJ] * 16;
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(256) mesh_vertex_grad_kernel(MeshBwdParams P)
     for (int i = 0; i < 12; i++) s[i] = 0.f;
 
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
-        const int e0 = P.vert_face_ptr[vbase + v], e1 = P.vert_face_ptr[vbase + v + 1];
+        const int e0 = P.vert_face_ptr[abase + v], e1 = P.vert_face_ptr[abase + v + 1];
         float g2x = 0.f, g2y = 0.f, gdep = 0.f;
         float ga[DIBR_MAX_ATTR_INTERNAL];
 #pragma unroll

@@ -287,7 +287,6 @@ dibr_forward_kernel(FwdParams P)
     const float4* __restrict__ bbox = P.bbox + f_lo;
     const int D = P.num_attr;
     const size_t img_pix = (size_t)b * P.height * P.width;
-    float* __restrict__ im = P.im + img_pix * D;
     float* __restrict__ improb = P.improb + img_pix;
     float* __restrict__ imcomp = P.imcomp + img_pix;
     int* __restrict__ imidx = P.imidx + img_pix;
@@ -343,7 +342,7 @@ dibr_forward_kernel(FwdParams P)
         if (valid) {
             const size_t gp = (size_t)(ty0 + ly) * P.width + (tx0 + lx);
             const unsigned long long key = s.zkey[ly * TILE + lx];
-            float* o = im + gp * D;
+            const size_t px = img_pix + gp;
             if (key != 0ull) {
                 const int f = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
                 const FaceRec r = recs[f];
@@ -351,30 +350,36 @@ dibr_forward_kernel(FwdParams P)
                 float w0, w1, w2;
                 bary(fk, s.xs[lx], s.ys[ly], w0, w1, w2);
                 const float* a = fattr + (size_t)f * 3 * D;
-                if ((D & 3) == 0) {
-                    for (int d = 0; d < D; d += 4) {
-                        const float4 r0 = __ldg(reinterpret_cast<const float4*>(a + d));
-                        const float4 r1 = __ldg(reinterpret_cast<const float4*>(a + D + d));
-                        const float4 r2 = __ldg(reinterpret_cast<const float4*>(a + 2 * D + d));
+                int base = 0;
+                for (int g = 0; g < P.n_out; g++) {
+                    const int ch = P.out_ch[g];
+                    float* o = P.out[g] + px * ch;
+                    if (ch == 4 && ((D | base) & 3) == 0) {
+                        const float4 r0 = __ldg(reinterpret_cast<const float4*>(a + base));
+                        const float4 r1 = __ldg(reinterpret_cast<const float4*>(a + D + base));
+                        const float4 r2 = __ldg(reinterpret_cast<const float4*>(a + 2 * D + base));
                         float4 v;
                         v.x = blend(w0, w1, w2, r0.x, r1.x, r2.x);
                         v.y = blend(w0, w1, w2, r0.y, r1.y, r2.y);
                         v.z = blend(w0, w1, w2, r0.z, r1.z, r2.z);
                         v.w = blend(w0, w1, w2, r0.w, r1.w, r2.w);
-                        *reinterpret_cast<float4*>(o + d) = v;
+                        *reinterpret_cast<float4*>(o) = v;
+                    } else {
+                        for (int c = 0; c < ch; c++)
+                            o[c] = blend(w0, w1, w2, __ldg(a + base + c), __ldg(a + D + base + c), __ldg(a + 2 * D + base + c));
                     }
-                } else {
-                    for (int d = 0; d < D; d++) o[d] = blend(w0, w1, w2, __ldg(a + d), __ldg(a + D + d), __ldg(a + 2 * D + d));
+                    base += ch;
                 }
                 improb[gp] = 1.0f;
                 imcomp[gp] = 0.0f;
                 imidx[gp] = f + 1;
                 s.cnt[ly * TILE + lx] = 255;
             } else {
-                if ((D & 3) == 0) {
-                    for (int d = 0; d < D; d += 4) *reinterpret_cast<float4*>(o + d) = make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-                    for (int d = 0; d < D; d++) o[d] = 0.f;
+                for (int g = 0; g < P.n_out; g++) {
+                    const int ch = P.out_ch[g];
+                    float* o = P.out[g] + px * ch;
+                    if (ch == 4) *reinterpret_cast<float4*>(o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    else for (int c = 0; c < ch; c++) o[c] = 0.f;
                 }
                 imidx[gp] = 0;                   // may be overwritten with the K-th face in phase D
                 unc = true;

@@ -5,6 +5,8 @@
 
 #include "dibr_common.cuh"
 
+#define DIBR_MAX_ATTR_INTERNAL 12
+
 namespace dibr {
 
 // workspace carved out of DibrPass::workspace by dibr_abi.cu
@@ -18,7 +20,6 @@ struct Workspace {
     size_t bytes;
 };
 
-#define DIBR_MAX_ATTR_INTERNAL 12
 constexpr int POSE_BLOCKS = 16;   // vertex blocks per instance in the pose-gradient reduction
 
 struct SetupParams {
@@ -54,7 +55,9 @@ struct FwdParams {
     const float4* bbox;
     const uint4* imgbox;
     const float* face_attr;
-    float* im;
+    int n_out;                 // channel groups (>= 1)
+    int out_ch[6];
+    float* out[6];             // [batch,H,W,out_ch[g]]
     float* improb;
     float* imcomp;
     int32_t* imidx;
@@ -72,7 +75,9 @@ struct BwdParams {
     const float* improb;
     const float* imcomp;
     const int32_t* imidx;
-    const float* grad_im;
+    const float* chan_grad[DIBR_MAX_ATTR_INTERNAL];   // per channel d: upstream gradient base (pre-offset) or null
+    int chan_stride[DIBR_MAX_ATTR_INTERNAL];          // floats per pixel of the tensor that holds channel d
+    int any_grad_im;
     const float* grad_improb;
     float* grad_points2d;
     float* grad_face_attr;

@@ -1,0 +1,258 @@
+"""Fused vertex-shader + rasterizer op: object-space meshes + per-instance cameras in, images out.
+
+One autograd ``Function`` replaces, for a whole ragged batch, what the reference does per sample in
+Python: ``perspective_projection`` (renderer/vertex_shaders/perpsective.py:29-111), the per-face
+attribute gather with the ones channel (renderer/vcrender_batch.py:84-88), ``prepare_tfpoints`` and
+``LinearRasterizer`` (rasterizer/rasterizer.py:36-294) -- and, in backward, the torch autograd tail
+down to ``cam_view_R`` / ``cam_view_pos`` (renderer/base.py:169-170).
+
+Terminology: an *instance* is one mesh under one camera; an *image* is rendered from one or more
+instances (VertexColorBatch: one instance per image; VertexColorMulti: all instances in one image,
+vcrender_multi.py:92-96).
+"""
+import ctypes
+
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .rasterizer import (DEFAULT_DELTA, DEFAULT_EXPAND, DEFAULT_KNUM, DEFAULT_MULTIPLIER, _alloc_workspace,
+                         _base_pass, _require_cuda_f32, _stream)
+
+INST_STRIDE = 12
+FLAG_ONES = 1
+FLAG_DEPTH = 2
+
+
+class MeshPack(object):
+    """Distinct meshes packed into flat device arrays + the vertex -> (face, corner) CSR adjacency
+    the deterministic vertex gather in ``dibr_backward_meshes`` walks.  Built with device-side torch
+    ops only (no host sync) and cached per set of face tensors (the reference keeps its models
+    resident on the GPU too, self_engine_utils.py:1361-1373)."""
+
+    def __init__(self, verts_list, faces_list, device):
+        self.device = device
+        self.n_meshes = len(verts_list)
+        nv = [int(v.shape[-2]) for v in verts_list]
+        nf = [int(f.shape[0]) for f in faces_list]
+        self.num_verts = nv
+        self.num_faces = nf
+        self.vert_base = np.concatenate([[0], np.cumsum(nv)]).astype(np.int64)
+        self.face_base = np.concatenate([[0], np.cumsum(nf)]).astype(np.int64)
+        total_v, total_f = int(self.vert_base[-1]), int(self.face_base[-1])
+        faces = [f.detach().to(device=device, dtype=torch.int32).reshape(-1, 3) for f in faces_list]
+        self.faces = (faces[0] if len(faces) == 1 else torch.cat(faces, dim=0)).contiguous()
+        # CSR over packed vertices: ascending list of LOCAL entries (face*3 + corner) per vertex
+        if total_f == 0:
+            self.vert_face_ptr = torch.zeros(total_v + 1, dtype=torch.int32, device=device)
+            self.vert_face_idx = torch.zeros(0, dtype=torch.int32, device=device)
+            return
+        vbase_per_face = torch.from_numpy(np.repeat(self.vert_base[:-1], nf).astype(np.int64)).to(device, non_blocking=True)
+        ebase_per_face = torch.from_numpy(np.repeat(3 * self.face_base[:-1], nf).astype(np.int64)).to(device, non_blocking=True)
+        glob_vert = (self.faces.to(torch.int64) + vbase_per_face[:, None]).reshape(-1)       # entry -> packed vertex
+        entry = torch.arange(3 * total_f, device=device, dtype=torch.int64)
+        local_entry = entry - ebase_per_face.repeat_interleave(3)
+        sorted_vert, order = torch.sort(glob_vert, stable=True)
+        self.vert_face_idx = local_entry[order].to(torch.int32).contiguous()
+        self.vert_face_ptr = torch.searchsorted(
+            sorted_vert, torch.arange(total_v + 1, device=device, dtype=torch.int64)).to(torch.int32).contiguous()
+
+
+_PACK_CACHE = {}
+
+
+def get_mesh_pack(verts_list, faces_list):
+    """verts_list[i]: [..., p, 3] tensor, faces_list[i]: [f, 3] integer tensor (distinct meshes only)."""
+    key = tuple((f.data_ptr(), tuple(f.shape), f._version, int(v.shape[-2])) for v, f in zip(verts_list, faces_list))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    pack = MeshPack(verts_list, faces_list, verts_list[0].device)
+    if len(_PACK_CACHE) > 64:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (pack, list(faces_list))      # keep the face tensors alive so data_ptr stays unique
+    return pack
+
+
+def dedup(tensors):
+    """-> (distinct tensors in first-seen order, index of each input in that list); identity by storage."""
+    seen, distinct, ids = {}, [], []
+    for t in tensors:
+        k = (t.data_ptr(), tuple(t.shape), t.dtype)
+        if k not in seen:
+            seen[k] = len(distinct)
+            distinct.append(t)
+        ids.append(seen[k])
+    return distinct, ids
+
+
+class RenderMeshes(Function):
+    """forward(verts_packed [SV,3], vattr_packed [SA,A], cam_rot [I,3,3], cam_pos [I,3], cam_proj [P,4,4], meta)
+    -> (out_0 [B,H,W,c0], ..., out_n [B,H,W,cn], improb [B,H,W,1], face_normal [TF,3] or empty).
+    The D = A (+ones)(+depth) interpolated channels are split over separately allocated tensors as
+    meta['out_split'] says (sum = D), written directly by the kernel: no views to slice, and in backward an
+    output nobody differentiated costs nothing (its grad pointer is NULL)."""
+
+    @staticmethod
+    def forward(ctx, verts, vattr, cam_rot, cam_pos, cam_proj, meta):
+        for n, t in (("vertices", verts), ("camera rotation", cam_rot), ("camera position", cam_pos),
+                     ("camera projection", cam_proj)):
+            _require_cuda_f32(n, t)
+        device = verts.device
+        B, H, W = meta["batch"], meta["height"], meta["width"]
+        A, flags = meta["attr_dim"], meta["attr_flags"]
+        D = A + (1 if flags & FLAG_ONES else 0) + (1 if flags & FLAG_DEPTH else 0)
+        TF = meta["total_faces"]
+        verts_c = verts.detach().contiguous()
+        vattr_c = vattr.detach().contiguous() if A > 0 else None
+        if A > 0:
+            _require_cuda_f32("vertex attributes", vattr)
+        rot_c = cam_rot.detach().contiguous()
+        pos_c = cam_pos.detach().contiguous()
+        proj_c = cam_proj.detach().contiguous()
+        with torch.cuda.device(device):
+            p = _base_pass(B, H, W, D, meta["knum"], meta["multiplier"], meta["delta"], meta["expand"], TF, 0)
+            p.face_offsets = _lib.ptr(meta["face_offsets"])
+            p.num_instances = meta["num_instances"]
+            ws = _alloc_workspace(p, device)
+            face_attr = torch.empty(max(TF, 1), 3, D, dtype=torch.float32, device=device)
+            face_normal = torch.empty(TF, 3, dtype=torch.float32, device=device) if meta["want_normals"] else None
+            split = meta.get("out_split") or [D]
+            assert sum(split) == D and len(split) <= 6, (split, D)
+            outs = [torch.empty(B, H, W, c, dtype=torch.float32, device=device) for c in split]
+            improb = torch.empty(B, H, W, 1, dtype=torch.float32, device=device)
+            imcomp = torch.empty(B, H, W, dtype=torch.float32, device=device)
+            imidx = torch.empty(B, H, W, dtype=torch.int32, device=device)
+            pack = meta["pack"]
+            p.inst_desc = _lib.ptr(meta["inst_desc"])
+            p.verts, p.mesh_faces = _lib.ptr(verts_c), _lib.ptr(pack.faces)
+            p.vert_attr, p.vert_attr_dim, p.attr_flags = _lib.ptr(vattr_c), A, flags
+            p.cam_rot, p.cam_pos, p.cam_proj = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
+            p.face_attr, p.face_normal = _lib.ptr(face_attr), _lib.ptr(face_normal)
+            p.improb, p.imidx, p.imcomp = _lib.ptr(improb), _lib.ptr(imidx), _lib.ptr(imcomp)
+            p.num_outputs = len(split)
+            for g, (c, o) in enumerate(zip(split, outs)):
+                p.out_channels[g] = c
+                p.out[g] = o.data_ptr()
+            lib = _lib.load()
+            st = _stream(device)
+            _lib.check(lib.dibr_setup_meshes(ctypes.byref(p), st), "dibr_setup_meshes")
+            _lib.check(lib.dibr_forward(ctypes.byref(p), st), "dibr_forward")
+        if meta.get("keep_pass"):      # bench_util.time_forward_kernel re-launches dibr_forward on these buffers
+            meta["_last_pass"] = (p, [verts_c, vattr_c, rot_c, pos_c, proj_c, face_attr, face_normal, outs, improb, imcomp, imidx, ws])
+        ctx.save_for_backward(verts_c, rot_c, pos_c, proj_c, face_attr, improb, imcomp, imidx, ws)
+        ctx.meta = meta
+        ctx.dims = (D, A, flags)
+        ctx.split = list(split)
+        ctx.needs = (verts.requires_grad, vattr.requires_grad if A > 0 else False)
+        meta["last_imidx"] = imidx
+        if face_normal is None:
+            face_normal = torch.empty(0, 3, dtype=torch.float32, device=device)
+        ctx.mark_non_differentiable(face_normal)
+        ctx.set_materialize_grads(False)
+        return (*outs, improb, face_normal)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        g_outs, g_prob = grads[:-2], grads[-2]
+        verts_c, rot_c, pos_c, proj_c, face_attr, improb, imcomp, imidx, ws = ctx.saved_tensors
+        meta = ctx.meta
+        D, A, flags = ctx.dims
+        need_verts, need_vattr = ctx.needs
+        device = verts_c.device
+        B, H, W, TF, I = meta["batch"], meta["height"], meta["width"], meta["total_faces"], meta["num_instances"]
+        g_outs = [g.contiguous() if g is not None else None for g in g_outs]
+        gP = g_prob.contiguous() if g_prob is not None else None
+        pack = meta["pack"]
+        with torch.cuda.device(device):
+            p = _base_pass(B, H, W, D, meta["knum"], meta["multiplier"], meta["delta"], meta["expand"], TF, 0)
+            p.face_offsets = _lib.ptr(meta["face_offsets"])
+            p.num_instances = I
+            p.workspace = ctypes.c_void_p(ws.data_ptr())
+            p.workspace_bytes = ws.numel()
+            p.inst_desc = _lib.ptr(meta["inst_desc"])
+            p.verts = _lib.ptr(verts_c)
+            p.vert_attr_dim, p.attr_flags = A, flags
+            p.cam_rot, p.cam_pos, p.cam_proj = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
+            p.face_attr = _lib.ptr(face_attr)
+            p.improb, p.imidx, p.imcomp = _lib.ptr(improb), _lib.ptr(imidx), _lib.ptr(imcomp)
+            p.grad_improb = _lib.ptr(gP)
+            p.num_outputs = len(ctx.split)
+            for g, (c, go) in enumerate(zip(ctx.split, g_outs)):
+                p.out_channels[g] = c
+                p.grad_out[g] = go.data_ptr() if go is not None else None
+            g_p2d = torch.empty(max(TF, 1), 6, dtype=torch.float32, device=device)
+            g_fattr = torch.empty(max(TF, 1), 3, D, dtype=torch.float32, device=device)
+            g_rot = torch.empty(I, 3, 3, dtype=torch.float32, device=device)
+            g_pos = torch.empty(I, 3, dtype=torch.float32, device=device)
+            n_rows = meta["num_inst_verts"]
+            g_verts = torch.empty(n_rows, 3, dtype=torch.float32, device=device) if need_verts else None
+            g_vattr = torch.empty(n_rows, max(A, 1), dtype=torch.float32, device=device) if need_vattr else None
+            p.grad_points2d, p.grad_face_attr = _lib.ptr(g_p2d), _lib.ptr(g_fattr)
+            p.grad_cam_rot, p.grad_cam_pos = _lib.ptr(g_rot), _lib.ptr(g_pos)
+            p.grad_verts, p.grad_vert_attr = _lib.ptr(g_verts), _lib.ptr(g_vattr)
+            p.vert_face_ptr, p.vert_face_idx = _lib.ptr(pack.vert_face_ptr), _lib.ptr(pack.vert_face_idx)
+            lib = _lib.load()
+            st = _stream(device)
+            _lib.check(lib.dibr_backward_faces(ctypes.byref(p), st), "dibr_backward_faces")
+            _lib.check(lib.dibr_backward_meshes(ctypes.byref(p), st), "dibr_backward_meshes")
+        gv = ga = None
+        if need_verts:      # instances that share a mesh sum into the same packed rows
+            gv = torch.zeros_like(verts_c).index_add_(0, meta["inst_vert_rows"], g_verts)
+        if need_vattr:
+            ga = torch.zeros(meta["num_attr_rows"], A, dtype=torch.float32, device=device)
+            ga.index_add_(0, meta["inst_attr_rows"], g_vattr)
+        # proj gradients (dL/dK) are not produced: intrinsics are data in Self6D++
+        return gv, ga, g_rot, g_pos, None, None
+
+
+def build_meta(pack, mesh_ids, attr_ids, attr_rows_base, image_ids, height, width, attr_dim, attr_flags,
+               proj_ids=None, vert_rows_base=None, out_split=None, knum=DEFAULT_KNUM, multiplier=DEFAULT_MULTIPLIER, delta=DEFAULT_DELTA,
+               expand=DEFAULT_EXPAND, want_normals=False, need_rows=False, num_attr_rows=0):
+    """Instance table for one render call.
+
+    mesh_ids[i]   : which packed mesh (topology) instance i renders
+    vert_rows_base[i]: first row of instance i's vertices in verts_packed (default: the pack's own base)
+    attr_ids/attr_rows_base: attribute tensor of instance i starts at row attr_rows_base[attr_ids[i]]
+    image_ids[i]  : image the instance lands in (non-decreasing)
+    proj_ids[i]   : row of cam_proj (default: 0 for all)
+    """
+    I = len(mesh_ids)
+    device = pack.device
+    desc = np.zeros((I, INST_STRIDE), dtype=np.int32)
+    out_base = 0
+    gv_base = 0
+    nimg = int(image_ids[-1]) + 1 if I else 0
+    face_off = np.zeros(nimg + 1, dtype=np.int32)
+    vert_rows, attr_rows = [], []
+    for i in range(I):
+        m = mesh_ids[i]
+        nv, nf = pack.num_verts[m], pack.num_faces[m]
+        vb = pack.vert_base[m] if vert_rows_base is None else vert_rows_base[i]
+        desc[i] = [vb, nv, pack.face_base[m], nf, out_base, i,
+                   0 if proj_ids is None else proj_ids[i], attr_rows_base[attr_ids[i]], gv_base, image_ids[i],
+                   pack.vert_base[m], 0]
+        face_off[image_ids[i] + 1] += nf
+        if need_rows:
+            vert_rows.append(np.arange(vb, vb + nv))
+            attr_rows.append(np.arange(attr_rows_base[attr_ids[i]], attr_rows_base[attr_ids[i]] + nv))
+        out_base += nf
+        gv_base += nv
+    face_off = np.cumsum(face_off).astype(np.int32)
+    # image-local face numbering: out_face_base is global; forward subtracts face_offsets[image]
+    meta = dict(batch=nimg, height=int(height), width=int(width), attr_dim=int(attr_dim), attr_flags=int(attr_flags),
+                total_faces=int(out_base), num_instances=I, num_inst_verts=int(gv_base), pack=pack,
+                knum=int(knum), multiplier=int(multiplier), delta=int(delta), expand=float(expand),
+                want_normals=bool(want_normals), num_attr_rows=int(num_attr_rows), out_split=out_split,
+                inst_desc=torch.from_numpy(desc).to(device, non_blocking=True),
+                face_offsets=torch.from_numpy(face_off).to(device, non_blocking=True),
+                face_offsets_host=face_off)
+    if need_rows:
+        meta["inst_vert_rows"] = torch.from_numpy(np.concatenate(vert_rows)).to(device)
+        meta["inst_attr_rows"] = torch.from_numpy(np.concatenate(attr_rows)).to(device)
+    return meta
+
+
+def render_meshes(verts_packed, vattr_packed, cam_rot, cam_pos, cam_proj, meta):
+    return RenderMeshes.apply(verts_packed, vattr_packed, cam_rot, cam_pos, cam_proj, meta)

@@ -1,0 +1,230 @@
+"""-m gpu: the fused path (DIBRenderer / Renderer_dibr API -> dibr_setup_meshes + dibr_forward +
+dibr_backward_faces + dibr_backward_meshes) against (1) the oracle on identical inputs and (2) golden
+vectors produced by the reference's own Python layers."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dibr_oracle as O
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def to_dev_models(meshes):
+    return [{"vertices": torch.tensor(m["vertices"], device=DEV), "colors": torch.tensor(m["colors"], device=DEV),
+             "normals": torch.tensor(m["normals"], device=DEV),
+             "faces": torch.tensor(m["faces"], device=DEV, dtype=torch.float32)}     # fp32 faces like the reference's cache
+            for m in meshes]
+
+
+def frac_bad(a, b, tol):
+    a = a.detach().float().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    return float((np.abs(a - b) > tol).mean())
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_fused_idx_bit_exact_and_values(seed):
+    """DIBRenderer(VertexColorBatch).forward on a ragged batch: face ids bit-exact vs the fp32 oracle with the
+    fixed-order vertex shader; colour / mask / soft mask within 1e-5 of float64."""
+    from self6dpp_b200 import DIBRenderer, synth
+    from tests.golden.make_golden import small_meshes
+    meshes = small_meshes()
+    H, W, B = 64, 80, 5
+    ids = [0, 1, 2, 1, 0]
+    batch = synth.roi_batch([meshes[i] for i in ids], B, res=W, seed=seed, fill=(0.45, 0.7))
+    cams = O.camera_params_from_RT_K(torch.tensor(batch["Rs"]), torch.tensor(batch["ts"]), torch.tensor(batch["Ks"]),
+                                     H, W, near=0.01, far=100.0)
+    ren = DIBRenderer(H, W, "VertexColorBatch")
+    ren.set_camera_parameters([c.to(DEV) for c in cams])
+    models = to_dev_models(meshes)
+    points = [[models[i]["vertices"][None], models[i]["faces"].long()] for i in ids]
+    colors = [models[i]["colors"][None] for i in ids]
+    im, prob, normals, mask = ren.forward(points=points, colors=colors)
+    assert im.shape == (B, H, W, 3) and prob.shape == (B, H, W, 1) and mask.shape == (B, H, W, 1)
+    assert len(normals) == B and normals[0].shape == (1, meshes[0]["faces"].shape[0], 3)
+    from self6dpp_b200.renderer import vc
+    # re-run through the internal entry to read the face-id buffer
+    _, _, _, meta = vc.render_instances(points, colors, ren.camera_params, H, W, multi=False, out_split=[3, 1])
+    imidx = meta["last_imidx"].cpu()
+    for i, mid in enumerate(ids):
+        m = meshes[mid]
+        v, f = torch.tensor(m["vertices"]), torch.tensor(m["faces"])
+        c = torch.tensor(m["colors"])
+        one = torch.ones(f.shape[0], 1)
+        fl = f.long()
+        at = torch.cat([c[fl[:, 0]], one, c[fl[:, 1]], one, c[fl[:, 2]], one], 1)[None]
+        p3, p2, nz, nn = O.project(v, f, cams[0][i], cams[1][i], cams[2][i])
+        fw32 = O.rasterize(W, H, p3, p2, nz, at)
+        assert torch.equal(imidx[i].clamp(min=0).float(), fw32["imidx"][0, ..., 0]), f"sample {i}: face ids differ"
+        # float64 rasterizer on the SAME fp32-projected corners (fp32 quantisation of the projected coordinates,
+        # ~6e-5 multiplier units, is a property of any fp32 vertex shader incl. the reference's and moves the soft
+        # mask by up to ~1e-4; the full float64 pipeline is compared in test_render_batch_pose_gradients_vs_float64)
+        fw64 = O.rasterize(W, H, p3.double(), p2.double(), nz.double(), at.double())
+        same = (fw32["imidx"].double() == fw64["imidx"])
+        assert same.float().mean() > 0.998
+        got = torch.cat([im[i:i + 1], mask[i:i + 1]], -1)
+        # same fp32 inputs, same operation order: the interpolated attributes are bit-identical to the fp32 oracle
+        assert torch.equal(got.cpu(), fw32["im"]), "im differs from the fp32 operation-order oracle"
+        Hh.assert_close("im", got, fw64["im"], mask=same.expand_as(fw64["im"]), outlier_frac=5e-4)
+        Hh.assert_close("prob", prob[i:i + 1], fw64["improb"], mask=same)
+        n_ref = nn / (nn.norm(dim=2, keepdim=True) + 1e-15)
+        Hh.assert_close("normal1", normals[i], n_ref, rtol=1e-4, atol_rel=1e-5)
+
+
+def test_render_batch_pose_gradients_vs_float64():
+    """Renderer_dibr.render_batch(mode=color,depth,prob): outputs and dL/dR, dL/dt vs the float64 pipeline."""
+    from self6dpp_b200 import Renderer_dibr, synth
+    from tests.golden.make_golden import small_meshes
+    meshes = small_meshes()
+    H = W = 64
+    ids = [2, 0, 1, 1]
+    B = len(ids)
+    batch = synth.roi_batch([meshes[i] for i in ids], B, res=W, seed=7, fill=(0.45, 0.7))
+    models = to_dev_models(meshes)
+    Rs = torch.tensor(batch["Rs"], device=DEV, requires_grad=True)
+    ts = torch.tensor(batch["ts"], device=DEV, requires_grad=True)
+    ren = Renderer_dibr(H, W, "VertexColorBatch")
+    ret = ren.render_batch(Rs, ts, [models[i] for i in ids], Ks=torch.tensor(batch["Ks"], device=DEV), width=W, height=H,
+                           mode=["color", "depth", "mask", "prob"])
+    assert ret["color"].shape == (B, H, W, 3) and ret["prob"].shape == (B, H, W) and ret["depth"].shape == (B, H, W)
+    g = torch.Generator().manual_seed(3)
+    g_color = torch.randn(B, H, W, 3, generator=g, dtype=torch.float64)
+    g_prob = torch.randn(B, H, W, 1, generator=g, dtype=torch.float64)
+    g_depth = torch.randn(B, H, W, 1, generator=g, dtype=torch.float64)
+    grads = {"im": torch.cat([g_color, torch.zeros(B, H, W, 1, dtype=torch.float64), g_depth], -1), "prob": g_prob}
+    ref = Hh.oracle_render_batch64(meshes, ids, batch["Rs"], batch["ts"], batch["Ks"], H, W, ["colors"], True, grads)
+    # restrict to pixels where the fp32 face ids equal the float64 ones (both in outputs and in the loss)
+    from self6dpp_b200.renderer import vc  # noqa: F401
+    got_im = torch.cat([ret["color"], ret["mask"].unsqueeze(-1), ret["depth"].unsqueeze(-1)], -1)
+    cov64 = ref["imidx"] > 0
+    cov32 = (ret["mask"].detach().cpu() > 0.5).unsqueeze(-1)
+    same = (cov64 == cov32)
+    assert same.float().mean() > 0.999
+    # full float64 pipeline (float64 vertex shader too): bounded by the fp32 quantisation of projected coordinates
+    Hh.assert_close("im", got_im, ref["im"], mask=same.expand_as(ref["im"]), rtol=1e-4, atol_rel=1e-4)
+    Hh.assert_close("prob", ret["prob"].unsqueeze(-1), ref["prob"], mask=same, rtol=1e-4, atol_rel=1e-4)
+    loss = (ret["color"] * g_color.float().to(DEV)).sum() + (ret["prob"] * g_prob[..., 0].float().to(DEV)).sum() \
+        + (ret["depth"] * g_depth[..., 0].float().to(DEV)).sum()
+    loss.backward()
+    e_R = Hh.assert_close("dL/dR", Rs.grad, ref["grad_Rs"], rtol=2e-4, atol_rel=2e-4)
+    e_t = Hh.assert_close("dL/dt", ts.grad, ref["grad_ts"], rtol=2e-4, atol_rel=2e-4)
+    print({"e_R": e_R, "e_t": e_t})
+    # deterministic
+    Rs2 = torch.tensor(batch["Rs"], device=DEV, requires_grad=True)
+    ts2 = torch.tensor(batch["ts"], device=DEV, requires_grad=True)
+    ret2 = ren.render_batch(Rs2, ts2, [models[i] for i in ids], Ks=torch.tensor(batch["Ks"], device=DEV), width=W,
+                            height=H, mode=["color", "depth", "mask", "prob"])
+    loss2 = (ret2["color"] * g_color.float().to(DEV)).sum() + (ret2["prob"] * g_prob[..., 0].float().to(DEV)).sum() \
+        + (ret2["depth"] * g_depth[..., 0].float().to(DEV)).sum()
+    loss2.backward()
+    assert torch.equal(Rs2.grad, Rs.grad) and torch.equal(ts2.grad, ts.grad)
+
+
+def test_golden_render_batch_from_reference_python():
+    """golden produced by the reference's VCRenderBatch + LinearRasterizer + autograd (CPU, oracle stub)."""
+    from self6dpp_b200 import Renderer_dibr
+    d, meshes = Hh.load_golden("ref_batch64.npz")
+    H, W = int(d["H"]), int(d["W"])
+    ids = [int(i) for i in d["ids"]]
+    models = to_dev_models(meshes)
+    Rs = torch.tensor(d["Rs"], device=DEV, requires_grad=True)
+    ts = torch.tensor(d["ts"], device=DEV, requires_grad=True)
+    ren = Renderer_dibr(H, W, "VertexColorBatch")
+    ret = ren.render_batch(Rs, ts, [models[i] for i in ids], Ks=torch.tensor(d["Ks"], device=DEV), width=W, height=H,
+                           mode=["color", "depth", "mask", "norm", "prob"])
+    assert frac_bad(ret["color"], d["color"], 1e-4) < 2e-3
+    assert frac_bad(ret["prob"], d["prob"][..., 0], 1e-4) < 2e-3
+    assert frac_bad(ret["mask"], d["mask"][..., 0], 1e-4) < 2e-3
+    assert frac_bad(ret["depth"], d["depth"], 1e-4) < 2e-3
+    assert frac_bad(ret["norm"], d["norm"], 1e-3) < 2e-3
+    dev = lambda k: torch.tensor(d[k], device=DEV)
+    loss = (ret["color"] * dev("g_color")).sum() + (ret["prob"] * dev("g_prob")[..., 0]).sum() \
+        + (ret["depth"] * dev("g_depth")).sum() + (ret["norm"] * dev("g_norm")).sum()
+    loss.backward()
+    # the reference's own fp32 chain (cancellation-prone dw terms of K3 + torch fp32 autograd) is itself ~5e-3 away
+    # from float64 on dL/dR for this fixture (tools/diag_fused.py); ours is ~5e-5 (previous test), so the golden
+    # can only be matched to the golden's own accuracy
+    for name, got, ref, tol in (("grad_Rs", Rs.grad, d["grad_Rs"], 2e-2), ("grad_ts", ts.grad, d["grad_ts"], 2e-3)):
+        rel = float(np.abs(got.cpu().numpy() - ref).max() / np.abs(ref).max())
+        print(name, rel)
+        assert rel < tol, (name, rel)
+
+
+def test_golden_render_scene_from_reference_python():
+    from self6dpp_b200 import Renderer_dibr
+    d, meshes = Hh.load_golden("ref_multi64.npz")
+    H, W = int(d["H"]), int(d["W"])
+    models = to_dev_models(meshes)
+    Rs = torch.tensor(d["Rs"], device=DEV, requires_grad=True)
+    ts = torch.tensor(d["ts"], device=DEV, requires_grad=True)
+    ren = Renderer_dibr(H, W, "VertexColorMulti")
+    ret = ren.render_scene(Rs, ts, models, K=torch.tensor(d["K"], device=DEV), width=W, height=H)
+    assert ret["color"].shape == (H, W, 3) and ret["prob"].shape == (H, W) and ret["depth"].shape == (H, W)
+    assert frac_bad(ret["color"], d["color"][0], 1e-4) < 2e-3
+    assert frac_bad(ret["prob"], d["prob"][0, ..., 0], 1e-4) < 2e-3
+    assert frac_bad(ret["mask"], d["mask"][0, ..., 0], 1e-4) < 2e-3
+    loss = (ret["color"] * torch.tensor(d["g_color"][0], device=DEV)).sum() + (ret["prob"] * torch.tensor(d["g_prob"][0, ..., 0], device=DEV)).sum()
+    loss.backward()
+    for name, got, ref, tol in (("grad_Rs", Rs.grad, d["grad_Rs"], 2e-2), ("grad_ts", ts.grad, d["grad_ts"], 2e-3)):
+        rel = float(np.abs(got.cpu().numpy() - ref).max() / np.abs(ref).max())
+        print(name, rel)
+        assert rel < tol, (name, rel)
+
+
+def test_golden_seam_from_reference_python():
+    from self6dpp_b200 import linear_rasterizer
+    d, _ = Hh.load_golden("ref_seam48x64.npz")
+    H, W = int(d["H"]), int(d["W"])
+    dev = lambda k: torch.tensor(d[k], device=DEV)
+    p2 = dev("points2d").requires_grad_(True)
+    at = dev("attr").requires_grad_(True)
+    im, prob = linear_rasterizer(W, H, dev("points3d"), p2, dev("normalz"), at)
+    assert frac_bad(im, d["im"], 2e-5) == 0.0            # same fp32 inputs: no face flips at all
+    assert frac_bad(prob, d["prob"], 2e-5) == 0.0
+    ((im * dev("g_im")).sum() + (prob * dev("g_prob")).sum()).backward()
+    for name, got, ref in (("grad_points2d", p2.grad, d["grad_points2d"]), ("grad_attr", at.grad, d["grad_attr"])):
+        rel = float(np.abs(got.cpu().numpy() - ref).max() / np.abs(ref).max())
+        print(name, rel)
+        assert rel < 1e-4, (name, rel)
+
+
+def test_vertex_and_colour_gradients_vcrender():
+    """DIBRenderer('VertexColor'): gradients reach the vertices and the vertex colours (float64 autograd check)."""
+    from self6dpp_b200 import DIBRenderer, synth
+    mesh = synth.icosphere(2, radius=0.05, noise_sigma=0.004, seed=4)
+    H = W = 64
+    B = 2
+    batch = synth.roi_batch([mesh], B, res=W, seed=11, fill=(0.5, 0.7))
+    cams = O.camera_params_from_RT_K(torch.tensor(batch["Rs"]), torch.tensor(batch["ts"]), torch.tensor(batch["Ks"]),
+                                     H, W, near=0.01, far=100.0)
+    verts = torch.tensor(mesh["vertices"], device=DEV)[None].repeat(B, 1, 1).requires_grad_(True)
+    cols = torch.tensor(mesh["colors"], device=DEV)[None].repeat(B, 1, 1).requires_grad_(True)
+    faces = torch.tensor(mesh["faces"], device=DEV).long()
+    ren = DIBRenderer(H, W, "VertexColor")
+    ren.set_camera_parameters([c.to(DEV) for c in cams])
+    im, prob, normal, mask = ren.forward(points=[verts, faces], colors_bxpx3=cols)
+    g = torch.Generator().manual_seed(5)
+    g_im = torch.randn(B, H, W, 3, generator=g, dtype=torch.float64)
+    g_prob = torch.randn(B, H, W, 1, generator=g, dtype=torch.float64)
+    ((im * g_im.float().to(DEV)).sum() + (prob * g_prob.float().to(DEV)).sum()).backward()
+    # float64 reference by autograd through the torch vertex shader + C oracle rasterizer
+    gv, gc = [], []
+    for i in range(B):
+        v = torch.tensor(mesh["vertices"], dtype=torch.float64, requires_grad=True)
+        c = torch.tensor(mesh["colors"], dtype=torch.float64, requires_grad=True)
+        f = torch.tensor(mesh["faces"])
+        p3, p2, nz, _ = Hh.torch_project(v, f, cams[0][i].double(), cams[1][i].double(), cams[2][i].double())
+        one = torch.ones(v.shape[0], 1, dtype=torch.float64)
+        va = torch.cat([c, one], 1)
+        fl = f.long()
+        at = torch.cat([va[fl[:, 0]], va[fl[:, 1]], va[fl[:, 2]]], 1)
+        fw = O.rasterize(W, H, p3.detach()[None], p2.detach()[None], nz.detach()[None], at.detach()[None])
+        gI = torch.cat([g_im[i:i + 1], torch.zeros(1, H, W, 1, dtype=torch.float64)], -1)
+        dp2, dat = O.rasterize_backward(fw, gI, g_prob[i:i + 1])
+        ((p2 * dp2[0]).sum() + (at * dat[0]).sum()).backward()
+        gv.append(v.grad)
+        gc.append(c.grad)
+    Hh.assert_close("dL/dverts", verts.grad, torch.stack(gv), rtol=1e-4, atol_rel=5e-5)
+    Hh.assert_close("dL/dcolors", cols.grad, torch.stack(gc), rtol=1e-4, atol_rel=2e-5)

@@ -23,7 +23,8 @@ def run_case(p3, p2, nz, at, H, W, knum=30, expand=0.02, seed=0, check_grad=True
     same = (fw32["imidx"].double() == fw64["imidx"])                  # pixels where fp32 and fp64 agree on the face
     assert same.float().mean() > min_same
     # 2. attributes and soft mask vs float64
-    e_im = Hh.assert_close("im", dbg["im"], fw64["im"], mask=same.expand_as(fw64["im"]))
+    assert torch.equal(dbg["im"].cpu(), fw32["im"]), "im differs from the fp32 operation-order oracle"
+    e_im = Hh.assert_close("im", dbg["im"], fw64["im"], mask=same.expand_as(fw64["im"]), outlier_frac=5e-4)
     e_pr = Hh.assert_close("improb", dbg["improb"], fw64["improb"], mask=same)
     out = {"e_im": e_im, "e_pr": e_pr, "covered": int((fw32["imidx"] > 0).sum())}
     if not check_grad:
