@@ -38,6 +38,7 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     w.xs = (float*)take(sizeof(float) * (size_t)p->width);
     w.ys = (float*)take(sizeof(float) * (size_t)p->height);
     w.pose_part = (float*)take(sizeof(float) * 12 * dibr::POSE_BLOCKS * (size_t)(p->num_instances > 0 ? p->num_instances : 0));
+    w.unc_blocks = (unsigned short*)take(sizeof(unsigned short) * (size_t)p->batch * ((p->height + dibr::TILE - 1) / dibr::TILE) * ((p->width + dibr::TILE - 1) / dibr::TILE));
     w.bytes = off;
     return w;
 }
@@ -151,7 +152,7 @@ int dibr_forward(const DibrPass* p, void* stream) {
     f.recs = w.recs; f.bbox = w.bbox; f.imgbox = w.imgbox; f.face_attr = p->face_attr;
     if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
     else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }
-    f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
+    f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx; f.unc_blocks = w.unc_blocks;
     g_launches += 1;
     return cuda_fail("dibr_forward", dibr::launch_forward(f, (cudaStream_t)stream));
 }
@@ -168,7 +169,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     b.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     b.total_faces = p->total_faces; b.faces_per_image = p->faces_per_image; b.face_offsets = p->face_offsets;
     b.recs = w.recs; b.xs = w.xs; b.ys = w.ys; b.face_attr = p->face_attr;
-    b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx;
+    b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx; b.unc_blocks = w.unc_blocks;
     if (p->num_outputs < 0 || p->num_outputs > DIBR_MAX_OUTPUTS) return fail("num_outputs=%d outside [0,%d]", p->num_outputs, DIBR_MAX_OUTPUTS);
     b.any_grad_im = 0;
     if (p->num_outputs == 0) {

@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(256) backward_faces_kernel(BwdParams P)
     const bool active = g < P.total_faces;
     const int D = P.num_attr;
     const int W = P.width, H = P.height;
+    const unsigned full = 0xffffffffu;
+    const unsigned gmask = 0xffu << ((tid & 31) & ~(GRP - 1));
 
     float acc[3 * DMAX];
 #pragma unroll
@@ -60,102 +62,121 @@ __global__ void __launch_bounds__(256) backward_faces_kernel(BwdParams P)
     bool any_c = false, any_p = false;
     FaceRec rec;
     int b = 0, f = 0;
+    size_t img = 0;
+    const int32_t* __restrict__ idx = P.imidx;
+    int sc0 = 0, sc1 = 0, sr0 = 0, sr1 = 0;          // soft part: pixel range of the expanded bbox
+    bool near_uncovered = false;
 
     if (active) {
         rec = P.recs[g];
         b = image_of_face_b(g, P.batch, P.faces_per_image, P.face_offsets);
         f = g - (P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image);
-        const size_t img = (size_t)b * H * W;
-        const int32_t* __restrict__ idx = P.imidx + img;
+        img = (size_t)b * H * W;
+        idx = P.imidx + img;
         const float sx = (float)W / (float)P.multiplier, sy = (float)H / (float)P.multiplier;
 
-        // ---- colour part: pixels this face won -------------------------------------------------
+        // ---- colour part: pixels this face won (lane = image row, inner loop over columns) ------------
         if (P.any_grad_im && rec.nz >= 0.0f) {
             const int c0 = col_lower(P.xs, W, rec.xmin, sx), c1 = col_lower(P.xs, W, rec.xmax, sx);
             const int r0 = row_lower(P.ys, H, rec.ymax, sy), r1 = row_lower(P.ys, H, rec.ymin, sy);
-            const int nc = c1 - c0, npx = nc * (r1 - r0);
-            if (nc > 0 && npx > 0) {
+            if (c1 > c0 && r1 > r0) {
                 const FaceK fk = make_facek(rec);
-                const size_t img_px = img;
-                for (int i = gl; i < npx; i += GRP) {
-                    const int r = r0 + i / nc, c = c0 + i % nc;
-                    const size_t pix = (size_t)r * W + c;
-                    if (idx[pix] != f + 1) continue;
-                    float w0, w1, w2;
-                    bary(fk, P.xs[c], P.ys[r], w0, w1, w2);
-                    any_c = true;
+                for (int r = r0 + gl; r < r1; r += GRP) {
+                    const int32_t* __restrict__ row = idx + (size_t)r * W;
+                    const float y0 = P.ys[r];
+                    for (int c = c0; c < c1; c++) {
+                        if (row[c] != f + 1) continue;
+                        const size_t pix = (size_t)r * W + c;
+                        float w0, w1, w2;
+                        bary(fk, P.xs[c], y0, w0, w1, w2);
+                        any_c = true;
 #pragma unroll
-                    for (int d = 0; d < DMAX; d++) {
-                        if (d < D && P.chan_grad[d]) {
-                            const float gv = __ldg(P.chan_grad[d] + (img_px + pix) * (size_t)P.chan_stride[d]);
-                            acc[0 * DMAX + d] = fmaf(gv, w0, acc[0 * DMAX + d]);
-                            acc[1 * DMAX + d] = fmaf(gv, w1, acc[1 * DMAX + d]);
-                            acc[2 * DMAX + d] = fmaf(gv, w2, acc[2 * DMAX + d]);
+                        for (int d = 0; d < DMAX; d++) {
+                            if (d < D && P.chan_grad[d]) {
+                                const float gv = __ldg(P.chan_grad[d] + (img + pix) * (size_t)P.chan_stride[d]);
+                                acc[0 * DMAX + d] = fmaf(gv, w0, acc[0 * DMAX + d]);
+                                acc[1 * DMAX + d] = fmaf(gv, w1, acc[1 * DMAX + d]);
+                                acc[2 * DMAX + d] = fmaf(gv, w2, acc[2 * DMAX + d]);
+                            }
                         }
                     }
                 }
             }
         }
-        // ---- soft part: uncovered pixels that counted this face ---------------------------------
+        // ---- soft part, step 1: does the expanded bbox touch an 8x8 block with an uncovered pixel? -----
         if (P.grad_improb && P.knum > 0) {
             const float ex = P.expand_mul;
-            const float xmin = rec.xmin - ex, xmax = rec.xmax + ex, ymin = rec.ymin - ex, ymax = rec.ymax + ex;
-            const int c0 = col_lower(P.xs, W, xmin, sx), c1 = col_lower(P.xs, W, xmax, sx);
-            const int r0 = row_lower(P.ys, H, ymax, sy), r1 = row_lower(P.ys, H, ymin, sy);
-            const int nc = c1 - c0, npx = nc * (r1 - r0);
-            if (nc > 0 && npx > 0) {
-                const float mult = (float)P.multiplier;
-                const float zscale = (float)P.delta / (mult * mult);
-                const float sentinel = 4.0f * mult * mult;
-                const float* __restrict__ gpr = P.grad_improb + img;
-                const float* __restrict__ comp = P.imcomp + img;
-                const float px[3] = {rec.ax, rec.bx, rec.cx}, py[3] = {rec.ay, rec.by, rec.cy};
-                for (int i = gl; i < npx; i += GRP) {
-                    const int r = r0 + i / nc, c = c0 + i % nc;
-                    const size_t pix = (size_t)r * W + c;
-                    const int v = idx[pix];
-                    if (v > 0 || (v < 0 && f + 1 > -v)) continue;      // covered, or beyond the K-th face
-                    const float x0 = P.xs[c], y0 = P.ys[r];
-                    const SoftHit h = soft_distance(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, x0, y0, sentinel);
-                    float p, om;
-                    soft_prob(h.d2 * zscale, p, om);
-                    // d improb / d p_k = prod_{j != k}(1 - p_j) = comp / (1 - p_k);  dp/dz = -p;
-                    // z = zscale * d2;  gradient w.r.t. UN-multiplied coordinates carries one more 'mult'
-                    const float coef = -__ldg(gpr + pix) * __ldg(comp + pix) / (om + 1e-15f) * p * zscale * mult;
-                    if (coef == 0.0f) continue;
-                    any_p = true;
-                    if (h.kase >= 3) {
-                        const int k = h.kase - 3;
-                        const float vx = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
-                        const float vy = (k == 0) ? py[0] : ((k == 1) ? py[1] : py[2]);
-                        const float gx = coef * 2.0f * (vx - x0), gy = coef * 2.0f * (vy - y0);
-                        if (k == 0) { gp[0] += gx; gp[1] += gy; }
-                        else if (k == 1) { gp[2] += gx; gp[3] += gy; }
-                        else { gp[4] += gx; gp[5] += gy; }
-                    } else {
-                        const int k = h.kase, k2 = (k + 1) % 3;
-                        const float x1 = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
-                        const float y1 = (k == 0) ? py[0] : ((k == 1) ? py[1] : py[2]);
-                        const float x2 = (k2 == 0) ? px[0] : ((k2 == 1) ? px[1] : px[2]);
-                        const float y2 = (k2 == 0) ? py[0] : ((k2 == 1) ? py[1] : py[2]);
-                        const float exx = x2 - x1, eyy = y2 - y1;
-                        const float s2 = 2.0f * coef / h.len2;
-                        const float gx1 = s2 * ((y0 - y2) * h.cr + h.d2 * exx);
-                        const float gy1 = s2 * (-(x0 - x2) * h.cr + h.d2 * eyy);
-                        const float gx2 = s2 * (-(y0 - y1) * h.cr - h.d2 * exx);
-                        const float gy2 = s2 * ((x0 - x1) * h.cr - h.d2 * eyy);
-                        if (k == 0) { gp[0] += gx1; gp[1] += gy1; gp[2] += gx2; gp[3] += gy2; }
-                        else if (k == 1) { gp[2] += gx1; gp[3] += gy1; gp[4] += gx2; gp[5] += gy2; }
-                        else { gp[4] += gx1; gp[5] += gy1; gp[0] += gx2; gp[1] += gy2; }
-                    }
+            sc0 = col_lower(P.xs, W, rec.xmin - ex, sx); sc1 = col_lower(P.xs, W, rec.xmax + ex, sx);
+            sr0 = row_lower(P.ys, H, rec.ymax + ex, sy); sr1 = row_lower(P.ys, H, rec.ymin - ex, sy);
+            if (sc1 > sc0 && sr1 > sr0) {
+                const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
+                const unsigned short* __restrict__ ub = P.unc_blocks + (size_t)b * tiles_x * tiles_y;
+                const int bx0 = sc0 >> 3, bx1 = (sc1 - 1) >> 3, by0 = sr0 >> 3, by1 = (sr1 - 1) >> 3;
+                const int nbx = bx1 - bx0 + 1, nblk = nbx * (by1 - by0 + 1);
+                for (int k = gl; k < nblk && !near_uncovered; k += GRP) {
+                    const int by = by0 + k / nbx, bx = bx0 + k % nbx;
+                    const unsigned m = ub[(by >> 2) * tiles_x + (bx >> 2)];
+                    near_uncovered = (m >> ((by & 3) * 4 + (bx & 3))) & 1u;
+                }
+            }
+        }
+    }
+    // the 8 lanes of a face decide together, so whole groups skip the walk (warp-wide vote: every lane gets here)
+    near_uncovered = (__ballot_sync(full, near_uncovered) & gmask) != 0u;
+
+    // ---- soft part, step 2: uncovered pixels that counted this face ------------------------------------------
+    if (active && near_uncovered) {
+        const float mult = (float)P.multiplier;
+        const float zscale = (float)P.delta / (mult * mult);
+        const float sentinel = 4.0f * mult * mult;
+        const float* __restrict__ gpr = P.grad_improb + img;
+        const float* __restrict__ comp = P.imcomp + img;
+        const float px[3] = {rec.ax, rec.bx, rec.cx}, py[3] = {rec.ay, rec.by, rec.cy};
+        for (int r = sr0 + gl; r < sr1; r += GRP) {
+            const int32_t* __restrict__ row = idx + (size_t)r * W;
+            const float y0 = P.ys[r];
+            for (int c = sc0; c < sc1; c++) {
+                const int v = row[c];
+                if (v > 0 || (v < 0 && f + 1 > -v)) continue;      // covered, or beyond the K-th face
+                const size_t pix = (size_t)r * W + c;
+                const float x0 = P.xs[c];
+                const SoftHit h = soft_distance(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, x0, y0, sentinel);
+                float p, om;
+                soft_prob(h.d2 * zscale, p, om);
+                // d improb / d p_k = prod_{j != k}(1 - p_j) = comp / (1 - p_k);  dp/dz = -p;
+                // z = zscale * d2;  gradient w.r.t. UN-multiplied coordinates carries one more 'mult'
+                const float coef = -__ldg(gpr + pix) * __ldg(comp + pix) / (om + 1e-15f) * p * zscale * mult;
+                if (coef == 0.0f) continue;
+                any_p = true;
+                if (h.kase >= 3) {
+                    const int k = h.kase - 3;
+                    const float vx = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
+                    const float vy = (k == 0) ? py[0] : ((k == 1) ? py[1] : py[2]);
+                    const float gx = coef * 2.0f * (vx - x0), gy = coef * 2.0f * (vy - y0);
+                    if (k == 0) { gp[0] += gx; gp[1] += gy; }
+                    else if (k == 1) { gp[2] += gx; gp[3] += gy; }
+                    else { gp[4] += gx; gp[5] += gy; }
+                } else {
+                    const int k = h.kase, k2 = (k + 1) % 3;
+                    const float x1 = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
+                    const float y1 = (k == 0) ? py[0] : ((k == 1) ? py[1] : py[2]);
+                    const float x2 = (k2 == 0) ? px[0] : ((k2 == 1) ? px[1] : px[2]);
+                    const float y2 = (k2 == 0) ? py[0] : ((k2 == 1) ? py[1] : py[2]);
+                    const float exx = x2 - x1, eyy = y2 - y1;
+                    const float s2 = 2.0f * coef / h.len2;
+                    const float gx1 = s2 * ((y0 - y2) * h.cr + h.d2 * exx);
+                    const float gy1 = s2 * (-(x0 - x2) * h.cr + h.d2 * eyy);
+                    const float gx2 = s2 * (-(y0 - y1) * h.cr - h.d2 * exx);
+                    const float gy2 = s2 * ((x0 - x1) * h.cr - h.d2 * eyy);
+                    if (k == 0) { gp[0] += gx1; gp[1] += gy1; gp[2] += gx2; gp[3] += gy2; }
+                    else if (k == 1) { gp[2] += gx1; gp[3] += gy1; gp[4] += gx2; gp[5] += gy2; }
+                    else { gp[4] += gx1; gp[5] += gy1; gp[0] += gx2; gp[1] += gy2; }
                 }
             }
         }
     }
 
     // ---- fixed-tree reduction over the 8 lanes of the face ------------------------------------------
-    const unsigned full = 0xffffffffu;
-    const unsigned gmask = 0xffu << ((tid & 31) & ~(GRP - 1));
     const bool grp_c = (__ballot_sync(full, any_c) & gmask) != 0u;
     const bool grp_p = (__ballot_sync(full, any_p) & gmask) != 0u;
     // the shuffles below are warp-wide collectives: every lane of the warp must execute the same

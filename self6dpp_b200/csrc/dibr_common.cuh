@@ -9,14 +9,14 @@
 
 namespace dibr {
 
-constexpr int TILE = 64;            // forward CTA tile (pixels per side)
+constexpr int TILE = 32;            // forward CTA tile (pixels per side)
 constexpr int FWD_THREADS = 256;
-constexpr int LCAP = 2048;          // faces per in-shared-memory batch of a tile
+constexpr int LCAP = 1024;          // faces per in-shared-memory batch of a tile
 constexpr int SUB = 16;             // sub-tile side for the soft-silhouette lists
 constexpr int NSUB = (TILE / SUB) * (TILE / SUB);
-constexpr int SUBCAP = 384;         // entries per sub-tile list
-constexpr int BIGCAP = 128;         // deferred large faces per batch
-constexpr int BIG_AREA = 96;        // pixels of a face inside the tile above which the CTA cooperates
+constexpr int SUBCAP = 512;         // entries per sub-tile list
+constexpr int BIGCAP = 64;          // deferred large faces per batch
+constexpr int BIG_AREA = 128;       // pixels of a face inside the tile above which the CTA cooperates
 constexpr int SCAN_CHUNK = 256;     // faces per TMA-staged bbox chunk
 
 // 64 B face record, written by the set-up kernels.

@@ -1,18 +1,20 @@
-// Forward pass of the B200 DIB-R rasterizer: one CTA per 64x64 screen tile.
+// Forward pass of the B200 DIB-R rasterizer: one CTA (256 threads) per 32x32 screen tile, ~54 KB of
+// shared memory so four CTAs share an SM.
 //
 //   phase A  stream the image's face bboxes through shared memory with TMA bulk copies
 //            (cp.async.bulk + mbarrier, double buffered) and keep, in ascending face order, the
 //            faces whose EXPANDED bbox touches the tile (warp-ballot compaction)       [binning]
-//   phase B  face-parallel coverage: every listed front face walks the pixel centres inside
-//            its bbox, solves the barycentric system in the frozen fp32 order and does a 64-bit
-//            shared-memory atomicMax on (orderable z | ~face id): the winner is the face with
-//            the largest z and, on ties, the smallest index -- exactly what the reference's
-//            ascending loop with a strict '>' produces, independent of traversal order.
-//   phase C  resolve: per pixel recompute the winner's weights, interpolate D attributes,
-//            write im / improb=1 / imidx (coalesced, 128-bit stores when D % 4 == 0)
-//   phase D  soft silhouette for uncovered pixels: per 16x16 sub-tile ordered lists, then per
-//            8x4 pixel block (one warp) the first K faces in index order whose expanded bbox
-//            holds the pixel contribute exp(-delta d^2 / m^2).
+//   phase B  compact the front faces whose bbox really holds a pixel centre of the tile, then
+//            face-parallel coverage with 4 lanes per face: barycentric solve in the frozen fp32
+//            order and a 64-bit shared-memory atomicMax on (orderable z | ~face id).  The winner
+//            is the face with the largest z and, on ties, the smallest index -- what the
+//            reference's ascending loop with a strict '>' produces, independent of traversal order.
+//   phase C  resolve: per pixel recompute the winner's weights, interpolate the D attributes and
+//            write every output tensor / improb=1 / imidx (one image row per warp: coalesced)
+//   phase D  soft silhouette for uncovered pixels, one 8x4 pixel block per warp: (1) collect per
+//            pixel the first K listed faces whose expanded bbox holds the pixel (ballot pre-filter
+//            against the block, per-lane hit lists in shared memory), (2) evaluate
+//            exp(-delta d^2 / m^2) for the collected faces with all lanes busy.
 //
 // Replaces kaolin v0.1's dr_cuda_forward_render_batch + dr_cuda_forward_prob_batch, which the
 // reference calls at lib/dr_utils/dib_renderer_x/rasterizer/rasterizer.py:152-172 (one thread
@@ -24,35 +26,50 @@
 
 namespace dibr {
 
+constexpr int NWARP = FWD_THREADS / 32;
+constexpr int HITCAP = 24;              // collected faces per pixel per round of phase D
+constexpr int BW = 8, BH = 4;           // pixel block of one warp in phase D
+constexpr int NBX = TILE / BW, NBLK = NBX * (TILE / BH);
+static_assert(TILE == 32 && LCAP <= 1024, "rlist packing assumes 5-bit pixel coordinates and 10-bit list indices");
+
 struct FwdSmem {
-    unsigned long long zkey[TILE * TILE];   // 32 KB
-    float4 lbox[LCAP];                      // 32 KB  expanded bbox of listed faces
-    int lid[LCAP];                          //  8 KB  local face ids, ascending
-    float4 stage[2][SCAN_CHUNK];            //  8 KB  TMA landing buffers
-    float soft_q[TILE * TILE];              // 16 KB  1 - prod(1-p)
-    float soft_c[TILE * TILE];              // 16 KB  prod(1-p)
-    unsigned short sublist[NSUB][SUBCAP];   // 12 KB
-    unsigned char cnt[TILE * TILE];         //  4 KB  accepted faces per pixel (255 = covered)
+    unsigned long long zkey[TILE * TILE];       //  8 KB
+    float4 lbox[LCAP];                          // 16 KB  expanded bbox of listed faces
+    int lid[LCAP];                              //  4 KB  local face ids, ascending
+    union {                                     // 12 KB
+        struct {
+            float4 stage[2][SCAN_CHUNK];        //        TMA landing buffers (phase A)
+            unsigned int rlist[LCAP];           //        raster candidates (phase B)
+        } ab;
+        unsigned short hits[HITCAP][FWD_THREADS];   //    per-lane collected list entries (phase D)
+    } u;
+    float soft_q[TILE * TILE];                  //  4 KB  1 - prod(1-p)
+    float soft_c[TILE * TILE];                  //  4 KB  prod(1-p)
+    unsigned short sublist[NSUB][SUBCAP];       //  4 KB
+    unsigned char cnt[TILE * TILE];             //  1 KB  accepted faces per pixel (255 = covered)
     int subcnt[NSUB];
     int big[BIGCAP];
     float xs[TILE], ys[TILE];
-    int warp_tot[FWD_THREADS / 32];
-    int nbig, lcount, next_block, flag;
+    int warp_tot[NWARP];
+    int nbig, lcount, next_block, pad0;
     unsigned int sub_uncovered;
+    unsigned int unc_blocks;                    // bit (by*4+bx): 8x8 block holds an uncovered pixel
     uint64_t bar[2];
 };
 
-// first index i in [0,n) with v[i] >= x, v ascending (n if none)
-__device__ __forceinline__ int lower_asc(const float* v, int n, float x) {
-    int lo = 0, hi = n;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (v[mid] >= x) hi = mid; else lo = mid + 1; }
-    return lo;
+// first column c in [0,n] with xs[c] >= x (xs ascending, pitch 1/inv_dx): arithmetic guess + exact fix-up
+__device__ __forceinline__ int col_first_ge(const float* xs, int n, float x, float inv_dx) {
+    int c = (int)fminf(fmaxf(ceilf((x - xs[0]) * inv_dx), 0.f), (float)n);
+    while (c > 0 && xs[c - 1] >= x) c--;
+    while (c < n && xs[c] < x) c++;
+    return c;
 }
-// first index i in [0,n) with v[i] < x, v descending (n if none)
-__device__ __forceinline__ int lower_desc(const float* v, int n, float x) {
-    int lo = 0, hi = n;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (v[mid] < x) hi = mid; else lo = mid + 1; }
-    return lo;
+// first row r in [0,n] with ys[r] < y (ys descending)
+__device__ __forceinline__ int row_first_lt(const float* ys, int n, float y, float inv_dy) {
+    int r = (int)fminf(fmaxf(floorf((ys[0] - y) * inv_dy) + 1.0f, 0.f), (float)n);
+    while (r > 0 && ys[r - 1] < y) r--;
+    while (r < n && ys[r] >= y) r++;
+    return r;
 }
 
 // Phase A: append to the list, in ascending order, the faces in [pos, fnum) whose expanded bbox
@@ -62,21 +79,19 @@ __device__ int fill_list(FwdSmem& s, const float4* __restrict__ bbox, int pos, i
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int lcount = 0;
-    // prologue: stage the first chunk
     if (tid == 0 && pos < fnum) {
         const int nf = min(SCAN_CHUNK, fnum - pos);
         mbar_arrive_expect_tx(&s.bar[0], nf * 16);
-        tma_load_1d(&s.stage[0][0], bbox + pos, nf * 16, &s.bar[0]);
+        tma_load_1d(&s.u.ab.stage[0][0], bbox + pos, nf * 16, &s.bar[0]);
     }
     int buf = 0;
     while (pos < fnum) {
         const int nf = min(SCAN_CHUNK, fnum - pos);
         const int npos = pos + nf;
-        // prefetch the following chunk into the other buffer
-        if (tid == 0 && npos < fnum) {
+        if (tid == 0 && npos < fnum) {                  // prefetch the following chunk
             const int nf2 = min(SCAN_CHUNK, fnum - npos);
             mbar_arrive_expect_tx(&s.bar[buf ^ 1], nf2 * 16);
-            tma_load_1d(&s.stage[buf ^ 1][0], bbox + npos, nf2 * 16, &s.bar[buf ^ 1]);
+            tma_load_1d(&s.u.ab.stage[buf ^ 1][0], bbox + npos, nf2 * 16, &s.bar[buf ^ 1]);
         }
         uint32_t& ph = buf ? phase1 : phase0;
         mbar_wait(&s.bar[buf], ph);
@@ -85,7 +100,7 @@ __device__ int fill_list(FwdSmem& s, const float4* __restrict__ bbox, int pos, i
         bool hit = false;
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid < nf) {
-            bb = s.stage[buf][tid];
+            bb = s.u.ab.stage[buf][tid];
             bb.x -= ex; bb.y -= ex; bb.z += ex; bb.w += ex;        // rasterizer.py:55-57
             // some pixel centre of the tile passes xmin <= x0 < xmax and ymin <= y0 < ymax
             hit = (bb.x <= tx_hi) && (bb.z > tx_lo) && (bb.y <= ty_hi) && (bb.w > ty_lo);
@@ -95,7 +110,7 @@ __device__ int fill_list(FwdSmem& s, const float4* __restrict__ bbox, int pos, i
         __syncthreads();
         int base = lcount, tot = 0;
 #pragma unroll
-        for (int w = 0; w < FWD_THREADS / 32; w++) {
+        for (int w = 0; w < NWARP; w++) {
             const int c = s.warp_tot[w];
             if (w < warp) base += c;
             tot += c;
@@ -136,37 +151,95 @@ __device__ __forceinline__ void raster_pixel(FwdSmem& s, const FaceK& fk, int f,
     atomicMax(&s.zkey[ly * TILE + lx], key);
 }
 
+struct RasterEntry { int li, c0, nc, r0, nr; };
+__device__ __forceinline__ RasterEntry unpack_entry(unsigned int p) {
+    RasterEntry e;
+    e.li = p & 1023; e.c0 = (p >> 10) & 31; e.nc = ((p >> 15) & 31) + 1; e.r0 = (p >> 20) & 31; e.nr = ((p >> 25) & 31) + 1;
+    return e;
+}
+
+__device__ __forceinline__ void raster_face_cta(FwdSmem& s, const FaceRec* __restrict__ recs, unsigned int packed) {
+    const RasterEntry e = unpack_entry(packed);
+    const int f = s.lid[e.li];
+    const FaceRec r = recs[f];
+    const FaceK fk = make_facek(r);
+    for (int i = threadIdx.x; i < e.nc * e.nr; i += FWD_THREADS) raster_pixel(s, fk, f, e.c0 + i % e.nc, e.r0 + i / e.nc);
+}
+
 // Phase B
-__device__ void raster_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw, int th)
+__device__ void raster_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw, int th, float inv_dx, float inv_dy)
 {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lcount = s.lcount;
-    for (int i = tid; i < lcount; i += FWD_THREADS) {
-        const int f = s.lid[i];
-        const FaceRec r = recs[f];
-        if (r.nz < 0.0f) continue;                 // back face (K1 only)
-        const int c0 = lower_asc(s.xs, tw, r.xmin), c1 = lower_asc(s.xs, tw, r.xmax);
-        const int r0 = lower_desc(s.ys, th, r.ymax), r1 = lower_desc(s.ys, th, r.ymin);
-        const int nc = c1 - c0, nr = r1 - r0;
-        if (nc <= 0 || nr <= 0) continue;
-        if (nc * nr > BIG_AREA) {
-            const int slot = atomicAdd(&s.nbig, 1);
-            if (slot < BIGCAP) { s.big[slot] = f; continue; }
+    // ---- B1: front faces with a non-empty pixel range -> rlist (packed: list index | c0 | nc-1 | r0 | nr-1)
+    int rcount = 0;
+    for (int i0 = 0; i0 < lcount; i0 += FWD_THREADS) {
+        const int i = i0 + tid;
+        unsigned int packed = 0;
+        bool keep = false;
+        if (i < lcount) {
+            const float4* rp = reinterpret_cast<const float4*>(recs + s.lid[i]);
+            const float4 t2 = __ldg(rp + 2);                       // cz, nz, -, -
+            if (t2.y >= 0.0f) {                                     // front face (K1 culls normalz < 0)
+                const float4 bb = __ldg(rp + 3);                   // xmin, ymin, xmax, ymax
+                const int c0 = col_first_ge(s.xs, tw, bb.x, inv_dx), c1 = col_first_ge(s.xs, tw, bb.z, inv_dx);
+                const int r0 = row_first_lt(s.ys, th, bb.w, inv_dy), r1 = row_first_lt(s.ys, th, bb.y, inv_dy);
+                if (c1 > c0 && r1 > r0) {
+                    keep = true;
+                    packed = (unsigned)i | ((unsigned)c0 << 10) | ((unsigned)(c1 - c0 - 1) << 15) |
+                             ((unsigned)r0 << 20) | ((unsigned)(r1 - r0 - 1) << 25);
+                }
+            }
         }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s.warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int base = rcount, tot = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) {
+            const int c = s.warp_tot[w];
+            if (w < warp) base += c;
+            tot += c;
+        }
+        if (keep) s.u.ab.rlist[base + __popc(bal & ((1u << lane) - 1u))] = packed;
+        rcount += tot;
+        __syncthreads();
+    }
+    // ---- B2: 4 lanes per face; faces with many pixels in the tile are deferred to the whole CTA
+    const int q = tid >> 2, ql = tid & 3;
+    for (int e = q; e < rcount; e += FWD_THREADS / 4) {
+        const unsigned int packed = s.u.ab.rlist[e];
+        const RasterEntry en = unpack_entry(packed);
+        const int npx = en.nc * en.nr;
+        if (npx > BIG_AREA) {
+            if (ql == 0) {
+                const int slot = atomicAdd(&s.nbig, 1);
+                if (slot < BIGCAP) s.big[slot] = (int)packed;      // beyond BIGCAP: picked up by the rescan below
+            }
+            continue;
+        }
+        const int f = s.lid[en.li];
+        const FaceRec r = recs[f];
         const FaceK fk = make_facek(r);
-        for (int ly = r0; ly < r1; ly++)
-            for (int lx = c0; lx < c1; lx++) raster_pixel(s, fk, f, lx, ly);
+        const unsigned inv = 65536u / (unsigned)en.nc + 1u;        // exact i / nc for i < 1024
+        for (int i = ql; i < npx; i += 4) {
+            const int row = (int)(((unsigned)i * inv) >> 16);
+            raster_pixel(s, fk, f, en.c0 + (i - row * en.nc), en.r0 + row);
+        }
     }
     __syncthreads();
-    const int nbig = min(s.nbig, BIGCAP);
-    for (int j = 0; j < nbig; j++) {
-        const int f = s.big[j];
-        const FaceRec r = recs[f];
-        const int c0 = lower_asc(s.xs, tw, r.xmin), c1 = lower_asc(s.xs, tw, r.xmax);
-        const int r0 = lower_desc(s.ys, th, r.ymax), r1 = lower_desc(s.ys, th, r.ymin);
-        const int nc = c1 - c0, npx = nc * (r1 - r0);
-        const FaceK fk = make_facek(r);
-        for (int i = tid; i < npx; i += FWD_THREADS) raster_pixel(s, fk, f, c0 + i % nc, r0 + i / nc);
+    // ---- B3: large faces, all threads per face
+    const int nbig_all = s.nbig;
+    for (int j = 0; j < min(nbig_all, BIGCAP); j++) raster_face_cta(s, recs, (unsigned)s.big[j]);
+    if (nbig_all > BIGCAP) {
+        for (int e = 0; e < rcount; e++) {
+            const unsigned int packed = s.u.ab.rlist[e];
+            const RasterEntry en = unpack_entry(packed);
+            if (en.nc * en.nr <= BIG_AREA) continue;
+            bool listed = false;
+            for (int j = 0; j < BIGCAP; j++) listed |= ((unsigned)s.big[j] == packed);
+            if (!listed) raster_face_cta(s, recs, packed);
+        }
     }
     __syncthreads();
     if (tid == 0) s.nbig = 0;
@@ -177,39 +250,40 @@ __device__ void raster_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw
 __device__ void soft_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw, int th, int knum,
                           float zscale, float sentinel, int* __restrict__ imidx_img, int width, int tx0, int ty0)
 {
+    const unsigned full_mask = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lcount = s.lcount;
-    // ---- per-sub-tile ordered lists -----------------------------------------------------------
-    for (int st = warp; st < NSUB; st += FWD_THREADS / 32) {
-        if (!((s.sub_uncovered >> st) & 1u)) { if (lane == 0) s.subcnt[st] = 0; continue; }
+    // ---- per-sub-tile (16x16) ordered lists: warp w builds sub-tile w -----------------------------------
+    if (warp < NSUB) {
+        const int st = warp;
         const int sx = (st % (TILE / SUB)) * SUB, sy = (st / (TILE / SUB)) * SUB;
-        if (sx >= tw || sy >= th) { if (lane == 0) s.subcnt[st] = 0; continue; }
-        const float x_lo = s.xs[sx], x_hi = s.xs[min(sx + SUB, tw) - 1];
-        const float y_hi = s.ys[sy], y_lo = s.ys[min(sy + SUB, th) - 1];
         int n = 0;
-        for (int i0 = 0; i0 < lcount; i0 += 32) {
-            const int i = i0 + lane;
-            bool hit = false;
-            if (i < lcount) {
-                const float4 bb = s.lbox[i];
-                hit = (bb.x <= x_hi) && (bb.z > x_lo) && (bb.y <= y_hi) && (bb.w > y_lo);
+        if (((s.sub_uncovered >> st) & 1u) && sx < tw && sy < th) {
+            const float x_lo = s.xs[sx], x_hi = s.xs[min(sx + SUB, tw) - 1];
+            const float y_hi = s.ys[sy], y_lo = s.ys[min(sy + SUB, th) - 1];
+            for (int i0 = 0; i0 < lcount; i0 += 32) {
+                const int i = i0 + lane;
+                bool hit = false;
+                if (i < lcount) {
+                    const float4 bb = s.lbox[i];
+                    hit = (bb.x <= x_hi) && (bb.z > x_lo) && (bb.y <= y_hi) && (bb.w > y_lo);
+                }
+                const unsigned bal = __ballot_sync(full_mask, hit);
+                if (hit) {
+                    const int slot = n + __popc(bal & ((1u << lane) - 1u));
+                    if (slot < SUBCAP) s.sublist[st][slot] = (unsigned short)i;
+                }
+                n += __popc(bal);
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
-                const int slot = n + __popc(bal & ((1u << lane) - 1u));
-                if (slot < SUBCAP) s.sublist[st][slot] = (unsigned short)i;
-            }
-            n += __popc(bal);
         }
         if (lane == 0) s.subcnt[st] = n;          // n > SUBCAP: overflow, fall back to the full list
     }
     __syncthreads();
-    // ---- 8x4 pixel blocks, handed out dynamically ---------------------------------------------
-    constexpr int BW = 8, BH = 4, NBX = TILE / BW, NBLK = NBX * (TILE / BH);
+    // ---- 8x4 pixel blocks, handed out dynamically ---------------------------------------------------------
     for (;;) {
         int blk = 0;
         if (lane == 0) blk = atomicAdd(&s.next_block, 1);
-        blk = __shfl_sync(0xffffffffu, blk, 0);
+        blk = __shfl_sync(full_mask, blk, 0);
         if (blk >= NBLK) break;
         const int bx = (blk % NBX) * BW, by = (blk / NBX) * BH;
         if (bx >= tw || by >= th) continue;
@@ -218,60 +292,98 @@ __device__ void soft_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw, 
         const int pix = ly * TILE + lx;
         int c = valid ? (int)s.cnt[pix] : 255;
         bool open = (c < knum);                    // uncovered and not yet saturated
-        if (!__any_sync(0xffffffffu, open)) continue;
+        if (!__any_sync(full_mask, open)) continue;
         const int st = (by / SUB) * (TILE / SUB) + (bx / SUB);
         const int sn = s.subcnt[st];
         if (sn == 0) continue;
-        const bool full = (sn > SUBCAP);
-        const int n = full ? lcount : sn;
+        const bool whole = (sn > SUBCAP);
+        const int n = whole ? lcount : sn;
         const float x0 = valid ? s.xs[lx] : 0.f, y0 = valid ? s.ys[ly] : 0.f;
         const float x_lo = s.xs[bx], x_hi = s.xs[min(bx + BW, tw) - 1];
         const float y_hi = s.ys[by], y_lo = s.ys[min(by + BH, th) - 1];
-        float q = valid ? s.soft_q[pix] : 0.f, cc = valid ? s.soft_c[pix] : 1.f;
+        const bool had = open;
+        float q = had ? s.soft_q[pix] : 0.f, cc = had ? s.soft_c[pix] : 1.f;
+        int nh = 0;                                // collected, not yet evaluated
+
+        // (2) evaluate the collected faces: every lane works on its own k-th face
+        auto flush_hits = [&]() {
+            const int kmax = __reduce_max_sync(full_mask, nh);
+            for (int k = 0; k < kmax; k++) {
+                if (k < nh) {
+                    const int lj = s.u.hits[k][tid];
+                    const float4* rp = reinterpret_cast<const float4*>(recs + s.lid[lj]);
+                    const float4 g0 = __ldg(rp), g1 = __ldg(rp + 1);
+                    const SoftHit h = soft_distance(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, x0, y0, sentinel);
+                    float p, om;
+                    soft_prob(h.d2 * zscale, p, om);
+                    q = fmaf(p, cc, q);            // 1 - prod(1-p), accurate for small p
+                    cc = cc * om;                  // prod(1-p), accurate for p near 1
+                }
+            }
+            nh = 0;
+        };
+
+        // (1) collect, in ascending face order
         for (int i0 = 0; i0 < n; i0 += 32) {
             const int i = i0 + lane;
             int li = -1;
             bool hit = false;
             if (i < n) {
-                li = full ? i : (int)s.sublist[st][i];
+                li = whole ? i : (int)s.sublist[st][i];
                 const float4 bb = s.lbox[li];
                 hit = (bb.x <= x_hi) && (bb.z > x_lo) && (bb.y <= y_hi) && (bb.w > y_lo);
             }
-            unsigned bal = __ballot_sync(0xffffffffu, hit);
+            unsigned bal = __ballot_sync(full_mask, hit);
+            const int nb = __popc(bal);
+            if (nb == 0) continue;
+            if (__reduce_max_sync(full_mask, nh) + nb > HITCAP) flush_hits();
+            const bool careful = nb > HITCAP;      // more candidates than a lane can hold even when empty
             while (bal) {
                 const int src = __ffs(bal) - 1;
                 bal &= bal - 1;
-                const int lj = __shfl_sync(0xffffffffu, li, src);
+                const int lj = __shfl_sync(full_mask, li, src);
                 const float4 bb = s.lbox[lj];
-                const bool mine = open && !(x0 < bb.x || x0 >= bb.z || y0 < bb.y || y0 >= bb.w);
-                if (__any_sync(0xffffffffu, mine)) {
-                    const int f = s.lid[lj];
-                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(recs + f));
-                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(recs + f) + 1);
-                    if (mine) {
-                        const SoftHit h = soft_distance(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, x0, y0, sentinel);
-                        float p, om;
-                        soft_prob(h.d2 * zscale, p, om);
-                        q = fmaf(p, cc, q);        // 1 - prod(1-p), accurate for small p
-                        cc = cc * om;              // prod(1-p), accurate for p near 1
-                        c++;
-                        if (c >= knum) {           // the K-th accepted face closes the pixel
-                            open = false;
-                            imidx_img[(size_t)(ty0 + ly) * width + (tx0 + lx)] = -(f + 1);
-                        }
+                if (open && !(x0 < bb.x || x0 >= bb.z || y0 < bb.y || y0 >= bb.w)) {
+                    s.u.hits[nh][tid] = (unsigned short)lj;
+                    nh++;
+                    c++;
+                    if (c >= knum) {               // the K-th accepted face closes the pixel
+                        open = false;
+                        imidx_img[(size_t)(ty0 + ly) * width + (tx0 + lx)] = -(s.lid[lj] + 1);
                     }
                 }
+                if (careful && __any_sync(full_mask, nh >= HITCAP)) flush_hits();
             }
-            if (!__any_sync(0xffffffffu, open)) break;
+            if (!__any_sync(full_mask, open)) break;
         }
-        if (valid && s.cnt[pix] != 255) { s.soft_q[pix] = q; s.soft_c[pix] = cc; s.cnt[pix] = (unsigned char)c; }
+        flush_hits();
+        if (had) { s.soft_q[pix] = q; s.soft_c[pix] = cc; s.cnt[pix] = (unsigned char)c; }
     }
     __syncthreads();
     if (tid == 0) s.next_block = 0;
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(FWD_THREADS, 2)
+// zero-fill rows [0,th) x [0,tw) of one [H,W,ch] image tile; 128-bit stores when the rows are 16 B aligned
+__device__ __forceinline__ void zero_tile(float* __restrict__ img, int width, int ch, int tx0, int ty0, int tw, int th)
+{
+    const int tid = threadIdx.x;
+    const int rowf = tw * ch;
+    if ((((size_t)width * ch) & 3) == 0 && ((tx0 * ch) & 3) == 0 && (rowf & 3) == 0 && ((reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
+        const int rv = rowf >> 2;
+        for (int i = tid; i < rv * th; i += FWD_THREADS) {
+            const int r = i / rv, c = i - r * rv;
+            reinterpret_cast<float4*>(img + ((size_t)(ty0 + r) * width + tx0) * ch)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (int i = tid; i < rowf * th; i += FWD_THREADS) {
+            const int r = i / rowf, c = i - r * rowf;
+            img[((size_t)(ty0 + r) * width + tx0) * ch + c] = 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 4)
 dibr_forward_kernel(FwdParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -290,6 +402,29 @@ dibr_forward_kernel(FwdParams P)
     float* __restrict__ improb = P.improb + img_pix;
     float* __restrict__ imcomp = P.imcomp + img_pix;
     int* __restrict__ imidx = P.imidx + img_pix;
+    const float ex = P.expand_mul;
+
+    // ---- whole-image cull (imgbox: ordered maxima of (-xmin,-ymin,xmax,ymax) over the image's faces) ----------
+    const float t_xlo = pix_x(tx0, P.width, P.multiplier), t_xhi = pix_x(tx0 + tw - 1, P.width, P.multiplier);
+    const float t_yhi = pix_y(ty0, P.height, P.multiplier), t_ylo = pix_y(ty0 + th - 1, P.height, P.multiplier);
+    bool touched = false;
+    if (fnum > 0) {
+        const uint4 ib = P.imgbox[b];
+        const float ixmin = -ord2f(ib.x), iymin = -ord2f(ib.y), ixmax = ord2f(ib.z), iymax = ord2f(ib.w);
+        touched = (ib.z != 0u) && (ixmin - ex <= t_xhi) && (ixmax + ex > t_xlo) && (iymin - ex <= t_yhi) && (iymax + ex > t_ylo);
+    }
+    unsigned short* __restrict__ unc_out = P.unc_blocks + ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (!touched) {          // nothing near this tile: zeros everywhere (imcomp = 1: empty product)
+        if (tid == 0) *unc_out = 0xffffu;
+        for (int g = 0; g < P.n_out; g++) zero_tile(P.out[g] + img_pix * P.out_ch[g], P.width, P.out_ch[g], tx0, ty0, tw, th);
+        zero_tile(improb, P.width, 1, tx0, ty0, tw, th);
+        zero_tile(reinterpret_cast<float*>(imidx), P.width, 1, tx0, ty0, tw, th);
+        for (int i = tid; i < tw * th; i += FWD_THREADS) {
+            const int r = i / tw, c = i - r * tw;
+            imcomp[(size_t)(ty0 + r) * P.width + tx0 + c] = 1.0f;
+        }
+        return;
+    }
 
     // ---- tile set-up ----------------------------------------------------------------------------
     if (tid < TILE) {
@@ -302,7 +437,7 @@ dibr_forward_kernel(FwdParams P)
         mbar_init(&s.bar[0], 1);
         mbar_init(&s.bar[1], 1);
         mbar_fence_init();
-        s.nbig = 0; s.next_block = 0; s.lcount = 0; s.flag = 0; s.sub_uncovered = 0u;
+        s.nbig = 0; s.next_block = 0; s.lcount = 0; s.sub_uncovered = 0u; s.unc_blocks = 0u;
     }
     for (int i = tid; i < TILE * TILE; i += FWD_THREADS) {
         s.zkey[i] = 0ull; s.soft_q[i] = 0.f; s.soft_c[i] = 1.f; s.cnt[i] = 0;
@@ -310,33 +445,26 @@ dibr_forward_kernel(FwdParams P)
     __syncthreads();
     const float tx_lo = s.xs[0], tx_hi = s.xs[tw - 1];
     const float ty_hi = s.ys[0], ty_lo = s.ys[th - 1];
-    const float ex = P.expand_mul;
+    const float inv_dx = 0.5f * (float)P.width / (float)P.multiplier;     // pixel pitch is 2m/W
+    const float inv_dy = 0.5f * (float)P.height / (float)P.multiplier;
     uint32_t phase0 = 0, phase1 = 0;
 
-    // whole-image cull: does the union of expanded bboxes touch this tile?  (imgbox holds ordered
-    // maxima of (-xmin, -ymin, xmax, ymax), zero-initialised = empty)
-    bool touched = false;
-    if (fnum > 0) {
-        const uint4 ib = P.imgbox[b];
-        const float ixmin = -ord2f(ib.x), iymin = -ord2f(ib.y), ixmax = ord2f(ib.z), iymax = ord2f(ib.w);
-        touched = (ib.z != 0u) && (ixmin - ex <= tx_hi) && (ixmax + ex > tx_lo) && (iymin - ex <= ty_hi) && (iymax + ex > ty_lo);
-    }
-
     int nbatch = 0;
-    if (touched) {
+    {
         int pos = 0;
         while (pos < fnum) {
             pos = fill_list(s, bbox, pos, fnum, ex, tx_lo, tx_hi, ty_lo, ty_hi, phase0, phase1);
-            if (s.lcount > 0) raster_list(s, recs, tw, th);
+            if (s.lcount > 0) raster_list(s, recs, tw, th, inv_dx, inv_dy);
             nbatch++;
         }
     }
 
-    // ---- phase C: resolve --------------------------------------------------------------------------
+    // ---- phase C: resolve (one image row per warp) ---------------------------------------------------------
     const float* __restrict__ fattr = P.face_attr + (size_t)f_lo * 3 * D;
     bool any_unc = false;
+#pragma unroll 1
     for (int it = 0; it < (TILE * TILE) / FWD_THREADS; it++) {
-        const int ly = it * (FWD_THREADS / TILE) + tid / TILE, lx = tid % TILE;
+        const int ly = it * NWARP + (tid >> 5), lx = tid & 31;
         const bool valid = (lx < tw) && (ly < th);
         bool unc = false;
         if (valid) {
@@ -385,24 +513,31 @@ dibr_forward_kernel(FwdParams P)
                 unc = true;
             }
         }
-        // which 16x16 sub-tiles still hold uncovered pixels
+        // which 16x16 sub-tiles still hold uncovered pixels (a warp is one row: lanes 0-15 | 16-31)
         const unsigned bal = __ballot_sync(0xffffffffu, unc);
         if (bal) {
             any_unc = true;
             if ((tid & 31) == 0) {
-                const int st_row = ly / SUB;
-                const int st0 = st_row * (TILE / SUB) + (lx / SUB);       // warp spans 32 columns = 2 sub-tiles
+                const int st0 = (ly / SUB) * (TILE / SUB);
                 unsigned m = 0;
                 if (bal & 0x0000ffffu) m |= 1u << st0;
                 if (bal & 0xffff0000u) m |= 1u << (st0 + 1);
                 atomicOr(&s.sub_uncovered, m);
+                unsigned m8 = 0;
+                const int brow = (ly >> 3) * 4;
+                if (bal & 0x000000ffu) m8 |= 1u << brow;
+                if (bal & 0x0000ff00u) m8 |= 1u << (brow + 1);
+                if (bal & 0x00ff0000u) m8 |= 1u << (brow + 2);
+                if (bal & 0xff000000u) m8 |= 1u << (brow + 3);
+                atomicOr(&s.unc_blocks, m8);
             }
         }
     }
     const int tile_unc = __syncthreads_or(any_unc ? 1 : 0);
+    if (tid == 0) *unc_out = (unsigned short)s.unc_blocks;
 
     // ---- phase D: soft silhouette ------------------------------------------------------------------
-    if (tile_unc && touched && P.knum > 0) {
+    if (tile_unc && P.knum > 0) {
         const float zscale = (float)P.delta / ((float)P.multiplier * (float)P.multiplier);
         const float sentinel = 4.0f * (float)P.multiplier * (float)P.multiplier;
         if (nbatch == 1) {
@@ -419,8 +554,9 @@ dibr_forward_kernel(FwdParams P)
             }
         }
     }
+#pragma unroll 1
     for (int it = 0; it < (TILE * TILE) / FWD_THREADS; it++) {
-        const int ly = it * (FWD_THREADS / TILE) + tid / TILE, lx = tid % TILE;
+        const int ly = it * NWARP + (tid >> 5), lx = tid & 31;
         if (lx < tw && ly < th && s.cnt[ly * TILE + lx] != 255) {
             const size_t gp = (size_t)(ty0 + ly) * P.width + (tx0 + lx);
             improb[gp] = s.soft_q[ly * TILE + lx];

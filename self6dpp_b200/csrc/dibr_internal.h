@@ -17,6 +17,7 @@ struct Workspace {
     float* xs;          // [width]  pixel-centre x
     float* ys;          // [height] pixel-centre y
     float* pose_part;   // [num_instances * POSE_BLOCKS * 12] partial pose-gradient sums
+    unsigned short* unc_blocks;  // [batch, tiles_y, tiles_x] bit (by*4+bx): the 8x8 pixel block of the 32x32 tile holds an uncovered pixel
     size_t bytes;
 };
 
@@ -61,6 +62,7 @@ struct FwdParams {
     float* improb;
     float* imcomp;
     int32_t* imidx;
+    unsigned short* unc_blocks;
 };
 
 struct BwdParams {
@@ -75,6 +77,7 @@ struct BwdParams {
     const float* improb;
     const float* imcomp;
     const int32_t* imidx;
+    const unsigned short* unc_blocks;
     const float* chan_grad[DIBR_MAX_ATTR_INTERNAL];   // per channel d: upstream gradient base (pre-offset) or null
     int chan_stride[DIBR_MAX_ATTR_INTERNAL];          // floats per pixel of the tensor that holds channel d
     int any_grad_im;
