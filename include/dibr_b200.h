@@ -84,6 +84,19 @@ typedef struct DibrPass {
     const float *cam_pos;           /* [ncam, 3]  cam_view_pos = -(R^T t)        (base.py:170) */
     const float *cam_proj;          /* [nproj, 16] row-major 4x4 used as [p,1] @ proj (perspective.py:122-129) */
 
+    /* ---- pose mode (optional): cameras given as object pose + intrinsics --------------------------
+     * When pose_R is non-NULL the library derives cam_rot / cam_pos / cam_proj itself (into the workspace),
+     * restating renderer/base.py:131-191 + utils/perspective.py:95-130 in one tiny kernel, and
+     * dibr_backward_meshes chains the gradients down to R and t.  cam_index of instance i is i and its
+     * proj_index column selects the row of pose_K. */
+    const float *pose_R;            /* [num_instances, 9] rotation object -> camera (OpenCV convention) */
+    const float *pose_t;            /* [num_instances, 3] */
+    const float *pose_K;            /* [num_K, 9] intrinsics */
+    int32_t num_K;
+    float znear, zfar;              /* only shape the unused clip-z column (perspective.py:98-99) */
+    float *grad_pose_R;             /* [num_instances, 9] */
+    float *grad_pose_t;             /* [num_instances, 3] */
+
     /* ---- workspace written by set-up, read by forward/backward (sizes: dibr_workspace_bytes) - */
     void *workspace;
     size_t workspace_bytes;

@@ -207,6 +207,17 @@ def project(verts_px3, faces_fx3, cam_rot_3x3, cam_pos_3, cam_proj_4x4):
     return p3, p2, nz, nn
 
 
+def camera_from_pose(R_3x3, t_3, K_3x3, width, height, near=0.01, far=10.0):
+    """Fixed-operation-order camera set-up (dibr_oracle_camera): -> (cam_rot 3x3, cam_pos 3, proj 4x4)."""
+    dt = R_3x3.dtype
+    sfx = _suffix(R_3x3)
+    cr, cp, pj = torch.zeros(3, 3, dtype=dt), torch.zeros(3, dtype=dt), torch.zeros(4, 4, dtype=dt)
+    getattr(lib(), "dibr_oracle_camera" + sfx)(
+        _p(R_3x3.contiguous()), _p(t_3.to(dt).contiguous()), _p(K_3x3.to(dt).contiguous()), int(width), int(height),
+        ctypes.c_double(near), ctypes.c_double(far), _p(cr), _p(cp), _p(pj))
+    return cr, cp, pj
+
+
 # ----------------------------------------------------------------------------------------------
 # camera set-up restated (renderer/base.py:131-191 hard-codes .cuda(); utils/perspective.py:95-130)
 # ----------------------------------------------------------------------------------------------

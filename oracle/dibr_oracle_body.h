@@ -403,6 +403,31 @@ void FN(dibr_oracle_project)(
     }
 }
 
+/* Camera set-up in a FIXED fp32 operation order (spec of the fused path's pose mode).  Restates
+ * renderer/base.py:169-170 (cam_view_R = diag(1,-1,-1) R, cam_view_pos = -(R^T t)) and
+ * utils/perspective.py:96-129 (projectiveprojection_real with x0 = y0 = 0).  The reference does the
+ * R^T t product with torch.matmul (order unspecified); fixed here as fma(R2k,t2,fma(R1k,t1,R0k*t0)). */
+void FN(dibr_oracle_camera)(const REAL *R_3x3, const REAL *t_3, const REAL *K_3x3, int width, int height,
+                            double znear, double zfar, REAL *cam_rot_3x3, REAL *cam_pos_3, REAL *cam_proj_4x4)
+{
+    for (int k = 0; k < 3; k++) {
+        cam_rot_3x3[k] = R_3x3[k];
+        cam_rot_3x3[3 + k] = -R_3x3[3 + k];
+        cam_rot_3x3[6 + k] = -R_3x3[6 + k];
+        cam_pos_3[k] = -FMA(R_3x3[6 + k], t_3[2], FMA(R_3x3[3 + k], t_3[1], R_3x3[k] * t_3[0]));
+    }
+    const REAL w = (REAL)width, h = (REAL)height;
+    for (int i = 0; i < 16; i++) cam_proj_4x4[i] = 0;
+    cam_proj_4x4[0] = ((REAL)2 * K_3x3[0]) / w;
+    cam_proj_4x4[4] = ((REAL)-2 * K_3x3[1]) / w;
+    cam_proj_4x4[5] = ((REAL)2 * K_3x3[4]) / h;
+    cam_proj_4x4[8] = (((REAL)-2 * K_3x3[2]) + w) / w;
+    cam_proj_4x4[9] = (((REAL)2 * K_3x3[5]) - h) / h;
+    cam_proj_4x4[10] = (REAL)(-(zfar + znear) / (zfar - znear));
+    cam_proj_4x4[14] = (REAL)(-2.0 * (zfar * znear) / (zfar - znear));
+    cam_proj_4x4[11] = (REAL)-1;
+}
+
 #undef CAT_
 #undef CAT
 #undef FN

@@ -28,6 +28,8 @@ class DibrPass(ctypes.Structure):
         ("num_instances", ctypes.c_int32), ("inst_desc", _c_i32p), ("verts", _c_f32p),
         ("mesh_faces", _c_i32p), ("vert_attr", _c_f32p), ("vert_attr_dim", ctypes.c_int32),
         ("attr_flags", ctypes.c_int32), ("cam_rot", _c_f32p), ("cam_pos", _c_f32p), ("cam_proj", _c_f32p),
+        ("pose_R", _c_f32p), ("pose_t", _c_f32p), ("pose_K", _c_f32p), ("num_K", ctypes.c_int32),
+        ("znear", ctypes.c_float), ("zfar", ctypes.c_float), ("grad_pose_R", _c_f32p), ("grad_pose_t", _c_f32p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("face_attr", _c_f32p), ("face_normal", _c_f32p),
         ("im", _c_f32p), ("improb", _c_f32p), ("imidx", _c_i32p), ("imcomp", _c_f32p),

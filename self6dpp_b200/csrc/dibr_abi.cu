@@ -38,6 +38,10 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     w.xs = (float*)take(sizeof(float) * (size_t)p->width);
     w.ys = (float*)take(sizeof(float) * (size_t)p->height);
     w.pose_part = (float*)take(sizeof(float) * 12 * dibr::POSE_BLOCKS * (size_t)(p->num_instances > 0 ? p->num_instances : 0));
+    const size_t ni = (size_t)(p->num_instances > 0 ? p->num_instances : 0);
+    w.cam_rot = (float*)take(sizeof(float) * 9 * ni);
+    w.cam_pos = (float*)take(sizeof(float) * 3 * ni);
+    w.cam_proj = (float*)take(sizeof(float) * 16 * (size_t)(p->num_K > 0 ? p->num_K : 0));
     w.unc_blocks = (unsigned short*)take(sizeof(unsigned short) * (size_t)p->batch * ((p->height + dibr::TILE - 1) / dibr::TILE) * ((p->width + dibr::TILE - 1) / dibr::TILE));
     w.bytes = off;
     return w;
@@ -85,6 +89,11 @@ dibr::SetupParams setup_params(const DibrPass* p) {
     s.cam_rot = p->cam_rot; s.cam_pos = p->cam_pos; s.cam_proj = p->cam_proj;
     s.face_attr = p->face_attr; s.face_normal = p->face_normal;
     s.ws = carve(p, p->workspace);
+    s.pose_R = p->pose_R; s.pose_t = p->pose_t; s.pose_K = p->pose_K; s.num_K = p->num_K;
+    const double nc = p->znear, fc = p->zfar;
+    s.q = (float)(-(fc + nc) / (fc - nc));
+    s.qn = (float)(-2.0 * (fc * nc) / (fc - nc));
+    if (p->pose_R) { s.cam_rot = s.ws.cam_rot; s.cam_pos = s.ws.cam_pos; s.cam_proj = s.ws.cam_proj; }
     return s;
 }
 
@@ -127,14 +136,16 @@ int dibr_setup_faces(const DibrPass* p, void* stream) {
 
 int dibr_setup_meshes(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
-    if (p->num_instances <= 0 || !p->inst_desc || !p->verts || !p->mesh_faces || !p->cam_rot || !p->cam_pos || !p->cam_proj)
-        return fail("setup_meshes: instances, verts, mesh_faces and cameras required");
+    if (p->num_instances <= 0 || !p->inst_desc || !p->verts || !p->mesh_faces) return fail("setup_meshes: instances, verts, mesh_faces required");
+    if (p->pose_R) {
+        if (!p->pose_t || !p->pose_K || p->num_K <= 0 || !(p->zfar > p->znear)) return fail("setup_meshes: pose mode needs pose_t, pose_K, num_K > 0 and zfar > znear");
+    } else if (!p->cam_rot || !p->cam_pos || !p->cam_proj) return fail("setup_meshes: cameras required");
     if (!p->face_attr) return fail("setup_meshes: face_attr output required");
     const int d = p->vert_attr_dim + ((p->attr_flags & 1) ? 1 : 0) + ((p->attr_flags & 2) ? 1 : 0);
     if (d != p->num_attr) return fail("setup_meshes: vert_attr_dim + flags = %d but num_attr = %d", d, p->num_attr);
     if (p->vert_attr_dim > 0 && !p->vert_attr) return fail("setup_meshes: vert_attr is null");
     const dibr::SetupParams s = setup_params(p);
-    g_launches += 1;
+    g_launches += p->pose_R ? 2 : 1;
     return cuda_fail("dibr_setup_meshes", dibr::launch_setup_meshes(s, (cudaStream_t)stream));
 }
 
@@ -195,15 +206,18 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
 
 int dibr_backward_meshes(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
-    if (p->num_instances <= 0 || !p->inst_desc || !p->verts || !p->cam_rot || !p->cam_pos || !p->cam_proj)
-        return fail("backward_meshes: instances, verts and cameras required");
+    if (p->num_instances <= 0 || !p->inst_desc || !p->verts) return fail("backward_meshes: instances and verts required");
+    if (!p->pose_R && (!p->cam_rot || !p->cam_pos || !p->cam_proj)) return fail("backward_meshes: cameras required");
+    if (p->pose_R && (!p->pose_t || !p->grad_pose_R || !p->grad_pose_t)) return fail("backward_meshes: pose mode needs pose_t, grad_pose_R, grad_pose_t");
     if (!p->grad_points2d || !p->grad_face_attr || !p->vert_face_ptr || !p->vert_face_idx) return fail("backward_meshes: face grads and vertex adjacency required");
-    if (!p->grad_cam_rot || !p->grad_cam_pos) return fail("backward_meshes: grad_cam_rot/grad_cam_pos required");
+    if (!p->pose_R && (!p->grad_cam_rot || !p->grad_cam_pos)) return fail("backward_meshes: grad_cam_rot/grad_cam_pos required");
     const dibr::Workspace w = carve(p, p->workspace);
     dibr::MeshBwdParams m;
     memset(&m, 0, sizeof(m));
     m.num_instances = p->num_instances; m.inst_desc = p->inst_desc; m.verts = p->verts;
-    m.cam_rot = p->cam_rot; m.cam_pos = p->cam_pos; m.cam_proj = p->cam_proj;
+    m.cam_rot = p->pose_R ? w.cam_rot : p->cam_rot; m.cam_pos = p->pose_R ? w.cam_pos : p->cam_pos;
+    m.cam_proj = p->pose_R ? w.cam_proj : p->cam_proj;
+    m.pose_R = p->pose_R; m.pose_t = p->pose_t; m.grad_pose_R = p->grad_pose_R; m.grad_pose_t = p->grad_pose_t;
     m.vert_attr_dim = p->vert_attr_dim; m.attr_flags = p->attr_flags; m.num_attr = p->num_attr;
     m.grad_points2d = p->grad_points2d; m.grad_face_attr = p->grad_face_attr;
     m.vert_face_ptr = p->vert_face_ptr; m.vert_face_idx = p->vert_face_idx;

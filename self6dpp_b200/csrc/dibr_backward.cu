@@ -346,15 +346,44 @@ __global__ void __launch_bounds__(256) mesh_vertex_grad_kernel(MeshBwdParams P)
     }
 }
 
+// one thread per instance: sum the per-block partials in a fixed order; in pose mode chain
+// cam_view_R = F R (F = diag(1,-1,-1)) and cam_view_pos = -(R^T t) down to R and t:
+//   dL/dR[j][k] = F_jj dL/dcamR[j][k] - t[j] dL/dpos[k],   dL/dt[j] = -sum_k R[j][k] dL/dpos[k]
 __global__ void pose_finalize_kernel(MeshBwdParams P, int nblocks)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.num_instances * 12) return;
-    const int inst = t / 12, i = t % 12;
-    float v = 0.f;
-    for (int b = 0; b < nblocks; b++) v += P.pose_part[((size_t)inst * nblocks + b) * 12 + i];
-    if (i < 9) P.grad_cam_rot[(size_t)inst * 9 + i] = v;
-    else P.grad_cam_pos[(size_t)inst * 3 + (i - 9)] = v;
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= P.num_instances) return;
+    float v[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) v[i] = 0.f;
+    for (int b = 0; b < nblocks; b++) {
+        const float* pp = P.pose_part + ((size_t)inst * nblocks + b) * 12;
+#pragma unroll
+        for (int i = 0; i < 12; i++) v[i] += pp[i];
+    }
+    if (P.grad_cam_rot) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) P.grad_cam_rot[(size_t)inst * 9 + i] = v[i];
+    }
+    if (P.grad_cam_pos) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) P.grad_cam_pos[(size_t)inst * 3 + i] = v[9 + i];
+    }
+    if (P.pose_R) {
+        const float* R = P.pose_R + (size_t)inst * 9;
+        const float* T = P.pose_t + (size_t)inst * 3;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const float sgn = (j == 0) ? 1.f : -1.f;
+            float gt = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                P.grad_pose_R[(size_t)inst * 9 + j * 3 + k] = sgn * v[j * 3 + k] - T[j] * v[9 + k];
+                gt -= R[j * 3 + k] * v[9 + k];
+            }
+            P.grad_pose_t[(size_t)inst * 3 + j] = gt;
+        }
+    }
 }
 
 int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream)
@@ -364,7 +393,7 @@ int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream)
     mesh_vertex_grad_kernel<<<grid, 256, 0, stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    pose_finalize_kernel<<<(P.num_instances * 12 + 127) / 128, 128, 0, stream>>>(P, POSE_BLOCKS);
+    pose_finalize_kernel<<<(P.num_instances + 63) / 64, 64, 0, stream>>>(P, POSE_BLOCKS);
     return (int)cudaGetLastError();
 }
 

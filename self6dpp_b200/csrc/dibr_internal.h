@@ -17,6 +17,9 @@ struct Workspace {
     float* xs;          // [width]  pixel-centre x
     float* ys;          // [height] pixel-centre y
     float* pose_part;   // [num_instances * POSE_BLOCKS * 12] partial pose-gradient sums
+    float* cam_rot;     // pose mode: [num_instances, 9]
+    float* cam_pos;     // pose mode: [num_instances, 3]
+    float* cam_proj;    // pose mode: [num_K, 16]
     unsigned short* unc_blocks;  // [batch, tiles_y, tiles_x] bit (by*4+bx): the 8x8 pixel block of the 32x32 tile holds an uncovered pixel
     size_t bytes;
 };
@@ -43,7 +46,12 @@ struct SetupParams {
     const float* cam_proj;
     float* face_attr;
     float* face_normal;
-    float* points2d_out;     // optional [total_faces,6] un-multiplied NDC (fused mode, for the backward)
+    // pose mode
+    const float* pose_R;
+    const float* pose_t;
+    const float* pose_K;
+    int num_K;
+    float q, qn;             // -(f+n)/(f-n), -2fn/(f-n)
     Workspace ws;
 };
 
@@ -103,6 +111,11 @@ struct MeshBwdParams {
     float* grad_cam_rot;
     float* grad_cam_pos;
     float* pose_part;
+    // pose mode: chain to R, t
+    const float* pose_R;
+    const float* pose_t;
+    float* grad_pose_R;
+    float* grad_pose_t;
 };
 
 constexpr int INST_STRIDE = 12;

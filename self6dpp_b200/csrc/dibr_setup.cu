@@ -149,6 +149,39 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(SetupParams P)
     store_face(P, g, b, x2[0], y2[0], x2[1], y2[1], x2[2], y2[2], zc[0], zc[1], zc[2], nz, active);
 }
 
+// pose mode: cam_view_R = diag(1,-1,-1) R, cam_view_pos = -(R^T t)  (renderer/base.py:169-170) and the 4x4
+// projection of utils/perspective.py:122-129, in the fp32 operation order frozen in oracle dibr_oracle_camera.
+__global__ void pose_to_camera_kernel(SetupParams P)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < P.num_instances) {
+        const float* R = P.pose_R + (size_t)t * 9;
+        const float* T = P.pose_t + (size_t)t * 3;
+        float* cr = P.ws.cam_rot + (size_t)t * 9;
+        float* cp = P.ws.cam_pos + (size_t)t * 3;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            cr[k] = R[k]; cr[3 + k] = -R[3 + k]; cr[6 + k] = -R[6 + k];
+            cp[k] = -__fmaf_rn(R[6 + k], T[2], __fmaf_rn(R[3 + k], T[1], __fmul_rn(R[k], T[0])));
+        }
+    }
+    if (t < P.num_K) {
+        const float* K = P.pose_K + (size_t)t * 9;
+        float* pm = P.ws.cam_proj + (size_t)t * 16;
+        const float w = (float)P.width, h = (float)P.height;
+#pragma unroll
+        for (int i = 0; i < 16; i++) pm[i] = 0.f;
+        pm[0] = __fdiv_rn(__fmul_rn(2.f, K[0]), w);
+        pm[4] = __fdiv_rn(__fmul_rn(-2.f, K[1]), w);
+        pm[5] = __fdiv_rn(__fmul_rn(2.f, K[4]), h);
+        pm[8] = __fdiv_rn(__fadd_rn(__fmul_rn(-2.f, K[2]), w), w);
+        pm[9] = __fdiv_rn(__fsub_rn(__fmul_rn(2.f, K[5]), h), h);
+        pm[10] = P.q;
+        pm[14] = P.qn;
+        pm[11] = -1.0f;
+    }
+}
+
 static inline int setup_grid(const SetupParams& P) {
     const int n = max(P.total_faces, P.width + P.height);
     return (n + 255) / 256;
@@ -166,6 +199,12 @@ int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
 {
     cudaError_t e = cudaMemsetAsync(P.ws.imgbox, 0, sizeof(uint4) * (size_t)P.batch, stream);
     if (e != cudaSuccess) return (int)e;
+    if (P.pose_R) {
+        const int n = max(P.num_instances, P.num_K);
+        pose_to_camera_kernel<<<(n + 127) / 128, 128, 0, stream>>>(P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
     setup_meshes_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
     return (int)cudaGetLastError();
 }

@@ -115,6 +115,8 @@ class RenderMeshes(Function):
             p = _base_pass(B, H, W, D, meta["knum"], meta["multiplier"], meta["delta"], meta["expand"], TF, 0)
             p.face_offsets = _lib.ptr(meta["face_offsets"])
             p.num_instances = meta["num_instances"]
+            if meta.get("pose_mode"):
+                p.num_K = int(proj_c.shape[0])          # the workspace holds the derived cameras
             ws = _alloc_workspace(p, device)
             face_attr = torch.empty(max(TF, 1), 3, D, dtype=torch.float32, device=device)
             face_normal = torch.empty(TF, 3, dtype=torch.float32, device=device) if meta["want_normals"] else None
@@ -128,7 +130,12 @@ class RenderMeshes(Function):
             p.inst_desc = _lib.ptr(meta["inst_desc"])
             p.verts, p.mesh_faces = _lib.ptr(verts_c), _lib.ptr(pack.faces)
             p.vert_attr, p.vert_attr_dim, p.attr_flags = _lib.ptr(vattr_c), A, flags
-            p.cam_rot, p.cam_pos, p.cam_proj = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
+            if meta.get("pose_mode"):      # cam_rot / cam_pos / cam_proj carry R [I,3,3], t [I,3], K [nK,3,3]
+                p.pose_R, p.pose_t, p.pose_K = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
+                p.num_K = int(proj_c.shape[0])
+                p.znear, p.zfar = float(meta["znear"]), float(meta["zfar"])
+            else:
+                p.cam_rot, p.cam_pos, p.cam_proj = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
             p.face_attr, p.face_normal = _lib.ptr(face_attr), _lib.ptr(face_normal)
             p.improb, p.imidx, p.imcomp = _lib.ptr(improb), _lib.ptr(imidx), _lib.ptr(imcomp)
             p.num_outputs = len(split)
@@ -174,7 +181,13 @@ class RenderMeshes(Function):
             p.inst_desc = _lib.ptr(meta["inst_desc"])
             p.verts = _lib.ptr(verts_c)
             p.vert_attr_dim, p.attr_flags = A, flags
-            p.cam_rot, p.cam_pos, p.cam_proj = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
+            pose_mode = bool(meta.get("pose_mode"))
+            if pose_mode:
+                p.pose_R, p.pose_t, p.pose_K = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
+                p.num_K = int(proj_c.shape[0])
+                p.znear, p.zfar = float(meta["znear"]), float(meta["zfar"])
+            else:
+                p.cam_rot, p.cam_pos, p.cam_proj = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
             p.face_attr = _lib.ptr(face_attr)
             p.improb, p.imidx, p.imcomp = _lib.ptr(improb), _lib.ptr(imidx), _lib.ptr(imcomp)
             p.grad_improb = _lib.ptr(gP)
@@ -190,7 +203,10 @@ class RenderMeshes(Function):
             g_verts = torch.empty(n_rows, 3, dtype=torch.float32, device=device) if need_verts else None
             g_vattr = torch.empty(n_rows, max(A, 1), dtype=torch.float32, device=device) if need_vattr else None
             p.grad_points2d, p.grad_face_attr = _lib.ptr(g_p2d), _lib.ptr(g_fattr)
-            p.grad_cam_rot, p.grad_cam_pos = _lib.ptr(g_rot), _lib.ptr(g_pos)
+            if pose_mode:
+                p.grad_pose_R, p.grad_pose_t = _lib.ptr(g_rot), _lib.ptr(g_pos)
+            else:
+                p.grad_cam_rot, p.grad_cam_pos = _lib.ptr(g_rot), _lib.ptr(g_pos)
             p.grad_verts, p.grad_vert_attr = _lib.ptr(g_verts), _lib.ptr(g_vattr)
             p.vert_face_ptr, p.vert_face_idx = _lib.ptr(pack.vert_face_ptr), _lib.ptr(pack.vert_face_idx)
             lib = _lib.load()

@@ -46,7 +46,26 @@ class Renderer(nn.Module):
             self.camera_up = np.array([0, 1, 0], dtype=np.float32)
         if camera_fov_y is None:
             self.camera_fov_y = 49.13434207744484 * np.pi / 180.0
-        self.camera_params = None
+        self._camera_params = None
+        self._camera_pending = None
+
+    @property
+    def camera_params(self):
+        if self._camera_params is None and self._camera_pending is not None:
+            Rs, ts, Ks, height, width, near, far, rot_type = self._camera_pending
+            self._camera_params = camera_params_from_RT_K(Rs, ts, Ks, height, width, near=near, far=far, rot_type=rot_type)
+            self._camera_pending = None
+        return self._camera_params
+
+    @camera_params.setter
+    def camera_params(self, value):
+        self._camera_params = value
+        self._camera_pending = None
+
+    def set_camera_parameters_lazy(self, Rs, ts, Ks, height, width, near, far, rot_type):
+        """same result as set_camera_parameters_from_RT_K, computed only if somebody reads .camera_params"""
+        self._camera_params = None
+        self._camera_pending = (Rs, ts, Ks, height, width, near, far, rot_type)
 
     def forward(self, points, *args, **kwargs):
         if self.camera_params is None:

@@ -9,11 +9,12 @@ here every requested attribute rides through ONE fused rasterisation (vertex att
 concatenated per model, the ones-channel and the view depth are synthesised in the set-up kernel),
 and the backward is one deterministic pass that ends in dL/dR, dL/dt.
 """
+import numpy as np
 import torch
 
 from . import fused
 from .renderer.base import Renderer as DIBRenderer
-from .renderer.cameras import camera_params_from_RT_K
+from .renderer.cameras import quat2mat_torch
 from .renderer.vc import render_instances
 
 _FACES_I32 = {}
@@ -52,9 +53,126 @@ def _model_attrs(model, names):
     return hit[0]
 
 
+class _ModelRegistry(object):
+    """Resident models of one renderer, packed once: the self-supervised loop renders the same dozen meshes
+    every iteration (self_engine_utils.py:1361-1373 builds them once), only the per-sample choice changes.
+    Per call the instance table is then pure numpy indexing + ONE pinned H2D copy."""
+
+    def __init__(self):
+        self.index = {}          # id(model dict) -> slot
+        self.models = []
+        self.sigs = []
+        self.pack = None
+        self.verts = None
+        self.table = None        # [n, 4] vert_base, num_verts, face_base, num_faces
+        self.attrs = {}          # tuple(attr names) -> [sum verts, 3*len] tensor
+
+    @staticmethod
+    def _sig(model):
+        return tuple((model[k].data_ptr(), model[k]._version) for k in ("vertices", "faces"))
+
+    def slots(self, models):
+        """slot per sample, or None when a model cannot be cached (requires grad)."""
+        out = np.empty(len(models), dtype=np.int64)
+        dirty = False
+        for i, m in enumerate(models):
+            slot = self.index.get(id(m))
+            if slot is None:
+                if m["vertices"].requires_grad:
+                    return None
+                slot = len(self.models)
+                self.index[id(m)] = slot
+                self.models.append(m)
+                self.sigs.append(self._sig(m))
+                dirty = True
+            out[i] = slot
+        for slot in set(out.tolist()):
+            m = self.models[slot]
+            if m["vertices"].requires_grad:
+                return None
+            if self._sig(m) != self.sigs[slot]:          # tensors replaced or modified in place
+                self.sigs[slot] = self._sig(m)
+                dirty = True
+        if dirty:
+            self._rebuild()
+        return out
+
+    def _rebuild(self):
+        verts = [m["vertices"].detach().reshape(-1, 3) for m in self.models]
+        faces = [_faces_int32(m["faces"]) for m in self.models]
+        self.pack = fused.MeshPack(verts, faces, verts[0].device)
+        self.verts = torch.cat(verts, dim=0).contiguous() if len(verts) > 1 else verts[0].contiguous()
+        pk = self.pack
+        self.table = np.stack([pk.vert_base[:-1], np.asarray(pk.num_verts), pk.face_base[:-1], np.asarray(pk.num_faces)],
+                              axis=1).astype(np.int64)
+        self.attrs = {}
+
+    def attr_matrix(self, names):
+        key = tuple(names)
+        hit = self.attrs.get(key)
+        if hit is None:
+            if any(m[n].requires_grad for m in self.models for n in names):
+                return None
+            per_model = [torch.cat([m[n].detach().reshape(-1, m[n].shape[-1]) for n in names], dim=1) if len(names) > 1
+                         else m[names[0]].detach().reshape(-1, m[names[0]].shape[-1]) for m in self.models]
+            hit = (torch.cat(per_model, dim=0) if len(per_model) > 1 else per_model[0]).contiguous()
+            self.attrs[key] = hit
+        return hit
+
+
 class Renderer_dibr(object):
     def __init__(self, height, width, mode):
         self.dib_ren = DIBRenderer(height, width, mode)
+        self._registry = _ModelRegistry()
+
+    def _render_batch_fast(self, Rs, ts, models, Ks, width, height, znear, zfar, rot_type, names, split, flags):
+        """pose-mode fast path: resident models, R/t/K handed straight to the kernels (no camera torch ops)."""
+        reg = self._registry
+        slots = reg.slots(models)
+        if slots is None:
+            return None
+        vattr = reg.attr_matrix(names) if names else torch.zeros(0, 1, dtype=torch.float32, device=reg.verts.device)
+        if vattr is None:
+            return None
+        device = reg.verts.device
+        if not (isinstance(Rs, torch.Tensor) and isinstance(ts, torch.Tensor)):
+            return None
+        B = len(models)
+        R = quat2mat_torch(Rs) if rot_type == "quat" else Rs
+        K = torch.as_tensor(Ks)
+        if K.device != device or K.dtype != torch.float32:
+            K = K.to(device=device, dtype=torch.float32)
+        K = K.reshape(-1, 3, 3)
+        if R.device != device or ts.device != device or R.dtype != torch.float32 or ts.dtype != torch.float32:
+            return None
+        tab = reg.table[slots]                                         # [B,4]
+        nf, nv = tab[:, 3], tab[:, 1]
+        host = torch.empty(B * fused.INST_STRIDE + B + 1, dtype=torch.int32, pin_memory=True)
+        hn = host.numpy()
+        desc = hn[:B * fused.INST_STRIDE].reshape(B, fused.INST_STRIDE)
+        out_base = np.cumsum(nf) - nf
+        ar = np.arange(B)
+        desc[:, 0], desc[:, 1], desc[:, 2], desc[:, 3], desc[:, 4] = tab[:, 0], nv, tab[:, 2], nf, out_base
+        desc[:, 5] = ar
+        desc[:, 6] = ar if K.shape[0] > 1 else 0
+        desc[:, 7] = tab[:, 0]
+        desc[:, 8] = np.cumsum(nv) - nv
+        desc[:, 9] = ar
+        desc[:, 10] = tab[:, 0]
+        desc[:, 11] = 0
+        hn[B * fused.INST_STRIDE] = 0
+        hn[B * fused.INST_STRIDE + 1:] = np.cumsum(nf)
+        dev = torch.empty_like(host, device=device)
+        dev.copy_(host, non_blocking=True)
+        A = 3 * len(names)
+        meta = dict(batch=B, height=int(height), width=int(width), attr_dim=A, attr_flags=int(flags),
+                    total_faces=int(nf.sum()), num_instances=B, num_inst_verts=int(nv.sum()), pack=reg.pack,
+                    knum=fused.DEFAULT_KNUM, multiplier=fused.DEFAULT_MULTIPLIER, delta=fused.DEFAULT_DELTA,
+                    expand=fused.DEFAULT_EXPAND, want_normals=False, num_attr_rows=int(reg.verts.shape[0]),
+                    out_split=split, inst_desc=dev[:B * fused.INST_STRIDE], face_offsets=dev[B * fused.INST_STRIDE:],
+                    pose_mode=True, znear=float(znear), zfar=float(zfar))
+        res = fused.render_meshes(reg.verts, vattr, R, ts.reshape(B, 3), K, meta)
+        return list(res[:-2]), res[-2], meta
 
     # ------------------------------------------------------------------------------------------
     def render_batch(self, Rs, ts, models, *, Ks, width, height, znear=0.01, zfar=100, rot_type="mat",
@@ -71,7 +189,6 @@ class Renderer_dibr(object):
         """
         assert self.dib_ren.mode in ["VertexColorBatch"], self.dib_ren.mode
         ret = {}
-        self.dib_ren.set_camera_parameters_from_RT_K(Rs, ts, Ks, height, width, near=znear, far=zfar, rot_type=rot_type)
         names, split, keys = [], [], []
         for key, attr in (("color", "colors"), ("norm", "normals"), ("xyz", "vertices")):
             if key in mode:
@@ -85,10 +202,17 @@ class Renderer_dibr(object):
             flags |= fused.FLAG_DEPTH
             keys.append("depth")
             split.append(1)
-        points = [[model["vertices"], _faces_int32(model["faces"])] for model in models]
-        attrs = [_model_attrs(model, names) for model in models] if names else None
-        outs, improb, _, meta = render_instances(points, attrs, self.dib_ren.camera_params, height, width, multi=False,
-                                                 want_normals=False, attr_flags=flags, out_split=split)
+        fast = self._render_batch_fast(Rs, ts, models, Ks, width, height, znear, zfar, rot_type, names, split, flags)
+        if fast is not None:
+            outs, improb, meta = fast
+            # the reference sets the camera as a side effect (renderer_dibr.py:261); keep that, lazily
+            self.dib_ren.set_camera_parameters_lazy(Rs, ts, Ks, height, width, znear, zfar, rot_type)
+        else:       # models that require grad, list-of-tensor poses, ...: generic path
+            self.dib_ren.set_camera_parameters_from_RT_K(Rs, ts, Ks, height, width, near=znear, far=zfar, rot_type=rot_type)
+            points = [[model["vertices"], _faces_int32(model["faces"])] for model in models]
+            attrs = [_model_attrs(model, names) for model in models] if names else None
+            outs, improb, _, meta = render_instances(points, attrs, self.dib_ren.camera_params, height, width, multi=False,
+                                                     want_normals=False, attr_flags=flags, out_split=split)
         out = dict(zip(keys, outs))
         im_mask = out["ones"]                                       # hardmask, bhw1
         if "color" in mode:
