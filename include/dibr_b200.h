@@ -132,6 +132,11 @@ typedef struct DibrPass {
     int32_t out_channels[DIBR_MAX_OUTPUTS];
     float *out[DIBR_MAX_OUTPUTS];
     const float *grad_out[DIBR_MAX_OUTPUTS];
+    /* ---- optional batch-global minimum of one output group (renderer_dibr.py:284 `_ren_norms.min()`) ---- */
+    int32_t min_output;                        /* index of the output group to minimise over, or -1 */
+    uint32_t *out_min_ordered;                 /* [1] order-preserving uint32 encoding of the float minimum over
+                                                  ALL pixels of that group (uncovered pixels count as 0); reset by
+                                                  the set-up call, decoded by dibr_normal_map */
     const int32_t *vert_face_ptr;  /* CSR vertex -> incident (face,corner) list, per packed mesh vertex: [sum verts + 1] */
     const int32_t *vert_face_idx;  /* [3 * sum mesh faces] entries face*3+corner, ascending */
     int32_t num_cams;
@@ -154,6 +159,12 @@ int dibr_setup_meshes(const DibrPass *pass, void *stream);
 int dibr_forward(const DibrPass *pass, void *stream);
 int dibr_backward_faces(const DibrPass *pass, void *stream);
 int dibr_backward_meshes(const DibrPass *pass, void *stream);
+
+/* normal-map post-processing of Renderer_dibr.render_batch(mode=["norm"]) (renderer_dibr.py:281-286):
+ *   out = (n - min) / (||n - min||_2 + 1e-5) * mask      per pixel, n = interpolated vertex normal (3 channels),
+ * min = the batch-global minimum accumulated by dibr_forward into min_ordered. */
+int dibr_normal_map(const float *normals_nx3, const float *mask_n, const uint32_t *min_ordered, float *out_nx3,
+                    long long num_pixels, void *stream);
 
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);

@@ -38,6 +38,7 @@ class DibrPass(ctypes.Structure):
         ("grad_cam_rot", _c_f32p), ("grad_cam_pos", _c_f32p),
         ("num_outputs", ctypes.c_int32), ("out_channels", ctypes.c_int32 * 6),
         ("out", ctypes.c_void_p * 6), ("grad_out", ctypes.c_void_p * 6),
+        ("min_output", ctypes.c_int32), ("out_min_ordered", ctypes.c_void_p),
         ("vert_face_ptr", _c_i32p), ("vert_face_idx", _c_i32p),
         ("num_cams", ctypes.c_int32), ("reserved0", ctypes.c_int32),
     ]
@@ -45,7 +46,7 @@ class DibrPass(ctypes.Structure):
 
 EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_device_count", "dibr_workspace_bytes",
            "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
-           "dibr_backward_meshes", "dibr_launch_count"]
+           "dibr_backward_meshes", "dibr_normal_map", "dibr_launch_count"]
 
 _lib = None
 
@@ -79,6 +80,9 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrPass), ctypes.c_void_p]
         fn.restype = ctypes.c_int
+    lib.dibr_normal_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_longlong, ctypes.c_void_p]
+    lib.dibr_normal_map.restype = ctypes.c_int
     if lib.dibr_abi_version() != 1:
         raise RuntimeError("libdibr_b200.so ABI version mismatch")
     if lib.dibr_sizeof_pass() != ctypes.sizeof(DibrPass):

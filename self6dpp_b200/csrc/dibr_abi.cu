@@ -42,6 +42,10 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     w.cam_rot = (float*)take(sizeof(float) * 9 * ni);
     w.cam_pos = (float*)take(sizeof(float) * 3 * ni);
     w.cam_proj = (float*)take(sizeof(float) * 16 * (size_t)(p->num_K > 0 ? p->num_K : 0));
+    w.list_counts = (int*)take(sizeof(int) * 64);
+    w.face_flags = (unsigned int*)take(sizeof(unsigned int) * (size_t)p->total_faces);   // directly after list_counts: one memset
+    w.color_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
+    w.soft_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
     w.unc_blocks = (unsigned short*)take(sizeof(unsigned short) * (size_t)p->batch * ((p->height + dibr::TILE - 1) / dibr::TILE) * ((p->width + dibr::TILE - 1) / dibr::TILE));
     w.bytes = off;
     return w;
@@ -164,6 +168,19 @@ int dibr_forward(const DibrPass* p, void* stream) {
     if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
     else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }
     f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx; f.unc_blocks = w.unc_blocks;
+    f.list_counts = w.list_counts; f.face_flags = w.face_flags; f.color_list = w.color_list; f.soft_list = w.soft_list;
+    {
+        const size_t nbytes = (size_t)((char*)w.color_list - (char*)w.list_counts);
+        cudaError_t e = cudaMemsetAsync(w.list_counts, 0, nbytes, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail("dibr_forward (reset face lists)", (int)e);
+    }
+    f.min_group = -1; f.out_min = nullptr;
+    if (p->min_output >= 0 && p->out_min_ordered) {
+        if (p->min_output >= f.n_out) return fail("forward: min_output=%d but only %d output groups", p->min_output, f.n_out);
+        f.min_group = p->min_output; f.out_min = p->out_min_ordered;
+        cudaError_t e = cudaMemsetAsync(p->out_min_ordered, 0xff, sizeof(uint32_t), (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail("dibr_forward (reset min)", (int)e);
+    }
     g_launches += 1;
     return cuda_fail("dibr_forward", dibr::launch_forward(f, (cudaStream_t)stream));
 }
@@ -181,6 +198,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     b.total_faces = p->total_faces; b.faces_per_image = p->faces_per_image; b.face_offsets = p->face_offsets;
     b.recs = w.recs; b.xs = w.xs; b.ys = w.ys; b.face_attr = p->face_attr;
     b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx; b.unc_blocks = w.unc_blocks;
+    b.list_counts = w.list_counts; b.color_list = w.color_list; b.soft_list = w.soft_list;
     if (p->num_outputs < 0 || p->num_outputs > DIBR_MAX_OUTPUTS) return fail("num_outputs=%d outside [0,%d]", p->num_outputs, DIBR_MAX_OUTPUTS);
     b.any_grad_im = 0;
     if (p->num_outputs == 0) {
@@ -200,7 +218,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     }
     b.grad_improb = p->grad_improb;
     b.grad_points2d = p->grad_points2d; b.grad_face_attr = p->grad_face_attr;
-    g_launches += 1;
+    g_launches += 2;
     return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream));
 }
 
@@ -225,6 +243,13 @@ int dibr_backward_meshes(const DibrPass* p, void* stream) {
     m.grad_cam_rot = p->grad_cam_rot; m.grad_cam_pos = p->grad_cam_pos; m.pose_part = w.pose_part;
     g_launches += 2;
     return cuda_fail("dibr_backward_meshes", dibr::launch_backward_meshes(m, (cudaStream_t)stream));
+}
+
+int dibr_normal_map(const float* normals, const float* mask, const uint32_t* min_ordered, float* out, long long npix, void* stream) {
+    if (!normals || !mask || !min_ordered || !out || npix < 0) return fail("normal_map: null argument");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    g_launches += 1;
+    return cuda_fail("dibr_normal_map", dibr::launch_normal_map(normals, mask, min_ordered, out, npix, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -3,10 +3,13 @@
 // The reference (kaolin v0.1 dr_cuda_backward_color_batch / dr_cuda_backward_prob_batch, called at
 // /root/reference/lib/dr_utils/dib_renderer_x/rasterizer/rasterizer.py:249-269) runs one thread per
 // PIXEL and scatters into its face with fp32 atomicAdd (9*D + up to 4*K atomics per pixel, order
-// undefined).  Here the loop is turned inside out: 8 lanes own one FACE, walk the pixel centres
-// inside its bbox (colour part) and expanded bbox (soft part), pick up the pixels that belong to
-// it (imidx == face+1, or uncovered with the face among the first K), accumulate in registers in a
-// fixed order and reduce with a fixed shuffle tree.  Every output element is written exactly once.
+// undefined).  Here the loop is turned inside out: the forward kernel leaves two work lists -- faces
+// that won a pixel, faces that entered a soft-silhouette product -- and a group of lanes owns one
+// listed FACE: it walks the pixel centres inside its bbox (colour part, 8 lanes) or expanded bbox
+// (soft part, one warp), picks up the pixels that belong to it (imidx == face+1, or uncovered with
+// the face among the first K), accumulates in registers in a fixed order and reduces with a fixed
+// shuffle tree.  The order of the work lists is arbitrary but no result depends on it: every face is
+// reduced on its own and written to its own slot, so the gradients are bit-reproducible run to run.
 //
 // Algebra used (see DESIGN.md "Backward"): with acc[i][d] = sum_pix w_i * dL/dI_d (which IS
 // dL/dattr, rasterizer.py:278-291 'dldc'),  A_i = sum_d (c1-c0)_d acc[i][d],
@@ -41,215 +44,233 @@ __device__ __forceinline__ int image_of_face_b(int g, int batch, int faces_per_i
     return lo;
 }
 
-constexpr int GRP = 8;     // lanes per face
+constexpr int GRP = 8;     // lanes per face in the colour kernel
 
+// ---- colour part: one 8-lane group per face that WON at least one pixel (work list written by the forward) ------
 template <int DMAX>
-__global__ void __launch_bounds__(256) backward_faces_kernel(BwdParams P)
+__global__ void __launch_bounds__(256) backward_color_kernel(BwdParams P)
 {
     const int tid = threadIdx.x;
     const int gl = tid & (GRP - 1);
-    const int g = blockIdx.x * (256 / GRP) + (tid / GRP);
-    const bool active = g < P.total_faces;
+    const int gi = blockIdx.x * (256 / GRP) + (tid / GRP);
+    const int nlist = P.list_counts[0];
+    if (blockIdx.x * (256 / GRP) >= nlist) return;          // whole CTA beyond the list
+    const bool active = gi < nlist;
     const int D = P.num_attr;
     const int W = P.width, H = P.height;
     const unsigned full = 0xffffffffu;
-    const unsigned gmask = 0xffu << ((tid & 31) & ~(GRP - 1));
 
     float acc[3 * DMAX];
 #pragma unroll
     for (int i = 0; i < 3 * DMAX; i++) acc[i] = 0.f;
-    float gp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    bool any_c = false, any_p = false;
     FaceRec rec;
-    int b = 0, f = 0;
-    size_t img = 0;
-    const int32_t* __restrict__ idx = P.imidx;
-    int sc0 = 0, sc1 = 0, sr0 = 0, sr1 = 0;          // soft part: pixel range of the expanded bbox
-    bool near_uncovered = false;
-
+    int g = 0;
     if (active) {
+        g = P.color_list[gi];
         rec = P.recs[g];
-        b = image_of_face_b(g, P.batch, P.faces_per_image, P.face_offsets);
-        f = g - (P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image);
-        img = (size_t)b * H * W;
-        idx = P.imidx + img;
+        const int b = image_of_face_b(g, P.batch, P.faces_per_image, P.face_offsets);
+        const int f = g - (P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image);
+        const size_t img = (size_t)b * H * W;
+        const int32_t* __restrict__ idx = P.imidx + img;
         const float sx = (float)W / (float)P.multiplier, sy = (float)H / (float)P.multiplier;
-
-        // ---- colour part: pixels this face won (lane = image row, inner loop over columns) ------------
-        if (P.any_grad_im && rec.nz >= 0.0f) {
-            const int c0 = col_lower(P.xs, W, rec.xmin, sx), c1 = col_lower(P.xs, W, rec.xmax, sx);
-            const int r0 = row_lower(P.ys, H, rec.ymax, sy), r1 = row_lower(P.ys, H, rec.ymin, sy);
-            if (c1 > c0 && r1 > r0) {
-                const FaceK fk = make_facek(rec);
-                for (int r = r0 + gl; r < r1; r += GRP) {
-                    const int32_t* __restrict__ row = idx + (size_t)r * W;
-                    const float y0 = P.ys[r];
-                    for (int c = c0; c < c1; c++) {
-                        if (row[c] != f + 1) continue;
-                        const size_t pix = (size_t)r * W + c;
-                        float w0, w1, w2;
-                        bary(fk, P.xs[c], y0, w0, w1, w2);
-                        any_c = true;
+        const int c0 = col_lower(P.xs, W, rec.xmin, sx), c1 = col_lower(P.xs, W, rec.xmax, sx);
+        const int r0 = row_lower(P.ys, H, rec.ymax, sy), r1 = row_lower(P.ys, H, rec.ymin, sy);
+        const int nc = c1 - c0, npx = nc * (r1 - r0);
+        if (nc > 0 && npx > 0 && P.any_grad_im) {
+            const FaceK fk = make_facek(rec);
+            for (int i = gl; i < npx; i += GRP) {
+                const int rr = i / nc;
+                const int r = r0 + rr, c = c0 + (i - rr * nc);
+                const size_t pix = (size_t)r * W + c;
+                if (idx[pix] != f + 1) continue;
+                float w0, w1, w2;
+                bary(fk, P.xs[c], P.ys[r], w0, w1, w2);
 #pragma unroll
-                        for (int d = 0; d < DMAX; d++) {
-                            if (d < D && P.chan_grad[d]) {
-                                const float gv = __ldg(P.chan_grad[d] + (img + pix) * (size_t)P.chan_stride[d]);
-                                acc[0 * DMAX + d] = fmaf(gv, w0, acc[0 * DMAX + d]);
-                                acc[1 * DMAX + d] = fmaf(gv, w1, acc[1 * DMAX + d]);
-                                acc[2 * DMAX + d] = fmaf(gv, w2, acc[2 * DMAX + d]);
-                            }
-                        }
+                for (int d = 0; d < DMAX; d++) {
+                    if (d < D && P.chan_grad[d]) {
+                        const float gv = __ldg(P.chan_grad[d] + (img + pix) * (size_t)P.chan_stride[d]);
+                        acc[0 * DMAX + d] = fmaf(gv, w0, acc[0 * DMAX + d]);
+                        acc[1 * DMAX + d] = fmaf(gv, w1, acc[1 * DMAX + d]);
+                        acc[2 * DMAX + d] = fmaf(gv, w2, acc[2 * DMAX + d]);
                     }
                 }
             }
         }
-        // ---- soft part, step 1: does the expanded bbox touch an 8x8 block with an uncovered pixel? -----
-        if (P.grad_improb && P.knum > 0) {
-            const float ex = P.expand_mul;
-            sc0 = col_lower(P.xs, W, rec.xmin - ex, sx); sc1 = col_lower(P.xs, W, rec.xmax + ex, sx);
-            sr0 = row_lower(P.ys, H, rec.ymax + ex, sy); sr1 = row_lower(P.ys, H, rec.ymin - ex, sy);
-            if (sc1 > sc0 && sr1 > sr0) {
-                const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
-                const unsigned short* __restrict__ ub = P.unc_blocks + (size_t)b * tiles_x * tiles_y;
-                const int bx0 = sc0 >> 3, bx1 = (sc1 - 1) >> 3, by0 = sr0 >> 3, by1 = (sr1 - 1) >> 3;
-                const int nbx = bx1 - bx0 + 1, nblk = nbx * (by1 - by0 + 1);
-                for (int k = gl; k < nblk && !near_uncovered; k += GRP) {
-                    const int by = by0 + k / nbx, bx = bx0 + k % nbx;
-                    const unsigned m = ub[(by >> 2) * tiles_x + (bx >> 2)];
-                    near_uncovered = (m >> ((by & 3) * 4 + (bx & 3))) & 1u;
-                }
-            }
-        }
     }
-    // the 8 lanes of a face decide together, so whole groups skip the walk (warp-wide vote: every lane gets here)
-    near_uncovered = (__ballot_sync(full, near_uncovered) & gmask) != 0u;
-
-    // ---- soft part, step 2: uncovered pixels that counted this face ------------------------------------------
-    if (active && near_uncovered) {
-        const float mult = (float)P.multiplier;
-        const float zscale = (float)P.delta / (mult * mult);
-        const float sentinel = 4.0f * mult * mult;
-        const float* __restrict__ gpr = P.grad_improb + img;
-        const float* __restrict__ comp = P.imcomp + img;
-        const float px[3] = {rec.ax, rec.bx, rec.cx}, py[3] = {rec.ay, rec.by, rec.cy};
-        for (int r = sr0 + gl; r < sr1; r += GRP) {
-            const int32_t* __restrict__ row = idx + (size_t)r * W;
-            const float y0 = P.ys[r];
-            for (int c = sc0; c < sc1; c++) {
-                const int v = row[c];
-                if (v > 0 || (v < 0 && f + 1 > -v)) continue;      // covered, or beyond the K-th face
-                const size_t pix = (size_t)r * W + c;
-                const float x0 = P.xs[c];
-                const SoftHit h = soft_distance(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, x0, y0, sentinel);
-                float p, om;
-                soft_prob(h.d2 * zscale, p, om);
-                // d improb / d p_k = prod_{j != k}(1 - p_j) = comp / (1 - p_k);  dp/dz = -p;
-                // z = zscale * d2;  gradient w.r.t. UN-multiplied coordinates carries one more 'mult'
-                const float coef = -__ldg(gpr + pix) * __ldg(comp + pix) / (om + 1e-15f) * p * zscale * mult;
-                if (coef == 0.0f) continue;
-                any_p = true;
-                if (h.kase >= 3) {
-                    const int k = h.kase - 3;
-                    const float vx = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
-                    const float vy = (k == 0) ? py[0] : ((k == 1) ? py[1] : py[2]);
-                    const float gx = coef * 2.0f * (vx - x0), gy = coef * 2.0f * (vy - y0);
-                    if (k == 0) { gp[0] += gx; gp[1] += gy; }
-                    else if (k == 1) { gp[2] += gx; gp[3] += gy; }
-                    else { gp[4] += gx; gp[5] += gy; }
-                } else {
-                    const int k = h.kase, k2 = (k + 1) % 3;
-                    const float x1 = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
-                    const float y1 = (k == 0) ? py[0] : ((k == 1) ? py[1] : py[2]);
-                    const float x2 = (k2 == 0) ? px[0] : ((k2 == 1) ? px[1] : px[2]);
-                    const float y2 = (k2 == 0) ? py[0] : ((k2 == 1) ? py[1] : py[2]);
-                    const float exx = x2 - x1, eyy = y2 - y1;
-                    const float s2 = 2.0f * coef / h.len2;
-                    const float gx1 = s2 * ((y0 - y2) * h.cr + h.d2 * exx);
-                    const float gy1 = s2 * (-(x0 - x2) * h.cr + h.d2 * eyy);
-                    const float gx2 = s2 * (-(y0 - y1) * h.cr - h.d2 * exx);
-                    const float gy2 = s2 * ((x0 - x1) * h.cr - h.d2 * eyy);
-                    if (k == 0) { gp[0] += gx1; gp[1] += gy1; gp[2] += gx2; gp[3] += gy2; }
-                    else if (k == 1) { gp[2] += gx1; gp[3] += gy1; gp[4] += gx2; gp[5] += gy2; }
-                    else { gp[4] += gx1; gp[5] += gy1; gp[0] += gx2; gp[1] += gy2; }
-                }
-            }
-        }
-    }
-
-    // ---- fixed-tree reduction over the 8 lanes of the face ------------------------------------------
-    const bool grp_c = (__ballot_sync(full, any_c) & gmask) != 0u;
-    const bool grp_p = (__ballot_sync(full, any_p) & gmask) != 0u;
-    // the shuffles below are warp-wide collectives: every lane of the warp must execute the same
-    // sequence, so the "skip if nothing accumulated" test is made warp-uniform
-    const bool warp_c = __any_sync(full, any_c), warp_p = __any_sync(full, any_p);
-    if (warp_c) {
+    // fixed-tree reduction over the 8 lanes of the face
 #pragma unroll
-        for (int i = 0; i < 3 * DMAX; i++) {
-            float v = acc[i];
-            v += __shfl_xor_sync(full, v, 4);
-            v += __shfl_xor_sync(full, v, 2);
-            v += __shfl_xor_sync(full, v, 1);
-            acc[i] = v;
-        }
-    }
-    if (warp_p) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            float v = gp[i];
-            v += __shfl_xor_sync(full, v, 4);
-            v += __shfl_xor_sync(full, v, 2);
-            v += __shfl_xor_sync(full, v, 1);
-            gp[i] = v;
-        }
+    for (int i = 0; i < 3 * DMAX; i++) {
+        float v = acc[i];
+        v += __shfl_xor_sync(full, v, 4);
+        v += __shfl_xor_sync(full, v, 2);
+        v += __shfl_xor_sync(full, v, 1);
+        acc[i] = v;
     }
     if (!active || gl != 0) return;
-
-    float* __restrict__ gpo = P.grad_points2d + (size_t)g * 6;
-    float* __restrict__ gao = P.grad_face_attr + (size_t)g * 3 * D;
-    float out[6];
+    // dL/dattr is acc itself; dL/dP follows from it (see the header comment)
+    const FaceK fk = make_facek(rec);
+    const float* __restrict__ a = P.face_attr + (size_t)g * 3 * D;
+    float A[3] = {0.f, 0.f, 0.f}, Bv[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 6; i++) out[i] = grp_p ? gp[i] : 0.f;
-    if (grp_c) {
-        const FaceK fk = make_facek(rec);
-        const float* __restrict__ a = P.face_attr + (size_t)g * 3 * D;
-        float A[3] = {0.f, 0.f, 0.f}, Bv[3] = {0.f, 0.f, 0.f};
+    for (int d = 0; d < DMAX; d++) {
+        if (d < D) {
+            const float c0v = a[d], e1 = a[D + d] - c0v, e2 = a[2 * D + d] - c0v;
 #pragma unroll
-        for (int d = 0; d < DMAX; d++) {
-            if (d < D) {
-                const float c0 = a[d], e1 = a[D + d] - c0, e2 = a[2 * D + d] - c0;
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    A[i] = fmaf(e1, acc[i * DMAX + d], A[i]);
-                    Bv[i] = fmaf(e2, acc[i * DMAX + d], Bv[i]);
-                }
+            for (int i = 0; i < 3; i++) {
+                A[i] = fmaf(e1, acc[i * DMAX + d], A[i]);
+                Bv[i] = fmaf(e2, acc[i * DMAX + d], Bv[i]);
             }
         }
-        // multiplier * k3 / (k3^2 + eps): the reference's multiplier * g / (k3*k3 + eps) times the k3 the
-        // un-normalised dw terms carry
-        const float inv = (float)P.multiplier * fk.k3 / (fk.k3 * fk.k3 + 1e-15f);
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            out[2 * i + 0] += inv * (-fk.q * A[i] + fk.p * Bv[i]);
-            out[2 * i + 1] += inv * (fk.n * A[i] - fk.m * Bv[i]);
-        }
     }
+    // multiplier * k3 / (k3^2 + eps): the reference's multiplier * g / (k3*k3 + eps) times the k3 the
+    // un-normalised dw terms carry
+    const float inv = (float)P.multiplier * fk.k3 / (fk.k3 * fk.k3 + 1e-15f);
+    float* __restrict__ gpo = P.grad_points2d + (size_t)g * 6;
+    float* __restrict__ gao = P.grad_face_attr + (size_t)g * 3 * D;
 #pragma unroll
-    for (int i = 0; i < 6; i++) gpo[i] = out[i];
+    for (int i = 0; i < 3; i++) {
+        gpo[2 * i + 0] = inv * (-fk.q * A[i] + fk.p * Bv[i]);
+        gpo[2 * i + 1] = inv * (fk.n * A[i] - fk.m * Bv[i]);
+    }
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int d = 0; d < DMAX; d++)
-            if (d < D) gao[i * D + d] = grp_c ? acc[i * DMAX + d] : 0.f;
+            if (d < D) gao[i * D + d] = acc[i * DMAX + d];
+}
+
+// ---- soft part: one warp per face that entered at least one soft-silhouette product -------------------------------
+// The warp walks the pixel centres of the expanded bbox 32 at a time, keeps (ballot compaction, ascending pixel
+// order) the uncovered pixels that counted this face, and evaluates them 32 at a time with every lane busy.
+constexpr int SOFT_Q = 64;
+__global__ void __launch_bounds__(256) backward_soft_kernel(BwdParams P)
+{
+    __shared__ int queue[8][SOFT_Q];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wi = blockIdx.x * 8 + warp;
+    if (wi >= P.list_counts[1]) return;                      // warp-uniform
+    const unsigned full = 0xffffffffu;
+    const int W = P.width, H = P.height;
+    const int g = P.soft_list[wi];
+    const FaceRec rec = P.recs[g];
+    const int b = image_of_face_b(g, P.batch, P.faces_per_image, P.face_offsets);
+    const int f = g - (P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image);
+    const size_t img = (size_t)b * H * W;
+    const int32_t* __restrict__ idx = P.imidx + img;
+    const float* __restrict__ gpr = P.grad_improb + img;
+    const float* __restrict__ comp = P.imcomp + img;
+    const float sx = (float)W / (float)P.multiplier, sy = (float)H / (float)P.multiplier;
+    const float ex = P.expand_mul;
+    const int c0 = col_lower(P.xs, W, rec.xmin - ex, sx), c1 = col_lower(P.xs, W, rec.xmax + ex, sx);
+    const int r0 = row_lower(P.ys, H, rec.ymax + ex, sy), r1 = row_lower(P.ys, H, rec.ymin - ex, sy);
+    const int nc = c1 - c0, npx = nc * (r1 - r0);
+    if (nc <= 0 || npx <= 0) return;
+    const float mult = (float)P.multiplier;
+    const float zscale = (float)P.delta / (mult * mult);
+    const float sentinel = 4.0f * mult * mult;
+    const float px[3] = {rec.ax, rec.bx, rec.cx}, py[3] = {rec.ay, rec.by, rec.cy};
+    float gp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int* q = queue[warp];
+    int qn = 0;
+
+    auto evaluate = [&](int i) {
+        const int rr = i / nc;
+        const int r = r0 + rr, c = c0 + (i - rr * nc);
+        const size_t pix = (size_t)r * W + c;
+        const float x0 = P.xs[c], y0 = P.ys[r];
+        const SoftHit h = soft_distance(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, x0, y0, sentinel);
+        float p, om;
+        soft_prob(h.d2 * zscale, p, om);
+        // d improb / d p_k = prod_{j != k}(1 - p_j) = comp / (1 - p_k);  dp/dz = -p;  z = zscale * d2;
+        // the gradient w.r.t. UN-multiplied coordinates carries one more 'mult'
+        const float coef = -__ldg(gpr + pix) * __ldg(comp + pix) / (om + 1e-15f) * p * zscale * mult;
+        if (h.kase >= 3) {
+            const int k = h.kase - 3;
+            const float vx = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
+            const float vy = (k == 0) ? py[0] : ((k == 1) ? py[1] : py[2]);
+            const float gx = coef * 2.0f * (vx - x0), gy = coef * 2.0f * (vy - y0);
+            if (k == 0) { gp[0] += gx; gp[1] += gy; }
+            else if (k == 1) { gp[2] += gx; gp[3] += gy; }
+            else { gp[4] += gx; gp[5] += gy; }
+        } else {
+            const int k = h.kase, k2 = (k + 1) % 3;
+            const float x1 = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
+            const float y1 = (k == 0) ? py[0] : ((k == 1) ? py[1] : py[2]);
+            const float x2 = (k2 == 0) ? px[0] : ((k2 == 1) ? px[1] : px[2]);
+            const float y2 = (k2 == 0) ? py[0] : ((k2 == 1) ? py[1] : py[2]);
+            const float exx = x2 - x1, eyy = y2 - y1;
+            const float s2 = 2.0f * coef / h.len2;
+            const float gx1 = s2 * ((y0 - y2) * h.cr + h.d2 * exx);
+            const float gy1 = s2 * (-(x0 - x2) * h.cr + h.d2 * eyy);
+            const float gx2 = s2 * (-(y0 - y1) * h.cr - h.d2 * exx);
+            const float gy2 = s2 * ((x0 - x1) * h.cr - h.d2 * eyy);
+            if (k == 0) { gp[0] += gx1; gp[1] += gy1; gp[2] += gx2; gp[3] += gy2; }
+            else if (k == 1) { gp[2] += gx1; gp[3] += gy1; gp[4] += gx2; gp[5] += gy2; }
+            else { gp[4] += gx1; gp[5] += gy1; gp[0] += gx2; gp[1] += gy2; }
+        }
+    };
+
+    for (int base = 0; base < npx; base += 32) {
+        const int i = base + lane;
+        bool take = false;
+        if (i < npx) {
+            const int rr = i / nc;
+            const int v = idx[(size_t)(r0 + rr) * W + c0 + (i - rr * nc)];
+            take = !(v > 0 || (v < 0 && f + 1 > -v));        // uncovered and this face is within the first K
+        }
+        const unsigned bal = __ballot_sync(full, take);
+        if (take) q[qn + __popc(bal & ((1u << lane) - 1u))] = i;
+        qn += __popc(bal);
+        __syncwarp();
+        if (qn >= 32) {
+            evaluate(q[lane]);
+            __syncwarp();
+            const int rest = qn - 32;
+            const int moved = (lane < rest) ? q[32 + lane] : 0;
+            __syncwarp();
+            if (lane < rest) q[lane] = moved;
+            qn = rest;
+            __syncwarp();
+        }
+    }
+    if (lane < qn) evaluate(q[lane]);
+    // fixed-tree warp reduction, then add to what the colour kernel wrote (stream order makes this race-free)
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        float v = gp[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+        gp[i] = v;
+    }
+    if (lane == 0) {
+        float* __restrict__ gpo = P.grad_points2d + (size_t)g * 6;
+#pragma unroll
+        for (int i = 0; i < 6; i++) gpo[i] += gp[i];
+    }
 }
 
 int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
 {
     if (P.total_faces <= 0) return 0;
-    const int grid = (P.total_faces + (256 / GRP) - 1) / (256 / GRP);
-    if (P.num_attr <= 4) backward_faces_kernel<4><<<grid, 256, 0, stream>>>(P);
-    else if (P.num_attr <= 8) backward_faces_kernel<8><<<grid, 256, 0, stream>>>(P);
-    else backward_faces_kernel<12><<<grid, 256, 0, stream>>>(P);
-    return (int)cudaGetLastError();
+    // faces on neither work list keep a zero gradient
+    cudaError_t e = cudaMemsetAsync(P.grad_points2d, 0, sizeof(float) * 6 * (size_t)P.total_faces, stream);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(P.grad_face_attr, 0, sizeof(float) * 3 * (size_t)P.num_attr * (size_t)P.total_faces, stream);
+    if (e != cudaSuccess) return (int)e;
+    // the list lengths live on the device: launch for the worst case, surplus CTAs exit at once
+    if (P.any_grad_im) {
+        const int grid = (P.total_faces + (256 / GRP) - 1) / (256 / GRP);
+        if (P.num_attr <= 4) backward_color_kernel<4><<<grid, 256, 0, stream>>>(P);
+        else if (P.num_attr <= 8) backward_color_kernel<8><<<grid, 256, 0, stream>>>(P);
+        else backward_color_kernel<12><<<grid, 256, 0, stream>>>(P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (P.grad_improb && P.knum > 0) {
+        backward_soft_kernel<<<(P.total_faces + 7) / 8, 256, 0, stream>>>(P);
+        e = cudaGetLastError();
+    }
+    return (int)e;
 }
 
 // -------------------------------------------------------------------------------------------------

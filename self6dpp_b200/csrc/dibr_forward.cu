@@ -54,8 +54,18 @@ struct FwdSmem {
     int nbig, lcount, next_block, pad0;
     unsigned int sub_uncovered;
     unsigned int unc_blocks;                    // bit (by*4+bx): 8x8 block holds an uncovered pixel
+    unsigned int soft_used[LCAP / 32];          // listed faces that entered some pixel's soft product
     uint64_t bar[2];
 };
+
+// first time a face is seen doing `bit`-type work, append it to the matching list for the backward
+__device__ __forceinline__ void mark_face(const FwdParams& P, int g, unsigned bit) {
+    if ((__ldcg(&P.face_flags[g]) & bit) != 0u) return;
+    const unsigned old = atomicOr(&P.face_flags[g], bit);
+    if (old & bit) return;
+    if (bit == 1u) P.color_list[atomicAdd(&P.list_counts[0], 1)] = g;
+    else P.soft_list[atomicAdd(&P.list_counts[1], 1)] = g;
+}
 
 // first column c in [0,n] with xs[c] >= x (xs ascending, pitch 1/inv_dx): arithmetic guess + exact fix-up
 __device__ __forceinline__ int col_first_ge(const float* xs, int n, float x, float inv_dx) {
@@ -247,12 +257,13 @@ __device__ void raster_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw
 }
 
 // Phase D for one batch of listed faces
-__device__ void soft_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw, int th, int knum,
+__device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRec* __restrict__ recs, int tw, int th, int knum,
                           float zscale, float sentinel, int* __restrict__ imidx_img, int width, int tx0, int ty0)
 {
     const unsigned full_mask = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lcount = s.lcount;
+    if (tid < LCAP / 32) s.soft_used[tid] = 0u;
     // ---- per-sub-tile (16x16) ordered lists: warp w builds sub-tile w -----------------------------------
     if (warp < NSUB) {
         const int st = warp;
@@ -311,6 +322,7 @@ __device__ void soft_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw, 
             for (int k = 0; k < kmax; k++) {
                 if (k < nh) {
                     const int lj = s.u.hits[k][tid];
+                    if (!((s.soft_used[lj >> 5] >> (lj & 31)) & 1u)) atomicOr(&s.soft_used[lj >> 5], 1u << (lj & 31));
                     const float4* rp = reinterpret_cast<const float4*>(recs + s.lid[lj]);
                     const float4 g0 = __ldg(rp), g1 = __ldg(rp + 1);
                     const SoftHit h = soft_distance(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, x0, y0, sentinel);
@@ -361,6 +373,9 @@ __device__ void soft_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw, 
     }
     __syncthreads();
     if (tid == 0) s.next_block = 0;
+    // hand the faces that contributed to the backward's work list
+    for (int li = tid; li < lcount; li += FWD_THREADS)
+        if ((s.soft_used[li >> 5] >> (li & 31)) & 1u) mark_face(P, f_lo + s.lid[li], 2u);
     __syncthreads();
 }
 
@@ -416,6 +431,7 @@ dibr_forward_kernel(FwdParams P)
     unsigned short* __restrict__ unc_out = P.unc_blocks + ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     if (!touched) {          // nothing near this tile: zeros everywhere (imcomp = 1: empty product)
         if (tid == 0) *unc_out = 0xffffu;
+        if (tid == 0 && P.min_group >= 0) atomicMin(P.out_min, f2ord(0.0f));
         for (int g = 0; g < P.n_out; g++) zero_tile(P.out[g] + img_pix * P.out_ch[g], P.width, P.out_ch[g], tx0, ty0, tw, th);
         zero_tile(improb, P.width, 1, tx0, ty0, tw, th);
         zero_tile(reinterpret_cast<float*>(imidx), P.width, 1, tx0, ty0, tw, th);
@@ -462,17 +478,20 @@ dibr_forward_kernel(FwdParams P)
     // ---- phase C: resolve (one image row per warp) ---------------------------------------------------------
     const float* __restrict__ fattr = P.face_attr + (size_t)f_lo * 3 * D;
     bool any_unc = false;
+    float vmin = 3.0e38f;                        // running minimum of output group P.min_group
 #pragma unroll 1
     for (int it = 0; it < (TILE * TILE) / FWD_THREADS; it++) {
         const int ly = it * NWARP + (tid >> 5), lx = tid & 31;
         const bool valid = (lx < tw) && (ly < th);
         bool unc = false;
+        int fwin = -1;
         if (valid) {
             const size_t gp = (size_t)(ty0 + ly) * P.width + (tx0 + lx);
             const unsigned long long key = s.zkey[ly * TILE + lx];
             const size_t px = img_pix + gp;
             if (key != 0ull) {
                 const int f = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+                fwin = f;
                 const FaceRec r = recs[f];
                 const FaceK fk = make_facek(r);
                 float w0, w1, w2;
@@ -492,9 +511,13 @@ dibr_forward_kernel(FwdParams P)
                         v.z = blend(w0, w1, w2, r0.z, r1.z, r2.z);
                         v.w = blend(w0, w1, w2, r0.w, r1.w, r2.w);
                         *reinterpret_cast<float4*>(o) = v;
+                        if (g == P.min_group) vmin = fminf(vmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
                     } else {
-                        for (int c = 0; c < ch; c++)
-                            o[c] = blend(w0, w1, w2, __ldg(a + base + c), __ldg(a + D + base + c), __ldg(a + 2 * D + base + c));
+                        for (int c = 0; c < ch; c++) {
+                            const float v = blend(w0, w1, w2, __ldg(a + base + c), __ldg(a + D + base + c), __ldg(a + 2 * D + base + c));
+                            o[c] = v;
+                            if (g == P.min_group) vmin = fminf(vmin, v);
+                        }
                     }
                     base += ch;
                 }
@@ -511,7 +534,13 @@ dibr_forward_kernel(FwdParams P)
                 }
                 imidx[gp] = 0;                   // may be overwritten with the K-th face in phase D
                 unc = true;
+                vmin = fminf(vmin, 0.0f);
             }
+        }
+        // winners go on the backward's colour work list (run-length de-duplicated along the row)
+        {
+            const int prev = __shfl_up_sync(0xffffffffu, fwin, 1);
+            if (fwin >= 0 && ((tid & 31) == 0 || prev != fwin)) mark_face(P, f_lo + fwin, 1u);
         }
         // which 16x16 sub-tiles still hold uncovered pixels (a warp is one row: lanes 0-15 | 16-31)
         const unsigned bal = __ballot_sync(0xffffffffu, unc);
@@ -533,6 +562,10 @@ dibr_forward_kernel(FwdParams P)
             }
         }
     }
+    if (P.min_group >= 0) {
+        const unsigned ov = __reduce_min_sync(0xffffffffu, f2ord(vmin));
+        if ((tid & 31) == 0 && ov != f2ord(3.0e38f)) atomicMin(P.out_min, ov);
+    }
     const int tile_unc = __syncthreads_or(any_unc ? 1 : 0);
     if (tid == 0) *unc_out = (unsigned short)s.unc_blocks;
 
@@ -541,12 +574,12 @@ dibr_forward_kernel(FwdParams P)
         const float zscale = (float)P.delta / ((float)P.multiplier * (float)P.multiplier);
         const float sentinel = 4.0f * (float)P.multiplier * (float)P.multiplier;
         if (nbatch == 1) {
-            if (s.lcount > 0) soft_list(s, recs, tw, th, P.knum, zscale, sentinel, imidx, P.width, tx0, ty0);
+            if (s.lcount > 0) soft_list(s, P, f_lo, recs, tw, th, P.knum, zscale, sentinel, imidx, P.width, tx0, ty0);
         } else {
             int pos = 0;
             while (pos < fnum) {
                 pos = fill_list(s, bbox, pos, fnum, ex, tx_lo, tx_hi, ty_lo, ty_hi, phase0, phase1);
-                if (s.lcount > 0) soft_list(s, recs, tw, th, P.knum, zscale, sentinel, imidx, P.width, tx0, ty0);
+                if (s.lcount > 0) soft_list(s, P, f_lo, recs, tw, th, P.knum, zscale, sentinel, imidx, P.width, tx0, ty0);
                 // stop early once every uncovered pixel has its K faces
                 bool open = false;
                 for (int i = tid; i < TILE * TILE; i += FWD_THREADS) open |= ((int)s.cnt[i] < P.knum);
@@ -563,6 +596,27 @@ dibr_forward_kernel(FwdParams P)
             imcomp[gp] = s.soft_c[ly * TILE + lx];
         }
     }
+}
+
+// out = (n - min) / (||n - min|| + 1e-5) * mask  (renderer_dibr.py:284-285)
+__global__ void __launch_bounds__(256) normal_map_kernel(const float* __restrict__ n, const float* __restrict__ mask,
+                                                         const unsigned int* __restrict__ min_ordered, float* __restrict__ out, long long npix)
+{
+    const float mn = ord2f(*min_ordered);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        const float a = n[3 * i] - mn, b = n[3 * i + 1] - mn, c = n[3 * i + 2] - mn;
+        const float len = sqrtf(a * a + b * b + c * c) + 1e-5f;
+        const float m = mask[i];
+        out[3 * i] = a / len * m; out[3 * i + 1] = b / len * m; out[3 * i + 2] = c / len * m;
+    }
+}
+
+int launch_normal_map(const float* n, const float* mask, const unsigned int* min_ordered, float* out, long long npix, cudaStream_t stream)
+{
+    if (npix == 0) return 0;
+    const int grid = (int)((npix + 255) / 256 < 148 * 16 ? (npix + 255) / 256 : 148 * 16);
+    normal_map_kernel<<<grid, 256, 0, stream>>>(n, mask, min_ordered, out, npix);
+    return (int)cudaGetLastError();
 }
 
 int launch_forward(const FwdParams& P, cudaStream_t stream)

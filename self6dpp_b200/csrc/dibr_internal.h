@@ -20,6 +20,10 @@ struct Workspace {
     float* cam_rot;     // pose mode: [num_instances, 9]
     float* cam_pos;     // pose mode: [num_instances, 3]
     float* cam_proj;    // pose mode: [num_K, 16]
+    int* list_counts;   // [2] entries in color_list / soft_list (+ padding), zeroed by dibr_forward
+    unsigned int* face_flags;   // [total_faces] bit0: won a pixel, bit1: evaluated for a soft pixel (zeroed by dibr_forward)
+    int* color_list;    // [total_faces] global face ids that won at least one pixel (arbitrary order)
+    int* soft_list;     // [total_faces] global face ids that entered at least one soft-silhouette product
     unsigned short* unc_blocks;  // [batch, tiles_y, tiles_x] bit (by*4+bx): the 8x8 pixel block of the 32x32 tile holds an uncovered pixel
     size_t bytes;
 };
@@ -71,6 +75,12 @@ struct FwdParams {
     float* imcomp;
     int32_t* imidx;
     unsigned short* unc_blocks;
+    int* list_counts;
+    unsigned int* face_flags;
+    int* color_list;
+    int* soft_list;
+    int min_group;             // output group whose batch-global minimum is accumulated, or -1
+    unsigned int* out_min;     // ordered-uint encoding
 };
 
 struct BwdParams {
@@ -86,6 +96,9 @@ struct BwdParams {
     const float* imcomp;
     const int32_t* imidx;
     const unsigned short* unc_blocks;
+    const int* list_counts;
+    const int* color_list;
+    const int* soft_list;
     const float* chan_grad[DIBR_MAX_ATTR_INTERNAL];   // per channel d: upstream gradient base (pre-offset) or null
     int chan_stride[DIBR_MAX_ATTR_INTERNAL];          // floats per pixel of the tensor that holds channel d
     int any_grad_im;
@@ -128,5 +141,6 @@ int launch_setup_meshes(const SetupParams& P, cudaStream_t stream);
 int launch_forward(const FwdParams& P, cudaStream_t stream);
 int launch_backward_faces(const BwdParams& P, cudaStream_t stream);
 int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream);
+int launch_normal_map(const float* n, const float* mask, const unsigned int* min_ordered, float* out, long long npix, cudaStream_t stream);
 
 }  // namespace dibr

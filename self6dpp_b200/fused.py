@@ -142,6 +142,11 @@ class RenderMeshes(Function):
             for g, (c, o) in enumerate(zip(split, outs)):
                 p.out_channels[g] = c
                 p.out[g] = o.data_ptr()
+            if meta.get("min_output") is not None:      # batch-global minimum of one output group (normal maps)
+                out_min = torch.empty(1, dtype=torch.int32, device=device)
+                p.min_output = int(meta["min_output"])
+                p.out_min_ordered = ctypes.c_void_p(out_min.data_ptr())
+                meta["out_min"] = out_min
             lib = _lib.load()
             st = _stream(device)
             _lib.check(lib.dibr_setup_meshes(ctypes.byref(p), st), "dibr_setup_meshes")
@@ -268,6 +273,33 @@ def build_meta(pack, mesh_ids, attr_ids, attr_rows_base, image_ids, height, widt
         meta["inst_vert_rows"] = torch.from_numpy(np.concatenate(vert_rows)).to(device)
         meta["inst_attr_rows"] = torch.from_numpy(np.concatenate(attr_rows)).to(device)
     return meta
+
+
+class NormalMap(Function):
+    """(n - min) / (||n - min|| + 1e-5) * mask with the batch-global min the forward kernel accumulated
+    (renderer_dibr.py:284-285).  Forward: one fused kernel (dibr_normal_map).  Backward (rare: nobody in
+    Self6D++ differentiates the rendered normal map) re-evaluates the torch expression under autograd."""
+
+    @staticmethod
+    def forward(ctx, normals, mask, out_min):
+        n_c, m_c = normals.contiguous(), mask.contiguous()
+        out = torch.empty_like(n_c)
+        with torch.cuda.device(n_c.device):
+            _lib.check(_lib.load().dibr_normal_map(n_c.data_ptr(), m_c.data_ptr(), out_min.data_ptr(), out.data_ptr(),
+                                                   n_c.numel() // 3, _stream(n_c.device)), "dibr_normal_map")
+        ctx.save_for_backward(n_c, m_c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n_c, m_c = ctx.saved_tensors
+        with torch.enable_grad():
+            n = n_c.detach().requires_grad_(True)
+            m = m_c.detach().requires_grad_(True)
+            shift = n - n.min()
+            y = shift / (torch.norm(shift, dim=-1, keepdim=True) + 1e-5) * m
+            gn, gm = torch.autograd.grad(y, [n, m], g)
+        return gn, gm, None
 
 
 def render_meshes(verts_packed, vattr_packed, cam_rot, cam_pos, cam_proj, meta):

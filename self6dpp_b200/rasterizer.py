@@ -48,6 +48,7 @@ def _base_pass(batch, height, width, num_attr, knum, multiplier, delta, expand, 
     p.num_attr, p.knum = int(num_attr), int(knum)
     p.multiplier, p.delta, p.expand = int(multiplier), int(delta), float(expand)
     p.total_faces, p.faces_per_image = int(total_faces), int(faces_per_image)
+    p.min_output = -1
     return p
 
 

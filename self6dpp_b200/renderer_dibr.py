@@ -125,7 +125,8 @@ class Renderer_dibr(object):
         self.dib_ren = DIBRenderer(height, width, mode)
         self._registry = _ModelRegistry()
 
-    def _render_batch_fast(self, Rs, ts, models, Ks, width, height, znear, zfar, rot_type, names, split, flags):
+    def _render_batch_fast(self, Rs, ts, models, Ks, width, height, znear, zfar, rot_type, names, split, flags,
+                           min_output=None):
         """pose-mode fast path: resident models, R/t/K handed straight to the kernels (no camera torch ops)."""
         reg = self._registry
         slots = reg.slots(models)
@@ -170,7 +171,7 @@ class Renderer_dibr(object):
                     knum=fused.DEFAULT_KNUM, multiplier=fused.DEFAULT_MULTIPLIER, delta=fused.DEFAULT_DELTA,
                     expand=fused.DEFAULT_EXPAND, want_normals=False, num_attr_rows=int(reg.verts.shape[0]),
                     out_split=split, inst_desc=dev[:B * fused.INST_STRIDE], face_offsets=dev[B * fused.INST_STRIDE:],
-                    pose_mode=True, znear=float(znear), zfar=float(zfar))
+                    pose_mode=True, znear=float(znear), zfar=float(zfar), min_output=min_output)
         res = fused.render_meshes(reg.verts, vattr, R, ts.reshape(B, 3), K, meta)
         return list(res[:-2]), res[-2], meta
 
@@ -202,7 +203,9 @@ class Renderer_dibr(object):
             flags |= fused.FLAG_DEPTH
             keys.append("depth")
             split.append(1)
-        fast = self._render_batch_fast(Rs, ts, models, Ks, width, height, znear, zfar, rot_type, names, split, flags)
+        min_output = keys.index("norm") if "norm" in keys else None
+        fast = self._render_batch_fast(Rs, ts, models, Ks, width, height, znear, zfar, rot_type, names, split, flags,
+                                       min_output=min_output)
         if fast is not None:
             outs, improb, meta = fast
             # the reference sets the camera as a side effect (renderer_dibr.py:261); keep that, lazily
@@ -221,8 +224,11 @@ class Renderer_dibr(object):
             ret["mask"] = im_mask.squeeze(-1)
         if "norm" in mode:
             _ren_norms = out["norm"]
-            ren_norms_shift = _ren_norms - _ren_norms.min()          # batch-global shift, renderer_dibr.py:284
-            ret["norm"] = ren_norms_shift / (torch.norm(ren_norms_shift, dim=-1, keepdim=True) + 1e-5) * im_mask
+            if meta.get("out_min") is not None:                      # one fused kernel, min came with the rasterisation
+                ret["norm"] = fused.NormalMap.apply(_ren_norms, im_mask, meta["out_min"])
+            else:
+                ren_norms_shift = _ren_norms - _ren_norms.min()      # batch-global shift, renderer_dibr.py:284
+                ret["norm"] = ren_norms_shift / (torch.norm(ren_norms_shift, dim=-1, keepdim=True) + 1e-5) * im_mask
         if "depth" in mode:
             ret["depth"] = out["depth"].squeeze(-1)                  # z of R v + t, renderer_dibr.py:296-301
         if "xyz" in mode:
