@@ -146,6 +146,7 @@ typedef struct DibrPass {
 int dibr_abi_version(void);
 /* sizeof(DibrPass) as compiled, so a binding can verify its struct mirror */
 int dibr_sizeof_pass(void);
+int dibr_sizeof_step(void);
 const char *dibr_last_error(void);
 
 /* number of CUDA devices visible to the library (0 when there is no driver/GPU) */
@@ -165,6 +166,35 @@ int dibr_backward_meshes(const DibrPass *pass, void *stream);
  * min = the batch-global minimum accumulated by dibr_forward into min_ordered. */
 int dibr_normal_map(const float *normals_nx3, const float *mask_n, const uint32_t *min_ordered, float *out_nx3,
                     long long num_pixels, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * One render-and-compare step of Self6D++'s compute_self_loss_pose (core/self6dpp/engine/self_engine_utils.py:426-447)
+ * from HOST buffers, enqueued with a single call:
+ *   1. one H2D copy of the packed per-step inputs (poses, intrinsics, instance table) from pinned host memory,
+ *   2. student pass  : dibr_setup_meshes + dibr_forward (+ dibr_normal_map when student_normal_* are set),
+ *   3. teacher pass  : the same for the pseudo-label pose (skipped when teacher.num_instances == 0),
+ *   4. backward      : dibr_backward_faces + dibr_backward_meshes of the student pass with the caller's upstream
+ *                      gradients (student.grad_out[] / grad_improb), skipped when run_backward == 0,
+ *   5. one D2H copy of dL/dR, dL/dt (num_instances x 12 floats) into pinned host memory.
+ * Both passes are ordinary pose-mode DibrPass structs whose DEVICE pointers for pose_R / pose_t / pose_K /
+ * inst_desc / face_offsets point INTO `staging_device`, laid out exactly like `staging_host`.
+ * Nothing is synchronised: the caller waits on the stream before reading host_grad_pose. */
+typedef struct DibrStep {
+    DibrPass student;
+    DibrPass teacher;
+    const void *staging_host;      /* pinned */
+    void *staging_device;
+    size_t staging_bytes;
+    /* optional normal-map post-processing (renderer_dibr.py:281-286); inputs are output groups of the pass */
+    const float *student_normal_in, *student_mask_in; float *student_normal_out;
+    const float *teacher_normal_in, *teacher_mask_in; float *teacher_normal_out;
+    int32_t run_backward;
+    int32_t reserved;
+    float *host_grad_pose;         /* pinned [num_instances, 12]: 9 of dL/dR then 3 of dL/dt per instance, or NULL */
+    float *device_grad_pose;       /* [num_instances, 12] scratch the D2H copy reads from */
+} DibrStep;
+
+int dibr_render_step(const DibrStep *step, void *stream);
 
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);

@@ -44,9 +44,22 @@ class DibrPass(ctypes.Structure):
     ]
 
 
+class DibrStep(ctypes.Structure):
+    """Mirror of ``struct DibrStep`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("student", DibrPass), ("teacher", DibrPass),
+        ("staging_host", ctypes.c_void_p), ("staging_device", ctypes.c_void_p), ("staging_bytes", ctypes.c_size_t),
+        ("student_normal_in", _c_f32p), ("student_mask_in", _c_f32p), ("student_normal_out", _c_f32p),
+        ("teacher_normal_in", _c_f32p), ("teacher_mask_in", _c_f32p), ("teacher_normal_out", _c_f32p),
+        ("run_backward", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("host_grad_pose", _c_f32p), ("device_grad_pose", _c_f32p),
+    ]
+
+
 EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_device_count", "dibr_workspace_bytes",
            "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
-           "dibr_backward_meshes", "dibr_normal_map", "dibr_launch_count"]
+           "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_launch_count"]
 
 _lib = None
 
@@ -83,6 +96,10 @@ def load():
     lib.dibr_normal_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_longlong, ctypes.c_void_p]
     lib.dibr_normal_map.restype = ctypes.c_int
+    lib.dibr_render_step.argtypes = [ctypes.POINTER(DibrStep), ctypes.c_void_p]
+    lib.dibr_render_step.restype = ctypes.c_int
+    if lib.dibr_sizeof_step() != ctypes.sizeof(DibrStep):
+        raise RuntimeError("DibrStep mirror out of date")
     if lib.dibr_abi_version() != 1:
         raise RuntimeError("libdibr_b200.so ABI version mismatch")
     if lib.dibr_sizeof_pass() != ctypes.sizeof(DibrPass):

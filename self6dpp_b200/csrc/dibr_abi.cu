@@ -109,6 +109,8 @@ int dibr_abi_version(void) { return DIBR_ABI_VERSION; }
 
 int dibr_sizeof_pass(void) { return (int)sizeof(DibrPass); }
 
+int dibr_sizeof_step(void) { return (int)sizeof(DibrStep); }
+
 const char* dibr_last_error(void) { return g_err; }
 
 int dibr_device_count(void) {
@@ -250,6 +252,54 @@ int dibr_normal_map(const float* normals, const float* mask, const uint32_t* min
     if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
     g_launches += 1;
     return cuda_fail("dibr_normal_map", dibr::launch_normal_map(normals, mask, min_ordered, out, npix, (cudaStream_t)stream));
+}
+
+// gather [n,9] + [n,3] into [n,12] so ONE D2H copy returns the pose gradients
+__global__ void pack_pose_grad_kernel(const float* __restrict__ gR, const float* __restrict__ gt, float* __restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 12) return;
+    const int inst = i / 12, k = i % 12;
+    out[i] = (k < 9) ? gR[inst * 9 + k] : gt[inst * 3 + (k - 9)];
+}
+
+int dibr_render_step(const DibrStep* st, void* stream) {
+    if (!st) return fail("null DibrStep");
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (st->staging_bytes > 0) {
+        if (!st->staging_host || !st->staging_device) return fail("render_step: staging buffers are null");
+        cudaError_t e = cudaMemcpyAsync(st->staging_device, st->staging_host, st->staging_bytes, cudaMemcpyHostToDevice, cs);
+        if (e != cudaSuccess) return cuda_fail("render_step H2D", (int)e);
+    }
+    const DibrPass* passes[2] = {&st->student, &st->teacher};
+    const float* nin[2] = {st->student_normal_in, st->teacher_normal_in};
+    const float* nmask[2] = {st->student_mask_in, st->teacher_mask_in};
+    float* nout[2] = {st->student_normal_out, st->teacher_normal_out};
+    for (int k = 0; k < 2; k++) {
+        const DibrPass* p = passes[k];
+        if (p->num_instances <= 0) continue;
+        if (int e = dibr_setup_meshes(p, stream)) return e;
+        if (int e = dibr_forward(p, stream)) return e;
+        if (nin[k]) {
+            if (!p->out_min_ordered || p->min_output < 0) return fail("render_step: normal map needs min_output/out_min_ordered");
+            if (int e = dibr_normal_map(nin[k], nmask[k], p->out_min_ordered, nout[k], (long long)p->batch * p->height * p->width, stream)) return e;
+        }
+    }
+    if (st->run_backward) {
+        const DibrPass* p = &st->student;
+        if (int e = dibr_backward_faces(p, stream)) return e;
+        if (int e = dibr_backward_meshes(p, stream)) return e;
+        if (st->host_grad_pose) {
+            if (!st->device_grad_pose || !p->grad_pose_R || !p->grad_pose_t) return fail("render_step: pose-gradient buffers are null");
+            const int n = p->num_instances;
+            pack_pose_grad_kernel<<<(n * 12 + 127) / 128, 128, 0, cs>>>(p->grad_pose_R, p->grad_pose_t, st->device_grad_pose, n);
+            g_launches += 1;
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)n, cudaMemcpyDeviceToHost, cs);
+            if (e != cudaSuccess) return cuda_fail("render_step D2H", (int)e);
+        }
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -54,17 +54,22 @@ struct FwdSmem {
     int nbig, lcount, next_block, pad0;
     unsigned int sub_uncovered;
     unsigned int unc_blocks;                    // bit (by*4+bx): 8x8 block holds an uncovered pixel
-    unsigned int soft_used[LCAP / 32];          // listed faces that entered some pixel's soft product
+    unsigned char soft_used[LCAP];              // listed faces that entered some pixel's soft product
     uint64_t bar[2];
 };
 
-// first time a face is seen doing `bit`-type work, append it to the matching list for the backward
-__device__ __forceinline__ void mark_face(const FwdParams& P, int g, unsigned bit) {
-    if ((__ldcg(&P.face_flags[g]) & bit) != 0u) return;
-    const unsigned old = atomicOr(&P.face_flags[g], bit);
-    if (old & bit) return;
-    if (bit == 1u) P.color_list[atomicAdd(&P.list_counts[0], 1)] = g;
-    else P.soft_list[atomicAdd(&P.list_counts[1], 1)] = g;
+// The first time a face is seen doing `bit`-type work (1: won a pixel, 2: entered a soft product) it is appended
+// to the matching work list of the backward.  Warp-aggregated: one counter atomic per warp, every lane must call.
+__device__ __forceinline__ void mark_faces_warp(const FwdParams& P, bool want, int g, unsigned bit) {
+    bool isnew = false;
+    if (want && (__ldcg(&P.face_flags[g]) & bit) == 0u) isnew = (atomicOr(&P.face_flags[g], bit) & bit) == 0u;
+    const unsigned bal = __ballot_sync(0xffffffffu, isnew);
+    if (bal == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&P.list_counts[bit == 1u ? 0 : 1], __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (isnew) (bit == 1u ? P.color_list : P.soft_list)[base + __popc(bal & ((1u << lane) - 1u))] = g;
 }
 
 // first column c in [0,n] with xs[c] >= x (xs ascending, pitch 1/inv_dx): arithmetic guess + exact fix-up
@@ -263,7 +268,7 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
     const unsigned full_mask = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lcount = s.lcount;
-    if (tid < LCAP / 32) s.soft_used[tid] = 0u;
+    for (int i = tid; i < LCAP / 4; i += FWD_THREADS) reinterpret_cast<unsigned int*>(s.soft_used)[i] = 0u;
     // ---- per-sub-tile (16x16) ordered lists: warp w builds sub-tile w -----------------------------------
     if (warp < NSUB) {
         const int st = warp;
@@ -322,7 +327,7 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
             for (int k = 0; k < kmax; k++) {
                 if (k < nh) {
                     const int lj = s.u.hits[k][tid];
-                    if (!((s.soft_used[lj >> 5] >> (lj & 31)) & 1u)) atomicOr(&s.soft_used[lj >> 5], 1u << (lj & 31));
+                    s.soft_used[lj] = 1;           // benign race: everybody writes 1
                     const float4* rp = reinterpret_cast<const float4*>(recs + s.lid[lj]);
                     const float4 g0 = __ldg(rp), g1 = __ldg(rp + 1);
                     const SoftHit h = soft_distance(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, x0, y0, sentinel);
@@ -374,8 +379,11 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
     __syncthreads();
     if (tid == 0) s.next_block = 0;
     // hand the faces that contributed to the backward's work list
-    for (int li = tid; li < lcount; li += FWD_THREADS)
-        if ((s.soft_used[li >> 5] >> (li & 31)) & 1u) mark_face(P, f_lo + s.lid[li], 2u);
+    for (int li0 = 0; li0 < lcount; li0 += FWD_THREADS) {
+        const int li = li0 + tid;
+        const bool used = (li < lcount) && s.soft_used[li];
+        mark_faces_warp(P, used, used ? f_lo + s.lid[li] : 0, 2u);
+    }
     __syncthreads();
 }
 
@@ -540,7 +548,8 @@ dibr_forward_kernel(FwdParams P)
         // winners go on the backward's colour work list (run-length de-duplicated along the row)
         {
             const int prev = __shfl_up_sync(0xffffffffu, fwin, 1);
-            if (fwin >= 0 && ((tid & 31) == 0 || prev != fwin)) mark_face(P, f_lo + fwin, 1u);
+            const bool lead = fwin >= 0 && ((tid & 31) == 0 || prev != fwin);
+            mark_faces_warp(P, lead, f_lo + max(fwin, 0), 1u);
         }
         // which 16x16 sub-tiles still hold uncovered pixels (a warp is one row: lanes 0-15 | 16-31)
         const unsigned bal = __ballot_sync(0xffffffffu, unc);

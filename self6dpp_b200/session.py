@@ -1,0 +1,227 @@
+"""``RenderSession`` -- the render-and-compare step of Self6D++'s ``compute_self_loss_pose``
+(/root/reference/core/self6dpp/engine/self_engine_utils.py:426-447) behind ONE C-ABI call
+(``dibr_render_step``, include/dibr_b200.h) that takes HOST buffers.
+
+``Renderer_dibr.render_batch`` is the drop-in for the reference's Python API; it pays ~0.4 ms of
+Python / torch.autograd bookkeeping per call, which is more than the kernels need.  A session
+pre-allocates every device buffer once (resident meshes, workspaces, outputs, gradient buffers, a
+pinned staging block) and per step only (1) writes poses / intrinsics / the instance table into
+pinned memory with numpy, (2) makes one ctypes call.  The call enqueues: one H2D copy, student
+rasterisation (colour + normal + mask + depth + soft mask in ONE pass), teacher rasterisation
+(normal map), the deterministic backward to dL/dR, dL/dt, one D2H copy.
+
+Outputs are persistent device tensors (overwritten by the next step); the pose gradients arrive in
+pinned host memory after ``session.synchronize()``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, fused
+from .renderer_dibr import _ModelRegistry
+
+_MODE_ATTR = (("color", "colors"), ("norm", "normals"), ("xyz", "vertices"))
+
+
+class _PassBuffers(object):
+    def __init__(self, reg, mode, batch, height, width, max_faces, device, znear, zfar):
+        self.names = [a for k, a in _MODE_ATTR if k in mode]
+        self.keys = [k for k, a in _MODE_ATTR if k in mode] + ["ones"] + (["depth"] if "depth" in mode else [])
+        self.split = [3] * len(self.names) + [1] + ([1] if "depth" in mode else [])
+        self.flags = fused.FLAG_ONES | (fused.FLAG_DEPTH if "depth" in mode else 0)
+        self.A = 3 * len(self.names)
+        self.D = sum(self.split)
+        self.vattr = reg.attr_matrix(self.names) if self.names else torch.zeros(0, 1, dtype=torch.float32, device=device)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.outs = [torch.empty(batch, height, width, c, **f32) for c in self.split]
+        self.out = dict(zip(self.keys, self.outs))
+        self.improb = torch.empty(batch, height, width, 1, **f32)
+        self.imcomp = torch.empty(batch, height, width, **f32)
+        self.imidx = torch.empty(batch, height, width, dtype=torch.int32, device=device)
+        self.face_attr = torch.empty(max_faces, 3, self.D, **f32)
+        self.out_min = torch.empty(1, dtype=torch.int32, device=device)
+        self.normal_map = torch.empty(batch, height, width, 3, **f32) if "norm" in mode else None
+        p = _lib.DibrPass()
+        p.batch, p.height, p.width = batch, height, width
+        p.num_attr, p.knum = self.D, fused.DEFAULT_KNUM
+        p.multiplier, p.delta, p.expand = fused.DEFAULT_MULTIPLIER, fused.DEFAULT_DELTA, fused.DEFAULT_EXPAND
+        p.total_faces, p.faces_per_image = max_faces, 0
+        p.num_instances, p.num_K = batch, batch
+        p.znear, p.zfar = znear, zfar
+        nbytes = _lib.workspace_bytes(p)                      # worst case: every sample renders the largest mesh
+        self.ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=device)
+        p.workspace, p.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        p.verts, p.mesh_faces = reg.verts.data_ptr(), reg.pack.faces.data_ptr()
+        p.vert_attr = self.vattr.data_ptr() if self.A else None
+        p.vert_attr_dim, p.attr_flags = self.A, self.flags
+        p.face_attr = self.face_attr.data_ptr()
+        p.improb, p.imidx, p.imcomp = self.improb.data_ptr(), self.imidx.data_ptr(), self.imcomp.data_ptr()
+        p.num_outputs = len(self.split)
+        for g, (c, o) in enumerate(zip(self.split, self.outs)):
+            p.out_channels[g] = c
+            p.out[g] = o.data_ptr()
+        if "norm" in mode:
+            p.min_output = self.keys.index("norm")
+            p.out_min_ordered = self.out_min.data_ptr()
+        else:
+            p.min_output = -1
+        p.vert_face_ptr, p.vert_face_idx = reg.pack.vert_face_ptr.data_ptr(), reg.pack.vert_face_idx.data_ptr()
+        self.p = p
+
+
+class RenderSession(object):
+    def __init__(self, models, batch, height, width, student_mode=("color", "depth", "mask", "norm", "prob"),
+                 teacher_mode=("norm",), device="cuda:0", znear=0.01, zfar=100.0):
+        self.device = torch.device(device)
+        self.B, self.H, self.W = int(batch), int(height), int(width)
+        self.lib = _lib.load()
+        reg = _ModelRegistry()
+        slots = reg.slots(models)
+        if slots is None:
+            raise RuntimeError("RenderSession needs resident models that do not require grad")
+        self.reg = reg
+        self.model_slot = {id(m): int(s) for m, s in zip(models, slots)}
+        B = self.B
+        max_faces = B * int(reg.table[:, 3].max())
+        with torch.cuda.device(self.device):
+            self.student = _PassBuffers(reg, student_mode, B, self.H, self.W, max_faces, self.device, znear, zfar)
+            self.teacher = _PassBuffers(reg, teacher_mode, B, self.H, self.W, max_faces, self.device, znear, zfar) \
+                if teacher_mode else None
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self.g_p2d = torch.empty(max_faces, 6, **f32)
+            self.g_fattr = torch.empty(max_faces, 3, self.student.D, **f32)
+            self.g_pose_R = torch.empty(B, 9, **f32)
+            self.g_pose_t = torch.empty(B, 3, **f32)
+            self.g_pose_dev = torch.empty(B, 12, **f32)
+            self.g_pose_host = torch.empty(B, 12, dtype=torch.float32, pin_memory=True)
+            # staging block, 4-byte words: sR[9B] st[3B] K[9B] tR[9B] tt[3B] desc[12B] face_off[B+1]
+            self.off = {}
+            o = 0
+            for name, n in (("sR", 9 * B), ("st", 3 * B), ("K", 9 * B), ("tR", 9 * B), ("tt", 3 * B),
+                            ("desc", fused.INST_STRIDE * B), ("foff", B + 1)):
+                o = (o + 3) // 4 * 4                             # 16-byte aligned sections
+                self.off[name] = (o, n)
+                o += n
+            self.stage_words = o
+            self.stage_host = torch.empty(o, dtype=torch.int32, pin_memory=True)
+            self.stage_dev = torch.empty(o, dtype=torch.int32, device=self.device)
+        self._h_i32 = self.stage_host.numpy()
+        self._h_f32 = self._h_i32.view(np.float32)
+        st = _lib.DibrStep()
+        base = self.stage_dev.data_ptr()
+        for name, pb in (("student", self.student), ("teacher", self.teacher)):
+            if pb is None:
+                continue
+            p = pb.p
+            p.pose_R = base + 4 * self.off["sR" if name == "student" else "tR"][0]
+            p.pose_t = base + 4 * self.off["st" if name == "student" else "tt"][0]
+            p.pose_K = base + 4 * self.off["K"][0]
+            p.inst_desc = base + 4 * self.off["desc"][0]
+            p.face_offsets = base + 4 * self.off["foff"][0]
+        sp = self.student.p
+        sp.grad_points2d, sp.grad_face_attr = self.g_p2d.data_ptr(), self.g_fattr.data_ptr()
+        sp.grad_pose_R, sp.grad_pose_t = self.g_pose_R.data_ptr(), self.g_pose_t.data_ptr()
+        st.student = sp
+        if self.teacher is not None:
+            st.teacher = self.teacher.p
+        st.staging_host, st.staging_device = self.stage_host.data_ptr(), base
+        st.staging_bytes = 4 * self.stage_words
+        if self.student.normal_map is not None:
+            st.student_normal_in = self.student.out["norm"].data_ptr()
+            st.student_mask_in = self.student.out["ones"].data_ptr()
+            st.student_normal_out = self.student.normal_map.data_ptr()
+        if self.teacher is not None and self.teacher.normal_map is not None:
+            st.teacher_normal_in = self.teacher.out["norm"].data_ptr()
+            st.teacher_mask_in = self.teacher.out["ones"].data_ptr()
+            st.teacher_normal_out = self.teacher.normal_map.data_ptr()
+        st.host_grad_pose, st.device_grad_pose = self.g_pose_host.data_ptr(), self.g_pose_dev.data_ptr()
+        self.st = st
+        self._ar = np.arange(B)
+        self._keep = None
+
+    # ------------------------------------------------------------------------------------------
+    def _fill(self, name, arr):
+        o, n = self.off[name]
+        self._h_f32[o:o + n] = np.asarray(arr, dtype=np.float32).reshape(-1)
+
+    def step(self, Rs, ts, Ks, models, teacher_Rs=None, teacher_ts=None, grad_color=None, grad_prob=None,
+             grad_depth=None, backward=True, upload=True, download=True):
+        """Rs [B,3,3], ts [B,3], Ks [B,3,3] (+ teacher pose): HOST arrays.  grad_*: DEVICE tensors (dL/dcolor
+        [B,H,W,3], dL/dprob [B,H,W], dL/ddepth [B,H,W]) or None.  Returns the dict of persistent output tensors;
+        call ``synchronize()`` before reading ``grad_pose`` (pinned [B,12]: dL/dR then dL/dt)."""
+        B = self.B
+        assert len(models) == B
+        slots = np.fromiter((self.model_slot[id(m)] for m in models), dtype=np.int64, count=B)
+        tab = self.reg.table[slots]
+        nf, nv = tab[:, 3], tab[:, 1]
+        self._fill("sR", Rs)
+        self._fill("st", ts)
+        K = np.asarray(Ks, dtype=np.float32)
+        self._fill("K", np.broadcast_to(K.reshape(-1, 3, 3), (B, 3, 3)))
+        if self.teacher is not None:
+            self._fill("tR", teacher_Rs)
+            self._fill("tt", teacher_ts)
+        o, n = self.off["desc"]
+        desc = self._h_i32[o:o + n].reshape(B, fused.INST_STRIDE)
+        cf = np.cumsum(nf)
+        desc[:, 0], desc[:, 1], desc[:, 2], desc[:, 3], desc[:, 4] = tab[:, 0], nv, tab[:, 2], nf, cf - nf
+        desc[:, 5] = self._ar
+        desc[:, 6] = self._ar
+        desc[:, 7] = tab[:, 0]
+        desc[:, 8] = np.cumsum(nv) - nv
+        desc[:, 9] = self._ar
+        desc[:, 10] = tab[:, 0]
+        desc[:, 11] = 0
+        o, n = self.off["foff"]
+        self._h_i32[o] = 0
+        self._h_i32[o + 1:o + n] = cf
+        total = int(cf[-1])
+        st = self.st
+        st.student.total_faces = total
+        st.teacher.total_faces = total
+        sp = st.student
+        keep = []
+        grads = {"color": grad_color, "depth": grad_depth}
+        for g, key in enumerate(self.student.keys):
+            t = grads.get(key)
+            if t is not None:
+                t = t.contiguous()
+                keep.append(t)
+                sp.grad_out[g] = t.data_ptr()
+            else:
+                sp.grad_out[g] = None
+        if grad_prob is not None:
+            gp = grad_prob.contiguous()
+            keep.append(gp)
+            sp.grad_improb = gp.data_ptr()
+        else:
+            sp.grad_improb = None
+        self._keep = keep
+        st.run_backward = 1 if backward else 0
+        st.staging_bytes = 4 * self.stage_words if upload else 0       # upload=False: inputs already resident
+        st.host_grad_pose = self.g_pose_host.data_ptr() if download else None
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.dibr_render_step(ctypes.byref(st), stream), "dibr_render_step")
+        return self.outputs()
+
+    def outputs(self):
+        s = self.student
+        ret = {"prob": s.improb.squeeze(-1), "mask": s.out["ones"].squeeze(-1)}
+        if "color" in s.out:
+            ret["color"] = s.out["color"]
+        if "depth" in s.out:
+            ret["depth"] = s.out["depth"].squeeze(-1)
+        if s.normal_map is not None:
+            ret["norm"] = s.normal_map
+        if self.teacher is not None and self.teacher.normal_map is not None:
+            ret["teacher_norm"] = self.teacher.normal_map
+        return ret
+
+    @property
+    def grad_pose(self):
+        return self.g_pose_host
+
+    def synchronize(self):
+        torch.cuda.current_stream(self.device).synchronize()
