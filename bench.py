@@ -233,11 +233,11 @@ def main_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from self6dpp_b200 import dist_utils as du
+
     def allreduce_check(gR, gt):
-        if world > 1:      # cfg5: loss vector + 12-float pose-gradient checksum, NCCL over NVLink
-            vec = torch.cat([gR.sum(0).reshape(9), gt.sum(0)])
-            dist.all_reduce(vec)
-            return vec
+        if world > 1:      # cfg5: 12-float pose-gradient check-sum, one NCCL all-reduce over NVLink per step
+            return du.allreduce_sum(du.pose_grad_checksum(gR, gt))
         return None
 
     def timed(fn, steps, warmup, with_collective):

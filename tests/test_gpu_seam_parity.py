@@ -110,3 +110,46 @@ def test_cpu_tensor_raises():
     from self6dpp_b200 import rasterizer as Rz
     with pytest.raises(RuntimeError):
         Rz.linear_rasterizer(8, 8, torch.zeros(1, 1, 9), torch.zeros(1, 1, 6), torch.zeros(1, 1, 1), torch.zeros(1, 1, 12))
+
+
+def test_dense_mesh_multi_batch_lists():
+    """20k faces on a 64x64 image: > 1024 faces per 32x32 tile, so the tile lists are processed in several batches
+    (forward re-scans for the soft pass) and the K cap is active almost everywhere near the silhouette."""
+    from self6dpp_b200 import synth
+    mesh = synth.icosphere(5, radius=0.05, noise_sigma=0.002, seed=3)        # 20480 faces
+    R, _ = synth.random_rotations(2, 17)
+    ts = np.array([[0.0, 0.0, 0.6], [0.01, -0.01, 0.7]], np.float32)
+    K = synth.crop_K(synth.K_LM, (325.26, 242.05), 150.0, 64)
+    p3, p2, nz, at = Hh.seam_inputs([mesh, mesh], R, ts, np.stack([K, K]), 64, 64)
+    out = run_case(p3, p2, nz, at, 64, 64, seed=11)
+    print(out)
+
+
+def test_large_faces_many_per_tile():
+    """80 overlapping large triangles: every face exceeds the 4-lane budget and goes through the CTA-cooperative
+    path, more of them than the deferred list holds (overflow rescan)."""
+    H = W = 64
+    g = torch.Generator().manual_seed(5)
+    n = 80
+    c = torch.rand(n, 1, 2, generator=g) * 1.2 - 0.6
+    d = (torch.rand(n, 3, 2, generator=g) - 0.5) * 1.4
+    p2 = (c + d).reshape(1, n, 6).contiguous()
+    p3 = torch.zeros(1, n, 9)
+    p3[0, :, 2::3] = -(torch.rand(n, 1, generator=g) + 0.5)
+    e1 = p2[0, :, 2:4] - p2[0, :, 0:2]
+    e2 = p2[0, :, 4:6] - p2[0, :, 0:2]
+    nz = (e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]).reshape(1, n, 1).contiguous()
+    at = torch.rand(1, n, 12, generator=g)
+    print(run_case(p3, p2, nz, at, H, W, seed=12, min_same=0.99))
+
+
+@pytest.mark.parametrize("hw", [(480, 640)])
+def test_cfg1_full_size_forward(hw):
+    """cfg1 at the reference's full 480x640 (renderer_base.py:7-8): forward only against the fp32 oracle
+    (face ids + interpolated attributes bit-exact), soft mask vs float64."""
+    from self6dpp_b200 import synth
+    H, W = hw
+    mesh = synth.icosphere(4, radius=0.05, noise_sigma=0.005, seed=0)
+    R, _ = synth.random_rotations(1, 0)
+    p3, p2, nz, at = Hh.seam_inputs([mesh], R, np.array([[0, 0, 0.8]], np.float32), synth.K_LM[None], H, W)
+    print(run_case(p3, p2, nz, at, H, W, seed=13, check_grad=False))
