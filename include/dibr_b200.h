@@ -191,7 +191,8 @@ typedef struct DibrStep {
     int32_t run_backward;
     int32_t reserved;
     float *host_grad_pose;         /* pinned [num_instances, 12]: 9 of dL/dR then 3 of dL/dt per instance, or NULL */
-    float *device_grad_pose;       /* [num_instances, 12] scratch the D2H copy reads from */
+    float *device_grad_pose;       /* [num_instances, 12] packed dL/dR | dL/dt on the device (always written when non-NULL);
+                                      the D2H copy reads from it */
 } DibrStep;
 
 int dibr_render_step(const DibrStep *step, void *stream);

@@ -289,14 +289,15 @@ int dibr_render_step(const DibrStep* st, void* stream) {
         const DibrPass* p = &st->student;
         if (int e = dibr_backward_faces(p, stream)) return e;
         if (int e = dibr_backward_meshes(p, stream)) return e;
-        if (st->host_grad_pose) {
-            if (!st->device_grad_pose || !p->grad_pose_R || !p->grad_pose_t) return fail("render_step: pose-gradient buffers are null");
+        if (st->device_grad_pose) {
+            if (!p->grad_pose_R || !p->grad_pose_t) return fail("render_step: pose-gradient buffers are null");
             const int n = p->num_instances;
             pack_pose_grad_kernel<<<(n * 12 + 127) / 128, 128, 0, cs>>>(p->grad_pose_R, p->grad_pose_t, st->device_grad_pose, n);
             g_launches += 1;
             cudaError_t e = cudaGetLastError();
-            if (e == cudaSuccess) e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)n, cudaMemcpyDeviceToHost, cs);
-            if (e != cudaSuccess) return cuda_fail("render_step D2H", (int)e);
+            if (e == cudaSuccess && st->host_grad_pose)
+                e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)n, cudaMemcpyDeviceToHost, cs);
+            if (e != cudaSuccess) return cuda_fail("render_step pose gradients", (int)e);
         }
     }
     return 0;

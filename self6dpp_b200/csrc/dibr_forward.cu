@@ -315,27 +315,56 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
         const bool whole = (sn > SUBCAP);
         const int n = whole ? lcount : sn;
         const float x0 = valid ? s.xs[lx] : 0.f, y0 = valid ? s.ys[ly] : 0.f;
-        const float x_lo = s.xs[bx], x_hi = s.xs[min(bx + BW, tw) - 1];
-        const float y_hi = s.ys[by], y_lo = s.ys[min(by + BH, th) - 1];
+        // pre-filter rectangle = bounding box of the block's OPEN pixels (they only ever close, so it stays valid)
+        const unsigned colmask = __reduce_or_sync(full_mask, open ? (1u << (lane & 7)) : 0u);
+        const unsigned rowmask = __reduce_or_sync(full_mask, open ? (1u << (lane >> 3)) : 0u);
+        const float x_lo = s.xs[bx + __ffs(colmask) - 1], x_hi = s.xs[bx + 31 - __clz(colmask)];
+        const float y_hi = s.ys[by + __ffs(rowmask) - 1], y_lo = s.ys[by + 31 - __clz(rowmask)];
         const bool had = open;
         float q = had ? s.soft_q[pix] : 0.f, cc = had ? s.soft_c[pix] : 1.f;
         int nh = 0;                                // collected, not yet evaluated
 
-        // (2) evaluate the collected faces: every lane works on its own k-th face
+        // (2) evaluate the collected (pixel, face) pairs.  Lanes hold very different numbers of hits, so the pairs
+        // of three k-levels at a time are flattened (warp scan) and dealt out evenly: every lane evaluates one
+        // pair per pass; then each pixel folds ITS results in ascending face order.  Scratch lives in the z-buffer
+        // (dead after phase C): 1 KB per warp.
+        float2* const res = reinterpret_cast<float2*>(s.zkey) + warp * 128;                    // 96 used
+        unsigned short* const prs = reinterpret_cast<unsigned short*>(res + 96);                // 96 used
         auto flush_hits = [&]() {
+            __syncwarp();                          // the hit lists were written by other lanes
             const int kmax = __reduce_max_sync(full_mask, nh);
-            for (int k = 0; k < kmax; k++) {
-                if (k < nh) {
-                    const int lj = s.u.hits[k][tid];
+            for (int k0 = 0; k0 < kmax; k0 += 3) {
+                const int cnt = min(max(nh - k0, 0), 3);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(full_mask, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int excl = incl - cnt;
+                const int T = __shfl_sync(full_mask, incl, 31);
+                for (int i = 0; i < cnt; i++) prs[excl + i] = (unsigned short)((lane << 8) | (k0 + i));
+                __syncwarp();
+                for (int j = lane; j < T; j += 32) {
+                    const int pk = prs[j];
+                    const int l = pk >> 8, k = pk & 255;
+                    const int lj = s.u.hits[k][warp * 32 + l];
                     s.soft_used[lj] = 1;           // benign race: everybody writes 1
                     const float4* rp = reinterpret_cast<const float4*>(recs + s.lid[lj]);
                     const float4 g0 = __ldg(rp), g1 = __ldg(rp + 1);
-                    const SoftHit h = soft_distance(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, x0, y0, sentinel);
+                    const SoftHit h = soft_distance(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y,
+                                                    s.xs[bx + (l & 7)], s.ys[by + (l >> 3)], sentinel);
                     float p, om;
                     soft_prob(h.d2 * zscale, p, om);
-                    q = fmaf(p, cc, q);            // 1 - prod(1-p), accurate for small p
-                    cc = cc * om;                  // prod(1-p), accurate for p near 1
+                    res[j] = make_float2(p, om);
                 }
+                __syncwarp();
+                for (int i = 0; i < cnt; i++) {
+                    const float2 r = res[excl + i];
+                    q = fmaf(r.x, cc, q);          // 1 - prod(1-p), accurate for small p
+                    cc = cc * r.y;                 // prod(1-p), accurate for p near 1
+                }
+                __syncwarp();
             }
             nh = 0;
         };
@@ -387,21 +416,19 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
     __syncthreads();
 }
 
-// zero-fill rows [0,th) x [0,tw) of one [H,W,ch] image tile; 128-bit stores when the rows are 16 B aligned
+// zero-fill rows [0,th) x [0,tw) of one [H,W,ch] image tile: a warp per row, 128-bit stores when the rows are 16 B aligned
 __device__ __forceinline__ void zero_tile(float* __restrict__ img, int width, int ch, int tx0, int ty0, int tw, int th)
 {
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rowf = tw * ch;
-    if ((((size_t)width * ch) & 3) == 0 && ((tx0 * ch) & 3) == 0 && (rowf & 3) == 0 && ((reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
-        const int rv = rowf >> 2;
-        for (int i = tid; i < rv * th; i += FWD_THREADS) {
-            const int r = i / rv, c = i - r * rv;
-            reinterpret_cast<float4*>(img + ((size_t)(ty0 + r) * width + tx0) * ch)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    } else {
-        for (int i = tid; i < rowf * th; i += FWD_THREADS) {
-            const int r = i / rowf, c = i - r * rowf;
-            img[((size_t)(ty0 + r) * width + tx0) * ch + c] = 0.f;
+    const bool vec = (((size_t)width * ch) & 3) == 0 && ((tx0 * ch) & 3) == 0 && (rowf & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+    for (int r = warp; r < th; r += NWARP) {
+        float* row = img + ((size_t)(ty0 + r) * width + tx0) * ch;
+        if (vec) {
+            for (int c = lane; c < (rowf >> 2); c += 32) reinterpret_cast<float4*>(row)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int c = lane; c < rowf; c += 32) row[c] = 0.f;
         }
     }
 }
@@ -443,10 +470,8 @@ dibr_forward_kernel(FwdParams P)
         for (int g = 0; g < P.n_out; g++) zero_tile(P.out[g] + img_pix * P.out_ch[g], P.width, P.out_ch[g], tx0, ty0, tw, th);
         zero_tile(improb, P.width, 1, tx0, ty0, tw, th);
         zero_tile(reinterpret_cast<float*>(imidx), P.width, 1, tx0, ty0, tw, th);
-        for (int i = tid; i < tw * th; i += FWD_THREADS) {
-            const int r = i / tw, c = i - r * tw;
-            imcomp[(size_t)(ty0 + r) * P.width + tx0 + c] = 1.0f;
-        }
+        for (int r = tid >> 5; r < th; r += NWARP)
+            for (int c = tid & 31; c < tw; c += 32) imcomp[(size_t)(ty0 + r) * P.width + tx0 + c] = 1.0f;
         return;
     }
 
