@@ -51,6 +51,7 @@ struct FwdSmem {
     int big[BIGCAP];
     float xs[TILE], ys[TILE];
     int warp_tot[NWARP];
+    alignas(16) unsigned short warp_cnt16[NWARP];   // per-warp hit counts of one scan chunk, read back as two 64-bit words
     int nbig, lcount, next_block, pad0;
     unsigned int sub_uncovered;
     unsigned int unc_blocks;                    // bit (by*4+bx): 8x8 block holds an uncovered pixel
@@ -121,15 +122,17 @@ __device__ int fill_list(FwdSmem& s, const float4* __restrict__ bbox, int pos, i
             hit = (bb.x <= tx_hi) && (bb.z > tx_lo) && (bb.y <= ty_hi) && (bb.w > ty_lo);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s.warp_tot[warp] = __popc(bal);
+        if (lane == 0) s.warp_cnt16[warp] = (unsigned short)__popc(bal);
         __syncthreads();
-        int base = lcount, tot = 0;
-#pragma unroll
-        for (int w = 0; w < NWARP; w++) {
-            const int c = s.warp_tot[w];
-            if (w < warp) base += c;
-            tot += c;
-        }
+        // the 8 per-warp counts sit in two 64-bit words (16-bit fields): prefix and total by field-wise multiply
+        const unsigned long long lo = reinterpret_cast<const unsigned long long*>(s.warp_cnt16)[0];
+        const unsigned long long hi = reinterpret_cast<const unsigned long long*>(s.warp_cnt16)[1];
+        constexpr unsigned long long ONES = 0x0001000100010001ull;
+        const int sum_lo = (int)((lo * ONES) >> 48), sum_hi = (int)((hi * ONES) >> 48);
+        const int w4 = warp & 3;
+        const unsigned long long part = (warp < 4 ? lo : hi) & ((1ull << (16 * w4)) - 1ull);
+        const int base = lcount + (warp < 4 ? 0 : sum_lo) + (int)((part * ONES) >> 48);
+        const int tot = sum_lo + sum_hi;
         const bool fits = (lcount + tot <= LCAP);
         if (fits && hit) {
             const int slot = base + __popc(bal & ((1u << lane) - 1u));
@@ -416,24 +419,43 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
     __syncthreads();
 }
 
-// zero-fill rows [0,th) x [0,tw) of one [H,W,ch] image tile: a warp per row, 128-bit stores when the rows are 16 B aligned
-__device__ __forceinline__ void zero_tile(float* __restrict__ img, int width, int ch, int tx0, int ty0, int tw, int th)
+// zero-fill a full 32x32 tile of one [H,W,CH] image with 128-bit stores: CH stores per thread, no divisions at run time
+template <int CH>
+__device__ __forceinline__ void zero_full_tile(float* __restrict__ img, int width, int tx0, int ty0)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rowf = tw * ch;
-    const bool vec = (((size_t)width * ch) & 3) == 0 && ((tx0 * ch) & 3) == 0 && (rowf & 3) == 0 &&
-                     ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
-    for (int r = warp; r < th; r += NWARP) {
-        float* row = img + ((size_t)(ty0 + r) * width + tx0) * ch;
-        if (vec) {
-            for (int c = lane; c < (rowf >> 2); c += 32) reinterpret_cast<float4*>(row)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            for (int c = lane; c < rowf; c += 32) row[c] = 0.f;
-        }
+    constexpr int RV = TILE * CH / 4;                    // float4 per tile row
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+        const int i = k * FWD_THREADS + threadIdx.x;
+        const int r = i / RV, c = i - r * RV;
+        reinterpret_cast<float4*>(img + ((size_t)(ty0 + r) * width + tx0) * CH)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
-__global__ void __launch_bounds__(FWD_THREADS, 4)
+// zero-fill rows [0,th) x [0,tw) of one [H,W,ch] image tile
+__device__ __forceinline__ void zero_tile(float* __restrict__ img, int width, int ch, int tx0, int ty0, int tw, int th)
+{
+    const bool aligned = (((size_t)width * ch) & 3) == 0 && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+    if (tw == TILE && th == TILE && aligned && ch <= 4) {          // tx0 is a multiple of 32: rows start 16 B aligned
+        switch (ch) {
+            case 1: zero_full_tile<1>(img, width, tx0, ty0); return;
+            case 2: zero_full_tile<2>(img, width, tx0, ty0); return;
+            case 3: zero_full_tile<3>(img, width, tx0, ty0); return;
+            default: zero_full_tile<4>(img, width, tx0, ty0); return;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rowf = tw * ch;
+    for (int r = warp; r < th; r += NWARP) {
+        float* row = img + ((size_t)(ty0 + r) * width + tx0) * ch;
+        for (int c = lane; c < rowf; c += 32) row[c] = 0.f;
+    }
+}
+
+#ifndef DIBR_FWD_MIN_CTAS
+#define DIBR_FWD_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(FWD_THREADS, DIBR_FWD_MIN_CTAS)
 dibr_forward_kernel(FwdParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
