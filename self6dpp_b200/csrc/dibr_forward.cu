@@ -26,6 +26,13 @@
 
 namespace dibr {
 
+#ifdef DIBR_PHASE_TIMING
+__device__ unsigned long long g_phase[8];
+#define PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase[k], (unsigned long long)(t_ - t_phase)); t_phase = t_; } } while (0)
+#else
+#define PHASE_MARK(k) do { } while (0)
+#endif
+
 constexpr int NWARP = FWD_THREADS / 32;
 constexpr int HITCAP = 24;              // collected faces per pixel per round of phase D
 constexpr int BW = 8, BH = 4;           // pixel block of one warp in phase D
@@ -43,20 +50,19 @@ struct FwdSmem {
         } ab;
         unsigned short hits[HITCAP][FWD_THREADS];   //    per-lane collected list entries (phase D)
     } u;
-    float soft_q[TILE * TILE];                  //  4 KB  1 - prod(1-p)
-    float soft_c[TILE * TILE];                  //  4 KB  prod(1-p)
+    float4 aux[2 * SCAN_CHUNK];                 //  8 KB  phase A: TMA stages 2,3 (first pass); phase D: per-warp scratch
     unsigned short sublist[NSUB][SUBCAP];       //  4 KB
     unsigned char cnt[TILE * TILE];             //  1 KB  accepted faces per pixel (255 = covered)
     int subcnt[NSUB];
     int big[BIGCAP];
     float xs[TILE], ys[TILE];
-    int warp_tot[NWARP];
-    alignas(16) unsigned short warp_cnt16[NWARP];   // per-warp hit counts of one scan chunk, read back as two 64-bit words
+    int warp_tot[2 * NWARP];
+    alignas(16) unsigned short warp_cnt16[2][NWARP];   // per-warp hit counts of one scan chunk, read back as two 64-bit words
     int nbig, lcount, next_block, pad0;
     unsigned int sub_uncovered;
     unsigned int unc_blocks;                    // bit (by*4+bx): 8x8 block holds an uncovered pixel
     unsigned char soft_used[LCAP];              // listed faces that entered some pixel's soft product
-    uint64_t bar[2];
+    uint64_t bar[4];
 };
 
 // The first time a face is seen doing `bit`-type work (1: won a pixel, 2: entered a soft product) it is appended
@@ -90,43 +96,50 @@ __device__ __forceinline__ int row_first_lt(const float* ys, int n, float y, flo
 
 // Phase A: append to the list, in ascending order, the faces in [pos, fnum) whose expanded bbox
 // touches the tile, until the list is full.  Returns the next unread face.  Uniform across the CTA.
+// The bbox array is streamed through a ring of `nst` TMA stages (256 faces = 4 KB each): a bulk copy takes
+// ~1 us to land, so several must be in flight for the scan not to be latency-bound.
+__device__ __forceinline__ float4* stage_ptr(FwdSmem& s, int k) {
+    return (k < 2) ? &s.u.ab.stage[k][0] : &s.aux[(k - 2) * SCAN_CHUNK];
+}
+
 __device__ int fill_list(FwdSmem& s, const float4* __restrict__ bbox, int pos, int fnum, float ex,
-                         float tx_lo, float tx_hi, float ty_lo, float ty_hi, uint32_t& phase0, uint32_t& phase1)
+                         float tx_lo, float tx_hi, float ty_lo, float ty_hi, uint32_t& phases, int nst)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int lcount = 0;
-    if (tid == 0 && pos < fnum) {
-        const int nf = min(SCAN_CHUNK, fnum - pos);
-        mbar_arrive_expect_tx(&s.bar[0], nf * 16);
-        tma_load_1d(&s.u.ab.stage[0][0], bbox + pos, nf * 16, &s.bar[0]);
+    // prologue: fill the ring
+    if (tid == 0) {
+        for (int k = 0; k < nst; k++) {
+            const int p0 = pos + k * SCAN_CHUNK;
+            if (p0 < fnum) {
+                const int nf = min(SCAN_CHUNK, fnum - p0);
+                mbar_arrive_expect_tx(&s.bar[k], nf * 16);
+                tma_load_1d(stage_ptr(s, k), bbox + p0, nf * 16, &s.bar[k]);
+            }
+        }
     }
-    int buf = 0;
+    int buf = 0, par = 0;
+    bool stopped = false;
     while (pos < fnum) {
         const int nf = min(SCAN_CHUNK, fnum - pos);
         const int npos = pos + nf;
-        if (tid == 0 && npos < fnum) {                  // prefetch the following chunk
-            const int nf2 = min(SCAN_CHUNK, fnum - npos);
-            mbar_arrive_expect_tx(&s.bar[buf ^ 1], nf2 * 16);
-            tma_load_1d(&s.u.ab.stage[buf ^ 1][0], bbox + npos, nf2 * 16, &s.bar[buf ^ 1]);
-        }
-        uint32_t& ph = buf ? phase1 : phase0;
-        mbar_wait(&s.bar[buf], ph);
-        ph ^= 1;
+        mbar_wait(&s.bar[buf], (phases >> buf) & 1u);
+        phases ^= (1u << buf);
 
         bool hit = false;
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid < nf) {
-            bb = s.u.ab.stage[buf][tid];
+            bb = stage_ptr(s, buf)[tid];
             bb.x -= ex; bb.y -= ex; bb.z += ex; bb.w += ex;        // rasterizer.py:55-57
             // some pixel centre of the tile passes xmin <= x0 < xmax and ymin <= y0 < ymax
             hit = (bb.x <= tx_hi) && (bb.z > tx_lo) && (bb.y <= ty_hi) && (bb.w > ty_lo);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s.warp_cnt16[warp] = (unsigned short)__popc(bal);
-        __syncthreads();
+        if (lane == 0) s.warp_cnt16[par][warp] = (unsigned short)__popc(bal);
+        __syncthreads();            // counts visible; everybody has read stage[buf]  (the only barrier per chunk)
         // the 8 per-warp counts sit in two 64-bit words (16-bit fields): prefix and total by field-wise multiply
-        const unsigned long long lo = reinterpret_cast<const unsigned long long*>(s.warp_cnt16)[0];
-        const unsigned long long hi = reinterpret_cast<const unsigned long long*>(s.warp_cnt16)[1];
+        const unsigned long long lo = reinterpret_cast<const unsigned long long*>(s.warp_cnt16[par])[0];
+        const unsigned long long hi = reinterpret_cast<const unsigned long long*>(s.warp_cnt16[par])[1];
         constexpr unsigned long long ONES = 0x0001000100010001ull;
         const int sum_lo = (int)((lo * ONES) >> 48), sum_hi = (int)((hi * ONES) >> 48);
         const int w4 = warp & 3;
@@ -139,20 +152,30 @@ __device__ int fill_list(FwdSmem& s, const float4* __restrict__ bbox, int pos, i
             s.lbox[slot] = bb;
             s.lid[slot] = pos + tid;
         }
-        __syncthreads();            // stage[buf] and warp_tot are free again
-        if (!fits) {
-            // leave this chunk for the next batch; drain the prefetch so the phases stay in step
-            if (npos < fnum) {
-                uint32_t& ph2 = (buf ^ 1) ? phase1 : phase0;
-                mbar_wait(&s.bar[buf ^ 1], ph2);
-                ph2 ^= 1;
-            }
-            __syncthreads();
-            break;
+        if (!fits) { stopped = true; break; }
+        // refill this stage with the chunk nst ahead (everybody is past reading it: see the barrier above)
+        const int p2 = pos + nst * SCAN_CHUNK;
+        if (tid == 0 && p2 < fnum) {
+            const int nf2 = min(SCAN_CHUNK, fnum - p2);
+            mbar_arrive_expect_tx(&s.bar[buf], nf2 * 16);
+            tma_load_1d(stage_ptr(s, buf), bbox + p2, nf2 * 16, &s.bar[buf]);
         }
         lcount += tot;
         pos = npos;
-        buf ^= 1;
+        buf = (buf + 1 == nst) ? 0 : buf + 1;
+        par ^= 1;                   // the counts are double buffered: a writer of parity p has passed the barrier of
+                                    // the previous chunk, which every reader of the older parity-p counts reached after reading
+    }
+    if (stopped) {
+        // the chunk at `pos` stays for the next batch.  Drain every copy still in flight so the barrier phases
+        // stay in step: stages buf+1 .. buf+nst-1 hold chunks pos+SCAN_CHUNK .. (the one at `buf` was consumed).
+        for (int k = 1; k < nst; k++) {
+            const int b2 = (buf + k) % nst;
+            if (pos + k * SCAN_CHUNK < fnum) {
+                mbar_wait(&s.bar[b2], (phases >> b2) & 1u);
+                phases ^= (1u << b2);
+            }
+        }
     }
     if (tid == 0) s.lcount = lcount;
     __syncthreads();
@@ -189,38 +212,49 @@ __device__ void raster_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lcount = s.lcount;
-    // ---- B1: front faces with a non-empty pixel range -> rlist (packed: list index | c0 | nc-1 | r0 | nr-1)
+    // ---- B1: front faces with a non-empty pixel range -> rlist (packed: list index | c0 | nc-1 | r0 | nr-1).
+    //      Two entries per thread per round, their record loads issued together (the records come from L2).
     int rcount = 0;
-    for (int i0 = 0; i0 < lcount; i0 += FWD_THREADS) {
-        const int i = i0 + tid;
-        unsigned int packed = 0;
-        bool keep = false;
-        if (i < lcount) {
-            const float4* rp = reinterpret_cast<const float4*>(recs + s.lid[i]);
-            const float4 t2 = __ldg(rp + 2);                       // cz, nz, -, -
-            if (t2.y >= 0.0f) {                                     // front face (K1 culls normalz < 0)
-                const float4 bb = __ldg(rp + 3);                   // xmin, ymin, xmax, ymax
-                const int c0 = col_first_ge(s.xs, tw, bb.x, inv_dx), c1 = col_first_ge(s.xs, tw, bb.z, inv_dx);
-                const int r0 = row_first_lt(s.ys, th, bb.w, inv_dy), r1 = row_first_lt(s.ys, th, bb.y, inv_dy);
+    for (int i0 = 0; i0 < lcount; i0 += 2 * FWD_THREADS) {
+        float4 t2[2], bb[2];
+        int idx[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            idx[u] = i0 + u * FWD_THREADS + tid;
+            if (idx[u] < lcount) {
+                const float4* rp = reinterpret_cast<const float4*>(recs + s.lid[idx[u]]);
+                t2[u] = __ldg(rp + 2);                              // cz, nz, -, -
+                bb[u] = __ldg(rp + 3);                              // xmin, ymin, xmax, ymax
+            }
+        }
+        unsigned int packed[2] = {0u, 0u};
+        bool keep[2] = {false, false};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (idx[u] < lcount && t2[u].y >= 0.0f) {               // front face (K1 culls normalz < 0)
+                const int c0 = col_first_ge(s.xs, tw, bb[u].x, inv_dx), c1 = col_first_ge(s.xs, tw, bb[u].z, inv_dx);
+                const int r0 = row_first_lt(s.ys, th, bb[u].w, inv_dy), r1 = row_first_lt(s.ys, th, bb[u].y, inv_dy);
                 if (c1 > c0 && r1 > r0) {
-                    keep = true;
-                    packed = (unsigned)i | ((unsigned)c0 << 10) | ((unsigned)(c1 - c0 - 1) << 15) |
-                             ((unsigned)r0 << 20) | ((unsigned)(r1 - r0 - 1) << 25);
+                    keep[u] = true;
+                    packed[u] = (unsigned)idx[u] | ((unsigned)c0 << 10) | ((unsigned)(c1 - c0 - 1) << 15) |
+                                ((unsigned)r0 << 20) | ((unsigned)(r1 - r0 - 1) << 25);
                 }
             }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) s.warp_tot[warp] = __popc(bal);
+        const unsigned bal0 = __ballot_sync(0xffffffffu, keep[0]), bal1 = __ballot_sync(0xffffffffu, keep[1]);
+        if (lane == 0) { s.warp_tot[warp] = __popc(bal0); s.warp_tot[NWARP + warp] = __popc(bal1); }
         __syncthreads();
-        int base = rcount, tot = 0;
+        int base0 = rcount, tot0 = 0, base1 = 0, tot1 = 0;
 #pragma unroll
         for (int w = 0; w < NWARP; w++) {
-            const int c = s.warp_tot[w];
-            if (w < warp) base += c;
-            tot += c;
+            const int a = s.warp_tot[w], c = s.warp_tot[NWARP + w];
+            if (w < warp) { base0 += a; base1 += c; }
+            tot0 += a; tot1 += c;
         }
-        if (keep) s.u.ab.rlist[base + __popc(bal & ((1u << lane) - 1u))] = packed;
-        rcount += tot;
+        base1 += rcount + tot0;
+        if (keep[0]) s.u.ab.rlist[base0 + __popc(bal0 & ((1u << lane) - 1u))] = packed[0];
+        if (keep[1]) s.u.ab.rlist[base1 + __popc(bal1 & ((1u << lane) - 1u))] = packed[1];
+        rcount += tot0 + tot1;
         __syncthreads();
     }
     // ---- B2: 4 lanes per face; faces with many pixels in the tile are deferred to the whole CTA
@@ -266,7 +300,8 @@ __device__ void raster_list(FwdSmem& s, const FaceRec* __restrict__ recs, int tw
 
 // Phase D for one batch of listed faces
 __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRec* __restrict__ recs, int tw, int th, int knum,
-                          float zscale, float sentinel, int* __restrict__ imidx_img, int width, int tx0, int ty0)
+                          float zscale, float sentinel, int* __restrict__ imidx_img, float* __restrict__ improb_img,
+                          float* __restrict__ imcomp_img, int width, int tx0, int ty0, bool first_batch)
 {
     const unsigned full_mask = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -324,20 +359,22 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
         const float x_lo = s.xs[bx + __ffs(colmask) - 1], x_hi = s.xs[bx + 31 - __clz(colmask)];
         const float y_hi = s.ys[by + __ffs(rowmask) - 1], y_lo = s.ys[by + 31 - __clz(rowmask)];
         const bool had = open;
-        float q = had ? s.soft_q[pix] : 0.f, cc = had ? s.soft_c[pix] : 1.f;
+        const size_t gpix = (size_t)(ty0 + ly) * width + (tx0 + lx);
+        // running 1 - prod(1-p) and prod(1-p): start of the product, or what earlier list batches left in the images
+        float q = (had && !first_batch) ? improb_img[gpix] : 0.f, cc = (had && !first_batch) ? imcomp_img[gpix] : 1.f;
         int nh = 0;                                // collected, not yet evaluated
 
         // (2) evaluate the collected (pixel, face) pairs.  Lanes hold very different numbers of hits, so the pairs
-        // of three k-levels at a time are flattened (warp scan) and dealt out evenly: every lane evaluates one
+        // of four k-levels at a time are flattened (warp scan) and dealt out evenly: every lane evaluates one
         // pair per pass; then each pixel folds ITS results in ascending face order.  Scratch lives in the z-buffer
-        // (dead after phase C): 1 KB per warp.
-        float2* const res = reinterpret_cast<float2*>(s.zkey) + warp * 128;                    // 96 used
-        unsigned short* const prs = reinterpret_cast<unsigned short*>(res + 96);                // 96 used
+        // (dead after phase C) and in aux.
+        float2* const res = reinterpret_cast<float2*>(s.zkey) + warp * 128;                    // 1 KB of the dead z-buffer
+        unsigned short* const prs = reinterpret_cast<unsigned short*>(s.aux) + warp * 128;      // 256 B of aux
         auto flush_hits = [&]() {
             __syncwarp();                          // the hit lists were written by other lanes
             const int kmax = __reduce_max_sync(full_mask, nh);
-            for (int k0 = 0; k0 < kmax; k0 += 3) {
-                const int cnt = min(max(nh - k0, 0), 3);
+            for (int k0 = 0; k0 < kmax; k0 += 4) {
+                const int cnt = min(max(nh - k0, 0), 4);
                 int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -398,7 +435,7 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
                     c++;
                     if (c >= knum) {               // the K-th accepted face closes the pixel
                         open = false;
-                        imidx_img[(size_t)(ty0 + ly) * width + (tx0 + lx)] = -(s.lid[lj] + 1);
+                        imidx_img[gpix] = -(s.lid[lj] + 1);
                     }
                 }
                 if (careful && __any_sync(full_mask, nh >= HITCAP)) flush_hits();
@@ -406,7 +443,7 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
             if (!__any_sync(full_mask, open)) break;
         }
         flush_hits();
-        if (had) { s.soft_q[pix] = q; s.soft_c[pix] = cc; s.cnt[pix] = (unsigned char)c; }
+        if (had) { improb_img[gpix] = q; imcomp_img[gpix] = cc; s.cnt[pix] = (unsigned char)c; }
     }
     __syncthreads();
     if (tid == 0) s.next_block = 0;
@@ -497,6 +534,10 @@ dibr_forward_kernel(FwdParams P)
         return;
     }
 
+#ifdef DIBR_PHASE_TIMING
+    long long t_phase = clock64();
+    if (tid == 0) atomicAdd(&g_phase[7], 1ull);
+#endif
     // ---- tile set-up ----------------------------------------------------------------------------
     if (tid < TILE) {
         s.xs[tid] = (tid < tw) ? pix_x(tx0 + tid, P.width, P.multiplier) : 3.0e38f;
@@ -507,25 +548,30 @@ dibr_forward_kernel(FwdParams P)
     if (tid == 0) {
         mbar_init(&s.bar[0], 1);
         mbar_init(&s.bar[1], 1);
+        mbar_init(&s.bar[2], 1);
+        mbar_init(&s.bar[3], 1);
         mbar_fence_init();
         s.nbig = 0; s.next_block = 0; s.lcount = 0; s.sub_uncovered = 0u; s.unc_blocks = 0u;
     }
     for (int i = tid; i < TILE * TILE; i += FWD_THREADS) {
-        s.zkey[i] = 0ull; s.soft_q[i] = 0.f; s.soft_c[i] = 1.f; s.cnt[i] = 0;
+        s.zkey[i] = 0ull; s.cnt[i] = 0;
     }
     __syncthreads();
     const float tx_lo = s.xs[0], tx_hi = s.xs[tw - 1];
     const float ty_hi = s.ys[0], ty_lo = s.ys[th - 1];
     const float inv_dx = 0.5f * (float)P.width / (float)P.multiplier;     // pixel pitch is 2m/W
     const float inv_dy = 0.5f * (float)P.height / (float)P.multiplier;
-    uint32_t phase0 = 0, phase1 = 0;
+    uint32_t phases = 0;          // one parity bit per TMA stage barrier
 
     int nbatch = 0;
     {
         int pos = 0;
+        PHASE_MARK(0);
         while (pos < fnum) {
-            pos = fill_list(s, bbox, pos, fnum, ex, tx_lo, tx_hi, ty_lo, ty_hi, phase0, phase1);
+            pos = fill_list(s, bbox, pos, fnum, ex, tx_lo, tx_hi, ty_lo, ty_hi, phases, 4);
+            PHASE_MARK(1);
             if (s.lcount > 0) raster_list(s, recs, tw, th, inv_dx, inv_dy);
+            PHASE_MARK(2);
             nbatch++;
         }
     }
@@ -534,87 +580,128 @@ dibr_forward_kernel(FwdParams P)
     const float* __restrict__ fattr = P.face_attr + (size_t)f_lo * 3 * D;
     bool any_unc = false;
     float vmin = 3.0e38f;                        // running minimum of output group P.min_group
+    // two image rows per pass: the winners' 2-D corners (32 B of the record) for both pixels are requested before
+    // either is used, then the face-flag words of both winners -- every one of these comes from L2
 #pragma unroll 1
-    for (int it = 0; it < (TILE * TILE) / FWD_THREADS; it++) {
-        const int ly = it * NWARP + (tid >> 5), lx = tid & 31;
-        const bool valid = (lx < tw) && (ly < th);
-        bool unc = false;
-        int fwin = -1;
-        if (valid) {
-            const size_t gp = (size_t)(ty0 + ly) * P.width + (tx0 + lx);
-            const unsigned long long key = s.zkey[ly * TILE + lx];
-            const size_t px = img_pix + gp;
-            if (key != 0ull) {
-                const int f = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
-                fwin = f;
-                const FaceRec r = recs[f];
-                const FaceK fk = make_facek(r);
-                float w0, w1, w2;
-                bary(fk, s.xs[lx], s.ys[ly], w0, w1, w2);
-                const float* a = fattr + (size_t)f * 3 * D;
-                int base = 0;
-                for (int g = 0; g < P.n_out; g++) {
-                    const int ch = P.out_ch[g];
-                    float* o = P.out[g] + px * ch;
-                    if (ch == 4 && ((D | base) & 3) == 0) {
-                        const float4 r0 = __ldg(reinterpret_cast<const float4*>(a + base));
-                        const float4 r1 = __ldg(reinterpret_cast<const float4*>(a + D + base));
-                        const float4 r2 = __ldg(reinterpret_cast<const float4*>(a + 2 * D + base));
-                        float4 v;
-                        v.x = blend(w0, w1, w2, r0.x, r1.x, r2.x);
-                        v.y = blend(w0, w1, w2, r0.y, r1.y, r2.y);
-                        v.z = blend(w0, w1, w2, r0.z, r1.z, r2.z);
-                        v.w = blend(w0, w1, w2, r0.w, r1.w, r2.w);
-                        *reinterpret_cast<float4*>(o) = v;
-                        if (g == P.min_group) vmin = fminf(vmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
-                    } else {
-                        for (int c = 0; c < ch; c++) {
-                            const float v = blend(w0, w1, w2, __ldg(a + base + c), __ldg(a + D + base + c), __ldg(a + 2 * D + base + c));
-                            o[c] = v;
-                            if (g == P.min_group) vmin = fminf(vmin, v);
-                        }
-                    }
-                    base += ch;
+    for (int it = 0; it < (TILE * TILE) / FWD_THREADS; it += 2) {
+        const int lx = tid & 31;
+        int lys[2], fw[2];
+        float4 c0[2], c1[2];
+        bool val[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            lys[u] = (it + u) * NWARP + (tid >> 5);
+            val[u] = (lx < tw) && (lys[u] < th);
+            fw[u] = -1;
+            if (val[u]) {
+                const unsigned long long key = s.zkey[lys[u] * TILE + lx];
+                if (key != 0ull) {
+                    fw[u] = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+                    const float4* rp = reinterpret_cast<const float4*>(recs + fw[u]);
+                    c0[u] = __ldg(rp);
+                    c1[u] = __ldg(rp + 1);
                 }
-                improb[gp] = 1.0f;
-                imcomp[gp] = 0.0f;
-                imidx[gp] = f + 1;
-                s.cnt[ly * TILE + lx] = 255;
-            } else {
-                for (int g = 0; g < P.n_out; g++) {
-                    const int ch = P.out_ch[g];
-                    float* o = P.out[g] + px * ch;
-                    if (ch == 4) *reinterpret_cast<float4*>(o) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    else for (int c = 0; c < ch; c++) o[c] = 0.f;
-                }
-                imidx[gp] = 0;                   // may be overwritten with the K-th face in phase D
-                unc = true;
-                vmin = fminf(vmin, 0.0f);
             }
         }
-        // winners go on the backward's colour work list (run-length de-duplicated along the row)
-        {
-            const int prev = __shfl_up_sync(0xffffffffu, fwin, 1);
-            const bool lead = fwin >= 0 && ((tid & 31) == 0 || prev != fwin);
-            mark_faces_warp(P, lead, f_lo + max(fwin, 0), 1u);
+        unsigned fl[2];
+        bool lead[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            // winners go on the backward's colour work list (run-length de-duplicated along the row)
+            const int prev = __shfl_up_sync(0xffffffffu, fw[u], 1);
+            lead[u] = fw[u] >= 0 && (lx == 0 || prev != fw[u]);
+            fl[u] = lead[u] ? __ldcg(&P.face_flags[f_lo + fw[u]]) : 1u;
         }
-        // which 16x16 sub-tiles still hold uncovered pixels (a warp is one row: lanes 0-15 | 16-31)
-        const unsigned bal = __ballot_sync(0xffffffffu, unc);
-        if (bal) {
-            any_unc = true;
-            if ((tid & 31) == 0) {
-                const int st0 = (ly / SUB) * (TILE / SUB);
-                unsigned m = 0;
-                if (bal & 0x0000ffffu) m |= 1u << st0;
-                if (bal & 0xffff0000u) m |= 1u << (st0 + 1);
-                atomicOr(&s.sub_uncovered, m);
-                unsigned m8 = 0;
-                const int brow = (ly >> 3) * 4;
-                if (bal & 0x000000ffu) m8 |= 1u << brow;
-                if (bal & 0x0000ff00u) m8 |= 1u << (brow + 1);
-                if (bal & 0x00ff0000u) m8 |= 1u << (brow + 2);
-                if (bal & 0xff000000u) m8 |= 1u << (brow + 3);
-                atomicOr(&s.unc_blocks, m8);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int ly = lys[u];
+            bool unc = false;
+            if (val[u]) {
+                const size_t gp = (size_t)(ty0 + ly) * P.width + (tx0 + lx);
+                const size_t px = img_pix + gp;
+                if (fw[u] >= 0) {
+                    const int f = fw[u];
+                    FaceRec r;
+                    r.ax = c0[u].x; r.ay = c0[u].y; r.bx = c0[u].z; r.by = c0[u].w; r.cx = c1[u].x; r.cy = c1[u].y;
+                    r.az = r.bz = r.cz = 0.f;
+                    const FaceK fk = make_facek(r);
+                    float w0, w1, w2;
+                    bary(fk, s.xs[lx], s.ys[ly], w0, w1, w2);
+                    const float* a = fattr + (size_t)f * 3 * D;
+                    int base = 0;
+                    for (int g = 0; g < P.n_out; g++) {
+                        const int ch = P.out_ch[g];
+                        float* o = P.out[g] + px * ch;
+                        if (ch == 4 && ((D | base) & 3) == 0) {
+                            const float4 r0 = __ldg(reinterpret_cast<const float4*>(a + base));
+                            const float4 r1 = __ldg(reinterpret_cast<const float4*>(a + D + base));
+                            const float4 r2 = __ldg(reinterpret_cast<const float4*>(a + 2 * D + base));
+                            float4 v;
+                            v.x = blend(w0, w1, w2, r0.x, r1.x, r2.x);
+                            v.y = blend(w0, w1, w2, r0.y, r1.y, r2.y);
+                            v.z = blend(w0, w1, w2, r0.z, r1.z, r2.z);
+                            v.w = blend(w0, w1, w2, r0.w, r1.w, r2.w);
+                            *reinterpret_cast<float4*>(o) = v;
+                            if (g == P.min_group) vmin = fminf(vmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+                        } else {
+                            for (int c = 0; c < ch; c++) {
+                                const float v = blend(w0, w1, w2, __ldg(a + base + c), __ldg(a + D + base + c), __ldg(a + 2 * D + base + c));
+                                o[c] = v;
+                                if (g == P.min_group) vmin = fminf(vmin, v);
+                            }
+                        }
+                        base += ch;
+                    }
+                    improb[gp] = 1.0f;
+                    imcomp[gp] = 0.0f;
+                    imidx[gp] = f + 1;
+                    s.cnt[ly * TILE + lx] = 255;
+                } else {
+                    for (int g = 0; g < P.n_out; g++) {
+                        const int ch = P.out_ch[g];
+                        float* o = P.out[g] + px * ch;
+                        if (ch == 4) *reinterpret_cast<float4*>(o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        else for (int c = 0; c < ch; c++) o[c] = 0.f;
+                    }
+                    imidx[gp] = 0;                   // may be overwritten with the K-th face in phase D
+                    improb[gp] = 0.0f;               // empty product; phase D overwrites the pixels it reaches
+                    imcomp[gp] = 1.0f;
+                    unc = true;
+                    vmin = fminf(vmin, 0.0f);
+                }
+            }
+            // append first-time winners to the colour list: one counter atomic per warp
+            {
+                bool isnew = false;
+                const int g = f_lo + max(fw[u], 0);
+                if (lead[u] && (fl[u] & 1u) == 0u) isnew = (atomicOr(&P.face_flags[g], 1u) & 1u) == 0u;
+                const unsigned nb = __ballot_sync(0xffffffffu, isnew);
+                if (nb) {
+                    const int leader = __ffs(nb) - 1;
+                    int lb = 0;
+                    if (lx == leader) lb = atomicAdd(&P.list_counts[0], __popc(nb));
+                    lb = __shfl_sync(0xffffffffu, lb, leader);
+                    if (isnew) P.color_list[lb + __popc(nb & ((1u << lx) - 1u))] = g;
+                }
+            }
+            // which 16x16 sub-tiles / 8x8 blocks still hold uncovered pixels (a warp is one row: lanes 0-15 | 16-31)
+            const unsigned bal = __ballot_sync(0xffffffffu, unc);
+            if (bal) {
+                any_unc = true;
+                if (lx == 0) {
+                    const int st0 = (ly / SUB) * (TILE / SUB);
+                    unsigned m = 0;
+                    if (bal & 0x0000ffffu) m |= 1u << st0;
+                    if (bal & 0xffff0000u) m |= 1u << (st0 + 1);
+                    atomicOr(&s.sub_uncovered, m);
+                    unsigned m8 = 0;
+                    const int brow = (ly >> 3) * 4;
+                    if (bal & 0x000000ffu) m8 |= 1u << brow;
+                    if (bal & 0x0000ff00u) m8 |= 1u << (brow + 1);
+                    if (bal & 0x00ff0000u) m8 |= 1u << (brow + 2);
+                    if (bal & 0xff000000u) m8 |= 1u << (brow + 3);
+                    atomicOr(&s.unc_blocks, m8);
+                }
             }
         }
     }
@@ -623,6 +710,7 @@ dibr_forward_kernel(FwdParams P)
         if ((tid & 31) == 0 && ov != f2ord(3.0e38f)) atomicMin(P.out_min, ov);
     }
     const int tile_unc = __syncthreads_or(any_unc ? 1 : 0);
+    PHASE_MARK(3);
     if (tid == 0) *unc_out = (unsigned short)s.unc_blocks;
 
     // ---- phase D: soft silhouette ------------------------------------------------------------------
@@ -630,12 +718,16 @@ dibr_forward_kernel(FwdParams P)
         const float zscale = (float)P.delta / ((float)P.multiplier * (float)P.multiplier);
         const float sentinel = 4.0f * (float)P.multiplier * (float)P.multiplier;
         if (nbatch == 1) {
-            if (s.lcount > 0) soft_list(s, P, f_lo, recs, tw, th, P.knum, zscale, sentinel, imidx, P.width, tx0, ty0);
+            if (s.lcount > 0) soft_list(s, P, f_lo, recs, tw, th, P.knum, zscale, sentinel, imidx, improb, imcomp, P.width, tx0, ty0, true);
         } else {
             int pos = 0;
+            bool first = true;
             while (pos < fnum) {
-                pos = fill_list(s, bbox, pos, fnum, ex, tx_lo, tx_hi, ty_lo, ty_hi, phase0, phase1);
-                if (s.lcount > 0) soft_list(s, P, f_lo, recs, tw, th, P.knum, zscale, sentinel, imidx, P.width, tx0, ty0);
+                pos = fill_list(s, bbox, pos, fnum, ex, tx_lo, tx_hi, ty_lo, ty_hi, phases, 2);      // aux holds soft scratch
+                if (s.lcount > 0) {
+                    soft_list(s, P, f_lo, recs, tw, th, P.knum, zscale, sentinel, imidx, improb, imcomp, P.width, tx0, ty0, first);
+                    first = false;
+                }
                 // stop early once every uncovered pixel has its K faces
                 bool open = false;
                 for (int i = tid; i < TILE * TILE; i += FWD_THREADS) open |= ((int)s.cnt[i] < P.knum);
@@ -643,15 +735,7 @@ dibr_forward_kernel(FwdParams P)
             }
         }
     }
-#pragma unroll 1
-    for (int it = 0; it < (TILE * TILE) / FWD_THREADS; it++) {
-        const int ly = it * NWARP + (tid >> 5), lx = tid & 31;
-        if (lx < tw && ly < th && s.cnt[ly * TILE + lx] != 255) {
-            const size_t gp = (size_t)(ty0 + ly) * P.width + (tx0 + lx);
-            improb[gp] = s.soft_q[ly * TILE + lx];
-            imcomp[gp] = s.soft_c[ly * TILE + lx];
-        }
-    }
+    PHASE_MARK(4);
 }
 
 // out = (n - min) / (||n - min|| + 1e-5) * mask  (renderer_dibr.py:284-285)
@@ -674,6 +758,14 @@ int launch_normal_map(const float* n, const float* mask, const unsigned int* min
     normal_map_kernel<<<grid, 256, 0, stream>>>(n, mask, min_ordered, out, npix);
     return (int)cudaGetLastError();
 }
+
+#ifdef DIBR_PHASE_TIMING
+extern "C" void dibr_debug_phase_cycles(unsigned long long* out8, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_phase, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_phase, z, sizeof(z)); }
+}
+#endif
 
 int launch_forward(const FwdParams& P, cudaStream_t stream)
 {
