@@ -443,7 +443,7 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
             if (!__any_sync(full_mask, open)) break;
         }
         flush_hits();
-        if (had) { improb_img[gpix] = q; imcomp_img[gpix] = cc; s.cnt[pix] = (unsigned char)c; }
+        if (had) { improb_img[gpix] = fminf(q, 1.0f); imcomp_img[gpix] = cc; s.cnt[pix] = (unsigned char)c; }   // the recurrence can overshoot 1 by an ulp
     }
     __syncthreads();
     if (tid == 0) s.next_block = 0;

@@ -99,8 +99,16 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(SetupParams P)
     float x2[3] = {0, 0, 0}, y2[3] = {0, 0, 0}, zc[3] = {0, 0, 0};
     float nz = 0.f;
     int b = -1;
+    // instance lookup once per warp (faces of an instance are contiguous: lanes only ever step forward a little)
+    int inst0 = 0;
+    {
+        const int gw = min(blockIdx.x * blockDim.x + (threadIdx.x & ~31), max(P.total_faces - 1, 0));
+        if ((threadIdx.x & 31) == 0) inst0 = instance_of_face(gw, P.num_instances, P.inst_desc);
+        inst0 = __shfl_sync(0xffffffffu, inst0, 0);
+    }
     if (active) {
-        const int inst = instance_of_face(g, P.num_instances, P.inst_desc);
+        int inst = inst0;
+        while (inst + 1 < P.num_instances && P.inst_desc[(inst + 1) * INST_STRIDE + I_OUT_FACE_BASE] <= g) inst++;
         const int32_t* de = P.inst_desc + inst * INST_STRIDE;
         const int lf = g - de[I_OUT_FACE_BASE];
         b = de[I_IMAGE];
@@ -126,13 +134,27 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(SetupParams P)
             const float xn = __fdiv_rn(clip[0], clip[3]), yn = __fdiv_rn(clip[1], clip[3]);
             x2[c] = __fmul_rn(m, xn); y2[c] = __fmul_rn(m, yn);
             zc[c] = pc[c][2];
-            // per-face corner attributes: [vertex attrs | ones | view depth]
+            // per-face corner attributes: [vertex attrs | ones | view depth], 128-bit stores when D % 4 == 0
             float* fa = P.face_attr + ((size_t)g * 3 + c) * D;
             const float* va = P.vert_attr + (size_t)(de[I_ATTR_BASE] + vid) * A;
-            for (int d = 0; d < A; d++) fa[d] = va[d];
-            int d = A;
-            if (P.attr_flags & 1) fa[d++] = 1.0f;
-            if (P.attr_flags & 2) fa[d++] = -pc[c][2];
+            float av[DIBR_MAX_ATTR_INTERNAL];
+#pragma unroll
+            for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) {
+                float x = 0.f;
+                if (d < A) x = __ldg(va + d);
+                else if (d == A && (P.attr_flags & 1)) x = 1.0f;
+                else if (d == A + (P.attr_flags & 1) && (P.attr_flags & 2)) x = -pc[c][2];
+                av[d] = x;
+            }
+            if ((D & 3) == 0) {
+#pragma unroll
+                for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d += 4)
+                    if (d < D) reinterpret_cast<float4*>(fa)[d >> 2] = make_float4(av[d], av[d + 1], av[d + 2], av[d + 3]);
+            } else {
+#pragma unroll
+                for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++)
+                    if (d < D) fa[d] = av[d];
+            }
         }
         const float e1x = __fsub_rn(pc[1][0], pc[0][0]), e1y = __fsub_rn(pc[1][1], pc[0][1]), e1z = __fsub_rn(pc[1][2], pc[0][2]);
         const float e2x = __fsub_rn(pc[2][0], pc[0][0]), e2y = __fsub_rn(pc[2][1], pc[0][1]), e2z = __fsub_rn(pc[2][2], pc[0][2]);

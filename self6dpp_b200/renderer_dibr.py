@@ -126,7 +126,7 @@ class Renderer_dibr(object):
         self._registry = _ModelRegistry()
 
     def _render_batch_fast(self, Rs, ts, models, Ks, width, height, znear, zfar, rot_type, names, split, flags,
-                           min_output=None):
+                           min_output=None, multi=False):
         """pose-mode fast path: resident models, R/t/K handed straight to the kernels (no camera torch ops)."""
         reg = self._registry
         slots = reg.slots(models)
@@ -158,19 +158,23 @@ class Renderer_dibr(object):
         desc[:, 6] = ar if K.shape[0] > 1 else 0
         desc[:, 7] = tab[:, 0]
         desc[:, 8] = np.cumsum(nv) - nv
-        desc[:, 9] = ar
+        desc[:, 9] = 0 if multi else ar                               # image the instance lands in
         desc[:, 10] = tab[:, 0]
         desc[:, 11] = 0
         hn[B * fused.INST_STRIDE] = 0
         hn[B * fused.INST_STRIDE + 1:] = np.cumsum(nf)
+        nimg = 1 if multi else B
+        if multi:                                                      # one image owns every face
+            hn[B * fused.INST_STRIDE + 1] = int(nf.sum())
         dev = torch.empty_like(host, device=device)
         dev.copy_(host, non_blocking=True)
         A = 3 * len(names)
-        meta = dict(batch=B, height=int(height), width=int(width), attr_dim=A, attr_flags=int(flags),
+        meta = dict(batch=nimg, height=int(height), width=int(width), attr_dim=A, attr_flags=int(flags),
                     total_faces=int(nf.sum()), num_instances=B, num_inst_verts=int(nv.sum()), pack=reg.pack,
                     knum=fused.DEFAULT_KNUM, multiplier=fused.DEFAULT_MULTIPLIER, delta=fused.DEFAULT_DELTA,
                     expand=fused.DEFAULT_EXPAND, want_normals=False, num_attr_rows=int(reg.verts.shape[0]),
-                    out_split=split, inst_desc=dev[:B * fused.INST_STRIDE], face_offsets=dev[B * fused.INST_STRIDE:],
+                    out_split=split, inst_desc=dev[:B * fused.INST_STRIDE],
+                    face_offsets=dev[B * fused.INST_STRIDE:B * fused.INST_STRIDE + nimg + 1],
                     pose_mode=True, znear=float(znear), zfar=float(zfar), min_output=min_output)
         res = fused.render_meshes(reg.verts, vattr, R, ts.reshape(B, 3), K, meta)
         return list(res[:-2]), res[-2], meta
@@ -244,13 +248,23 @@ class Renderer_dibr(object):
         """
         ret = {}
         self.scene_ren = DIBRenderer(height, width, mode="VertexColorMulti")
-        self.scene_ren.set_camera_parameters_from_RT_K(Rs, ts, K, height, width, near=znear, far=zfar, rot_type=rot_type)
-        points = [[model["vertices"], _faces_int32(model["faces"])] for model in models]
-        attrs = [_model_attrs(model, ["colors"]) for model in models]
         flags = fused.FLAG_ONES | (fused.FLAG_DEPTH if with_depth else 0)
-        outs, improb, _, meta = render_instances(points, attrs, self.scene_ren.camera_params, height, width, multi=True,
-                                                 want_normals=False, attr_flags=flags,
-                                                 out_split=[3, 1, 1] if with_depth else [3, 1])
+        split = [3, 1, 1] if with_depth else [3, 1]
+        if not isinstance(Rs, torch.Tensor) and isinstance(Rs, (list, tuple)) and all(isinstance(r, torch.Tensor) for r in Rs):
+            Rs = torch.stack(list(Rs))
+        if not isinstance(ts, torch.Tensor) and isinstance(ts, (list, tuple)) and all(isinstance(t, torch.Tensor) for t in ts):
+            ts = torch.stack(list(ts))
+        fast = self._render_batch_fast(Rs, ts, models, K, width, height, znear, zfar, rot_type, ["colors"], split, flags,
+                                       multi=True)
+        if fast is not None:
+            outs, improb, meta = fast
+            self.scene_ren.set_camera_parameters_lazy(Rs, ts, K, height, width, znear, zfar, rot_type)
+        else:
+            self.scene_ren.set_camera_parameters_from_RT_K(Rs, ts, K, height, width, near=znear, far=zfar, rot_type=rot_type)
+            points = [[model["vertices"], _faces_int32(model["faces"])] for model in models]
+            attrs = [_model_attrs(model, ["colors"]) for model in models]
+            outs, improb, _, meta = render_instances(points, attrs, self.scene_ren.camera_params, height, width, multi=True,
+                                                     want_normals=False, attr_flags=flags, out_split=split)
         ret["color"] = outs[0].squeeze()
         ret["prob"] = improb.squeeze()
         ret["mask"] = outs[1].squeeze()
