@@ -10,14 +10,17 @@
 namespace dibr {
 
 constexpr int TILE = 32;            // forward CTA tile (pixels per side)
-constexpr int FWD_THREADS = 256;
+#ifndef DIBR_FWD_THREADS
+#define DIBR_FWD_THREADS 512
+#endif
+constexpr int FWD_THREADS = DIBR_FWD_THREADS;   // threads per tile CTA (16 warps: the heaviest tiles set the kernel's tail)
 constexpr int LCAP = 1024;          // faces per in-shared-memory batch of a tile
 constexpr int SUB = 16;             // sub-tile side for the soft-silhouette lists
 constexpr int NSUB = (TILE / SUB) * (TILE / SUB);
 constexpr int SUBCAP = 512;         // entries per sub-tile list
 constexpr int BIGCAP = 64;          // deferred large faces per batch
 constexpr int BIG_AREA = 128;       // pixels of a face inside the tile above which the CTA cooperates
-constexpr int SCAN_CHUNK = 256;     // faces per TMA-staged bbox chunk
+constexpr int SCAN_CHUNK = FWD_THREADS;   // faces per TMA-staged bbox chunk (one per thread)
 
 // 64 B face record, written by the set-up kernels.
 struct __align__(16) FaceRec {

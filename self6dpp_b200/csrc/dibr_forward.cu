@@ -38,6 +38,7 @@ constexpr int HITCAP = 24;              // collected faces per pixel per round o
 constexpr int BW = 8, BH = 4;           // pixel block of one warp in phase D
 constexpr int NBX = TILE / BW, NBLK = NBX * (TILE / BH);
 static_assert(TILE == 32 && LCAP <= 1024, "rlist packing assumes 5-bit pixel coordinates and 10-bit list indices");
+static_assert(NWARP % 4 == 0 && NWARP * 128 * sizeof(float2) <= 2 * SCAN_CHUNK * sizeof(float4), "soft scratch must fit in aux");
 
 struct FwdSmem {
     unsigned long long zkey[TILE * TILE];       //  8 KB
@@ -137,15 +138,18 @@ __device__ int fill_list(FwdSmem& s, const float4* __restrict__ bbox, int pos, i
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
         if (lane == 0) s.warp_cnt16[par][warp] = (unsigned short)__popc(bal);
         __syncthreads();            // counts visible; everybody has read stage[buf]  (the only barrier per chunk)
-        // the 8 per-warp counts sit in two 64-bit words (16-bit fields): prefix and total by field-wise multiply
-        const unsigned long long lo = reinterpret_cast<const unsigned long long*>(s.warp_cnt16[par])[0];
-        const unsigned long long hi = reinterpret_cast<const unsigned long long*>(s.warp_cnt16[par])[1];
+        // the per-warp counts sit in NWARP/4 64-bit words (16-bit fields): prefix and total by field-wise multiply
+        const unsigned long long* wc = reinterpret_cast<const unsigned long long*>(s.warp_cnt16[par]);
         constexpr unsigned long long ONES = 0x0001000100010001ull;
-        const int sum_lo = (int)((lo * ONES) >> 48), sum_hi = (int)((hi * ONES) >> 48);
-        const int w4 = warp & 3;
-        const unsigned long long part = (warp < 4 ? lo : hi) & ((1ull << (16 * w4)) - 1ull);
-        const int base = lcount + (warp < 4 ? 0 : sum_lo) + (int)((part * ONES) >> 48);
-        const int tot = sum_lo + sum_hi;
+        int base = lcount, tot = 0;
+#pragma unroll
+        for (int k = 0; k < NWARP / 4; k++) {
+            const unsigned long long wv = wc[k];
+            const int sk = (int)((wv * ONES) >> 48);
+            if (k < (warp >> 2)) base += sk;
+            else if (k == (warp >> 2)) base += (int)(((wv & ((1ull << (16 * (warp & 3))) - 1ull)) * ONES) >> 48);
+            tot += sk;
+        }
         const bool fits = (lcount + tot <= LCAP);
         if (fits && hit) {
             const int slot = base + __popc(bal & ((1u << lane) - 1u));
@@ -368,8 +372,8 @@ __device__ void soft_list(FwdSmem& s, const FwdParams& P, int f_lo, const FaceRe
         // of four k-levels at a time are flattened (warp scan) and dealt out evenly: every lane evaluates one
         // pair per pass; then each pixel folds ITS results in ascending face order.  Scratch lives in the z-buffer
         // (dead after phase C) and in aux.
-        float2* const res = reinterpret_cast<float2*>(s.zkey) + warp * 128;                    // 1 KB of the dead z-buffer
-        unsigned short* const prs = reinterpret_cast<unsigned short*>(s.aux) + warp * 128;      // 256 B of aux
+        float2* const res = reinterpret_cast<float2*>(s.aux) + warp * 128;                      // 1 KB of aux
+        unsigned short* const prs = reinterpret_cast<unsigned short*>(s.zkey) + warp * 128;     // 256 B of the dead z-buffer
         auto flush_hits = [&]() {
             __syncwarp();                          // the hit lists were written by other lanes
             const int kmax = __reduce_max_sync(full_mask, nh);
@@ -462,10 +466,12 @@ __device__ __forceinline__ void zero_full_tile(float* __restrict__ img, int widt
 {
     constexpr int RV = TILE * CH / 4;                    // float4 per tile row
 #pragma unroll
-    for (int k = 0; k < CH; k++) {
-        const int i = k * FWD_THREADS + threadIdx.x;
-        const int r = i / RV, c = i - r * RV;
-        reinterpret_cast<float4*>(img + ((size_t)(ty0 + r) * width + tx0) * CH)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i0 = 0; i0 < TILE * RV; i0 += FWD_THREADS) {
+        const int i = i0 + threadIdx.x;
+        if (i < TILE * RV) {
+            const int r = i / RV, c = i - r * RV;
+            reinterpret_cast<float4*>(img + ((size_t)(ty0 + r) * width + tx0) * CH)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
@@ -490,7 +496,7 @@ __device__ __forceinline__ void zero_tile(float* __restrict__ img, int width, in
 }
 
 #ifndef DIBR_FWD_MIN_CTAS
-#define DIBR_FWD_MIN_CTAS 4
+#define DIBR_FWD_MIN_CTAS (1024 / DIBR_FWD_THREADS)
 #endif
 __global__ void __launch_bounds__(FWD_THREADS, DIBR_FWD_MIN_CTAS)
 dibr_forward_kernel(FwdParams P)
