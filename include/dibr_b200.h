@@ -197,6 +197,25 @@ typedef struct DibrStep {
 
 int dibr_render_step(const DibrStep *step, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Chamfer nearest-neighbour distance -- replaces the reference's torch_nndistance extension
+ * (core/csrc/torch_nndistance/src/nnd_cuda.cpp:86-89 nnd_forward_cuda / nnd_backward_cuda; CPU twin nnd_cpu.cpp).
+ * Clouds are padded: sample b of cloud i occupies rows [b*stride_i, b*stride_i + count_i[b]) of xyz_i ([batch*stride_i, 3]);
+ * count_i == NULL means every row is a point (the reference's dense [b, n, 3] layout).  dist = squared distance to the
+ * nearest point of the other cloud, idx = its row within the sample (first minimum in ascending order).  Rows beyond
+ * count are not written by the forward and get zero gradient. */
+typedef struct DibrNnd {
+    int32_t batch, stride1, stride2, reserved;
+    const int32_t *count1, *count2;          /* device [batch] or NULL */
+    const float *xyz1, *xyz2;
+    float *dist1, *dist2;                    /* [batch*stride_i] */
+    int32_t *idx1, *idx2;
+    const float *graddist1, *graddist2;      /* backward inputs */
+    float *gradxyz1, *gradxyz2;              /* backward outputs [batch*stride_i, 3] */
+} DibrNnd;
+int dibr_nnd_forward(const DibrNnd *p, void *stream);
+int dibr_nnd_backward(const DibrNnd *p, void *stream);
+
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);
 

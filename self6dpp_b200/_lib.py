@@ -57,9 +57,20 @@ class DibrStep(ctypes.Structure):
     ]
 
 
+class DibrNnd(ctypes.Structure):
+    """Mirror of ``struct DibrNnd`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("stride1", ctypes.c_int32), ("stride2", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("count1", _c_i32p), ("count2", _c_i32p), ("xyz1", _c_f32p), ("xyz2", _c_f32p),
+        ("dist1", _c_f32p), ("dist2", _c_f32p), ("idx1", _c_i32p), ("idx2", _c_i32p),
+        ("graddist1", _c_f32p), ("graddist2", _c_f32p), ("gradxyz1", _c_f32p), ("gradxyz2", _c_f32p),
+    ]
+
+
 EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_device_count", "dibr_workspace_bytes",
            "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
-           "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_launch_count"]
+           "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_launch_count"]
 
 _lib = None
 
@@ -100,6 +111,10 @@ def load():
     lib.dibr_render_step.restype = ctypes.c_int
     if lib.dibr_sizeof_step() != ctypes.sizeof(DibrStep):
         raise RuntimeError("DibrStep mirror out of date")
+    for name in ("dibr_nnd_forward", "dibr_nnd_backward"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrNnd), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
     if lib.dibr_abi_version() != 1:
         raise RuntimeError("libdibr_b200.so ABI version mismatch")
     if lib.dibr_sizeof_pass() != ctypes.sizeof(DibrPass):

@@ -254,6 +254,33 @@ int dibr_normal_map(const float* normals, const float* mask, const uint32_t* min
     return cuda_fail("dibr_normal_map", dibr::launch_normal_map(normals, mask, min_ordered, out, npix, (cudaStream_t)stream));
 }
 
+static int nnd_params(const DibrNnd* p, dibr::NndParams& n, bool backward) {
+    if (!p) return fail("null DibrNnd");
+    if (p->batch < 0 || p->stride1 < 0 || p->stride2 < 0) return fail("nnd: negative sizes");
+    if (!p->xyz1 || !p->xyz2 || !p->idx1 || !p->idx2) return fail("nnd: xyz / idx buffers required");
+    if (!backward && (!p->dist1 || !p->dist2)) return fail("nnd_forward: dist buffers required");
+    if (backward && (!p->graddist1 || !p->graddist2 || !p->gradxyz1 || !p->gradxyz2)) return fail("nnd_backward: gradient buffers required");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    n.batch = p->batch; n.stride1 = p->stride1; n.stride2 = p->stride2; n.count1 = p->count1; n.count2 = p->count2;
+    n.xyz1 = p->xyz1; n.xyz2 = p->xyz2; n.dist1 = p->dist1; n.dist2 = p->dist2; n.idx1 = p->idx1; n.idx2 = p->idx2;
+    n.graddist1 = p->graddist1; n.graddist2 = p->graddist2; n.gradxyz1 = p->gradxyz1; n.gradxyz2 = p->gradxyz2;
+    return 0;
+}
+
+int dibr_nnd_forward(const DibrNnd* p, void* stream) {
+    dibr::NndParams n;
+    if (int e = nnd_params(p, n, false)) return e;
+    g_launches += 2;
+    return cuda_fail("dibr_nnd_forward", dibr::launch_nnd_forward(n, (cudaStream_t)stream));
+}
+
+int dibr_nnd_backward(const DibrNnd* p, void* stream) {
+    dibr::NndParams n;
+    if (int e = nnd_params(p, n, true)) return e;
+    g_launches += 2;
+    return cuda_fail("dibr_nnd_backward", dibr::launch_nnd_backward(n, (cudaStream_t)stream));
+}
+
 // gather [n,9] + [n,3] into [n,12] so ONE D2H copy returns the pose gradients
 __global__ void pack_pose_grad_kernel(const float* __restrict__ gR, const float* __restrict__ gt, float* __restrict__ out, int n)
 {

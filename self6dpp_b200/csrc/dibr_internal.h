@@ -136,6 +136,25 @@ constexpr int INST_STRIDE = 12;
 enum { I_VERT_BASE = 0, I_NUM_VERTS, I_MESH_FACE_BASE, I_NUM_FACES, I_OUT_FACE_BASE, I_CAM, I_PROJ, I_ATTR_BASE,
        I_GVERT_BASE, I_IMAGE, I_ADJ_BASE, I_RESERVED };
 
+// chamfer nearest-neighbour op: cloud i of sample b = rows [b*stride_i, b*stride_i + count_i[b]) (count NULL: all rows)
+struct NndParams {
+    int batch, stride1, stride2;
+    const int* count1;
+    const int* count2;
+    const float* xyz1;
+    const float* xyz2;
+    float* dist1;
+    float* dist2;
+    int* idx1;
+    int* idx2;
+    const float* graddist1;
+    const float* graddist2;
+    float* gradxyz1;
+    float* gradxyz2;
+};
+
+int launch_nnd_forward(const NndParams& P, cudaStream_t stream);
+int launch_nnd_backward(const NndParams& P, cudaStream_t stream);
 int launch_setup_faces(const SetupParams& P, cudaStream_t stream);
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream);
 int launch_forward(const FwdParams& P, cudaStream_t stream);

@@ -1,0 +1,146 @@
+"""Chamfer nearest-neighbour distance and the depth back-projection chamfer loss on B200.
+
+Drop-ins for
+  * ``core.csrc.torch_nndistance.torch_nndistance.nnd`` (/root/reference/core/csrc/torch_nndistance/torch_nndistance.py:13-85):
+    ``nnd(xyz1 [b,n,3], xyz2 [b,m,3]) -> (dist1 [b,n], dist2 [b,m])`` squared distances to the nearest point of the other
+    cloud, differentiable w.r.t. both clouds;
+  * ``depth_bp_chamfer_loss`` (core/self6dpp/losses/depth_bp_chamfer_loss.py:12-62) and ``backproject_th``
+    (lib/pysixd/misc.py:350-367).
+
+The reference loops over the batch in Python (boolean-mask compaction forces a host sync per sample) and its CUDA
+kernel then runs 16 blocks.  Here the whole batch is compacted on the device (cumsum + scatter, no sync), one launch
+per direction covers every sample, and the backward is a deterministic gather (``dibr_nnd_forward`` /
+``dibr_nnd_backward`` in include/dibr_b200.h).  No CPU fallback.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .rasterizer import _require_cuda_f32, _stream
+
+
+def _launch(fn_name, p, device):
+    with torch.cuda.device(device):
+        _lib.check(getattr(_lib.load(), fn_name)(ctypes.byref(p), _stream(device)), fn_name)
+
+
+class NNDFunction(Function):
+    """Padded clouds: sample b of cloud i = rows [0, count_i[b]) of xyz_i[b] (count None: all rows)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, count1=None, count2=None):
+        _require_cuda_f32("xyz1", xyz1)
+        _require_cuda_f32("xyz2", xyz2)
+        b, n, _ = xyz1.shape
+        m = xyz2.shape[1]
+        assert xyz2.shape[0] == b and xyz1.shape[2] == 3 and xyz2.shape[2] == 3
+        x1, x2 = xyz1.detach().contiguous(), xyz2.detach().contiguous()
+        device = x1.device
+        dist1 = torch.zeros(b, n, dtype=torch.float32, device=device)
+        dist2 = torch.zeros(b, m, dtype=torch.float32, device=device)
+        idx1 = torch.zeros(b, n, dtype=torch.int32, device=device)
+        idx2 = torch.zeros(b, m, dtype=torch.int32, device=device)
+        c1 = count1.to(torch.int32).contiguous() if count1 is not None else None
+        c2 = count2.to(torch.int32).contiguous() if count2 is not None else None
+        p = _lib.DibrNnd()
+        p.batch, p.stride1, p.stride2 = b, n, m
+        p.count1, p.count2 = _lib.ptr(c1), _lib.ptr(c2)
+        p.xyz1, p.xyz2 = _lib.ptr(x1), _lib.ptr(x2)
+        p.dist1, p.dist2, p.idx1, p.idx2 = _lib.ptr(dist1), _lib.ptr(dist2), _lib.ptr(idx1), _lib.ptr(idx2)
+        _launch("dibr_nnd_forward", p, device)
+        ctx.save_for_backward(x1, x2, idx1, idx2, *( [c1] if c1 is not None else []), *([c2] if c2 is not None else []))
+        ctx.has_counts = (c1 is not None, c2 is not None)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return dist1, dist2, idx1, idx2
+
+    @staticmethod
+    def backward(ctx, graddist1, graddist2, _gi1, _gi2):
+        saved = list(ctx.saved_tensors)
+        x1, x2, idx1, idx2 = saved[:4]
+        rest = saved[4:]
+        c1 = rest.pop(0) if ctx.has_counts[0] else None
+        c2 = rest.pop(0) if ctx.has_counts[1] else None
+        device = x1.device
+        b, n, _ = x1.shape
+        m = x2.shape[1]
+        g1 = (graddist1 if graddist1 is not None else torch.zeros(b, n, device=device)).contiguous()
+        g2 = (graddist2 if graddist2 is not None else torch.zeros(b, m, device=device)).contiguous()
+        gx1 = torch.empty(b, n, 3, dtype=torch.float32, device=device)
+        gx2 = torch.empty(b, m, 3, dtype=torch.float32, device=device)
+        p = _lib.DibrNnd()
+        p.batch, p.stride1, p.stride2 = b, n, m
+        p.count1, p.count2 = _lib.ptr(c1), _lib.ptr(c2)
+        p.xyz1, p.xyz2, p.idx1, p.idx2 = _lib.ptr(x1), _lib.ptr(x2), _lib.ptr(idx1), _lib.ptr(idx2)
+        p.graddist1, p.graddist2, p.gradxyz1, p.gradxyz2 = _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(gx1), _lib.ptr(gx2)
+        _launch("dibr_nnd_backward", p, device)
+        return gx1, gx2, None, None
+
+
+def nnd(xyz1, xyz2):
+    """reference signature (torch_nndistance.py:82-85): -> (dist1, dist2)"""
+    d1, d2, _, _ = NNDFunction.apply(xyz1, xyz2, None, None)
+    return d1, d2
+
+
+def nnd_padded(xyz1, count1, xyz2, count2):
+    """ragged batch: -> (dist1, dist2, idx1, idx2); rows beyond count are zero"""
+    return NNDFunction.apply(xyz1, xyz2, count1, count2)
+
+
+def backproject_th(depth, K):
+    """lib/pysixd/misc.py:350-367; depth [H,W] or [B,H,W], K [3,3] or [B,3,3] -> organised cloud [...,H,W,3]"""
+    squeeze = depth.ndim == 2
+    d = depth[None] if squeeze else depth
+    Kb = K.reshape(-1, 3, 3).to(d)
+    H, W = d.shape[-2:]
+    ys = torch.arange(H, device=d.device, dtype=d.dtype).view(1, H, 1) - Kb[:, 1, 2].view(-1, 1, 1)
+    xs = torch.arange(W, device=d.device, dtype=d.dtype).view(1, 1, W) - Kb[:, 0, 2].view(-1, 1, 1)
+    out = torch.stack((xs * d / Kb[:, 0, 0].view(-1, 1, 1), ys * d / Kb[:, 1, 1].view(-1, 1, 1), d), dim=-1)
+    return out[0] if squeeze else out
+
+
+def compact_valid_points(cloud_bxhxwx3):
+    """points with z > 0 of every sample, in row-major order (what boolean-mask indexing gives the reference), padded to
+    H*W rows: -> (points [B, H*W, 3], count [B] int32).  Differentiable, no host sync."""
+    B, H, W, _ = cloud_bxhxwx3.shape
+    flat = cloud_bxhxwx3.reshape(B, H * W, 3)
+    valid = flat[:, :, 2] > 0
+    pos = torch.cumsum(valid.to(torch.int32), dim=1) - 1
+    count = (pos[:, -1] + 1).to(torch.int32)
+    slot = torch.where(valid, pos, torch.full_like(pos, H * W)).to(torch.int64)      # invalid -> dump row
+    out = torch.zeros(B, H * W + 1, 3, dtype=flat.dtype, device=flat.device)
+    out = out.scatter(1, slot.unsqueeze(-1).expand(B, H * W, 3), flat)
+    return out[:, :H * W].contiguous(), count
+
+
+def depth_bp_chamfer_loss(ren_depths, real_depths, Ks, distance_threshold=0.05, center_lw=0):
+    """
+    Args (core/self6dpp/losses/depth_bp_chamfer_loss.py:12-19):
+        ren_depths: BHW, real_depths: BHW (target points: depth(masked) => backproject (K)), Ks: [3,3] or [B,3,3]
+    Returns (loss / max(num_valid,1), loss_center / max(num_valid,1)) like the reference, for the whole batch at once.
+    """
+    B, H, W = ren_depths.shape
+    real_pts, real_cnt = compact_valid_points(backproject_th(real_depths, Ks))
+    rend_pts, rend_cnt = compact_valid_points(backproject_th(ren_depths, Ks))
+    dist1, dist2, _, _ = nnd_padded(real_pts, real_cnt, rend_pts, rend_cnt)
+    ar = torch.arange(H * W, device=ren_depths.device).view(1, -1)
+    v1, v2 = ar < real_cnt.view(-1, 1), ar < rend_cnt.view(-1, 1)
+    s1, s2 = v1, v2
+    if distance_threshold > 0:
+        s1 = v1 & (dist1 < distance_threshold)
+        s2 = v2 & (dist2 < distance_threshold)
+    mean1 = (dist1 * s1).sum(1) / s1.sum(1)                    # 0/0 = nan when nothing is selected, like torch.mean([])
+    mean2 = (dist2 * s2).sum(1) / s2.sum(1)
+    cur = mean1 + mean2
+    ok = ~torch.isnan(cur)                                     # the reference skips such samples (:47-48)
+    num_valid = ok.sum().clamp(min=1)
+    loss = torch.where(ok, cur, torch.zeros_like(cur)).sum() / num_valid
+    loss_center = torch.zeros((), dtype=ren_depths.dtype, device=ren_depths.device)
+    if center_lw > 0:
+        c_real = (real_pts * v1.unsqueeze(-1)).sum(1) / real_cnt.view(-1, 1)
+        c_rend = (rend_pts * v2.unsqueeze(-1)).sum(1) / rend_cnt.view(-1, 1)
+        per = (c_real - c_rend).abs().mean(1) * center_lw       # smooth_l1(beta=0, "mean") = mean |.|
+        loss_center = torch.where(ok, per, torch.zeros_like(per)).sum() / num_valid
+    return loss, loss_center

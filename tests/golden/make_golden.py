@@ -137,10 +137,78 @@ def golden_seam(ref, H=48, W=64, seed=5):
     print("ref_seam48x64: covered", int((im[..., 3] > 0.5).sum()))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--nnd" not in sys.argv:
     import warnings
     warnings.filterwarnings("ignore")
     ref = O.import_reference()
     golden_seam(ref)
     golden_batch(ref)
     golden_multi(ref)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# chamfer nearest-neighbour op + depth back-projection chamfer loss: driven through the reference's OWN Python
+# (core/csrc/torch_nndistance/torch_nndistance.py, core/self6dpp/losses/depth_bp_chamfer_loss.py) on top of the
+# reference's OWN nnd_cpu.cpp compiled into oracle/_ref/libnnd_ref.so (make -C oracle ref).
+# ------------------------------------------------------------------------------------------------------------------
+def import_reference_chamfer():
+    import importlib.util
+    import types
+    from oracle import nnd_oracle as N
+    ref = N.ref_module()
+    assert ref is not None, "run `make -C oracle ref` first"
+    sys.modules["torch_nndistance_aten"] = ref
+    spec = importlib.util.spec_from_file_location(
+        "ref_torch_nndistance", "/root/reference/core/csrc/torch_nndistance/torch_nndistance.py")
+    nnd_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nnd_mod)
+    # the loss module's imports: only backproject_th, smooth_l1_loss and NND are used on the path
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+    for pkg in ("core", "core.csrc", "core.csrc.torch_nndistance", "fvcore", "lib", "lib.pysixd", "lib.vis_utils"):
+        sys.modules.setdefault(pkg, types.ModuleType(pkg))
+    stub("core.csrc.torch_nndistance.torch_nndistance", nnd=nnd_mod.nnd)
+    sys.modules["core.csrc.torch_nndistance"].torch_nndistance = sys.modules["core.csrc.torch_nndistance.torch_nndistance"]
+    stub("fvcore.nn", smooth_l1_loss=lambda a, b, beta, reduction: (a - b).abs().mean())
+    stub("lib.pysixd.misc", backproject_th=N.backproject_th)          # lib/pysixd/misc.py:350-367 restated (needs numba/mmcv)
+    stub("lib.vis_utils.image", heatmap=lambda *a, **k: None)
+    spec = importlib.util.spec_from_file_location(
+        "ref_depth_bp_chamfer_loss", "/root/reference/core/self6dpp/losses/depth_bp_chamfer_loss.py")
+    loss_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(loss_mod)
+    return nnd_mod, loss_mod
+
+
+def golden_nnd():
+    nnd_mod, loss_mod = import_reference_chamfer()
+    g = torch.Generator().manual_seed(11)
+    x1 = (torch.randn(2, 500, 3, generator=g) * 0.05).requires_grad_(True)
+    x2 = (torch.randn(2, 700, 3, generator=g) * 0.05).requires_grad_(True)
+    x2.data[0, 10] = x2.data[0, 3]                                   # duplicate target: first index must win
+    d1, d2 = nnd_mod.nnd(x1, x2)
+    g1, g2 = torch.randn(d1.shape, generator=g), torch.randn(d2.shape, generator=g)
+    ((d1 * g1).sum() + (d2 * g2).sum()).backward()
+    # depth loss: two 40x48 depth maps of a tilted plane / bumpy blob with holes
+    H, W, B = 40, 48, 3
+    K = torch.tensor([[60.0, 0, 23.5], [0, 60.0, 19.5], [0, 0, 1]])
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    real = 0.8 + 0.002 * xx + 0.001 * yy + 0.01 * torch.randn(B, H, W, generator=g)
+    real = real * (((xx - 24) ** 2 + (yy - 20) ** 2) < 15 ** 2)
+    ren = (0.82 + 0.0015 * xx + 0.0012 * yy + 0.01 * torch.randn(B, H, W, generator=g))
+    ren = ren * (((xx - 22) ** 2 + (yy - 21) ** 2) < 14 ** 2)
+    ren[2] = 0                                                        # an empty render: the reference skips the sample (nan)
+    ren = ren.requires_grad_(True)
+    loss, loss_c = loss_mod.depth_bp_chamfer_loss(ren, real, K, distance_threshold=0.05, center_lw=0.5)
+    (loss + loss_c).backward()
+    np.savez_compressed(os.path.join(OUT, "ref_nnd.npz"), x1=x1.detach().numpy(), x2=x2.detach().numpy(),
+                        d1=d1.detach().numpy(), d2=d2.detach().numpy(), g1=g1.numpy(), g2=g2.numpy(),
+                        gx1=x1.grad.numpy(), gx2=x2.grad.numpy(), K=K.numpy(), real=real.numpy(), ren=ren.detach().numpy(),
+                        loss=loss.detach().numpy(), loss_center=loss_c.detach().numpy(), g_ren=ren.grad.numpy())
+    print("ref_nnd: loss", float(loss), "center", float(loss_c))
+
+
+if __name__ == "__main__" and "--nnd" in sys.argv:
+    golden_nnd()
