@@ -33,7 +33,8 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     char* b = (char*)base;
     auto take = [&](size_t bytes) { void* r = b ? (void*)(b + off) : nullptr; off += align_up(bytes, 256); return r; };
     w.recs = (dibr::FaceRec*)take(sizeof(dibr::FaceRec) * (size_t)p->total_faces);
-    w.bbox = (float4*)take(sizeof(float4) * (size_t)p->total_faces);
+    w.bins_bytes = sizeof(uint32_t) * dibr::bin_total_words(p->width, p->height, p->batch, p->total_faces);
+    w.bins = (uint32_t*)take(w.bins_bytes);
     w.imgbox = (uint4*)take(sizeof(uint4) * (size_t)p->batch);
     w.xs = (float*)take(sizeof(float) * (size_t)p->width);
     w.ys = (float*)take(sizeof(float) * (size_t)p->height);
@@ -46,7 +47,6 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     w.face_flags = (unsigned int*)take(sizeof(unsigned int) * (size_t)p->total_faces);   // directly after list_counts: one memset
     w.color_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
     w.soft_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
-    w.unc_blocks = (unsigned short*)take(sizeof(unsigned short) * (size_t)p->batch * ((p->height + dibr::TILE - 1) / dibr::TILE) * ((p->width + dibr::TILE - 1) / dibr::TILE));
     w.bytes = off;
     return w;
 }
@@ -54,6 +54,7 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
 int check_common(const DibrPass* p, bool need_ws) {
     if (!p) return fail("null DibrPass");
     if (p->batch <= 0 || p->height <= 0 || p->width <= 0) return fail("bad image size b=%d h=%d w=%d", p->batch, p->height, p->width);
+    if (p->height > dibr::MAX_IMAGE_SIDE || p->width > dibr::MAX_IMAGE_SIDE) return fail("image side above %d", dibr::MAX_IMAGE_SIDE);
     if (p->num_attr <= 0 || p->num_attr > DIBR_MAX_ATTR) return fail("num_attr=%d outside [1,%d]", p->num_attr, DIBR_MAX_ATTR);
     if (p->knum < 0 || p->knum > 250) return fail("knum=%d outside [0,250]", p->knum);
     if (p->multiplier <= 0 || p->delta < 0) return fail("bad multiplier/delta");
@@ -95,6 +96,7 @@ dibr::SetupParams setup_params(const DibrPass* p) {
     s.ws = carve(p, p->workspace);
     s.pose_R = p->pose_R; s.pose_t = p->pose_t; s.pose_K = p->pose_K; s.num_K = p->num_K;
     const double nc = p->znear, fc = p->zfar;
+    s.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     s.q = (float)(-(fc + nc) / (fc - nc));
     s.qn = (float)(-2.0 * (fc * nc) / (fc - nc));
     if (p->pose_R) { s.cam_rot = s.ws.cam_rot; s.cam_pos = s.ws.cam_pos; s.cam_proj = s.ws.cam_proj; }
@@ -166,10 +168,10 @@ int dibr_forward(const DibrPass* p, void* stream) {
     f.multiplier = p->multiplier; f.delta = p->delta;
     f.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     f.faces_per_image = p->faces_per_image; f.face_offsets = p->face_offsets;
-    f.recs = w.recs; f.bbox = w.bbox; f.imgbox = w.imgbox; f.face_attr = p->face_attr;
+    f.recs = w.recs; f.bins = w.bins; f.xs = w.xs; f.ys = w.ys; f.imgbox = w.imgbox; f.face_attr = p->face_attr;
     if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
     else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }
-    f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx; f.unc_blocks = w.unc_blocks;
+    f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
     f.list_counts = w.list_counts; f.face_flags = w.face_flags; f.color_list = w.color_list; f.soft_list = w.soft_list;
     {
         const size_t nbytes = (size_t)((char*)w.color_list - (char*)w.list_counts);
@@ -199,7 +201,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     b.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     b.total_faces = p->total_faces; b.faces_per_image = p->faces_per_image; b.face_offsets = p->face_offsets;
     b.recs = w.recs; b.xs = w.xs; b.ys = w.ys; b.face_attr = p->face_attr;
-    b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx; b.unc_blocks = w.unc_blocks;
+    b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx;
     b.list_counts = w.list_counts; b.color_list = w.color_list; b.soft_list = w.soft_list;
     if (p->num_outputs < 0 || p->num_outputs > DIBR_MAX_OUTPUTS) return fail("num_outputs=%d outside [0,%d]", p->num_outputs, DIBR_MAX_OUTPUTS);
     b.any_grad_im = 0;

@@ -9,18 +9,16 @@
 
 namespace dibr {
 
-constexpr int TILE = 32;            // forward CTA tile (pixels per side)
+constexpr int TILE = 16;            // forward CTA tile (pixels per side): one pixel per thread
 #ifndef DIBR_FWD_THREADS
-#define DIBR_FWD_THREADS 512
+#define DIBR_FWD_THREADS 256
 #endif
-constexpr int FWD_THREADS = DIBR_FWD_THREADS;   // threads per tile CTA (16 warps: the heaviest tiles set the kernel's tail)
-constexpr int LCAP = 1024;          // faces per in-shared-memory batch of a tile
-constexpr int SUB = 16;             // sub-tile side for the soft-silhouette lists
-constexpr int NSUB = (TILE / SUB) * (TILE / SUB);
-constexpr int SUBCAP = 512;         // entries per sub-tile list
-constexpr int BIGCAP = 64;          // deferred large faces per batch
-constexpr int BIG_AREA = 128;       // pixels of a face inside the tile above which the CTA cooperates
-constexpr int SCAN_CHUNK = FWD_THREADS;   // faces per TMA-staged bbox chunk (one per thread)
+constexpr int FWD_THREADS = DIBR_FWD_THREADS;   // threads per tile CTA (8 warps, one 8x4 pixel block each in the soft phase)
+constexpr int LCAP = 512;           // faces per in-shared-memory batch of a tile
+constexpr int BIGCAP = 32;          // deferred large faces per batch
+constexpr int BIG_AREA = 64;        // pixels of a face inside the tile above which the CTA cooperates
+static_assert(FWD_THREADS == TILE * TILE, "one pixel per thread");
+constexpr int MAX_IMAGE_SIDE = 16384;           // largest image side the ABI accepts
 
 // 64 B face record, written by the set-up kernels.
 struct __align__(16) FaceRec {
@@ -130,10 +128,26 @@ __device__ __forceinline__ SoftHit soft_distance(float x1, float y1, float x2, f
     return h;
 }
 
-// prob = exp(-z) and om = 1 - prob, both with full relative accuracy
+// prob = exp(-z) and om = 1 - prob, both with full relative accuracy, carried by ONE float: a value with the sign
+// bit clear is om (small z: alternating series, truncation < 2e-9 relative), one with the sign bit set is -prob.
+__device__ __forceinline__ float soft_prob_enc(float z) {
+    if (z < 0.25f) {
+        float t = fmaf(z, -1.0f / 7.0f, 1.0f);
+        t = fmaf(z * (-1.0f / 6.0f), t, 1.0f);
+        t = fmaf(z * (-1.0f / 5.0f), t, 1.0f);
+        t = fmaf(z * (-1.0f / 4.0f), t, 1.0f);
+        t = fmaf(z * (-1.0f / 3.0f), t, 1.0f);
+        t = fmaf(z * (-1.0f / 2.0f), t, 1.0f);
+        return z * t;
+    }
+    return __uint_as_float(__float_as_uint(expf(-z)) | 0x80000000u);
+}
+__device__ __forceinline__ void soft_prob_dec(float v, float& p, float& om) {
+    if (__float_as_int(v) < 0) { p = -v; om = 1.0f - p; }
+    else { om = v; p = 1.0f - om; }
+}
 __device__ __forceinline__ void soft_prob(float z, float& p, float& om) {
-    p = expf(-z);
-    om = (z < 0.25f) ? -expm1f(-z) : (1.0f - p);
+    soft_prob_dec(soft_prob_enc(z), p, om);
 }
 
 // ---------------------------------------------------------------------------------------------

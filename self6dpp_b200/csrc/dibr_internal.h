@@ -12,7 +12,8 @@ namespace dibr {
 // workspace carved out of DibrPass::workspace by dibr_abi.cu
 struct Workspace {
     FaceRec* recs;      // [total_faces]
-    float4* bbox;       // [total_faces]
+    uint32_t* bins;     // per image, per 16x16 tile: bitmap over the image's faces (bit = face may reach the tile); layout in bin_words()
+    size_t bins_bytes;
     uint4* imgbox;      // [batch]  ordered maxima of (-xmin,-ymin,xmax,ymax); 0 = empty
     float* xs;          // [width]  pixel-centre x
     float* ys;          // [height] pixel-centre y
@@ -24,7 +25,6 @@ struct Workspace {
     unsigned int* face_flags;   // [total_faces] bit0: won a pixel, bit1: evaluated for a soft pixel (zeroed by dibr_forward)
     int* color_list;    // [total_faces] global face ids that won at least one pixel (arbitrary order)
     int* soft_list;     // [total_faces] global face ids that entered at least one soft-silhouette product
-    unsigned short* unc_blocks;  // [batch, tiles_y, tiles_x] bit (by*4+bx): the 8x8 pixel block of the 32x32 tile holds an uncovered pixel
     size_t bytes;
 };
 
@@ -56,6 +56,7 @@ struct SetupParams {
     const float* pose_K;
     int num_K;
     float q, qn;             // -(f+n)/(f-n), -2fn/(f-n)
+    float expand_mul;        // expand * multiplier: the bins cover the EXPANDED bboxes
     Workspace ws;
 };
 
@@ -65,7 +66,9 @@ struct FwdParams {
     int faces_per_image;
     const int32_t* face_offsets;
     const FaceRec* recs;
-    const float4* bbox;
+    const uint32_t* bins;
+    const float* xs;           // [width], [height] pixel-centre tables
+    const float* ys;
     const uint4* imgbox;
     const float* face_attr;
     int n_out;                 // channel groups (>= 1)
@@ -74,7 +77,6 @@ struct FwdParams {
     float* improb;
     float* imcomp;
     int32_t* imidx;
-    unsigned short* unc_blocks;
     int* list_counts;
     unsigned int* face_flags;
     int* color_list;
@@ -95,7 +97,6 @@ struct BwdParams {
     const float* improb;
     const float* imcomp;
     const int32_t* imidx;
-    const unsigned short* unc_blocks;
     const int* list_counts;
     const int* color_list;
     const int* soft_list;
@@ -130,6 +131,15 @@ struct MeshBwdParams {
     float* grad_pose_R;
     float* grad_pose_t;
 };
+
+// Tile bins.  Image b owns the global 32-face words [f_lo >> 5, (f_hi - 1) >> 5]; its bitmaps start at word
+// tiles * ((f_lo >> 5) + b) (images never overlap: consecutive images share at most one boundary word, and the "+ b"
+// pays for it), one run of nw words per tile.  Total: tiles * (ceil(total_faces / 32) + batch + 1) words.
+struct BinGeom { int tiles_x, tiles_y; };
+__host__ __device__ inline size_t bin_total_words(int width, int height, int batch, int total_faces) {
+    const size_t tiles = (size_t)((width + TILE - 1) / TILE) * (size_t)((height + TILE - 1) / TILE);
+    return tiles * ((size_t)((total_faces + 31) / 32) + (size_t)batch + 1);
+}
 
 constexpr int INST_STRIDE = 12;
 // inst_desc columns

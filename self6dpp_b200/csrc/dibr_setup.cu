@@ -1,4 +1,4 @@
-// Face set-up kernels: build the 64 B face records + bbox array the forward/backward kernels read.
+// Face set-up kernels: build the 64 B face records and the per-tile face bitmaps the forward/backward kernels read.
 //
 //   setup_faces_kernel   operator-seam mode: inputs are the reference's points3d_bxfx9 /
 //                        points2d_bxfx6 / normalz_bxfx1; replaces prepare_tfpoints
@@ -43,6 +43,32 @@ __device__ __forceinline__ void write_tables(const SetupParams& P, int gtid) {
     else if (gtid < P.width + P.height) P.ws.ys[gtid - P.width] = pix_y(gtid - P.width, P.height, P.multiplier);
 }
 
+// Tile binning: set the face's bit in the bitmap of every 16x16 tile its EXPANDED bbox can reach (conservative: one
+// pixel of slack on every side).  Pixel column of x is x W/(2m) + (W-1)/2, pixel row of y is (H-1)/2 - y H/(2m)
+// (inverse of pix_x / pix_y).  Bitmaps instead of lists: OR is order independent, so the forward kernel reads the
+// faces of a tile in ascending order without any sort, and the result is the same run to run.
+__device__ __forceinline__ void bin_face(const SetupParams& P, int g, int b, float xmin, float ymin, float xmax, float ymax) {
+    const float ex = P.expand_mul;
+    const float sx = 0.5f * (float)P.width / (float)P.multiplier, sy = 0.5f * (float)P.height / (float)P.multiplier;
+    const float hw = 0.5f * (float)(P.width - 1), hh = 0.5f * (float)(P.height - 1);
+    const float lim = 1.0e6f;
+    const int cmin = (int)fminf(fmaxf(floorf(fmaf(xmin - ex, sx, hw)) - 1.0f, -lim), lim);
+    const int cmax = (int)fminf(fmaxf(ceilf(fmaf(xmax + ex, sx, hw)) + 1.0f, -lim), lim);
+    const int rmin = (int)fminf(fmaxf(floorf(fmaf(-(ymax + ex), sy, hh)) - 1.0f, -lim), lim);
+    const int rmax = (int)fminf(fmaxf(ceilf(fmaf(-(ymin - ex), sy, hh)) + 1.0f, -lim), lim);
+    if (cmax < 0 || rmax < 0 || cmin >= P.width || rmin >= P.height) return;
+    const int tiles_x = (P.width + TILE - 1) / TILE, tiles_y = (P.height + TILE - 1) / TILE;
+    const int tx0 = max(cmin, 0) / TILE, tx1 = min(cmax, P.width - 1) / TILE;
+    const int ty0 = max(rmin, 0) / TILE, ty1 = min(rmax, P.height - 1) / TILE;
+    const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
+    const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
+    const int w0 = f_lo >> 5, nw = ((f_hi - 1) >> 5) - w0 + 1;
+    uint32_t* img = P.ws.bins + (size_t)tiles_x * tiles_y * ((size_t)w0 + b) + ((g >> 5) - w0);
+    const uint32_t bit = 1u << (g & 31);
+    for (int ty = ty0; ty <= ty1; ty++)
+        for (int tx = tx0; tx <= tx1; tx++) atomicOr(img + (size_t)(ty * tiles_x + tx) * nw, bit);
+}
+
 __device__ __forceinline__ void store_face(const SetupParams& P, int g, int b, float ax, float ay, float bx, float by,
                                            float cx, float cy, float az, float bz, float cz, float nz, bool active)
 {
@@ -59,7 +85,7 @@ __device__ __forceinline__ void store_face(const SetupParams& P, int g, int b, f
         r.az = az; r.bz = bz; r.cz = cz; r.nz = nz; r.pad0 = 0.f; r.pad1 = 0.f;
         r.xmin = xmin; r.ymin = ymin; r.xmax = xmax; r.ymax = ymax;
         P.ws.recs[g] = r;
-        P.ws.bbox[g] = make_float4(xmin, ymin, xmax, ymax);
+        if (ok) bin_face(P, g, b, xmin, ymin, xmax, ymax);
     }
     image_box_update(P.ws.imgbox, active ? b : -1, ok, xmin, ymin, xmax, ymax);
 }
@@ -213,6 +239,8 @@ int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
 {
     cudaError_t e = cudaMemsetAsync(P.ws.imgbox, 0, sizeof(uint4) * (size_t)P.batch, stream);
     if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(P.ws.bins, 0, P.ws.bins_bytes, stream);
+    if (e != cudaSuccess) return (int)e;
     setup_faces_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
     return (int)cudaGetLastError();
 }
@@ -220,6 +248,8 @@ int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
 {
     cudaError_t e = cudaMemsetAsync(P.ws.imgbox, 0, sizeof(uint4) * (size_t)P.batch, stream);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(P.ws.bins, 0, P.ws.bins_bytes, stream);
     if (e != cudaSuccess) return (int)e;
     if (P.pose_R) {
         const int n = max(P.num_instances, P.num_K);

@@ -65,5 +65,28 @@ def src(fname, ln):
             L = src_cache[p]
             return L[ln - 1].strip()[:100] if 0 < ln <= len(L) else ""
     return ""
-for key, (s, i, t) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
+for key, (s, i, t) in sorted(agg.items(), key=lambda kv: -kv[1][1 if "--by-inst" in sys.argv else 0])[:topn]:
     print(f"{key[0]:20s}:{key[1]:4d} samp {100*s/max(tot_s,1):5.1f}% inst {100*i/max(tot_i,1):5.1f}% thr/inst {t/max(i,1):5.1f} | {src(*key)}")
+
+# ---- per-phase view for the forward kernel: helper lines (inlined .cuh code) inherit the phase of the nearest
+# preceding dibr_forward.cu line in address order
+if "--phases" in sys.argv:
+    bounds = [(112, 175, "A scan"), (176, 212, "A gather"), (214, 290, "B raster"), (292, 323, "zero/fill"), (325, 370, "prologue+untouched"),
+              (371, 392, "tile setup"), (393, 414, "batch loop"), (415, 528, "C resolve"), (529, 552, "D setup"), (553, 612, "D collect"),
+              (613, 653, "D evaluate"), (654, 666, "D fold"), (667, 680, "D marks")]
+    def phase_of(ln):
+        for a, b, n in bounds:
+            if a <= ln <= b:
+                return n
+        return "other"
+    cur = "other"
+    pagg = collections.defaultdict(lambda: [0.0, 0.0])
+    for d in body:
+        off = int(d["Address"], 16) - base
+        (fname, ln), _ = lines.get(off, (("?", 0), ""))
+        if fname == "dibr_forward.cu":
+            cur = phase_of(ln)
+        pagg[cur][0] += num(d["# Samples"]); pagg[cur][1] += num(d["Instructions Executed"])
+    print("phase view:")
+    for k, (s, i) in sorted(pagg.items(), key=lambda kv: -kv[1][0]):
+        print(f"  {k:18s} samples {100*s/max(tot_s,1):5.1f}%  warp-instr {100*i/max(tot_i,1):5.1f}%")

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Debug: build variant libraries with -D switches (on the GPU box) and time dibr_forward_kernel with each.
+usage: variants.py NAME=-DFLAG1,-DFLAG2 ...   (NAME 'base' = no flags); add :phase to a name to print phase cycles"""
+import sys, os, subprocess, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+csrc = os.path.join(ROOT, "self6dpp_b200", "csrc")
+specs = [a.split("=", 1) if "=" in a else [a, ""] for a in sys.argv[1:]] or [["base", ""]]
+child = os.environ.get("DIBR_VARIANT_LIB")
+if child:
+    from self6dpp_b200 import _lib
+    _lib.LIB_PATH = child
+    import torch, bench
+    from self6dpp_b200 import Renderer_dibr
+    from self6dpp_b200.bench_util import time_forward_kernel
+    dev = torch.device("cuda:0")
+    meshes, student, teacher = bench.workload(0)
+    models = [{"vertices": torch.tensor(m["vertices"], device=dev), "colors": torch.tensor(m["colors"], device=dev),
+               "normals": torch.tensor(m["normals"], device=dev), "faces": torch.tensor(m["faces"], device=dev, dtype=torch.int32)} for m in meshes]
+    cur = [models[int(i)] for i in student["ids"]]
+    ren = Renderer_dibr(256, 256, "VertexColorBatch")
+    dev_in = {k: torch.tensor(student[k], device=dev) for k in ("Rs", "ts", "Ks")}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+    phase = os.environ.get("DIBR_VARIANT_PHASE") == "1"
+    buf = (ctypes.c_ulonglong * 8)()
+    if phase:
+        lib.dibr_debug_phase_cycles(buf, 1)
+    reps = 20
+    ms = time_forward_kernel(ren, dev_in, cur, ["color", "depth", "mask", "norm", "prob"], 256, flush, reps=reps)
+    print("%-28s forward kernel %.1f us" % (os.environ["DIBR_VARIANT_NAME"], ms * 1e3), flush=True)
+    if phase:
+        lib.dibr_debug_phase_cycles(buf, 1)
+        n = buf[7]
+        names = ["setup", "scan+gather", "raster", "resolve", "soft"]
+        print("   touched CTAs per launch %.0f" % (n / (reps + 4)))
+        tot = sum(buf[:5])
+        for k in range(5):
+            print("   %-12s %8.0f cycles/CTA  %5.1f%%" % (names[k], buf[k] / max(n, 1), 100.0 * buf[k] / max(tot, 1)))
+    sys.exit(0)
+for name, flags in specs:
+    phase = name.endswith(":phase")
+    name = name.replace(":phase", "")
+    fl = [f for f in flags.split(",") if f] + (["-DDIBR_PHASE_TIMING"] if phase else [])
+    out = os.path.join(ROOT, "self6dpp_b200", "lib", f"libdibr_b200_{name}.so")
+    cmd = ["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+           "--expt-relaxed-constexpr", "-shared", "-cudart", "static", "-o", out] + fl + \
+          [os.path.join(csrc, f) for f in ("dibr_abi.cu", "dibr_setup.cu", "dibr_forward.cu", "dibr_backward.cu", "dibr_nnd.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        print(name, "BUILD FAILED", r.stderr[-2000:]); continue
+    env = dict(os.environ, DIBR_VARIANT_LIB=out, DIBR_VARIANT_NAME=name + " " + " ".join(fl), DIBR_VARIANT_PHASE="1" if phase else "0")
+    subprocess.run([sys.executable, os.path.abspath(__file__)], env=env)
+    os.remove(out)
