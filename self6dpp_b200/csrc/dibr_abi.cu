@@ -35,6 +35,11 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     w.recs = (dibr::FaceRec*)take(sizeof(dibr::FaceRec) * (size_t)p->total_faces);
     w.bins_bytes = sizeof(uint32_t) * dibr::bin_total_words(p->width, p->height, p->batch, p->total_faces);
     w.bins = (uint32_t*)take(w.bins_bytes);
+    {
+        const size_t ntiles = (size_t)p->batch * ((p->height + dibr::TILE - 1) / dibr::TILE) * ((p->width + dibr::TILE - 1) / dibr::TILE);
+        w.order_cnt = (int*)take(sizeof(int) * dibr::ORDER_BUCKETS);
+        w.order_seg = (int*)take(sizeof(int) * dibr::ORDER_BUCKETS * ntiles);
+    }
     w.imgbox = (uint4*)take(sizeof(uint4) * (size_t)p->batch);
     w.xs = (float*)take(sizeof(float) * (size_t)p->width);
     w.ys = (float*)take(sizeof(float) * (size_t)p->height);
@@ -138,7 +143,7 @@ int dibr_setup_faces(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
     if (!p->points3d || !p->points2d || !p->normalz) return fail("setup_faces: points3d/points2d/normalz required");
     const dibr::SetupParams s = setup_params(p);
-    g_launches += 1;
+    g_launches += 2;
     return cuda_fail("dibr_setup_faces", dibr::launch_setup_faces(s, (cudaStream_t)stream));
 }
 
@@ -153,7 +158,7 @@ int dibr_setup_meshes(const DibrPass* p, void* stream) {
     if (d != p->num_attr) return fail("setup_meshes: vert_attr_dim + flags = %d but num_attr = %d", d, p->num_attr);
     if (p->vert_attr_dim > 0 && !p->vert_attr) return fail("setup_meshes: vert_attr is null");
     const dibr::SetupParams s = setup_params(p);
-    g_launches += p->pose_R ? 2 : 1;
+    g_launches += p->pose_R ? 3 : 2;
     return cuda_fail("dibr_setup_meshes", dibr::launch_setup_meshes(s, (cudaStream_t)stream));
 }
 
@@ -168,7 +173,7 @@ int dibr_forward(const DibrPass* p, void* stream) {
     f.multiplier = p->multiplier; f.delta = p->delta;
     f.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     f.faces_per_image = p->faces_per_image; f.face_offsets = p->face_offsets;
-    f.recs = w.recs; f.bins = w.bins; f.xs = w.xs; f.ys = w.ys; f.imgbox = w.imgbox; f.face_attr = p->face_attr;
+    f.recs = w.recs; f.bins = w.bins; f.order_cnt = w.order_cnt; f.order_seg = w.order_seg; f.xs = w.xs; f.ys = w.ys; f.imgbox = w.imgbox; f.face_attr = p->face_attr;
     if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
     else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }
     f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;

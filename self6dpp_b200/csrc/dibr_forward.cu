@@ -332,14 +332,35 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
     FwdSmem& s = *reinterpret_cast<FwdSmem*>(smem_raw);
     const unsigned full_mask = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.z;
-    const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
+    // ---- which tile: the plan (set-up: plan_tiles_kernel) lists the tiles by cost bucket, heaviest first
+    const int tiles_x = (P.width + TILE - 1) / TILE, tiles_y = (P.height + TILE - 1) / TILE;
+    const int ntiles = tiles_x * tiles_y * P.batch;
+    int tile, bucket;
+    {
+        // lane k looks at bucket 31-k: one load each, a warp scan finds the bucket that holds position blockIdx.x
+        static_assert(ORDER_BUCKETS == 32, "one bucket per lane");
+        const int n = __ldg(P.order_cnt + (ORDER_BUCKETS - 1 - lane));
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(full_mask, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned past = __ballot_sync(full_mask, incl > (int)blockIdx.x);       // non-empty: the grid is the tile count
+        const int src = __ffs(past) - 1;
+        bucket = ORDER_BUCKETS - 1 - src;
+        const int before = __shfl_sync(full_mask, incl - n, src);
+        tile = __ldg(P.order_seg + (size_t)bucket * ntiles + ((int)blockIdx.x - before));
+    }
+    const int b = tile / (tiles_x * tiles_y);
+    const int tile_in = tile - b * (tiles_x * tiles_y);
+    const int tile_y = tile_in / tiles_x, tile_x = tile_in - tile_y * tiles_x;
+    const int tx0 = tile_x * TILE, ty0 = tile_y * TILE;
     TileGeom T;
     T.tw = min(TILE, P.width - tx0); T.th = min(TILE, P.height - ty0);
     const int tw = T.tw, th = T.th;
     const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
     const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
-    const int fnum = f_hi - f_lo;
     const int D = P.num_attr;
     const size_t img_pix = (size_t)b * P.height * P.width;
     float* __restrict__ improb = P.improb + img_pix;
@@ -347,16 +368,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
     int* __restrict__ imidx = P.imidx + img_pix;
     const float ex = P.expand_mul;
 
-    // ---- whole-image cull (imgbox: ordered maxima of (-xmin,-ymin,xmax,ymax) over the image's faces) ----------
-    bool touched = false;
-    if (fnum > 0) {
-        const float t_xlo = __ldg(P.xs + tx0), t_xhi = __ldg(P.xs + tx0 + tw - 1);
-        const float t_yhi = __ldg(P.ys + ty0), t_ylo = __ldg(P.ys + ty0 + th - 1);
-        const uint4 ib = P.imgbox[b];
-        const float ixmin = -ord2f(ib.x), iymin = -ord2f(ib.y), ixmax = ord2f(ib.z), iymax = ord2f(ib.w);
-        touched = (ib.z != 0u) && (ixmin - ex <= t_xhi) && (ixmax + ex > t_xlo) && (iymin - ex <= t_yhi) && (iymax + ex > t_ylo);
-    }
-    if (!touched) { fill_untouched(P, img_pix, tx0, ty0, tw, th); return; }
+    if (bucket == 0) { fill_untouched(P, img_pix, tx0, ty0, tw, th); return; }      // empty bitmap: nothing near this tile
 
 #ifdef DIBR_PHASE_TIMING
     long long t_phase = clock64();
@@ -378,7 +390,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         const int w0 = f_lo >> 5;
         T.nw = ((f_hi - 1) >> 5) - w0 + 1;
         T.id0 = (w0 << 5) - f_lo;
-        T.words = P.bins + (size_t)gridDim.x * gridDim.y * ((size_t)w0 + b) + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * T.nw;
+        T.words = P.bins + (size_t)tiles_x * tiles_y * ((size_t)w0 + b) + (size_t)tile_in * T.nw;
     }
     __syncthreads();
 
@@ -388,7 +400,6 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         PHASE_MARK(0);
         while (wpos < T.nw) {
             wpos = fill_list(s, P, f_lo, wpos, T, true, parity);
-            if (nbatch == 0 && s.lcount == 0 && wpos >= T.nw) { fill_untouched(P, img_pix, tx0, ty0, tw, th); return; }     // inside the image's box, but no face near
             PHASE_MARK(1);
             const int lcount = s.lcount;
             if (s.rcount > 0) raster_list(s, nprev);
@@ -705,8 +716,8 @@ int launch_forward(const FwdParams& P, cudaStream_t stream)
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    dim3 grid((P.width + TILE - 1) / TILE, (P.height + TILE - 1) / TILE, P.batch);
-    dibr_forward_kernel<<<grid, FWD_THREADS, smem, stream>>>(P);
+    const int ntiles = ((P.width + TILE - 1) / TILE) * ((P.height + TILE - 1) / TILE) * P.batch;
+    dibr_forward_kernel<<<ntiles, FWD_THREADS, smem, stream>>>(P);
     return (int)cudaGetLastError();
 }
 

@@ -14,6 +14,8 @@ struct Workspace {
     FaceRec* recs;      // [total_faces]
     uint32_t* bins;     // per image, per 16x16 tile: bitmap over the image's faces (bit = face may reach the tile); layout in bin_words()
     size_t bins_bytes;
+    int* order_cnt;     // [ORDER_BUCKETS] tiles per cost bucket (bucket = ceil(listed faces / 32), capped)
+    int* order_seg;     // [ORDER_BUCKETS, batch * tiles] tile ids of each bucket: the forward kernel works heaviest bucket first
     uint4* imgbox;      // [batch]  ordered maxima of (-xmin,-ymin,xmax,ymax); 0 = empty
     float* xs;          // [width]  pixel-centre x
     float* ys;          // [height] pixel-centre y
@@ -67,6 +69,8 @@ struct FwdParams {
     const int32_t* face_offsets;
     const FaceRec* recs;
     const uint32_t* bins;
+    const int* order_cnt;
+    const int* order_seg;
     const float* xs;           // [width], [height] pixel-centre tables
     const float* ys;
     const uint4* imgbox;
@@ -135,7 +139,7 @@ struct MeshBwdParams {
 // Tile bins.  Image b owns the global 32-face words [f_lo >> 5, (f_hi - 1) >> 5]; its bitmaps start at word
 // tiles * ((f_lo >> 5) + b) (images never overlap: consecutive images share at most one boundary word, and the "+ b"
 // pays for it), one run of nw words per tile.  Total: tiles * (ceil(total_faces / 32) + batch + 1) words.
-struct BinGeom { int tiles_x, tiles_y; };
+constexpr int ORDER_BUCKETS = 32;
 __host__ __device__ inline size_t bin_total_words(int width, int height, int batch, int total_faces) {
     const size_t tiles = (size_t)((width + TILE - 1) / TILE) * (size_t)((height + TILE - 1) / TILE);
     return tiles * ((size_t)((total_faces + 31) / 32) + (size_t)batch + 1);

@@ -230,6 +230,35 @@ __global__ void pose_to_camera_kernel(SetupParams P)
     }
 }
 
+// Work plan of the forward kernel: tiles bucketed by how many faces their bitmap lists (one warp per tile).  The
+// forward kernel takes the buckets heaviest first, so the long tiles start early and the short ones fill the tail.
+__global__ void __launch_bounds__(256) plan_tiles_kernel(SetupParams P)
+{
+    const int tiles = ((P.width + TILE - 1) / TILE) * ((P.height + TILE - 1) / TILE);
+    const int ntiles = tiles * P.batch;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= ntiles) return;
+    const int b = t / tiles, tl = t - b * tiles;
+    const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
+    const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
+    const int w0 = f_lo >> 5, nw = ((f_hi - 1) >> 5) - w0 + 1;
+    const uint32_t* words = P.ws.bins + (size_t)tiles * ((size_t)w0 + b) + (size_t)tl * nw;
+    int cost = 0;
+    for (int w = lane; w < nw; w += 32) cost += __popc(__ldg(words + w));
+    cost = __reduce_add_sync(0xffffffffu, cost);
+    if (lane == 0) {
+        const int kb = min((cost + 31) >> 5, ORDER_BUCKETS - 1);
+        const int pos = atomicAdd(&P.ws.order_cnt[kb], 1);
+        P.ws.order_seg[(size_t)kb * ntiles + pos] = t;
+    }
+}
+
+static inline int launch_plan(const SetupParams& P, cudaStream_t stream) {
+    const int ntiles = ((P.width + TILE - 1) / TILE) * ((P.height + TILE - 1) / TILE) * P.batch;
+    plan_tiles_kernel<<<(ntiles + 7) / 8, 256, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
 static inline int setup_grid(const SetupParams& P) {
     const int n = max(P.total_faces, P.width + P.height);
     return (n + 255) / 256;
@@ -241,8 +270,12 @@ int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(P.ws.bins, 0, P.ws.bins_bytes, stream);
     if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(P.ws.order_cnt, 0, sizeof(int) * ORDER_BUCKETS, stream);
+    if (e != cudaSuccess) return (int)e;
     setup_faces_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
-    return (int)cudaGetLastError();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    return launch_plan(P, stream);
 }
 
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
@@ -257,8 +290,12 @@ int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
+    e = cudaMemsetAsync(P.ws.order_cnt, 0, sizeof(int) * ORDER_BUCKETS, stream);
+    if (e != cudaSuccess) return (int)e;
     setup_meshes_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
-    return (int)cudaGetLastError();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    return launch_plan(P, stream);
 }
 
 }  // namespace dibr
