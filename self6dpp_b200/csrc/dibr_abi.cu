@@ -60,6 +60,7 @@ int check_common(const DibrPass* p, bool need_ws) {
     if (!p) return fail("null DibrPass");
     if (p->batch <= 0 || p->height <= 0 || p->width <= 0) return fail("bad image size b=%d h=%d w=%d", p->batch, p->height, p->width);
     if (p->height > dibr::MAX_IMAGE_SIDE || p->width > dibr::MAX_IMAGE_SIDE) return fail("image side above %d", dibr::MAX_IMAGE_SIDE);
+    if (p->batch > 4096) return fail("batch above 4096");
     if (p->num_attr <= 0 || p->num_attr > DIBR_MAX_ATTR) return fail("num_attr=%d outside [1,%d]", p->num_attr, DIBR_MAX_ATTR);
     if (p->knum < 0 || p->knum > 250) return fail("knum=%d outside [0,250]", p->knum);
     if (p->multiplier <= 0 || p->delta < 0) return fail("bad multiplier/delta");

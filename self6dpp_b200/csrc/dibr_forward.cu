@@ -281,48 +281,60 @@ __device__ void raster_list(FwdSmem& s, int nprev)
     __syncthreads();
 }
 
-// fill a full 16x16 tile of one [H,W,CH] image with 128-bit stores: at most one store per thread
+// One WARP fills a 16x16 tile of one [H,W,CH] image: 128-bit stores, 2*CH per lane
 template <int CH>
-__device__ __forceinline__ void fill_full_tile(float* __restrict__ img, int width, int tx0, int ty0, float val)
+__device__ __forceinline__ void fill_full_tile_warp(float* __restrict__ img, int width, int tx0, int ty0, float val)
 {
     constexpr int RV = TILE * CH / 4;                    // float4 per tile row
-    static_assert(TILE * RV <= FWD_THREADS, "one store per thread");
-    const int i = threadIdx.x;
-    if (i < TILE * RV) {
+    const int lane = threadIdx.x & 31;
+    const float4 v = make_float4(val, val, val, val);
+#pragma unroll
+    for (int i0 = 0; i0 < TILE * RV; i0 += 32) {
+        const int i = i0 + lane;
         const int r = i / RV, c = i - r * RV;
-        reinterpret_cast<float4*>(img + ((size_t)(ty0 + r) * width + tx0) * CH)[c] = make_float4(val, val, val, val);
+        reinterpret_cast<float4*>(img + ((size_t)(ty0 + r) * width + tx0) * CH)[c] = v;
     }
 }
 
-// fill rows [0,th) x [0,tw) of one [H,W,ch] image tile with `val`
-__device__ __forceinline__ void fill_tile(float* __restrict__ img, int width, int ch, int tx0, int ty0, int tw, int th, float val)
+// one warp fills rows [0,th) x [0,tw) of one [H,W,ch] image tile with `val`
+__device__ __forceinline__ void fill_tile_warp(float* __restrict__ img, int width, int ch, int tx0, int ty0, int tw, int th, float val)
 {
     const bool aligned = (((size_t)width * ch) & 3) == 0 && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
     if (tw == TILE && th == TILE && aligned && ch <= 4) {          // tx0 is a multiple of 16: rows start 16 B aligned
         switch (ch) {
-            case 1: fill_full_tile<1>(img, width, tx0, ty0, val); return;
-            case 2: fill_full_tile<2>(img, width, tx0, ty0, val); return;
-            case 3: fill_full_tile<3>(img, width, tx0, ty0, val); return;
-            default: fill_full_tile<4>(img, width, tx0, ty0, val); return;
+            case 1: fill_full_tile_warp<1>(img, width, tx0, ty0, val); return;
+            case 2: fill_full_tile_warp<2>(img, width, tx0, ty0, val); return;
+            case 3: fill_full_tile_warp<3>(img, width, tx0, ty0, val); return;
+            default: fill_full_tile_warp<4>(img, width, tx0, ty0, val); return;
         }
     }
     const int rowf = tw * ch;
-    for (int i = threadIdx.x; i < th * rowf; i += FWD_THREADS) {
+    for (int i = threadIdx.x & 31; i < th * rowf; i += 32) {
         const int r = i / rowf;
         img[((size_t)(ty0 + r) * width + tx0) * ch + (i - r * rowf)] = val;
     }
 }
 
-// nothing near this tile: zeros everywhere (imcomp = 1: empty product)
-__device__ __noinline__ void fill_untouched(const FwdParams& P, size_t img_pix, int tx0, int ty0, int tw, int th)
+// tile ids of the plan: image | tile row | tile column
+__device__ __forceinline__ void unpack_tile(int packed, int& b, int& ty, int& tx) {
+    b = (int)((unsigned)packed >> 20); ty = (packed >> 10) & 1023; tx = packed & 1023;
+}
+
+// nothing near this tile: zeros everywhere (imcomp = 1: empty product).  One warp per tile.
+__device__ __noinline__ void fill_untouched_warp(const FwdParams& P, int packed_tile)
 {
+    int b, ty, tx;
+    unpack_tile(packed_tile, b, ty, tx);
+    const int tx0 = tx * TILE, ty0 = ty * TILE;
+    const int tw = min(TILE, P.width - tx0), th = min(TILE, P.height - ty0);
+    const size_t img_pix = (size_t)b * P.height * P.width;
 #ifndef DIBR_X_NO_OUTMIN
-    if (threadIdx.x == 0 && P.min_group >= 0) atomicMin(P.out_min, f2ord(0.0f));
+    if ((threadIdx.x & 31) == 0 && P.min_group >= 0) atomicMin(P.out_min, f2ord(0.0f));
 #endif
-    for (int g = 0; g < P.n_out; g++) fill_tile(P.out[g] + img_pix * P.out_ch[g], P.width, P.out_ch[g], tx0, ty0, tw, th, 0.0f);
-    fill_tile(P.improb + img_pix, P.width, 1, tx0, ty0, tw, th, 0.0f);
-    fill_tile(reinterpret_cast<float*>(P.imidx + img_pix), P.width, 1, tx0, ty0, tw, th, 0.0f);
-    fill_tile(P.imcomp + img_pix, P.width, 1, tx0, ty0, tw, th, 1.0f);
+    for (int g = 0; g < P.n_out; g++) fill_tile_warp(P.out[g] + img_pix * P.out_ch[g], P.width, P.out_ch[g], tx0, ty0, tw, th, 0.0f);
+    fill_tile_warp(P.improb + img_pix, P.width, 1, tx0, ty0, tw, th, 0.0f);
+    fill_tile_warp(reinterpret_cast<float*>(P.imidx + img_pix), P.width, 1, tx0, ty0, tw, th, 0.0f);
+    fill_tile_warp(P.imcomp + img_pix, P.width, 1, tx0, ty0, tw, th, 1.0f);
 }
 
 __global__ void __launch_bounds__(FWD_THREADS, 1024 / FWD_THREADS)
@@ -332,12 +344,12 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
     FwdSmem& s = *reinterpret_cast<FwdSmem*>(smem_raw);
     const unsigned full_mask = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // ---- which tile: the plan (set-up: plan_tiles_kernel) lists the tiles by cost bucket, heaviest first
+    // ---- which tile: the plan (set-up: plan_tiles_kernel) lists the tiles by cost bucket, heaviest first.  Lane k
+    //      looks at bucket 31-k: one load each, a warp scan finds the bucket that holds position blockIdx.x.
     const int tiles_x = (P.width + TILE - 1) / TILE, tiles_y = (P.height + TILE - 1) / TILE;
     const int ntiles = tiles_x * tiles_y * P.batch;
-    int tile, bucket;
+    int tile;
     {
-        // lane k looks at bucket 31-k: one load each, a warp scan finds the bucket that holds position blockIdx.x
         static_assert(ORDER_BUCKETS == 32, "one bucket per lane");
         const int n = __ldg(P.order_cnt + (ORDER_BUCKETS - 1 - lane));
         int incl = n;
@@ -346,15 +358,21 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
             const int t = __shfl_up_sync(full_mask, incl, o);
             if (lane >= o) incl += t;
         }
-        const unsigned past = __ballot_sync(full_mask, incl > (int)blockIdx.x);       // non-empty: the grid is the tile count
+        const int touched = __shfl_sync(full_mask, incl, 30);                           // tiles of buckets 31..1
+        if ((int)blockIdx.x >= touched) {
+            // bucket 0 (empty bitmaps): one warp per tile, 8 tiles per CTA; the surplus CTAs of the grid leave at once
+            const int j = ((int)blockIdx.x - touched) * NWARP + warp;
+            if (j < __shfl_sync(full_mask, n, 31)) fill_untouched_warp(P, __ldg(P.order_seg + j));
+            return;
+        }
+        const unsigned past = __ballot_sync(full_mask, incl > (int)blockIdx.x);
         const int src = __ffs(past) - 1;
-        bucket = ORDER_BUCKETS - 1 - src;
         const int before = __shfl_sync(full_mask, incl - n, src);
-        tile = __ldg(P.order_seg + (size_t)bucket * ntiles + ((int)blockIdx.x - before));
+        tile = __ldg(P.order_seg + (size_t)(ORDER_BUCKETS - 1 - src) * ntiles + ((int)blockIdx.x - before));
     }
-    const int b = tile / (tiles_x * tiles_y);
-    const int tile_in = tile - b * (tiles_x * tiles_y);
-    const int tile_y = tile_in / tiles_x, tile_x = tile_in - tile_y * tiles_x;
+    int b, tile_y, tile_x;
+    unpack_tile(tile, b, tile_y, tile_x);
+    const int tile_in = tile_y * tiles_x + tile_x;
     const int tx0 = tile_x * TILE, ty0 = tile_y * TILE;
     TileGeom T;
     T.tw = min(TILE, P.width - tx0); T.th = min(TILE, P.height - ty0);
@@ -368,7 +386,6 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
     int* __restrict__ imidx = P.imidx + img_pix;
     const float ex = P.expand_mul;
 
-    if (bucket == 0) { fill_untouched(P, img_pix, tx0, ty0, tw, th); return; }      // empty bitmap: nothing near this tile
 
 #ifdef DIBR_PHASE_TIMING
     long long t_phase = clock64();

@@ -71,8 +71,8 @@ for key, (s, i, t) in sorted(agg.items(), key=lambda kv: -kv[1][1 if "--by-inst"
 # ---- per-phase view for the forward kernel: helper lines (inlined .cuh code) inherit the phase of the nearest
 # preceding dibr_forward.cu line in address order
 if "--phases" in sys.argv:
-    bounds = [(112, 175, "A scan"), (176, 212, "A gather"), (214, 290, "B raster"), (292, 323, "zero/fill"), (325, 370, "prologue+untouched"),
-              (371, 392, "tile setup"), (393, 414, "batch loop"), (415, 528, "C resolve"), (529, 552, "D setup"), (553, 612, "D collect"),
+    bounds = [(112, 168, "A bitmap"), (169, 205, "A gather"), (206, 283, "B raster"), (284, 326, "fill"), (328, 376, "prologue"),
+              (377, 398, "tile setup"), (399, 421, "batch loop"), (422, 535, "C resolve"), (536, 571, "D setup+masks"), (572, 612, "D collect"),
               (613, 653, "D evaluate"), (654, 666, "D fold"), (667, 680, "D marks")]
     def phase_of(ln):
         for a, b, n in bounds:
