@@ -177,6 +177,11 @@ int dibr_forward(const DibrPass* p, void* stream) {
     f.recs = w.recs; f.bins = w.bins; f.order_cnt = w.order_cnt; f.order_seg = w.order_seg; f.xs = w.xs; f.ys = w.ys; f.imgbox = w.imgbox; f.face_attr = p->face_attr;
     if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
     else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }
+    {
+        int d = 0;
+        for (int g = 0; g < f.n_out; g++)
+            for (int c = 0; c < f.out_ch[g] && d < DIBR_MAX_ATTR_INTERNAL; c++, d++) { f.chan_out[d] = f.out[g] + c; f.chan_stride[d] = f.out_ch[g]; }
+    }
     f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
     f.list_counts = w.list_counts; f.face_flags = w.face_flags; f.color_list = w.color_list; f.soft_list = w.soft_list;
     {
@@ -188,6 +193,8 @@ int dibr_forward(const DibrPass* p, void* stream) {
     if (p->min_output >= 0 && p->out_min_ordered) {
         if (p->min_output >= f.n_out) return fail("forward: min_output=%d but only %d output groups", p->min_output, f.n_out);
         f.min_group = p->min_output; f.out_min = p->out_min_ordered;
+        for (int g = 0, d = 0; g < f.n_out; d += f.out_ch[g], g++)
+            if (g == f.min_group) f.min_mask = ((1u << f.out_ch[g]) - 1u) << d;
         cudaError_t e = cudaMemsetAsync(p->out_min_ordered, 0xff, sizeof(uint32_t), (cudaStream_t)stream);
         if (e != cudaSuccess) return cuda_fail("dibr_forward (reset min)", (int)e);
     }

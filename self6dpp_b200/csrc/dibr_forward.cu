@@ -470,6 +470,9 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         if (val) {
             const size_t gp = (size_t)(ty0 + ly) * P.width + (tx0 + lx);
             const size_t px = img_pix + gp;
+            float v[DIBR_MAX_ATTR_INTERNAL];
+#pragma unroll
+            for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) v[d] = 0.f;
             if (fw >= 0) {
                 FaceRec r;
                 r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
@@ -478,46 +481,41 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
                 float w0, w1, w2;
                 bary(fk, s.xs[lx], s.ys[ly], w0, w1, w2);
                 const float* a = fattr + (size_t)fw * 3 * D;
-                int base = 0;
-                for (int g = 0; g < P.n_out; g++) {
-                    const int ch = P.out_ch[g];
-                    float* o = P.out[g] + px * ch;
-                    if (ch == 4 && ((D | base) & 3) == 0) {
-                        const float4 r0 = __ldg(reinterpret_cast<const float4*>(a + base));
-                        const float4 r1 = __ldg(reinterpret_cast<const float4*>(a + D + base));
-                        const float4 r2 = __ldg(reinterpret_cast<const float4*>(a + 2 * D + base));
-                        float4 v;
-                        v.x = blend(w0, w1, w2, r0.x, r1.x, r2.x);
-                        v.y = blend(w0, w1, w2, r0.y, r1.y, r2.y);
-                        v.z = blend(w0, w1, w2, r0.z, r1.z, r2.z);
-                        v.w = blend(w0, w1, w2, r0.w, r1.w, r2.w);
-                        *reinterpret_cast<float4*>(o) = v;
-                        if (g == P.min_group) vmin = fminf(vmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
-                    } else {
-                        for (int c = 0; c < ch; c++) {
-                            const float v = blend(w0, w1, w2, __ldg(a + base + c), __ldg(a + D + base + c), __ldg(a + 2 * D + base + c));
-                            o[c] = v;
-                            if (g == P.min_group) vmin = fminf(vmin, v);
+                if ((D & 3) == 0) {                  // the three corner rows as 128-bit loads
+#pragma unroll
+                    for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d += 4) {
+                        if (d < D) {
+                            const float4 r0 = __ldg(reinterpret_cast<const float4*>(a + d));
+                            const float4 r1 = __ldg(reinterpret_cast<const float4*>(a + D + d));
+                            const float4 r2 = __ldg(reinterpret_cast<const float4*>(a + 2 * D + d));
+                            v[d] = blend(w0, w1, w2, r0.x, r1.x, r2.x);
+                            v[d + 1] = blend(w0, w1, w2, r0.y, r1.y, r2.y);
+                            v[d + 2] = blend(w0, w1, w2, r0.z, r1.z, r2.z);
+                            v[d + 3] = blend(w0, w1, w2, r0.w, r1.w, r2.w);
                         }
                     }
-                    base += ch;
+                } else {
+#pragma unroll
+                    for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++)
+                        if (d < D) v[d] = blend(w0, w1, w2, __ldg(a + d), __ldg(a + D + d), __ldg(a + 2 * D + d));
                 }
                 improb[gp] = 1.0f;
                 imcomp[gp] = 0.0f;
                 imidx[gp] = fw + 1;
                 s.cnt[ly * TILE + lx] = 255;
             } else {
-                for (int g = 0; g < P.n_out; g++) {
-                    const int ch = P.out_ch[g];
-                    float* o = P.out[g] + px * ch;
-                    if (ch == 4) *reinterpret_cast<float4*>(o) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    else for (int c = 0; c < ch; c++) o[c] = 0.f;
-                }
                 imidx[gp] = 0;                   // may be overwritten with the K-th face in phase D
                 improb[gp] = 0.0f;               // empty product; phase D overwrites the pixels it reaches
                 imcomp[gp] = 1.0f;
                 unc = true;
-                vmin = fminf(vmin, 0.0f);
+            }
+            // every channel goes to its own (tensor, slot): the tables unroll, no group loop at run time
+#pragma unroll
+            for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) {
+                if (d < D) {
+                    P.chan_out[d][px * P.chan_stride[d]] = v[d];
+                    if ((P.min_mask >> d) & 1u) vmin = fminf(vmin, v[d]);
+                }
             }
         }
         // append first-time winners to the colour list: one counter atomic per warp

@@ -78,6 +78,9 @@ struct FwdParams {
     int n_out;                 // channel groups (>= 1)
     int out_ch[6];
     float* out[6];             // [batch,H,W,out_ch[g]]
+    float* chan_out[DIBR_MAX_ATTR_INTERNAL];    // per attribute channel d: its output tensor, pre-offset by the channel's slot in the group
+    int chan_stride[DIBR_MAX_ATTR_INTERNAL];    // floats per pixel of that tensor
+    unsigned min_mask;         // channels of the output group whose batch-global minimum is accumulated
     float* improb;
     float* imcomp;
     int32_t* imidx;
