@@ -33,14 +33,13 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     char* b = (char*)base;
     auto take = [&](size_t bytes) { void* r = b ? (void*)(b + off) : nullptr; off += align_up(bytes, 256); return r; };
     w.recs = (dibr::FaceRec*)take(sizeof(dibr::FaceRec) * (size_t)p->total_faces);
-    w.bins_bytes = sizeof(uint32_t) * dibr::bin_total_words(p->width, p->height, p->batch, p->total_faces);
-    w.bins = (uint32_t*)take(w.bins_bytes);
     {
         const size_t ntiles = (size_t)p->batch * ((p->height + dibr::TILE - 1) / dibr::TILE) * ((p->width + dibr::TILE - 1) / dibr::TILE);
-        w.order_cnt = (int*)take(sizeof(int) * dibr::ORDER_BUCKETS);
         w.order_seg = (int*)take(sizeof(int) * dibr::ORDER_BUCKETS * ntiles);
+        w.order_cnt = (int*)take(sizeof(int) * dibr::ORDER_BUCKETS);       // directly before the bins: one memset clears both
     }
-    w.imgbox = (uint4*)take(sizeof(uint4) * (size_t)p->batch);
+    w.bins_bytes = sizeof(uint32_t) * dibr::bin_total_words(p->width, p->height, p->batch, p->total_faces);
+    w.bins = (uint32_t*)take(w.bins_bytes);
     w.xs = (float*)take(sizeof(float) * (size_t)p->width);
     w.ys = (float*)take(sizeof(float) * (size_t)p->height);
     w.pose_part = (float*)take(sizeof(float) * 12 * dibr::POSE_BLOCKS * (size_t)(p->num_instances > 0 ? p->num_instances : 0));
@@ -174,7 +173,7 @@ int dibr_forward(const DibrPass* p, void* stream) {
     f.multiplier = p->multiplier; f.delta = p->delta;
     f.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     f.faces_per_image = p->faces_per_image; f.face_offsets = p->face_offsets;
-    f.recs = w.recs; f.bins = w.bins; f.order_cnt = w.order_cnt; f.order_seg = w.order_seg; f.xs = w.xs; f.ys = w.ys; f.imgbox = w.imgbox; f.face_attr = p->face_attr;
+    f.recs = w.recs; f.bins = w.bins; f.order_cnt = w.order_cnt; f.order_seg = w.order_seg; f.xs = w.xs; f.ys = w.ys; f.face_attr = p->face_attr;
     if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
     else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }
     {

@@ -16,7 +16,6 @@ struct Workspace {
     size_t bins_bytes;
     int* order_cnt;     // [ORDER_BUCKETS] tiles per cost bucket (bucket = ceil(listed faces / 32), capped)
     int* order_seg;     // [ORDER_BUCKETS, batch * tiles] tile ids of each bucket: the forward kernel works heaviest bucket first
-    uint4* imgbox;      // [batch]  ordered maxima of (-xmin,-ymin,xmax,ymax); 0 = empty
     float* xs;          // [width]  pixel-centre x
     float* ys;          // [height] pixel-centre y
     float* pose_part;   // [num_instances * POSE_BLOCKS * 12] partial pose-gradient sums
@@ -73,7 +72,6 @@ struct FwdParams {
     const int* order_seg;
     const float* xs;           // [width], [height] pixel-centre tables
     const float* ys;
-    const uint4* imgbox;
     const float* face_attr;
     int n_out;                 // channel groups (>= 1)
     int out_ch[6];

@@ -20,24 +20,6 @@ __device__ __forceinline__ int image_of_face(int g, int batch, int faces_per_ima
     return lo;
 }
 
-// union of the faces' bboxes per image, as ordered maxima of (-xmin,-ymin,xmax,ymax)
-__device__ __forceinline__ void image_box_update(uint4* imgbox, int b, bool ok, float xmin, float ymin, float xmax, float ymax) {
-    uint32_t v0 = ok ? f2ord(-xmin) : 0u, v1 = ok ? f2ord(-ymin) : 0u, v2 = ok ? f2ord(xmax) : 0u, v3 = ok ? f2ord(ymax) : 0u;
-    const unsigned full = 0xffffffffu;
-    const int b0 = __shfl_sync(full, b, 0);
-    if (__all_sync(full, b == b0)) {
-        v0 = __reduce_max_sync(full, v0); v1 = __reduce_max_sync(full, v1);
-        v2 = __reduce_max_sync(full, v2); v3 = __reduce_max_sync(full, v3);
-        if ((threadIdx.x & 31) == 0 && b0 >= 0 && v2 != 0u) {
-            atomicMax(&imgbox[b0].x, v0); atomicMax(&imgbox[b0].y, v1);
-            atomicMax(&imgbox[b0].z, v2); atomicMax(&imgbox[b0].w, v3);
-        }
-    } else if (ok && b >= 0) {
-        atomicMax(&imgbox[b].x, v0); atomicMax(&imgbox[b].y, v1);
-        atomicMax(&imgbox[b].z, v2); atomicMax(&imgbox[b].w, v3);
-    }
-}
-
 __device__ __forceinline__ void write_tables(const SetupParams& P, int gtid) {
     if (gtid < P.width) P.ws.xs[gtid] = pix_x(gtid, P.width, P.multiplier);
     else if (gtid < P.width + P.height) P.ws.ys[gtid - P.width] = pix_y(gtid - P.width, P.height, P.multiplier);
@@ -87,7 +69,6 @@ __device__ __forceinline__ void store_face(const SetupParams& P, int g, int b, f
         P.ws.recs[g] = r;
         if (ok) bin_face(P, g, b, xmin, ymin, xmax, ymax);
     }
-    image_box_update(P.ws.imgbox, active ? b : -1, ok, xmin, ymin, xmax, ymax);
 }
 
 __global__ void __launch_bounds__(256) setup_faces_kernel(SetupParams P)
@@ -285,11 +266,8 @@ static inline int setup_grid(const SetupParams& P) {
 
 int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
 {
-    cudaError_t e = cudaMemsetAsync(P.ws.imgbox, 0, sizeof(uint4) * (size_t)P.batch, stream);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(P.ws.bins, 0, P.ws.bins_bytes, stream);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(P.ws.order_cnt, 0, sizeof(int) * ORDER_BUCKETS, stream);
+    // plan counters + tile bitmaps are adjacent in the workspace
+    cudaError_t e = cudaMemsetAsync(P.ws.order_cnt, 0, (size_t)((char*)P.ws.bins - (char*)P.ws.order_cnt) + P.ws.bins_bytes, stream);
     if (e != cudaSuccess) return (int)e;
     setup_faces_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
     e = cudaGetLastError();
@@ -299,9 +277,8 @@ int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
 
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
 {
-    cudaError_t e = cudaMemsetAsync(P.ws.imgbox, 0, sizeof(uint4) * (size_t)P.batch, stream);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(P.ws.bins, 0, P.ws.bins_bytes, stream);
+    // plan counters + tile bitmaps are adjacent in the workspace
+    cudaError_t e = cudaMemsetAsync(P.ws.order_cnt, 0, (size_t)((char*)P.ws.bins - (char*)P.ws.order_cnt) + P.ws.bins_bytes, stream);
     if (e != cudaSuccess) return (int)e;
     if (P.pose_R) {
         const int n = max(P.num_instances, P.num_K);
@@ -309,8 +286,6 @@ int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
-    e = cudaMemsetAsync(P.ws.order_cnt, 0, sizeof(int) * ORDER_BUCKETS, stream);
-    if (e != cudaSuccess) return (int)e;
     setup_meshes_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
