@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdibr_b200.so")
+LIB_PATH = os.environ.get("DIBR_B200_LIB") or os.path.join(_HERE, "lib", "libdibr_b200.so")   # override: debug builds (tools/variants.py)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dibr_b200.h")
 
 _c_f32p = ctypes.c_void_p

@@ -48,6 +48,7 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     w.cam_pos = (float*)take(sizeof(float) * 3 * ni);
     w.cam_proj = (float*)take(sizeof(float) * 16 * (size_t)(p->num_K > 0 ? p->num_K : 0));
     w.list_counts = (int*)take(sizeof(int) * 64);
+    w.pose_done = (unsigned int*)take(sizeof(unsigned int) * ni);          // between the counters and the flags: same memset
     w.face_flags = (unsigned int*)take(sizeof(unsigned int) * (size_t)p->total_faces);   // directly after list_counts: one memset
     w.color_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
     w.soft_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
@@ -256,8 +257,8 @@ int dibr_backward_meshes(const DibrPass* p, void* stream) {
     m.grad_points2d = p->grad_points2d; m.grad_face_attr = p->grad_face_attr;
     m.vert_face_ptr = p->vert_face_ptr; m.vert_face_idx = p->vert_face_idx;
     m.grad_verts = p->grad_verts; m.grad_vert_attr = p->grad_vert_attr;
-    m.grad_cam_rot = p->grad_cam_rot; m.grad_cam_pos = p->grad_cam_pos; m.pose_part = w.pose_part;
-    g_launches += 2;
+    m.grad_cam_rot = p->grad_cam_rot; m.grad_cam_pos = p->grad_cam_pos; m.pose_part = w.pose_part; m.pose_done = w.pose_done;
+    g_launches += 1;
     return cuda_fail("dibr_backward_meshes", dibr::launch_backward_meshes(m, (cudaStream_t)stream));
 }
 

@@ -301,17 +301,34 @@ __global__ void __launch_bounds__(256) mesh_vertex_grad_kernel(MeshBwdParams P)
         float ga[DIBR_MAX_ATTR_INTERNAL];
 #pragma unroll
         for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) ga[d] = 0.f;
-        for (int e = e0; e < e1; e++) {
-            const int fc = P.vert_face_idx[e];
-            const int gf = fbase + fc / 3, c = fc % 3;
-            g2x += P.grad_points2d[(size_t)gf * 6 + c * 2 + 0];
-            g2y += P.grad_points2d[(size_t)gf * 6 + c * 2 + 1];
-            const float* gfa = P.grad_face_attr + ((size_t)gf * 3 + c) * D;
-            if (P.grad_vert_attr) {
+        // incident (face, corner) pairs, 8 at a time: all indices first, then all gradient loads, then the sums in
+        // list order (the order fixes the rounding; the loads overlap instead of chaining L2 round trips)
+        for (int eb = e0; eb < e1; eb += 8) {
+            int fcs[8];
 #pragma unroll
-                for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) if (d < A) ga[d] += gfa[d];
+            for (int k = 0; k < 8; k++) fcs[k] = (eb + k < e1) ? __ldg(P.vert_face_idx + eb + k) : -1;
+            float2 g2[8];
+            float gdk[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                g2[k] = make_float2(0.f, 0.f); gdk[k] = 0.f;
+                if (fcs[k] >= 0) {
+                    const int gf = fbase + fcs[k] / 3, c = fcs[k] % 3;
+                    g2[k] = *reinterpret_cast<const float2*>(P.grad_points2d + (size_t)gf * 6 + c * 2);
+                    if (depth_ch >= 0) gdk[k] = P.grad_face_attr[((size_t)gf * 3 + c) * D + depth_ch];
+                }
             }
-            if (depth_ch >= 0) gdep += gfa[depth_ch];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (fcs[k] >= 0) {
+                    g2x += g2[k].x; g2y += g2[k].y; gdep += gdk[k];
+                    if (P.grad_vert_attr) {
+                        const float* gfa = P.grad_face_attr + ((size_t)(fbase + fcs[k] / 3) * 3 + fcs[k] % 3) * D;
+#pragma unroll
+                        for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) if (d < A) ga[d] += gfa[d];
+                    }
+                }
+            }
         }
         if (P.grad_vert_attr) {
             float* o = P.grad_vert_attr + (size_t)(gvbase + v) * A;
@@ -365,43 +382,46 @@ __global__ void __launch_bounds__(256) mesh_vertex_grad_kernel(MeshBwdParams P)
         for (int w = 0; w < 8; w++) v += red[w][threadIdx.x];
         P.pose_part[((size_t)inst * gridDim.x + blockIdx.x) * 12 + threadIdx.x] = v;
     }
-}
-
-// one thread per instance: sum the per-block partials in a fixed order; in pose mode chain
-// cam_view_R = F R (F = diag(1,-1,-1)) and cam_view_pos = -(R^T t) down to R and t:
-//   dL/dR[j][k] = F_jj dL/dcamR[j][k] - t[j] dL/dpos[k],   dL/dt[j] = -sum_k R[j][k] dL/dpos[k]
-__global__ void pose_finalize_kernel(MeshBwdParams P, int nblocks)
-{
-    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
-    if (inst >= P.num_instances) return;
-    float v[12];
+    // ---- the block that delivers last sums the partials of its instance in block order (fixed, so the result does not
+    //      depend on which block that is) and, in pose mode, chains cam_view_R = F R (F = diag(1,-1,-1)) and
+    //      cam_view_pos = -(R^T t) down to R and t:
+    //        dL/dR[j][k] = F_jj dL/dcamR[j][k] - t[j] dL/dpos[k],   dL/dt[j] = -sum_k R[j][k] dL/dpos[k]
+    __shared__ unsigned int ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket = atomicAdd(&P.pose_done[inst], 1u);
+    __syncthreads();
+    if (ticket != gridDim.x - 1) return;
+    if (threadIdx.x == 0) P.pose_done[inst] = 0u;          // ready for another backward over the same forward
+    __threadfence();
+    __shared__ float tot[12];
+    if (threadIdx.x < 12) {
+        const int nblocks = gridDim.x;
+        float v = 0.f;
+        for (int b0 = 0; b0 < nblocks; b0 += 8) {
+            float t[8];
 #pragma unroll
-    for (int i = 0; i < 12; i++) v[i] = 0.f;
-    for (int b = 0; b < nblocks; b++) {
-        const float* pp = P.pose_part + ((size_t)inst * nblocks + b) * 12;
+            for (int k = 0; k < 8; k++) t[k] = (b0 + k < nblocks) ? __ldcg(P.pose_part + ((size_t)inst * nblocks + b0 + k) * 12 + threadIdx.x) : 0.f;
 #pragma unroll
-        for (int i = 0; i < 12; i++) v[i] += pp[i];
+            for (int k = 0; k < 8; k++) v += t[k];
+        }
+        tot[threadIdx.x] = v;
+        if (threadIdx.x < 9) { if (P.grad_cam_rot) P.grad_cam_rot[(size_t)inst * 9 + threadIdx.x] = v; }
+        else if (P.grad_cam_pos) P.grad_cam_pos[(size_t)inst * 3 + threadIdx.x - 9] = v;
     }
-    if (P.grad_cam_rot) {
-#pragma unroll
-        for (int i = 0; i < 9; i++) P.grad_cam_rot[(size_t)inst * 9 + i] = v[i];
-    }
-    if (P.grad_cam_pos) {
-#pragma unroll
-        for (int i = 0; i < 3; i++) P.grad_cam_pos[(size_t)inst * 3 + i] = v[9 + i];
-    }
-    if (P.pose_R) {
-        const float* R = P.pose_R + (size_t)inst * 9;
-        const float* T = P.pose_t + (size_t)inst * 3;
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
+    __syncthreads();
+    if (P.pose_R && threadIdx.x < 12) {
+        const float* Rp = P.pose_R + (size_t)inst * 9;
+        const float* Tp = P.pose_t + (size_t)inst * 3;
+        if (threadIdx.x < 9) {
+            const int j = threadIdx.x / 3, k = threadIdx.x - 3 * j;
             const float sgn = (j == 0) ? 1.f : -1.f;
+            P.grad_pose_R[(size_t)inst * 9 + threadIdx.x] = sgn * tot[j * 3 + k] - Tp[j] * tot[9 + k];
+        } else {
+            const int j = threadIdx.x - 9;
             float gt = 0.f;
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                P.grad_pose_R[(size_t)inst * 9 + j * 3 + k] = sgn * v[j * 3 + k] - T[j] * v[9 + k];
-                gt -= R[j * 3 + k] * v[9 + k];
-            }
+            for (int k = 0; k < 3; k++) gt -= Rp[j * 3 + k] * tot[9 + k];
             P.grad_pose_t[(size_t)inst * 3 + j] = gt;
         }
     }
@@ -411,10 +431,7 @@ int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream)
 {
     if (P.num_instances <= 0) return 0;
     dim3 grid(POSE_BLOCKS, P.num_instances);
-    mesh_vertex_grad_kernel<<<grid, 256, 0, stream>>>(P);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    pose_finalize_kernel<<<(P.num_instances + 63) / 64, 64, 0, stream>>>(P, POSE_BLOCKS);
+    mesh_vertex_grad_kernel<<<grid, 256, 0, stream>>>(P);        // the last block of every instance finalises it
     return (int)cudaGetLastError();
 }
 

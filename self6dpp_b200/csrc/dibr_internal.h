@@ -23,6 +23,7 @@ struct Workspace {
     float* cam_pos;     // pose mode: [num_instances, 3]
     float* cam_proj;    // pose mode: [num_K, 16]
     int* list_counts;   // [2] entries in color_list / soft_list (+ padding), zeroed by dibr_forward
+    unsigned int* pose_done;    // [num_instances] vertex blocks that have delivered their pose sums (zeroed by dibr_forward with the lists)
     unsigned int* face_flags;   // [total_faces] bit0: won a pixel, bit1: evaluated for a soft pixel (zeroed by dibr_forward)
     int* color_list;    // [total_faces] global face ids that won at least one pixel (arbitrary order)
     int* soft_list;     // [total_faces] global face ids that entered at least one soft-silhouette product
@@ -130,6 +131,7 @@ struct MeshBwdParams {
     float* grad_cam_rot;
     float* grad_cam_pos;
     float* pose_part;
+    unsigned int* pose_done;
     // pose mode: chain to R, t
     const float* pose_R;
     const float* pose_t;

@@ -67,7 +67,9 @@ __device__ __forceinline__ void store_face(const SetupParams& P, int g, int b, f
         r.az = az; r.bz = bz; r.cz = cz; r.nz = nz; r.pad0 = 0.f; r.pad1 = 0.f;
         r.xmin = xmin; r.ymin = ymin; r.xmax = xmax; r.ymax = ymax;
         P.ws.recs[g] = r;
+#ifndef DIBR_X_NO_BIN
         if (ok) bin_face(P, g, b, xmin, ymin, xmax, ymax);
+#endif
     }
 }
 
@@ -213,21 +215,19 @@ __global__ void pose_to_camera_kernel(SetupParams P)
 
 // Work plan of the forward kernel: tiles bucketed by how many faces their bitmap lists (one warp per tile).  The
 // forward kernel takes the buckets heaviest first, so the long tiles start early and the short ones fill the tail.
-constexpr int PLAN_TILES_PER_WARP = 8, PLAN_TILES_PER_CTA = 8 * PLAN_TILES_PER_WARP;
-__global__ void __launch_bounds__(256) plan_tiles_kernel(SetupParams P)
+constexpr int PLAN_TILES_PER_CTA = 32;          // one warp per tile, 1024 threads: the bucket counters are bumped once per CTA
+__global__ void __launch_bounds__(32 * PLAN_TILES_PER_CTA) plan_tiles_kernel(SetupParams P)
 {
     __shared__ int hist[ORDER_BUCKETS], base[ORDER_BUCKETS];
-    __shared__ int t_bucket[PLAN_TILES_PER_CTA], t_pos[PLAN_TILES_PER_CTA], t_id[PLAN_TILES_PER_CTA];
     const int tiles_x = (P.width + TILE - 1) / TILE;
     const int tiles = tiles_x * ((P.height + TILE - 1) / TILE);
     const int ntiles = tiles * P.batch;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < ORDER_BUCKETS) hist[threadIdx.x] = 0;
     __syncthreads();
-    for (int k = 0; k < PLAN_TILES_PER_WARP; k++) {
-        const int slot = warp * PLAN_TILES_PER_WARP + k;
-        const int t = blockIdx.x * PLAN_TILES_PER_CTA + slot;
-        if (t >= ntiles) { if (lane == 0) t_bucket[slot] = -1; continue; }
+    const int t = blockIdx.x * PLAN_TILES_PER_CTA + warp;
+    int kb = -1, pos = 0, id = 0;
+    if (t < ntiles) {
         const int b = t / tiles, tl = t - b * tiles;
         const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
         const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
@@ -236,26 +236,20 @@ __global__ void __launch_bounds__(256) plan_tiles_kernel(SetupParams P)
         int cost = 0;
         for (int w = lane; w < nw; w += 32) cost += __popc(__ldg(words + w));
         cost = __reduce_add_sync(0xffffffffu, cost);
-        if (lane == 0) {
-            const int kb = min((cost + 31) >> 5, ORDER_BUCKETS - 1);
-            const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
-            t_bucket[slot] = kb;
-            t_pos[slot] = atomicAdd(&hist[kb], 1);
-            t_id[slot] = (int)(((unsigned)b << 20) | ((unsigned)ty << 10) | (unsigned)tx);     // forward: unpack_tile
-        }
+        kb = min((cost + 31) >> 5, ORDER_BUCKETS - 1);
+        const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
+        id = (int)(((unsigned)b << 20) | ((unsigned)ty << 10) | (unsigned)tx);                 // forward: unpack_tile
+        if (lane == 0) pos = atomicAdd(&hist[kb], 1);
     }
     __syncthreads();
     if (threadIdx.x < ORDER_BUCKETS && hist[threadIdx.x] > 0) base[threadIdx.x] = atomicAdd(&P.ws.order_cnt[threadIdx.x], hist[threadIdx.x]);
     __syncthreads();
-    if (threadIdx.x < PLAN_TILES_PER_CTA && t_bucket[threadIdx.x] >= 0) {
-        const int kb = t_bucket[threadIdx.x];
-        P.ws.order_seg[(size_t)kb * ntiles + base[kb] + t_pos[threadIdx.x]] = t_id[threadIdx.x];
-    }
+    if (lane == 0 && kb >= 0) P.ws.order_seg[(size_t)kb * ntiles + base[kb] + pos] = id;
 }
 
 static inline int launch_plan(const SetupParams& P, cudaStream_t stream) {
     const int ntiles = ((P.width + TILE - 1) / TILE) * ((P.height + TILE - 1) / TILE) * P.batch;
-    plan_tiles_kernel<<<(ntiles + PLAN_TILES_PER_CTA - 1) / PLAN_TILES_PER_CTA, 256, 0, stream>>>(P);
+    plan_tiles_kernel<<<(ntiles + PLAN_TILES_PER_CTA - 1) / PLAN_TILES_PER_CTA, 32 * PLAN_TILES_PER_CTA, 0, stream>>>(P);
     return (int)cudaGetLastError();
 }
 

@@ -5,7 +5,11 @@ import sys, os, subprocess, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 csrc = os.path.join(ROOT, "self6dpp_b200", "csrc")
-specs = [a.split("=", 1) if "=" in a else [a, ""] for a in sys.argv[1:]] or [["base", ""]]
+script = None
+argv = sys.argv[1:]
+if argv and argv[0] == "--run":          # run another tool against every variant instead of the built-in forward timing
+    script, argv = argv[1], argv[2:]
+specs = [a.split("=", 1) if "=" in a else [a, ""] for a in argv] or [["base", ""]]
 child = os.environ.get("DIBR_VARIANT_LIB")
 if child:
     from self6dpp_b200 import _lib
@@ -50,5 +54,11 @@ for name, flags in specs:
     if r.returncode != 0:
         print(name, "BUILD FAILED", r.stderr[-2000:]); continue
     env = dict(os.environ, DIBR_VARIANT_LIB=out, DIBR_VARIANT_NAME=name + " " + " ".join(fl), DIBR_VARIANT_PHASE="1" if phase else "0")
-    subprocess.run([sys.executable, os.path.abspath(__file__)], env=env)
+    if script:
+        print("==== variant", name, " ".join(fl), flush=True)
+        env.pop("DIBR_VARIANT_LIB")
+        env["DIBR_B200_LIB"] = out
+        subprocess.run([sys.executable, os.path.join(ROOT, script)], env=env)
+    else:
+        subprocess.run([sys.executable, os.path.abspath(__file__)], env=env)
     os.remove(out)
