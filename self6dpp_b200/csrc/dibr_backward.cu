@@ -24,6 +24,10 @@ namespace dibr {
 __device__ __forceinline__ int col_lower(const float* __restrict__ xs, int W, float x, float scale) {
     const float e = ceilf((x * scale + (float)(W - 1)) * 0.5f);
     int c = (int)fminf(fmaxf(e, 0.f), (float)W);
+    {   // the guess is almost always right: check both neighbours with loads issued together
+        const float a = (c > 0) ? __ldg(xs + c - 1) : -3.0e38f, b = (c < W) ? __ldg(xs + c) : 3.0e38f;
+        if (a < x && b >= x) return c;
+    }
     while (c > 0 && xs[c - 1] >= x) c--;
     while (c < W && xs[c] < x) c++;
     return c;
@@ -32,29 +36,26 @@ __device__ __forceinline__ int col_lower(const float* __restrict__ xs, int W, fl
 __device__ __forceinline__ int row_lower(const float* __restrict__ ys, int H, float y, float scale) {
     const float e = floorf(((float)(H - 1) - y * scale) * 0.5f) + 1.0f;
     int r = (int)fminf(fmaxf(e, 0.f), (float)H);
+    {
+        const float a = (r > 0) ? __ldg(ys + r - 1) : 3.0e38f, b = (r < H) ? __ldg(ys + r) : -3.0e38f;
+        if (a >= y && b < y) return r;
+    }
     while (r > 0 && ys[r - 1] < y) r--;
     while (r < H && ys[r] >= y) r++;
     return r;
-}
-
-__device__ __forceinline__ int image_of_face_b(int g, int batch, int faces_per_image, const int32_t* __restrict__ off) {
-    if (!off) return g / faces_per_image;
-    int lo = 0, hi = batch;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= g) lo = mid; else hi = mid; }
-    return lo;
 }
 
 constexpr int GRP = 8;     // lanes per face in the colour kernel
 
 // ---- colour part: one 8-lane group per face that WON at least one pixel (work list written by the forward) ------
 template <int DMAX>
-__global__ void __launch_bounds__(256) backward_color_kernel(BwdParams P)
+__device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
 {
     const int tid = threadIdx.x;
     const int gl = tid & (GRP - 1);
-    const int gi = blockIdx.x * (256 / GRP) + (tid / GRP);
+    const int gi = bid * (256 / GRP) + (tid / GRP);
     const int nlist = P.list_counts[0];
-    if (blockIdx.x * (256 / GRP) >= nlist) return;          // whole CTA beyond the list
+    if (bid * (256 / GRP) >= nlist) return;          // whole CTA beyond the list
     const bool active = gi < nlist;
     const int D = P.num_attr;
     const int W = P.width, H = P.height;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) backward_color_kernel(BwdParams P)
     if (active) {
         g = P.color_list[gi];
         rec = P.recs[g];
-        const int b = image_of_face_b(g, P.batch, P.faces_per_image, P.face_offsets);
+        const int b = __float_as_int(rec.image);
         const int f = g - (P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image);
         const size_t img = (size_t)b * H * W;
         const int32_t* __restrict__ idx = P.imidx + img;
@@ -78,8 +79,10 @@ __global__ void __launch_bounds__(256) backward_color_kernel(BwdParams P)
         const int nc = c1 - c0, npx = nc * (r1 - r0);
         if (nc > 0 && npx > 0 && P.any_grad_im) {
             const FaceK fk = make_facek(rec);
+            const unsigned nc_magic = (unsigned)((0x100000000ull + (unsigned)nc - 1ull) / (unsigned)nc);   // ceil(2^32 / nc)
+            const bool magic_ok = (nc > 1) && ((unsigned long long)npx * (unsigned)nc < 0xffffffffull);
             for (int i = gl; i < npx; i += GRP) {
-                const int rr = i / nc;
+                const int rr = magic_ok ? (int)__umulhi((unsigned)i, nc_magic) : i / nc;
                 const int r = r0 + rr, c = c0 + (i - rr * nc);
                 const size_t pix = (size_t)r * W + c;
                 if (idx[pix] != f + 1) continue;
@@ -129,8 +132,10 @@ __global__ void __launch_bounds__(256) backward_color_kernel(BwdParams P)
     float* __restrict__ gao = P.grad_face_attr + (size_t)g * 3 * D;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        gpo[2 * i + 0] = inv * (-fk.q * A[i] + fk.p * Bv[i]);
-        gpo[2 * i + 1] = inv * (fk.n * A[i] - fk.m * Bv[i]);
+        // the soft part adds to the same six slots from CTAs of the same launch: two addends on a zeroed slot, and
+        // a + b == b + a, so the sum does not depend on who comes first
+        atomicAdd(gpo + 2 * i + 0, inv * (-fk.q * A[i] + fk.p * Bv[i]));
+        atomicAdd(gpo + 2 * i + 1, inv * (fk.n * A[i] - fk.m * Bv[i]));
     }
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -143,17 +148,16 @@ __global__ void __launch_bounds__(256) backward_color_kernel(BwdParams P)
 // The warp walks the pixel centres of the expanded bbox 32 at a time, keeps (ballot compaction, ascending pixel
 // order) the uncovered pixels that counted this face, and evaluates them 32 at a time with every lane busy.
 constexpr int SOFT_Q = 64;
-__global__ void __launch_bounds__(256) backward_soft_kernel(BwdParams P)
+__device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, int (*queue)[SOFT_Q])
 {
-    __shared__ int queue[8][SOFT_Q];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wi = blockIdx.x * 8 + warp;
+    const int wi = bid * 8 + warp;
     if (wi >= P.list_counts[1]) return;                      // warp-uniform
     const unsigned full = 0xffffffffu;
     const int W = P.width, H = P.height;
     const int g = P.soft_list[wi];
     const FaceRec rec = P.recs[g];
-    const int b = image_of_face_b(g, P.batch, P.faces_per_image, P.face_offsets);
+    const int b = __float_as_int(rec.image);
     const int f = g - (P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image);
     const size_t img = (size_t)b * H * W;
     const int32_t* __restrict__ idx = P.imidx + img;
@@ -173,8 +177,11 @@ __global__ void __launch_bounds__(256) backward_soft_kernel(BwdParams P)
     int* q = queue[warp];
     int qn = 0;
 
+    const unsigned nc_magic = (unsigned)((0x100000000ull + (unsigned)nc - 1ull) / (unsigned)nc);   // ceil(2^32 / nc)
+    const bool magic_ok = (nc > 1) && ((unsigned long long)npx * (unsigned)nc < 0xffffffffull);       // exact for i < 2^32 / nc
+    auto div_nc = [&](int i) { return magic_ok ? (int)__umulhi((unsigned)i, nc_magic) : i / nc; };
     auto evaluate = [&](int i) {
-        const int rr = i / nc;
+        const int rr = div_nc(i);
         const int r = r0 + rr, c = c0 + (i - rr * nc);
         const size_t pix = (size_t)r * W + c;
         const float x0 = P.xs[c], y0 = P.ys[r];
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(256) backward_soft_kernel(BwdParams P)
         const int i = base + lane;
         bool take = false;
         if (i < npx) {
-            const int rr = i / nc;
+            const int rr = div_nc(i);
             const int v = idx[(size_t)(r0 + rr) * W + c0 + (i - rr * nc)];
             take = !(v > 0 || (v < 0 && f + 1 > -v));        // uncovered and this face is within the first K
         }
@@ -242,10 +249,26 @@ __global__ void __launch_bounds__(256) backward_soft_kernel(BwdParams P)
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
         gp[i] = v;
     }
-    if (lane == 0) {
-        float* __restrict__ gpo = P.grad_points2d + (size_t)g * 6;
+    {   // every lane holds the totals: lanes 0..5 deliver one each
+        float v = gp[0];
 #pragma unroll
-        for (int i = 0; i < 6; i++) gpo[i] += gp[i];
+        for (int i = 1; i < 6; i++) v = (lane == i) ? gp[i] : v;
+        if (lane < 6) atomicAdd(P.grad_points2d + (size_t)g * 6 + lane, v);
+    }
+}
+
+// One launch for both parts: CTA i does colour faces when i % 5 == 0, soft faces otherwise (the soft list needs four
+// times the CTAs), so the two kinds share the SMs and fill each other's stalls.
+template <int DMAX>
+__global__ void __launch_bounds__(256) backward_faces_kernel(const __grid_constant__ BwdParams P, int color_blocks, int soft_blocks)
+{
+    __shared__ int queue[8][SOFT_Q];
+    const int i = blockIdx.x, q = i / 5;
+    if (i - q * 5 == 0) {
+        if (q < color_blocks) backward_color_body<DMAX>(P, q);
+    } else {
+        const int si = i - q - 1;
+        if (si < soft_blocks) backward_soft_body(P, si, queue);
     }
 }
 
@@ -258,19 +281,14 @@ int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
     e = cudaMemsetAsync(P.grad_face_attr, 0, sizeof(float) * 3 * (size_t)P.num_attr * (size_t)P.total_faces, stream);
     if (e != cudaSuccess) return (int)e;
     // the list lengths live on the device: launch for the worst case, surplus CTAs exit at once
-    if (P.any_grad_im) {
-        const int grid = (P.total_faces + (256 / GRP) - 1) / (256 / GRP);
-        if (P.num_attr <= 4) backward_color_kernel<4><<<grid, 256, 0, stream>>>(P);
-        else if (P.num_attr <= 8) backward_color_kernel<8><<<grid, 256, 0, stream>>>(P);
-        else backward_color_kernel<12><<<grid, 256, 0, stream>>>(P);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-    }
-    if (P.grad_improb && P.knum > 0) {
-        backward_soft_kernel<<<(P.total_faces + 7) / 8, 256, 0, stream>>>(P);
-        e = cudaGetLastError();
-    }
-    return (int)e;
+    const int cb = P.any_grad_im ? (P.total_faces + (256 / GRP) - 1) / (256 / GRP) : 0;
+    const int sb = (P.grad_improb && P.knum > 0) ? (P.total_faces + 7) / 8 : 0;
+    if (cb == 0 && sb == 0) return 0;
+    const int grid = 5 * max(cb, (sb + 3) / 4);
+    if (P.num_attr <= 4) backward_faces_kernel<4><<<grid, 256, 0, stream>>>(P, cb, sb);
+    else if (P.num_attr <= 8) backward_faces_kernel<8><<<grid, 256, 0, stream>>>(P, cb, sb);
+    else backward_faces_kernel<12><<<grid, 256, 0, stream>>>(P, cb, sb);
+    return (int)cudaGetLastError();
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ constexpr int MAX_IMAGE_SIDE = 16384;           // largest image side the ABI ac
 struct __align__(16) FaceRec {
     float ax, ay, bx, by;           // 2D corners, already x multiplier
     float cx, cy, az, bz;           // third corner, view-space z of a and b
-    float cz, nz, pad0, pad1;       // view-space z of c, z of the face normal (< 0: back face)
+    float cz, nz, image, pad1;      // view-space z of c, z of the face normal (< 0: back face), image index (int bits)
     float xmin, ymin, xmax, ymax;   // bbox of the 2D corners (rasterizer.py:49-52)
 };
 

@@ -64,7 +64,7 @@ __device__ __forceinline__ void store_face(const SetupParams& P, int g, int b, f
         if (!ok) { xmin = ymin = 3.0e38f; xmax = ymax = -3.0e38f; }
         FaceRec r;
         r.ax = ax; r.ay = ay; r.bx = bx; r.by = by; r.cx = cx; r.cy = cy;
-        r.az = az; r.bz = bz; r.cz = cz; r.nz = nz; r.pad0 = 0.f; r.pad1 = 0.f;
+        r.az = az; r.bz = bz; r.cz = cz; r.nz = nz; r.image = __int_as_float(b); r.pad1 = 0.f;
         r.xmin = xmin; r.ymin = ymin; r.xmax = xmax; r.ymax = ymax;
         P.ws.recs[g] = r;
 #ifndef DIBR_X_NO_BIN
