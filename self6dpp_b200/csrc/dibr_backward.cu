@@ -257,18 +257,19 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
     }
 }
 
-// One launch for both parts: CTA i does colour faces when i % 5 == 0, soft faces otherwise (the soft list needs four
-// times the CTAs), so the two kinds share the SMs and fill each other's stalls.
+// One persistent launch for both parts.  The list lengths live on the device, so a grid sized for the worst case would
+// be mostly CTAs that find nothing to do; instead a fixed grid strides over the work items that exist: first the
+// colour items (32 faces each), then the soft items (8 faces each) -- both kinds share the SMs as the first run out.
 template <int DMAX>
-__global__ void __launch_bounds__(256) backward_faces_kernel(const __grid_constant__ BwdParams P, int color_blocks, int soft_blocks)
+__global__ void __launch_bounds__(256) backward_faces_kernel(const __grid_constant__ BwdParams P, int do_color, int do_soft)
 {
     __shared__ int queue[8][SOFT_Q];
-    const int i = blockIdx.x, q = i / 5;
-    if (i - q * 5 == 0) {
-        if (q < color_blocks) backward_color_body<DMAX>(P, q);
-    } else {
-        const int si = i - q - 1;
-        if (si < soft_blocks) backward_soft_body(P, si, queue);
+    const int cbn = do_color ? (P.list_counts[0] + (256 / GRP) - 1) / (256 / GRP) : 0;
+    const int sbn = do_soft ? (P.list_counts[1] + 7) / 8 : 0;
+    for (int it = blockIdx.x; it < cbn + sbn; it += gridDim.x) {
+        __syncwarp();                        // lanes leave the bodies at different points
+        if (it < cbn) backward_color_body<DMAX>(P, it);
+        else backward_soft_body(P, it - cbn, queue);
     }
 }
 
@@ -280,14 +281,13 @@ int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(P.grad_face_attr, 0, sizeof(float) * 3 * (size_t)P.num_attr * (size_t)P.total_faces, stream);
     if (e != cudaSuccess) return (int)e;
-    // the list lengths live on the device: launch for the worst case, surplus CTAs exit at once
-    const int cb = P.any_grad_im ? (P.total_faces + (256 / GRP) - 1) / (256 / GRP) : 0;
-    const int sb = (P.grad_improb && P.knum > 0) ? (P.total_faces + 7) / 8 : 0;
-    if (cb == 0 && sb == 0) return 0;
-    const int grid = 5 * max(cb, (sb + 3) / 4);
-    if (P.num_attr <= 4) backward_faces_kernel<4><<<grid, 256, 0, stream>>>(P, cb, sb);
-    else if (P.num_attr <= 8) backward_faces_kernel<8><<<grid, 256, 0, stream>>>(P, cb, sb);
-    else backward_faces_kernel<12><<<grid, 256, 0, stream>>>(P, cb, sb);
+    const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
+    if (!do_color && !do_soft) return 0;
+    const int worst = (do_color ? (P.total_faces + (256 / GRP) - 1) / (256 / GRP) : 0) + (do_soft ? (P.total_faces + 7) / 8 : 0);
+    const int grid = min(worst, 148 * 6);
+    if (P.num_attr <= 4) backward_faces_kernel<4><<<grid, 256, 0, stream>>>(P, do_color, do_soft);
+    else if (P.num_attr <= 8) backward_faces_kernel<8><<<grid, 256, 0, stream>>>(P, do_color, do_soft);
+    else backward_faces_kernel<12><<<grid, 256, 0, stream>>>(P, do_color, do_soft);
     return (int)cudaGetLastError();
 }
 
