@@ -260,8 +260,14 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
 // One persistent launch for both parts.  The list lengths live on the device, so a grid sized for the worst case would
 // be mostly CTAs that find nothing to do; instead a fixed grid strides over the work items that exist: first the
 // colour items (32 faces each), then the soft items (8 faces each) -- both kinds share the SMs as the first run out.
+#ifndef DIBR_BWD_MIN_CTAS
+#define DIBR_BWD_MIN_CTAS 4        // 64 registers: measured faster than 80 registers at 3 CTAs per SM
+#endif
+#ifndef DIBR_BWD_GRID
+#define DIBR_BWD_GRID (148 * 16)
+#endif
 template <int DMAX>
-__global__ void __launch_bounds__(256) backward_faces_kernel(const __grid_constant__ BwdParams P, int do_color, int do_soft)
+__global__ void __launch_bounds__(256, (DMAX <= 8) ? DIBR_BWD_MIN_CTAS : 2) backward_faces_kernel(const __grid_constant__ BwdParams P, int do_color, int do_soft)
 {
     __shared__ int queue[8][SOFT_Q];
     const int cbn = do_color ? (P.list_counts[0] + (256 / GRP) - 1) / (256 / GRP) : 0;
@@ -284,7 +290,7 @@ int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
     const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
     if (!do_color && !do_soft) return 0;
     const int worst = (do_color ? (P.total_faces + (256 / GRP) - 1) / (256 / GRP) : 0) + (do_soft ? (P.total_faces + 7) / 8 : 0);
-    const int grid = min(worst, 148 * 6);
+    const int grid = min(worst, DIBR_BWD_GRID);
     if (P.num_attr <= 4) backward_faces_kernel<4><<<grid, 256, 0, stream>>>(P, do_color, do_soft);
     else if (P.num_attr <= 8) backward_faces_kernel<8><<<grid, 256, 0, stream>>>(P, do_color, do_soft);
     else backward_faces_kernel<12><<<grid, 256, 0, stream>>>(P, do_color, do_soft);
