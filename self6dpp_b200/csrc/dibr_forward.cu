@@ -204,6 +204,8 @@ __device__ int fill_list(FwdSmem& s, const FwdParams& P, int f_lo, int wpos, con
     return wpos;
 }
 
+__constant__ unsigned c_inv16[17] = {0u, 65537u, 32769u, 21846u, 16385u, 13108u, 10923u, 9363u, 8193u, 7282u, 6554u, 5958u, 5462u, 5042u, 4682u, 4370u, 4097u};
+
 struct RasterEntry { int li, c0, nc, r0, nr; };
 __device__ __forceinline__ RasterEntry unpack_entry(unsigned int p) {
     RasterEntry e;
@@ -249,7 +251,7 @@ __device__ void raster_list(FwdSmem& s, int nprev)
             continue;
         }
         const FaceK fk = facek_from_list(s, en.li);
-        const unsigned inv = 65536u / (unsigned)en.nc + 1u;            // exact i / nc for i < 256
+        const unsigned inv = c_inv16[en.nc];                           // 65536 / nc + 1: exact i / nc for i < 256
         for (int i = ql; i < npx; i += 4) {
             const int row = (int)(((unsigned)i * inv) >> 16);
             raster_pixel(s, fk, (unsigned)(nprev + en.li), en.c0 + (i - row * en.nc), en.r0 + row);

@@ -125,6 +125,19 @@ def test_dense_mesh_multi_batch_lists():
     print(out)
 
 
+def test_knum_above_hit_capacity():
+    """K = 45 on the dense mesh: pixels near the silhouette collect more faces than one pass of the soft phase holds
+    (30 per pixel), so the tile re-collects with a skip window; also K > 30 in the backward's 'first K' rule."""
+    from self6dpp_b200 import synth
+    mesh = synth.icosphere(5, radius=0.05, noise_sigma=0.002, seed=4)        # 20480 faces
+    R, _ = synth.random_rotations(1, 23)
+    ts = np.array([[0.0, 0.0, 0.65]], np.float32)
+    K = synth.crop_K(synth.K_LM, (325.26, 242.05), 150.0, 64)
+    p3, p2, nz, at = Hh.seam_inputs([mesh], R, ts, K[None], 64, 64)
+    out = run_case(p3, p2, nz, at, 64, 64, knum=45, seed=13)
+    print(out)
+
+
 def test_large_faces_many_per_tile():
     """80 overlapping large triangles: every face exceeds the 4-lane budget and goes through the CTA-cooperative
     path, more of them than the deferred list holds (overflow rescan)."""

@@ -71,9 +71,9 @@ for key, (s, i, t) in sorted(agg.items(), key=lambda kv: -kv[1][1 if "--by-inst"
 # ---- per-phase view for the forward kernel: helper lines (inlined .cuh code) inherit the phase of the nearest
 # preceding dibr_forward.cu line in address order
 if "--phases" in sys.argv:
-    bounds = [(112, 168, "A bitmap"), (169, 205, "A gather"), (206, 283, "B raster"), (284, 326, "fill"), (328, 376, "prologue"),
-              (377, 398, "tile setup"), (399, 421, "batch loop"), (422, 535, "C resolve"), (536, 571, "D setup+masks"), (572, 612, "D collect"),
-              (613, 653, "D evaluate"), (654, 666, "D fold"), (667, 680, "D marks")]
+    bounds = [(112, 168, "A bitmap"), (169, 205, "A gather"), (206, 283, "B raster"), (284, 338, "fill untouched"), (340, 393, "prologue"),
+              (394, 415, "tile setup"), (416, 438, "batch loop"), (439, 550, "C resolve"), (551, 586, "D setup+masks"), (587, 627, "D collect"),
+              (628, 668, "D evaluate"), (669, 681, "D fold"), (682, 695, "D marks")]
     def phase_of(ln):
         for a, b, n in bounds:
             if a <= ln <= b:
