@@ -105,7 +105,6 @@ dibr::SetupParams setup_params(const DibrPass* p) {
     s.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     s.q = (float)(-(fc + nc) / (fc - nc));
     s.qn = (float)(-2.0 * (fc * nc) / (fc - nc));
-    if (p->pose_R) { s.cam_rot = s.ws.cam_rot; s.cam_pos = s.ws.cam_pos; s.cam_proj = s.ws.cam_proj; }
     return s;
 }
 
@@ -159,7 +158,7 @@ int dibr_setup_meshes(const DibrPass* p, void* stream) {
     if (d != p->num_attr) return fail("setup_meshes: vert_attr_dim + flags = %d but num_attr = %d", d, p->num_attr);
     if (p->vert_attr_dim > 0 && !p->vert_attr) return fail("setup_meshes: vert_attr is null");
     const dibr::SetupParams s = setup_params(p);
-    g_launches += p->pose_R ? 3 : 2;
+    g_launches += 2;
     return cuda_fail("dibr_setup_meshes", dibr::launch_setup_meshes(s, (cudaStream_t)stream));
 }
 

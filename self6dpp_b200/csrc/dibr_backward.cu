@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(256) mesh_vertex_grad_kernel(MeshBwdParams P)
 {
     const int inst = blockIdx.y;
     const int32_t* de = P.inst_desc + inst * INST_STRIDE;
-    const int nv = de[I_NUM_VERTS], vbase = de[I_VERT_BASE], fbase = de[I_OUT_FACE_BASE], gvbase = de[I_GVERT_BASE];
+    // an instance without faces has no camera in the workspace (the set-up kernel's first face writes it) and no gradient
+    const int nv = (de[I_NUM_FACES] > 0) ? de[I_NUM_VERTS] : 0, vbase = de[I_VERT_BASE], fbase = de[I_OUT_FACE_BASE], gvbase = de[I_GVERT_BASE];
     const int abase = de[I_ADJ_BASE];      // row of this mesh's vertex 0 in the CSR pointer array
     const float* R = P.cam_rot + (size_t)de[I_CAM] * 9;
     const float* T = P.cam_pos + (size_t)de[I_CAM] * 3;

@@ -122,9 +122,53 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(SetupParams P)
         const int lf = g - de[I_OUT_FACE_BASE];
         b = de[I_IMAGE];
         const int32_t* fv = P.mesh_faces + (size_t)(de[I_MESH_FACE_BASE] + lf) * 3;
-        const float* R = P.cam_rot + (size_t)de[I_CAM] * 9;
-        const float* T = P.cam_pos + (size_t)de[I_CAM] * 3;
-        const float* Pm = P.cam_proj + (size_t)de[I_PROJ] * 16;
+        // camera of the instance.  Pose mode: cam_view_R = diag(1,-1,-1) R, cam_view_pos = -(R^T t)
+        // (renderer/base.py:169-170) and the 4x4 projection of utils/perspective.py:122-129 straight from R, t, K, in
+        // the fp32 operation order frozen in oracle dibr_oracle_camera; the first face of the instance also leaves them
+        // in the workspace for the backward (no separate camera kernel).
+        float R[9], T[3], Pm[16];
+        if (P.pose_R) {
+            const float* Rp = P.pose_R + (size_t)de[I_CAM] * 9;
+            const float* Tp = P.pose_t + (size_t)de[I_CAM] * 3;
+            const float* K = P.pose_K + (size_t)de[I_PROJ] * 9;
+            const float w = (float)P.width, h = (float)P.height;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                R[k] = Rp[k]; R[3 + k] = -Rp[3 + k]; R[6 + k] = -Rp[6 + k];
+                T[k] = -__fmaf_rn(Rp[6 + k], Tp[2], __fmaf_rn(Rp[3 + k], Tp[1], __fmul_rn(Rp[k], Tp[0])));
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) Pm[i] = 0.f;
+            Pm[0] = __fdiv_rn(__fmul_rn(2.f, K[0]), w);
+            Pm[4] = __fdiv_rn(__fmul_rn(-2.f, K[1]), w);
+            Pm[5] = __fdiv_rn(__fmul_rn(2.f, K[4]), h);
+            Pm[8] = __fdiv_rn(__fadd_rn(__fmul_rn(-2.f, K[2]), w), w);
+            Pm[9] = __fdiv_rn(__fsub_rn(__fmul_rn(2.f, K[5]), h), h);
+            Pm[10] = P.q;
+            Pm[14] = P.qn;
+            Pm[11] = -1.0f;
+            if (lf == 0) {
+                float* cr = P.ws.cam_rot + (size_t)de[I_CAM] * 9;
+                float* cp = P.ws.cam_pos + (size_t)de[I_CAM] * 3;
+                float* pm = P.ws.cam_proj + (size_t)de[I_PROJ] * 16;     // instances that share K write the same values
+#pragma unroll
+                for (int k = 0; k < 9; k++) cr[k] = R[k];
+#pragma unroll
+                for (int k = 0; k < 3; k++) cp[k] = T[k];
+#pragma unroll
+                for (int k = 0; k < 16; k++) pm[k] = Pm[k];
+            }
+        } else {
+            const float* Rg = P.cam_rot + (size_t)de[I_CAM] * 9;
+            const float* Tg = P.cam_pos + (size_t)de[I_CAM] * 3;
+            const float* Pg = P.cam_proj + (size_t)de[I_PROJ] * 16;
+#pragma unroll
+            for (int k = 0; k < 9; k++) R[k] = Rg[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) T[k] = Tg[k];
+#pragma unroll
+            for (int k = 0; k < 16; k++) Pm[k] = Pg[k];
+        }
         const float m = (float)P.multiplier;
         const int A = P.vert_attr_dim, D = P.num_attr;
         float pc[3][3];
@@ -178,39 +222,6 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(SetupParams P)
         }
     }
     store_face(P, g, b, x2[0], y2[0], x2[1], y2[1], x2[2], y2[2], zc[0], zc[1], zc[2], nz, active);
-}
-
-// pose mode: cam_view_R = diag(1,-1,-1) R, cam_view_pos = -(R^T t)  (renderer/base.py:169-170) and the 4x4
-// projection of utils/perspective.py:122-129, in the fp32 operation order frozen in oracle dibr_oracle_camera.
-__global__ void pose_to_camera_kernel(SetupParams P)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < P.num_instances) {
-        const float* R = P.pose_R + (size_t)t * 9;
-        const float* T = P.pose_t + (size_t)t * 3;
-        float* cr = P.ws.cam_rot + (size_t)t * 9;
-        float* cp = P.ws.cam_pos + (size_t)t * 3;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            cr[k] = R[k]; cr[3 + k] = -R[3 + k]; cr[6 + k] = -R[6 + k];
-            cp[k] = -__fmaf_rn(R[6 + k], T[2], __fmaf_rn(R[3 + k], T[1], __fmul_rn(R[k], T[0])));
-        }
-    }
-    if (t < P.num_K) {
-        const float* K = P.pose_K + (size_t)t * 9;
-        float* pm = P.ws.cam_proj + (size_t)t * 16;
-        const float w = (float)P.width, h = (float)P.height;
-#pragma unroll
-        for (int i = 0; i < 16; i++) pm[i] = 0.f;
-        pm[0] = __fdiv_rn(__fmul_rn(2.f, K[0]), w);
-        pm[4] = __fdiv_rn(__fmul_rn(-2.f, K[1]), w);
-        pm[5] = __fdiv_rn(__fmul_rn(2.f, K[4]), h);
-        pm[8] = __fdiv_rn(__fadd_rn(__fmul_rn(-2.f, K[2]), w), w);
-        pm[9] = __fdiv_rn(__fsub_rn(__fmul_rn(2.f, K[5]), h), h);
-        pm[10] = P.q;
-        pm[14] = P.qn;
-        pm[11] = -1.0f;
-    }
 }
 
 // Work plan of the forward kernel: tiles bucketed by how many faces their bitmap lists (one warp per tile).  The
@@ -274,12 +285,6 @@ int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
     // plan counters + tile bitmaps are adjacent in the workspace
     cudaError_t e = cudaMemsetAsync(P.ws.order_cnt, 0, (size_t)((char*)P.ws.bins - (char*)P.ws.order_cnt) + P.ws.bins_bytes, stream);
     if (e != cudaSuccess) return (int)e;
-    if (P.pose_R) {
-        const int n = max(P.num_instances, P.num_K);
-        pose_to_camera_kernel<<<(n + 127) / 128, 128, 0, stream>>>(P);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-    }
     setup_meshes_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
