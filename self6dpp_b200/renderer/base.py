@@ -5,22 +5,28 @@ reference's /root/reference/lib/dr_utils/dib_renderer_x/renderer/base.py:53-191 
 running on the fused B200 kernels.  Differences, all deliberate:
   * tensors live on the inputs' device (the reference hard-codes cuda:0, base.py:69,153,164-166);
   * camera set-up is a few batched torch ops instead of a Python loop over the batch;
-  * the texture / SH / Phong modes (fragment shading in plain torch on top of the same rasterizer,
-    SURVEY.md 8(f) rank 3) are not built yet and raise NotImplementedError.
+  * the texture / SH / Phong modes (renderer/tex.py) keep the reference's structure -- torch vertex shader, the B200
+    rasterizer operator, torch fragment shader -- with the per-object rasterizer loop replaced by one padded call.
 """
 import numpy as np
 import torch
 import torch.nn as nn
 
 from .cameras import camera_params_from_RT_K, look_at_camera_params
+from .tex import PhongRender, SHRender, TexRender, TexRenderBatch, TexRenderMulti
 from .vc import VCRender, VCRenderBatch, VCRenderMulti
 
 renderers = {
     "VertexColor": VCRender,
     "VertexColorMulti": VCRenderMulti,
     "VertexColorBatch": VCRenderBatch,
+    "Lambertian": TexRender,
+    "Texture": TexRender,  # alias
+    "TextureMulti": TexRenderMulti,
+    "TextureBatch": TexRenderBatch,
+    "SphericalHarmonics": SHRender,
+    "Phong": PhongRender,
 }
-_NOT_BUILT = ["Lambertian", "Texture", "TextureMulti", "TextureBatch", "SphericalHarmonics", "Phong"]
 
 
 def perspectiveprojectionnp(fovy, ratio=1.0, near=0.01, far=10.0):
@@ -32,9 +38,6 @@ def perspectiveprojectionnp(fovy, ratio=1.0, near=0.01, far=10.0):
 class Renderer(nn.Module):
     def __init__(self, height, width, mode="VertexColor", camera_center=None, camera_up=None, camera_fov_y=None):
         super(Renderer, self).__init__()
-        if mode in _NOT_BUILT:
-            raise NotImplementedError("mode {} (texture / SH / Phong fragment shaders) is not built in self6dpp_b200 yet; "
-                                      "vertex-colour modes are: {}".format(mode, list(renderers)))
         assert mode in renderers, "Passed mode {0} must in in list of accepted modes: {1}".format(mode, renderers)
         self.mode = mode
         self.height = height

@@ -137,7 +137,7 @@ def golden_seam(ref, H=48, W=64, seed=5):
     print("ref_seam48x64: covered", int((im[..., 3] > 0.5).sum()))
 
 
-if __name__ == "__main__" and "--nnd" not in sys.argv:
+if __name__ == "__main__" and "--nnd" not in sys.argv and "--tex" not in sys.argv:
     import warnings
     warnings.filterwarnings("ignore")
     ref = O.import_reference()
@@ -212,3 +212,128 @@ def golden_nnd():
 
 if __name__ == "__main__" and "--nnd" in sys.argv:
     golden_nnd()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# texture / SH / Phong modes: the reference's OWN TexRender, TexRenderBatch, TexRenderMulti,
+# SHRender, PhongRender (+ fragment shaders) on CPU with the oracle at the kaolin boundary.
+# ------------------------------------------------------------------------------------------------------------------
+def import_reference_tex():
+    O.install_reference_stubs()
+    from lib.dr_utils.dib_renderer_x.renderer.texrender import TexRender
+    from lib.dr_utils.dib_renderer_x.renderer.texrender_batch import TexRenderBatch
+    from lib.dr_utils.dib_renderer_x.renderer.texrender_multi import TexRenderMulti
+    from lib.dr_utils.dib_renderer_x.renderer.shrender import SHRender
+    from lib.dr_utils.dib_renderer_x.renderer.phongrender import PhongRender
+    return dict(TexRender=TexRender, TexRenderBatch=TexRenderBatch, TexRenderMulti=TexRenderMulti, SHRender=SHRender,
+                PhongRender=PhongRender)
+
+
+def sphere_uv(verts):
+    """a (u, v) per vertex from the direction of the vertex; deliberately leaves [0,1] so the wrap-around is used"""
+    v = verts / verts.norm(dim=1, keepdim=True)
+    return torch.stack((torch.atan2(v[:, 1], v[:, 0]) / (2 * np.pi) + 0.55, torch.asin(v[:, 2].clamp(-1, 1)) / np.pi + 0.6), dim=1)
+
+
+def face_uv_layout(verts, faces, seed):
+    """'face uv' layout: every face owns three uv rows (a permutation of the welded ones), so ft != faces"""
+    g = torch.Generator().manual_seed(seed)
+    uv_v = sphere_uv(verts)
+    f = faces.long()
+    perm = torch.randperm(3 * f.shape[0], generator=g)
+    uv_rows = torch.empty(3 * f.shape[0], 2)
+    uv_rows[perm] = uv_v[f.reshape(-1)]
+    return uv_rows, perm.reshape(-1, 3)
+
+
+def golden_tex():
+    ref = import_reference_tex()
+    H, W = 48, 64
+    meshes = small_meshes()
+    models = to_models(meshes)
+    g = torch.Generator().manual_seed(21)
+    ids = [0, 1, 2]
+    batch = synth.roi_batch([meshes[i] for i in ids], 3, res=H, seed=5, fill=(0.5, 0.8))
+    Rs, ts = torch.tensor(batch["Rs"]), torch.tensor(batch["ts"])
+    K = torch.tensor(batch["Ks"][0])
+    K[0, 2] += (W - H) / 2.0
+    out = {"H": H, "W": W, "Rs": Rs.numpy(), "ts": ts.numpy(), "K": K.numpy()}
+    cams = O.camera_params_from_RT_K(Rs, ts, K, H, W, near=0.01, far=100.0)
+    # ---- TexRenderBatch + TexRenderMulti: three objects, textures of different sizes, object 1 with face uvs
+    verts = [models[i]["vertices"].clone().requires_grad_(True) for i in ids]
+    faces = [models[i]["faces"].long() for i in ids]
+    uvs, fts, texs = [], [], []
+    for k, i in enumerate(ids):
+        if k == 1:
+            uv_rows, ft = face_uv_layout(models[i]["vertices"], faces[k], seed=3)
+        else:
+            uv_rows, ft = sphere_uv(models[i]["vertices"]), faces[k]
+        uvs.append(uv_rows.clone().requires_grad_(True))
+        fts.append(ft)
+        texs.append(torch.rand(1, 3, 16 + 8 * k, 24 - 4 * k, generator=g).requires_grad_(True))
+    points = [[v[None], f] for v, f in zip(verts, faces)]
+    for name in ("TexRenderBatch", "TexRenderMulti"):
+        ren = ref[name](H, W)
+        if name == "TexRenderMulti":
+            # the reference composites with in-place indexed writes (texrender_multi.py:124-136), which autograd rejects:
+            # forward only
+            with torch.no_grad():
+                im, prob, normal1, mask = ren(points, cams, [u[None] for u in uvs], texs, ts=ts, ft_fx3=fts)
+            out.update({f"{name}_im": im.numpy(), f"{name}_prob": prob.numpy(), f"{name}_mask": mask.numpy()})
+            continue
+        im, prob, normal1, mask = ren(points, cams, [u[None] for u in uvs], texs, ft_fx3=fts)
+        gi, gp = torch.randn(im.shape, generator=g), torch.randn(prob.shape, generator=g)
+        for t in verts + uvs + texs:
+            t.grad = None
+        ((im * gi).sum() + (prob * gp).sum()).backward()
+        out.update({f"{name}_im": im.detach().numpy(), f"{name}_prob": prob.detach().numpy(), f"{name}_mask": mask.detach().numpy(),
+                    f"{name}_gi": gi.numpy(), f"{name}_gp": gp.numpy()})
+        for k in range(3):
+            out[f"{name}_gv{k}"] = verts[k].grad.numpy().copy()
+            out[f"{name}_gtex{k}"] = texs[k].grad.numpy().copy()
+            out[f"{name}_normal1_{k}"] = normal1[k].detach().numpy()
+    for k in range(3):
+        out[f"verts{k}"], out[f"faces{k}"] = verts[k].detach().numpy(), faces[k].numpy()
+        out[f"uv{k}"], out[f"ft{k}"], out[f"tex{k}"] = uvs[k].detach().numpy(), fts[k].numpy(), texs[k].detach().numpy()
+    # ---- one topology, batch of 2 vertex sets: TexRender (bilinear), SHRender (flat and smooth), PhongRender
+    m = models[1]
+    f1 = m["faces"].long()
+    vb = torch.stack((m["vertices"], m["vertices"] * 1.05 + 0.002)).requires_grad_(True)
+    cams2 = O.camera_params_from_RT_K(Rs[:2], ts[:2], K, H, W, near=0.01, far=100.0)
+    uvb = torch.stack((sphere_uv(m["vertices"]), sphere_uv(m["vertices"]) * 1.3))
+    texb = torch.rand(2, 3, 20, 28, generator=g).requires_grad_(True)
+    # vertex <- face averaging matrix for smooth shading (p x f)
+    P_, F_ = m["vertices"].shape[0], f1.shape[0]
+    pf = torch.zeros(P_, F_)
+    for c in range(3):
+        pf[f1[:, c], torch.arange(F_)] = 1.0
+    pf = pf / pf.sum(1, keepdim=True).clamp(min=1)
+    light9 = torch.randn(2, 9, generator=g) * 0.5 + 0.6
+    lightdir = torch.tensor([[0.3, 0.2, 1.0], [-0.4, 0.5, 0.8]])
+    material = torch.rand(2, 3, 3, generator=g) * 0.5 + 0.2
+    shin = torch.tensor([[4.0], [9.0]])
+    out.update(vb=vb.detach().numpy(), f1=f1.numpy(), uvb=uvb.numpy(), texb=texb.detach().numpy(), pf=pf.numpy(),
+               light9=light9.numpy(), lightdir=lightdir.numpy(), material=material.numpy(), shin=shin.numpy())
+
+    def run(tag, ren, *args):
+        vb.grad = None
+        texb.grad = None
+        im, prob, normal1, mask = ren([vb, f1], cams2, uvb, texb, *args)
+        gi, gp = torch.randn(im.shape, generator=g), torch.randn(prob.shape, generator=g)
+        ((im * gi).sum() + (prob * gp).sum()).backward()
+        out.update({f"{tag}_im": im.detach().numpy(), f"{tag}_prob": prob.detach().numpy(), f"{tag}_mask": mask.detach().numpy(),
+                    f"{tag}_normal1": normal1.detach().numpy(), f"{tag}_gi": gi.numpy(), f"{tag}_gp": gp.numpy(),
+                    f"{tag}_gv": vb.grad.numpy().copy(), f"{tag}_gtex": texb.grad.numpy().copy()})
+        print(tag, "covered", int((mask > 0.5).sum()), "im mean", float(im.mean()))
+    run("TexRender", ref["TexRender"](H, W, filtering="bilinear"))
+    run("SHflat", ref["SHRender"](H, W), light9)
+    sh = ref["SHRender"](H, W)
+    sh.set_smooth(pf[None])
+    run("SHsmooth", sh, light9)
+    run("Phong", ref["PhongRender"](H, W), lightdir, material, shin)
+    np.savez_compressed(os.path.join(OUT, "ref_tex.npz"), **out)
+    print("ref_tex written:", len(out), "arrays")
+
+
+if __name__ == "__main__" and "--tex" in sys.argv:
+    golden_tex()

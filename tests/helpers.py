@@ -50,8 +50,8 @@ def assert_close(name, got, ref, rtol=1e-5, atol_rel=1e-5, mask=None, outlier_fr
     Needed only where the reference's own fp32 formula is ill-conditioned (weights of sliver triangles are
     k1/k3 with k3 -> 0, so ANY fp32 evaluation is 1/k3 away from float64); such elements are additionally
     pinned bit-exactly against the fp32 operation-order oracle by the callers."""
-    got = got.detach().double().cpu()
-    ref = ref.detach().double().cpu()
+    got = torch.as_tensor(got).detach().double().cpu()
+    ref = torch.as_tensor(ref).detach().double().cpu()
     assert got.shape == ref.shape, (name, got.shape, ref.shape)
     scale = float(ref.abs().max()) if ref.numel() else 0.0
     err = (got - ref).abs()
