@@ -28,6 +28,11 @@
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*).
  *   - return 0 on success, non-zero on error; dibr_last_error() gives a thread-local message.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ *   - one DibrPass describes one rasterisation: set-up, forward and backward must be called with the SAME sizes
+ *     and scalar parameters (the set-up kernel already bins the faces into screen tiles with the expanded
+ *     bboxes, so `expand`, `multiplier`, `height`, `width` are baked into the workspace).
+ *   - limits: image sides <= 16384, batch <= 4096, num_attr <= DIBR_MAX_ATTR, knum <= 250; the workspace
+ *     (dibr_workspace_bytes) grows with tiles x faces / 8 bytes for the tile bitmaps.
  *
  * Image/face layout
  *   images b = 0..batch-1; image b owns faces [face_offsets[b], face_offsets[b+1]) of one global

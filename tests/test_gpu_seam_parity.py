@@ -113,7 +113,7 @@ def test_cpu_tensor_raises():
 
 
 def test_dense_mesh_multi_batch_lists():
-    """20k faces on a 64x64 image: > 1024 faces per 32x32 tile, so the tile lists are processed in several batches
+    """20k faces on a 64x64 image: > 512 faces per 16x16 tile, so the tile lists are processed in several batches
     (forward re-scans for the soft pass) and the K cap is active almost everywhere near the silhouette."""
     from self6dpp_b200 import synth
     mesh = synth.icosphere(5, radius=0.05, noise_sigma=0.002, seed=3)        # 20480 faces
