@@ -208,7 +208,10 @@ int dibr_render_step(const DibrStep *step, void *stream);
  * Clouds are padded: sample b of cloud i occupies rows [b*stride_i, b*stride_i + count_i[b]) of xyz_i ([batch*stride_i, 3]);
  * count_i == NULL means every row is a point (the reference's dense [b, n, 3] layout).  dist = squared distance to the
  * nearest point of the other cloud, idx = its row within the sample (first minimum in ascending order).  Rows beyond
- * count are not written by the forward and get zero gradient. */
+ * count are not written by the forward and get zero gradient.
+ * With a workspace (dibr_nnd_workspace_bytes, 256-byte aligned, the SAME buffer for the forward and its backward) the
+ * search runs on a uniform grid over the target cloud and the backward on an inverse index -- same answers bit for
+ * bit (coordinates must be finite); with workspace == NULL both are the reference's exhaustive O(n m) loops. */
 typedef struct DibrNnd {
     int32_t batch, stride1, stride2, reserved;
     const int32_t *count1, *count2;          /* device [batch] or NULL */
@@ -217,7 +220,10 @@ typedef struct DibrNnd {
     int32_t *idx1, *idx2;
     const float *graddist1, *graddist2;      /* backward inputs */
     float *gradxyz1, *gradxyz2;              /* backward outputs [batch*stride_i, 3] */
+    void *workspace;                         /* optional scratch, see above */
+    size_t workspace_bytes;
 } DibrNnd;
+int dibr_nnd_workspace_bytes(const DibrNnd *p, size_t *bytes);
 int dibr_nnd_forward(const DibrNnd *p, void *stream);
 int dibr_nnd_backward(const DibrNnd *p, void *stream);
 

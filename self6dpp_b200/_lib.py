@@ -65,12 +65,13 @@ class DibrNnd(ctypes.Structure):
         ("count1", _c_i32p), ("count2", _c_i32p), ("xyz1", _c_f32p), ("xyz2", _c_f32p),
         ("dist1", _c_f32p), ("dist2", _c_f32p), ("idx1", _c_i32p), ("idx2", _c_i32p),
         ("graddist1", _c_f32p), ("graddist2", _c_f32p), ("gradxyz1", _c_f32p), ("gradxyz2", _c_f32p),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
     ]
 
 
 EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_device_count", "dibr_workspace_bytes",
            "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
-           "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_launch_count"]
+           "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_launch_count"]
 
 _lib = None
 
@@ -111,6 +112,8 @@ def load():
     lib.dibr_render_step.restype = ctypes.c_int
     if lib.dibr_sizeof_step() != ctypes.sizeof(DibrStep):
         raise RuntimeError("DibrStep mirror out of date")
+    lib.dibr_nnd_workspace_bytes.argtypes = [ctypes.POINTER(DibrNnd), ctypes.POINTER(ctypes.c_size_t)]
+    lib.dibr_nnd_workspace_bytes.restype = ctypes.c_int
     for name in ("dibr_nnd_forward", "dibr_nnd_backward"):
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrNnd), ctypes.c_void_p]

@@ -281,9 +281,28 @@ static int nnd_params(const DibrNnd* p, dibr::NndParams& n, bool backward) {
     return 0;
 }
 
+int dibr_nnd_workspace_bytes(const DibrNnd* p, size_t* bytes) {
+    if (!p || !bytes) return fail("null argument");
+    if (p->batch < 0 || p->stride1 < 0 || p->stride2 < 0) return fail("nnd: negative sizes");
+    *bytes = dibr::nnd_grid_workspace_bytes(p->batch, p->stride1, p->stride2);
+    return 0;
+}
+
+static int nnd_check_ws(const DibrNnd* p) {
+    if (((uintptr_t)p->workspace & 255u) != 0) return fail("nnd: workspace must be 256-byte aligned");
+    const size_t need = dibr::nnd_grid_workspace_bytes(p->batch, p->stride1, p->stride2);
+    if (p->workspace_bytes < need) return fail("nnd: workspace too small: %zu < %zu", p->workspace_bytes, need);
+    return 0;
+}
+
 int dibr_nnd_forward(const DibrNnd* p, void* stream) {
     dibr::NndParams n;
     if (int e = nnd_params(p, n, false)) return e;
+    if (p->workspace) {
+        if (int e = nnd_check_ws(p)) return e;
+        g_launches += 5;
+        return cuda_fail("dibr_nnd_forward", dibr::launch_nnd_forward_grid(n, p->workspace, (cudaStream_t)stream));
+    }
     g_launches += 2;
     return cuda_fail("dibr_nnd_forward", dibr::launch_nnd_forward(n, (cudaStream_t)stream));
 }
@@ -291,6 +310,11 @@ int dibr_nnd_forward(const DibrNnd* p, void* stream) {
 int dibr_nnd_backward(const DibrNnd* p, void* stream) {
     dibr::NndParams n;
     if (int e = nnd_params(p, n, true)) return e;
+    if (p->workspace) {
+        if (int e = nnd_check_ws(p)) return e;
+        g_launches += 5;
+        return cuda_fail("dibr_nnd_backward", dibr::launch_nnd_backward_grid(n, p->workspace, (cudaStream_t)stream));
+    }
     g_launches += 2;
     return cuda_fail("dibr_nnd_backward", dibr::launch_nnd_backward(n, (cudaStream_t)stream));
 }

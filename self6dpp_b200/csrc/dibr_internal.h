@@ -171,6 +171,9 @@ struct NndParams {
 };
 
 int launch_nnd_forward(const NndParams& P, cudaStream_t stream);
+size_t nnd_grid_workspace_bytes(int batch, int stride1, int stride2);
+int launch_nnd_forward_grid(const NndParams& P, void* workspace, cudaStream_t stream);
+int launch_nnd_backward_grid(const NndParams& P, void* workspace, cudaStream_t stream);
 int launch_nnd_backward(const NndParams& P, cudaStream_t stream);
 int launch_setup_faces(const SetupParams& P, cudaStream_t stream);
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream);

@@ -26,8 +26,31 @@ def _launch(fn_name, p, device):
         _lib.check(getattr(_lib.load(), fn_name)(ctypes.byref(p), _stream(device)), fn_name)
 
 
+_WS_CACHE = {}
+
+
+def _workspace(p, device):
+    """scratch of the grid search / inverse index, reused between calls of the same shape (stream order keeps a forward
+    and the backward that follows it consistent; concurrent streams need their own call sites)"""
+    n = ctypes.c_size_t(0)
+    _lib.check(_lib.load().dibr_nnd_workspace_bytes(ctypes.byref(p), ctypes.byref(n)), "dibr_nnd_workspace_bytes")
+    key = (str(device), n.value)
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        if len(_WS_CACHE) > 8:
+            _WS_CACHE.clear()
+        ws = torch.empty(n.value + 256, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    off = (-ws.data_ptr()) % 256
+    p.workspace, p.workspace_bytes = ws.data_ptr() + off, n.value
+    return ws
+
+
 class NNDFunction(Function):
-    """Padded clouds: sample b of cloud i = rows [0, count_i[b]) of xyz_i[b] (count None: all rows)."""
+    """Padded clouds: sample b of cloud i = rows [0, count_i[b]) of xyz_i[b] (count None: all rows).
+    ``exhaustive=True`` runs the reference's O(n m) loops instead of the grid search (same answers)."""
+
+    exhaustive = False
 
     @staticmethod
     def forward(ctx, xyz1, xyz2, count1=None, count2=None):
@@ -49,7 +72,10 @@ class NNDFunction(Function):
         p.count1, p.count2 = _lib.ptr(c1), _lib.ptr(c2)
         p.xyz1, p.xyz2 = _lib.ptr(x1), _lib.ptr(x2)
         p.dist1, p.dist2, p.idx1, p.idx2 = _lib.ptr(dist1), _lib.ptr(dist2), _lib.ptr(idx1), _lib.ptr(idx2)
+        ctx.use_grid = not NNDFunction.exhaustive
+        keep = _workspace(p, device) if ctx.use_grid else None
         _launch("dibr_nnd_forward", p, device)
+        del keep
         ctx.save_for_backward(x1, x2, idx1, idx2, *( [c1] if c1 is not None else []), *([c2] if c2 is not None else []))
         ctx.has_counts = (c1 is not None, c2 is not None)
         ctx.mark_non_differentiable(idx1, idx2)
@@ -74,7 +100,9 @@ class NNDFunction(Function):
         p.count1, p.count2 = _lib.ptr(c1), _lib.ptr(c2)
         p.xyz1, p.xyz2, p.idx1, p.idx2 = _lib.ptr(x1), _lib.ptr(x2), _lib.ptr(idx1), _lib.ptr(idx2)
         p.graddist1, p.graddist2, p.gradxyz1, p.gradxyz2 = _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(gx1), _lib.ptr(gx2)
+        keep = _workspace(p, device) if ctx.use_grid else None
         _launch("dibr_nnd_backward", p, device)
+        del keep
         return gx1, gx2, None, None
 
 

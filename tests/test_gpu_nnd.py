@@ -93,3 +93,52 @@ def test_nnd_cpu_tensor_raises():
     from self6dpp_b200.nndistance import nnd
     with pytest.raises(RuntimeError):
         nnd(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+
+
+def _both(x1, c1, x2, c2, g1, g2):
+    """grid search + inverse-index backward vs the exhaustive kernels on the same inputs"""
+    from self6dpp_b200 import nndistance as ND
+    outs = []
+    for exhaustive in (False, True):
+        ND.NNDFunction.exhaustive = exhaustive
+        try:
+            X1, X2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+            d1, d2, i1, i2 = ND.nnd_padded(X1, c1, X2, c2)
+            ((d1 * g1).sum() + (d2 * g2).sum()).backward()
+            outs.append((d1.detach(), d2.detach(), i1, i2, X1.grad, X2.grad))
+        finally:
+            ND.NNDFunction.exhaustive = False
+    return outs
+
+
+@pytest.mark.parametrize("case", ["surfaces", "far_apart", "duplicates_and_lines", "tiny_and_empty", "crowd"])
+def test_grid_search_is_bit_identical_to_the_exhaustive_search(case):
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    B, S1, S2 = 3, 4000, 5000
+    x1, x2 = torch.zeros(B, S1, 3), torch.zeros(B, S2, 3)
+    c1, c2 = torch.full((B,), S1, dtype=torch.int32), torch.full((B,), S2, dtype=torch.int32)
+
+    def surface(n, shift):
+        uv = torch.rand(n, 2, generator=g) * 0.12 - 0.06
+        z = 0.8 + 0.3 * uv[:, 0] ** 2 - 0.2 * uv[:, 1] + 0.001 * torch.randn(n, generator=g)
+        return torch.stack((uv[:, 0], uv[:, 1], z), 1) + torch.tensor(shift)
+    for b in range(B):
+        x1[b], x2[b] = surface(S1, [0.0, 0.0, 0.0]), surface(S2, [0.002 * b, -0.001, 0.003])
+    if case == "far_apart":                       # every query is far outside the target's box: the exhaustive fallback
+        x2 += torch.tensor([0.5, -0.3, 0.4])
+    elif case == "duplicates_and_lines":
+        x2[0, 100:200] = x2[0, 5]                 # equal minima: the lowest index must win
+        x1[1, :, 1:] = 0.0                        # a cloud on a line: two grid axes collapse
+        x2[1, :, 1:] = 0.0
+        x1[2] = torch.round(x1[2] * 500) / 500    # points on a lattice: many exact ties
+        x2[2] = torch.round(x2[2] * 500) / 500
+    elif case == "tiny_and_empty":
+        c1 = torch.tensor([1, 0, 3], dtype=torch.int32)
+        c2 = torch.tensor([2, 7, 0], dtype=torch.int32)
+    elif case == "crowd":                         # thousands of queries share one nearest neighbour (backward fallback)
+        x2[0, :, :] = x2[0, :, :] * 0.001 + torch.tensor([0.3, 0.3, 1.5])
+        x2[1, 10:] = x2[1, 3]
+    g1, g2 = torch.randn(B, S1, generator=g).to(DEV), torch.randn(B, S2, generator=g).to(DEV)
+    a, e = _both(x1.to(DEV), c1.to(DEV), x2.to(DEV), c2.to(DEV), g1, g2)
+    for k, name in enumerate(("dist1", "dist2", "idx1", "idx2", "grad1", "grad2")):
+        assert torch.equal(a[k], e[k]), f"{case}: {name} differs at {int((a[k] != e[k]).sum())} entries"
