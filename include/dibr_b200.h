@@ -145,6 +145,9 @@ typedef struct DibrPass {
     const int32_t *vert_face_ptr;  /* CSR vertex -> incident (face,corner) list, per packed mesh vertex: [sum verts + 1] */
     const int32_t *vert_face_idx;  /* [3 * sum mesh faces] entries face*3+corner, ascending */
     int32_t num_cams;
+    int32_t verts_stride;          /* floats per row of verts: 0 or 3 = packed [.,3]; 4 = rows padded to 16 B (one 128-bit gather per vertex) */
+    int32_t vert_attr_stride;      /* floats per row of vert_attr: 0 = vert_attr_dim; a multiple of 4 (and a 16 B aligned base) turns the
+                                      per-corner attribute gather into 128-bit loads */
     int32_t reserved0;
 } DibrPass;
 

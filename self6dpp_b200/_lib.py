@@ -40,7 +40,8 @@ class DibrPass(ctypes.Structure):
         ("out", ctypes.c_void_p * 6), ("grad_out", ctypes.c_void_p * 6),
         ("min_output", ctypes.c_int32), ("out_min_ordered", ctypes.c_void_p),
         ("vert_face_ptr", _c_i32p), ("vert_face_idx", _c_i32p),
-        ("num_cams", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("num_cams", ctypes.c_int32), ("verts_stride", ctypes.c_int32), ("vert_attr_stride", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
     ]
 
 

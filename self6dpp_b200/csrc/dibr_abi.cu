@@ -97,6 +97,8 @@ dibr::SetupParams setup_params(const DibrPass* p) {
     s.points3d = p->points3d; s.points2d = p->points2d; s.normalz = p->normalz;
     s.num_instances = p->num_instances; s.inst_desc = p->inst_desc; s.verts = p->verts; s.mesh_faces = p->mesh_faces;
     s.vert_attr = p->vert_attr; s.vert_attr_dim = p->vert_attr_dim; s.attr_flags = p->attr_flags; s.num_attr = p->num_attr;
+    s.verts_stride = p->verts_stride > 0 ? p->verts_stride : 3;
+    s.vert_attr_stride = p->vert_attr_stride > 0 ? p->vert_attr_stride : p->vert_attr_dim;
     s.cam_rot = p->cam_rot; s.cam_pos = p->cam_pos; s.cam_proj = p->cam_proj;
     s.face_attr = p->face_attr; s.face_normal = p->face_normal;
     s.ws = carve(p, p->workspace);
@@ -157,6 +159,8 @@ int dibr_setup_meshes(const DibrPass* p, void* stream) {
     const int d = p->vert_attr_dim + ((p->attr_flags & 1) ? 1 : 0) + ((p->attr_flags & 2) ? 1 : 0);
     if (d != p->num_attr) return fail("setup_meshes: vert_attr_dim + flags = %d but num_attr = %d", d, p->num_attr);
     if (p->vert_attr_dim > 0 && !p->vert_attr) return fail("setup_meshes: vert_attr is null");
+    if (p->verts_stride != 0 && p->verts_stride < 3) return fail("setup_meshes: verts_stride %d < 3", p->verts_stride);
+    if (p->vert_attr_stride != 0 && p->vert_attr_stride < p->vert_attr_dim) return fail("setup_meshes: vert_attr_stride %d < vert_attr_dim %d", p->vert_attr_stride, p->vert_attr_dim);
     const dibr::SetupParams s = setup_params(p);
     g_launches += 2;
     return cuda_fail("dibr_setup_meshes", dibr::launch_setup_meshes(s, (cudaStream_t)stream));
@@ -249,6 +253,7 @@ int dibr_backward_meshes(const DibrPass* p, void* stream) {
     dibr::MeshBwdParams m;
     memset(&m, 0, sizeof(m));
     m.num_instances = p->num_instances; m.inst_desc = p->inst_desc; m.verts = p->verts;
+    m.verts_stride = p->verts_stride > 0 ? p->verts_stride : 3;
     m.cam_rot = p->pose_R ? w.cam_rot : p->cam_rot; m.cam_pos = p->pose_R ? w.cam_pos : p->cam_pos;
     m.cam_proj = p->pose_R ? w.cam_proj : p->cam_proj;
     m.pose_R = p->pose_R; m.pose_t = p->pose_t; m.grad_pose_R = p->grad_pose_R; m.grad_pose_t = p->grad_pose_t;

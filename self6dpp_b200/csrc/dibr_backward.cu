@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(256) mesh_vertex_grad_kernel(MeshBwdParams P)
             for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) if (d < A) o[d] = ga[d];
         }
         // forward recomputation (cheap) for the chain rule
-        const float* vp = P.verts + (size_t)(vbase + v) * 3;
+        const float* vp = P.verts + (size_t)(vbase + v) * P.verts_stride;
         const float d0 = vp[0] - T[0], d1 = vp[1] - T[1], d2 = vp[2] - T[2];
         float pc[3];
 #pragma unroll

@@ -47,6 +47,7 @@ struct SetupParams {
     const int32_t* mesh_faces;
     const float* vert_attr;
     int vert_attr_dim, attr_flags, num_attr;
+    int verts_stride, vert_attr_stride;      // floats per row (3 / vert_attr_dim when packed)
     const float* cam_rot;
     const float* cam_pos;
     const float* cam_proj;
@@ -118,6 +119,7 @@ struct MeshBwdParams {
     int num_instances;
     const int32_t* inst_desc;
     const float* verts;
+    int verts_stride;
     const float* cam_rot;
     const float* cam_pos;
     const float* cam_proj;

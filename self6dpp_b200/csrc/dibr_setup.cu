@@ -94,13 +94,10 @@ __global__ void __launch_bounds__(256) setup_faces_kernel(SetupParams P)
     store_face(P, g, b, ax, ay, bx, by, cx, cy, az, bz, cz, nz, active);
 }
 
-__device__ __forceinline__ int instance_of_face(int g, int n, const int32_t* __restrict__ desc) {
-    int lo = 0, hi = n;                  // last i with out_face_base[i] <= g
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (desc[mid * INST_STRIDE + I_OUT_FACE_BASE] <= g) lo = mid; else hi = mid; }
-    return lo;
-}
-
-__global__ void __launch_bounds__(256) setup_meshes_kernel(SetupParams P)
+#ifndef DIBR_SETUP_MIN_CTAS
+#define DIBR_SETUP_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(256, DIBR_SETUP_MIN_CTAS) setup_meshes_kernel(SetupParams P)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     write_tables(P, g);
@@ -108,12 +105,19 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(SetupParams P)
     float x2[3] = {0, 0, 0}, y2[3] = {0, 0, 0}, zc[3] = {0, 0, 0};
     float nz = 0.f;
     int b = -1;
-    // instance lookup once per warp (faces of an instance are contiguous: lanes only ever step forward a little)
+    // instance lookup once per warp, all lanes at once: lane i looks at instances i, i+32, ...; the instance of the warp's
+    // first face is the number of instances that start at or before it, minus one (faces of an instance are
+    // contiguous, so lanes then only ever step forward a little)
     int inst0 = 0;
     {
         const int gw = min(blockIdx.x * blockDim.x + (threadIdx.x & ~31), max(P.total_faces - 1, 0));
-        if ((threadIdx.x & 31) == 0) inst0 = instance_of_face(gw, P.num_instances, P.inst_desc);
-        inst0 = __shfl_sync(0xffffffffu, inst0, 0);
+        int below = 0;
+        for (int i0 = 0; i0 < P.num_instances; i0 += 32) {
+            const int i = i0 + (threadIdx.x & 31);
+            const bool le = (i < P.num_instances) && (__ldg(P.inst_desc + i * INST_STRIDE + I_OUT_FACE_BASE) <= gw);
+            below += __popc(__ballot_sync(0xffffffffu, le));
+        }
+        inst0 = max(below - 1, 0);
     }
     if (active) {
         int inst = inst0;
@@ -171,12 +175,21 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(SetupParams P)
         }
         const float m = (float)P.multiplier;
         const int A = P.vert_attr_dim, D = P.num_attr;
+        const bool vec_verts = (P.verts_stride == 4) && ((reinterpret_cast<uintptr_t>(P.verts) & 15) == 0);
+        const bool vec_attr = A > 0 && (P.vert_attr_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.vert_attr) & 15) == 0);
         float pc[3][3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const int vid = fv[c];
-            const float* v = P.verts + (size_t)(de[I_VERT_BASE] + vid) * 3;
-            const float d0 = __fsub_rn(v[0], T[0]), d1 = __fsub_rn(v[1], T[1]), d2 = __fsub_rn(v[2], T[2]);
+            float vx, vy, vz;
+            if (vec_verts) {                                     // rows padded to 16 B: one 128-bit gather
+                const float4 v4 = __ldg(reinterpret_cast<const float4*>(P.verts) + (de[I_VERT_BASE] + vid));
+                vx = v4.x; vy = v4.y; vz = v4.z;
+            } else {
+                const float* v = P.verts + (size_t)(de[I_VERT_BASE] + vid) * P.verts_stride;
+                vx = v[0]; vy = v[1]; vz = v[2];
+            }
+            const float d0 = __fsub_rn(vx, T[0]), d1 = __fsub_rn(vy, T[1]), d2 = __fsub_rn(vz, T[2]);
 #pragma unroll
             for (int j = 0; j < 3; j++)
                 pc[c][j] = __fmaf_rn(R[j * 3 + 2], d2, __fmaf_rn(R[j * 3 + 1], d1, __fmul_rn(R[j * 3 + 0], d0)));
@@ -189,12 +202,25 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(SetupParams P)
             zc[c] = pc[c][2];
             // per-face corner attributes: [vertex attrs | ones | view depth], 128-bit stores when D % 4 == 0
             float* fa = P.face_attr + ((size_t)g * 3 + c) * D;
-            const float* va = P.vert_attr + (size_t)(de[I_ATTR_BASE] + vid) * A;
+            const float* va = P.vert_attr + (size_t)(de[I_ATTR_BASE] + vid) * P.vert_attr_stride;
+            float raw[DIBR_MAX_ATTR_INTERNAL];
+            if (vec_attr) {                                      // rows padded to a multiple of 16 B
+#pragma unroll
+                for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d += 4) {
+                    if (d < A) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(va + d));
+                        raw[d] = t.x; raw[d + 1] = t.y; raw[d + 2] = t.z; raw[d + 3] = t.w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) if (d < A) raw[d] = __ldg(va + d);
+            }
             float av[DIBR_MAX_ATTR_INTERNAL];
 #pragma unroll
             for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) {
                 float x = 0.f;
-                if (d < A) x = __ldg(va + d);
+                if (d < A) x = raw[d];
                 else if (d == A && (P.attr_flags & 1)) x = 1.0f;
                 else if (d == A + (P.attr_flags & 1) && (P.attr_flags & 2)) x = -pc[c][2];
                 av[d] = x;

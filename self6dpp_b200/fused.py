@@ -130,6 +130,7 @@ class RenderMeshes(Function):
             p.inst_desc = _lib.ptr(meta["inst_desc"])
             p.verts, p.mesh_faces = _lib.ptr(verts_c), _lib.ptr(pack.faces)
             p.vert_attr, p.vert_attr_dim, p.attr_flags = _lib.ptr(vattr_c), A, flags
+            p.verts_stride, p.vert_attr_stride = int(meta.get("verts_stride", 0)), int(meta.get("vert_attr_stride", 0))
             if meta.get("pose_mode"):      # cam_rot / cam_pos / cam_proj carry R [I,3,3], t [I,3], K [nK,3,3]
                 p.pose_R, p.pose_t, p.pose_K = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
                 p.num_K = int(proj_c.shape[0])
@@ -186,6 +187,7 @@ class RenderMeshes(Function):
             p.inst_desc = _lib.ptr(meta["inst_desc"])
             p.verts = _lib.ptr(verts_c)
             p.vert_attr_dim, p.attr_flags = A, flags
+            p.verts_stride, p.vert_attr_stride = int(meta.get("verts_stride", 0)), int(meta.get("vert_attr_stride", 0))
             pose_mode = bool(meta.get("pose_mode"))
             if pose_mode:
                 p.pose_R, p.pose_t, p.pose_K = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)

@@ -102,6 +102,8 @@ class _ModelRegistry(object):
         faces = [_faces_int32(m["faces"]) for m in self.models]
         self.pack = fused.MeshPack(verts, faces, verts[0].device)
         self.verts = torch.cat(verts, dim=0).contiguous() if len(verts) > 1 else verts[0].contiguous()
+        # rows padded to 16 B for the kernels (one 128-bit gather per vertex instead of three scalar ones)
+        self.verts4 = torch.cat((self.verts, torch.zeros_like(self.verts[:, :1])), dim=1).contiguous()
         pk = self.pack
         self.table = np.stack([pk.vert_base[:-1], np.asarray(pk.num_verts), pk.face_base[:-1], np.asarray(pk.num_faces)],
                               axis=1).astype(np.int64)
@@ -116,6 +118,9 @@ class _ModelRegistry(object):
             per_model = [torch.cat([m[n].detach().reshape(-1, m[n].shape[-1]) for n in names], dim=1) if len(names) > 1
                          else m[names[0]].detach().reshape(-1, m[names[0]].shape[-1]) for m in self.models]
             hit = (torch.cat(per_model, dim=0) if len(per_model) > 1 else per_model[0]).contiguous()
+            pad = (-hit.shape[1]) % 4                                  # rows padded to a multiple of 16 B, same reason
+            if pad:
+                hit = torch.cat((hit, hit.new_zeros(hit.shape[0], pad)), dim=1).contiguous()
             self.attrs[key] = hit
         return hit
 
@@ -176,7 +181,9 @@ class Renderer_dibr(object):
                     out_split=split, inst_desc=dev[:B * fused.INST_STRIDE],
                     face_offsets=dev[B * fused.INST_STRIDE:B * fused.INST_STRIDE + nimg + 1],
                     pose_mode=True, znear=float(znear), zfar=float(zfar), min_output=min_output)
-        res = fused.render_meshes(reg.verts, vattr, R, ts.reshape(B, 3), K, meta)
+        meta["verts_stride"] = 4
+        meta["vert_attr_stride"] = int(vattr.shape[1]) if names else 0
+        res = fused.render_meshes(reg.verts4, vattr, R, ts.reshape(B, 3), K, meta)
         return list(res[:-2]), res[-2], meta
 
     # ------------------------------------------------------------------------------------------

@@ -32,7 +32,7 @@ class _PassBuffers(object):
         self.flags = fused.FLAG_ONES | (fused.FLAG_DEPTH if "depth" in mode else 0)
         self.A = 3 * len(self.names)
         self.D = sum(self.split)
-        self.vattr = reg.attr_matrix(self.names) if self.names else torch.zeros(0, 1, dtype=torch.float32, device=device)
+        self.vattr = reg.attr_matrix(self.names) if self.names else torch.zeros(0, 4, dtype=torch.float32, device=device)
         f32 = dict(dtype=torch.float32, device=device)
         self.outs = [torch.empty(batch, height, width, c, **f32) for c in self.split]
         self.out = dict(zip(self.keys, self.outs))
@@ -52,9 +52,10 @@ class _PassBuffers(object):
         nbytes = _lib.workspace_bytes(p)                      # worst case: every sample renders the largest mesh
         self.ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=device)
         p.workspace, p.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
-        p.verts, p.mesh_faces = reg.verts.data_ptr(), reg.pack.faces.data_ptr()
+        p.verts, p.mesh_faces = reg.verts4.data_ptr(), reg.pack.faces.data_ptr()          # rows padded to 16 B
         p.vert_attr = self.vattr.data_ptr() if self.A else None
         p.vert_attr_dim, p.attr_flags = self.A, self.flags
+        p.verts_stride, p.vert_attr_stride = 4, int(self.vattr.shape[1]) if self.A else 0
         p.face_attr = self.face_attr.data_ptr()
         p.improb, p.imidx, p.imcomp = self.improb.data_ptr(), self.imidx.data_ptr(), self.imcomp.data_ptr()
         p.num_outputs = len(self.split)
