@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "../../include/dibr_b200.h"
+#include <mutex>
 #include "dibr_internal.h"
 
 namespace {
@@ -333,6 +334,26 @@ __global__ void pack_pose_grad_kernel(const float* __restrict__ gR, const float*
     out[i] = (k < 9) ? gR[inst * 9 + k] : gt[inst * 3 + (k - 9)];
 }
 
+// one side stream + fork/join events per device, created on first use and kept for the life of the process
+struct AuxStream { cudaStream_t stream; cudaEvent_t fork, join; };
+static AuxStream* aux_stream() {
+    static std::mutex mu;
+    static AuxStream slots[64];
+    static bool ready[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ready[dev]) {
+        AuxStream a;
+        if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        slots[dev] = a;
+        ready[dev] = true;
+    }
+    return &slots[dev];
+}
+
 int dibr_render_step(const DibrStep* st, void* stream) {
     if (!st) return fail("null DibrStep");
     cudaStream_t cs = (cudaStream_t)stream;
@@ -345,14 +366,24 @@ int dibr_render_step(const DibrStep* st, void* stream) {
     const float* nin[2] = {st->student_normal_in, st->teacher_normal_in};
     const float* nmask[2] = {st->student_mask_in, st->teacher_mask_in};
     float* nout[2] = {st->student_normal_out, st->teacher_normal_out};
+    // The teacher rasterisation depends on nothing the student pass or the backward produce (and vice versa): it runs on
+    // a side stream, forked after the staging copy and joined at the end of the call, so its CTAs fill the tails and
+    // stalls of the other chain.  Everything is ordered in `stream` again when the call returns.
+    AuxStream* aux = (st->student.num_instances > 0 && st->teacher.num_instances > 0) ? aux_stream() : nullptr;
+    if (aux) {
+        cudaError_t e = cudaEventRecord(aux->fork, cs);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(aux->stream, aux->fork, 0);
+        if (e != cudaSuccess) return cuda_fail("render_step fork", (int)e);
+    }
     for (int k = 0; k < 2; k++) {
         const DibrPass* p = passes[k];
         if (p->num_instances <= 0) continue;
-        if (int e = dibr_setup_meshes(p, stream)) return e;
-        if (int e = dibr_forward(p, stream)) return e;
+        void* ks = (k == 1 && aux) ? (void*)aux->stream : stream;
+        if (int e = dibr_setup_meshes(p, ks)) return e;
+        if (int e = dibr_forward(p, ks)) return e;
         if (nin[k]) {
             if (!p->out_min_ordered || p->min_output < 0) return fail("render_step: normal map needs min_output/out_min_ordered");
-            if (int e = dibr_normal_map(nin[k], nmask[k], p->out_min_ordered, nout[k], (long long)p->batch * p->height * p->width, stream)) return e;
+            if (int e = dibr_normal_map(nin[k], nmask[k], p->out_min_ordered, nout[k], (long long)p->batch * p->height * p->width, ks)) return e;
         }
     }
     if (st->run_backward) {
@@ -369,6 +400,11 @@ int dibr_render_step(const DibrStep* st, void* stream) {
                 e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)n, cudaMemcpyDeviceToHost, cs);
             if (e != cudaSuccess) return cuda_fail("render_step pose gradients", (int)e);
         }
+    }
+    if (aux) {
+        cudaError_t e = cudaEventRecord(aux->join, aux->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, aux->join, 0);
+        if (e != cudaSuccess) return cuda_fail("render_step join", (int)e);
     }
     return 0;
 }
