@@ -345,7 +345,11 @@ static AuxStream* aux_stream() {
     std::lock_guard<std::mutex> lock(mu);
     if (!ready[dev]) {
         AuxStream a;
-        if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        // the side stream carries the LONG chain (student forward + backward) at high priority; the short teacher chain stays on
+        // the caller's stream and fills in behind it
+        if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, greatest) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         slots[dev] = a;
@@ -366,9 +370,11 @@ int dibr_render_step(const DibrStep* st, void* stream) {
     const float* nin[2] = {st->student_normal_in, st->teacher_normal_in};
     const float* nmask[2] = {st->student_mask_in, st->teacher_mask_in};
     float* nout[2] = {st->student_normal_out, st->teacher_normal_out};
-    // The teacher rasterisation depends on nothing the student pass or the backward produce (and vice versa): it runs on
-    // a side stream, forked after the staging copy and joined at the end of the call, so its CTAs fill the tails and
-    // stalls of the other chain.  Everything is ordered in `stream` again when the call returns.
+    // The teacher rasterisation depends on nothing the student pass or the backward produce (and vice versa).  The long
+    // chain (student set-up, forward, backward, pose-gradient read-back) goes to a high-priority side stream, forked
+    // after the staging copy; the teacher pass stays on the caller's stream and its CTAs fill the tails and stalls of the
+    // long chain.  The caller's stream waits for the side stream before the call returns, so for the caller everything
+    // is ordered in `stream` as before.
     AuxStream* aux = (st->student.num_instances > 0 && st->teacher.num_instances > 0) ? aux_stream() : nullptr;
     if (aux) {
         cudaError_t e = cudaEventRecord(aux->fork, cs);
@@ -378,7 +384,7 @@ int dibr_render_step(const DibrStep* st, void* stream) {
     for (int k = 0; k < 2; k++) {
         const DibrPass* p = passes[k];
         if (p->num_instances <= 0) continue;
-        void* ks = (k == 1 && aux) ? (void*)aux->stream : stream;
+        void* ks = (k == 0 && aux) ? (void*)aux->stream : stream;
         if (int e = dibr_setup_meshes(p, ks)) return e;
         if (int e = dibr_forward(p, ks)) return e;
         if (nin[k]) {
@@ -388,16 +394,18 @@ int dibr_render_step(const DibrStep* st, void* stream) {
     }
     if (st->run_backward) {
         const DibrPass* p = &st->student;
-        if (int e = dibr_backward_faces(p, stream)) return e;
-        if (int e = dibr_backward_meshes(p, stream)) return e;
+        void* ls = aux ? (void*)aux->stream : stream;           // the student chain's stream
+        cudaStream_t lcs = (cudaStream_t)ls;
+        if (int e = dibr_backward_faces(p, ls)) return e;
+        if (int e = dibr_backward_meshes(p, ls)) return e;
         if (st->device_grad_pose) {
             if (!p->grad_pose_R || !p->grad_pose_t) return fail("render_step: pose-gradient buffers are null");
             const int n = p->num_instances;
-            pack_pose_grad_kernel<<<(n * 12 + 127) / 128, 128, 0, cs>>>(p->grad_pose_R, p->grad_pose_t, st->device_grad_pose, n);
+            pack_pose_grad_kernel<<<(n * 12 + 127) / 128, 128, 0, lcs>>>(p->grad_pose_R, p->grad_pose_t, st->device_grad_pose, n);
             g_launches += 1;
             cudaError_t e = cudaGetLastError();
             if (e == cudaSuccess && st->host_grad_pose)
-                e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)n, cudaMemcpyDeviceToHost, cs);
+                e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)n, cudaMemcpyDeviceToHost, lcs);
             if (e != cudaSuccess) return cuda_fail("render_step pose gradients", (int)e);
         }
     }
