@@ -30,7 +30,15 @@ def _require_cuda_f32(name, t):
         raise RuntimeError(f"{name} must be float32, got {t.dtype}")
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(device):
+    """cudaStream_t of torch's current stream on ``device`` (the raw accessor is ~40x cheaper than building a
+    torch.cuda.Stream object per call)"""
+    if _RAW_STREAM is not None:
+        index = device.index if isinstance(device, torch.device) else torch.device(device).index
+        return ctypes.c_void_p(_RAW_STREAM(torch.cuda.current_device() if index is None else index))
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

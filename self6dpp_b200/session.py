@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib, fused
+from .rasterizer import _stream
 from .renderer_dibr import _ModelRegistry
 
 _MODE_ATTR = (("color", "colors"), ("norm", "normals"), ("xyz", "vertices"))
@@ -203,7 +204,7 @@ class RenderSession(object):
         st.staging_bytes = 4 * self.stage_words if upload else 0       # upload=False: inputs already resident
         st.host_grad_pose = self.g_pose_host.data_ptr() if download else None
         with torch.cuda.device(self.device):
-            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            stream = _stream(self.device)
             _lib.check(self.lib.dibr_render_step(ctypes.byref(st), stream), "dibr_render_step")
         return self.outputs()
 
