@@ -173,7 +173,7 @@ class Renderer_dibr(object):
             hn[B * fused.INST_STRIDE + 1] = int(nf.sum())
         dev = torch.empty_like(host, device=device)
         dev.copy_(host, non_blocking=True)
-        A = 3 * len(names)
+        A = sum(int(models[0][n].shape[-1]) for n in names)          # 3 per colour / normal / xyz set, 2 for uvs
         meta = dict(batch=nimg, height=int(height), width=int(width), attr_dim=A, attr_flags=int(flags),
                     total_faces=int(nf.sum()), num_instances=B, num_inst_verts=int(nv.sum()), pack=reg.pack,
                     knum=fused.DEFAULT_KNUM, multiplier=fused.DEFAULT_MULTIPLIER, delta=fused.DEFAULT_DELTA,
@@ -330,6 +330,33 @@ class Renderer_dibr(object):
         """
         assert self.dib_ren.mode in ["TextureBatch"], self.dib_ren.mode
         ret = {}
+        if uv_type == "vertex" and all("vertex_uvs" in m for m in models):
+            # resident models with per-vertex uvs: the uvs ride through the fused rasterisation as a 2-channel vertex
+            # attribute (one launch for the batch, depth in the same pass); only the texture lookup stays in torch
+            flags = fused.FLAG_ONES | (fused.FLAG_DEPTH if "depth" in mode else 0)
+            split = [2, 1] + ([1] if "depth" in mode else [])
+            fast = self._render_batch_fast(Rs, ts, models, Ks, width, height, znear, zfar, rot_type, ["vertex_uvs"], split, flags)
+            if fast is not None:
+                from .renderer.tex import shade_tex
+                outs, improb, meta = fast
+                self.dib_ren.set_camera_parameters_lazy(Rs, ts, Ks, height, width, znear, zfar, rot_type)
+                uvimg, mask = outs[0], outs[1]
+                shapes = {tuple(m["texture"].shape) for m in models}
+                if len(shapes) == 1:
+                    ret["color"] = shade_tex(uvimg, torch.stack([m["texture"] for m in models]), mask)
+                else:       # textures of different sizes: one lookup per object, as in the reference
+                    ret["color"] = torch.cat([shade_tex(uvimg[i:i + 1], m["texture"][None], mask[i:i + 1]) for i, m in enumerate(models)])
+                ret["prob"] = improb.squeeze(-1)
+                ret["mask"] = mask.squeeze(-1)
+                if "depth" in mode:
+                    ret["depth"] = outs[2].squeeze(-1)
+                if "xyz" in mode:
+                    ren = DIBRenderer(height, width, mode="VertexColorBatch")
+                    ren.set_camera_parameters(self.dib_ren.camera_params)
+                    ret["xyz"], _, _, _ = ren.forward(points=[[m["vertices"][None], _faces_int32(m["faces"])] for m in models],
+                                                      colors=[m["vertices"][None] for m in models])
+                self.last_meta = meta
+                return ret
         self.dib_ren.set_camera_parameters_from_RT_K(Rs, ts, Ks, height, width, near=znear, far=zfar, rot_type=rot_type)
         points, uvs, textures, fts = self._tex_inputs(models, uv_type)
         im, prob, _, mask = self.dib_ren.forward(points=points, uv_bxpx2=uvs, texture_bx3xthxtw=textures, ft_fx3=fts)

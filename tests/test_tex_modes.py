@@ -137,3 +137,43 @@ def test_render_batch_tex_entry_point():
     sc = ren.render_scene_tex(t("Rs"), t("ts"), face_models, K=t("K"), width=W, height=H, uv_type="face")
     assert sc["color"].shape == (H, W, 3) and sc["depth"].shape == (H, W)
     Hh.assert_close("render_scene_tex color", sc["color"], torch.as_tensor(d["TexRenderMulti_im"])[0], rtol=1e-4, atol_rel=1e-4, outlier_frac=3e-3, outlier_tol=2.0)
+
+
+@pytest.mark.gpu
+def test_render_batch_tex_vertex_uv_fast_path_equals_the_module():
+    """per-vertex uvs take the fused rasterisation (uv as a 2-channel vertex attribute, depth in the same pass); the
+    result must be what TexRenderBatch gives through the operator seam, gradients to the pose and the texture included"""
+    from self6dpp_b200 import Renderer_dibr
+    from self6dpp_b200.renderer import tex as T
+    from self6dpp_b200.renderer.cameras import camera_params_from_RT_K
+    dev = torch.device("cuda:0")
+    d = _load()
+    H, W = int(d["H"]), int(d["W"])
+    t = lambda k: torch.tensor(d[k], device=dev)
+    pick = [0, 2, 0]
+    models = [{"vertices": t(f"verts{k}"), "faces": t(f"faces{k}"), "vertex_uvs": t(f"uv{k}"),
+               "texture": t("tex0")[0].clone().requires_grad_(True)} for k in pick]
+    Rs = t("Rs").clone().requires_grad_(True)
+    ts = t("ts").clone().requires_grad_(True)
+    ren = Renderer_dibr(H, W, mode="TextureBatch")
+    out = ren.render_batch_tex(Rs, ts, models, Ks=t("K"), width=W, height=H, uv_type="vertex", mode=["color", "depth"])
+    assert getattr(ren, "last_meta", None) is not None, "fast path not taken"
+    g = torch.Generator().manual_seed(3)
+    gi, gp = torch.randn(out["color"].shape, generator=g).to(dev), torch.randn(out["prob"].shape, generator=g).to(dev)
+    ((out["color"] * gi).sum() + (out["prob"] * gp).sum()).backward()
+    # the module path on the same inputs
+    Rs2, ts2 = t("Rs").clone().requires_grad_(True), t("ts").clone().requires_grad_(True)
+    tex2 = [m["texture"].detach().clone().requires_grad_(True) for m in models]
+    cams = camera_params_from_RT_K(Rs2, ts2, t("K"), H, W, near=0.01, far=100.0, device=dev)
+    im, prob, _, mask = T.TexRenderBatch(H, W)([[m["vertices"][None], m["faces"].long()] for m in models], cams,
+                                               [m["vertex_uvs"][None] for m in models], [x[None] for x in tex2])
+    ((im * gi).sum() + (prob.squeeze(-1) * gp).sum()).backward()
+    Hh.assert_close("color", out["color"], im, rtol=3e-4, atol_rel=3e-4, outlier_frac=3e-3, outlier_tol=2.0)
+    Hh.assert_close("prob", out["prob"], prob.squeeze(-1), rtol=1e-4, atol_rel=1e-4, outlier_frac=3e-3, outlier_tol=2.0)
+    Hh.assert_close("mask", out["mask"], mask.squeeze(-1), rtol=1e-5, atol_rel=1e-5, outlier_frac=3e-3, outlier_tol=2.0)
+    covered = out["mask"] > 0.5
+    assert float((out["depth"][covered] - t("ts")[:, 2].view(3, 1, 1).expand(3, H, W)[covered]).abs().max()) < 0.1
+    for a, b in zip(models, tex2):
+        Hh.assert_close("dL/dtexture", a["texture"].grad, b.grad, rtol=1e-3, atol_rel=1e-3)
+    Hh.assert_close("dL/dR", Rs.grad, Rs2.grad, rtol=2e-2, atol_rel=2e-2)
+    Hh.assert_close("dL/dt", ts.grad, ts2.grad, rtol=2e-2, atol_rel=2e-2)

@@ -60,4 +60,24 @@ def cfg4():
     ret = bren.render_batch(Rs, ts, mb * B, Ks=torch.tensor(synth.K_YCBV, device=DEV), width=W, height=H, mode=["color", "depth", "mask", "prob"])
     torch.autograd.backward([ret["color"], ret["prob"], ret["depth"]], [gbc, gbp, gbd])
 ms = timeit(cfg4, reps=5); out.append({"config": "cfg4 (B=16, 480x640, F=100352, colour+depth+prob fwd+bwd)", "ms": ms, "samples_per_s": 16e3 / ms})
+# texture batch: 32 textured cfg2 objects, 256x256, vertex uvs, 64x64 textures, fwd + bwd to the pose and the texture
+import bench
+meshes2, student, _ = bench.workload(0)
+def uv_of(v):
+    n = v / np.linalg.norm(v, axis=1, keepdims=True)
+    return np.stack((np.arctan2(n[:, 1], n[:, 0]) / (2 * np.pi) + 0.5, np.arcsin(np.clip(n[:, 2], -1, 1)) / np.pi + 0.5), 1).astype(np.float32)
+tex_models = []
+for m in meshes2:
+    tex_models.append({"vertices": torch.tensor(m["vertices"], device=DEV), "faces": torch.tensor(m["faces"], device=DEV, dtype=torch.int32),
+                       "vertex_uvs": torch.tensor(uv_of(m["vertices"]), device=DEV),
+                       "texture": torch.rand(3, 64, 64, generator=g).to(DEV).requires_grad_(True)})
+cur = [tex_models[int(i)] for i in student["ids"]]
+tren = Renderer_dibr(256, 256, "TextureBatch")
+gtc = torch.randn(32, 256, 256, 3, generator=g).to(DEV); gtp = torch.randn(32, 256, 256, generator=g).to(DEV)
+Kt = torch.tensor(student["Ks"], device=DEV)
+def tex():
+    Rs = torch.tensor(student["Rs"], device=DEV, requires_grad=True); ts = torch.tensor(student["ts"], device=DEV, requires_grad=True)
+    ret = tren.render_batch_tex(Rs, ts, cur, Ks=Kt, width=256, height=256, uv_type="vertex", mode=["color"])
+    torch.autograd.backward([ret["color"], ret["prob"]], [gtc, gtp])
+ms = timeit(tex, reps=5); out.append({"config": "texture batch (B=32, 256x256, cfg2 meshes, TextureBatch colour+prob fwd+bwd, torch vertex/fragment shaders)", "ms": ms, "samples_per_s": 32e3 / ms})
 for o in out: print(json.dumps(o))
