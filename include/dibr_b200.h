@@ -230,6 +230,26 @@ int dibr_nnd_workspace_bytes(const DibrNnd *p, size_t *bytes);
 int dibr_nnd_forward(const DibrNnd *p, void *stream);
 int dibr_nnd_backward(const DibrNnd *p, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Depth map -> compacted point cloud: backproject_th (lib/pysixd/misc.py:350-367) followed by the per-sample boolean
+ * mask `pc[pc[:, :, 2] > 0]` of core/self6dpp/losses/depth_bp_chamfer_loss.py:27-36, for the whole batch, without a
+ * host sync.  points rows [0, count[b]) hold (X, Y, Z) of the pixels with depth > 0 in row-major pixel order (the
+ * order boolean indexing gives); slot maps a pixel to its row (-1: dropped); chunk_count is scratch of
+ * batch * ceil(H*W / 1024) ints.  The backward turns d loss / d points into d loss / d depth. */
+typedef struct DibrBackproject {
+    int32_t batch, height, width, num_K;     /* num_K = 1 (shared intrinsics) or batch */
+    const float *depth;                      /* [batch, H, W] */
+    const float *K;                          /* [num_K, 3, 3] */
+    float *points;                           /* [batch, H*W, 3] */
+    int32_t *count;                          /* [batch] */
+    int32_t *slot;                           /* [batch, H*W] */
+    int32_t *chunk_count;                    /* scratch */
+    const float *grad_points;                /* backward in:  [batch, H*W, 3] */
+    float *grad_depth;                       /* backward out: [batch, H, W] */
+} DibrBackproject;
+int dibr_backproject_compact(const DibrBackproject *p, void *stream);
+int dibr_backproject_compact_backward(const DibrBackproject *p, void *stream);
+
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);
 

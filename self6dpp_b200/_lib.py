@@ -70,9 +70,20 @@ class DibrNnd(ctypes.Structure):
     ]
 
 
+class DibrBackproject(ctypes.Structure):
+    """Mirror of ``struct DibrBackproject`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32), ("num_K", ctypes.c_int32),
+        ("depth", _c_f32p), ("K", _c_f32p), ("points", _c_f32p), ("count", _c_i32p), ("slot", _c_i32p),
+        ("chunk_count", _c_i32p), ("grad_points", _c_f32p), ("grad_depth", _c_f32p),
+    ]
+
+
 EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_device_count", "dibr_workspace_bytes",
            "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
-           "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_launch_count"]
+           "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_backproject_compact",
+           "dibr_backproject_compact_backward", "dibr_launch_count"]
 
 _lib = None
 
@@ -113,6 +124,10 @@ def load():
     lib.dibr_render_step.restype = ctypes.c_int
     if lib.dibr_sizeof_step() != ctypes.sizeof(DibrStep):
         raise RuntimeError("DibrStep mirror out of date")
+    for name in ("dibr_backproject_compact", "dibr_backproject_compact_backward"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrBackproject), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
     lib.dibr_nnd_workspace_bytes.argtypes = [ctypes.POINTER(DibrNnd), ctypes.POINTER(ctypes.c_size_t)]
     lib.dibr_nnd_workspace_bytes.restype = ctypes.c_int
     for name in ("dibr_nnd_forward", "dibr_nnd_backward"):

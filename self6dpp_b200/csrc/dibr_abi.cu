@@ -325,6 +325,35 @@ int dibr_nnd_backward(const DibrNnd* p, void* stream) {
     return cuda_fail("dibr_nnd_backward", dibr::launch_nnd_backward(n, (cudaStream_t)stream));
 }
 
+static int bp_params(const DibrBackproject* p, dibr::BackprojectParams& q, bool backward) {
+    if (!p) return fail("null DibrBackproject");
+    if (p->batch < 0 || p->height <= 0 || p->width <= 0) return fail("backproject: bad sizes");
+    if (p->num_K != 1 && p->num_K != p->batch) return fail("backproject: num_K must be 1 or batch");
+    if (!p->K || !p->slot) return fail("backproject: K / slot required");
+    if (!backward && (!p->depth || !p->points || !p->count || !p->chunk_count)) return fail("backproject: depth, points, count, chunk_count required");
+    if (backward && (!p->grad_points || !p->grad_depth)) return fail("backproject backward: grad_points / grad_depth required");
+    if ((long long)p->batch * p->height * p->width >= (1ll << 31)) return fail("backproject: too many pixels");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    q.batch = p->batch; q.height = p->height; q.width = p->width; q.num_K = p->num_K;
+    q.depth = p->depth; q.K = p->K; q.points = p->points; q.count = p->count; q.slot = p->slot; q.chunk_count = p->chunk_count;
+    q.grad_points = p->grad_points; q.grad_depth = p->grad_depth;
+    return 0;
+}
+
+int dibr_backproject_compact(const DibrBackproject* p, void* stream) {
+    dibr::BackprojectParams q;
+    if (int e = bp_params(p, q, false)) return e;
+    g_launches += 2;
+    return cuda_fail("dibr_backproject_compact", dibr::launch_backproject(q, (cudaStream_t)stream));
+}
+
+int dibr_backproject_compact_backward(const DibrBackproject* p, void* stream) {
+    dibr::BackprojectParams q;
+    if (int e = bp_params(p, q, true)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_backproject_compact_backward", dibr::launch_backproject_backward(q, (cudaStream_t)stream));
+}
+
 // gather [n,9] + [n,3] into [n,12] so ONE D2H copy returns the pose gradients
 __global__ void pack_pose_grad_kernel(const float* __restrict__ gR, const float* __restrict__ gt, float* __restrict__ out, int n)
 {

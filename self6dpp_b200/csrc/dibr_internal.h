@@ -172,6 +172,20 @@ struct NndParams {
     float* gradxyz2;
 };
 
+// depth map -> compacted cloud (dibr_backproject.cu)
+struct BackprojectParams {
+    int batch, height, width, num_K;
+    const float* depth;        // [batch, H, W]
+    const float* K;            // [num_K, 9], num_K = 1 or batch
+    float* points;             // [batch, H*W, 3] rows [0, count[b]) valid, row-major pixel order
+    int* count;                // [batch]
+    int* slot;                 // [batch, H*W] pixel -> row, -1 where depth <= 0
+    int* chunk_count;          // [batch, ceil(H*W / 1024)] scratch
+    const float* grad_points;  // backward
+    float* grad_depth;
+};
+int launch_backproject(const BackprojectParams& P, cudaStream_t stream);
+int launch_backproject_backward(const BackprojectParams& P, cudaStream_t stream);
 int launch_nnd_forward(const NndParams& P, cudaStream_t stream);
 size_t nnd_grid_workspace_bytes(int batch, int stride1, int stride2);
 int launch_nnd_forward_grid(const NndParams& P, void* workspace, cudaStream_t stream);

@@ -115,8 +115,10 @@ __global__ void __launch_bounds__(NND_THREADS) nnd_backward_kernel(NndParams P, 
             for (int k = 0; k < nt; k++) {
                 if (tidx[k] == j) {
                     const float4 t = tpt[k];
-                    const float g = t.w * 2.0f;
-                    gx -= g * (t.x - ax); gy -= g * (t.y - ay); gz -= g * (t.z - az);
+                    const float g = t.w * 2.0f;          // explicit roundings: dibr_nnd_grid.cu must reproduce this sum
+                    gx = __fsub_rn(gx, __fmul_rn(g, __fsub_rn(t.x, ax)));
+                    gy = __fsub_rn(gy, __fmul_rn(g, __fsub_rn(t.y, ay)));
+                    gz = __fsub_rn(gz, __fmul_rn(g, __fsub_rn(t.z, az)));
                 }
             }
         }

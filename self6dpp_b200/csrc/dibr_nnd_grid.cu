@@ -142,27 +142,35 @@ __global__ void __launch_bounds__(NND_T) nnd_bin_kernel(NndParams P, const unsig
     out[pos] = make_float4(x, y, z, __int_as_float(k));
 }
 
-// ---- exclusive scan in place, one CTA of 1024 threads per row; coalesced chunks of 1024 with the next chunk's load in
-//      flight.  `box` != NULL: row = (dir, sample) of the cell counters, length = the cells the sample's grid really has.
-__global__ void __launch_bounds__(1024) nnd_scan_kernel(int* base, size_t row_stride, int fixed_len, NndParams P, const unsigned int* box)
+// ---- exclusive scan in place, one CTA of 1024 threads per row, 4096 elements per round with the next round's loads in
+//      flight.  mode 0: row = (dir, sample) of the cell counters, length = the cells the sample's grid really has;
+//      mode 1 / 2: inverse-index counters of cloud 1 / cloud 2, length = the cloud's point count.
+__global__ void __launch_bounds__(1024) nnd_scan_kernel(int* base, size_t row_stride, int mode, NndParams P, const unsigned int* box)
 {
     __shared__ int wsum[32];
     __shared__ int carry;
     int* a = base + (size_t)blockIdx.x * row_stride;
-    int len = fixed_len;
-    if (box) {
+    int len;
+    if (mode == 0) {
         const int dir = blockIdx.x / P.batch, b = blockIdx.x - dir * P.batch;
         const int n = cloud_of(P, dir == 0 ? 1 : 0, b).n;
         if (n == 0) return;
         const Grid g = grid_of(box + (size_t)blockIdx.x * 8, n);
         len = g.d[0] * g.d[1] * g.d[2];
+    } else {
+        len = cloud_of(P, mode - 1, blockIdx.x).n;
+        if (len == 0) return;
     }
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) carry = 0;
-    int v = (t < len) ? a[t] : 0;
-    for (int c0 = 0; c0 < len; c0 += 1024) {
-        const int vn = (c0 + 1024 + t < len) ? a[c0 + 1024 + t] : 0;          // prefetch
-        int incl = v;
+    int v[4], vn[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (4 * t + k < len) ? a[4 * t + k] : 0;
+    for (int c0 = 0; c0 < len; c0 += 4096) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) vn[k] = (c0 + 4096 + 4 * t + k < len) ? a[c0 + 4096 + 4 * t + k] : 0;      // prefetch
+        const int mine = v[0] + v[1] + v[2] + v[3];
+        int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
         if (lane == 31) wsum[warp] = incl;
@@ -170,11 +178,13 @@ __global__ void __launch_bounds__(1024) nnd_scan_kernel(int* base, size_t row_st
         int wb = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < 32; w++) { const int u = wsum[w]; if (w < warp) wb += u; tot += u; }
-        const int run = carry;
-        if (c0 + t < len) a[c0 + t] = run + wb + incl - v;
+        int run = carry + wb + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { if (c0 + 4 * t + k < len) a[c0 + 4 * t + k] = run; run += v[k]; }
         __syncthreads();
-        if (t == 0) carry = run + tot;
-        v = vn;
+        if (t == 0) carry += tot;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = vn[k];
     }
 }
 
@@ -343,28 +353,33 @@ __global__ void __launch_bounds__(NND_T) nnd_backward_inv_kernel(NndParams P, co
 {
     const int dir = blockIdx.z, b = blockIdx.y;
     const int sA = dir == 0 ? P.stride1 : P.stride2, sB = dir == 0 ? P.stride2 : P.stride1;
+    if ((int)(blockIdx.x * NND_T) >= sA) return;
     const int j = blockIdx.x * NND_T + threadIdx.x;
-    if (j >= sA) return;
+    const int lane = threadIdx.x & 31;
     const CloudView A = cloud_of(P, dir, b), Bc = cloud_of(P, dir == 0 ? 1 : 0, b);
-    float* out = (dir == 0 ? P.gradxyz1 : P.gradxyz2) + ((size_t)sA * b + j) * 3;
-    if (j >= A.n) { out[0] = 0.f; out[1] = 0.f; out[2] = 0.f; return; }              // padded rows get zeros
+    const bool row = j < sA, live = j < A.n;
     const float* gA = (dir == 0 ? P.graddist1 : P.graddist2) + (size_t)sA * b;
     const float* gB = (dir == 0 ? P.graddist2 : P.graddist1) + (size_t)sB * b;
     const int* idxA = (dir == 0 ? P.idx1 : P.idx2) + (size_t)sA * b;
-    const float ax = A.xyz[(size_t)j * 3], ay = A.xyz[(size_t)j * 3 + 1], az = A.xyz[(size_t)j * 3 + 2];
-    float gx = 0.f, gy = 0.f, gz = 0.f;
-    if (Bc.n > 0) {
+    const int* idxB = (dir == 0 ? P.idx2 : P.idx1) + (size_t)sB * b;
+    float ax = 0.f, ay = 0.f, az = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+    bool crowd = false;                    // a target that attracts many queries: left to the warp (below)
+    auto pull = [&](int k) {
+        // explicit roundings (no contraction): the same sum must come out of the per-thread, the warp and the exhaustive path
+        const float gk = gB[k] * 2.0f;
+        gx = __fsub_rn(gx, __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3], ax)));
+        gy = __fsub_rn(gy, __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3 + 1], ay)));
+        gz = __fsub_rn(gz, __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3 + 2], az)));
+    };
+    if (live && Bc.n > 0) {
+        ax = A.xyz[(size_t)j * 3]; ay = A.xyz[(size_t)j * 3 + 1]; az = A.xyz[(size_t)j * 3 + 2];
         const int j2 = idxA[j];
         const float g = gA[j] * 2.0f;
         gx = g * (ax - Bc.xyz[(size_t)j2 * 3]); gy = g * (ay - Bc.xyz[(size_t)j2 * 3 + 1]); gz = g * (az - Bc.xyz[(size_t)j2 * 3 + 2]);
         const int* cnt = (dir == 0 ? cnt0 : cnt1) + (size_t)b * (sA + 1);
         const int* list = (dir == 0 ? list0 : list1) + (size_t)b * sB;
         const int s = (j == 0) ? 0 : cnt[j - 1], e = cnt[j];
-        auto pull = [&](int k) {
-            const float gk = gB[k] * 2.0f;
-            gx -= gk * (Bc.xyz[(size_t)k * 3] - ax); gy -= gk * (Bc.xyz[(size_t)k * 3 + 1] - ay); gz -= gk * (Bc.xyz[(size_t)k * 3 + 2] - az);
-        };
-        if (e - s <= 48) {
+        if (e - s <= 8) {
             // ascending k, whatever order the cursor produced: repeatedly take the smallest k above the last one taken
             int last = -1;
             for (int t = s; t < e; t++) {
@@ -374,12 +389,45 @@ __global__ void __launch_bounds__(NND_T) nnd_backward_inv_kernel(NndParams P, co
                 pull(kmin);
             }
         } else {
-            // a point that attracts a crowd: the linear scan of the other cloud's index array is cheaper than sorting
-            const int* idxB = (dir == 0 ? P.idx2 : P.idx1) + (size_t)sB * b;
-            for (int k = 0; k < Bc.n; k++) if (idxB[k] == j) pull(k);
+            crowd = true;
         }
     }
-    out[0] = gx; out[1] = gy; out[2] = gz;
+    // crowds: the warp walks the other cloud's index array 32 entries at a time for one such target at a time; the matches
+    // of a round are handed over in lane order, so the sum still runs in ascending k like the exhaustive gather
+    __syncwarp();
+    unsigned todo = __ballot_sync(0xffffffffu, crowd);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int jt = __shfl_sync(0xffffffffu, j, src);
+        const float tx = __shfl_sync(0xffffffffu, ax, src), ty = __shfl_sync(0xffffffffu, ay, src), tz = __shfl_sync(0xffffffffu, az, src);
+        float sx = __shfl_sync(0xffffffffu, gx, src), sy = __shfl_sync(0xffffffffu, gy, src), sz = __shfl_sync(0xffffffffu, gz, src);
+        for (int k0 = 0; k0 < Bc.n; k0 += 32) {
+            const int k = k0 + lane;
+            const bool hit = (k < Bc.n) && (idxB[k] == jt);
+            unsigned hits = __ballot_sync(0xffffffffu, hit);
+            if (hits == 0u) continue;
+            float cx = 0.f, cy = 0.f, cz = 0.f;
+            if (hit) {
+                const float gk = gB[k] * 2.0f;
+                cx = __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3], tx));
+                cy = __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3 + 1], ty));
+                cz = __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3 + 2], tz));
+            }
+            while (hits) {
+                const int l = __ffs(hits) - 1;
+                hits &= hits - 1;
+                sx = __fsub_rn(sx, __shfl_sync(0xffffffffu, cx, l));
+                sy = __fsub_rn(sy, __shfl_sync(0xffffffffu, cy, l));
+                sz = __fsub_rn(sz, __shfl_sync(0xffffffffu, cz, l));
+            }
+        }
+        if (lane == src) { gx = sx; gy = sy; gz = sz; }
+    }
+    if (row) {
+        float* out = (dir == 0 ? P.gradxyz1 : P.gradxyz2) + ((size_t)sA * b + j) * 3;
+        out[0] = live ? gx : 0.f; out[1] = live ? gy : 0.f; out[2] = live ? gz : 0.f;           // padded rows get zeros
+    }
 }
 
 int launch_nnd_backward_grid(const NndParams& P, void* workspace, cudaStream_t stream)
@@ -392,8 +440,8 @@ int launch_nnd_backward_grid(const NndParams& P, void* workspace, cudaStream_t s
     const dim3 gpts((smax + NND_T - 1) / NND_T, P.batch, 2);
     nnd_inverse_kernel<0><<<gpts, NND_T, 0, stream>>>(P, w.inv_cnt[0], w.inv_cnt[1], w.inv_list[0], w.inv_list[1]);
     // dir 0 counters: [batch][stride1 + 1];  dir 1 counters: [batch][stride2 + 1]
-    if (P.stride1 > 0) nnd_scan_kernel<<<P.batch, 1024, 0, stream>>>(w.inv_cnt[0], (size_t)P.stride1 + 1, P.stride1, P, nullptr);
-    if (P.stride2 > 0) nnd_scan_kernel<<<P.batch, 1024, 0, stream>>>(w.inv_cnt[1], (size_t)P.stride2 + 1, P.stride2, P, nullptr);
+    if (P.stride1 > 0) nnd_scan_kernel<<<P.batch, 1024, 0, stream>>>(w.inv_cnt[0], (size_t)P.stride1 + 1, 1, P, nullptr);
+    if (P.stride2 > 0) nnd_scan_kernel<<<P.batch, 1024, 0, stream>>>(w.inv_cnt[1], (size_t)P.stride2 + 1, 2, P, nullptr);
     nnd_inverse_kernel<1><<<gpts, NND_T, 0, stream>>>(P, w.inv_cnt[0], w.inv_cnt[1], w.inv_list[0], w.inv_list[1]);
     nnd_backward_inv_kernel<<<gpts, NND_T, 0, stream>>>(P, w.inv_cnt[0], w.inv_cnt[1], w.inv_list[0], w.inv_list[1]);
     return (int)cudaGetLastError();

@@ -143,6 +143,50 @@ def compact_valid_points(cloud_bxhxwx3):
     return out[:, :H * W].contiguous(), count
 
 
+class BackprojectCompact(Function):
+    """depth [B,H,W], K [3,3] or [B,3,3] -> (points [B, H*W, 3], count [B] int32): ``backproject_th`` followed by the
+    reference's per-sample ``pc[pc[:, :, 2] > 0]`` (depth_bp_chamfer_loss.py:27-36) for the whole batch in two launches
+    (``dibr_backproject_compact``); the backward is one launch.  Same fp32 expressions as the torch version."""
+
+    @staticmethod
+    def forward(ctx, depth, K):
+        _require_cuda_f32("depth", depth)
+        B, H, W = depth.shape
+        device = depth.device
+        d = depth.detach().contiguous()
+        Kc = K.detach().to(device=device, dtype=torch.float32).reshape(-1, 3, 3).contiguous()
+        points = torch.zeros(B, H * W, 3, dtype=torch.float32, device=device)       # rows beyond count stay zero
+        count = torch.empty(B, dtype=torch.int32, device=device)
+        slot = torch.empty(B, H * W, dtype=torch.int32, device=device)
+        chunks = torch.empty(B, (H * W + 1023) // 1024, dtype=torch.int32, device=device)
+        p = _lib.DibrBackproject()
+        p.batch, p.height, p.width, p.num_K = B, H, W, int(Kc.shape[0])
+        p.depth, p.K, p.points = _lib.ptr(d), _lib.ptr(Kc), _lib.ptr(points)
+        p.count, p.slot, p.chunk_count = _lib.ptr(count), _lib.ptr(slot), _lib.ptr(chunks)
+        _launch("dibr_backproject_compact", p, device)
+        ctx.save_for_backward(slot, Kc)
+        ctx.dims = (B, H, W)
+        ctx.mark_non_differentiable(count)
+        return points, count
+
+    @staticmethod
+    def backward(ctx, grad_points, _gc):
+        slot, Kc = ctx.saved_tensors
+        B, H, W = ctx.dims
+        gp = grad_points.contiguous()
+        gd = torch.empty(B, H, W, dtype=torch.float32, device=gp.device)
+        p = _lib.DibrBackproject()
+        p.batch, p.height, p.width, p.num_K = B, H, W, int(Kc.shape[0])
+        p.K, p.slot, p.grad_points, p.grad_depth = _lib.ptr(Kc), _lib.ptr(slot), _lib.ptr(gp), _lib.ptr(gd)
+        _launch("dibr_backproject_compact_backward", p, gp.device)
+        return gd, None
+
+
+def backproject_compact(depth, K):
+    """-> (points [B, H*W, 3], count [B]) of the pixels with depth > 0, row-major order"""
+    return BackprojectCompact.apply(depth, K)
+
+
 def depth_bp_chamfer_loss(ren_depths, real_depths, Ks, distance_threshold=0.05, center_lw=0):
     """
     Args (core/self6dpp/losses/depth_bp_chamfer_loss.py:12-19):
@@ -150,8 +194,9 @@ def depth_bp_chamfer_loss(ren_depths, real_depths, Ks, distance_threshold=0.05, 
     Returns (loss / max(num_valid,1), loss_center / max(num_valid,1)) like the reference, for the whole batch at once.
     """
     B, H, W = ren_depths.shape
-    real_pts, real_cnt = compact_valid_points(backproject_th(real_depths, Ks))
-    rend_pts, rend_cnt = compact_valid_points(backproject_th(ren_depths, Ks))
+    Kt = torch.as_tensor(Ks)
+    real_pts, real_cnt = backproject_compact(real_depths, Kt)
+    rend_pts, rend_cnt = backproject_compact(ren_depths, Kt)
     dist1, dist2, _, _ = nnd_padded(real_pts, real_cnt, rend_pts, rend_cnt)
     ar = torch.arange(H * W, device=ren_depths.device).view(1, -1)
     v1, v2 = ar < real_cnt.view(-1, 1), ar < rend_cnt.view(-1, 1)

@@ -142,3 +142,25 @@ def test_grid_search_is_bit_identical_to_the_exhaustive_search(case):
     a, e = _both(x1.to(DEV), c1.to(DEV), x2.to(DEV), c2.to(DEV), g1, g2)
     for k, name in enumerate(("dist1", "dist2", "idx1", "idx2", "grad1", "grad2")):
         assert torch.equal(a[k], e[k]), f"{case}: {name} differs at {int((a[k] != e[k]).sum())} entries"
+
+
+def test_backproject_compact_equals_the_torch_expressions():
+    """dibr_backproject_compact vs backproject_th + compact_valid_points (the restated reference expressions):
+    points and counts bit-exact, d loss / d depth to 1e-6"""
+    from self6dpp_b200.nndistance import backproject_compact, backproject_th, compact_valid_points
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 3, 37, 53                                  # not a multiple of the 1024-pixel chunk
+    depth = (torch.rand(B, H, W, generator=g) + 0.5) * (torch.rand(B, H, W, generator=g) > 0.4)
+    depth[1] = 0                                          # an empty map
+    K = torch.tensor([[[60.0, 0, 25.5], [0, 62.0, 18.0], [0, 0, 1]]]).repeat(B, 1, 1)
+    K[2, 0, 2] += 3.0
+    for Kin in (K, K[0]):
+        d1 = depth.to(DEV).requires_grad_(True)
+        d2 = depth.to(DEV).requires_grad_(True)
+        p1, c1 = backproject_compact(d1, Kin.to(DEV))
+        p2, c2 = compact_valid_points(backproject_th(d2, Kin.to(DEV)))
+        assert torch.equal(c1, c2) and torch.equal(p1, p2)
+        w = torch.randn(p1.shape, generator=g).to(DEV)
+        (p1 * w).sum().backward()
+        (p2 * w).sum().backward()
+        assert float((d1.grad - d2.grad).abs().max()) <= 1e-6 * float(d2.grad.abs().max())
