@@ -250,6 +250,23 @@ typedef struct DibrBackproject {
 int dibr_backproject_compact(const DibrBackproject *p, void *stream);
 int dibr_backproject_compact_backward(const DibrBackproject *p, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Re-weighted BCE on probabilities: weighted_ex_loss_probs (core/self6dpp/losses/mask_losses.py:63-108), the loss the
+ * rendered soft mask feeds (self_engine_utils.py:541-545).  scratch: dibr_mask_loss_scratch_floats(n) floats followed by
+ * one uint32 that must be ZERO before the first call (the kernel re-arms it).  out[0] = loss, out[1] = |target > 0|,
+ * out[2] = |target == 0|; the backward reads out[1..2] and grad_out[0] (d L / d loss) and writes d L / d probs. */
+typedef struct DibrMaskLoss {
+    int64_t n;                               /* elements of probs / target / weight */
+    const float *probs, *target, *weight;    /* weight may be NULL */
+    float *scratch;                          /* see above */
+    float *out;                              /* [3] */
+    const float *grad_out;                   /* backward in:  [1] */
+    float *grad_probs;                       /* backward out: [n] */
+} DibrMaskLoss;
+int dibr_mask_loss_scratch_floats(int64_t n);
+int dibr_mask_loss_forward(const DibrMaskLoss *p, void *stream);
+int dibr_mask_loss_backward(const DibrMaskLoss *p, void *stream);
+
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);
 

@@ -80,10 +80,20 @@ class DibrBackproject(ctypes.Structure):
     ]
 
 
+class DibrMaskLoss(ctypes.Structure):
+    """Mirror of ``struct DibrMaskLoss`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("n", ctypes.c_int64), ("probs", _c_f32p), ("target", _c_f32p), ("weight", _c_f32p),
+        ("scratch", _c_f32p), ("out", _c_f32p), ("grad_out", _c_f32p), ("grad_probs", _c_f32p),
+    ]
+
+
 EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_device_count", "dibr_workspace_bytes",
            "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
            "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_backproject_compact",
-           "dibr_backproject_compact_backward", "dibr_launch_count"]
+           "dibr_backproject_compact_backward", "dibr_mask_loss_scratch_floats", "dibr_mask_loss_forward",
+           "dibr_mask_loss_backward", "dibr_launch_count"]
 
 _lib = None
 
@@ -127,6 +137,12 @@ def load():
     for name in ("dibr_backproject_compact", "dibr_backproject_compact_backward"):
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrBackproject), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    lib.dibr_mask_loss_scratch_floats.argtypes = [ctypes.c_int64]
+    lib.dibr_mask_loss_scratch_floats.restype = ctypes.c_int
+    for name in ("dibr_mask_loss_forward", "dibr_mask_loss_backward"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrMaskLoss), ctypes.c_void_p]
         fn.restype = ctypes.c_int
     lib.dibr_nnd_workspace_bytes.argtypes = [ctypes.POINTER(DibrNnd), ctypes.POINTER(ctypes.c_size_t)]
     lib.dibr_nnd_workspace_bytes.restype = ctypes.c_int

@@ -354,6 +354,33 @@ int dibr_backproject_compact_backward(const DibrBackproject* p, void* stream) {
     return cuda_fail("dibr_backproject_compact_backward", dibr::launch_backproject_backward(q, (cudaStream_t)stream));
 }
 
+int dibr_mask_loss_scratch_floats(int64_t n) { return dibr::mask_loss_partial_floats(n) + 1; }
+
+static int ml_params(const DibrMaskLoss* p, dibr::MaskLossParams& q, bool backward) {
+    if (!p) return fail("null DibrMaskLoss");
+    if (p->n < 0) return fail("mask_loss: negative size");
+    if (!p->probs || !p->target || !p->out) return fail("mask_loss: probs / target / out required");
+    if (!backward && !p->scratch) return fail("mask_loss: scratch required");
+    if (backward && (!p->grad_out || !p->grad_probs)) return fail("mask_loss backward: grad_out / grad_probs required");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    q.n = p->n; q.probs = p->probs; q.target = p->target; q.weight = p->weight;
+    q.partial = p->scratch; q.ticket = p->scratch ? (unsigned int*)(p->scratch + dibr::mask_loss_partial_floats(p->n)) : nullptr;
+    q.out = p->out; q.grad_out = p->grad_out; q.grad_probs = p->grad_probs;
+    return 0;
+}
+int dibr_mask_loss_forward(const DibrMaskLoss* p, void* stream) {
+    dibr::MaskLossParams q;
+    if (int e = ml_params(p, q, false)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_mask_loss_forward", dibr::launch_mask_loss_forward(q, (cudaStream_t)stream));
+}
+int dibr_mask_loss_backward(const DibrMaskLoss* p, void* stream) {
+    dibr::MaskLossParams q;
+    if (int e = ml_params(p, q, true)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_mask_loss_backward", dibr::launch_mask_loss_backward(q, (cudaStream_t)stream));
+}
+
 // gather [n,9] + [n,3] into [n,12] so ONE D2H copy returns the pose gradients
 __global__ void pack_pose_grad_kernel(const float* __restrict__ gR, const float* __restrict__ gt, float* __restrict__ out, int n)
 {

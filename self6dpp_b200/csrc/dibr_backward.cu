@@ -148,12 +148,20 @@ __device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
 // The warp walks the pixel centres of the expanded bbox 32 at a time, keeps (ballot compaction, ascending pixel
 // order) the uncovered pixels that counted this face, and evaluates them 32 at a time with every lane busy.
 constexpr int SOFT_Q = 64;
+#ifndef DIBR_SOFT_LANES
+#define DIBR_SOFT_LANES 16
+#endif
+constexpr int SOFT_LANES = DIBR_SOFT_LANES;          // lanes per face: a face has ~12 contributing pixels out of ~80 scanned,
+constexpr int SOFT_GROUPS = 256 / SOFT_LANES;        // so a full warp per face leaves most lanes idle in the evaluation
+static_assert(SOFT_LANES == 8 || SOFT_LANES == 16 || SOFT_LANES == 32, "a sub-warp group");
 __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, int (*queue)[SOFT_Q])
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wi = bid * 8 + warp;
-    if (wi >= P.list_counts[1]) return;                      // warp-uniform
-    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x;
+    const int grp = tid / SOFT_LANES, lane = tid % SOFT_LANES;          // lane = position inside the group
+    const int shift = ((tid & 31) / SOFT_LANES) * SOFT_LANES;           // first lane of the group inside its warp
+    const unsigned full = (SOFT_LANES == 32) ? 0xffffffffu : (((1u << SOFT_LANES) - 1u) << shift);      // the group's lanes
+    const int wi = bid * SOFT_GROUPS + grp;
+    if (wi >= P.list_counts[1]) return;                      // group-uniform
     const int W = P.width, H = P.height;
     const int g = P.soft_list[wi];
     const FaceRec rec = P.recs[g];
@@ -174,7 +182,7 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
     const float sentinel = 4.0f * mult * mult;
     const float px[3] = {rec.ax, rec.bx, rec.cx}, py[3] = {rec.ay, rec.by, rec.cy};
     float gp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int* q = queue[warp];
+    int* q = queue[grp];
     int qn = 0;
 
     const unsigned nc_magic = (unsigned)((0x100000000ull + (unsigned)nc - 1ull) / (unsigned)nc);   // ceil(2^32 / nc)
@@ -217,7 +225,7 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
         }
     };
 
-    for (int base = 0; base < npx; base += 32) {
+    for (int base = 0; base < npx; base += SOFT_LANES) {
         const int i = base + lane;
         bool take = false;
         if (i < npx) {
@@ -225,31 +233,31 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
             const int v = idx[(size_t)(r0 + rr) * W + c0 + (i - rr * nc)];
             take = !(v > 0 || (v < 0 && f + 1 > -v));        // uncovered and this face is within the first K
         }
-        const unsigned bal = __ballot_sync(full, take);
+        const unsigned bal = __ballot_sync(full, take) >> shift;
         if (take) q[qn + __popc(bal & ((1u << lane) - 1u))] = i;
         qn += __popc(bal);
-        __syncwarp();
-        if (qn >= 32) {
+        __syncwarp(full);
+        if (qn >= SOFT_LANES) {
             evaluate(q[lane]);
-            __syncwarp();
-            const int rest = qn - 32;
-            const int moved = (lane < rest) ? q[32 + lane] : 0;
-            __syncwarp();
+            __syncwarp(full);
+            const int rest = qn - SOFT_LANES;
+            const int moved = (lane < rest) ? q[SOFT_LANES + lane] : 0;
+            __syncwarp(full);
             if (lane < rest) q[lane] = moved;
             qn = rest;
-            __syncwarp();
+            __syncwarp(full);
         }
     }
     if (lane < qn) evaluate(q[lane]);
-    // fixed-tree warp reduction, then add to what the colour kernel wrote (stream order makes this race-free)
+    // fixed-tree reduction over the group, then add to the face's six slots
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         float v = gp[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+        for (int o = SOFT_LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
         gp[i] = v;
     }
-    {   // every lane holds the totals: lanes 0..5 deliver one each
+    {   // every lane of the group holds the totals: lanes 0..5 deliver one each
         float v = gp[0];
 #pragma unroll
         for (int i = 1; i < 6; i++) v = (lane == i) ? gp[i] : v;
@@ -259,7 +267,7 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
 
 // One persistent launch for both parts.  The list lengths live on the device, so a grid sized for the worst case would
 // be mostly CTAs that find nothing to do; instead a fixed grid strides over the work items that exist: first the
-// colour items (32 faces each), then the soft items (8 faces each) -- both kinds share the SMs as the first run out.
+// colour items (32 faces each), then the soft items (256 / SOFT_LANES faces each) -- both kinds share the SMs as the first run out.
 #ifndef DIBR_BWD_MIN_CTAS
 #define DIBR_BWD_MIN_CTAS 4        // 64 registers: measured faster than 80 registers at 3 CTAs per SM
 #endif
@@ -269,9 +277,9 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
 template <int DMAX>
 __global__ void __launch_bounds__(256, (DMAX <= 8) ? DIBR_BWD_MIN_CTAS : 2) backward_faces_kernel(const __grid_constant__ BwdParams P, int do_color, int do_soft)
 {
-    __shared__ int queue[8][SOFT_Q];
+    __shared__ int queue[SOFT_GROUPS][SOFT_Q];
     const int cbn = do_color ? (P.list_counts[0] + (256 / GRP) - 1) / (256 / GRP) : 0;
-    const int sbn = do_soft ? (P.list_counts[1] + 7) / 8 : 0;
+    const int sbn = do_soft ? (P.list_counts[1] + SOFT_GROUPS - 1) / SOFT_GROUPS : 0;
     for (int it = blockIdx.x; it < cbn + sbn; it += gridDim.x) {
         __syncwarp();                        // lanes leave the bodies at different points
         if (it < cbn) backward_color_body<DMAX>(P, it);
@@ -287,9 +295,15 @@ int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(P.grad_face_attr, 0, sizeof(float) * 3 * (size_t)P.num_attr * (size_t)P.total_faces, stream);
     if (e != cudaSuccess) return (int)e;
-    const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
+    int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
+#ifdef DIBR_X_NO_SOFTBWD
+    do_soft = 0;
+#endif
+#ifdef DIBR_X_NO_COLORBWD
+    do_color = 0;
+#endif
     if (!do_color && !do_soft) return 0;
-    const int worst = (do_color ? (P.total_faces + (256 / GRP) - 1) / (256 / GRP) : 0) + (do_soft ? (P.total_faces + 7) / 8 : 0);
+    const int worst = (do_color ? (P.total_faces + (256 / GRP) - 1) / (256 / GRP) : 0) + (do_soft ? (P.total_faces + SOFT_GROUPS - 1) / SOFT_GROUPS : 0);
     const int grid = min(worst, DIBR_BWD_GRID);
     if (P.num_attr <= 4) backward_faces_kernel<4><<<grid, 256, 0, stream>>>(P, do_color, do_soft);
     else if (P.num_attr <= 8) backward_faces_kernel<8><<<grid, 256, 0, stream>>>(P, do_color, do_soft);

@@ -172,6 +172,21 @@ struct NndParams {
     float* gradxyz2;
 };
 
+// re-weighted BCE on probabilities (dibr_maskloss.cu)
+struct MaskLossParams {
+    long long n;
+    const float* probs;
+    const float* target;
+    const float* weight;       // or null
+    float* partial;            // [4 * CTAs] scratch
+    unsigned int* ticket;      // [1], zero between calls
+    float* out;                // [3]: loss, |pos|, |neg|
+    const float* grad_out;     // backward: [1]
+    float* grad_probs;         // backward: [n]
+};
+int mask_loss_partial_floats(long long n);
+int launch_mask_loss_forward(const MaskLossParams& P, cudaStream_t stream);
+int launch_mask_loss_backward(const MaskLossParams& P, cudaStream_t stream);
 // depth map -> compacted cloud (dibr_backproject.cu)
 struct BackprojectParams {
     int batch, height, width, num_K;

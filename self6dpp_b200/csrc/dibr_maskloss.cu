@@ -1,0 +1,101 @@
+// Re-weighted BCE on probabilities -- the consumer of the rendered soft mask on Self6D++'s mask-loss path
+// (core/self6dpp/losses/mask_losses.py:63-108 weighted_ex_loss_probs, called on ren_prob at
+// core/self6dpp/engine/self_engine_utils.py:541-545):
+//     pos = target > 0, neg = target == 0, p = clamp(probs, 1e-7, 1 - 1e-7)
+//     loss = sum_pos(-target log p * w) / |pos|  +  sum_neg(-log(1 - p) * w) / |neg|      (a term with an empty set is dropped)
+// The reference builds four boolean-indexed temporaries and syncs with the host four times (two `.any()`, two `if num >
+// 0`).  Here: one pass that produces the two sums and the two counts (per-thread strided accumulation, fixed shuffle /
+// shared-memory trees, per-CTA partials added in CTA order by the CTA that finishes last -- bit-reproducible), and one
+// elementwise pass for d loss / d probs.  No host sync.
+#include "dibr_internal.h"
+
+namespace dibr {
+
+constexpr int ML_T = 256;
+
+__device__ __forceinline__ float clamp_prob(float p) { return fminf(fmaxf(p, 1e-7f), 1.0f - 1e-7f); }
+
+__global__ void __launch_bounds__(ML_T) mask_loss_forward_kernel(MaskLossParams P)
+{
+    __shared__ float red[ML_T / 32][4];
+    __shared__ int last;
+    float s_pos = 0.f, s_neg = 0.f, n_pos = 0.f, n_neg = 0.f;
+    for (long long i = (long long)blockIdx.x * ML_T + threadIdx.x; i < P.n; i += (long long)gridDim.x * ML_T) {
+        const float t = P.target[i];
+        const float w = P.weight ? P.weight[i] : 1.0f;
+        const float p = clamp_prob(P.probs[i]);
+        if (t > 0.0f) { s_pos += -t * logf(p) * w; n_pos += 1.0f; }
+        else if (t == 0.0f) { s_neg += -logf(1.0f - p) * w; n_neg += 1.0f; }
+    }
+    float v[4] = {s_pos, s_neg, n_pos, n_neg};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < ML_T / 32; w++) s += red[w][threadIdx.x];
+        P.partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 4) {
+        float s = 0.f;
+        for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(P.partial + (size_t)b * 4 + threadIdx.x);     // CTA order: fixed
+        red[0][threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float sp = red[0][0], sn = red[0][1], np = red[0][2], nn = red[0][3];
+        float loss = 0.f;
+        if (np > 0.f) loss += 1.0f / np * sp;
+        if (nn > 0.f) loss += 1.0f / nn * sn;
+        P.out[0] = loss; P.out[1] = np; P.out[2] = nn;
+        *P.ticket = 0u;                          // re-armed for the next call
+    }
+}
+
+// d loss / d probs (clamp passes the gradient inside [1e-7, 1 - 1e-7] only)
+__global__ void __launch_bounds__(ML_T) mask_loss_backward_kernel(MaskLossParams P)
+{
+    const float np = P.out[1], nn = P.out[2], go = P.grad_out[0];
+    for (long long i = (long long)blockIdx.x * ML_T + threadIdx.x; i < P.n; i += (long long)gridDim.x * ML_T) {
+        const float t = P.target[i];
+        const float w = P.weight ? P.weight[i] : 1.0f;
+        const float p = P.probs[i];
+        float g = 0.f;
+        if (p >= 1e-7f && p <= 1.0f - 1e-7f) {
+            if (t > 0.0f) g = -t * w / p / np;
+            else if (t == 0.0f) g = w / (1.0f - p) / nn;
+        }
+        P.grad_probs[i] = g * go;
+    }
+}
+
+static inline int ml_grid(long long n) {
+    const long long want = (n + ML_T * 4 - 1) / (ML_T * 4);
+    return (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+}
+int mask_loss_partial_floats(long long n) { return 4 * ml_grid(n); }
+
+int launch_mask_loss_forward(const MaskLossParams& P, cudaStream_t stream)
+{
+    mask_loss_forward_kernel<<<ml_grid(P.n), ML_T, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+int launch_mask_loss_backward(const MaskLossParams& P, cudaStream_t stream)
+{
+    if (P.n <= 0) return 0;
+    mask_loss_backward_kernel<<<ml_grid(P.n), ML_T, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dibr

@@ -137,7 +137,7 @@ def golden_seam(ref, H=48, W=64, seed=5):
     print("ref_seam48x64: covered", int((im[..., 3] > 0.5).sum()))
 
 
-if __name__ == "__main__" and "--nnd" not in sys.argv and "--tex" not in sys.argv:
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--nnd", "--tex", "--maskloss")):
     import warnings
     warnings.filterwarnings("ignore")
     ref = O.import_reference()
@@ -337,3 +337,35 @@ def golden_tex():
 
 if __name__ == "__main__" and "--tex" in sys.argv:
     golden_tex()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# re-weighted BCE on probabilities: the reference's OWN weighted_ex_loss_probs (mask_losses.py:63-108) on CPU
+# ------------------------------------------------------------------------------------------------------------------
+def golden_maskloss():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_mask_losses", "/root/reference/core/self6dpp/losses/mask_losses.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(31)
+    out = {}
+    for tag, shape, with_w in (("a", (3, 1, 40, 56), True), ("b", (2, 1, 33, 47), False), ("c", (1, 1, 8, 8), True)):
+        probs = torch.rand(shape, generator=g)
+        probs.view(-1)[:5] = torch.tensor([0.0, 1.0, 1e-9, 1 - 1e-9, 0.5])          # the clamp's both sides
+        target = (torch.rand(shape, generator=g) > 0.6).float() * (0.5 + 0.5 * torch.rand(shape, generator=g))   # soft positives
+        if tag == "c":
+            target[:] = 0                                                             # no positives: the term is dropped
+        weight = torch.rand(shape, generator=g) + 0.5 if with_w else None
+        probs.requires_grad_(True)
+        loss = mod.weighted_ex_loss_probs(probs, target, weight=weight)
+        (loss * 1.7).backward()
+        out.update({f"{tag}_probs": probs.detach().numpy(), f"{tag}_target": target.numpy(), f"{tag}_loss": loss.detach().numpy(),
+                    f"{tag}_grad": probs.grad.numpy()})
+        if with_w:
+            out[f"{tag}_weight"] = weight.numpy()
+        print("maskloss", tag, float(loss))
+    np.savez_compressed(os.path.join(OUT, "ref_maskloss.npz"), **out)
+
+
+if __name__ == "__main__" and "--maskloss" in sys.argv:
+    golden_maskloss()

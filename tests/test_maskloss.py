@@ -1,0 +1,62 @@
+"""Re-weighted BCE on probabilities (self6dpp_b200.losses.weighted_ex_loss_probs) against golden vectors produced by the
+reference's own function (tests/golden/make_golden.py --maskloss)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_maskloss.npz")
+
+
+def test_oracle_restatement_matches_reference_golden():
+    from oracle import maskloss_oracle as M
+    d = np.load(GOLD)
+    for tag in "abc":
+        w = d[f"{tag}_weight"] if f"{tag}_weight" in d else None
+        loss, grad = M.weighted_ex_loss_probs(d[f"{tag}_probs"], d[f"{tag}_target"], w)
+        assert abs(loss - float(d[f"{tag}_loss"])) <= 1e-5 * abs(float(d[f"{tag}_loss"]))
+        ref = d[f"{tag}_grad"] / 1.7
+        assert np.abs(grad - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_golden_and_is_reproducible():
+    from self6dpp_b200.losses import weighted_ex_loss_probs
+    dev = "cuda:0"
+    d = np.load(GOLD)
+    for tag in "abc":
+        w = torch.tensor(d[f"{tag}_weight"], device=dev) if f"{tag}_weight" in d else None
+        outs = []
+        for _ in range(2):
+            p = torch.tensor(d[f"{tag}_probs"], device=dev, requires_grad=True)
+            loss = weighted_ex_loss_probs(p, torch.tensor(d[f"{tag}_target"], device=dev), weight=w)
+            (loss * 1.7).backward()
+            outs.append((loss.detach().clone(), p.grad.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])      # bit-reproducible
+        assert abs(float(outs[0][0]) - float(d[f"{tag}_loss"])) <= 1e-5 * abs(float(d[f"{tag}_loss"]))   # tolerance: 1e-5 relative
+        ref = d[f"{tag}_grad"]
+        assert np.abs(outs[0][1].cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_gpu_large_input_against_oracle():
+    """cfg2-sized soft mask (32 x 256 x 256) straight from random data: many CTAs, the last-CTA reduction"""
+    from oracle import maskloss_oracle as M
+    from self6dpp_b200.losses import weighted_ex_loss_probs
+    g = torch.Generator().manual_seed(2)
+    probs = torch.rand(32, 1, 256, 256, generator=g)
+    target = (torch.rand(32, 1, 256, 256, generator=g) > 0.7).float()
+    weight = torch.rand(32, 1, 256, 256, generator=g) + 0.5
+    p = probs.to("cuda:0").requires_grad_(True)
+    loss = weighted_ex_loss_probs(p, target.to("cuda:0"), weight=weight.to("cuda:0"))
+    loss.backward()
+    ref_loss, ref_grad = M.weighted_ex_loss_probs(probs.numpy(), target.numpy(), weight.numpy())
+    assert abs(float(loss) - ref_loss) <= 1e-5 * abs(ref_loss)
+    assert np.abs(p.grad.cpu().numpy() - ref_grad).max() <= 1e-5 * np.abs(ref_grad).max()
+
+
+def test_cpu_tensor_raises():
+    from self6dpp_b200.losses import weighted_ex_loss_probs
+    with pytest.raises(Exception):
+        weighted_ex_loss_probs(torch.rand(2, 1, 4, 4), torch.zeros(2, 1, 4, 4))

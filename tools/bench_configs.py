@@ -80,4 +80,21 @@ def tex():
     ret = tren.render_batch_tex(Rs, ts, cur, Ks=Kt, width=256, height=256, uv_type="vertex", mode=["color"])
     torch.autograd.backward([ret["color"], ret["prob"]], [gtc, gtp])
 ms = timeit(tex, reps=5); out.append({"config": "texture batch (B=32, 256x256, cfg2 meshes, TextureBatch colour+prob fwd+bwd, torch vertex/fragment shaders)", "ms": ms, "samples_per_s": 32e3 / ms})
+# RW-BCE mask loss (loss half): ours vs the reference's expression in torch (boolean indexing, host syncs)
+from self6dpp_b200.losses import weighted_ex_loss_probs
+mp = torch.rand(32, 1, 256, 256, generator=g).to(DEV); mt = (torch.rand(32, 1, 256, 256, generator=g) > 0.7).float().to(DEV)
+mw = (torch.rand(32, 1, 256, 256, generator=g) + 0.5).to(DEV)
+def ours():
+    p = mp.clone().requires_grad_(True); weighted_ex_loss_probs(p, mt, weight=mw).backward()
+def torch_ref():          # mask_losses.py:63-108 restated
+    p = mp.clone().requires_grad_(True)
+    pos, neg = mt > 0, mt == 0
+    q = p.clamp(min=1e-7, max=1 - 1e-7)
+    pl = -mt[pos] * torch.log(q[pos]) * mw[pos]; nl = -(torch.log(1 - q[neg])) * mw[neg]
+    if torch.isnan(pl).any() or torch.isnan(nl).any(): print("nan")
+    loss = 0.0; npos, nneg = pos.sum(), neg.sum()
+    if npos > 0: loss = loss + 1.0 / npos.float() * pl.sum()
+    if nneg > 0: loss = loss + 1.0 / nneg.float() * nl.sum()
+    loss.backward()
+out.append({"config": "RW-BCE mask loss fwd+bwd on [32,1,256,256]", "ms": timeit(ours), "torch_expression_ms": timeit(torch_ref)})
 for o in out: print(json.dumps(o))
