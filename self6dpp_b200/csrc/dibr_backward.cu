@@ -295,13 +295,7 @@ int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(P.grad_face_attr, 0, sizeof(float) * 3 * (size_t)P.num_attr * (size_t)P.total_faces, stream);
     if (e != cudaSuccess) return (int)e;
-    int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
-#ifdef DIBR_X_NO_SOFTBWD
-    do_soft = 0;
-#endif
-#ifdef DIBR_X_NO_COLORBWD
-    do_color = 0;
-#endif
+    const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
     if (!do_color && !do_soft) return 0;
     const int worst = (do_color ? (P.total_faces + (256 / GRP) - 1) / (256 / GRP) : 0) + (do_soft ? (P.total_faces + SOFT_GROUPS - 1) / SOFT_GROUPS : 0);
     const int grid = min(worst, DIBR_BWD_GRID);

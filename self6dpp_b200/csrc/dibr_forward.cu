@@ -70,9 +70,6 @@ struct FwdSmem {
 // to the matching work list of the backward.  Warp-aggregated: one counter atomic per warp, every lane must call.
 __device__ __forceinline__ void mark_faces_warp(const FwdParams& P, bool want, int g, unsigned bit) {
     bool isnew = false;
-#ifdef DIBR_X_NO_MARKS
-    want = false;
-#endif
     if (want && (__ldcg(&P.face_flags[g]) & bit) == 0u) isnew = (atomicOr(&P.face_flags[g], bit) & bit) == 0u;
     const unsigned bal = __ballot_sync(0xffffffffu, isnew);
     if (bal == 0u) return;
@@ -330,9 +327,7 @@ __device__ __noinline__ void fill_untouched_warp(const FwdParams& P, int packed_
     const int tx0 = tx * TILE, ty0 = ty * TILE;
     const int tw = min(TILE, P.width - tx0), th = min(TILE, P.height - ty0);
     const size_t img_pix = (size_t)b * P.height * P.width;
-#ifndef DIBR_X_NO_OUTMIN
     if ((threadIdx.x & 31) == 0 && P.min_group >= 0) atomicMin(P.out_min, f2ord(0.0f));
-#endif
     for (int g = 0; g < P.n_out; g++) fill_tile_warp(P.out[g] + img_pix * P.out_ch[g], P.width, P.out_ch[g], tx0, ty0, tw, th, 0.0f);
     fill_tile_warp(P.improb + img_pix, P.width, 1, tx0, ty0, tw, th, 0.0f);
     fill_tile_warp(reinterpret_cast<float*>(P.imidx + img_pix), P.width, 1, tx0, ty0, tw, th, 0.0f);
@@ -524,9 +519,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         {
             bool isnew = false;
             const int g = f_lo + max(fw, 0);
-#ifndef DIBR_X_NO_MARKS
             if (lead && (fl & 1u) == 0u) isnew = (atomicOr(&P.face_flags[g], 1u) & 1u) == 0u;
-#endif
             const unsigned nb = __ballot_sync(full_mask, isnew);
             if (nb) {
                 const int leader = __ffs(nb) - 1;
@@ -536,18 +529,13 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
                 if (isnew) P.color_list[lb + __popc(nb & ((1u << lane) - 1u))] = g;
             }
         }
-#ifndef DIBR_X_NO_OUTMIN
         if (P.min_group >= 0) {
             const unsigned ov = __reduce_min_sync(full_mask, f2ord(vmin));
             if (lane == 0 && ov != f2ord(3.0e38f)) atomicMin(P.out_min, ov);
         }
-#endif
     }
     const int tile_unc = __syncthreads_or(unc ? 1 : 0);        // also: cnt[] complete, the z-buffer is dead
     PHASE_MARK(3);
-#ifdef DIBR_X_NO_SOFT
-    return;
-#endif
     if (!tile_unc || P.knum <= 0) return;
 
     // ---- phase D: soft silhouette.  Thread = pixel, block-major: warp w owns the 8x4 block w ---------------------

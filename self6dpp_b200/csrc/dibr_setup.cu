@@ -67,9 +67,7 @@ __device__ __forceinline__ void store_face(const SetupParams& P, int g, int b, f
         r.az = az; r.bz = bz; r.cz = cz; r.nz = nz; r.image = __int_as_float(b); r.pad1 = 0.f;
         r.xmin = xmin; r.ymin = ymin; r.xmax = xmax; r.ymax = ymax;
         P.ws.recs[g] = r;
-#ifndef DIBR_X_NO_BIN
         if (ok) bin_face(P, g, b, xmin, ymin, xmax, ymax);
-#endif
     }
 }
 
