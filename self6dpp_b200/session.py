@@ -26,7 +26,7 @@ _MODE_ATTR = (("color", "colors"), ("norm", "normals"), ("xyz", "vertices"))
 
 
 class _PassBuffers(object):
-    def __init__(self, reg, mode, batch, height, width, max_faces, device, znear, zfar):
+    def __init__(self, reg, mode, batch, height, width, max_faces, device, znear, zfar, knum=None):
         self.names = [a for k, a in _MODE_ATTR if k in mode]
         self.keys = [k for k, a in _MODE_ATTR if k in mode] + ["ones"] + (["depth"] if "depth" in mode else [])
         self.split = [3] * len(self.names) + [1] + ([1] if "depth" in mode else [])
@@ -45,7 +45,7 @@ class _PassBuffers(object):
         self.normal_map = torch.empty(batch, height, width, 3, **f32) if "norm" in mode else None
         p = _lib.DibrPass()
         p.batch, p.height, p.width = batch, height, width
-        p.num_attr, p.knum = self.D, fused.DEFAULT_KNUM
+        p.num_attr, p.knum = self.D, fused.DEFAULT_KNUM if knum is None else int(knum)
         p.multiplier, p.delta, p.expand = fused.DEFAULT_MULTIPLIER, fused.DEFAULT_DELTA, fused.DEFAULT_EXPAND
         p.total_faces, p.faces_per_image = max_faces, 0
         p.num_instances, p.num_K = batch, batch
@@ -74,7 +74,10 @@ class _PassBuffers(object):
 
 class RenderSession(object):
     def __init__(self, models, batch, height, width, student_mode=("color", "depth", "mask", "norm", "prob"),
-                 teacher_mode=("norm",), device="cuda:0", znear=0.01, zfar=100.0):
+                 teacher_mode=("norm",), device="cuda:0", znear=0.01, zfar=100.0, teacher_soft_mask=True):
+        """``teacher_soft_mask=False`` skips the soft-silhouette phase of the teacher rasterisation (K = 0).  The reference
+        always computes it (kaolin's forward does) and then drops it when ``mode`` has no "color"
+        (renderer_dibr.py:273-286), so nothing a caller can observe changes; the default keeps the reference's work."""
         self.device = torch.device(device)
         self.B, self.H, self.W = int(batch), int(height), int(width)
         self.lib = _lib.load()
@@ -88,8 +91,8 @@ class RenderSession(object):
         max_faces = B * int(reg.table[:, 3].max())
         with torch.cuda.device(self.device):
             self.student = _PassBuffers(reg, student_mode, B, self.H, self.W, max_faces, self.device, znear, zfar)
-            self.teacher = _PassBuffers(reg, teacher_mode, B, self.H, self.W, max_faces, self.device, znear, zfar) \
-                if teacher_mode else None
+            self.teacher = _PassBuffers(reg, teacher_mode, B, self.H, self.W, max_faces, self.device, znear, zfar,
+                                        knum=None if teacher_soft_mask else 0) if teacher_mode else None
             f32 = dict(dtype=torch.float32, device=self.device)
             self.g_p2d = torch.empty(max_faces, 6, **f32)
             self.g_fattr = torch.empty(max_faces, 3, self.student.D, **f32)
