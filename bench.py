@@ -360,7 +360,7 @@ def main_b200(args):
                 "config": {"workload": "cfg2: batch 32 x 256x256 ROI crops per GPU, 13 LINEMOD-shaped meshes (4.1k-5.9k faces); "
                                        "student colour+depth+mask+norm+prob fwd+bwd, teacher norm fwd",
                            "batch_per_gpu": BATCH, "faces_in_batch": faces_total, "l2": "flushed between steps (256 MiB memset)",
-                           "passes": "2 fused rasterisations + 1 backward per step (reference: 4 fwd + 2 bwd per sample)",
+                           "passes": "2 fused rasterisations + 1 backward per step (reference: 4 fwd + 2 bwd per sample); inside the call the teacher rasterisation runs on a side stream next to the student chain",
                            "api": "value/e2e: RenderSession.step -> dibr_render_step (one C-ABI call per step); "
                                   "python_api: Renderer_dibr.render_batch x2 + torch.autograd.backward (drop-in reference API)"},
                 "option_teacher_without_soft_mask": {"value": BATCH * n * args.steps / (lean_ms * 1e-3), "unit": UNIT,
