@@ -66,6 +66,7 @@ class _ModelRegistry(object):
         self.verts = None
         self.table = None        # [n, 4] vert_base, num_verts, face_base, num_faces
         self.attrs = {}          # tuple(attr names) -> [sum verts, 3*len] tensor
+        self.generation = 0      # bumped whenever the packed tables are rebuilt
 
     @staticmethod
     def _sig(model):
@@ -108,6 +109,7 @@ class _ModelRegistry(object):
         self.table = np.stack([pk.vert_base[:-1], np.asarray(pk.num_verts), pk.face_base[:-1], np.asarray(pk.num_faces)],
                               axis=1).astype(np.int64)
         self.attrs = {}
+        self.generation += 1
 
     def attr_matrix(self, names):
         key = tuple(names)
@@ -129,6 +131,7 @@ class Renderer_dibr(object):
     def __init__(self, height, width, mode):
         self.dib_ren = DIBRenderer(height, width, mode)
         self._registry = _ModelRegistry()
+        self._table_cache = {}
 
     def _render_batch_fast(self, Rs, ts, models, Ks, width, height, znear, zfar, rot_type, names, split, flags,
                            min_output=None, multi=False):
@@ -151,31 +154,41 @@ class Renderer_dibr(object):
         K = K.reshape(-1, 3, 3)
         if R.device != device or ts.device != device or R.dtype != torch.float32 or ts.dtype != torch.float32:
             return None
-        tab = reg.table[slots]                                         # [B,4]
-        nf, nv = tab[:, 3], tab[:, 1]
-        host = torch.empty(B * fused.INST_STRIDE + B + 1, dtype=torch.int32, pin_memory=True)
-        hn = host.numpy()
-        desc = hn[:B * fused.INST_STRIDE].reshape(B, fused.INST_STRIDE)
-        out_base = np.cumsum(nf) - nf
-        ar = np.arange(B)
-        desc[:, 0], desc[:, 1], desc[:, 2], desc[:, 3], desc[:, 4] = tab[:, 0], nv, tab[:, 2], nf, out_base
-        desc[:, 5] = ar
-        desc[:, 6] = ar if K.shape[0] > 1 else 0
-        desc[:, 7] = tab[:, 0]
-        desc[:, 8] = np.cumsum(nv) - nv
-        desc[:, 9] = 0 if multi else ar                               # image the instance lands in
-        desc[:, 10] = tab[:, 0]
-        desc[:, 11] = 0
-        hn[B * fused.INST_STRIDE] = 0
-        hn[B * fused.INST_STRIDE + 1:] = np.cumsum(nf)
+        # instance table: a function of WHICH models sit in the batch only (poses travel separately), so the device copy is
+        # kept per batch composition -- the self-supervised loop draws from a dozen models, compositions repeat
+        key = (slots.tobytes(), bool(multi), K.shape[0] > 1, reg.generation)
+        hit = self._table_cache.get(key)
+        if hit is None:
+            tab = reg.table[slots]                                         # [B,4]
+            nf, nv = tab[:, 3], tab[:, 1]
+            host = torch.empty(B * fused.INST_STRIDE + B + 1, dtype=torch.int32, pin_memory=True)
+            hn = host.numpy()
+            desc = hn[:B * fused.INST_STRIDE].reshape(B, fused.INST_STRIDE)
+            out_base = np.cumsum(nf) - nf
+            ar = np.arange(B)
+            desc[:, 0], desc[:, 1], desc[:, 2], desc[:, 3], desc[:, 4] = tab[:, 0], nv, tab[:, 2], nf, out_base
+            desc[:, 5] = ar
+            desc[:, 6] = ar if K.shape[0] > 1 else 0
+            desc[:, 7] = tab[:, 0]
+            desc[:, 8] = np.cumsum(nv) - nv
+            desc[:, 9] = 0 if multi else ar                               # image the instance lands in
+            desc[:, 10] = tab[:, 0]
+            desc[:, 11] = 0
+            hn[B * fused.INST_STRIDE] = 0
+            hn[B * fused.INST_STRIDE + 1:] = np.cumsum(nf)
+            if multi:                                                      # one image owns every face
+                hn[B * fused.INST_STRIDE + 1] = int(nf.sum())
+            dev = torch.empty_like(host, device=device)
+            dev.copy_(host, non_blocking=True)
+            hit = (dev, host, int(nf.sum()), int(nv.sum()))                # the pinned source stays alive with the copy
+            if len(self._table_cache) > 64:
+                self._table_cache.clear()
+            self._table_cache[key] = hit
+        dev, _, total_faces, total_verts = hit
         nimg = 1 if multi else B
-        if multi:                                                      # one image owns every face
-            hn[B * fused.INST_STRIDE + 1] = int(nf.sum())
-        dev = torch.empty_like(host, device=device)
-        dev.copy_(host, non_blocking=True)
         A = sum(int(models[0][n].shape[-1]) for n in names)          # 3 per colour / normal / xyz set, 2 for uvs
         meta = dict(batch=nimg, height=int(height), width=int(width), attr_dim=A, attr_flags=int(flags),
-                    total_faces=int(nf.sum()), num_instances=B, num_inst_verts=int(nv.sum()), pack=reg.pack,
+                    total_faces=total_faces, num_instances=B, num_inst_verts=total_verts, pack=reg.pack,
                     knum=fused.DEFAULT_KNUM, multiplier=fused.DEFAULT_MULTIPLIER, delta=fused.DEFAULT_DELTA,
                     expand=fused.DEFAULT_EXPAND, want_normals=False, num_attr_rows=int(reg.verts.shape[0]),
                     out_split=split, inst_desc=dev[:B * fused.INST_STRIDE],
