@@ -144,7 +144,7 @@ int dibr_workspace_bytes(const DibrPass* p, size_t* bytes) {
 
 int dibr_setup_faces(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
-    if (!p->points3d || !p->points2d || !p->normalz) return fail("setup_faces: points3d/points2d/normalz required");
+    if (p->total_faces > 0 && (!p->points3d || !p->points2d || !p->normalz)) return fail("setup_faces: points3d/points2d/normalz required");
     const dibr::SetupParams s = setup_params(p);
     g_launches += 2;
     return cuda_fail("dibr_setup_faces", dibr::launch_setup_faces(s, (cudaStream_t)stream));
@@ -169,7 +169,7 @@ int dibr_setup_meshes(const DibrPass* p, void* stream) {
 
 int dibr_forward(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
-    if (!p->face_attr || !p->improb || !p->imidx || !p->imcomp) return fail("forward: face_attr/improb/imidx/imcomp required");
+    if ((p->total_faces > 0 && !p->face_attr) || !p->improb || !p->imidx || !p->imcomp) return fail("forward: face_attr/improb/imidx/imcomp required");
     if (int e = check_outputs(p)) return e;
     const dibr::Workspace w = carve(p, p->workspace);
     dibr::FwdParams f;
@@ -208,6 +208,7 @@ int dibr_forward(const DibrPass* p, void* stream) {
 
 int dibr_backward_faces(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
+    if (p->total_faces == 0) return 0;                      // nothing to differentiate
     if (!p->face_attr || !p->improb || !p->imidx || !p->imcomp) return fail("backward_faces: saved forward buffers required");
     if (!p->grad_points2d || !p->grad_face_attr) return fail("backward_faces: grad outputs required");
     const dibr::Workspace w = carve(p, p->workspace);
