@@ -5,8 +5,8 @@
 // PIXEL and scatters into its face with fp32 atomicAdd (9*D + up to 4*K atomics per pixel, order
 // undefined).  Here the loop is turned inside out: the forward kernel leaves two work lists -- faces
 // that won a pixel, faces that entered a soft-silhouette product -- and a group of lanes owns one
-// listed FACE: it walks the pixel centres inside its bbox (colour part, 8 lanes) or expanded bbox
-// (soft part, one warp), picks up the pixels that belong to it (imidx == face+1, or uncovered with
+// listed FACE: it walks the pixel centres inside its bbox (colour part, 4 lanes) or expanded bbox
+// (soft part, 16 lanes), picks up the pixels that belong to it (imidx == face+1, or uncovered with
 // the face among the first K), accumulates in registers in a fixed order and reduces with a fixed
 // shuffle tree.  The order of the work lists is arbitrary but no result depends on it: every face is
 // reduced on its own and written to its own slot, so the gradients are bit-reproducible run to run.
@@ -45,7 +45,10 @@ __device__ __forceinline__ int row_lower(const float* __restrict__ ys, int H, fl
     return r;
 }
 
-constexpr int GRP = 8;     // lanes per face in the colour kernel
+#ifndef DIBR_COLOR_LANES
+#define DIBR_COLOR_LANES 4        // measured on cfg2 (faces win ~13 pixels): 16 lanes 126 us, 8: 116, 4: 112, 2: 110, 1: 144 for the launch
+#endif
+constexpr int GRP = DIBR_COLOR_LANES;     // lanes per face in the colour part
 
 // ---- colour part: one 8-lane group per face that WON at least one pixel (work list written by the forward) ------
 template <int DMAX>
@@ -100,13 +103,12 @@ __device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
             }
         }
     }
-    // fixed-tree reduction over the 8 lanes of the face
+    // fixed-tree reduction over the lanes of the face
 #pragma unroll
     for (int i = 0; i < 3 * DMAX; i++) {
         float v = acc[i];
-        v += __shfl_xor_sync(full, v, 4);
-        v += __shfl_xor_sync(full, v, 2);
-        v += __shfl_xor_sync(full, v, 1);
+#pragma unroll
+        for (int o = GRP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
         acc[i] = v;
     }
     if (!active || gl != 0) return;
