@@ -267,6 +267,25 @@ int dibr_mask_loss_scratch_floats(int64_t n);
 int dibr_mask_loss_forward(const DibrMaskLoss *p, void *stream);
 int dibr_mask_loss_backward(const DibrMaskLoss *p, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Chamfer distances -> the depth loss of core/self6dpp/losses/depth_bp_chamfer_loss.py:38-62: per sample the mean of the
+ * distances below `threshold` (threshold <= 0: all) in both directions, samples with an empty selection skipped (the
+ * reference's NaN test), the sum divided by max(#valid samples, 1).  stats: [batch, 4] scratch that the backward reads;
+ * ticket: one uint32, ZERO before the first call (re-armed by the kernel); out[0] = loss, out[1] = #valid samples. */
+typedef struct DibrChamferReduce {
+    int32_t batch, stride1, stride2;
+    float threshold;
+    const int32_t *count1, *count2;          /* device [batch] or NULL (all rows) */
+    const float *dist1, *dist2;              /* [batch, stride_i] */
+    float *stats;                            /* [batch, 4] */
+    uint32_t *ticket;
+    float *out;                              /* [2] */
+    const float *grad_out;                   /* backward in:  [1] */
+    float *grad_dist1, *grad_dist2;          /* backward out: [batch, stride_i] */
+} DibrChamferReduce;
+int dibr_chamfer_reduce_forward(const DibrChamferReduce *p, void *stream);
+int dibr_chamfer_reduce_backward(const DibrChamferReduce *p, void *stream);
+
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);
 

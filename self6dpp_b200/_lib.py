@@ -89,11 +89,22 @@ class DibrMaskLoss(ctypes.Structure):
     ]
 
 
+class DibrChamferReduce(ctypes.Structure):
+    """Mirror of ``struct DibrChamferReduce`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("stride1", ctypes.c_int32), ("stride2", ctypes.c_int32), ("threshold", ctypes.c_float),
+        ("count1", _c_i32p), ("count2", _c_i32p), ("dist1", _c_f32p), ("dist2", _c_f32p),
+        ("stats", _c_f32p), ("ticket", ctypes.c_void_p), ("out", _c_f32p),
+        ("grad_out", _c_f32p), ("grad_dist1", _c_f32p), ("grad_dist2", _c_f32p),
+    ]
+
+
 EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_device_count", "dibr_workspace_bytes",
            "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
            "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_backproject_compact",
            "dibr_backproject_compact_backward", "dibr_mask_loss_scratch_floats", "dibr_mask_loss_forward",
-           "dibr_mask_loss_backward", "dibr_launch_count"]
+           "dibr_mask_loss_backward", "dibr_chamfer_reduce_forward", "dibr_chamfer_reduce_backward", "dibr_launch_count"]
 
 _lib = None
 
@@ -137,6 +148,10 @@ def load():
     for name in ("dibr_backproject_compact", "dibr_backproject_compact_backward"):
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrBackproject), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    for name in ("dibr_chamfer_reduce_forward", "dibr_chamfer_reduce_backward"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrChamferReduce), ctypes.c_void_p]
         fn.restype = ctypes.c_int
     lib.dibr_mask_loss_scratch_floats.argtypes = [ctypes.c_int64]
     lib.dibr_mask_loss_scratch_floats.restype = ctypes.c_int

@@ -382,6 +382,32 @@ int dibr_mask_loss_backward(const DibrMaskLoss* p, void* stream) {
     return cuda_fail("dibr_mask_loss_backward", dibr::launch_mask_loss_backward(q, (cudaStream_t)stream));
 }
 
+static int cr_params(const DibrChamferReduce* p, dibr::ChamferReduceParams& q, bool backward) {
+    if (!p) return fail("null DibrChamferReduce");
+    if (p->batch < 0 || p->stride1 < 0 || p->stride2 < 0) return fail("chamfer_reduce: negative sizes");
+    if (!p->dist1 || !p->dist2 || !p->stats || !p->out) return fail("chamfer_reduce: dist / stats / out required");
+    if (!backward && !p->ticket) return fail("chamfer_reduce: ticket required");
+    if (backward && (!p->grad_out || !p->grad_dist1 || !p->grad_dist2)) return fail("chamfer_reduce backward: gradient buffers required");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    q.batch = p->batch; q.stride1 = p->stride1; q.stride2 = p->stride2; q.threshold = p->threshold;
+    q.count1 = p->count1; q.count2 = p->count2; q.dist1 = p->dist1; q.dist2 = p->dist2;
+    q.stats = p->stats; q.ticket = p->ticket; q.out = p->out;
+    q.grad_out = p->grad_out; q.grad_dist1 = p->grad_dist1; q.grad_dist2 = p->grad_dist2;
+    return 0;
+}
+int dibr_chamfer_reduce_forward(const DibrChamferReduce* p, void* stream) {
+    dibr::ChamferReduceParams q;
+    if (int e = cr_params(p, q, false)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_chamfer_reduce_forward", dibr::launch_chamfer_reduce_forward(q, (cudaStream_t)stream));
+}
+int dibr_chamfer_reduce_backward(const DibrChamferReduce* p, void* stream) {
+    dibr::ChamferReduceParams q;
+    if (int e = cr_params(p, q, true)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_chamfer_reduce_backward", dibr::launch_chamfer_reduce_backward(q, (cudaStream_t)stream));
+}
+
 // gather [n,9] + [n,3] into [n,12] so ONE D2H copy returns the pose gradients
 __global__ void pack_pose_grad_kernel(const float* __restrict__ gR, const float* __restrict__ gt, float* __restrict__ out, int n)
 {

@@ -187,6 +187,23 @@ struct MaskLossParams {
 int mask_loss_partial_floats(long long n);
 int launch_mask_loss_forward(const MaskLossParams& P, cudaStream_t stream);
 int launch_mask_loss_backward(const MaskLossParams& P, cudaStream_t stream);
+// chamfer distances -> depth loss (dibr_maskloss.cu)
+struct ChamferReduceParams {
+    int batch, stride1, stride2;
+    float threshold;
+    const int* count1;
+    const int* count2;
+    const float* dist1;
+    const float* dist2;
+    float* stats;              // [batch, 4]: sum1, n1, sum2, n2 of the selected distances
+    unsigned int* ticket;      // [1], zero between calls
+    float* out;                // [2]: loss, number of valid samples
+    const float* grad_out;     // backward: [1]
+    float* grad_dist1;
+    float* grad_dist2;
+};
+int launch_chamfer_reduce_forward(const ChamferReduceParams& P, cudaStream_t stream);
+int launch_chamfer_reduce_backward(const ChamferReduceParams& P, cudaStream_t stream);
 // depth map -> compacted cloud (dibr_backproject.cu)
 struct BackprojectParams {
     int batch, height, width, num_K;

@@ -99,3 +99,87 @@ int launch_mask_loss_backward(const MaskLossParams& P, cudaStream_t stream)
 }
 
 }  // namespace dibr
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reduction of the chamfer distances into the depth loss of core/self6dpp/losses/depth_bp_chamfer_loss.py:38-62:
+//   per sample  cur = mean(dist1[dist1 < thr]) + mean(dist2[dist2 < thr])   (thr <= 0: all points), NaN when a
+//   selection is empty -> the sample is skipped;   loss = sum(cur over the valid samples) / max(#valid, 1)
+// One CTA per sample (strided sums, fixed trees), the last CTA adds the samples in order; one elementwise backward.
+// ---------------------------------------------------------------------------------------------------------------
+namespace dibr {
+
+constexpr int CR_T = 512;
+
+__global__ void __launch_bounds__(CR_T) chamfer_reduce_forward_kernel(ChamferReduceParams P)
+{
+    __shared__ float red[CR_T / 32][4];
+    __shared__ int last;
+    const int b = blockIdx.x;
+    const int n1 = P.count1 ? min(P.count1[b], P.stride1) : P.stride1, n2 = P.count2 ? min(P.count2[b], P.stride2) : P.stride2;
+    const float* d1 = P.dist1 + (size_t)b * P.stride1;
+    const float* d2 = P.dist2 + (size_t)b * P.stride2;
+    const bool all = !(P.threshold > 0.0f);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < n1; i += CR_T) { const float d = d1[i]; if (all || d < P.threshold) { v[0] += d; v[1] += 1.0f; } }
+    for (int i = threadIdx.x; i < n2; i += CR_T) { const float d = d2[i]; if (all || d < P.threshold) { v[2] += d; v[3] += 1.0f; } }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < CR_T / 32; w++) s += red[w][threadIdx.x];
+        P.stats[(size_t)b * 4 + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last || threadIdx.x != 0) return;
+    __threadfence();
+    float loss = 0.f, nvalid = 0.f;
+    for (int s = 0; s < P.batch; s++) {                       // sample order: fixed
+        const float s1 = __ldcg(P.stats + (size_t)s * 4), c1 = __ldcg(P.stats + (size_t)s * 4 + 1);
+        const float s2 = __ldcg(P.stats + (size_t)s * 4 + 2), c2 = __ldcg(P.stats + (size_t)s * 4 + 3);
+        if (c1 > 0.f && c2 > 0.f) { loss += s1 / c1 + s2 / c2; nvalid += 1.0f; }
+    }
+    P.out[0] = loss / fmaxf(nvalid, 1.0f);
+    P.out[1] = nvalid;
+    *P.ticket = 0u;
+}
+
+__global__ void __launch_bounds__(256) chamfer_reduce_backward_kernel(ChamferReduceParams P)
+{
+    const int b = blockIdx.y, which = blockIdx.z;
+    const int stride = which == 0 ? P.stride1 : P.stride2;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= stride) return;
+    const int* cnt = which == 0 ? P.count1 : P.count2;
+    const int n = cnt ? min(cnt[b], stride) : stride;
+    const float c1 = P.stats[(size_t)b * 4 + 1], c2 = P.stats[(size_t)b * 4 + 3];
+    const float d = (which == 0 ? P.dist1 : P.dist2)[(size_t)b * stride + i];
+    float g = 0.f;
+    if (i < n && c1 > 0.f && c2 > 0.f && (!(P.threshold > 0.0f) || d < P.threshold))
+        g = P.grad_out[0] / (which == 0 ? c1 : c2) / fmaxf(P.out[1], 1.0f);
+    (which == 0 ? P.grad_dist1 : P.grad_dist2)[(size_t)b * stride + i] = g;
+}
+
+int launch_chamfer_reduce_forward(const ChamferReduceParams& P, cudaStream_t stream)
+{
+    if (P.batch <= 0) return 0;
+    chamfer_reduce_forward_kernel<<<P.batch, CR_T, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+int launch_chamfer_reduce_backward(const ChamferReduceParams& P, cudaStream_t stream)
+{
+    const int smax = P.stride1 > P.stride2 ? P.stride1 : P.stride2;
+    if (P.batch <= 0 || smax <= 0) return 0;
+    chamfer_reduce_backward_kernel<<<dim3((smax + 255) / 256, P.batch, 2), 256, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dibr

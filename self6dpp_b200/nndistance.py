@@ -187,6 +187,53 @@ def backproject_compact(depth, K):
     return BackprojectCompact.apply(depth, K)
 
 
+_TICKETS = {}
+
+
+def _ticket(device):
+    t = _TICKETS.get(str(device))
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)      # zero between calls: the kernel re-arms it
+        _TICKETS[str(device)] = t
+    return t
+
+
+class ChamferReduce(Function):
+    """(dist1 [B,S1], count1, dist2 [B,S2], count2, threshold) -> loss of depth_bp_chamfer_loss.py:38-62 (without the
+    centre term): one reduction launch (``dibr_chamfer_reduce_forward``), one elementwise launch for the backward."""
+
+    @staticmethod
+    def forward(ctx, dist1, count1, dist2, count2, threshold):
+        device = dist1.device
+        d1, d2 = dist1.detach().contiguous(), dist2.detach().contiguous()
+        B = d1.shape[0]
+        stats = torch.empty(B, 4, dtype=torch.float32, device=device)
+        out = torch.empty(2, dtype=torch.float32, device=device)
+        q = _lib.DibrChamferReduce()
+        q.batch, q.stride1, q.stride2, q.threshold = B, d1.shape[1], d2.shape[1], float(threshold)
+        q.count1, q.count2, q.dist1, q.dist2 = _lib.ptr(count1), _lib.ptr(count2), _lib.ptr(d1), _lib.ptr(d2)
+        q.stats, q.out = _lib.ptr(stats), _lib.ptr(out)
+        q.ticket = ctypes.c_void_p(_ticket(device).data_ptr())
+        _launch("dibr_chamfer_reduce_forward", q, device)
+        ctx.save_for_backward(d1, d2, count1, count2, stats, out)
+        ctx.threshold = float(threshold)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        d1, d2, count1, count2, stats, out = ctx.saved_tensors
+        device = d1.device
+        go = grad_out.detach().reshape(1).to(torch.float32).contiguous()
+        g1, g2 = torch.empty_like(d1), torch.empty_like(d2)
+        q = _lib.DibrChamferReduce()
+        q.batch, q.stride1, q.stride2, q.threshold = d1.shape[0], d1.shape[1], d2.shape[1], ctx.threshold
+        q.count1, q.count2, q.dist1, q.dist2 = _lib.ptr(count1), _lib.ptr(count2), _lib.ptr(d1), _lib.ptr(d2)
+        q.stats, q.out, q.grad_out = _lib.ptr(stats), _lib.ptr(out), _lib.ptr(go)
+        q.grad_dist1, q.grad_dist2 = _lib.ptr(g1), _lib.ptr(g2)
+        _launch("dibr_chamfer_reduce_backward", q, device)
+        return g1, None, g2, None, None
+
+
 def depth_bp_chamfer_loss(ren_depths, real_depths, Ks, distance_threshold=0.05, center_lw=0):
     """
     Args (core/self6dpp/losses/depth_bp_chamfer_loss.py:12-19):
@@ -198,6 +245,9 @@ def depth_bp_chamfer_loss(ren_depths, real_depths, Ks, distance_threshold=0.05, 
     real_pts, real_cnt = backproject_compact(real_depths, Kt)
     rend_pts, rend_cnt = backproject_compact(ren_depths, Kt)
     dist1, dist2, _, _ = nnd_padded(real_pts, real_cnt, rend_pts, rend_cnt)
+    if not center_lw > 0:            # the usual configuration: the whole reduction is one launch
+        loss = ChamferReduce.apply(dist1, real_cnt, dist2, rend_cnt, float(distance_threshold))
+        return loss, torch.zeros((), dtype=ren_depths.dtype, device=ren_depths.device)
     ar = torch.arange(H * W, device=ren_depths.device).view(1, -1)
     v1, v2 = ar < real_cnt.view(-1, 1), ar < rend_cnt.view(-1, 1)
     s1, s2 = v1, v2

@@ -164,3 +164,20 @@ def test_backproject_compact_equals_the_torch_expressions():
         (p1 * w).sum().backward()
         (p2 * w).sum().backward()
         assert float((d1.grad - d2.grad).abs().max()) <= 1e-6 * float(d2.grad.abs().max())
+
+
+@pytest.mark.parametrize("thr", [0.05, 0.0])
+def test_fused_loss_reduction_equals_the_torch_expressions(thr):
+    """center_lw = 0 takes the one-launch reduction (dibr_chamfer_reduce_*); it must agree with the torch restatement of
+    depth_bp_chamfer_loss.py:38-62 (same path with the centre term switched on at a negligible weight), incl. an empty sample"""
+    from self6dpp_b200.nndistance import depth_bp_chamfer_loss
+    d = np.load(GOLD)
+    real, K = torch.tensor(d["real"], device=DEV), torch.tensor(d["K"], device=DEV)
+    r1 = torch.tensor(d["ren"], device=DEV, requires_grad=True)
+    r2 = torch.tensor(d["ren"], device=DEV, requires_grad=True)
+    l1, _ = depth_bp_chamfer_loss(r1, real, K, thr, 0)
+    l2, _ = depth_bp_chamfer_loss(r2, real, K, thr, 1e-30)          # torch path (centre term contributes ~0)
+    l1.backward()
+    l2.backward()
+    assert abs(float(l1) - float(l2)) <= 1e-5 * abs(float(l2))
+    assert float((r1.grad - r2.grad).abs().max()) <= 1e-5 * float(r2.grad.abs().max())
