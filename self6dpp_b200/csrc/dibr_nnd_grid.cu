@@ -392,34 +392,54 @@ __global__ void __launch_bounds__(NND_T) nnd_backward_inv_kernel(NndParams P, co
             crowd = true;
         }
     }
-    // crowds: the warp walks the other cloud's index array 32 entries at a time for one such target at a time; the matches
-    // of a round are handed over in lane order, so the sum still runs in ascending k like the exhaustive gather
+    // crowds, one target at a time for the whole warp, the sum still in ascending k like the exhaustive gather:
+    //   up to 256 queries: every round the lanes look through the target's list for the smallest k above the last one
+    //   taken (strided reads + a warp min), the owner's running sums take that query's pull;
+    //   beyond: the warp walks the other cloud's index array 32 entries at a time and hands the matches of a round over
+    //   in lane order.
     __syncwarp();
     unsigned todo = __ballot_sync(0xffffffffu, crowd);
+    const int* cntw = (dir == 0 ? cnt0 : cnt1) + (size_t)b * (sA + 1);
+    const int* listw = (dir == 0 ? list0 : list1) + (size_t)b * sB;
     while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
         const int jt = __shfl_sync(0xffffffffu, j, src);
         const float tx = __shfl_sync(0xffffffffu, ax, src), ty = __shfl_sync(0xffffffffu, ay, src), tz = __shfl_sync(0xffffffffu, az, src);
         float sx = __shfl_sync(0xffffffffu, gx, src), sy = __shfl_sync(0xffffffffu, gy, src), sz = __shfl_sync(0xffffffffu, gz, src);
-        for (int k0 = 0; k0 < Bc.n; k0 += 32) {
-            const int k = k0 + lane;
-            const bool hit = (k < Bc.n) && (idxB[k] == jt);
-            unsigned hits = __ballot_sync(0xffffffffu, hit);
-            if (hits == 0u) continue;
-            float cx = 0.f, cy = 0.f, cz = 0.f;
-            if (hit) {
-                const float gk = gB[k] * 2.0f;
-                cx = __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3], tx));
-                cy = __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3 + 1], ty));
-                cz = __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3 + 2], tz));
+        const int s = (jt == 0) ? 0 : cntw[jt - 1], e = cntw[jt];
+        if (e - s <= 256) {
+            int last = -1;
+            for (int t = s; t < e; t++) {
+                int kmin = 0x7fffffff;
+                for (int u = s + lane; u < e; u += 32) { const int k = listw[u]; if (k > last && k < kmin) kmin = k; }
+                kmin = __reduce_min_sync(0xffffffffu, kmin);
+                last = kmin;
+                const float gk = gB[kmin] * 2.0f;
+                sx = __fsub_rn(sx, __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)kmin * 3], tx)));
+                sy = __fsub_rn(sy, __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)kmin * 3 + 1], ty)));
+                sz = __fsub_rn(sz, __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)kmin * 3 + 2], tz)));
             }
-            while (hits) {
-                const int l = __ffs(hits) - 1;
-                hits &= hits - 1;
-                sx = __fsub_rn(sx, __shfl_sync(0xffffffffu, cx, l));
-                sy = __fsub_rn(sy, __shfl_sync(0xffffffffu, cy, l));
-                sz = __fsub_rn(sz, __shfl_sync(0xffffffffu, cz, l));
+        } else {
+            for (int k0 = 0; k0 < Bc.n; k0 += 32) {
+                const int k = k0 + lane;
+                const bool hit = (k < Bc.n) && (idxB[k] == jt);
+                unsigned hits = __ballot_sync(0xffffffffu, hit);
+                if (hits == 0u) continue;
+                float cx = 0.f, cy = 0.f, cz = 0.f;
+                if (hit) {
+                    const float gk = gB[k] * 2.0f;
+                    cx = __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3], tx));
+                    cy = __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3 + 1], ty));
+                    cz = __fmul_rn(gk, __fsub_rn(Bc.xyz[(size_t)k * 3 + 2], tz));
+                }
+                while (hits) {
+                    const int l = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    sx = __fsub_rn(sx, __shfl_sync(0xffffffffu, cx, l));
+                    sy = __fsub_rn(sy, __shfl_sync(0xffffffffu, cy, l));
+                    sz = __fsub_rn(sz, __shfl_sync(0xffffffffu, cz, l));
+                }
             }
         }
         if (lane == src) { gx = sx; gy = sy; gz = sz; }
