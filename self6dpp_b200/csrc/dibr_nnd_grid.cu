@@ -27,6 +27,11 @@ constexpr int NND_G = 64;                       // cells per axis at most
 constexpr int NND_G3 = NND_G * NND_G * NND_G;
 constexpr int NND_RMAX = 4;                     // shells before a query falls back to the exhaustive scan
 constexpr int NND_T = 256;
+#ifndef DIBR_NND_QL
+#define DIBR_NND_QL 1        // measured (tools/nnd_variants.sh): 1 lane 0.50 ms, 2: 0.51, 4: 0.56, 8: 0.70 for the cfg2 batch
+#endif
+constexpr int NND_QL = DIBR_NND_QL;              // lanes per query: they split every cell range and share the shell walk
+static_assert(NND_QL == 1 || NND_QL == 2 || NND_QL == 4 || NND_QL == 8, "a sub-warp group");
 
 // workspace regions:
 //   box      [2 dirs][batch][8]   ordered-uint min xyz (words 0..2), max xyz (words 4..6) of the dir's target cloud
@@ -202,9 +207,10 @@ __global__ void __launch_bounds__(NND_T) nnd_query_kernel(NndParams P, const uns
 {
     const int dir = blockIdx.z, b = blockIdx.y;
     const CloudView Q = cloud_of(P, dir == 0 ? 0 : 1, b);
-    if ((int)(blockIdx.x * NND_T) >= Q.n) return;                  // whole CTA beyond the cloud
-    const int j = blockIdx.x * NND_T + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    if ((int)(blockIdx.x * (NND_T / NND_QL)) >= Q.n) return;       // whole CTA beyond the cloud
+    const int j = (blockIdx.x * NND_T + threadIdx.x) / NND_QL;
+    const int lane = threadIdx.x & 31, sub = threadIdx.x % NND_QL;
+    const unsigned gmask = (NND_QL == 32) ? 0xffffffffu : (((1u << NND_QL) - 1u) << ((lane / NND_QL) * NND_QL));
     const int m = cloud_of(P, dir == 0 ? 1 : 0, b).n;
     float* dist = (dir == 0 ? P.dist1 + (size_t)P.stride1 * b : P.dist2 + (size_t)P.stride2 * b);
     int* idx = (dir == 0 ? P.idx1 + (size_t)P.stride1 * b : P.idx2 + (size_t)P.stride2 * b);
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(NND_T) nnd_query_kernel(NndParams P, const uns
 #ifdef DIBR_NND_STATS
         npts_stat += e - s;
 #endif
-        for (int k = s; k < e; k++) {
+        for (int k = s + sub; k < e; k += NND_QL) {
             const float4 t = __ldg(pts + k);
             const float d = sqdist_exact(qx, qy, qz, t.x, t.y, t.z);
             const int ti = __float_as_int(t.w);
@@ -262,6 +268,13 @@ __global__ void __launch_bounds__(NND_T) nnd_query_kernel(NndParams P, const uns
                 }
             }
         }
+        // the lanes of the query agree on the best so far (they walk the shells in lock step, so the group mask is safe)
+#pragma unroll
+        for (int o = NND_QL / 2; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(gmask, best, o);
+            const int oi = __shfl_xor_sync(gmask, bi, o);
+            if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+        }
         // everything not visited yet is at least lb away (a side of the cube that already reaches the grid's edge has
         // nothing beyond it); the margins cover the rounding of the cell boundaries and of the distances
         float lb = 3.4e38f;
@@ -278,7 +291,7 @@ __global__ void __launch_bounds__(NND_T) nnd_query_kernel(NndParams P, const uns
     // queries far from every target point (a part of one cloud the other does not have): the exhaustive scan, done by
     // the whole warp for one such query at a time -- a lone lane walking the cloud would set the kernel's duration
     __syncwarp();
-    unsigned todo = __ballot_sync(0xffffffffu, far);
+    unsigned todo = __ballot_sync(0xffffffffu, far && sub == 0);
     while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -297,12 +310,12 @@ __global__ void __launch_bounds__(NND_T) nnd_query_kernel(NndParams P, const uns
             const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
             if (od < wb || (od == wb && oi < wi)) { wb = od; wi = oi; }
         }
-        if (lane == src) { best = wb; bi = wi; }
+        if (lane / NND_QL == src / NND_QL) { best = wb; bi = wi; }
     }
 #ifdef DIBR_NND_STATS
-    if (live) { atomicAdd(&g_nnd_stats[min(rr_stat, 7)], 1ull); atomicAdd(&g_nnd_stats[8], (unsigned long long)npts_stat); }
+    if (live && sub == 0) { atomicAdd(&g_nnd_stats[min(rr_stat, 7)], 1ull); atomicAdd(&g_nnd_stats[8], (unsigned long long)npts_stat); }
 #endif
-    if (live) { dist[j] = best; idx[j] = bi; }
+    if (live && sub == 0) { dist[j] = best; idx[j] = bi; }
 }
 
 int launch_nnd_forward_grid(const NndParams& P, void* workspace, cudaStream_t stream)
@@ -322,7 +335,8 @@ int launch_nnd_forward_grid(const NndParams& P, void* workspace, cudaStream_t st
     nnd_bin_kernel<false><<<gpts, NND_T, 0, stream>>>(P, w.box, w.cells, w.sorted[0], w.sorted[1]);
     nnd_scan_kernel<<<2 * P.batch, 1024, 0, stream>>>(w.cells, NND_G3 + 1, 0, P, w.box);
     nnd_bin_kernel<true><<<gpts, NND_T, 0, stream>>>(P, w.box, w.cells, w.sorted[0], w.sorted[1]);
-    nnd_query_kernel<<<gpts, NND_T, 0, stream>>>(P, w.box, w.cells, w.sorted[0], w.sorted[1]);
+    const dim3 gq((smax * NND_QL + NND_T - 1) / NND_T, P.batch, 2);
+    nnd_query_kernel<<<gq, NND_T, 0, stream>>>(P, w.box, w.cells, w.sorted[0], w.sorted[1]);
     return (int)cudaGetLastError();
 }
 
