@@ -334,7 +334,10 @@ __device__ __noinline__ void fill_untouched_warp(const FwdParams& P, int packed_
     fill_tile_warp(P.imcomp + img_pix, P.width, 1, tx0, ty0, tw, th, 1.0f);
 }
 
-__global__ void __launch_bounds__(FWD_THREADS, 1024 / FWD_THREADS)
+#ifndef DIBR_FWD_MIN_CTAS
+#define DIBR_FWD_MIN_CTAS (1024 / DIBR_FWD_THREADS)
+#endif
+__global__ void __launch_bounds__(FWD_THREADS, DIBR_FWD_MIN_CTAS)
 dibr_forward_kernel(const __grid_constant__ FwdParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
