@@ -8,7 +8,7 @@
 //            load); the hits are compacted in ascending face order with warp ballots and one CTA barrier per
 //            round of 4096 faces.  Then the records of the listed faces are gathered into shared memory (corners,
 //            depths) and the front faces that really hold a pixel centre of the tile go on the raster list.
-//   phase B  face-parallel coverage with 4 lanes per face: barycentric solve in the frozen fp32 order and a 64-bit
+//   phase B  face-parallel coverage with 8 lanes per face: barycentric solve in the frozen fp32 order and a 64-bit
 //            shared-memory atomicMax on (orderable z | ~rank in the list).  The winner is the face with the largest z
 //            and, on ties, the smallest index -- what the reference's ascending loop with a strict '>' produces,
 //            independent of traversal order.
@@ -40,6 +40,10 @@ constexpr int NWARP = FWD_THREADS / 32;
 constexpr int HITCAP = 30;              // collected faces per pixel per pass of phase D (>= the default K: one pass)
 constexpr int BW = 8, BH = 4;           // pixel block of one warp in phase D
 constexpr int NBX = TILE / BW;
+#ifndef DIBR_RASTER_LANES
+#define DIBR_RASTER_LANES 8
+#endif
+constexpr int RASTER_LANES = DIBR_RASTER_LANES;      // lanes per face in phase B
 static_assert(NBX * (TILE / BH) == NWARP, "one 8x4 block per warp");
 static_assert(LCAP >= 32, "one bitmap word must fit an empty list");
 static_assert(LCAP <= 512 && TILE == 16, "rlist packing: 9-bit list index, 4-bit pixel coordinates");
@@ -234,9 +238,9 @@ __device__ void raster_list(FwdSmem& s, int nprev)
 {
     const int tid = threadIdx.x;
     const int rcount = s.rcount;
-    // ---- 4 lanes per face; faces with many pixels in the tile are deferred to the whole CTA
-    const int q = tid >> 2, ql = tid & 3;
-    for (int e = q; e < rcount; e += FWD_THREADS / 4) {
+    // ---- RASTER_LANES lanes per face; faces with many pixels in the tile are deferred to the whole CTA
+    const int q = tid / RASTER_LANES, ql = tid % RASTER_LANES;
+    for (int e = q; e < rcount; e += FWD_THREADS / RASTER_LANES) {
         const unsigned int packed = s.u.ab.rlist[e];
         const RasterEntry en = unpack_entry(packed);
         const int npx = en.nc * en.nr;
@@ -249,7 +253,7 @@ __device__ void raster_list(FwdSmem& s, int nprev)
         }
         const FaceK fk = facek_from_list(s, en.li);
         const unsigned inv = c_inv16[en.nc];                           // 65536 / nc + 1: exact i / nc for i < 256
-        for (int i = ql; i < npx; i += 4) {
+        for (int i = ql; i < npx; i += RASTER_LANES) {
             const int row = (int)(((unsigned)i * inv) >> 16);
             raster_pixel(s, fk, (unsigned)(nprev + en.li), en.c0 + (i - row * en.nc), en.r0 + row);
         }
