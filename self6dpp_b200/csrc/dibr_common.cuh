@@ -16,7 +16,10 @@ constexpr int TILE = 16;            // forward CTA tile (pixels per side): one p
 constexpr int FWD_THREADS = DIBR_FWD_THREADS;   // threads per tile CTA (8 warps, one 8x4 pixel block each in the soft phase)
 constexpr int LCAP = 512;           // faces per in-shared-memory batch of a tile
 constexpr int BIGCAP = 32;          // deferred large faces per batch
-constexpr int BIG_AREA = 64;        // pixels of a face inside the tile above which the CTA cooperates
+#ifndef DIBR_BIG_AREA
+#define DIBR_BIG_AREA 64
+#endif
+constexpr int BIG_AREA = DIBR_BIG_AREA;   // pixels of a face inside the tile above which the CTA cooperates
 static_assert(FWD_THREADS == TILE * TILE, "one pixel per thread");
 constexpr int MAX_IMAGE_SIDE = 16384;           // largest image side the ABI accepts
 
