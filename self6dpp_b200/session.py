@@ -8,7 +8,9 @@ pre-allocates every device buffer once (resident meshes, workspaces, outputs, gr
 pinned staging block) and per step only (1) writes poses / intrinsics / the instance table into
 pinned memory with numpy, (2) makes one ctypes call.  The call enqueues: one H2D copy, student
 rasterisation (colour + normal + mask + depth + soft mask in ONE pass), teacher rasterisation
-(normal map), the deterministic backward to dL/dR, dL/dt, one D2H copy.
+(normal map), the deterministic backward to dL/dR, dL/dt, one D2H copy.  Inside the call the student chain
+runs on a side stream next to the teacher rasterisation; the caller's stream waits for both before the call
+returns, so for the caller everything is ordered in its own stream.
 
 Outputs are persistent device tensors (overwritten by the next step); the pose gradients arrive in
 pinned host memory after ``session.synchronize()``.
