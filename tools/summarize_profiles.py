@@ -53,7 +53,14 @@ if os.path.exists(rep):
             def mb(x, u): 
                 v = float(x.replace(",", "")); return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[u]
             t = mb(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + mb(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
-            json.dump({"dibr_forward_kernel_bytes_per_launch": t, "source": f"profiles/{tag}_ncu_full_metrics.csv (ncu --set full, student pass)"},
+            def num(m):
+                return float(r[idx[m]].replace(",", "")) if m in idx and r[idx[m]] not in ("", "n/a") else None
+            json.dump({"dibr_forward_kernel_bytes_per_launch": t,
+                       "warp_instructions_per_launch": num("smsp__inst_executed.sum"),
+                       "issue_slots_busy_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                       "warp_slots_occupied_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                       "active_lanes_per_instruction": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                       "source": f"profiles/{tag}_ncu_full_metrics.csv (ncu --set full, student pass)"},
                       open(os.path.join(out_dir, "traffic.json"), "w"))
             break
 print(open(os.path.join(out_dir, f"{tag}_launches_step.csv")).read())
