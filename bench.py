@@ -239,10 +239,11 @@ def main_b200(args):
 
     def allreduce_check(gR, gt):
         """cfg5: 12-float pose-gradient check-sum, one NCCL all-reduce over NVLink per step, issued asynchronously
-        (NCCL's own stream) so it overlaps the next step's kernels; the previous one is waited for first."""
+        (NCCL's own stream) so it overlaps the following steps' kernels; up to four are in flight, the oldest is waited
+        for first (stream-side wait), and all of them are drained inside the timed region."""
         if world > 1:
-            if pending:
-                pending.pop().wait()
+            if len(pending) >= 4:
+                pending.pop(0).wait()
             vec = gR.sum(0) if gt is None else du.pose_grad_checksum(gR, gt)
             pending.append(dist.all_reduce(vec, async_op=True))
             return vec

@@ -146,6 +146,7 @@ class RenderSession(object):
         self.st = st
         self._ar = np.arange(B)
         self._keep = None
+        self._last_slots, self._last_total = None, 0
 
     # ------------------------------------------------------------------------------------------
     def _fill(self, name, arr):
@@ -160,8 +161,6 @@ class RenderSession(object):
         B = self.B
         assert len(models) == B
         slots = np.fromiter((self.model_slot[id(m)] for m in models), dtype=np.int64, count=B)
-        tab = self.reg.table[slots]
-        nf, nv = tab[:, 3], tab[:, 1]
         self._fill("sR", Rs)
         self._fill("st", ts)
         K = np.asarray(Ks, dtype=np.float32)
@@ -169,21 +168,28 @@ class RenderSession(object):
         if self.teacher is not None:
             self._fill("tR", teacher_Rs)
             self._fill("tt", teacher_ts)
-        o, n = self.off["desc"]
-        desc = self._h_i32[o:o + n].reshape(B, fused.INST_STRIDE)
-        cf = np.cumsum(nf)
-        desc[:, 0], desc[:, 1], desc[:, 2], desc[:, 3], desc[:, 4] = tab[:, 0], nv, tab[:, 2], nf, cf - nf
-        desc[:, 5] = self._ar
-        desc[:, 6] = self._ar
-        desc[:, 7] = tab[:, 0]
-        desc[:, 8] = np.cumsum(nv) - nv
-        desc[:, 9] = self._ar
-        desc[:, 10] = tab[:, 0]
-        desc[:, 11] = 0
-        o, n = self.off["foff"]
-        self._h_i32[o] = 0
-        self._h_i32[o + 1:o + n] = cf
-        total = int(cf[-1])
+        if self._last_slots is None or not np.array_equal(slots, self._last_slots):
+            # the instance table depends on WHICH models sit in the batch only: rebuilt when the composition changes
+            tab = self.reg.table[slots]
+            nf, nv = tab[:, 3], tab[:, 1]
+            o, n = self.off["desc"]
+            desc = self._h_i32[o:o + n].reshape(B, fused.INST_STRIDE)
+            cf = np.cumsum(nf)
+            desc[:, 0], desc[:, 1], desc[:, 2], desc[:, 3], desc[:, 4] = tab[:, 0], nv, tab[:, 2], nf, cf - nf
+            desc[:, 5] = self._ar
+            desc[:, 6] = self._ar
+            desc[:, 7] = tab[:, 0]
+            desc[:, 8] = np.cumsum(nv) - nv
+            desc[:, 9] = self._ar
+            desc[:, 10] = tab[:, 0]
+            desc[:, 11] = 0
+            o, n = self.off["foff"]
+            self._h_i32[o] = 0
+            self._h_i32[o + 1:o + n] = cf
+            self._last_total = int(cf[-1])
+            self._last_slots = slots
+            upload = True                 # a new instance table must reach the device even if the caller says the inputs are resident
+        total = self._last_total
         st = self.st
         st.student.total_faces = total
         st.teacher.total_faces = total
