@@ -14,7 +14,10 @@ constexpr int TILE = 16;            // forward CTA tile (pixels per side): one p
 #define DIBR_FWD_THREADS 256
 #endif
 constexpr int FWD_THREADS = DIBR_FWD_THREADS;   // threads per tile CTA (8 warps, one 8x4 pixel block each in the soft phase)
-constexpr int LCAP = 512;           // faces per in-shared-memory batch of a tile
+#ifndef DIBR_LCAP
+#define DIBR_LCAP 512
+#endif
+constexpr int LCAP = DIBR_LCAP;     // faces per in-shared-memory batch of a tile (multiple of 16, <= 512)
 constexpr int BIGCAP = 32;          // deferred large faces per batch
 #ifndef DIBR_BIG_AREA
 #define DIBR_BIG_AREA 64

@@ -46,17 +46,17 @@ constexpr int NBX = TILE / BW;
 constexpr int RASTER_LANES = DIBR_RASTER_LANES;      // lanes per face in phase B
 static_assert(NBX * (TILE / BH) == NWARP, "one 8x4 block per warp");
 static_assert(LCAP >= 32, "one bitmap word must fit an empty list");
-static_assert(LCAP <= 512 && TILE == 16, "rlist packing: 9-bit list index, 4-bit pixel coordinates");
+static_assert(LCAP <= 512 && LCAP % 16 == 0 && TILE == 16, "rlist packing: 9-bit list index, 4-bit pixel coordinates");
 
 struct FwdSmem {
     float4 c0[LCAP];                            //  8 KB  ax ay bx by   (x multiplier)
     float2 c1[LCAP];                            //  4 KB  cx cy
-    float z[3][LCAP];                           //  6 KB  view-space depth of the corners
     int lid[LCAP];                              //  2 KB  local face ids, ascending
     union {                                     // 30 KB
         struct {
             unsigned long long zkey[TILE * TILE];   //    z-buffer (phases B, C)
             unsigned int rlist[LCAP];           //        raster candidates (phase B)
+            float z[3][LCAP];                   //        view-space depth of the corners (coverage only)
             unsigned int wf[TILE * TILE];       //        winner's face id, committed per batch when a tile needs several
             int big[BIGCAP];
         } ab;
@@ -65,6 +65,7 @@ struct FwdSmem {
     unsigned short E[FWD_THREADS + 2];          // phase D: exclusive scan of the pixels' hit counts
     unsigned char cnt[TILE * TILE];             // accepted faces per pixel (255 = covered)
     unsigned char soft_used[LCAP];              // listed faces that entered some pixel's soft product
+    unsigned int smask[LCAP];                   //  2 KB  phase D: tile columns (bits 0-15) / rows (16-31) inside the face's expanded bbox
     float xs[TILE], ys[TILE];
     int warp_tot[2][NWARP];
     int nbig, lcount, rcount, pad0;
@@ -179,7 +180,7 @@ __device__ int fill_list(FwdSmem& s, const FwdParams& P, int f_lo, int wpos, con
             const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
             s.c0[i] = r0;
             s.c1[i] = make_float2(r1.x, r1.y);
-            s.z[0][i] = r1.z; s.z[1][i] = r1.w; s.z[2][i] = r2.x;
+            if (raster) { s.u.ab.z[0][i] = r1.z; s.u.ab.z[1][i] = r1.w; s.u.ab.z[2][i] = r2.x; }
             if (raster && r2.y >= 0.0f) {                       // front face (K1 culls normalz < 0)
                 const int c0 = col_first_ge(s.xs, T.tw, r3.x, T.inv_dx), c1 = col_first_ge(s.xs, T.tw, r3.z, T.inv_dx);
                 const int q0 = row_first_lt(s.ys, T.th, r3.w, T.inv_dy), q1 = row_first_lt(s.ys, T.th, r3.y, T.inv_dy);
@@ -219,7 +220,7 @@ __device__ __forceinline__ FaceK facek_from_list(const FwdSmem& s, int li) {
     const float2 b = s.c1[li];
     FaceRec r;
     r.ax = a.x; r.ay = a.y; r.bx = a.z; r.by = a.w; r.cx = b.x; r.cy = b.y;
-    r.az = s.z[0][li]; r.bz = s.z[1][li]; r.cz = s.z[2][li];
+    r.az = s.u.ab.z[0][li]; r.bz = s.u.ab.z[1][li]; r.cz = s.u.ab.z[2][li];
     return make_facek(r);
 }
 
@@ -566,8 +567,8 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         const int lcount = s.lcount;
         for (int i = tid; i < LCAP / 4; i += FWD_THREADS) reinterpret_cast<unsigned int*>(s.soft_used)[i] = 0u;
         // per listed face: the tile's columns (bits 0-15) and rows (bits 16-31) whose pixel centres lie inside its
-        // expanded bbox; kept where the corner depths were (dead once the z-buffer is final)
-        unsigned int* const smask = reinterpret_cast<unsigned int*>(&s.z[0][0]);
+        // expanded bbox
+        unsigned int* const smask = s.smask;
         for (int li = tid; li < lcount; li += FWD_THREADS) {
             const float4 a = s.c0[li];
             const float2 d = s.c1[li];
