@@ -1,5 +1,6 @@
-// Forward pass of the B200 DIB-R rasterizer: one CTA (256 threads, one per pixel) per 16x16 screen tile, ~54 KB of
-// shared memory and <= 64 registers so four CTAs share an SM.  Everything after the list build runs out of shared
+// Forward pass of the B200 DIB-R rasterizer: one CTA (256 threads, one per pixel) per 16x16 screen tile, 47.5 KB of
+// shared memory and <= 64 registers so four CTAs share an SM (194 KB of the SM's 256 KB: the 196 KB carve-out, 60 KB
+// of L1 left -- at 53 KB per CTA the next carve-out step took half of that L1 away and cost 5 %).  Everything after the list build runs out of shared
 // memory; the only trips to L2 are the bbox scan, ONE gather of the listed faces' records, the winners' attributes
 // and the work-list flags.
 //
