@@ -1,14 +1,15 @@
 // Forward pass of the B200 DIB-R rasterizer: one CTA (256 threads, one per pixel) per 16x16 screen tile, 47.5 KB of
-// shared memory and <= 64 registers so four CTAs share an SM (194 KB of the SM's 256 KB: the 196 KB carve-out, 60 KB
-// of L1 left -- at 53 KB per CTA the next carve-out step took half of that L1 away and cost 5 %).  Everything after the list build runs out of shared
-// memory; the only trips to L2 are the bbox scan, ONE gather of the listed faces' records, the winners' attributes
-// and the work-list flags.
+// shared memory and <= 64 registers so four CTAs share an SM (194 KB of the SM's 256 KB: the 196 KB carve-out leaves
+// 60 KB of L1 -- at 53 KB per CTA the next carve-out step took half of that L1 away and cost 5 %).  CTA i takes the
+// i-th tile of the plan the set-up call left (plan_tiles_kernel: tiles bucketed by list length, heaviest first); tiles
+// whose bitmap is empty are filled by one warp each.  Everything after the list build runs out of shared memory; the
+// only trips to L2 are the tile's bitmap, ONE gather of the listed faces' records, the winners' attributes and the
+// work-list flags.
 //
-//   phase A  scan the image's faces: 8 B conservative pixel boxes (4 x int16, written by the set-up kernel), each
-//            warp owns a contiguous span and issues all of its 128-bit loads before testing any (two faces per
-//            load); the hits are compacted in ascending face order with warp ballots and one CTA barrier per
-//            round of 4096 faces.  Then the records of the listed faces are gathered into shared memory (corners,
-//            depths) and the front faces that really hold a pixel centre of the tile go on the raster list.
+//   phase A  read the tile's face bitmap (one bit per face of the image, set by the set-up kernel's binning), scan the
+//            popcounts across the CTA and expand the set bits into the ascending list of face ids -- no per-tile scan
+//            over all faces and no sort.  Then the records of the listed faces are gathered into shared memory
+//            (corners, depths) and the front faces that really hold a pixel centre of the tile go on the raster list.
 //   phase B  face-parallel coverage with 8 lanes per face: barycentric solve in the frozen fp32 order and a 64-bit
 //            shared-memory atomicMax on (orderable z | ~rank in the list).  The winner is the face with the largest z
 //            and, on ties, the smallest index -- what the reference's ascending loop with a strict '>' produces,
