@@ -313,3 +313,42 @@ def test_render_session_matches_renderer_dibr():
     ret2 = ren.render_batch(torch.tensor(batch["Rs"], device=DEV), torch.tensor(batch["ts"], device=DEV), [models[i] for i in ids2],
                             Ks=Ks, width=W, height=H, mode=["color", "prob", "mask"])
     assert torch.equal(out2["color"], ret2["color"]) and torch.equal(out2["prob"], ret2["prob"])
+
+
+def test_render_session_composition_change_and_lean_teacher():
+    """(1) a step that says its inputs are resident (upload=False) after the batch composition changed must still get the
+    new instance table to the device; (2) RenderSession(teacher_soft_mask=False) returns the same teacher normal map and
+    the same student outputs / pose gradients (it only skips work whose result nobody reads)."""
+    from self6dpp_b200 import synth
+    from self6dpp_b200.session import RenderSession
+    from tests.golden.make_golden import small_meshes
+    meshes = small_meshes()
+    H = W = 64
+    models = to_dev_models(meshes)
+    for m in models:
+        m["faces"] = m["faces"].to(torch.int32)
+    ids_a, ids_b = [2, 0, 1, 1], [0, 0, 2, 1]
+    B = 4
+    batch = synth.roi_batch([meshes[i] for i in ids_b], B, res=W, seed=41, fill=(0.45, 0.7))
+    tea = synth.roi_batch([meshes[i] for i in ids_b], B, res=W, seed=42, fill=(0.45, 0.7))
+    g = torch.Generator().manual_seed(5)
+    gc, gp, gd = torch.randn(B, H, W, 3, generator=g).to(DEV), torch.randn(B, H, W, generator=g).to(DEV), torch.randn(B, H, W, generator=g).to(DEV)
+
+    def run(sess, ids, **kw):
+        out = sess.step(batch["Rs"], batch["ts"], batch["Ks"], [models[i] for i in ids], tea["Rs"], tea["ts"],
+                        grad_color=gc, grad_prob=gp, grad_depth=gd, **kw)
+        sess.synchronize()
+        return {k: v.clone() for k, v in out.items()}, sess.g_pose_dev.clone()
+    ref_sess = RenderSession(models, B, H, W)
+    ref_out, ref_grad = run(ref_sess, ids_b)                               # composition B, everything uploaded
+    sess = RenderSession(models, B, H, W)
+    run(sess, ids_a)                                                       # composition A first
+    out, grad = run(sess, ids_b, upload=False, download=False)             # "resident" step with a NEW composition
+    for k in ref_out:
+        assert torch.equal(out[k], ref_out[k]), k
+    assert torch.equal(grad, ref_grad)
+    lean = RenderSession(models, B, H, W, teacher_soft_mask=False)
+    out_l, grad_l = run(lean, ids_b)
+    for k in ref_out:
+        assert torch.equal(out_l[k], ref_out[k]), k
+    assert torch.equal(grad_l, ref_grad)
