@@ -244,7 +244,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream));
 }
 
-int dibr_backward_meshes(const DibrPass* p, void* stream) {
+static int backward_meshes_impl(const DibrPass* p, void* stream, float* packed) {
     if (int e = check_common(p, true)) return e;
     if (p->num_instances <= 0 || !p->inst_desc || !p->verts) return fail("backward_meshes: instances and verts required");
     if (!p->pose_R && (!p->cam_rot || !p->cam_pos || !p->cam_proj)) return fail("backward_meshes: cameras required");
@@ -264,9 +264,12 @@ int dibr_backward_meshes(const DibrPass* p, void* stream) {
     m.vert_face_ptr = p->vert_face_ptr; m.vert_face_idx = p->vert_face_idx;
     m.grad_verts = p->grad_verts; m.grad_vert_attr = p->grad_vert_attr;
     m.grad_cam_rot = p->grad_cam_rot; m.grad_cam_pos = p->grad_cam_pos; m.pose_part = w.pose_part; m.pose_done = w.pose_done;
+    m.grad_pose_packed = p->pose_R ? packed : nullptr;
     g_launches += 1;
     return cuda_fail("dibr_backward_meshes", dibr::launch_backward_meshes(m, (cudaStream_t)stream));
 }
+
+int dibr_backward_meshes(const DibrPass* p, void* stream) { return backward_meshes_impl(p, stream, nullptr); }
 
 int dibr_normal_map(const float* normals, const float* mask, const uint32_t* min_ordered, float* out, long long npix, void* stream) {
     if (!normals || !mask || !min_ordered || !out || npix < 0) return fail("normal_map: null argument");
@@ -408,15 +411,6 @@ int dibr_chamfer_reduce_backward(const DibrChamferReduce* p, void* stream) {
     return cuda_fail("dibr_chamfer_reduce_backward", dibr::launch_chamfer_reduce_backward(q, (cudaStream_t)stream));
 }
 
-// gather [n,9] + [n,3] into [n,12] so ONE D2H copy returns the pose gradients
-__global__ void pack_pose_grad_kernel(const float* __restrict__ gR, const float* __restrict__ gt, float* __restrict__ out, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * 12) return;
-    const int inst = i / 12, k = i % 12;
-    out[i] = (k < 9) ? gR[inst * 9 + k] : gt[inst * 3 + (k - 9)];
-}
-
 // one side stream + fork/join events per device, created on first use and kept for the life of the process
 struct AuxStream { cudaStream_t stream; cudaEvent_t fork, join; };
 static AuxStream* aux_stream() {
@@ -480,14 +474,13 @@ int dibr_render_step(const DibrStep* st, void* stream) {
         void* ls = aux ? (void*)aux->stream : stream;           // the student chain's stream
         cudaStream_t lcs = (cudaStream_t)ls;
         if (int e = dibr_backward_faces(p, ls)) return e;
-        if (int e = dibr_backward_meshes(p, ls)) return e;
+        if (st->device_grad_pose && (!p->grad_pose_R || !p->grad_pose_t)) return fail("render_step: pose-gradient buffers are null");
+        // the kernel's finalising block writes the [n,12] layout itself: no packing launch
+        if (int e = backward_meshes_impl(p, ls, st->device_grad_pose)) return e;
         if (st->device_grad_pose) {
-            if (!p->grad_pose_R || !p->grad_pose_t) return fail("render_step: pose-gradient buffers are null");
             const int n = p->num_instances;
-            pack_pose_grad_kernel<<<(n * 12 + 127) / 128, 128, 0, lcs>>>(p->grad_pose_R, p->grad_pose_t, st->device_grad_pose, n);
-            g_launches += 1;
-            cudaError_t e = cudaGetLastError();
-            if (e == cudaSuccess && st->host_grad_pose)
+            cudaError_t e = cudaSuccess;
+            if (st->host_grad_pose)
                 e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)n, cudaMemcpyDeviceToHost, lcs);
             if (e != cudaSuccess) return cuda_fail("render_step pose gradients", (int)e);
         }

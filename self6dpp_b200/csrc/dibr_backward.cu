@@ -451,13 +451,16 @@ __global__ void __launch_bounds__(256) mesh_vertex_grad_kernel(MeshBwdParams P)
         if (threadIdx.x < 9) {
             const int j = threadIdx.x / 3, k = threadIdx.x - 3 * j;
             const float sgn = (j == 0) ? 1.f : -1.f;
-            P.grad_pose_R[(size_t)inst * 9 + threadIdx.x] = sgn * tot[j * 3 + k] - Tp[j] * tot[9 + k];
+            const float v = sgn * tot[j * 3 + k] - Tp[j] * tot[9 + k];
+            P.grad_pose_R[(size_t)inst * 9 + threadIdx.x] = v;
+            if (P.grad_pose_packed) P.grad_pose_packed[(size_t)inst * 12 + threadIdx.x] = v;
         } else {
             const int j = threadIdx.x - 9;
             float gt = 0.f;
 #pragma unroll
             for (int k = 0; k < 3; k++) gt -= Rp[j * 3 + k] * tot[9 + k];
             P.grad_pose_t[(size_t)inst * 3 + j] = gt;
+            if (P.grad_pose_packed) P.grad_pose_packed[(size_t)inst * 12 + 9 + j] = gt;
         }
     }
 }

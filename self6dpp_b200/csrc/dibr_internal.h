@@ -139,6 +139,7 @@ struct MeshBwdParams {
     const float* pose_t;
     float* grad_pose_R;
     float* grad_pose_t;
+    float* grad_pose_packed;   // optional [num_instances, 12]: dL/dR then dL/dt, the layout dibr_render_step copies back to the host
 };
 
 // Tile bins.  Image b owns the global 32-face words [f_lo >> 5, (f_hi - 1) >> 5]; its bitmaps start at word
