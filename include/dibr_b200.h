@@ -286,6 +286,27 @@ typedef struct DibrChamferReduce {
 int dibr_chamfer_reduce_forward(const DibrChamferReduce *p, void *stream);
 int dibr_chamfer_reduce_backward(const DibrChamferReduce *p, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * L1 loss in normalised CIE-Lab between the real crop and the rendered crop: core/self6dpp/engine/self_engine_utils.py:
+ * 745-773 over lib/torch_utils/color/lab.py:16-82 (rgb_to_lab + normalize_lab) and color/xyz.py:28-30:
+ *     loss = sum |lab(gt) * m - lab(ren) * m| / max(1, sum m)      (a and b channels only when no_l, the LAB_NO_L switch)
+ * gt / ren are planar [n_img, 3, H*W]; bgr != 0 when the planes are B,G,R (the reference's [:, [2,1,0]] flip is then done
+ * in the load).  mask is [n_img, H*W] or NULL (ones).  scratch: dibr_lab_loss_scratch_floats(n_img * hw) floats followed
+ * by one uint32 that must be ZERO before the first call (re-armed by the kernel).  out[0] = loss, out[1] = sum |diff|,
+ * out[2] = max(1, sum m).  The backward reads out[2] and grad_out[0] and writes d L / d ren (same layout as ren); like the
+ * reference's autograd it yields NaN at exactly-black rendered pixels (pow(0, 1/3) backward). */
+typedef struct DibrLabLoss {
+    int32_t n_img, hw, bgr, no_l;
+    const float *gt, *ren, *mask;
+    float *scratch;
+    float *out;                              /* [3] */
+    const float *grad_out;                   /* backward in:  [1] */
+    float *grad_ren;                         /* backward out: [n_img, 3, hw] */
+} DibrLabLoss;
+int dibr_lab_loss_scratch_floats(int64_t pixels);
+int dibr_lab_loss_forward(const DibrLabLoss *p, void *stream);
+int dibr_lab_loss_backward(const DibrLabLoss *p, void *stream);
+
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);
 

@@ -89,6 +89,16 @@ class DibrMaskLoss(ctypes.Structure):
     ]
 
 
+class DibrLabLoss(ctypes.Structure):
+    """Mirror of ``struct DibrLabLoss`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("n_img", ctypes.c_int32), ("hw", ctypes.c_int32), ("bgr", ctypes.c_int32), ("no_l", ctypes.c_int32),
+        ("gt", _c_f32p), ("ren", _c_f32p), ("mask", _c_f32p),
+        ("scratch", _c_f32p), ("out", _c_f32p), ("grad_out", _c_f32p), ("grad_ren", _c_f32p),
+    ]
+
+
 class DibrChamferReduce(ctypes.Structure):
     """Mirror of ``struct DibrChamferReduce`` (include/dibr_b200.h)."""
 
@@ -104,7 +114,8 @@ EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_devi
            "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
            "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_backproject_compact",
            "dibr_backproject_compact_backward", "dibr_mask_loss_scratch_floats", "dibr_mask_loss_forward",
-           "dibr_mask_loss_backward", "dibr_chamfer_reduce_forward", "dibr_chamfer_reduce_backward", "dibr_launch_count"]
+           "dibr_mask_loss_backward", "dibr_chamfer_reduce_forward", "dibr_chamfer_reduce_backward",
+           "dibr_lab_loss_scratch_floats", "dibr_lab_loss_forward", "dibr_lab_loss_backward", "dibr_launch_count"]
 
 _lib = None
 
@@ -158,6 +169,12 @@ def load():
     for name in ("dibr_mask_loss_forward", "dibr_mask_loss_backward"):
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrMaskLoss), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    lib.dibr_lab_loss_scratch_floats.argtypes = [ctypes.c_int64]
+    lib.dibr_lab_loss_scratch_floats.restype = ctypes.c_int
+    for name in ("dibr_lab_loss_forward", "dibr_lab_loss_backward"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrLabLoss), ctypes.c_void_p]
         fn.restype = ctypes.c_int
     lib.dibr_nnd_workspace_bytes.argtypes = [ctypes.POINTER(DibrNnd), ctypes.POINTER(ctypes.c_size_t)]
     lib.dibr_nnd_workspace_bytes.restype = ctypes.c_int

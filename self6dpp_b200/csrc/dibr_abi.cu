@@ -385,6 +385,35 @@ int dibr_mask_loss_backward(const DibrMaskLoss* p, void* stream) {
     return cuda_fail("dibr_mask_loss_backward", dibr::launch_mask_loss_backward(q, (cudaStream_t)stream));
 }
 
+int dibr_lab_loss_scratch_floats(int64_t pixels) { return dibr::lab_loss_partial_floats(pixels) + 1; }
+
+static int lab_params(const DibrLabLoss* p, dibr::LabLossParams& q, bool backward) {
+    if (!p) return fail("null DibrLabLoss");
+    if (p->n_img < 0 || p->hw < 0) return fail("lab_loss: negative size");
+    if (!p->gt || !p->ren || !p->out) return fail("lab_loss: gt / ren / out required");
+    if (!backward && !p->scratch) return fail("lab_loss: scratch required");
+    if (backward && (!p->grad_out || !p->grad_ren)) return fail("lab_loss backward: grad_out / grad_ren required");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    const long long pixels = (long long)p->n_img * p->hw;
+    q.n_img = p->n_img; q.hw = p->hw; q.bgr = p->bgr; q.no_l = p->no_l;
+    q.gt = p->gt; q.ren = p->ren; q.mask = p->mask;
+    q.partial = p->scratch; q.ticket = p->scratch ? (unsigned int*)(p->scratch + dibr::lab_loss_partial_floats(pixels)) : nullptr;
+    q.out = p->out; q.grad_out = p->grad_out; q.grad_ren = p->grad_ren;
+    return 0;
+}
+int dibr_lab_loss_forward(const DibrLabLoss* p, void* stream) {
+    dibr::LabLossParams q;
+    if (int e = lab_params(p, q, false)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_lab_loss_forward", dibr::launch_lab_loss_forward(q, (cudaStream_t)stream));
+}
+int dibr_lab_loss_backward(const DibrLabLoss* p, void* stream) {
+    dibr::LabLossParams q;
+    if (int e = lab_params(p, q, true)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_lab_loss_backward", dibr::launch_lab_loss_backward(q, (cudaStream_t)stream));
+}
+
 static int cr_params(const DibrChamferReduce* p, dibr::ChamferReduceParams& q, bool backward) {
     if (!p) return fail("null DibrChamferReduce");
     if (p->batch < 0 || p->stride1 < 0 || p->stride2 < 0) return fail("chamfer_reduce: negative sizes");

@@ -188,6 +188,24 @@ struct MaskLossParams {
 int mask_loss_partial_floats(long long n);
 int launch_mask_loss_forward(const MaskLossParams& P, cudaStream_t stream);
 int launch_mask_loss_backward(const MaskLossParams& P, cudaStream_t stream);
+// L1 in normalised CIE-Lab between the real and the rendered crop (dibr_photometric.cu)
+struct LabLossParams {
+    int n_img;                 // images
+    int hw;                    // pixels per plane
+    int bgr;                   // planes are B,G,R (the reference flips with [:, [2,1,0]]) instead of R,G,B
+    int no_l;                  // LAB_NO_L: only the a and b channels count
+    const float* gt;           // [n_img, 3, hw]
+    const float* ren;          // [n_img, 3, hw]
+    const float* mask;         // [n_img, hw] or null (all ones)
+    float* partial;            // [2 * CTAs] scratch
+    unsigned int* ticket;      // [1], zero between calls
+    float* out;                // [3]: loss, sum |diff|, max(1, sum mask)
+    const float* grad_out;     // backward: [1]
+    float* grad_ren;           // backward: [n_img, 3, hw]
+};
+int lab_loss_partial_floats(long long pixels);
+int launch_lab_loss_forward(const LabLossParams& P, cudaStream_t stream);
+int launch_lab_loss_backward(const LabLossParams& P, cudaStream_t stream);
 // chamfer distances -> depth loss (dibr_maskloss.cu)
 struct ChamferReduceParams {
     int batch, stride1, stride2;

@@ -6,6 +6,9 @@ soft mask (core/self6dpp/engine/self_engine_utils.py:541-545): same arguments, s
 boolean-indexed temporaries and synchronises with the host four times per call; here it is one reduction launch and one
 elementwise launch for the backward (``dibr_mask_loss_forward`` / ``_backward``), bit-reproducible, no host sync.  The
 reference's NaN diagnostics (prints) are not reproduced.  No CPU fallback.
+
+``lab_l1_loss`` is the Lab-space colour loss of ``compute_self_loss_pose`` (self_engine_utils.py:745-773, over
+lib/torch_utils/color/lab.py:16-82): ~60 elementwise torch launches there, one launch per direction here.
 """
 import ctypes
 
@@ -18,10 +21,11 @@ from .rasterizer import _require_cuda_f32, _stream
 _SCRATCH = {}
 
 
-def _scratch(n, device):
+def _scratch(n, device, kind="mask"):
     """partial sums + the ticket word (zero between calls: the kernel re-arms it), one buffer per (device, size)"""
-    floats = _lib.load().dibr_mask_loss_scratch_floats(n)
-    key = (str(device), floats)
+    lib = _lib.load()
+    floats = lib.dibr_mask_loss_scratch_floats(n) if kind == "mask" else lib.dibr_lab_loss_scratch_floats(n)
+    key = (str(device), floats, kind)
     buf = _SCRATCH.get(key)
     if buf is None:
         if len(_SCRATCH) > 16:
@@ -76,3 +80,64 @@ class _WeightedExLossProbs(Function):
 def weighted_ex_loss_probs(probs, target, weight=None):
     """mask_losses.py:63-108: loss = mean over target>0 of -target*log(p)*w  +  mean over target==0 of -log(1-p)*w"""
     return _WeightedExLossProbs.apply(probs, target, weight)
+
+
+class _LabL1Loss(Function):
+    @staticmethod
+    def forward(ctx, gt_img, ren_img, mask, no_l, bgr):
+        _require_cuda_f32("gt_img", gt_img)
+        _require_cuda_f32("ren_img", ren_img)
+        if gt_img.dim() != 4 or gt_img.shape[1] != 3 or gt_img.shape != ren_img.shape:
+            raise ValueError("gt_img / ren_img must both be (N, 3, H, W), got {} and {}".format(
+                tuple(gt_img.shape), tuple(ren_img.shape)))
+        device = ren_img.device
+        n, _, h, w = ren_img.shape
+        g_c, r_c = gt_img.detach().contiguous(), ren_img.detach().contiguous()
+        m_c = None
+        if mask is not None:
+            _require_cuda_f32("mask", mask)
+            if mask.numel() != n * h * w:
+                raise ValueError("mask must be (N, 1, H, W)")
+            m_c = mask.detach().contiguous()
+        out = torch.empty(3, dtype=torch.float32, device=device)
+        q = _lib.DibrLabLoss()
+        q.n_img, q.hw, q.bgr, q.no_l = n, h * w, int(bool(bgr)), int(bool(no_l))
+        q.gt, q.ren, q.mask = _lib.ptr(g_c), _lib.ptr(r_c), _lib.ptr(m_c)
+        scratch = _scratch(n * h * w, device, kind="lab")
+        q.scratch, q.out = _lib.ptr(scratch), _lib.ptr(out)
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().dibr_lab_loss_forward(ctypes.byref(q), _stream(device)), "dibr_lab_loss_forward")
+        ctx.save_for_backward(g_c, r_c, out, *([m_c] if m_c is not None else []))
+        ctx.has_m = m_c is not None
+        ctx.flags = (int(bool(bgr)), int(bool(no_l)))
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        saved = ctx.saved_tensors
+        g_c, r_c, out = saved[:3]
+        m_c = saved[3] if ctx.has_m else None
+        device = r_c.device
+        n, _, h, w = r_c.shape
+        go = grad_out.detach().reshape(1).to(torch.float32).contiguous()
+        gr = torch.empty_like(r_c)
+        q = _lib.DibrLabLoss()
+        q.n_img, q.hw = n, h * w
+        q.bgr, q.no_l = ctx.flags
+        q.gt, q.ren, q.mask = _lib.ptr(g_c), _lib.ptr(r_c), _lib.ptr(m_c)
+        q.out, q.grad_out, q.grad_ren = _lib.ptr(out), _lib.ptr(go), _lib.ptr(gr)
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().dibr_lab_loss_backward(ctypes.byref(q), _stream(device)), "dibr_lab_loss_backward")
+        return None, gr, None, None, None
+
+
+def lab_l1_loss(gt_img_roi, ren_img_roi, pseudo_vis_mask_roi=None, no_l=False, bgr=True):
+    """self_engine_utils.py:745-773 (without the LAB_LW factor):
+
+        lab_x = normalize_lab(rgb_to_lab(x[:, [2, 1, 0]]))
+        loss  = smooth_l1_loss(lab_gt * m, lab_ren * m, beta=0, reduction="sum") / max(1, m.sum())
+
+    over the a/b channels only when ``no_l`` (LAB_NO_L).  Images are (N, 3, H, W) with B,G,R planes like the
+    reference's crops (``bgr=False`` for R,G,B planes); the mask is (N, 1, H, W) or None (ones).  The gradient flows to
+    ``ren_img_roi`` only -- the real crop and the pseudo mask are data on this path."""
+    return _LabL1Loss.apply(gt_img_roi, ren_img_roi, pseudo_vis_mask_roi, no_l, bgr)
