@@ -307,6 +307,31 @@ int dibr_lab_loss_scratch_floats(int64_t pixels);
 int dibr_lab_loss_forward(const DibrLabLoss *p, void *stream);
 int dibr_lab_loss_backward(const DibrLabLoss *p, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * MS-SSIM: core/self6dpp/losses/ssim.py:58-160 (ssim + ms_ssim with use_padding=False), the MS_SSIM module the
+ * self-supervised loop builds at core/self6dpp/engine/self_engine.py:352 and applies to the real and the rendered crop at
+ * self_engine_utils.py:777-785.  x, y: [n_img, channels, height, width]; window: the 11 taps of ssim.py:13-30
+ * (create_window(11, sigma)); weights: `levels` level weights (ssim.py:222-229); out: [n_img] MS-SSIM values (the
+ * reference's product, last level's term raised to levels-1, normalisation (v+1)/2 when `normalize`).  Every level
+ * must keep at least 11x11 pixels.  The forward fills `workspace` (dibr_ms_ssim_workspace_bytes) with the pyramid and,
+ * when want_grad, the per-level coefficient maps; the backward must be given the same workspace untouched and writes
+ * d L / d y for grad_out = d L / d out ([n_img]).  x is data on this path (no gradient). */
+typedef struct DibrMsSsim {
+    int32_t n_img, channels, height, width, levels, normalize, want_grad, reserved0;
+    float data_range;
+    float window[11];
+    float weights[8];
+    const float *x, *y;
+    void *workspace;
+    size_t workspace_bytes;
+    float *out;                              /* [n_img] */
+    const float *grad_out;                   /* backward in:  [n_img] */
+    float *grad_y;                           /* backward out: [n_img, channels, height, width] */
+} DibrMsSsim;
+int dibr_ms_ssim_workspace_bytes(const DibrMsSsim *p, size_t *bytes);
+int dibr_ms_ssim_forward(const DibrMsSsim *p, void *stream);
+int dibr_ms_ssim_backward(const DibrMsSsim *p, void *stream);
+
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);
 

@@ -63,3 +63,122 @@ def lab_l1_loss(gt, ren, mask=None, no_l=False, bgr=True):
     if bgr:
         g_rgb = g_rgb[:, ::-1]
     return loss, np.ascontiguousarray(g_rgb)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# MS-SSIM: core/self6dpp/losses/ssim.py:13-160 (create_window, _gaussian_filter, ssim, ms_ssim; use_padding=False)
+# ------------------------------------------------------------------------------------------------------------------
+def create_window(window_size=11, sigma=1.5):
+    """ssim.py:13-30 (float32 arithmetic like torch's, then promoted)"""
+    coords = np.arange(window_size, dtype=np.float32) - np.float32(window_size // 2)
+    g = np.exp(-(coords ** 2) / np.float32(2 * sigma ** 2)).astype(np.float32)
+    g = g / g.sum(dtype=np.float32)
+    return g.astype(np.float64)
+
+
+def _filt(img, win):
+    """valid separable correlation over the last two axes (ssim.py:33-55)"""
+    k = len(win)
+    H, W = img.shape[-2:]
+    out = np.zeros(img.shape[:-1] + (W - k + 1,))
+    for i in range(k):
+        out += win[i] * img[..., :, i:i + W - k + 1]
+    out2 = np.zeros(img.shape[:-2] + (H - k + 1, W - k + 1))
+    for i in range(k):
+        out2 += win[i] * out[..., i:i + H - k + 1, :]
+    return out2
+
+
+def _filt_T(m, win):
+    """adjoint of _filt: (.., H-k+1, W-k+1) -> (.., H, W)"""
+    k = len(win)
+    Ho, Wo = m.shape[-2:]
+    mid = np.zeros(m.shape[:-2] + (Ho + k - 1, Wo))
+    for i in range(k):
+        mid[..., i:i + Ho, :] += win[i] * m
+    out = np.zeros(m.shape[:-2] + (Ho + k - 1, Wo + k - 1))
+    for i in range(k):
+        out[..., :, i:i + Wo] += win[i] * mid
+    return out
+
+
+def _pool(img):
+    """F.avg_pool2d(kernel 2, stride 2, padding (H % 2, W % 2)), zeros counted (ssim.py:143-145)"""
+    H, W = img.shape[-2:]
+    ph, pw = H % 2, W % 2
+    p = np.pad(img, [(0, 0)] * (img.ndim - 2) + [(ph, ph), (pw, pw)])
+    Ho, Wo = (H + 2 * ph - 2) // 2 + 1, (W + 2 * pw - 2) // 2 + 1
+    p = p[..., :2 * Ho, :2 * Wo]
+    return 0.25 * (p[..., 0::2, 0::2] + p[..., 0::2, 1::2] + p[..., 1::2, 0::2] + p[..., 1::2, 1::2])
+
+
+def _pool_T(g, H, W):
+    ph, pw = H % 2, W % 2
+    Ho, Wo = g.shape[-2:]
+    up = np.zeros(g.shape[:-2] + (2 * Ho, 2 * Wo))
+    for a in (0, 1):
+        for b in (0, 1):
+            up[..., a::2, b::2] = 0.25 * g
+    full = np.zeros(g.shape[:-2] + (H + 2 * ph, W + 2 * pw))
+    hh, ww = min(full.shape[-2], 2 * Ho), min(full.shape[-1], 2 * Wo)
+    full[..., :hh, :ww] = up[..., :hh, :ww]
+    return full[..., ph:ph + H, pw:pw + W]
+
+
+def ms_ssim(X, Y, data_range=1.0, weights=(0.0448, 0.2856, 0.3001, 0.2363, 0.1333), normalize=False, window=None,
+            grad_out=None):
+    """returns (ms [N], d sum(grad_out * ms) / d Y or None)"""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    win = create_window() if window is None else np.asarray(window, dtype=np.float64)
+    w = np.asarray(np.asarray(weights, dtype=np.float32), dtype=np.float64)
+    L = len(w)
+    C1, C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    xs, ys, keep = [X], [Y], []
+    cs_vals, ssim_vals = [], []
+    for l in range(L):
+        x, y = xs[-1], ys[-1]
+        mu1, mu2 = _filt(x, win), _filt(y, win)
+        e11, e22, e12 = _filt(x * x, win), _filt(y * y, win), _filt(x * y, win)
+        s11, s22, s12 = e11 - mu1 ** 2, e22 - mu2 ** 2, e12 - mu1 * mu2
+        dcs, dl = s11 + s22 + C2, mu1 ** 2 + mu2 ** 2 + C1
+        cs = (2 * s12 + C2) / dcs
+        lum = (2 * mu1 * mu2 + C1) / dl
+        ssim_vals.append((lum * cs).mean(axis=(1, 2, 3)))
+        cs_vals.append(cs.mean(axis=(1, 2, 3)))
+        keep.append((mu1, mu2, cs, lum, dcs, dl))
+        xs.append(_pool(x))
+        ys.append(_pool(y))
+    half = 1.0
+    if normalize:                                                                                 # ssim.py:150-152
+        ssim_vals = [(v + 1) / 2 for v in ssim_vals]
+        cs_vals = [(v + 1) / 2 for v in cs_vals]
+        half = 0.5
+    last = ssim_vals[-1] ** w[-1]
+    ms = np.ones_like(last)
+    for l in range(L - 1):                                                                        # ssim.py:153-156
+        ms = ms * (cs_vals[l] ** w[l]) * last
+    if grad_out is None:
+        return ms, None
+    go = np.asarray(grad_out, dtype=np.float64)
+    g_next = None
+    for l in range(L - 1, -1, -1):
+        x, y = xs[l], ys[l]
+        mu1, mu2, cs, lum, dcs, dl = keep[l]
+        npx = cs[0].size
+        g_mu = (2 * mu2 * cs - 2 * mu1) / dcs
+        g_22 = -cs / dcs
+        g_12 = 2.0 / dcs
+        if l == L - 1:
+            g_mu = lum * g_mu + cs * (2 * (mu1 - lum * mu2) / dl)
+            g_22 = lum * g_22
+            g_12 = lum * g_12
+            s = ms * (L - 1) * w[l] / ssim_vals[l] * half / npx
+        else:
+            s = ms * w[l] / cs_vals[l] * half / npx
+        s = (s * go).reshape(-1, 1, 1, 1)
+        g = s * (_filt_T(g_mu, win) + 2 * y * _filt_T(g_22, win) + x * _filt_T(g_12, win))
+        if g_next is not None:
+            g = g + _pool_T(g_next, x.shape[-2], x.shape[-1])
+        g_next = g
+    return ms, g_next

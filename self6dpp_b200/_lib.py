@@ -99,6 +99,18 @@ class DibrLabLoss(ctypes.Structure):
     ]
 
 
+class DibrMsSsim(ctypes.Structure):
+    """Mirror of ``struct DibrMsSsim`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("n_img", ctypes.c_int32), ("channels", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+        ("levels", ctypes.c_int32), ("normalize", ctypes.c_int32), ("want_grad", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("data_range", ctypes.c_float), ("window", ctypes.c_float * 11), ("weights", ctypes.c_float * 8),
+        ("x", _c_f32p), ("y", _c_f32p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("out", _c_f32p), ("grad_out", _c_f32p), ("grad_y", _c_f32p),
+    ]
+
+
 class DibrChamferReduce(ctypes.Structure):
     """Mirror of ``struct DibrChamferReduce`` (include/dibr_b200.h)."""
 
@@ -115,7 +127,8 @@ EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_devi
            "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_backproject_compact",
            "dibr_backproject_compact_backward", "dibr_mask_loss_scratch_floats", "dibr_mask_loss_forward",
            "dibr_mask_loss_backward", "dibr_chamfer_reduce_forward", "dibr_chamfer_reduce_backward",
-           "dibr_lab_loss_scratch_floats", "dibr_lab_loss_forward", "dibr_lab_loss_backward", "dibr_launch_count"]
+           "dibr_lab_loss_scratch_floats", "dibr_lab_loss_forward", "dibr_lab_loss_backward",
+           "dibr_ms_ssim_workspace_bytes", "dibr_ms_ssim_forward", "dibr_ms_ssim_backward", "dibr_launch_count"]
 
 _lib = None
 
@@ -175,6 +188,12 @@ def load():
     for name in ("dibr_lab_loss_forward", "dibr_lab_loss_backward"):
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrLabLoss), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    lib.dibr_ms_ssim_workspace_bytes.argtypes = [ctypes.POINTER(DibrMsSsim), ctypes.POINTER(ctypes.c_size_t)]
+    lib.dibr_ms_ssim_workspace_bytes.restype = ctypes.c_int
+    for name in ("dibr_ms_ssim_forward", "dibr_ms_ssim_backward"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrMsSsim), ctypes.c_void_p]
         fn.restype = ctypes.c_int
     lib.dibr_nnd_workspace_bytes.argtypes = [ctypes.POINTER(DibrNnd), ctypes.POINTER(ctypes.c_size_t)]
     lib.dibr_nnd_workspace_bytes.restype = ctypes.c_int

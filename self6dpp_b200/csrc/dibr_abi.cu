@@ -414,6 +414,112 @@ int dibr_lab_loss_backward(const DibrLabLoss* p, void* stream) {
     return cuda_fail("dibr_lab_loss_backward", dibr::launch_lab_loss_backward(q, (cudaStream_t)stream));
 }
 
+namespace {
+struct SsimPlan {
+    int levels, planes;
+    int H[dibr::SSIM_MAX_LEVELS], W[dibr::SSIM_MAX_LEVELS], tiles[dibr::SSIM_MAX_LEVELS];
+    size_t px[dibr::SSIM_MAX_LEVELS], py[dibr::SSIM_MAX_LEVELS], gp[dibr::SSIM_MAX_LEVELS];      // float offsets (level 0 unused)
+    size_t maps[dibr::SSIM_MAX_LEVELS], partial[dibr::SSIM_MAX_LEVELS], scale;
+    size_t total_floats;
+};
+}  // namespace
+
+static int ssim_plan(const DibrMsSsim* p, SsimPlan& s) {
+    if (!p) return fail("null DibrMsSsim");
+    if (p->n_img < 0 || p->channels <= 0) return fail("ms_ssim: bad n_img / channels");
+    if (p->levels < 2 || p->levels > dibr::SSIM_MAX_LEVELS) return fail("ms_ssim: levels must be in [2, 8]");
+    if ((long long)p->n_img * p->channels > 65535) return fail("ms_ssim: n_img * channels must be <= 65535");
+    s.levels = p->levels; s.planes = p->n_img * p->channels;
+    int h = p->height, w = p->width;
+    size_t off = 0;
+    for (int l = 0; l < s.levels; l++) {
+        if (h < 11 || w < 11) return fail("ms_ssim: every level must keep at least 11x11 pixels (ssim.py valid convolution)");
+        s.H[l] = h; s.W[l] = w; s.tiles[l] = dibr::ssim_forward_tiles(h, w);
+        const size_t img = (size_t)s.planes * h * w;
+        s.px[l] = off; if (l) off += img;
+        s.py[l] = off; if (l) off += img;
+        s.gp[l] = off; if (l && p->want_grad) off += img;
+        s.maps[l] = off; if (p->want_grad) off += (size_t)s.planes * 3 * (h - 10) * (w - 10);
+        s.partial[l] = off; off += (size_t)s.planes * s.tiles[l] * 2;
+        h = (h + 2 * (h & 1) - 2) / 2 + 1;          // avg_pool2d(kernel 2, stride 2, padding h % 2)
+        w = (w + 2 * (w & 1) - 2) / 2 + 1;
+    }
+    s.scale = off; off += (size_t)s.levels * (p->n_img > 0 ? p->n_img : 1);
+    s.total_floats = off;
+    return 0;
+}
+int dibr_ms_ssim_workspace_bytes(const DibrMsSsim* p, size_t* bytes) {
+    SsimPlan s;
+    if (int e = ssim_plan(p, s)) return e;
+    if (!bytes) return fail("ms_ssim: null bytes");
+    *bytes = s.total_floats * sizeof(float);
+    return 0;
+}
+static void ssim_level(const DibrMsSsim* p, const SsimPlan& s, int l, dibr::SsimLevelParams& q) {
+    float* ws = (float*)p->workspace;
+    q = dibr::SsimLevelParams{};
+    q.H = s.H[l]; q.W = s.W[l]; q.channels = p->channels; q.use_ssim = (l == s.levels - 1);
+    const double k1 = 0.01 * (double)p->data_range, k2 = 0.03 * (double)p->data_range;      // ssim.py:72-73, python doubles
+    q.C1 = (float)(k1 * k1);
+    q.C2 = (float)(k2 * k2);
+    for (int k = 0; k < 11; k++) q.win[k] = p->window[k];
+    q.x = l ? ws + s.px[l] : p->x;
+    q.y = l ? ws + s.py[l] : p->y;
+    q.maps = p->want_grad ? ws + s.maps[l] : nullptr;
+    q.partial = ws + s.partial[l];
+}
+int dibr_ms_ssim_forward(const DibrMsSsim* p, void* stream) {
+    SsimPlan s;
+    if (int e = ssim_plan(p, s)) return e;
+    if (!p->x || !p->y || !p->out || !p->workspace) return fail("ms_ssim: x / y / out / workspace required");
+    if (p->workspace_bytes < s.total_floats * sizeof(float)) return fail("ms_ssim: workspace too small");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    if (p->n_img == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = (float*)p->workspace;
+    dibr::SsimCombineParams c{};
+    c.n_img = p->n_img; c.channels = p->channels; c.levels = s.levels; c.normalize = p->normalize;
+    for (int l = 0; l < s.levels; l++) {
+        dibr::SsimLevelParams q;
+        ssim_level(p, s, l, q);
+        if (l) {
+            dibr::SsimLevelParams prev;
+            ssim_level(p, s, l - 1, prev);
+            g_launches += 1;
+            if (int e = cuda_fail("dibr_ms_ssim_forward(pool)", dibr::launch_ssim_pool(prev.x, prev.y, ws + s.px[l], ws + s.py[l], s.planes,
+                                                                                     s.H[l - 1], s.W[l - 1], s.H[l], s.W[l], st))) return e;
+        }
+        g_launches += 1;
+        if (int e = cuda_fail("dibr_ms_ssim_forward(level)", dibr::launch_ssim_level_forward(q, s.planes, st))) return e;
+        c.weights[l] = p->weights[l]; c.tiles[l] = s.tiles[l]; c.map_pixels[l] = (s.H[l] - 10) * (s.W[l] - 10);
+        c.partial_off[l] = (long long)s.partial[l];
+    }
+    c.partial = ws; c.out = p->out; c.scale = p->want_grad ? ws + s.scale : nullptr;
+    g_launches += 1;
+    return cuda_fail("dibr_ms_ssim_forward(combine)", dibr::launch_ssim_combine(c, st));
+}
+int dibr_ms_ssim_backward(const DibrMsSsim* p, void* stream) {
+    SsimPlan s;
+    if (int e = ssim_plan(p, s)) return e;
+    if (!p->want_grad) return fail("ms_ssim backward: the forward must have run with want_grad");
+    if (!p->x || !p->y || !p->workspace || !p->grad_out || !p->grad_y) return fail("ms_ssim backward: x / y / workspace / grad_out / grad_y required");
+    if (p->workspace_bytes < s.total_floats * sizeof(float)) return fail("ms_ssim: workspace too small");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    if (p->n_img == 0) return 0;
+    float* ws = (float*)p->workspace;
+    for (int l = s.levels - 1; l >= 0; l--) {
+        dibr::SsimLevelParams q;
+        ssim_level(p, s, l, q);
+        q.scale = ws + s.scale + (size_t)l * p->n_img;
+        q.grad_out = p->grad_out;
+        if (l < s.levels - 1) { q.grad_coarse = ws + s.gp[l + 1]; q.Hc = s.H[l + 1]; q.Wc = s.W[l + 1]; }
+        q.grad_y = l ? ws + s.gp[l] : p->grad_y;
+        g_launches += 1;
+        if (int e = cuda_fail("dibr_ms_ssim_backward(level)", dibr::launch_ssim_level_backward(q, s.planes, (cudaStream_t)stream))) return e;
+    }
+    return 0;
+}
+
 static int cr_params(const DibrChamferReduce* p, dibr::ChamferReduceParams& q, bool backward) {
     if (!p) return fail("null DibrChamferReduce");
     if (p->batch < 0 || p->stride1 < 0 || p->stride2 < 0) return fail("chamfer_reduce: negative sizes");

@@ -206,6 +206,39 @@ struct LabLossParams {
 int lab_loss_partial_floats(long long pixels);
 int launch_lab_loss_forward(const LabLossParams& P, cudaStream_t stream);
 int launch_lab_loss_backward(const LabLossParams& P, cudaStream_t stream);
+// MS-SSIM (dibr_photometric.cu): one level of the pyramid
+constexpr int SSIM_MAX_LEVELS = 8;
+struct SsimLevelParams {
+    int H, W;                  // this level's image size
+    int channels;
+    int use_ssim;              // last level: the maps are d ssim, otherwise d cs
+    float C1, C2;
+    float win[11];
+    const float* x;            // [planes, H, W]
+    const float* y;
+    float* maps;               // [planes, 3, H-10, W-10] or null (forward without gradient)
+    float* partial;            // forward: [planes, tiles, 2]
+    const float* scale;        // backward: [n_img] of this level
+    const float* grad_out;     // backward: [n_img]
+    const float* grad_coarse;  // backward: [planes, Hc, Wc] gradient of the next (pooled) level, or null
+    int Hc, Wc;
+    float* grad_y;             // backward: [planes, H, W]
+};
+struct SsimCombineParams {
+    int n_img, channels, levels, normalize;
+    float weights[SSIM_MAX_LEVELS];
+    int tiles[SSIM_MAX_LEVELS];
+    int map_pixels[SSIM_MAX_LEVELS];
+    long long partial_off[SSIM_MAX_LEVELS];   // in floats from `partial`
+    const float* partial;
+    float* out;                // [n_img]
+    float* scale;              // [levels, n_img] or null
+};
+int launch_ssim_pool(const float* x, const float* y, float* px, float* py, int planes, int H, int W, int Ho, int Wo, cudaStream_t stream);
+int ssim_forward_tiles(int H, int W);
+int launch_ssim_level_forward(const SsimLevelParams& P, int planes, cudaStream_t stream);
+int launch_ssim_combine(const SsimCombineParams& P, cudaStream_t stream);
+int launch_ssim_level_backward(const SsimLevelParams& P, int planes, cudaStream_t stream);
 // chamfer distances -> depth loss (dibr_maskloss.cu)
 struct ChamferReduceParams {
     int batch, stride1, stride2;

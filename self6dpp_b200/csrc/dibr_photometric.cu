@@ -188,4 +188,248 @@ int launch_lab_loss_backward(const LabLossParams& P, cudaStream_t stream)
     return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// (2) MS-SSIM -- core/self6dpp/losses/ssim.py:58-160 as instantiated at core/self6dpp/engine/self_engine.py:352
+//     (MS_SSIM(data_range=1.0, normalize=True): 11-tap Gaussian, valid convolution, 5 levels, 2x2 average pooling).
+//     Per level the reference runs 10 depthwise cuDNN convolutions (TF32 by default on this class of GPU) and ~25
+//     elementwise kernels with five (N,C,H,W) temporaries.  Here per level: ONE kernel that stages a 42x42 tile of X and Y
+//     in shared memory, runs the separable filter for the five moments (X, Y, XX, YY, XY) in fp32, evaluates cs / ssim per
+//     pixel, reduces them per CTA (fixed trees; per-image totals are added in plane / tile order by the combine kernel ->
+//     bit-reproducible) and, when a gradient is wanted, stores the three coefficient maps d q / d(mu_y, E[yy], E[xy]) of
+//     the one quantity the product uses at that level (cs below the last level, ssim at the last; ssim.py:150-153).
+//     Backward per level (coarse to fine): one kernel that runs the transposed separable filter over the three maps and
+//     writes  g_y = s * (A + 2 y B + x C) + 0.25 * g_pooled  -- no atomics.
+//     The reference's quirk is kept: prod over levels of [cs_l^w_l * ssim_L^w_L] raises the last level's term to the
+//     power (levels - 1).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SS_TILE = 32;
+constexpr int SS_WIN = 11;
+constexpr int SS_IN = SS_TILE + SS_WIN - 1;       // 42
+
+// 2x2 average pooling with zero padding (H % 2, W % 2), count_include_pad (ssim.py:143-145), X and Y in one launch
+__global__ void __launch_bounds__(256) ssim_pool_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ px,
+                                                        float* __restrict__ py, int planes, int H, int W, int Ho, int Wo)
+{
+    const int ph = H & 1, pw = W & 1;
+    const long long total = (long long)planes * Ho * Wo;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int wo = (int)(i % Wo);
+        const long long t = i / Wo;
+        const int ho = (int)(t % Ho);
+        const long long pl = t / Ho;
+        const int r0 = 2 * ho - ph, c0 = 2 * wo - pw;
+        float sx = 0.f, sy = 0.f;
+#pragma unroll
+        for (int dr = 0; dr < 2; dr++)
+#pragma unroll
+            for (int dc = 0; dc < 2; dc++) {
+                const int r = r0 + dr, c = c0 + dc;
+                if (r >= 0 && r < H && c >= 0 && c < W) {
+                    const long long o = (pl * H + r) * W + c;
+                    sx += x[o]; sy += y[o];
+                }
+            }
+        px[i] = sx * 0.25f; py[i] = sy * 0.25f;
+    }
+}
+
+__global__ void __launch_bounds__(256) ssim_level_forward_kernel(SsimLevelParams P)
+{
+    __shared__ float sx[SS_IN][SS_IN + 1];
+    __shared__ float sy[SS_IN][SS_IN + 1];
+    __shared__ float hz[5][SS_IN][SS_TILE + 1];
+    __shared__ float red[8][2];
+    const int Ho = P.H - (SS_WIN - 1), Wo = P.W - (SS_WIN - 1);
+    const int tiles_x = (Wo + SS_TILE - 1) / SS_TILE;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int plane = blockIdx.y;
+    const int r0 = ty * SS_TILE, c0 = tx * SS_TILE;
+    const float* X = P.x + (size_t)plane * P.H * P.W;
+    const float* Y = P.y + (size_t)plane * P.H * P.W;
+    for (int i = threadIdx.x; i < SS_IN * SS_IN; i += 256) {
+        const int r = i / SS_IN, c = i - r * SS_IN;
+        const int gr = r0 + r, gc = c0 + c;
+        const bool in = gr < P.H && gc < P.W;
+        sx[r][c] = in ? X[(size_t)gr * P.W + gc] : 0.f;
+        sy[r][c] = in ? Y[(size_t)gr * P.W + gc] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SS_IN * SS_TILE; i += 256) {
+        const int r = i / SS_TILE, c = i - r * SS_TILE;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+        for (int k = 0; k < SS_WIN; k++) {
+            const float w = P.win[k], xv = sx[r][c + k], yv = sy[r][c + k];
+            a0 = fmaf(w, xv, a0); a1 = fmaf(w, yv, a1);
+            a2 = fmaf(w, xv * xv, a2); a3 = fmaf(w, yv * yv, a3); a4 = fmaf(w, xv * yv, a4);
+        }
+        hz[0][r][c] = a0; hz[1][r][c] = a1; hz[2][r][c] = a2; hz[3][r][c] = a3; hz[4][r][c] = a4;
+    }
+    __syncthreads();
+    float s_ssim = 0.f, s_cs = 0.f;
+    for (int i = threadIdx.x; i < SS_TILE * SS_TILE; i += 256) {
+        const int r = i / SS_TILE, c = i - r * SS_TILE;
+        const int gr = r0 + r, gc = c0 + c;
+        if (gr >= Ho || gc >= Wo) continue;
+        float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < SS_WIN; k++) {
+            const float w = P.win[k];
+            mu1 = fmaf(w, hz[0][r + k][c], mu1); mu2 = fmaf(w, hz[1][r + k][c], mu2);
+            e11 = fmaf(w, hz[2][r + k][c], e11); e22 = fmaf(w, hz[3][r + k][c], e22); e12 = fmaf(w, hz[4][r + k][c], e12);
+        }
+        const float mu1s = mu1 * mu1, mu2s = mu2 * mu2, mu12 = mu1 * mu2;
+        const float s11 = e11 - mu1s, s22 = e22 - mu2s, s12 = e12 - mu12;
+        const float dcs = s11 + s22 + P.C2, dl = mu1s + mu2s + P.C1;
+        const float cs = (2.f * s12 + P.C2) / dcs;
+        const float l = (2.f * mu12 + P.C1) / dl;
+        s_ssim += l * cs; s_cs += cs;
+        if (P.maps) {
+            // d cs / d(mu2, e22, e12)
+            float g_mu = (2.f * mu2 * cs - 2.f * mu1) / dcs, g_22 = -cs / dcs, g_12 = 2.f / dcs;
+            if (P.use_ssim) {           // last level: d (l * cs)
+                g_mu = l * g_mu + cs * (2.f * (mu1 - l * mu2) / dl);
+                g_22 *= l; g_12 *= l;
+            }
+            const size_t msz = (size_t)Ho * Wo;
+            float* M = P.maps + (size_t)plane * 3 * msz + (size_t)gr * Wo + gc;
+            M[0] = g_mu; M[msz] = g_22; M[2 * msz] = g_12;
+        }
+    }
+    float v[2] = {s_ssim, s_cs};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += red[w][threadIdx.x];
+        P.partial[((size_t)plane * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = s;
+    }
+}
+
+// per image: level means in fixed order, the product, and the factors the backward multiplies the maps with
+__global__ void __launch_bounds__(128) ssim_combine_kernel(SsimCombineParams P)
+{
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= P.n_img) return;
+    float ms = 1.0f;
+    float csn[SSIM_MAX_LEVELS], ssn_last = 0.f;
+    const float half = P.normalize ? 0.5f : 1.0f;
+    for (int l = 0; l < P.levels; l++) {
+        const float* part = P.partial + P.partial_off[l];
+        const int tiles = P.tiles[l];
+        float s_ssim = 0.f, s_cs = 0.f;
+        for (int c = 0; c < P.channels; c++)
+            for (int t = 0; t < tiles; t++) {
+                const float* q = part + ((size_t)(n * P.channels + c) * tiles + t) * 2;
+                s_ssim += q[0]; s_cs += q[1];
+            }
+        const float inv = 1.0f / ((float)P.channels * (float)P.map_pixels[l]);
+        float ssim = s_ssim * inv, cs = s_cs * inv;
+        if (P.normalize) { ssim = (ssim + 1.0f) / 2.0f; cs = (cs + 1.0f) / 2.0f; }       // ssim.py:150-152
+        csn[l] = cs;
+        if (l == P.levels - 1) ssn_last = ssim;
+    }
+    const float last_term = powf(ssn_last, P.weights[P.levels - 1]);
+    for (int l = 0; l < P.levels - 1; l++) ms *= powf(csn[l], P.weights[l]) * last_term;     // ssim.py:153-156
+    P.out[n] = ms;
+    if (P.scale) {
+        for (int l = 0; l < P.levels - 1; l++)
+            P.scale[(size_t)l * P.n_img + n] = ms * P.weights[l] / csn[l] * half / ((float)P.channels * (float)P.map_pixels[l]);
+        const int L = P.levels - 1;
+        P.scale[(size_t)L * P.n_img + n] = ms * (float)(P.levels - 1) * P.weights[L] / ssn_last * half / ((float)P.channels * (float)P.map_pixels[L]);
+    }
+}
+
+// g_y(level) = grad_out[n] * scale[level][n] * (G^T mu-map + 2 y G^T e22-map + x G^T e12-map) + 0.25 * g_y(level + 1)[pooled]
+__global__ void __launch_bounds__(256) ssim_level_backward_kernel(SsimLevelParams P)
+{
+    __shared__ float sm[3][SS_IN][SS_IN + 1];
+    __shared__ float hz[3][SS_IN][SS_TILE + 1];
+    const int Ho = P.H - (SS_WIN - 1), Wo = P.W - (SS_WIN - 1);
+    const int tiles_x = (P.W + SS_TILE - 1) / SS_TILE;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int plane = blockIdx.y;
+    const int n = plane / P.channels;
+    const int r0 = ty * SS_TILE, c0 = tx * SS_TILE;
+    const size_t msz = (size_t)Ho * Wo;
+    const float* M = P.maps + (size_t)plane * 3 * msz;
+    // map pixel (u, v) feeds input pixels (u .. u+10, v .. v+10): this tile needs u in [r0 - 10, r0 + 31]
+    for (int i = threadIdx.x; i < SS_IN * SS_IN; i += 256) {
+        const int r = i / SS_IN, c = i - r * SS_IN;
+        const int u = r0 - (SS_WIN - 1) + r, v = c0 - (SS_WIN - 1) + c;
+        const bool in = u >= 0 && u < Ho && v >= 0 && v < Wo;
+        const size_t o = (size_t)u * Wo + v;
+        sm[0][r][c] = in ? M[o] : 0.f; sm[1][r][c] = in ? M[msz + o] : 0.f; sm[2][r][c] = in ? M[2 * msz + o] : 0.f;
+    }
+    __syncthreads();
+    // horizontal: out column c (input pixel c0 + c) = sum_k win[k] * map column (c0 + c - k) = sm[..][c + 10 - k]
+    for (int i = threadIdx.x; i < SS_IN * SS_TILE; i += 256) {
+        const int r = i / SS_TILE, c = i - r * SS_TILE;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < SS_WIN; k++) {
+            const float w = P.win[k];
+            a0 = fmaf(w, sm[0][r][c + SS_WIN - 1 - k], a0); a1 = fmaf(w, sm[1][r][c + SS_WIN - 1 - k], a1); a2 = fmaf(w, sm[2][r][c + SS_WIN - 1 - k], a2);
+        }
+        hz[0][r][c] = a0; hz[1][r][c] = a1; hz[2][r][c] = a2;
+    }
+    __syncthreads();
+    const float s = P.scale[n] * P.grad_out[n];
+    const int ph = P.H & 1, pw = P.W & 1;
+    for (int i = threadIdx.x; i < SS_TILE * SS_TILE; i += 256) {
+        const int r = i / SS_TILE, c = i - r * SS_TILE;
+        const int gr = r0 + r, gc = c0 + c;
+        if (gr >= P.H || gc >= P.W) continue;
+        float A = 0.f, B = 0.f, C = 0.f;
+#pragma unroll
+        for (int k = 0; k < SS_WIN; k++) {
+            const float w = P.win[k];
+            A = fmaf(w, hz[0][r + SS_WIN - 1 - k][c], A); B = fmaf(w, hz[1][r + SS_WIN - 1 - k][c], B); C = fmaf(w, hz[2][r + SS_WIN - 1 - k][c], C);
+        }
+        const size_t o = (size_t)plane * P.H * P.W + (size_t)gr * P.W + gc;
+        float g = s * (A + 2.f * P.y[o] * B + P.x[o] * C);
+        if (P.grad_coarse) {
+            const int pr = (gr + ph) >> 1, pc = (gc + pw) >> 1;
+            if (pr < P.Hc && pc < P.Wc) g += 0.25f * P.grad_coarse[(size_t)plane * P.Hc * P.Wc + (size_t)pr * P.Wc + pc];
+        }
+        P.grad_y[o] = g;
+    }
+}
+
+int launch_ssim_pool(const float* x, const float* y, float* px, float* py, int planes, int H, int W, int Ho, int Wo, cudaStream_t stream)
+{
+    const long long total = (long long)planes * Ho * Wo;
+    if (total <= 0) return 0;
+    ssim_pool_kernel<<<ph_grid(total), 256, 0, stream>>>(x, y, px, py, planes, H, W, Ho, Wo);
+    return (int)cudaGetLastError();
+}
+int ssim_forward_tiles(int H, int W)
+{
+    const int Ho = H - (SS_WIN - 1), Wo = W - (SS_WIN - 1);
+    return ((Ho + SS_TILE - 1) / SS_TILE) * ((Wo + SS_TILE - 1) / SS_TILE);
+}
+int launch_ssim_level_forward(const SsimLevelParams& P, int planes, cudaStream_t stream)
+{
+    dim3 grid(ssim_forward_tiles(P.H, P.W), planes);
+    ssim_level_forward_kernel<<<grid, 256, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+int launch_ssim_combine(const SsimCombineParams& P, cudaStream_t stream)
+{
+    ssim_combine_kernel<<<(P.n_img + 127) / 128, 128, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+int launch_ssim_level_backward(const SsimLevelParams& P, int planes, cudaStream_t stream)
+{
+    dim3 grid(((P.H + SS_TILE - 1) / SS_TILE) * ((P.W + SS_TILE - 1) / SS_TILE), planes);
+    ssim_level_backward_kernel<<<grid, 256, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace dibr

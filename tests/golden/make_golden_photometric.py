@@ -52,3 +52,37 @@ def golden_lab():
 if __name__ == "__main__":
     out = golden_lab()
     np.savez_compressed(os.path.join(OUT, "ref_photometric.npz"), **out)
+
+
+def golden_ms_ssim():
+    """core/self6dpp/losses/ssim.py: the MS_SSIM module itself, as self_engine.py:352 builds it, and two variations"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_ssim", "/root/reference/core/self6dpp/losses/ssim.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(91)
+    out = {}
+    cases = (("a", (2, 3, 192, 208), dict(data_range=1.0, normalize=True), None),         # the loop's configuration, 5 levels
+             ("b", (1, 3, 97, 113), dict(data_range=1.0, normalize=True, levels=3), None),  # odd sizes: padded pooling
+             ("c", (2, 1, 64, 48), dict(data_range=1.0, normalize=False, levels=2, channel=1), None))
+    for tag, shape, kw, _ in cases:
+        n, c, h, w = shape
+        gt, ren, mask = crops(g, n, h, w, black=True)
+        gt, ren = gt[:, :c], ren[:, :c].detach()
+        X = gt * mask
+        ren.requires_grad_(True)
+        m = mod.MS_SSIM(**kw)
+        val = m(X, ren * mask)                                                        # self_engine_utils.py:779-784
+        go = torch.rand(n, generator=g) + 0.5
+        (val * go).sum().backward()
+        out.update({f"ssim_{tag}_x": X.numpy(), f"ssim_{tag}_ren": ren.detach().numpy(), f"ssim_{tag}_mask": mask.numpy(),
+                    f"ssim_{tag}_levels": np.array(len(m.weights)), f"ssim_{tag}_weights": m.weights.numpy(),
+                    f"ssim_{tag}_normalize": np.array(int(kw["normalize"])), f"ssim_{tag}_window": m.window[0, 0, 0].numpy(),
+                    f"ssim_{tag}_val": val.detach().numpy(), f"ssim_{tag}_go": go.numpy(), f"ssim_{tag}_grad": ren.grad.numpy()})
+        print("ms_ssim", tag, val.detach().numpy())
+    return out
+
+
+if __name__ == "__main__":
+    out.update(golden_ms_ssim())
+    np.savez_compressed(os.path.join(OUT, "ref_photometric.npz"), **out)
