@@ -440,6 +440,7 @@ static int ssim_plan(const DibrMsSsim* p, SsimPlan& s) {
         s.py[l] = off; if (l) off += img;
         s.gp[l] = off; if (l && p->want_grad) off += img;
         s.maps[l] = off; if (p->want_grad) off += (size_t)s.planes * 3 * (h - 10) * (w - 10);
+        off = (off + 3) & ~(size_t)3;                // the combine kernel reads the partials as float2
         s.partial[l] = off; off += (size_t)s.planes * s.tiles[l] * 2;
         h = (h + 2 * (h & 1) - 2) / 2 + 1;          // avg_pool2d(kernel 2, stride 2, padding h % 2)
         w = (w + 2 * (w & 1) - 2) / 2 + 1;

@@ -97,4 +97,50 @@ def torch_ref():          # mask_losses.py:63-108 restated
     if nneg > 0: loss = loss + 1.0 / nneg.float() * nl.sum()
     loss.backward()
 out.append({"config": "RW-BCE mask loss fwd+bwd on [32,1,256,256]", "ms": timeit(ours), "torch_expression_ms": timeit(torch_ref)})
-for o in out: print(json.dumps(o))
+# photometric losses: ours vs the reference's expressions restated in torch eager on the same GPU
+import torch.nn.functional as F
+from self6dpp_b200.losses import lab_l1_loss
+from self6dpp_b200.ssim import MS_SSIM, create_window
+pg = torch.rand(32, 3, 256, 256, generator=g).to(DEV); pr = (pg + 0.1 * torch.randn(32, 3, 256, 256, generator=g).to(DEV)).clamp(0.002, 1)
+pm = (torch.rand(32, 1, 256, 256, generator=g) > 0.4).float().to(DEV)
+def t_rgb_to_lab_n(img):   # lab.py:16-82 + xyz.py:28-30
+    r, gg, b = img[..., 0, :, :], img[..., 1, :, :], img[..., 2, :, :]
+    rs = torch.where(r > 0.04045, torch.pow(((r + 0.055) / 1.055), 2.4), r / 12.92)
+    gs = torch.where(gg > 0.04045, torch.pow(((gg + 0.055) / 1.055), 2.4), gg / 12.92)
+    bs = torch.where(b > 0.04045, torch.pow(((b + 0.055) / 1.055), 2.4), b / 12.92)
+    x = 0.412453 * rs + 0.357580 * gs + 0.180423 * bs; y = 0.212671 * rs + 0.715160 * gs + 0.072169 * bs; z = 0.019334 * rs + 0.119193 * gs + 0.950227 * bs
+    xyz = torch.stack([x, y, z], -3) / torch.tensor([0.95047, 1.0, 1.08883], device=DEV)[..., :, None, None]
+    f = torch.where(xyz > 0.008856, torch.pow(xyz, 1 / 3), 7.787 * xyz + 4.0 / 29.0)
+    fx, fy, fz = f[..., 0, :, :], f[..., 1, :, :], f[..., 2, :, :]
+    lab = torch.stack([116.0 * fy - 16.0, 500.0 * (fx - fy), 200.0 * (fy - fz)], -3)
+    mn = torch.tensor([0.0, -110.0, -110.0]).view(3, 1, 1).to(lab); mx = torch.tensor([100.0, 110.0, 110.0]).view(3, 1, 1).to(lab)
+    return (lab - mn) / (mx - mn)
+def lab_ours():
+    r = pr.clone().requires_grad_(True); lab_l1_loss(pg, r, pm, no_l=True).backward()
+def lab_torch():           # self_engine_utils.py:745-773
+    r = pr.clone().requires_grad_(True)
+    a = t_rgb_to_lab_n(pg[:, [2, 1, 0]]); b = t_rgb_to_lab_n(r[:, [2, 1, 0]].contiguous())
+    (torch.abs(a[:, 1:] * pm - b[:, 1:] * pm).sum() / max(1, pm.sum())).backward()
+out.append({"config": "Lab (a,b) L1 colour loss fwd+bwd on [32,3,256,256]", "ms": timeit(lab_ours), "torch_expression_ms": timeit(lab_torch)})
+ms_mod = MS_SSIM(data_range=1.0, normalize=True).to(DEV)
+win = create_window(11, 1.5).to(DEV).reshape(1, 1, 1, -1).repeat(3, 1, 1, 1); wts = ms_mod.weights
+def t_filt(x):             # ssim.py:33-55
+    return F.conv2d(F.conv2d(x, win, groups=3), win.transpose(2, 3), groups=3)
+def ssim_ours():
+    r = pr.clone().requires_grad_(True); (1 - ms_mod(pg * pm, r * pm)).mean().backward()
+def ssim_torch():          # ssim.py:58-160 with normalize=True, as self_engine_utils.py:777-785 calls it
+    r = pr.clone().requires_grad_(True); X, Y = pg * pm, r * pm
+    css, ss = [], []
+    for _ in range(5):
+        mu1, mu2 = t_filt(X), t_filt(Y); s11, s22, s12 = t_filt(X * X) - mu1.pow(2), t_filt(Y * Y) - mu2.pow(2), t_filt(X * Y) - mu1 * mu2
+        cs_map = (2 * s12 + 9e-4) / (s11 + s22 + 9e-4); ssim_map = ((2 * mu1 * mu2 + 1e-4) / (mu1.pow(2) + mu2.pow(2) + 1e-4)) * cs_map
+        ss.append(ssim_map.mean(dim=(1, 2, 3))); css.append(cs_map.mean(dim=(1, 2, 3)))
+        X, Y = F.avg_pool2d(X, 2, 2), F.avg_pool2d(Y, 2, 2)
+    css = (torch.stack(css, 0) + 1) / 2; last = (ss[-1] + 1) / 2
+    ms = torch.prod((css[:-1] ** wts[:-1].unsqueeze(1)) * (last ** wts[-1]), dim=0)
+    (1 - ms).mean().backward()
+out.append({"config": "MS-SSIM loss fwd+bwd on [32,3,256,256] (5 levels, normalize)", "ms": timeit(ssim_ours), "torch_expression_ms": timeit(ssim_torch),
+            "note": "torch eager runs the depthwise convolutions through cuDNN with TF32 allowed (its default)"})
+for o in out[-2:]: print(json.dumps(o))
+if "--photometric-only" not in sys.argv:
+    for o in out[:-2]: print(json.dumps(o))
