@@ -39,7 +39,10 @@ __device__ unsigned long long g_phase[8];
 #endif
 
 constexpr int NWARP = FWD_THREADS / 32;
-constexpr int HITCAP = 30;              // collected faces per pixel per pass of phase D (>= the default K: one pass)
+#ifndef DIBR_HITCAP
+#define DIBR_HITCAP 30
+#endif
+constexpr int HITCAP = DIBR_HITCAP;     // collected faces per pixel per pass of phase D (pixels with more take another pass)
 constexpr int BW = 8, BH = 4;           // pixel block of one warp in phase D
 constexpr int NBX = TILE / BW;
 #ifndef DIBR_RASTER_LANES

@@ -46,7 +46,9 @@ def _proj_constants(width, height, near, far, device):
 
 
 def projection_from_K(Ks, width, height, near, far, device):
-    """Ks: [3,3] or [b,3,3] (tensor / ndarray) -> [4,4] or [b,4,4] float32 on ``device``."""
+    """Ks: [3,3] or [b,3,3] (tensor / ndarray / list of [3,3], base.py:136) -> [4,4] or [b,4,4] float32 on ``device``."""
+    if isinstance(Ks, (list, tuple)) and len(Ks) > 0 and isinstance(Ks[0], torch.Tensor):
+        Ks = torch.stack(list(Ks))
     Ks = torch.as_tensor(Ks)
     if Ks.device != device or Ks.dtype != torch.float32:
         Ks = Ks.to(device=device, dtype=torch.float32)

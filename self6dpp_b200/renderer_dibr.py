@@ -148,6 +148,8 @@ class Renderer_dibr(object):
             return None
         B = len(models)
         R = quat2mat_torch(Rs) if rot_type == "quat" else Rs
+        if isinstance(Ks, (list, tuple)) and len(Ks) > 0 and isinstance(Ks[0], torch.Tensor):
+            Ks = torch.stack(list(Ks))
         K = torch.as_tensor(Ks)
         if K.device != device or K.dtype != torch.float32:
             K = K.to(device=device, dtype=torch.float32)
