@@ -332,6 +332,28 @@ int dibr_ms_ssim_workspace_bytes(const DibrMsSsim *p, size_t *bytes);
 int dibr_ms_ssim_forward(const DibrMsSsim *p, void *stream);
 int dibr_ms_ssim_backward(const DibrMsSsim *p, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Crop & resize of rendered images: batch_crop_resize (core/utils/zoom_utils.py:80-95) = detectron2's
+ * ROIAlign(output_size, spatial_scale, sampling_ratio, aligned), the op Self6D++ applies to the rendered colour image and
+ * the teacher normals (self_engine_utils.py:528-533, 662-666, 690-692).  input: [num_images, channels, height, width]
+ * addressed through ELEMENT strides (any dense layout, e.g. the renderer's channels-last images, is read in place);
+ * rois: [num_rois, 5] = (image index, x1, y1, x2, y2); output: [num_rois, channels, pooled_h, pooled_w] contiguous.
+ * sampling_ratio <= 0: ceil(roi size / output size) samples per bin and axis (the reference's setting).  The backward
+ * writes EVERY element of grad_input (same strides as input; no memset needed) by a fixed-order gather: bit-reproducible,
+ * unlike the atomicAdd scatter it replaces. */
+typedef struct DibrRoiAlign {
+    int32_t num_rois, num_images, channels, height, width, pooled_h, pooled_w, sampling_ratio, aligned, reserved0;
+    float spatial_scale, reserved1;
+    int64_t stride_n, stride_c, stride_h, stride_w;
+    const float *input;
+    const float *rois;
+    float *output;
+    const float *grad_output;                /* backward in */
+    float *grad_input;                       /* backward out */
+} DibrRoiAlign;
+int dibr_roi_align_forward(const DibrRoiAlign *p, void *stream);
+int dibr_roi_align_backward(const DibrRoiAlign *p, void *stream);
+
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);
 

@@ -111,6 +111,18 @@ class DibrMsSsim(ctypes.Structure):
     ]
 
 
+class DibrRoiAlign(ctypes.Structure):
+    """Mirror of ``struct DibrRoiAlign`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("num_rois", ctypes.c_int32), ("num_images", ctypes.c_int32), ("channels", ctypes.c_int32), ("height", ctypes.c_int32),
+        ("width", ctypes.c_int32), ("pooled_h", ctypes.c_int32), ("pooled_w", ctypes.c_int32), ("sampling_ratio", ctypes.c_int32),
+        ("aligned", ctypes.c_int32), ("reserved0", ctypes.c_int32), ("spatial_scale", ctypes.c_float), ("reserved1", ctypes.c_float),
+        ("stride_n", ctypes.c_int64), ("stride_c", ctypes.c_int64), ("stride_h", ctypes.c_int64), ("stride_w", ctypes.c_int64),
+        ("input", _c_f32p), ("rois", _c_f32p), ("output", _c_f32p), ("grad_output", _c_f32p), ("grad_input", _c_f32p),
+    ]
+
+
 class DibrChamferReduce(ctypes.Structure):
     """Mirror of ``struct DibrChamferReduce`` (include/dibr_b200.h)."""
 
@@ -128,7 +140,8 @@ EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_devi
            "dibr_backproject_compact_backward", "dibr_mask_loss_scratch_floats", "dibr_mask_loss_forward",
            "dibr_mask_loss_backward", "dibr_chamfer_reduce_forward", "dibr_chamfer_reduce_backward",
            "dibr_lab_loss_scratch_floats", "dibr_lab_loss_forward", "dibr_lab_loss_backward",
-           "dibr_ms_ssim_workspace_bytes", "dibr_ms_ssim_forward", "dibr_ms_ssim_backward", "dibr_launch_count"]
+           "dibr_ms_ssim_workspace_bytes", "dibr_ms_ssim_forward", "dibr_ms_ssim_backward",
+           "dibr_roi_align_forward", "dibr_roi_align_backward", "dibr_launch_count"]
 
 _lib = None
 
@@ -194,6 +207,10 @@ def load():
     for name in ("dibr_ms_ssim_forward", "dibr_ms_ssim_backward"):
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrMsSsim), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    for name in ("dibr_roi_align_forward", "dibr_roi_align_backward"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrRoiAlign), ctypes.c_void_p]
         fn.restype = ctypes.c_int
     lib.dibr_nnd_workspace_bytes.argtypes = [ctypes.POINTER(DibrNnd), ctypes.POINTER(ctypes.c_size_t)]
     lib.dibr_nnd_workspace_bytes.restype = ctypes.c_int

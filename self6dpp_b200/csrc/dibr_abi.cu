@@ -129,6 +129,36 @@ int dibr_device_count(void) {
     return n;
 }
 
+static int ra_params(const DibrRoiAlign* p, dibr::RoiAlignParams& q, bool backward) {
+    if (!p) return fail("null DibrRoiAlign");
+    if (p->num_rois < 0 || p->num_images < 0 || p->channels < 0) return fail("roi_align: negative size");
+    if (p->height <= 0 || p->width <= 0 || p->pooled_h <= 0 || p->pooled_w <= 0) return fail("roi_align: bad image / output size");
+    if (p->num_rois > 0 && !p->rois) return fail("roi_align: rois required");
+    if (!backward && p->num_rois > 0 && p->channels > 0 && (!p->input || !p->output)) return fail("roi_align: input / output required");
+    if (backward && p->num_images > 0 && p->channels > 0 && (!p->grad_input || (p->num_rois > 0 && !p->grad_output)))
+        return fail("roi_align backward: grad_output / grad_input required");
+    if ((long long)p->num_images * ((p->width + 63) / 64) * ((p->height + 31) / 32) >= (1ll << 31)) return fail("roi_align: input too large");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    q.input = p->input; q.rois = p->rois; q.output = p->output; q.grad_output = p->grad_output; q.grad_input = p->grad_input;
+    q.num_rois = p->num_rois; q.num_images = p->num_images; q.channels = p->channels; q.height = p->height; q.width = p->width;
+    q.pooled_h = p->pooled_h; q.pooled_w = p->pooled_w; q.sampling_ratio = p->sampling_ratio; q.aligned = p->aligned;
+    q.spatial_scale = p->spatial_scale;
+    q.stride_n = p->stride_n; q.stride_c = p->stride_c; q.stride_h = p->stride_h; q.stride_w = p->stride_w;
+    return 0;
+}
+int dibr_roi_align_forward(const DibrRoiAlign* p, void* stream) {
+    dibr::RoiAlignParams q;
+    if (int e = ra_params(p, q, false)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_roi_align_forward", dibr::launch_roi_align_forward(q, (cudaStream_t)stream));
+}
+int dibr_roi_align_backward(const DibrRoiAlign* p, void* stream) {
+    dibr::RoiAlignParams q;
+    if (int e = ra_params(p, q, true)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_roi_align_backward", dibr::launch_roi_align_backward(q, (cudaStream_t)stream));
+}
+
 long long dibr_launch_count(int reset) {
     const long long v = g_launches;
     if (reset) g_launches = 0;

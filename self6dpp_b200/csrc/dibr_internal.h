@@ -188,6 +188,19 @@ struct MaskLossParams {
 int mask_loss_partial_floats(long long n);
 int launch_mask_loss_forward(const MaskLossParams& P, cudaStream_t stream);
 int launch_mask_loss_backward(const MaskLossParams& P, cudaStream_t stream);
+// ROIAlign crop & resize of rendered images (dibr_roialign.cu)
+struct RoiAlignParams {
+    const float* input;        // [num_images, channels, height, width] through element strides
+    const float* rois;         // [num_rois, 5]: image index, x1, y1, x2, y2
+    float* output;             // [num_rois, channels, pooled_h, pooled_w] contiguous
+    const float* grad_output;  // backward in, same layout as output
+    float* grad_input;         // backward out, same strides as input; every element is written
+    int num_rois, num_images, channels, height, width, pooled_h, pooled_w, sampling_ratio, aligned;
+    float spatial_scale;
+    long long stride_n, stride_c, stride_h, stride_w;
+};
+int launch_roi_align_forward(const RoiAlignParams& P, cudaStream_t stream);
+int launch_roi_align_backward(const RoiAlignParams& P, cudaStream_t stream);
 // L1 in normalised CIE-Lab between the real and the rendered crop (dibr_photometric.cu)
 struct LabLossParams {
     int n_img;                 // images

@@ -49,7 +49,7 @@ for name, flags in specs:
     out = os.path.join(ROOT, "self6dpp_b200", "lib", f"libdibr_b200_{name}.so")
     cmd = ["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
            "--expt-relaxed-constexpr", "-shared", "-cudart", "static", "-o", out] + fl + \
-          [os.path.join(csrc, f) for f in ("dibr_abi.cu", "dibr_setup.cu", "dibr_forward.cu", "dibr_backward.cu", "dibr_nnd.cu", "dibr_nnd_grid.cu", "dibr_backproject.cu", "dibr_maskloss.cu", "dibr_photometric.cu")]
+          [os.path.join(csrc, f) for f in ("dibr_abi.cu", "dibr_setup.cu", "dibr_forward.cu", "dibr_backward.cu", "dibr_nnd.cu", "dibr_nnd_grid.cu", "dibr_backproject.cu", "dibr_maskloss.cu", "dibr_photometric.cu", "dibr_roialign.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         print(name, "BUILD FAILED", r.stderr[-2000:]); continue
