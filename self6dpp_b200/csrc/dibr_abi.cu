@@ -137,7 +137,7 @@ static int ra_params(const DibrRoiAlign* p, dibr::RoiAlignParams& q, bool backwa
     if (!backward && p->num_rois > 0 && p->channels > 0 && (!p->input || !p->output)) return fail("roi_align: input / output required");
     if (backward && p->num_images > 0 && p->channels > 0 && (!p->grad_input || (p->num_rois > 0 && !p->grad_output)))
         return fail("roi_align backward: grad_output / grad_input required");
-    if ((long long)p->num_images * ((p->width + 63) / 64) * ((p->height + 31) / 32) >= (1ll << 31)) return fail("roi_align: input too large");
+    if ((long long)p->num_images * ((p->width + 63) / 64) * ((p->height + 3) / 4) >= (1ll << 31)) return fail("roi_align: input too large");
     if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
     q.input = p->input; q.rois = p->rois; q.output = p->output; q.grad_output = p->grad_output; q.grad_input = p->grad_input;
     q.num_rois = p->num_rois; q.num_images = p->num_images; q.channels = p->channels; q.height = p->height; q.width = p->width;

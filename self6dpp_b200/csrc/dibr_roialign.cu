@@ -9,7 +9,7 @@
 //   backward  the reference scatters with fp32 atomicAdd (order dependent).  Here the input gradient is GATHERED: one
 //             thread per input pixel walks, in ascending roi order, the sample rows and columns whose bilinear footprint
 //             holds the pixel -- the sample grid of a roi is regular, so they form one index range per axis, estimated
-//             in double with a margin and then evaluated with exactly the forward's expressions -- and adds
+//             with a margin and then evaluated with exactly the forward's expressions -- and adds
 //             wy * wx * g / count in a fixed order: bit-reproducible, and the dense gradient is written once (no memset).
 #include "dibr_common.cuh"
 #include "dibr_internal.h"
@@ -111,26 +111,36 @@ __global__ void __launch_bounds__(RA_T) roi_align_forward_kernel(RoiAlignParams 
 }
 
 // ---- backward ------------------------------------------------------------------------------------------------------
-constexpr int BT_W = 64, BT_H = 32;         // input tile of one CTA
+#ifndef DIBR_RA_TILE_H
+#define DIBR_RA_TILE_H 32
+#endif
+constexpr int BT_W = 64, BT_H = DIBR_RA_TILE_H;   // input tile of one CTA
 constexpr int BT_ROWS = RA_T / BT_W;        // rows the CTA covers at a time
 constexpr int BT_PIX = BT_H / BT_ROWS;      // pixels per thread
+constexpr int RA_MAXC = 8;                  // column taps of a pixel kept in registers (more: recomputed in the loop)
 constexpr int LISTCAP = 512;                // rois of one tile kept in shared memory between flushes (>= RA_T)
 
 // candidate sample indices j (over pooled * grid samples of one axis) whose footprint can hold pixel v: conservative
 __device__ __forceinline__ void sample_range(float start, float bin, int grid, int pooled, int v, int size, int& j0, int& j1)
 {
     const int n = pooled * grid;
-    const double d = (double)bin / (double)grid;                 // sample pitch
-    if (!(d > 0.0)) { j0 = 0; j1 = n - 1; return; }              // all samples coincide (or nan): examine all
+    const float d = bin / (float)grid;                           // sample pitch
+    // a pitch below 1e-3 px (a roi of less than a pixel), or nan: examine all samples -- the estimate below is good to
+    // ~1e-4 / d samples (fp32 rounding of v - start), far inside its margin of one sample otherwise
+    if (!(d > 1e-3f)) { j0 = 0; j1 = n - 1; return; }
     // unclamped samples reach v when they lie in (v-1, v+1); the borders also take the clamped ones in [-1,0] / [size-1,size]
-    const double lo = (v == 0) ? -1.5 : (double)v - 1.0, hi = (v == size - 1) ? (double)size + 0.5 : (double)v + 1.0;
-    const double a = (lo - (double)start) / d - 0.5, b = (hi - (double)start) / d - 0.5;
-    j0 = (a < -1.0) ? 0 : ((a > (double)n) ? n : (int)a - 1);
-    j1 = (b < -1.0) ? -1 : ((b > (double)n) ? n - 1 : (int)b + 2);
+    const float lo = (v == 0) ? -1.5f : (float)v - 1.0f, hi = (v == size - 1) ? (float)size + 0.5f : (float)v + 1.0f;
+    const float inv = 1.0f / d;
+    const float a = (lo - start) * inv - 0.5f, b = (hi - start) * inv - 0.5f;
+    j0 = (a < -1.0f) ? 0 : ((a > (float)n) ? n : (int)a - 1);
+    j1 = (b < -1.0f) ? -1 : ((b > (float)n) ? n - 1 : (int)b + 2);
     j0 = max(j0, 0); j1 = min(j1, n - 1);
 }
 
-__global__ void __launch_bounds__(RA_T) roi_align_backward_kernel(RoiAlignParams P)
+#ifndef DIBR_RA_MIN_CTAS
+#define DIBR_RA_MIN_CTAS 3          /* measured 2 / 3 / 4: 0.208 / 0.154 / 0.166 ms for the 256x256 crops of 32 frames */
+#endif
+__global__ void __launch_bounds__(RA_T, DIBR_RA_MIN_CTAS) roi_align_backward_kernel(RoiAlignParams P)
 {
     __shared__ int s_list[LISTCAP];
     __shared__ int s_wcount[RA_T / 32];
@@ -145,49 +155,136 @@ __global__ void __launch_bounds__(RA_T) roi_align_backward_kernel(RoiAlignParams
 
     for (int c0 = 0; c0 < P.channels; c0 += RA_CG) {
         float* gin = P.grad_input + (long long)n * P.stride_n + (long long)x * P.stride_w + (long long)c0 * P.stride_c;
-        // adds the listed rois (ascending) to this thread's pixels; `first` starts from zero, later flushes (only when a
-        // tile is reached by more than LISTCAP rois) continue from what the same thread stored: still one fixed order
+        // adds the listed rois (ascending) to this thread's pixels; `first` starts from zero, later rois / flushes continue
+        // from what the same thread stored (read back through L1/L2): one fixed order per pixel.  Per roi the thread's
+        // column taps are found once for its BT_PIX pixels; the row taps are the same for the whole warp (a warp is half a
+        // tile row), so lane t evaluates row candidate t and the loop broadcasts them.
         auto flush = [&](int nl, bool first) {
-            if (x >= P.width) return;
-            for (int i = 0; i < BT_PIX; i++) {
-                const int y = yb + i * BT_ROWS;
-                if (y >= P.height) break;
-                float* o = gin + (long long)y * P.stride_h;
-                float acc[RA_CG];
-#pragma unroll
-                for (int k = 0; k < RA_CG; k++) acc[k] = (first || c0 + k >= P.channels) ? 0.f : o[(long long)k * P.stride_c];
-                for (int li = 0; li < nl; li++) {
-                    const int rr = s_list[li];
-                    const RoiGeom g = roi_geom(P, rr);
-                    int jy0, jy1, jx0, jx1;
-                    sample_range(g.start_h, g.bin_h, g.grid_h, P.pooled_h, y, P.height, jy0, jy1);
-                    sample_range(g.start_w, g.bin_w, g.grid_w, P.pooled_w, x, P.width, jx0, jx1);
-                    if (jy1 < jy0 || jx1 < jx0) continue;
-                    const float count = (float)max(g.grid_h * g.grid_w, 1);
-                    const float* go = P.grad_output + (size_t)rr * P.channels * g_cs;
-                    for (int jy = jy0; jy <= jy1; jy++) {
-                        const int ph = jy / g.grid_h, iy = jy - ph * g.grid_h;
-                        int a0, a1; float wa0, wa1;
-                        if (!axis_taps(sample_coord(g.start_h, ph, g.bin_h, iy, g.grid_h), P.height, a0, a1, wa0, wa1)) continue;
-                        if (a0 != y && a1 != y) continue;
-                        const float wy = (a0 == y ? wa0 : 0.f) + (a1 == y ? wa1 : 0.f);
-                        for (int jx = jx0; jx <= jx1; jx++) {
-                            const int pw = jx / g.grid_w, ix = jx - pw * g.grid_w;
-                            int b0, b1; float wb0, wb1;
-                            if (!axis_taps(sample_coord(g.start_w, pw, g.bin_w, ix, g.grid_w), P.width, b0, b1, wb0, wb1)) continue;
-                            if (b0 != x && b1 != x) continue;
-                            const float wx = (b0 == x ? wb0 : 0.f) + (b1 == x ? wb1 : 0.f);
-                            const float w = wy * wx;
-                            const float* gp = go + (size_t)ph * P.pooled_w + pw;
-#pragma unroll
-                            for (int k = 0; k < RA_CG; k++)
-                                if (c0 + k < P.channels) acc[k] += w * (__ldg(gp + (size_t)(c0 + k) * g_cs) / count);
+            const bool col_ok = x < P.width;
+            if (first) {
+                // ---- zeros for the whole tile first (most tiles of a frame are reached by no roi and end here)
+                const bool linear = P.stride_c == 1 && P.stride_w == P.channels;      // channels-last: a tile row is one run
+                if (linear) {
+                    if (c0 == 0) {
+                        const int run = min(BT_W, P.width - tx0) * P.channels;
+                        float* tile0 = P.grad_input + (long long)n * P.stride_n + (long long)tx0 * P.stride_w;
+                        const bool vec = ((run | (int)(P.stride_h & 3) | (int)(P.stride_n & 3)) & 3) == 0 &&
+                                         (reinterpret_cast<uintptr_t>(P.grad_input) & 15) == 0;   // tx0 * channels is a multiple of 64
+                        for (int i = 0; i < BT_PIX; i++) {
+                            const int y = yb + i * BT_ROWS;
+                            if (y >= P.height) break;
+                            float* row = tile0 + (long long)y * P.stride_h;
+                            if (vec) {
+                                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                                for (int e = tid % BT_W; e < (run >> 2); e += BT_W) reinterpret_cast<float4*>(row)[e] = z;
+                            } else {
+                                for (int e = tid % BT_W; e < run; e += BT_W) row[e] = 0.f;
+                            }
                         }
                     }
-                }
+                    if (nl > 0) __syncthreads();                 // uniform; other threads read these zeros back below
+                } else if (col_ok) {
+                    for (int i = 0; i < BT_PIX; i++) {
+                        const int y = yb + i * BT_ROWS;
+                        if (y >= P.height) break;
 #pragma unroll
-                for (int k = 0; k < RA_CG; k++)
-                    if (c0 + k < P.channels) o[(long long)k * P.stride_c] = acc[k];
+                        for (int k = 0; k < RA_CG; k++)
+                            if (c0 + k < P.channels) gin[(long long)y * P.stride_h + (long long)k * P.stride_c] = 0.f;
+                    }
+                }
+            }
+            for (int li = 0; li < nl; li++) {
+                const int rr = s_list[li];
+                const RoiGeom g = roi_geom(P, rr);
+                const float inv_count = 1.0f / (float)max(g.grid_h * g.grid_w, 1);
+                const float* go = P.grad_output + (size_t)rr * P.channels * g_cs + (size_t)c0 * g_cs;
+                // ---- column taps of this thread: sample columns [jxs, jxs + ncx) with weights cwx (0 where a candidate misses)
+                int jx0 = 0, jx1 = -1;
+                if (col_ok) sample_range(g.start_w, g.bin_w, g.grid_w, P.pooled_w, x, P.width, jx0, jx1);
+                float cwx[RA_MAXC];
+                int jxs = 0, ncx = 0, nhit = 0;
+                bool spill = false;                              // more than RA_MAXC columns: weights recomputed in the loop
+                for (int jx = jx0; jx <= jx1; jx++) {
+                    const int pw = jx / g.grid_w, ix = jx - pw * g.grid_w;
+                    int b0, b1; float wb0, wb1;
+                    float wx = 0.f;
+                    bool hit = false;
+                    if (axis_taps(sample_coord(g.start_w, pw, g.bin_w, ix, g.grid_w), P.width, b0, b1, wb0, wb1) && (b0 == x || b1 == x)) {
+                        wx = (b0 == x ? wb0 : 0.f) + (b1 == x ? wb1 : 0.f);
+                        hit = true;
+                    }
+                    if (ncx == 0) { if (!hit) continue; jxs = jx; }
+                    if (ncx < RA_MAXC) {
+#pragma unroll
+                        for (int c = 0; c < RA_MAXC; c++) if (c == ncx) cwx[c] = wx;
+                    } else if (hit) spill = true;
+                    if (hit || ncx < RA_MAXC) ncx = min(ncx + 1, RA_MAXC + 1);
+                    if (hit) nhit = ncx;
+                }
+                if (!spill) ncx = nhit;                          // drop the trailing candidates that miss
+                const int jx_last = jx1;
+                if (!__any_sync(0xffffffffu, ncx > 0)) continue;     // the roi misses this warp's columns
+                for (int i = 0; i < BT_PIX; i++) {
+                    const int y = yb + i * BT_ROWS;              // uniform across the warp
+                    if (y >= P.height) break;
+                    int jy0, jy1;
+                    sample_range(g.start_h, g.bin_h, g.grid_h, P.pooled_h, y, P.height, jy0, jy1);
+                    float* o = gin + (long long)y * P.stride_h;
+                    float acc[RA_CG];
+#pragma unroll
+                    for (int k = 0; k < RA_CG; k++) acc[k] = 0.f;
+                    bool any = false;                            // some tap of this roi holds the pixel
+                    for (int jb = jy0; jb <= jy1; jb += 32) {
+                        const int jy = jb + lane;
+                        int my_ph = 0;
+                        float my_wy = 0.f;
+                        if (jy <= jy1) {
+                            const int ph = jy / g.grid_h, iy = jy - ph * g.grid_h;
+                            int a0, a1; float wa0, wa1;
+                            if (axis_taps(sample_coord(g.start_h, ph, g.bin_h, iy, g.grid_h), P.height, a0, a1, wa0, wa1) && (a0 == y || a1 == y)) {
+                                my_wy = (a0 == y ? wa0 : 0.f) + (a1 == y ? wa1 : 0.f);
+                                my_ph = ph;
+                            }
+                        }
+                        const int nin = min(32, jy1 - jb + 1);
+                        for (int t = 0; t < nin; t++) {
+                            const float wy = __shfl_sync(0xffffffffu, my_wy, t);
+                            const int ph = __shfl_sync(0xffffffffu, my_ph, t);
+                            if (wy == 0.f) continue;             // uniform
+                            const float* grow = go + (size_t)ph * P.pooled_w;
+                            any = any || ncx > 0;
+                            if (!spill) {
+#pragma unroll
+                                for (int c = 0; c < RA_MAXC; c++) {
+                                    if (c < ncx) {
+                                        const int jx = jxs + c;
+                                        const int pw = g.grid_w == 1 ? jx : jx / g.grid_w;
+                                        const float w = wy * cwx[c] * inv_count;
+#pragma unroll
+                                        for (int k = 0; k < RA_CG; k++)
+                                            if (c0 + k < P.channels) acc[k] = fmaf(w, __ldg(grow + (size_t)k * g_cs + pw), acc[k]);
+                                    }
+                                }
+                            } else {
+                                for (int jx = jxs; jx <= jx_last; jx++) {
+                                    const int pw = jx / g.grid_w, ix = jx - pw * g.grid_w;
+                                    int b0, b1; float wb0, wb1;
+                                    if (!axis_taps(sample_coord(g.start_w, pw, g.bin_w, ix, g.grid_w), P.width, b0, b1, wb0, wb1)) continue;
+                                    if (b0 != x && b1 != x) continue;
+                                    const float w = wy * ((b0 == x ? wb0 : 0.f) + (b1 == x ? wb1 : 0.f)) * inv_count;
+#pragma unroll
+                                    for (int k = 0; k < RA_CG; k++)
+                                        if (c0 + k < P.channels) acc[k] = fmaf(w, __ldg(grow + (size_t)k * g_cs + pw), acc[k]);
+                                }
+                            }
+                        }
+                    }
+                    if (col_ok && any) {                         // earlier rois' sum (or the zero) + this roi's, same thread every time
+#pragma unroll
+                        for (int k = 0; k < RA_CG; k++)
+                            if (c0 + k < P.channels) o[(long long)k * P.stride_c] += acc[k];
+                    }
+                }
             }
         };
         bool first = true;
