@@ -258,46 +258,71 @@ __global__ void __launch_bounds__(256) ssim_level_forward_kernel(SsimLevelParams
         sy[r][c] = in ? Y[(size_t)gr * P.W + gc] : 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < SS_IN * SS_TILE; i += 256) {
-        const int r = i / SS_TILE, c = i - r * SS_TILE;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    // horizontal pass, 4 adjacent outputs per item: 14 + 14 shared-memory loads feed 4 x 5 x 11 FMAs (one output per item
+    // needed 22 loads for 55 FMAs and the kernel was bound by shared-memory bandwidth).  Same FMA order per output as before.
+    for (int i = threadIdx.x; i < SS_IN * (SS_TILE / 4); i += 256) {
+        const int r = i / (SS_TILE / 4), c4 = (i - r * (SS_TILE / 4)) * 4;
+        float xv[SS_WIN + 3], yv[SS_WIN + 3];
 #pragma unroll
-        for (int k = 0; k < SS_WIN; k++) {
-            const float w = P.win[k], xv = sx[r][c + k], yv = sy[r][c + k];
-            a0 = fmaf(w, xv, a0); a1 = fmaf(w, yv, a1);
-            a2 = fmaf(w, xv * xv, a2); a3 = fmaf(w, yv * yv, a3); a4 = fmaf(w, xv * yv, a4);
+        for (int t = 0; t < SS_WIN + 3; t++) { xv[t] = sx[r][c4 + t]; yv[t] = sy[r][c4 + t]; }
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+            float src[SS_WIN + 3], a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < SS_WIN + 3; t++)
+                src[t] = m == 0 ? xv[t] : m == 1 ? yv[t] : m == 2 ? xv[t] * xv[t] : m == 3 ? yv[t] * yv[t] : xv[t] * yv[t];
+#pragma unroll
+            for (int k = 0; k < SS_WIN; k++) {
+                const float w = P.win[k];
+#pragma unroll
+                for (int j = 0; j < 4; j++) a[j] = fmaf(w, src[j + k], a[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) hz[m][r][c4 + j] = a[j];
         }
-        hz[0][r][c] = a0; hz[1][r][c] = a1; hz[2][r][c] = a2; hz[3][r][c] = a3; hz[4][r][c] = a4;
     }
     __syncthreads();
     float s_ssim = 0.f, s_cs = 0.f;
-    for (int i = threadIdx.x; i < SS_TILE * SS_TILE; i += 256) {
-        const int r = i / SS_TILE, c = i - r * SS_TILE;
-        const int gr = r0 + r, gc = c0 + c;
-        if (gr >= Ho || gc >= Wo) continue;
-        float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    {
+        // vertical pass: a thread owns 4 consecutive rows of one column (14 loads per moment instead of 44)
+        const int c = threadIdx.x & (SS_TILE - 1), r4 = (threadIdx.x / SS_TILE) * 4;
+        float res[5][4];
 #pragma unroll
-        for (int k = 0; k < SS_WIN; k++) {
-            const float w = P.win[k];
-            mu1 = fmaf(w, hz[0][r + k][c], mu1); mu2 = fmaf(w, hz[1][r + k][c], mu2);
-            e11 = fmaf(w, hz[2][r + k][c], e11); e22 = fmaf(w, hz[3][r + k][c], e22); e12 = fmaf(w, hz[4][r + k][c], e12);
-        }
-        const float mu1s = mu1 * mu1, mu2s = mu2 * mu2, mu12 = mu1 * mu2;
-        const float s11 = e11 - mu1s, s22 = e22 - mu2s, s12 = e12 - mu12;
-        const float dcs = s11 + s22 + P.C2, dl = mu1s + mu2s + P.C1;
-        const float cs = (2.f * s12 + P.C2) / dcs;
-        const float l = (2.f * mu12 + P.C1) / dl;
-        s_ssim += l * cs; s_cs += cs;
-        if (P.maps) {
-            // d cs / d(mu2, e22, e12)
-            float g_mu = (2.f * mu2 * cs - 2.f * mu1) / dcs, g_22 = -cs / dcs, g_12 = 2.f / dcs;
-            if (P.use_ssim) {           // last level: d (l * cs)
-                g_mu = l * g_mu + cs * (2.f * (mu1 - l * mu2) / dl);
-                g_22 *= l; g_12 *= l;
+        for (int m = 0; m < 5; m++) {
+            float col[SS_WIN + 3];
+#pragma unroll
+            for (int t = 0; t < SS_WIN + 3; t++) col[t] = hz[m][r4 + t][c];
+#pragma unroll
+            for (int j = 0; j < 4; j++) res[m][j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < SS_WIN; k++) {
+                const float w = P.win[k];
+#pragma unroll
+                for (int j = 0; j < 4; j++) res[m][j] = fmaf(w, col[j + k], res[m][j]);
             }
-            const size_t msz = (size_t)Ho * Wo;
-            float* M = P.maps + (size_t)plane * 3 * msz + (size_t)gr * Wo + gc;
-            M[0] = g_mu; M[msz] = g_22; M[2 * msz] = g_12;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int gr = r0 + r4 + j, gc = c0 + c;
+            if (gr >= Ho || gc >= Wo) continue;
+            const float mu1 = res[0][j], mu2 = res[1][j], e11 = res[2][j], e22 = res[3][j], e12 = res[4][j];
+            const float mu1s = mu1 * mu1, mu2s = mu2 * mu2, mu12 = mu1 * mu2;
+            const float s11 = e11 - mu1s, s22 = e22 - mu2s, s12 = e12 - mu12;
+            const float dcs = s11 + s22 + P.C2, dl = mu1s + mu2s + P.C1;
+            const float cs = (2.f * s12 + P.C2) / dcs;
+            const float l = (2.f * mu12 + P.C1) / dl;
+            s_ssim += l * cs; s_cs += cs;
+            if (P.maps) {
+                // d cs / d(mu2, e22, e12)
+                float g_mu = (2.f * mu2 * cs - 2.f * mu1) / dcs, g_22 = -cs / dcs, g_12 = 2.f / dcs;
+                if (P.use_ssim) {           // last level: d (l * cs)
+                    g_mu = l * g_mu + cs * (2.f * (mu1 - l * mu2) / dl);
+                    g_22 *= l; g_12 *= l;
+                }
+                const size_t msz = (size_t)Ho * Wo;
+                float* M = P.maps + (size_t)plane * 3 * msz + (size_t)gr * Wo + gc;
+                M[0] = g_mu; M[msz] = g_22; M[2 * msz] = g_12;
+            }
         }
     }
     float v[2] = {s_ssim, s_cs};
@@ -374,36 +399,56 @@ __global__ void __launch_bounds__(256) ssim_level_backward_kernel(SsimLevelParam
     }
     __syncthreads();
     // horizontal: out column c (input pixel c0 + c) = sum_k win[k] * map column (c0 + c - k) = sm[..][c + 10 - k]
-    for (int i = threadIdx.x; i < SS_IN * SS_TILE; i += 256) {
-        const int r = i / SS_TILE, c = i - r * SS_TILE;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int i = threadIdx.x; i < SS_IN * (SS_TILE / 4); i += 256) {       // 4 adjacent outputs per item, as in the forward
+        const int r = i / (SS_TILE / 4), c4 = (i - r * (SS_TILE / 4)) * 4;
 #pragma unroll
-        for (int k = 0; k < SS_WIN; k++) {
-            const float w = P.win[k];
-            a0 = fmaf(w, sm[0][r][c + SS_WIN - 1 - k], a0); a1 = fmaf(w, sm[1][r][c + SS_WIN - 1 - k], a1); a2 = fmaf(w, sm[2][r][c + SS_WIN - 1 - k], a2);
+        for (int m = 0; m < 3; m++) {
+            float src[SS_WIN + 3], a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < SS_WIN + 3; t++) src[t] = sm[m][r][c4 + t];
+#pragma unroll
+            for (int k = 0; k < SS_WIN; k++) {
+                const float w = P.win[k];
+#pragma unroll
+                for (int j = 0; j < 4; j++) a[j] = fmaf(w, src[j + SS_WIN - 1 - k], a[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) hz[m][r][c4 + j] = a[j];
         }
-        hz[0][r][c] = a0; hz[1][r][c] = a1; hz[2][r][c] = a2;
     }
     __syncthreads();
     const float s = P.scale[n] * P.grad_out[n];
     const int ph = P.H & 1, pw = P.W & 1;
-    for (int i = threadIdx.x; i < SS_TILE * SS_TILE; i += 256) {
-        const int r = i / SS_TILE, c = i - r * SS_TILE;
-        const int gr = r0 + r, gc = c0 + c;
-        if (gr >= P.H || gc >= P.W) continue;
-        float A = 0.f, B = 0.f, C = 0.f;
+    {
+        const int c = threadIdx.x & (SS_TILE - 1), r4 = (threadIdx.x / SS_TILE) * 4;
+        float res[3][4];
 #pragma unroll
-        for (int k = 0; k < SS_WIN; k++) {
-            const float w = P.win[k];
-            A = fmaf(w, hz[0][r + SS_WIN - 1 - k][c], A); B = fmaf(w, hz[1][r + SS_WIN - 1 - k][c], B); C = fmaf(w, hz[2][r + SS_WIN - 1 - k][c], C);
+        for (int m = 0; m < 3; m++) {
+            float col[SS_WIN + 3];
+#pragma unroll
+            for (int t = 0; t < SS_WIN + 3; t++) col[t] = hz[m][r4 + t][c];
+#pragma unroll
+            for (int j = 0; j < 4; j++) res[m][j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < SS_WIN; k++) {
+                const float w = P.win[k];
+#pragma unroll
+                for (int j = 0; j < 4; j++) res[m][j] = fmaf(w, col[j + SS_WIN - 1 - k], res[m][j]);
+            }
         }
-        const size_t o = (size_t)plane * P.H * P.W + (size_t)gr * P.W + gc;
-        float g = s * (A + 2.f * P.y[o] * B + P.x[o] * C);
-        if (P.grad_coarse) {
-            const int pr = (gr + ph) >> 1, pc = (gc + pw) >> 1;
-            if (pr < P.Hc && pc < P.Wc) g += 0.25f * P.grad_coarse[(size_t)plane * P.Hc * P.Wc + (size_t)pr * P.Wc + pc];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int gr = r0 + r4 + j, gc = c0 + c;
+            if (gr >= P.H || gc >= P.W) continue;
+            const float A = res[0][j], B = res[1][j], C = res[2][j];
+            const size_t o = (size_t)plane * P.H * P.W + (size_t)gr * P.W + gc;
+            float g = s * (A + 2.f * P.y[o] * B + P.x[o] * C);
+            if (P.grad_coarse) {
+                const int pr = (gr + ph) >> 1, pc = (gc + pw) >> 1;
+                if (pr < P.Hc && pc < P.Wc) g += 0.25f * P.grad_coarse[(size_t)plane * P.Hc * P.Wc + (size_t)pr * P.Wc + pc];
+            }
+            P.grad_y[o] = g;
         }
-        P.grad_y[o] = g;
     }
 }
 
