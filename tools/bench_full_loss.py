@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""cfg2 with the losses evaluated for real instead of synthetic upstream gradients: what `compute_self_loss_pose`
+(core/self6dpp/engine/self_engine_utils.py:426-800) does around the renderer, through the drop-in Python API --
+student render (colour, depth, mask, normals, soft mask) + teacher render (normals, depth as the pseudo geometry),
+RW-BCE on the soft mask, Lab (a,b) L1 and MS-SSIM between a "real" crop and the rendered colour, depth back-projection
+chamfer, one backward to the poses.  Rendering happens in crop space (crop intrinsics), so no ROIAlign on this path.
+The "real" crop is the teacher's colour render plus noise.  Context line, not the headline (that is bench.py).
+CUDA events, median of 20 after 5 warm-ups, L2 flushed between repetitions; also counts the library's launches."""
+import json, os, statistics, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from self6dpp_b200 import Renderer_dibr, _lib
+from self6dpp_b200.losses import weighted_ex_loss_probs, lab_l1_loss
+from self6dpp_b200.ssim import MS_SSIM
+from self6dpp_b200.nndistance import depth_bp_chamfer_loss
+
+dev = torch.device("cuda:0")
+RES, B = bench.RES, bench.BATCH
+meshes, student, teacher = bench.workload(0)
+models = [{"vertices": torch.tensor(m["vertices"], device=dev), "colors": torch.tensor(m["colors"], device=dev),
+           "normals": torch.tensor(m["normals"], device=dev), "faces": torch.tensor(m["faces"], device=dev, dtype=torch.int32)}
+          for m in meshes]
+cur = [models[int(i)] for i in student["ids"]]
+ren = Renderer_dibr(RES, RES, "VertexColorBatch")
+d_in = {k: torch.tensor(student[k], device=dev) for k in ("Rs", "ts", "Ks")}
+d_te = {k: torch.tensor(teacher[k], device=dev) for k in ("Rs", "ts")}
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+ms_ssim = MS_SSIM(data_range=1.0, normalize=True).to(dev)
+with torch.no_grad():
+    t0 = ren.render_batch(d_te["Rs"], d_te["ts"], cur, Ks=d_in["Ks"], width=RES, height=RES, mode=["color", "depth", "mask"])
+    g = torch.Generator().manual_seed(5)
+    real_rgb = (t0["color"] + 0.05 * torch.randn(B, RES, RES, 3, generator=g).to(dev)).clamp(0.002, 1).permute(0, 3, 1, 2).contiguous()
+    real_img = real_rgb[:, [2, 1, 0]].contiguous()
+    pseudo_mask = (t0["mask"] > 0.5).float()
+    real_depth = t0["depth"].clone()
+
+
+def step(flip=True):
+    Rs = d_in["Rs"].detach().clone().requires_grad_(True)
+    ts = d_in["ts"].detach().clone().requires_grad_(True)
+    ret = ren.render_batch(Rs, ts, cur, Ks=d_in["Ks"], width=RES, height=RES, mode=["color", "depth", "mask", "norm", "prob"])
+    with torch.no_grad():
+        ren.render_batch(d_te["Rs"], d_te["ts"], cur, Ks=d_in["Ks"], width=RES, height=RES, mode=["norm"])
+    m = pseudo_mask[:, None]
+    if flip:        # the reference's glue: channel flip by advanced indexing (a gather forward, an index_put backward)
+        ren_img = ret["color"][..., [2, 1, 0]].permute(0, 3, 1, 2)             # bgr, bchw (self_engine_utils.py:435-437)
+        gt_img, bgr = real_img, True
+    else:           # same losses without the flip: lab_l1_loss takes the plane order as a flag, MS-SSIM does not care
+        ren_img = ret["color"].permute(0, 3, 1, 2)
+        gt_img, bgr = real_rgb, False
+    loss = weighted_ex_loss_probs(ret["prob"][:, None], m)
+    loss = loss + 0.2 * lab_l1_loss(gt_img, ren_img, m, no_l=True, bgr=bgr)
+    loss = loss + (1 - ms_ssim(gt_img * m, ren_img * m)).mean()
+    loss = loss + 100.0 * depth_bp_chamfer_loss(ret["depth"], real_depth, d_in["Ks"])[0]
+    loss.backward()
+    return loss, Rs.grad, ts.grad
+
+
+def timed(fn, reps=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    out = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        out.append(a.elapsed_time(b))
+    return statistics.median(out)
+
+
+lib = _lib.load()
+ms = timed(step)
+ms_lean = timed(lambda: step(False))
+lib.dibr_launch_count(1)
+loss, gR, gt = step()
+torch.cuda.synchronize()
+n_launch = lib.dibr_launch_count(0)
+assert torch.isfinite(loss) and torch.isfinite(gR).all() and torch.isfinite(gt).all()
+l2, gR2, gt2 = step()
+print(json.dumps({"config": "cfg2 with real losses through the Python API (render x2, RW-BCE, Lab, MS-SSIM, chamfer, backward)",
+                  "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "ms_per_step_without_channel_flip": ms_lean, "library_calls_per_step": int(n_launch),
+                  "loss": float(loss), "bit_reproducible": bool(torch.equal(gR, gR2) and torch.equal(gt, gt2) and torch.equal(loss, l2))}))
