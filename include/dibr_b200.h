@@ -333,6 +333,26 @@ int dibr_ms_ssim_forward(const DibrMsSsim *p, void *stream);
 int dibr_ms_ssim_backward(const DibrMsSsim *p, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Soft dice loss on probabilities: soft_dice_loss (core/self6dpp/losses/mask_losses.py:444-463), the other loss the
+ * rendered soft mask can feed (MASK_INIT_REN_LOSS_TYPE == "dice", self_engine_utils.py:546-549).  probs / labels:
+ * [num, per]; reduction 0 = mean (1 - sum(score) / num), 1 = sum, 2 = none (out has num entries).  stats: [num, 3] scratch
+ * the backward reads; ticket: one uint32, ZERO before the first call (re-armed by the kernel).  The backward writes
+ * d L / d probs for grad_out = d L / d out ([1], or [num] for reduction 2); labels are data (no gradient). */
+typedef struct DibrDiceLoss {
+    int32_t num, reduction;
+    int64_t per;
+    float smooth, eps;
+    const float *probs, *labels;
+    float *stats;                            /* [num, 3] */
+    uint32_t *ticket;
+    float *out;
+    const float *grad_out;                   /* backward in */
+    float *grad_probs;                       /* backward out: [num, per] */
+} DibrDiceLoss;
+int dibr_dice_loss_forward(const DibrDiceLoss *p, void *stream);
+int dibr_dice_loss_backward(const DibrDiceLoss *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Crop & resize of rendered images: batch_crop_resize (core/utils/zoom_utils.py:80-95) = detectron2's
  * ROIAlign(output_size, spatial_scale, sampling_ratio, aligned), the op Self6D++ applies to the rendered colour image and
  * the teacher normals (self_engine_utils.py:528-533, 662-666, 690-692).  input: [num_images, channels, height, width]

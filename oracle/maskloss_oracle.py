@@ -22,3 +22,24 @@ def weighted_ex_loss_probs(probs, target, weight=None):
         loss += (-np.log(1 - p[neg]) * w[neg]).sum() / nneg
         grad[neg] = np.where(inside[neg], w[neg] / (1 - p[neg]) / nneg, 0.0)
     return loss, grad
+
+
+def soft_dice_loss(probs, labels, smooth=0.0, eps=1e-7, reduction="mean", grad_out=None):
+    """mask_losses.py:444-463 in float64, with d (sum(loss * grad_out)) / d probs.  Pinned by tests/golden/ref_diceloss.npz,
+    which the reference's OWN function produced (make_golden.py --diceloss)."""
+    p = np.asarray(probs, dtype=np.float64)
+    l = np.asarray(labels, dtype=np.float64)
+    num = l.shape[0]
+    m1, m2 = p.reshape(num, -1), l.reshape(num, -1)
+    inter = (m1 * m2).sum(1) + smooth
+    den = m1.sum(1) + m2.sum(1) + smooth + eps
+    score = 2.0 * inter / den                                                                      # :456
+    if reduction == "mean":
+        loss, c = 1 - score.sum() / num, np.full(num, 1.0 / num)
+    elif reduction == "sum":
+        loss, c = (1 - score).sum(), np.ones(num)
+    else:
+        loss, c = 1 - score, np.ones(num)
+    go = np.ones_like(c) if grad_out is None else np.broadcast_to(np.asarray(grad_out, dtype=np.float64).reshape(-1), c.shape)
+    grad = -(c * go)[:, None] * 2.0 * (m2 * den[:, None] - inter[:, None]) / (den[:, None] ** 2)
+    return loss, grad.reshape(p.shape)

@@ -111,6 +111,17 @@ class DibrMsSsim(ctypes.Structure):
     ]
 
 
+class DibrDiceLoss(ctypes.Structure):
+    """Mirror of ``struct DibrDiceLoss`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("num", ctypes.c_int32), ("reduction", ctypes.c_int32), ("per", ctypes.c_int64),
+        ("smooth", ctypes.c_float), ("eps", ctypes.c_float),
+        ("probs", _c_f32p), ("labels", _c_f32p), ("stats", _c_f32p), ("ticket", ctypes.c_void_p),
+        ("out", _c_f32p), ("grad_out", _c_f32p), ("grad_probs", _c_f32p),
+    ]
+
+
 class DibrRoiAlign(ctypes.Structure):
     """Mirror of ``struct DibrRoiAlign`` (include/dibr_b200.h)."""
 
@@ -141,7 +152,8 @@ EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_devi
            "dibr_mask_loss_backward", "dibr_chamfer_reduce_forward", "dibr_chamfer_reduce_backward",
            "dibr_lab_loss_scratch_floats", "dibr_lab_loss_forward", "dibr_lab_loss_backward",
            "dibr_ms_ssim_workspace_bytes", "dibr_ms_ssim_forward", "dibr_ms_ssim_backward",
-           "dibr_roi_align_forward", "dibr_roi_align_backward", "dibr_launch_count"]
+           "dibr_roi_align_forward", "dibr_roi_align_backward", "dibr_dice_loss_forward", "dibr_dice_loss_backward",
+           "dibr_launch_count"]
 
 _lib = None
 
@@ -207,6 +219,10 @@ def load():
     for name in ("dibr_ms_ssim_forward", "dibr_ms_ssim_backward"):
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrMsSsim), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    for name in ("dibr_dice_loss_forward", "dibr_dice_loss_backward"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrDiceLoss), ctypes.c_void_p]
         fn.restype = ctypes.c_int
     for name in ("dibr_roi_align_forward", "dibr_roi_align_backward"):
         fn = getattr(lib, name)

@@ -129,6 +129,34 @@ int dibr_device_count(void) {
     return n;
 }
 
+static int dl_params(const DibrDiceLoss* p, dibr::DiceLossParams& q, bool backward) {
+    if (!p) return fail("null DibrDiceLoss");
+    if (p->num < 0 || p->per < 0) return fail("dice_loss: negative size");
+    if (p->num > 65535) return fail("dice_loss: more than 65535 samples");
+    if (p->reduction < 0 || p->reduction > 2) return fail("dice_loss: reduction must be 0 (mean), 1 (sum) or 2 (none)");
+    if (!p->out || !p->stats) return fail("dice_loss: out / stats required");
+    if (p->num > 0 && p->per > 0 && (!p->probs || !p->labels)) return fail("dice_loss: probs / labels required");
+    if (!backward && !p->ticket) return fail("dice_loss: ticket required");
+    if (backward && (!p->grad_out || (p->num > 0 && p->per > 0 && !p->grad_probs))) return fail("dice_loss backward: grad_out / grad_probs required");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    q.num = p->num; q.per = p->per; q.reduction = p->reduction; q.smooth = p->smooth; q.eps = p->eps;
+    q.probs = p->probs; q.labels = p->labels; q.stats = p->stats; q.ticket = p->ticket; q.out = p->out;
+    q.grad_out = p->grad_out; q.grad_probs = p->grad_probs;
+    return 0;
+}
+int dibr_dice_loss_forward(const DibrDiceLoss* p, void* stream) {
+    dibr::DiceLossParams q;
+    if (int e = dl_params(p, q, false)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_dice_loss_forward", dibr::launch_dice_loss_forward(q, (cudaStream_t)stream));
+}
+int dibr_dice_loss_backward(const DibrDiceLoss* p, void* stream) {
+    dibr::DiceLossParams q;
+    if (int e = dl_params(p, q, true)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_dice_loss_backward", dibr::launch_dice_loss_backward(q, (cudaStream_t)stream));
+}
+
 static int ra_params(const DibrRoiAlign* p, dibr::RoiAlignParams& q, bool backward) {
     if (!p) return fail("null DibrRoiAlign");
     if (p->num_rois < 0 || p->num_images < 0 || p->channels < 0) return fail("roi_align: negative size");

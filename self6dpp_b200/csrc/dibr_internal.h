@@ -188,6 +188,22 @@ struct MaskLossParams {
 int mask_loss_partial_floats(long long n);
 int launch_mask_loss_forward(const MaskLossParams& P, cudaStream_t stream);
 int launch_mask_loss_backward(const MaskLossParams& P, cudaStream_t stream);
+// soft dice loss on probabilities (dibr_maskloss.cu)
+struct DiceLossParams {
+    int num;                   // samples
+    long long per;             // elements per sample
+    int reduction;             // 0 mean, 1 sum, 2 none
+    float smooth, eps;
+    const float* probs;        // [num, per]
+    const float* labels;       // [num, per]
+    float* stats;              // [num, 3]: sum p l, sum p, sum l (kept for the backward)
+    unsigned int* ticket;      // [1], zero between calls
+    float* out;                // [1] (mean, sum) or [num] (none)
+    const float* grad_out;     // backward: [1] or [num]
+    float* grad_probs;         // backward: [num, per]
+};
+int launch_dice_loss_forward(const DiceLossParams& P, cudaStream_t stream);
+int launch_dice_loss_backward(const DiceLossParams& P, cudaStream_t stream);
 // ROIAlign crop & resize of rendered images (dibr_roialign.cu)
 struct RoiAlignParams {
     const float* input;        // [num_images, channels, height, width] through element strides

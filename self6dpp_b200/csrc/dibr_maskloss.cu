@@ -183,3 +183,89 @@ int launch_chamfer_reduce_backward(const ChamferReduceParams& P, cudaStream_t st
 }
 
 }  // namespace dibr
+
+// ---------------------------------------------------------------------------------------------------------------
+// Soft dice loss on the rendered soft mask: soft_dice_loss (core/self6dpp/losses/mask_losses.py:444-463), the
+// MASK_INIT_REN_LOSS_TYPE == "dice" alternative at core/self6dpp/engine/self_engine_utils.py:546-549:
+//   per sample  score = 2 (sum p l + smooth) / (sum p + sum l + smooth + eps);   mean: 1 - sum(score) / num,
+//   sum: sum(1 - score), none: 1 - score.   One CTA per sample (strided sums, fixed trees) leaves (sum pl, sum p, sum l);
+//   the last CTA adds the scores in sample order.  One elementwise backward:
+//   d score / d p_i = 2 (l_i D - (I + smooth)) / D^2  with  D = sum p + sum l + smooth + eps.
+// ---------------------------------------------------------------------------------------------------------------
+namespace dibr {
+
+constexpr int DL_T = 512;
+
+__device__ __forceinline__ float dice_score(const float* st, float smooth, float eps) {
+    return 2.0f * (st[0] + smooth) / (st[1] + st[2] + smooth + eps);
+}
+
+__global__ void __launch_bounds__(DL_T) dice_loss_forward_kernel(DiceLossParams P)
+{
+    __shared__ float red[DL_T / 32][3];
+    __shared__ int last;
+    const int b = blockIdx.x;
+    const float* p = P.probs + (size_t)b * P.per;
+    const float* l = P.labels + (size_t)b * P.per;
+    float v[3] = {0.f, 0.f, 0.f};
+    for (long long i = threadIdx.x; i < P.per; i += DL_T) { const float a = p[i], c = l[i]; v[0] += a * c; v[1] += a; v[2] += c; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < DL_T / 32; w++) s += red[w][threadIdx.x];
+        P.stats[(size_t)b * 3 + threadIdx.x] = s;
+        red[0][threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (P.reduction == 2) {                                   // none: every sample writes its own value
+        if (threadIdx.x == 0) P.out[b] = 1.0f - dice_score(red[0], P.smooth, P.eps);
+        return;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last || threadIdx.x != 0) return;
+    __threadfence();
+    float acc = 0.f;
+    for (int s = 0; s < P.num; s++) {                         // sample order: fixed
+        const float st[3] = {__ldcg(P.stats + (size_t)s * 3), __ldcg(P.stats + (size_t)s * 3 + 1), __ldcg(P.stats + (size_t)s * 3 + 2)};
+        const float sc = dice_score(st, P.smooth, P.eps);
+        acc += P.reduction == 0 ? sc : 1.0f - sc;
+    }
+    P.out[0] = P.reduction == 0 ? 1.0f - acc / (float)P.num : acc;
+    *P.ticket = 0u;
+}
+
+__global__ void __launch_bounds__(256) dice_loss_backward_kernel(DiceLossParams P)
+{
+    const int b = blockIdx.y;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= P.per) return;
+    const float I = P.stats[(size_t)b * 3] + P.smooth, D = P.stats[(size_t)b * 3 + 1] + P.stats[(size_t)b * 3 + 2] + P.smooth + P.eps;
+    const float c = P.reduction == 0 ? P.grad_out[0] / (float)P.num : (P.reduction == 1 ? P.grad_out[0] : P.grad_out[b]);
+    const float l = P.labels[(size_t)b * P.per + i];
+    P.grad_probs[(size_t)b * P.per + i] = -c * (2.0f * (l * D - I) / (D * D));
+}
+
+int launch_dice_loss_forward(const DiceLossParams& P, cudaStream_t stream)
+{
+    if (P.num <= 0) return 0;
+    dice_loss_forward_kernel<<<P.num, DL_T, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+int launch_dice_loss_backward(const DiceLossParams& P, cudaStream_t stream)
+{
+    if (P.num <= 0 || P.per <= 0) return 0;
+    dice_loss_backward_kernel<<<dim3((unsigned)((P.per + 255) / 256), P.num), 256, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dibr

@@ -82,6 +82,52 @@ def weighted_ex_loss_probs(probs, target, weight=None):
     return _WeightedExLossProbs.apply(probs, target, weight)
 
 
+class _SoftDiceLoss(Function):
+    @staticmethod
+    def forward(ctx, probs, labels, smooth, eps, reduction):
+        _require_cuda_f32("probs", probs)
+        _require_cuda_f32("labels", labels)
+        num = labels.size(0)
+        p_c, l_c = probs.detach().reshape(num, -1).contiguous(), labels.detach().reshape(num, -1).contiguous()
+        if p_c.shape != l_c.shape:
+            raise RuntimeError("soft_dice_loss: probs and labels must hold the same number of elements per sample")
+        device = probs.device
+        red = {"mean": 0, "sum": 1}.get(reduction, 2)
+        out = torch.empty(num if red == 2 else 1, dtype=torch.float32, device=device)
+        scratch = torch.zeros(num * 3 + 1, dtype=torch.float32, device=device)          # stats + the ticket word
+        q = _lib.DibrDiceLoss()
+        q.num, q.reduction, q.per, q.smooth, q.eps = num, red, p_c.shape[1], float(smooth), float(eps)
+        q.probs, q.labels, q.stats, q.out = _lib.ptr(p_c), _lib.ptr(l_c), _lib.ptr(scratch), _lib.ptr(out)
+        q.ticket = scratch.data_ptr() + 4 * num * 3
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().dibr_dice_loss_forward(ctypes.byref(q), _stream(device)), "dibr_dice_loss_forward")
+        ctx.save_for_backward(p_c, l_c, scratch, out)
+        ctx.meta = (num, red, float(smooth), float(eps), probs.shape)
+        return out if red == 2 else out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p_c, l_c, scratch, out = ctx.saved_tensors
+        num, red, smooth, eps, shape = ctx.meta
+        g = grad_out.detach().reshape(-1).contiguous().float()
+        grad = torch.empty_like(p_c)
+        q = _lib.DibrDiceLoss()
+        q.num, q.reduction, q.per, q.smooth, q.eps = num, red, p_c.shape[1], smooth, eps
+        q.probs, q.labels, q.stats, q.out = _lib.ptr(p_c), _lib.ptr(l_c), _lib.ptr(scratch), _lib.ptr(out)
+        q.grad_out, q.grad_probs = _lib.ptr(g), _lib.ptr(grad)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.load().dibr_dice_loss_backward(ctypes.byref(q), _stream(g.device)), "dibr_dice_loss_backward")
+        return grad.reshape(shape), None, None, None, None
+
+
+def soft_dice_loss(probs, labels, smooth=0.0, eps=1e-7, reduction="mean"):
+    """mask_losses.py:444-463 (the "dice" choice of MASK_INIT_REN_LOSS_TYPE, self_engine_utils.py:546-549; SOLOv2 uses
+    eps=0.002): per sample score = 2 (sum p l + smooth) / (sum p + sum l + smooth + eps); "mean": 1 - sum(score) / num,
+    "sum": sum(1 - score), anything else: 1 - score per sample.  One reduction launch + one elementwise backward;
+    ``labels`` is data (no gradient)."""
+    return _SoftDiceLoss.apply(probs, labels, smooth, eps, reduction)
+
+
 class _LabL1Loss(Function):
     @staticmethod
     def forward(ctx, gt_img, ren_img, mask, no_l, bgr):

@@ -137,7 +137,7 @@ def golden_seam(ref, H=48, W=64, seed=5):
     print("ref_seam48x64: covered", int((im[..., 3] > 0.5).sum()))
 
 
-if __name__ == "__main__" and not any(a in sys.argv for a in ("--nnd", "--tex", "--maskloss")):
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--nnd", "--tex", "--maskloss", "--diceloss")):
     import warnings
     warnings.filterwarnings("ignore")
     ref = O.import_reference()
@@ -369,3 +369,35 @@ def golden_maskloss():
 
 if __name__ == "__main__" and "--maskloss" in sys.argv:
     golden_maskloss()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# soft dice loss: the reference's OWN soft_dice_loss (mask_losses.py:444-463) on CPU
+# ------------------------------------------------------------------------------------------------------------------
+def golden_diceloss():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_mask_losses", "/root/reference/core/self6dpp/losses/mask_losses.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(41)
+    out = {}
+    cases = (("a", (3, 1, 40, 56), 0.0, 0.002, "mean"), ("b", (2, 1, 33, 47), 1.0, 1e-7, "sum"), ("c", (4, 1, 9, 7), 0.0, 0.002, "none"),
+             ("d", (2, 1, 8, 8), 0.0, 0.002, "mean"))
+    for tag, shape, smooth, eps, red in cases:
+        probs = torch.rand(shape, generator=g)
+        labels = (torch.rand(shape, generator=g) > 0.6).float()
+        if tag == "d":
+            labels[1] = 0                                     # an empty label: score 0, loss contribution 1
+        go = torch.rand(shape[0] if red == "none" else 1, generator=g) + 0.5
+        probs.requires_grad_(True)
+        loss = mod.soft_dice_loss(probs, labels, smooth=smooth, eps=eps, reduction=red)
+        (loss * (go if red == "none" else go[0])).sum().backward()
+        out.update({f"{tag}_probs": probs.detach().numpy(), f"{tag}_labels": labels.numpy(), f"{tag}_loss": loss.detach().numpy(),
+                    f"{tag}_grad": probs.grad.numpy(), f"{tag}_go": go.numpy(), f"{tag}_cfg": np.array([smooth, eps]),
+                    f"{tag}_red": np.array(red)})
+        print("diceloss", tag, loss.detach().numpy())
+    np.savez_compressed(os.path.join(OUT, "ref_diceloss.npz"), **out)
+
+
+if __name__ == "__main__" and "--diceloss" in sys.argv:
+    golden_diceloss()

@@ -60,3 +60,66 @@ def test_cpu_tensor_raises():
     from self6dpp_b200.losses import weighted_ex_loss_probs
     with pytest.raises(Exception):
         weighted_ex_loss_probs(torch.rand(2, 1, 4, 4), torch.zeros(2, 1, 4, 4))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# soft dice loss (mask_losses.py:444-463), golden vectors from the reference's own function (make_golden.py --diceloss).
+# Tolerance: 1e-5 relative on the value, 1e-5 of the largest entry on the gradient.
+# ------------------------------------------------------------------------------------------------------------------
+DICE_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_diceloss.npz")
+DICE_TAGS = "abcd"
+
+
+def test_dice_oracle_matches_reference_golden():
+    from oracle import maskloss_oracle as M
+    d = np.load(DICE_GOLD)
+    for tag in DICE_TAGS:
+        smooth, eps = (float(v) for v in d[f"{tag}_cfg"])
+        loss, grad = M.soft_dice_loss(d[f"{tag}_probs"], d[f"{tag}_labels"], smooth, eps, str(d[f"{tag}_red"]), grad_out=d[f"{tag}_go"])
+        np.testing.assert_allclose(loss, d[f"{tag}_loss"], rtol=1e-5)
+        ref = d[f"{tag}_grad"]
+        assert np.abs(grad - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_dice_gpu_matches_reference_golden_and_is_reproducible():
+    from self6dpp_b200.losses import soft_dice_loss
+    dev = "cuda:0"
+    d = np.load(DICE_GOLD)
+    for tag in DICE_TAGS:
+        smooth, eps = (float(v) for v in d[f"{tag}_cfg"])
+        red = str(d[f"{tag}_red"])
+        go = torch.tensor(d[f"{tag}_go"], device=dev)
+        outs = []
+        for _ in range(2):
+            p = torch.tensor(d[f"{tag}_probs"], device=dev, requires_grad=True)
+            loss = soft_dice_loss(p, torch.tensor(d[f"{tag}_labels"], device=dev), smooth=smooth, eps=eps, reduction=red)
+            (loss * (go if red == "none" else go[0])).sum().backward()
+            outs.append((loss.detach().clone(), p.grad.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])      # bit-reproducible
+        np.testing.assert_allclose(outs[0][0].cpu().numpy(), d[f"{tag}_loss"], rtol=1e-5)
+        ref = d[f"{tag}_grad"]
+        assert outs[0][1].shape == ref.shape
+        assert np.abs(outs[0][1].cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_dice_gpu_crop_size_against_oracle():
+    """the loop's size (32 x 1 x 256 x 256, eps = 0.002 as self_engine_utils.py:548 passes it)"""
+    from oracle import maskloss_oracle as M
+    from self6dpp_b200.losses import soft_dice_loss
+    g = torch.Generator().manual_seed(6)
+    probs = torch.rand(32, 1, 256, 256, generator=g)
+    labels = (torch.rand(32, 1, 256, 256, generator=g) > 0.7).float()
+    p = probs.to("cuda:0").requires_grad_(True)
+    loss = soft_dice_loss(p, labels.to("cuda:0"), eps=0.002)
+    loss.backward()
+    ref_loss, ref_grad = M.soft_dice_loss(probs.numpy(), labels.numpy(), 0.0, 0.002, "mean")
+    assert abs(float(loss.detach()) - ref_loss) <= 1e-5 * abs(ref_loss)
+    assert np.abs(p.grad.cpu().numpy() - ref_grad).max() <= 1e-5 * np.abs(ref_grad).max()
+
+
+def test_dice_cpu_tensor_raises():
+    from self6dpp_b200.losses import soft_dice_loss
+    with pytest.raises(Exception):
+        soft_dice_loss(torch.rand(2, 1, 4, 4), torch.ones(2, 1, 4, 4))
