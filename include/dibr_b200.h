@@ -353,6 +353,25 @@ int dibr_dice_loss_forward(const DibrDiceLoss *p, void *stream);
 int dibr_dice_loss_backward(const DibrDiceLoss *p, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Normal-map loss: NORMLoss (core/self6dpp/losses/vf_norm_loss.py:56-103), which compares the network's normals with the
+ * cropped teacher render (self_engine_utils.py:667-680):  a = mask * out, b = mask * gt;
+ *     loss = [with_l1] mean |a - b|  +  [with_cs] sum mask * (1 - cos(a, b)) / #(mask != 0)
+ * out_norm / gt_norm: planar [n_img, 3, hw]; mask: [n_img, hw].  scratch: dibr_norm_loss_scratch_floats(n_img * hw) floats
+ * followed by one uint32 that must be ZERO before the first call (re-armed by the kernel).  out[0] = loss, out[1] =
+ * #(mask != 0); the backward reads out[1] and grad_out[0] and writes d L / d out_norm.  gt_norm and mask are data. */
+typedef struct DibrNormLoss {
+    int32_t n_img, hw, with_l1, with_cs;
+    const float *out_norm, *gt_norm, *mask;
+    float *scratch;
+    float *out;                              /* [2] */
+    const float *grad_out;                   /* backward in:  [1] */
+    float *grad_out_norm;                    /* backward out: [n_img, 3, hw] */
+} DibrNormLoss;
+int dibr_norm_loss_scratch_floats(int64_t pixels);
+int dibr_norm_loss_forward(const DibrNormLoss *p, void *stream);
+int dibr_norm_loss_backward(const DibrNormLoss *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Crop & resize of rendered images: batch_crop_resize (core/utils/zoom_utils.py:80-95) = detectron2's
  * ROIAlign(output_size, spatial_scale, sampling_ratio, aligned), the op Self6D++ applies to the rendered colour image and
  * the teacher normals (self_engine_utils.py:528-533, 662-666, 690-692).  input: [num_images, channels, height, width]

@@ -43,3 +43,22 @@ def soft_dice_loss(probs, labels, smooth=0.0, eps=1e-7, reduction="mean", grad_o
     go = np.ones_like(c) if grad_out is None else np.broadcast_to(np.asarray(grad_out, dtype=np.float64).reshape(-1), c.shape)
     grad = -(c * go)[:, None] * 2.0 * (m2 * den[:, None] - inter[:, None]) / (den[:, None] ** 2)
     return loss, grad.reshape(p.shape)
+
+
+def norm_loss(out_norm, gt_norm, mask, with_l1=True, with_cs=True):
+    """NORMLoss (core/self6dpp/losses/vf_norm_loss.py:56-103) in float64 with d loss / d out_norm.  Pinned by
+    tests/golden/ref_normloss.npz, which the reference's OWN module produced (make_golden.py --normloss)."""
+    o, g, m = (np.asarray(v, dtype=np.float64) for v in (out_norm, gt_norm, mask))
+    a, b = m * o, m * g                                                                            # :80-81
+    loss, grad_a = 0.0, np.zeros_like(a)
+    if with_l1:                                                                                    # :84-85, mean over all elements
+        loss += np.abs(a - b).mean()
+        grad_a += np.sign(a - b) / a.size
+    if with_cs:                                                                                    # :90-103
+        nfg = float((m != 0).sum())
+        na = np.maximum(np.sqrt((a * a).sum(1, keepdims=True)), 1e-8)
+        nb = np.maximum(np.sqrt((b * b).sum(1, keepdims=True)), 1e-8)
+        cs = ((a / na) * (b / nb)).sum(1, keepdims=True)
+        loss += (m * (1 - cs)).sum() / nfg
+        grad_a += -(m / nfg) * ((b / nb) / na - cs * a / (na * na))
+    return loss, grad_a * m

@@ -122,6 +122,16 @@ class DibrDiceLoss(ctypes.Structure):
     ]
 
 
+class DibrNormLoss(ctypes.Structure):
+    """Mirror of ``struct DibrNormLoss`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("n_img", ctypes.c_int32), ("hw", ctypes.c_int32), ("with_l1", ctypes.c_int32), ("with_cs", ctypes.c_int32),
+        ("out_norm", _c_f32p), ("gt_norm", _c_f32p), ("mask", _c_f32p),
+        ("scratch", _c_f32p), ("out", _c_f32p), ("grad_out", _c_f32p), ("grad_out_norm", _c_f32p),
+    ]
+
+
 class DibrRoiAlign(ctypes.Structure):
     """Mirror of ``struct DibrRoiAlign`` (include/dibr_b200.h)."""
 
@@ -153,6 +163,7 @@ EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_devi
            "dibr_lab_loss_scratch_floats", "dibr_lab_loss_forward", "dibr_lab_loss_backward",
            "dibr_ms_ssim_workspace_bytes", "dibr_ms_ssim_forward", "dibr_ms_ssim_backward",
            "dibr_roi_align_forward", "dibr_roi_align_backward", "dibr_dice_loss_forward", "dibr_dice_loss_backward",
+           "dibr_norm_loss_scratch_floats", "dibr_norm_loss_forward", "dibr_norm_loss_backward",
            "dibr_launch_count"]
 
 _lib = None
@@ -219,6 +230,12 @@ def load():
     for name in ("dibr_ms_ssim_forward", "dibr_ms_ssim_backward"):
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrMsSsim), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    lib.dibr_norm_loss_scratch_floats.argtypes = [ctypes.c_int64]
+    lib.dibr_norm_loss_scratch_floats.restype = ctypes.c_int
+    for name in ("dibr_norm_loss_forward", "dibr_norm_loss_backward"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrNormLoss), ctypes.c_void_p]
         fn.restype = ctypes.c_int
     for name in ("dibr_dice_loss_forward", "dibr_dice_loss_backward"):
         fn = getattr(lib, name)

@@ -157,6 +157,37 @@ int dibr_dice_loss_backward(const DibrDiceLoss* p, void* stream) {
     return cuda_fail("dibr_dice_loss_backward", dibr::launch_dice_loss_backward(q, (cudaStream_t)stream));
 }
 
+int dibr_norm_loss_scratch_floats(int64_t pixels) { return dibr::norm_loss_partial_floats(pixels) + 1; }
+
+static int nl_params(const DibrNormLoss* p, dibr::NormLossParams& q, bool backward) {
+    if (!p) return fail("null DibrNormLoss");
+    if (p->n_img < 0 || p->hw < 0) return fail("norm_loss: negative size");
+    if (!p->with_l1 && !p->with_cs) return fail("norm_loss: with_l1 or with_cs (vf_norm_loss.py:59)");
+    if (!p->out) return fail("norm_loss: out required");
+    const long long pixels = (long long)p->n_img * p->hw;
+    if (pixels > 0 && (!p->out_norm || !p->gt_norm || !p->mask)) return fail("norm_loss: out_norm / gt_norm / mask required");
+    if (!backward && !p->scratch) return fail("norm_loss: scratch required");
+    if (backward && (!p->grad_out || (pixels > 0 && !p->grad_out_norm))) return fail("norm_loss backward: grad_out / grad_out_norm required");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    q.n_img = p->n_img; q.hw = p->hw; q.with_l1 = p->with_l1; q.with_cs = p->with_cs;
+    q.out_norm = p->out_norm; q.gt_norm = p->gt_norm; q.mask = p->mask;
+    q.partial = p->scratch; q.ticket = p->scratch ? (unsigned int*)(p->scratch + dibr::norm_loss_partial_floats(pixels)) : nullptr;
+    q.out = p->out; q.grad_out = p->grad_out; q.grad_out_norm = p->grad_out_norm;
+    return 0;
+}
+int dibr_norm_loss_forward(const DibrNormLoss* p, void* stream) {
+    dibr::NormLossParams q;
+    if (int e = nl_params(p, q, false)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_norm_loss_forward", dibr::launch_norm_loss_forward(q, (cudaStream_t)stream));
+}
+int dibr_norm_loss_backward(const DibrNormLoss* p, void* stream) {
+    dibr::NormLossParams q;
+    if (int e = nl_params(p, q, true)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_norm_loss_backward", dibr::launch_norm_loss_backward(q, (cudaStream_t)stream));
+}
+
 static int ra_params(const DibrRoiAlign* p, dibr::RoiAlignParams& q, bool backward) {
     if (!p) return fail("null DibrRoiAlign");
     if (p->num_rois < 0 || p->num_images < 0 || p->channels < 0) return fail("roi_align: negative size");

@@ -204,6 +204,23 @@ struct DiceLossParams {
 };
 int launch_dice_loss_forward(const DiceLossParams& P, cudaStream_t stream);
 int launch_dice_loss_backward(const DiceLossParams& P, cudaStream_t stream);
+// L1 + cosine loss between predicted and rendered normals (dibr_maskloss.cu)
+struct NormLossParams {
+    int n_img;                 // images
+    int hw;                    // pixels per plane
+    int with_l1, with_cs;
+    const float* out_norm;     // [n_img, 3, hw]
+    const float* gt_norm;      // [n_img, 3, hw]
+    const float* mask;         // [n_img, hw]
+    float* partial;            // [3 * CTAs] scratch
+    unsigned int* ticket;      // [1], zero between calls
+    float* out;                // [2]: loss, #(mask != 0)
+    const float* grad_out;     // backward: [1]
+    float* grad_out_norm;      // backward: [n_img, 3, hw]
+};
+int norm_loss_partial_floats(long long pixels);
+int launch_norm_loss_forward(const NormLossParams& P, cudaStream_t stream);
+int launch_norm_loss_backward(const NormLossParams& P, cudaStream_t stream);
 // ROIAlign crop & resize of rendered images (dibr_roialign.cu)
 struct RoiAlignParams {
     const float* input;        // [num_images, channels, height, width] through element strides

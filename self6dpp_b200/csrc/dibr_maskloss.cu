@@ -269,3 +269,114 @@ int launch_dice_loss_backward(const DiceLossParams& P, cudaStream_t stream)
 }
 
 }  // namespace dibr
+
+// ---------------------------------------------------------------------------------------------------------------
+// Normal-map loss between the network's normals and the rendered teacher normals: NORMLoss
+// (core/self6dpp/losses/vf_norm_loss.py:56-103), applied to the cropped teacher render at
+// core/self6dpp/engine/self_engine_utils.py:667-680:
+//   a = mask * out, b = mask * gt;  loss = [mean |a - b|]  +  [sum mask * (1 - cos(a, b)) / #(mask != 0)]
+// with cos = sum_c (a / max(|a|, 1e-8)) (b / max(|b|, 1e-8)) (F.cosine_similarity over the channel axis).  The reference
+// runs ~15 launches and one host sync (.item()); here one reduction launch (fixed trees, last CTA in CTA order) and one
+// elementwise backward for d loss / d out.  Planar [n, 3, hw] normals, [n, hw] mask.
+// ---------------------------------------------------------------------------------------------------------------
+namespace dibr {
+
+constexpr int NL_T = 256;
+
+__global__ void __launch_bounds__(NL_T) norm_loss_forward_kernel(NormLossParams P)
+{
+    __shared__ float red[NL_T / 32][3];
+    __shared__ int last;
+    const long long total = (long long)P.n_img * P.hw;
+    float v[3] = {0.f, 0.f, 0.f};                             // sum |a - b|, sum m (1 - cos), #(m != 0)
+    for (long long i = (long long)blockIdx.x * NL_T + threadIdx.x; i < total; i += (long long)gridDim.x * NL_T) {
+        const long long n = i / P.hw, p = i - n * P.hw;
+        const float m = P.mask[i];
+        const float* o = P.out_norm + n * 3 * P.hw + p;
+        const float* g = P.gt_norm + n * 3 * P.hw + p;
+        const float a0 = m * o[0], a1 = m * o[P.hw], a2 = m * o[2 * (long long)P.hw];
+        const float b0 = m * g[0], b1 = m * g[P.hw], b2 = m * g[2 * (long long)P.hw];
+        v[0] += fabsf(a0 - b0) + fabsf(a1 - b1) + fabsf(a2 - b2);
+        const float na = fmaxf(sqrtf(a0 * a0 + a1 * a1 + a2 * a2), 1e-8f), nb = fmaxf(sqrtf(b0 * b0 + b1 * b1 + b2 * b2), 1e-8f);
+        const float cs = (a0 / na) * (b0 / nb) + (a1 / na) * (b1 / nb) + (a2 / na) * (b2 / nb);
+        v[1] += m * (1.0f - cs);
+        v[2] += (m != 0.f) ? 1.0f : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NL_T / 32; w++) s += red[w][threadIdx.x];
+        P.partial[(size_t)blockIdx.x * 3 + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last || threadIdx.x != 0) return;
+    __threadfence();
+    float t[3] = {0.f, 0.f, 0.f};
+    for (unsigned b = 0; b < gridDim.x; b++)                  // CTA order: fixed
+        for (int k = 0; k < 3; k++) t[k] += __ldcg(P.partial + (size_t)b * 3 + k);
+    float loss = 0.f;
+    if (P.with_l1) loss += t[0] / (3.0f * (float)total);
+    if (P.with_cs) loss += t[1] / t[2];
+    P.out[0] = loss; P.out[1] = t[2];
+    *P.ticket = 0u;
+}
+
+__global__ void __launch_bounds__(NL_T) norm_loss_backward_kernel(NormLossParams P)
+{
+    const long long total = (long long)P.n_img * P.hw;
+    const float go = P.grad_out[0], cnt = P.out[1];
+    const float k_l1 = P.with_l1 ? go / (3.0f * (float)total) : 0.f;
+    for (long long i = (long long)blockIdx.x * NL_T + threadIdx.x; i < total; i += (long long)gridDim.x * NL_T) {
+        const long long n = i / P.hw, p = i - n * P.hw;
+        const float m = P.mask[i];
+        const float* o = P.out_norm + n * 3 * P.hw + p;
+        const float* g = P.gt_norm + n * 3 * P.hw + p;
+        float a[3], b[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { a[c] = m * o[c * (long long)P.hw]; b[c] = m * g[c * (long long)P.hw]; }
+        const float ra = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), rb = sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+        const float na = fmaxf(ra, 1e-8f), nb = fmaxf(rb, 1e-8f);
+        const float cs = (a[0] / na) * (b[0] / nb) + (a[1] / na) * (b[1] / nb) + (a[2] / na) * (b[2] / nb);
+        const float k_cs = P.with_cs ? -go * m / cnt : 0.f;  // d loss / d cos at this pixel
+        float* out = P.grad_out_norm + n * 3 * P.hw + p;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float d = a[c] - b[c];
+            float ga = k_l1 * (d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f));
+            // d cos / d a_c = b_c / (|a| |b|) - cos * a_c / |a|^2   (the clamp of a vanishing norm carries no gradient)
+            if (ra > 1e-8f) ga += k_cs * ((b[c] / nb) / na - cs * a[c] / (na * na));
+            else ga += k_cs * ((b[c] / nb) / na);
+            out[c * (long long)P.hw] = ga * m;                // a = mask * out
+        }
+    }
+}
+
+static inline int nl_grid(long long n) {
+    const long long want = (n + NL_T * 2 - 1) / (NL_T * 2);
+    return (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+}
+int norm_loss_partial_floats(long long pixels) { return 3 * nl_grid(pixels); }
+
+int launch_norm_loss_forward(const NormLossParams& P, cudaStream_t stream)
+{
+    norm_loss_forward_kernel<<<nl_grid((long long)P.n_img * P.hw), NL_T, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+int launch_norm_loss_backward(const NormLossParams& P, cudaStream_t stream)
+{
+    if ((long long)P.n_img * P.hw <= 0) return 0;
+    norm_loss_backward_kernel<<<nl_grid((long long)P.n_img * P.hw), NL_T, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dibr

@@ -137,7 +137,7 @@ def golden_seam(ref, H=48, W=64, seed=5):
     print("ref_seam48x64: covered", int((im[..., 3] > 0.5).sum()))
 
 
-if __name__ == "__main__" and not any(a in sys.argv for a in ("--nnd", "--tex", "--maskloss", "--diceloss")):
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--nnd", "--tex", "--maskloss", "--diceloss", "--normloss")):
     import warnings
     warnings.filterwarnings("ignore")
     ref = O.import_reference()
@@ -401,3 +401,31 @@ def golden_diceloss():
 
 if __name__ == "__main__" and "--diceloss" in sys.argv:
     golden_diceloss()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# normal-map loss: the reference's OWN NORMLoss (vf_norm_loss.py:56-103) on CPU
+# ------------------------------------------------------------------------------------------------------------------
+def golden_normloss():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_vf_norm_loss", "/root/reference/core/self6dpp/losses/vf_norm_loss.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(51)
+    out = {}
+    for tag, shape, l1, cs in (("a", (3, 3, 16, 20), True, True), ("b", (2, 3, 9, 7), False, True), ("c", (2, 3, 8, 8), True, False)):
+        b, _, h, w = shape
+        o = torch.randn(shape, generator=g)
+        gt = torch.nn.functional.normalize(torch.randn(shape, generator=g), dim=1)
+        m = (torch.rand(b, 1, h, w, generator=g) > 0.4).float()
+        o.requires_grad_(True)
+        loss = mod.NORMLoss(with_l1=l1, with_cs=cs)(o, gt, m)
+        (loss * 1.3).backward()
+        out.update({f"{tag}_out": o.detach().numpy(), f"{tag}_gt": gt.numpy(), f"{tag}_mask": m.numpy(), f"{tag}_loss": loss.detach().numpy(),
+                    f"{tag}_grad": o.grad.numpy(), f"{tag}_flags": np.array([int(l1), int(cs)])})
+        print("normloss", tag, float(loss))
+    np.savez_compressed(os.path.join(OUT, "ref_normloss.npz"), **out)
+
+
+if __name__ == "__main__" and "--normloss" in sys.argv:
+    golden_normloss()

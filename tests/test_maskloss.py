@@ -123,3 +123,66 @@ def test_dice_cpu_tensor_raises():
     from self6dpp_b200.losses import soft_dice_loss
     with pytest.raises(Exception):
         soft_dice_loss(torch.rand(2, 1, 4, 4), torch.ones(2, 1, 4, 4))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# normal-map loss NORMLoss (vf_norm_loss.py:56-103), golden vectors from the reference's own module
+# (make_golden.py --normloss).  Tolerance: 1e-5 relative on the value, 1e-5 of the largest entry on the gradient.
+# ------------------------------------------------------------------------------------------------------------------
+NORM_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_normloss.npz")
+
+
+def test_normloss_oracle_matches_reference_golden():
+    from oracle import maskloss_oracle as M
+    d = np.load(NORM_GOLD)
+    for tag in "abc":
+        l1, cs = (bool(v) for v in d[f"{tag}_flags"])
+        loss, grad = M.norm_loss(d[f"{tag}_out"], d[f"{tag}_gt"], d[f"{tag}_mask"], l1, cs)
+        assert abs(loss - float(d[f"{tag}_loss"])) <= 1e-5 * abs(float(d[f"{tag}_loss"]))
+        ref = d[f"{tag}_grad"] / 1.3
+        assert np.abs(grad - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_normloss_gpu_matches_reference_golden_and_is_reproducible():
+    from self6dpp_b200.losses import NORMLoss
+    dev = "cuda:0"
+    d = np.load(NORM_GOLD)
+    for tag in "abc":
+        l1, cs = (bool(v) for v in d[f"{tag}_flags"])
+        mod = NORMLoss(with_l1=l1, with_cs=cs)
+        outs = []
+        for _ in range(2):
+            o = torch.tensor(d[f"{tag}_out"], device=dev, requires_grad=True)
+            loss = mod(o, torch.tensor(d[f"{tag}_gt"], device=dev), torch.tensor(d[f"{tag}_mask"], device=dev))
+            (loss * 1.3).backward()
+            outs.append((loss.detach().clone(), o.grad.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])      # bit-reproducible
+        assert abs(float(outs[0][0]) - float(d[f"{tag}_loss"])) <= 1e-5 * abs(float(d[f"{tag}_loss"]))
+        ref = d[f"{tag}_grad"]
+        assert np.abs(outs[0][1].cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_normloss_gpu_crop_size_against_oracle():
+    """the loop's size: 32 x 3 x 64 x 64 normals against the cropped teacher render"""
+    from oracle import maskloss_oracle as M
+    from self6dpp_b200.losses import NORMLoss
+    g = torch.Generator().manual_seed(9)
+    o = torch.randn(32, 3, 64, 64, generator=g)
+    gt = torch.nn.functional.normalize(torch.randn(32, 3, 64, 64, generator=g), dim=1)
+    m = (torch.rand(32, 1, 64, 64, generator=g) > 0.5).float()
+    x = o.to("cuda:0").requires_grad_(True)
+    loss = NORMLoss()(x, gt.to("cuda:0"), m.to("cuda:0"))
+    loss.backward()
+    ref_loss, ref_grad = M.norm_loss(o.numpy(), gt.numpy(), m.numpy())
+    assert abs(float(loss.detach()) - ref_loss) <= 1e-5 * abs(ref_loss)
+    assert np.abs(x.grad.cpu().numpy() - ref_grad).max() <= 1e-5 * np.abs(ref_grad).max()
+
+
+def test_normloss_cpu_tensor_raises():
+    from self6dpp_b200.losses import NORMLoss
+    with pytest.raises(Exception):
+        NORMLoss()(torch.rand(1, 3, 4, 4), torch.rand(1, 3, 4, 4), torch.ones(1, 1, 4, 4))
+    with pytest.raises(AssertionError):
+        NORMLoss(with_l1=False, with_cs=False)
