@@ -144,7 +144,7 @@ def test_golden_render_batch_from_reference_python():
         + (ret["depth"] * dev("g_depth")).sum() + (ret["norm"] * dev("g_norm")).sum()
     loss.backward()
     # the reference's own fp32 chain (cancellation-prone dw terms of K3 + torch fp32 autograd) is itself ~5e-3 away
-    # from float64 on dL/dR for this fixture (tools/diag_fused.py); ours is ~5e-5 (previous test), so the golden
+    # from float64 on dL/dR for this fixture (tests/tools/diag_fused.py); ours is ~5e-5 (previous test), so the golden
     # can only be matched to the golden's own accuracy
     for name, got, ref, tol in (("grad_Rs", Rs.grad, d["grad_Rs"], 2e-2), ("grad_ts", ts.grad, d["grad_ts"], 2e-3)):
         rel = float(np.abs(got.cpu().numpy() - ref).max() / np.abs(ref).max())

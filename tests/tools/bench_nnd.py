@@ -1,7 +1,7 @@
 """Throughput of the chamfer nearest-neighbour op on cfg2-shaped clouds (32 samples, rendered 256x256 depth vs a
 perturbed target), and of the reference's own CPU implementation (oracle/_ref) on one sample."""
 import sys, os, json, time, statistics
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import bench
 from self6dpp_b200 import Renderer_dibr

@@ -2,7 +2,7 @@
 """CPU-side statistics of the cfg2 workload's per-tile face lists (how large LCAP / sub-lists must be)."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench
 from oracle import dibr_oracle as O
 meshes, student, teacher = bench.workload(0)
