@@ -141,3 +141,26 @@ def test_batch_crop_resize_full_size_against_torchvision_on_the_gpu():
         # kernel do not: coordinates near 640 differ by one fp32 ulp (6e-5), and a random image has unit slopes
         _close(f"{out_res} y", y.detach().cpu().numpy(), y2.detach().cpu().numpy(), 2.5e-4)
         _close(f"{out_res} gx", x.grad.cpu().numpy(), x2.grad.cpu().numpy(), 2.5e-4)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_roialign_oracle_matches_torchvision_cpu_on_random_rois(seed):
+    """beyond the committed vectors: random rois (inside, straddling the border, tiny, larger than the image), both `aligned`
+    settings, fixed and adaptive sampling -- the restatement against torchvision's CPU op wherever that package is present"""
+    tv = pytest.importorskip("torchvision")
+    from oracle import roialign_oracle as O
+    g = torch.Generator().manual_seed(100 + seed)
+    N, C, H, W = 2, 2, 11 + seed, 14
+    x = torch.randn(N, C, H, W, generator=g, requires_grad=True)
+    R = 7
+    c = torch.rand(R, 2, generator=g) * torch.tensor([W + 4.0, H + 4.0]) - 2.0
+    s = torch.cat([torch.rand(R - 2, 2, generator=g) * 8 + 0.05, torch.tensor([[0.02, 0.03], [20.0, 17.0]])])
+    rois = torch.cat([torch.randint(0, N, (R, 1), generator=g).float(), c - s, c + s], dim=1)
+    for aligned, sr, (oh, ow) in ((True, 0, (4, 5)), (False, 0, (3, 3)), (True, 3, (2, 4))):
+        go = torch.randn(R, C, oh, ow, generator=g)
+        x.grad = None
+        y = tv.ops.roi_align(x, rois, (oh, ow), 1.0, sr, aligned)
+        (y * go).sum().backward()
+        ry, rgx = O.roi_align(x.detach().numpy(), rois.numpy(), oh, ow, 1.0, sr, aligned, grad_out=go.numpy())
+        _close(f"y aligned={aligned} sr={sr}", ry, y.detach().numpy(), 5e-6)
+        _close(f"gx aligned={aligned} sr={sr}", rgx, x.grad.numpy(), 5e-6)
