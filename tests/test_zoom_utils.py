@@ -164,3 +164,27 @@ def test_roialign_oracle_matches_torchvision_cpu_on_random_rois(seed):
         ry, rgx = O.roi_align(x.detach().numpy(), rois.numpy(), oh, ow, 1.0, sr, aligned, grad_out=go.numpy())
         _close(f"y aligned={aligned} sr={sr}", ry, y.detach().numpy(), 5e-6)
         _close(f"gx aligned={aligned} sr={sr}", rgx, x.grad.numpy(), 5e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_roialign_gpu_random_rois_against_oracle(seed):
+    """the gather backward's sample-range estimate under stress: rois far outside, straddling every border, a 0.01-pixel
+    roi (pitch below the estimate's threshold: all samples examined), one much larger than the image; odd sizes"""
+    from oracle import roialign_oracle as O
+    from self6dpp_b200.zoom_utils import roi_align
+    g = torch.Generator().manual_seed(200 + seed)
+    N, C, H, W = 2, 3, 37 + seed, 70 + 3 * seed                    # wider than one 64-pixel tile of the backward
+    xs = torch.randn(N, C, H, W, generator=g)
+    R = 9
+    c = torch.rand(R, 2, generator=g) * torch.tensor([W + 10.0, H + 10.0]) - 5.0
+    s = torch.cat([torch.rand(R - 3, 2, generator=g) * 20 + 0.3, torch.tensor([[0.005, 0.004], [0.3, 25.0], [90.0, 60.0]])])
+    rois = torch.cat([torch.randint(0, N, (R, 1), generator=g).float(), c - s, c + s], dim=1)
+    for aligned, sr, (oh, ow) in ((True, 0, (6, 5)), (False, 0, (3, 4)), (True, 2, (4, 4))):
+        go = torch.randn(R, C, oh, ow, generator=g)
+        x = xs.to("cuda:0").requires_grad_(True)
+        y = roi_align(x, rois.to("cuda:0"), (oh, ow), 1.0, sr, aligned)
+        (y * go.to("cuda:0")).sum().backward()
+        ry, rgx = O.roi_align(xs.numpy(), rois.numpy(), oh, ow, 1.0, sr, aligned, grad_out=go.numpy())
+        _close(f"y aligned={aligned} sr={sr}", y.detach().cpu().numpy(), ry)
+        _close(f"gx aligned={aligned} sr={sr}", x.grad.cpu().numpy(), rgx)
