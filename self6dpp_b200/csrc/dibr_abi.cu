@@ -271,9 +271,13 @@ int dibr_forward(const DibrPass* p, void* stream) {
     if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
     else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }
     {
-        int d = 0;
-        for (int g = 0; g < f.n_out; g++)
-            for (int c = 0; c < f.out_ch[g] && d < DIBR_MAX_ATTR_INTERNAL; c++, d++) { f.chan_out[d] = f.out[g] + c; f.chan_stride[d] = f.out_ch[g]; }
+        int d = 0, plane = 0;
+        for (int g = 0; g < f.n_out; g++) {
+            for (int c = 0; c < f.out_ch[g] && d < DIBR_MAX_ATTR_INTERNAL; c++, d++) {
+                f.chan_out[d] = f.out[g] + c; f.chan_stride[d] = f.out_ch[g]; f.chan_off[d] = plane + c;
+            }
+            plane += f.out_ch[g] * dibr::TILE * dibr::TILE;
+        }
     }
     f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
     f.list_counts = w.list_counts; f.face_flags = w.face_flags; f.color_list = w.color_list; f.soft_list = w.soft_list;

@@ -80,6 +80,7 @@ struct FwdParams {
     float* out[6];             // [batch,H,W,out_ch[g]]
     float* chan_out[DIBR_MAX_ATTR_INTERNAL];    // per attribute channel d: its output tensor, pre-offset by the channel's slot in the group
     int chan_stride[DIBR_MAX_ATTR_INTERNAL];    // floats per pixel of that tensor
+    int chan_off[DIBR_MAX_ATTR_INTERNAL];       // channel d of pixel p sits at chan_off[d] + p * chan_stride[d] in the tile's shared-memory copy
     unsigned min_mask;         // channels of the output group whose batch-global minimum is accumulated
     float* improb;
     float* imcomp;
@@ -324,6 +325,7 @@ int launch_nnd_backward(const NndParams& P, cudaStream_t stream);
 int launch_setup_faces(const SetupParams& P, cudaStream_t stream);
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream);
 int launch_forward(const FwdParams& P, cudaStream_t stream);
+int launch_forward_v2(const FwdParams& P, cudaStream_t stream);      // previous design, kept for the A/B (DIBR_FWD_IMPL=2)
 int launch_backward_faces(const BwdParams& P, cudaStream_t stream);
 int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream);
 int launch_normal_map(const float* n, const float* mask, const unsigned int* min_ordered, float* out, long long npix, cudaStream_t stream);

@@ -71,14 +71,15 @@ for key, (s, i, t) in sorted(agg.items(), key=lambda kv: -kv[1][1 if "--by-inst"
 # ---- per-phase view for the forward kernel: helper lines (inlined .cuh code) inherit the phase of the nearest
 # preceding dibr_forward.cu line in address order
 if "--phases" in sys.argv:
-    bounds = [(112, 168, "A bitmap"), (169, 205, "A gather"), (206, 283, "B raster"), (284, 338, "fill untouched"), (340, 393, "prologue"),
-              (394, 415, "tile setup"), (416, 438, "batch loop"), (439, 550, "C resolve"), (551, 586, "D setup+masks"), (587, 627, "D collect"),
-              (628, 668, "D evaluate"), (669, 681, "D fold"), (682, 695, "D marks")]
+    # phases are declared in the source: a "// @phase NAME" comment opens a phase that lasts until the next marker
+    srcfile = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "self6dpp_b200", "csrc", "dibr_forward.cu")
+    marks = [(n + 1, l.split("@phase", 1)[1].strip()) for n, l in enumerate(open(srcfile).read().splitlines()) if "// @phase" in l]
     def phase_of(ln):
-        for a, b, n in bounds:
-            if a <= ln <= b:
-                return n
-        return "other"
+        name = "other"
+        for a, n in marks:
+            if a <= ln:
+                name = n
+        return name
     cur = "other"
     pagg = collections.defaultdict(lambda: [0.0, 0.0])
     for d in body:

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Debug: build variant libraries with -D switches (on the GPU box) and time dibr_forward_kernel with each.
-usage: variants.py NAME=-DFLAG1,-DFLAG2 ...   (NAME 'base' = no flags); add :phase to a name to print phase cycles"""
+usage: variants.py NAME=-DFLAG1,-DFLAG2 ...   (NAME 'base' = no flags; a NAME starting with v2 runs the previous forward design,
+DIBR_FWD_IMPL=2); add :phase to a name to print phase cycles"""
 import sys, os, subprocess, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -36,11 +37,11 @@ if child:
     if phase:
         lib.dibr_debug_phase_cycles(buf, 1)
         n = buf[7]
-        names = ["setup", "scan+gather", "raster", "resolve", "soft"]
-        print("   touched CTAs per launch %.0f" % (n / (reps + 4)))
-        tot = sum(buf[:5])
-        for k in range(5):
-            print("   %-12s %8.0f cycles/CTA  %5.1f%%" % (names[k], buf[k] / max(n, 1), 100.0 * buf[k] / max(tot, 1)))
+        names = ["list+gather", "prep", "coverage", "resolve", "soft", "write", "fill"]
+        print("   touched tiles per launch %.0f" % (n / (reps + 3)))
+        tot = sum(buf[:7])
+        for k in range(7):
+            print("   %-12s %8.0f cycles/tile  %5.1f%%" % (names[k], buf[k] / max(n, 1), 100.0 * buf[k] / max(tot, 1)))
     sys.exit(0)
 for name, flags in specs:
     phase = name.endswith(":phase")
@@ -49,10 +50,14 @@ for name, flags in specs:
     out = os.path.join(ROOT, "self6dpp_b200", "lib", f"libdibr_b200_{name}.so")
     cmd = ["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
            "--expt-relaxed-constexpr", "-shared", "-cudart", "static", "-o", out] + fl + \
-          [os.path.join(csrc, f) for f in ("dibr_abi.cu", "dibr_setup.cu", "dibr_forward.cu", "dibr_backward.cu", "dibr_nnd.cu", "dibr_nnd_grid.cu", "dibr_backproject.cu", "dibr_maskloss.cu", "dibr_photometric.cu", "dibr_roialign.cu")]
+          [os.path.join(csrc, f) for f in ("dibr_abi.cu", "dibr_setup.cu", "dibr_forward.cu", "dibr_forward_v2.cu", "dibr_backward.cu", "dibr_nnd.cu", "dibr_nnd_grid.cu", "dibr_backproject.cu", "dibr_maskloss.cu", "dibr_photometric.cu", "dibr_roialign.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         print(name, "BUILD FAILED", r.stderr[-2000:]); continue
+    if name.startswith("v2"):
+        os.environ["DIBR_FWD_IMPL"] = "2"
+    else:
+        os.environ.pop("DIBR_FWD_IMPL", None)
     env = dict(os.environ, DIBR_VARIANT_LIB=out, DIBR_VARIANT_NAME=name + " " + " ".join(fl), DIBR_VARIANT_PHASE="1" if phase else "0")
     if script:
         print("==== variant", name, " ".join(fl), flush=True)
