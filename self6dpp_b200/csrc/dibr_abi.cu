@@ -37,10 +37,19 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     {
         const size_t ntiles = (size_t)p->batch * ((p->height + dibr::TILE - 1) / dibr::TILE) * ((p->width + dibr::TILE - 1) / dibr::TILE);
         w.order_seg = (int*)take(sizeof(int) * dibr::ORDER_BUCKETS * ntiles);
-        w.order_cnt = (int*)take(sizeof(int) * dibr::ORDER_BUCKETS);       // directly before the bins: one memset clears both
+        w.tile_desc = (int4*)take(sizeof(int4) * dibr::ORDER_BUCKETS * ntiles);
+        w.big_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
+        w.big_cap = p->total_faces;
+        w.order_cnt = (int*)take(sizeof(int) * 2 * dibr::ORDER_BUCKETS);   // counters, then the bins, then the z-buffer: one memset clears all three
+        w.big_count = w.order_cnt ? w.order_cnt + dibr::ORDER_BUCKETS : nullptr;
+        w.tile_blocks = (unsigned int*)take(sizeof(unsigned int) * ntiles);
     }
     w.bins_bytes = sizeof(uint32_t) * dibr::bin_total_words(p->width, p->height, p->batch, p->total_faces);
     w.bins = (uint32_t*)take(w.bins_bytes);
+    w.wordmask = (unsigned char*)take(w.bins_bytes / sizeof(uint32_t));
+    w.zbuf_bytes = sizeof(unsigned long long) * (size_t)p->batch * (size_t)p->height * (size_t)p->width;
+    w.zbuf = (unsigned long long*)take(w.zbuf_bytes);
+    w.fbox = (uint2*)take(sizeof(uint2) * (size_t)p->total_faces);
     w.xs = (float*)take(sizeof(float) * (size_t)p->width);
     w.ys = (float*)take(sizeof(float) * (size_t)p->height);
     w.pose_part = (float*)take(sizeof(float) * 12 * dibr::POSE_BLOCKS * (size_t)(p->num_instances > 0 ? p->num_instances : 0));
@@ -106,6 +115,7 @@ dibr::SetupParams setup_params(const DibrPass* p) {
     s.pose_R = p->pose_R; s.pose_t = p->pose_t; s.pose_K = p->pose_K; s.num_K = p->num_K;
     const double nc = p->znear, fc = p->zfar;
     s.expand_mul = (float)((double)p->expand * (double)p->multiplier);
+    s.fwd_impl = dibr::forward_impl();
     s.q = (float)(-(fc + nc) / (fc - nc));
     s.qn = (float)(-2.0 * (fc * nc) / (fc - nc));
     return s;
@@ -267,7 +277,8 @@ int dibr_forward(const DibrPass* p, void* stream) {
     f.multiplier = p->multiplier; f.delta = p->delta;
     f.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     f.faces_per_image = p->faces_per_image; f.face_offsets = p->face_offsets;
-    f.recs = w.recs; f.bins = w.bins; f.order_cnt = w.order_cnt; f.order_seg = w.order_seg; f.xs = w.xs; f.ys = w.ys; f.face_attr = p->face_attr;
+    f.total_faces = p->total_faces; f.zbuf = w.zbuf; f.big_count = w.big_count; f.big_list = w.big_list; f.tile_blocks = w.tile_blocks; f.wordmask = w.wordmask; f.fbox = w.fbox;
+    f.recs = w.recs; f.bins = w.bins; f.order_cnt = w.order_cnt; f.order_seg = w.order_seg; f.tile_desc = w.tile_desc; f.xs = w.xs; f.ys = w.ys; f.face_attr = p->face_attr;
     if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
     else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }
     {
@@ -275,9 +286,13 @@ int dibr_forward(const DibrPass* p, void* stream) {
         for (int g = 0; g < f.n_out; g++) {
             for (int c = 0; c < f.out_ch[g] && d < DIBR_MAX_ATTR_INTERNAL; c++, d++) {
                 f.chan_out[d] = f.out[g] + c; f.chan_stride[d] = f.out_ch[g]; f.chan_off[d] = plane + c;
+                f.chan_off32[d] = plane / (dibr::TILE * dibr::TILE) * 32 + c;
             }
             plane += f.out_ch[g] * dibr::TILE * dibr::TILE;
         }
+        f.vec_out = 1;
+        for (int g = 0; g < f.n_out; g++)
+            if (((uintptr_t)f.out[g] & 15u) != 0 || (((long long)p->width * f.out_ch[g]) & 3) != 0) f.vec_out = 0;
     }
     f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
     f.list_counts = w.list_counts; f.face_flags = w.face_flags; f.color_list = w.color_list; f.soft_list = w.soft_list;
@@ -295,7 +310,7 @@ int dibr_forward(const DibrPass* p, void* stream) {
         cudaError_t e = cudaMemsetAsync(p->out_min_ordered, 0xff, sizeof(uint32_t), (cudaStream_t)stream);
         if (e != cudaSuccess) return cuda_fail("dibr_forward (reset min)", (int)e);
     }
-    g_launches += 1;
+    g_launches += 2;           // coverage + tiles
     return cuda_fail("dibr_forward", dibr::launch_forward(f, (cudaStream_t)stream));
 }
 
@@ -313,7 +328,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     b.total_faces = p->total_faces; b.faces_per_image = p->faces_per_image; b.face_offsets = p->face_offsets;
     b.recs = w.recs; b.xs = w.xs; b.ys = w.ys; b.face_attr = p->face_attr;
     b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx;
-    b.list_counts = w.list_counts; b.color_list = w.color_list; b.soft_list = w.soft_list;
+    b.list_counts = w.list_counts; b.face_flags = (const unsigned char*)w.face_flags; b.color_list = w.color_list; b.soft_list = w.soft_list;
     if (p->num_outputs < 0 || p->num_outputs > DIBR_MAX_OUTPUTS) return fail("num_outputs=%d outside [0,%d]", p->num_outputs, DIBR_MAX_OUTPUTS);
     b.any_grad_im = 0;
     if (p->num_outputs == 0) {
@@ -333,7 +348,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     }
     b.grad_improb = p->grad_improb;
     b.grad_points2d = p->grad_points2d; b.grad_face_attr = p->grad_face_attr;
-    g_launches += 1;
+    g_launches += 2;           // work lists + faces
     return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream));
 }
 

@@ -20,31 +20,6 @@
 
 namespace dibr {
 
-// first column c in [0,W] with xs[c] >= x  (xs ascending)
-__device__ __forceinline__ int col_lower(const float* __restrict__ xs, int W, float x, float scale) {
-    const float e = ceilf((x * scale + (float)(W - 1)) * 0.5f);
-    int c = (int)fminf(fmaxf(e, 0.f), (float)W);
-    {   // the guess is almost always right: check both neighbours with loads issued together
-        const float a = (c > 0) ? __ldg(xs + c - 1) : -3.0e38f, b = (c < W) ? __ldg(xs + c) : 3.0e38f;
-        if (a < x && b >= x) return c;
-    }
-    while (c > 0 && xs[c - 1] >= x) c--;
-    while (c < W && xs[c] < x) c++;
-    return c;
-}
-// first row r in [0,H] with ys[r] < y  (ys descending)
-__device__ __forceinline__ int row_lower(const float* __restrict__ ys, int H, float y, float scale) {
-    const float e = floorf(((float)(H - 1) - y * scale) * 0.5f) + 1.0f;
-    int r = (int)fminf(fmaxf(e, 0.f), (float)H);
-    {
-        const float a = (r > 0) ? __ldg(ys + r - 1) : 3.0e38f, b = (r < H) ? __ldg(ys + r) : -3.0e38f;
-        if (a >= y && b < y) return r;
-    }
-    while (r > 0 && ys[r - 1] < y) r--;
-    while (r < H && ys[r] >= y) r++;
-    return r;
-}
-
 #ifndef DIBR_COLOR_LANES
 #define DIBR_COLOR_LANES 4        // measured on cfg2 (faces win ~13 pixels): 16 lanes 126 us, 8: 116, 4: 112, 2: 110, 1: 144 for the launch
 #endif
@@ -76,9 +51,9 @@ __device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
         const int f = g - (P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image);
         const size_t img = (size_t)b * H * W;
         const int32_t* __restrict__ idx = P.imidx + img;
-        const float sx = (float)W / (float)P.multiplier, sy = (float)H / (float)P.multiplier;
-        const int c0 = col_lower(P.xs, W, rec.xmin, sx), c1 = col_lower(P.xs, W, rec.xmax, sx);
-        const int r0 = row_lower(P.ys, H, rec.ymax, sy), r1 = row_lower(P.ys, H, rec.ymin, sy);
+        // pixel centres inside the face's bbox: the ranges the set-up kernel left in the record
+        const int c0 = (int)(rec.cols & 0xffffu), c1 = (int)(rec.cols >> 16);
+        const int r0 = (int)(rec.rows & 0xffffu), r1 = (int)(rec.rows >> 16);
         const int nc = c1 - c0, npx = nc * (r1 - r0);
         if (nc > 0 && npx > 0 && P.any_grad_im) {
             const FaceK fk = make_facek(rec);
@@ -173,10 +148,9 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
     const int32_t* __restrict__ idx = P.imidx + img;
     const float* __restrict__ gpr = P.grad_improb + img;
     const float* __restrict__ comp = P.imcomp + img;
-    const float sx = (float)W / (float)P.multiplier, sy = (float)H / (float)P.multiplier;
-    const float ex = P.expand_mul;
-    const int c0 = col_lower(P.xs, W, rec.xmin - ex, sx), c1 = col_lower(P.xs, W, rec.xmax + ex, sx);
-    const int r0 = row_lower(P.ys, H, rec.ymax + ex, sy), r1 = row_lower(P.ys, H, rec.ymin - ex, sy);
+    // pixel centres inside the expanded bbox (record, written by the set-up kernel)
+    const int c0 = (int)(rec.ecols & 0xffffu), c1 = (int)(rec.ecols >> 16);
+    const int r0 = (int)(rec.erows & 0xffffu), r1 = (int)(rec.erows >> 16);
     const int nc = c1 - c0, npx = nc * (r1 - r0);
     if (nc <= 0 || npx <= 0) return;
     const float mult = (float)P.multiplier;
@@ -289,6 +263,32 @@ __global__ void __launch_bounds__(256, (DMAX <= 8) ? DIBR_BWD_MIN_CTAS : 2) back
     }
 }
 
+// The work lists of the two bodies, compacted from the byte flags the forward left (faces that won a pixel / faces that
+// entered a soft product).  One counter atomic per CTA and list; the order of a list is arbitrary and no result depends
+// on it.
+__global__ void __launch_bounds__(256) build_lists_kernel(const BwdParams P)
+{
+    __shared__ int s_cnt[2][8], s_base[2];
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool fc = g < P.total_faces && P.face_flags[g] != 0;
+    const bool fs = g < P.total_faces && P.face_flags[(size_t)P.total_faces + g] != 0;
+    const unsigned bc = __ballot_sync(0xffffffffu, fc), bs = __ballot_sync(0xffffffffu, fs);
+    if (lane == 0) { s_cnt[0][warp] = __popc(bc); s_cnt[1][warp] = __popc(bs); }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) tot += s_cnt[threadIdx.x][w];
+        s_base[threadIdx.x] = tot ? atomicAdd(&P.list_counts[threadIdx.x], tot) : 0;
+    }
+    __syncthreads();
+    int oc = s_base[0], os = s_base[1];
+    for (int w = 0; w < warp; w++) { oc += s_cnt[0][w]; os += s_cnt[1][w]; }
+    const unsigned lt = (1u << lane) - 1u;
+    if (fc) P.color_list[oc + __popc(bc & lt)] = g;
+    if (fs) P.soft_list[os + __popc(bs & lt)] = g;
+}
+
 int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
 {
     if (P.total_faces <= 0) return 0;
@@ -299,6 +299,13 @@ int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
     if (e != cudaSuccess) return (int)e;
     const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
     if (!do_color && !do_soft) return 0;
+    if (forward_impl() != 2) {
+        e = cudaMemsetAsync(P.list_counts, 0, 2 * sizeof(int), stream);
+        if (e != cudaSuccess) return (int)e;
+        build_lists_kernel<<<(P.total_faces + 255) / 256, 256, 0, stream>>>(P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
     const int worst = (do_color ? (P.total_faces + (256 / GRP) - 1) / (256 / GRP) : 0) + (do_soft ? (P.total_faces + SOFT_GROUPS - 1) / SOFT_GROUPS : 0);
     const int grid = min(worst, DIBR_BWD_GRID);
     if (P.num_attr <= 4) backward_faces_kernel<4><<<grid, 256, 0, stream>>>(P, do_color, do_soft);

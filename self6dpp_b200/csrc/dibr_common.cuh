@@ -25,13 +25,17 @@ constexpr int BIGCAP = 32;          // deferred large faces per batch
 constexpr int BIG_AREA = DIBR_BIG_AREA;   // pixels of a face inside the tile above which the CTA cooperates
 static_assert(FWD_THREADS == TILE * TILE, "one pixel per thread");
 constexpr int MAX_IMAGE_SIDE = 16384;           // largest image side the ABI accepts
+constexpr int BIG_FACE_PIXELS = 512;            // bbox pixel centres above which a front face is rasterised by the whole grid
 
 // 64 B face record, written by the set-up kernels.
 struct __align__(16) FaceRec {
     float ax, ay, bx, by;           // 2D corners, already x multiplier
     float cx, cy, az, bz;           // third corner, view-space z of a and b
     float cz, nz, image, pad1;      // view-space z of c, z of the face normal (< 0: back face), image index (int bits)
-    float xmin, ymin, xmax, ymax;   // bbox of the 2D corners (rasterizer.py:49-52)
+    // pixel ranges, lo | hi << 16 (hi exclusive, both clamped to the image): the pixel centres inside the bbox of the 2D
+    // corners (rasterizer.py:49-52, half-open) and inside the expanded bbox (rasterizer.py:54-57).  All four are 0
+    // (empty) for a face with a non-finite corner.
+    unsigned int cols, rows, ecols, erows;
 };
 
 // float -> unsigned with the same ordering
@@ -89,6 +93,36 @@ __device__ __forceinline__ float pix_x(int w, int width, int multiplier) {
 }
 __device__ __forceinline__ float pix_y(int h, int height, int multiplier) {
     return (float)(1.0 * multiplier / height * (height - 2 * h - 1));
+}
+
+// first column c in [0,W] whose pixel centre pix_x(c) >= x.  Centre c sits at f == c; the fp32 guess is off by ~1e-5
+// columns (2e-6 |f| for the largest images), so only an x within `tol` of a centre is decided by the exact value.
+__device__ __forceinline__ int first_col_ge(float x, int W, int M) {
+    const float f = fmaf(x, 0.5f * (float)W / (float)M, 0.5f * (float)(W - 1));
+    if (!(f > -1.0f)) return 0;                   // left of everything (or NaN)
+    if (!(f < (float)W)) return W;
+    const float cf = ceilf(f);
+    int c = (int)cf;
+    const float d = cf - f, tol = 2e-3f + 2e-6f * fabsf(f);
+    if (d < tol || d > 1.0f - tol) {
+        const int k = min(max((int)rintf(f), 0), W - 1);
+        c = (pix_x(k, W, M) >= x) ? k : k + 1;
+    }
+    return min(max(c, 0), W);
+}
+// first row r in [0,H] whose pixel centre pix_y(r) < y  (centres descend: centre r sits at g == r)
+__device__ __forceinline__ int first_row_lt(float y, int H, int M) {
+    const float g = fmaf(-y, 0.5f * (float)H / (float)M, 0.5f * (float)(H - 1));
+    if (!(g > -1.0f)) return 0;                   // above everything (or NaN)
+    if (!(g < (float)H)) return H;
+    const float ff = floorf(g);
+    int r = (int)ff + 1;
+    const float d = g - ff, tol = 2e-3f + 2e-6f * fabsf(g);
+    if (d < tol || d > 1.0f - tol) {
+        const int k = min(max((int)rintf(g), 0), H - 1);
+        r = (pix_y(k, H, M) < y) ? k : k + 1;
+    }
+    return min(max(r, 0), H);
 }
 
 // Soft-silhouette distance of a pixel to a face: min over the 3 edges (perpendicular distance when

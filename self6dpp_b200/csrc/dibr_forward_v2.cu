@@ -178,7 +178,10 @@ __device__ int fill_list(FwdSmem& s, const FwdParams& P, int f_lo, int wpos, con
         unsigned int packed = 0u;
         if (i < lcount) {
             const float4* rp = reinterpret_cast<const float4*>(recs + s.lid[i]);
-            const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+            const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+            // bbox of the 2D corners (the record now carries pixel ranges instead): xmin ymin xmax ymax
+            const float4 r3 = make_float4(fminf(r0.x, fminf(r0.z, r1.x)), fminf(r0.y, fminf(r0.w, r1.y)),
+                                          fmaxf(r0.x, fmaxf(r0.z, r1.x)), fmaxf(r0.y, fmaxf(r0.w, r1.y)));
             s.c0[i] = r0;
             s.c1[i] = make_float2(r1.x, r1.y);
             if (raster) { s.u.ab.z[0][i] = r1.z; s.u.ab.z[1][i] = r1.w; s.u.ab.z[2][i] = r2.x; }

@@ -14,8 +14,19 @@ struct Workspace {
     FaceRec* recs;      // [total_faces]
     uint32_t* bins;     // per image, per 16x16 tile: bitmap over the image's faces (bit = face may reach the tile); layout in bin_words()
     size_t bins_bytes;
+    unsigned long long* zbuf;   // [batch*H*W] z-buffer of the forward: (orderable z << 32) | ~face, 0 = uncovered.  Directly after
+                                // the bins (one memset at set-up clears both); the forward leaves it all-zero again
+    size_t zbuf_bytes;
+    int* big_count;     // [1] faces on big_list (directly after order_cnt: same memset)
+    unsigned int* tile_blocks;  // [batch * tiles] bit k: some face's expanded pixel range meets 8x4 block k of the tile (after order_cnt: same memset)
+    unsigned char* wordmask;    // one byte per bitmap word (same layout as bins): bit k = some face of the word meets block k of the tile; directly
+                                // after the bins and before the z-buffer (same memset)
+    uint2* fbox;        // [total_faces] expanded pixel ranges (ecols, erows) of the records, packed for the soft phase's gathers
+    int* big_list;      // [total_faces] front faces with more than BIG_FACE_PIXELS pixel centres in their bbox
+    int big_cap;
     int* order_cnt;     // [ORDER_BUCKETS] tiles per cost bucket (bucket = ceil(listed faces / 32), capped)
     int* order_seg;     // [ORDER_BUCKETS, batch * tiles] tile ids of each bucket: the forward kernel works heaviest bucket first
+    int4* tile_desc;    // same shape: {tile id, first face of the image, bitmap words per tile, offset of the tile's words in bins}
     float* xs;          // [width]  pixel-centre x
     float* ys;          // [height] pixel-centre y
     float* pose_part;   // [num_instances * POSE_BLOCKS * 12] partial pose-gradient sums
@@ -24,8 +35,8 @@ struct Workspace {
     float* cam_proj;    // pose mode: [num_K, 16]
     int* list_counts;   // [2] entries in color_list / soft_list (+ padding), zeroed by dibr_forward
     unsigned int* pose_done;    // [num_instances] vertex blocks that have delivered their pose sums (zeroed by dibr_forward with the lists)
-    unsigned int* face_flags;   // [total_faces] bit0: won a pixel, bit1: evaluated for a soft pixel (zeroed by dibr_forward)
-    int* color_list;    // [total_faces] global face ids that won at least one pixel (arbitrary order)
+    unsigned int* face_flags;   // zeroed by dibr_forward.  Read as bytes: [0, F) face won a pixel, [F, 2F) face entered a soft product
+    int* color_list;    // [total_faces] global face ids that won at least one pixel (built from the flags by the backward, arbitrary order)
     int* soft_list;     // [total_faces] global face ids that entered at least one soft-silhouette product
     size_t bytes;
 };
@@ -60,6 +71,7 @@ struct SetupParams {
     int num_K;
     float q, qn;             // -(f+n)/(f-n), -2fn/(f-n)
     float expand_mul;        // expand * multiplier: the bins cover the EXPANDED bboxes
+    int fwd_impl;            // forward_impl(): the v4 forward needs the z-buffer cleared, block masks, packed ranges and the big-face list
     Workspace ws;
 };
 
@@ -68,10 +80,18 @@ struct FwdParams {
     float expand_mul;
     int faces_per_image;
     const int32_t* face_offsets;
+    int total_faces;
     const FaceRec* recs;
     const uint32_t* bins;
+    unsigned long long* zbuf;  // all-zero on entry and on exit
+    const int* big_count;
+    const int* big_list;
+    const unsigned int* tile_blocks;
+    const unsigned char* wordmask;
+    const uint2* fbox;
     const int* order_cnt;
     const int* order_seg;
+    const int4* tile_desc;
     const float* xs;           // [width], [height] pixel-centre tables
     const float* ys;
     const float* face_attr;
@@ -80,8 +100,10 @@ struct FwdParams {
     float* out[6];             // [batch,H,W,out_ch[g]]
     float* chan_out[DIBR_MAX_ATTR_INTERNAL];    // per attribute channel d: its output tensor, pre-offset by the channel's slot in the group
     int chan_stride[DIBR_MAX_ATTR_INTERNAL];    // floats per pixel of that tensor
+    int chan_off32[DIBR_MAX_ATTR_INTERNAL];     // channel d of lane l sits at chan_off32[d] + l * chan_stride[d] in a warp's 32-pixel transpose buffer
     int chan_off[DIBR_MAX_ATTR_INTERNAL];       // channel d of pixel p sits at chan_off[d] + p * chan_stride[d] in the tile's shared-memory copy
     unsigned min_mask;         // channels of the output group whose batch-global minimum is accumulated
+    int vec_out;               // every output group can be written with 16 B stores (aligned base, W * channels % 4 == 0)
     float* improb;
     float* imcomp;
     int32_t* imidx;
@@ -105,9 +127,10 @@ struct BwdParams {
     const float* improb;
     const float* imcomp;
     const int32_t* imidx;
-    const int* list_counts;
-    const int* color_list;
-    const int* soft_list;
+    int* list_counts;          // [0] colour list length, [1] soft list length
+    const unsigned char* face_flags;
+    int* color_list;
+    int* soft_list;
     const float* chan_grad[DIBR_MAX_ATTR_INTERNAL];   // per channel d: upstream gradient base (pre-offset) or null
     int chan_stride[DIBR_MAX_ATTR_INTERNAL];          // floats per pixel of the tensor that holds channel d
     int any_grad_im;
@@ -325,7 +348,8 @@ int launch_nnd_backward(const NndParams& P, cudaStream_t stream);
 int launch_setup_faces(const SetupParams& P, cudaStream_t stream);
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream);
 int launch_forward(const FwdParams& P, cudaStream_t stream);
-int launch_forward_v2(const FwdParams& P, cudaStream_t stream);      // previous design, kept for the A/B (DIBR_FWD_IMPL=2)
+int launch_forward_v2(const FwdParams& P, cudaStream_t stream);
+int forward_impl();               // 4 (current) or 2 (DIBR_FWD_IMPL=2: the round-1 kernel, which appends the work lists itself)      // previous design, kept for the A/B (DIBR_FWD_IMPL=2)
 int launch_backward_faces(const BwdParams& P, cudaStream_t stream);
 int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream);
 int launch_normal_map(const float* n, const float* mask, const unsigned int* min_ordered, float* out, long long npix, cudaStream_t stream);

@@ -25,50 +25,75 @@ __device__ __forceinline__ void write_tables(const SetupParams& P, int gtid) {
     else if (gtid < P.width + P.height) P.ws.ys[gtid - P.width] = pix_y(gtid - P.width, P.height, P.multiplier);
 }
 
-// Tile binning: set the face's bit in the bitmap of every 16x16 tile its EXPANDED bbox can reach (conservative: one
-// pixel of slack on every side).  Pixel column of x is x W/(2m) + (W-1)/2, pixel row of y is (H-1)/2 - y H/(2m)
-// (inverse of pix_x / pix_y).  Bitmaps instead of lists: OR is order independent, so the forward kernel reads the
-// faces of a tile in ascending order without any sort, and the result is the same run to run.
-__device__ __forceinline__ void bin_face(const SetupParams& P, int g, int b, float xmin, float ymin, float xmax, float ymax) {
-    const float ex = P.expand_mul;
-    const float sx = 0.5f * (float)P.width / (float)P.multiplier, sy = 0.5f * (float)P.height / (float)P.multiplier;
-    const float hw = 0.5f * (float)(P.width - 1), hh = 0.5f * (float)(P.height - 1);
-    const float lim = 1.0e6f;
-    const int cmin = (int)fminf(fmaxf(floorf(fmaf(xmin - ex, sx, hw)) - 1.0f, -lim), lim);
-    const int cmax = (int)fminf(fmaxf(ceilf(fmaf(xmax + ex, sx, hw)) + 1.0f, -lim), lim);
-    const int rmin = (int)fminf(fmaxf(floorf(fmaf(-(ymax + ex), sy, hh)) - 1.0f, -lim), lim);
-    const int rmax = (int)fminf(fmaxf(ceilf(fmaf(-(ymin - ex), sy, hh)) + 1.0f, -lim), lim);
-    if (cmax < 0 || rmax < 0 || cmin >= P.width || rmin >= P.height) return;
+// Tile binning: set the face's bit in the bitmap of every 16x16 tile that holds a pixel centre of its EXPANDED bbox
+// (exact: the pixel ranges come from first_col_ge / first_row_lt).  Bitmaps instead of lists: OR is order independent,
+// so the forward kernel reads the faces of a tile in ascending order without any sort, and the result is the same run
+// to run.
+__device__ __forceinline__ void bin_face(const SetupParams& P, int g, int b, int e0, int e1, int q0, int q1) {
+    if (e1 <= e0 || q1 <= q0) return;
     const int tiles_x = (P.width + TILE - 1) / TILE, tiles_y = (P.height + TILE - 1) / TILE;
-    const int tx0 = max(cmin, 0) / TILE, tx1 = min(cmax, P.width - 1) / TILE;
-    const int ty0 = max(rmin, 0) / TILE, ty1 = min(rmax, P.height - 1) / TILE;
+    const int tx0 = e0 / TILE, tx1 = (e1 - 1) / TILE;
+    const int ty0 = q0 / TILE, ty1 = (q1 - 1) / TILE;
     const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
     const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
     const int w0 = f_lo >> 5, nw = ((f_hi - 1) >> 5) - w0 + 1;
     uint32_t* img = P.ws.bins + (size_t)tiles_x * tiles_y * ((size_t)w0 + b) + ((g >> 5) - w0);
     const uint32_t bit = 1u << (g & 31);
-    for (int ty = ty0; ty <= ty1; ty++)
-        for (int tx = tx0; tx <= tx1; tx++) atomicOr(img + (size_t)(ty * tiles_x + tx) * nw, bit);
+    if (P.fwd_impl == 2) {                           // the round-1 forward only reads the bitmaps
+        for (int ty = ty0; ty <= ty1; ty++)
+            for (int tx = tx0; tx <= tx1; tx++) atomicOr(img + (size_t)(ty * tiles_x + tx) * nw, bit);
+        return;
+    }
+    unsigned int* tb = P.ws.tile_blocks + (size_t)b * tiles_x * tiles_y;
+    // per-word block masks: byte (word index) of the same layout as the bins, updated with 32-bit atomics
+    unsigned int* wm4 = reinterpret_cast<unsigned int*>(P.ws.wordmask);
+    const size_t wbase = (size_t)tiles_x * tiles_y * ((size_t)w0 + b) + ((g >> 5) - w0);
+    for (int ty = ty0; ty <= ty1; ty++) {
+        // 8x4 blocks of the tile the range meets: rows of blocks (4 pixel rows each) x two halves (8 pixel columns each)
+        const int rlo = max(q0 - ty * TILE, 0) >> 2, rhi = (min(q1 - ty * TILE, TILE) - 1) >> 2;
+        const unsigned rowbits = ((2u << (2 * rhi + 1)) - 1u) & ~((1u << (2 * rlo)) - 1u);         // both halves of block rows rlo..rhi
+        for (int tx = tx0; tx <= tx1; tx++) {
+            atomicOr(img + (size_t)(ty * tiles_x + tx) * nw, bit);
+            const unsigned halves = ((e0 < tx * TILE + 8) ? 0x55u : 0u) | ((e1 > tx * TILE + 8) ? 0xaau : 0u);
+            const unsigned m = rowbits & halves;
+            if ((__ldcg(tb + ty * tiles_x + tx) & m) != m) atomicOr(tb + ty * tiles_x + tx, m);
+            const size_t wi = wbase + (size_t)(ty * tiles_x + tx) * nw;
+            atomicOr(wm4 + (wi >> 2), m << ((wi & 3) * 8));
+        }
+    }
 }
 
 __device__ __forceinline__ void store_face(const SetupParams& P, int g, int b, float ax, float ay, float bx, float by,
                                            float cx, float cy, float az, float bz, float cz, float nz, bool active)
 {
-    float xmin = 0.f, ymin = 0.f, xmax = 0.f, ymax = 0.f;
-    bool ok = false;
-    if (active) {
-        xmin = fminf(ax, fminf(bx, cx)); xmax = fmaxf(ax, fmaxf(bx, cx));
-        ymin = fminf(ay, fminf(by, cy)); ymax = fmaxf(ay, fmaxf(by, cy));
-        // non-finite corners make the face invisible (torch.min/max would propagate the NaN)
-        ok = isfinite(ax) && isfinite(ay) && isfinite(bx) && isfinite(by) && isfinite(cx) && isfinite(cy);
-        if (!ok) { xmin = ymin = 3.0e38f; xmax = ymax = -3.0e38f; }
-        FaceRec r;
-        r.ax = ax; r.ay = ay; r.bx = bx; r.by = by; r.cx = cx; r.cy = cy;
-        r.az = az; r.bz = bz; r.cz = cz; r.nz = nz; r.image = __int_as_float(b); r.pad1 = 0.f;
-        r.xmin = xmin; r.ymin = ymin; r.xmax = xmax; r.ymax = ymax;
-        P.ws.recs[g] = r;
-        if (ok) bin_face(P, g, b, xmin, ymin, xmax, ymax);
+    if (!active) return;
+    FaceRec r;
+    r.ax = ax; r.ay = ay; r.bx = bx; r.by = by; r.cx = cx; r.cy = cy;
+    r.az = az; r.bz = bz; r.cz = cz; r.nz = nz; r.image = __int_as_float(b); r.pad1 = 0.f;
+    r.cols = r.rows = r.ecols = r.erows = 0u;
+    // non-finite corners make the face invisible (torch.min/max would propagate the NaN)
+    const bool ok = isfinite(ax) && isfinite(ay) && isfinite(bx) && isfinite(by) && isfinite(cx) && isfinite(cy);
+    int e0 = 0, e1 = 0, q0 = 0, q1 = 0;
+    if (ok) {
+        const float xmin = fminf(ax, fminf(bx, cx)), xmax = fmaxf(ax, fmaxf(bx, cx));     // rasterizer.py:49-52
+        const float ymin = fminf(ay, fminf(by, cy)), ymax = fmaxf(ay, fmaxf(by, cy));
+        const float ex = P.expand_mul;
+        const int W = P.width, H = P.height, M = P.multiplier;
+        const int c0 = first_col_ge(xmin, W, M), c1 = first_col_ge(xmax, W, M);
+        const int r0 = first_row_lt(ymax, H, M), r1 = first_row_lt(ymin, H, M);
+        e0 = first_col_ge(xmin - ex, W, M); e1 = first_col_ge(xmax + ex, W, M);            // rasterizer.py:54-57
+        q0 = first_row_lt(ymax + ex, H, M); q1 = first_row_lt(ymin - ex, H, M);
+        r.cols = (unsigned)c0 | ((unsigned)c1 << 16); r.rows = (unsigned)r0 | ((unsigned)r1 << 16);
+        r.ecols = (unsigned)e0 | ((unsigned)e1 << 16); r.erows = (unsigned)q0 | ((unsigned)q1 << 16);
+        // front faces with many pixel centres in their bbox are rasterised by the whole grid (coverage kernel, phase 2)
+        if (P.fwd_impl != 2 && nz >= 0.0f && (long long)(c1 - c0) * (r1 - r0) > BIG_FACE_PIXELS) {
+            const int slot = atomicAdd(P.ws.big_count, 1);
+            if (slot < P.ws.big_cap) P.ws.big_list[slot] = g;
+        }
     }
+    P.ws.recs[g] = r;
+    if (P.fwd_impl != 2) P.ws.fbox[g] = make_uint2(r.ecols, r.erows);
+    if (ok) bin_face(P, g, b, e0, e1, q0, q1);
 }
 
 __global__ void __launch_bounds__(256) setup_faces_kernel(SetupParams P)
@@ -262,6 +287,7 @@ __global__ void __launch_bounds__(32 * PLAN_TILES_PER_CTA) plan_tiles_kernel(Set
     __syncthreads();
     const int t = blockIdx.x * PLAN_TILES_PER_CTA + warp;
     int kb = -1, pos = 0, id = 0;
+    int4 desc = make_int4(0, 0, 0, 0);
     if (t < ntiles) {
         const int b = t / tiles, tl = t - b * tiles;
         const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
@@ -274,12 +300,16 @@ __global__ void __launch_bounds__(32 * PLAN_TILES_PER_CTA) plan_tiles_kernel(Set
         kb = min((cost + 31) >> 5, ORDER_BUCKETS - 1);
         const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
         id = (int)(((unsigned)b << 20) | ((unsigned)ty << 10) | (unsigned)tx);                 // forward: unpack_tile
+        desc = make_int4(id, f_lo, nw, (int)(words - P.ws.bins));
         if (lane == 0) pos = atomicAdd(&hist[kb], 1);
     }
     __syncthreads();
     if (threadIdx.x < ORDER_BUCKETS && hist[threadIdx.x] > 0) base[threadIdx.x] = atomicAdd(&P.ws.order_cnt[threadIdx.x], hist[threadIdx.x]);
     __syncthreads();
-    if (lane == 0 && kb >= 0) P.ws.order_seg[(size_t)kb * ntiles + base[kb] + pos] = id;
+    if (lane == 0 && kb >= 0) {
+        P.ws.order_seg[(size_t)kb * ntiles + base[kb] + pos] = id;
+        P.ws.tile_desc[(size_t)kb * ntiles + base[kb] + pos] = desc;
+    }
 }
 
 static inline int launch_plan(const SetupParams& P, cudaStream_t stream) {
@@ -295,8 +325,9 @@ static inline int setup_grid(const SetupParams& P) {
 
 int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
 {
-    // plan counters + tile bitmaps are adjacent in the workspace
-    cudaError_t e = cudaMemsetAsync(P.ws.order_cnt, 0, (size_t)((char*)P.ws.bins - (char*)P.ws.order_cnt) + P.ws.bins_bytes, stream);
+    // plan counters, tile bitmaps and the z-buffer are adjacent in the workspace
+    cudaError_t e = cudaMemsetAsync(P.ws.order_cnt, 0, P.fwd_impl == 2 ? (size_t)((char*)P.ws.wordmask - (char*)P.ws.order_cnt)
+                                                                      : (size_t)((char*)P.ws.zbuf - (char*)P.ws.order_cnt) + P.ws.zbuf_bytes, stream);
     if (e != cudaSuccess) return (int)e;
     setup_faces_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
     e = cudaGetLastError();
@@ -306,8 +337,9 @@ int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
 
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
 {
-    // plan counters + tile bitmaps are adjacent in the workspace
-    cudaError_t e = cudaMemsetAsync(P.ws.order_cnt, 0, (size_t)((char*)P.ws.bins - (char*)P.ws.order_cnt) + P.ws.bins_bytes, stream);
+    // plan counters, tile bitmaps and the z-buffer are adjacent in the workspace
+    cudaError_t e = cudaMemsetAsync(P.ws.order_cnt, 0, P.fwd_impl == 2 ? (size_t)((char*)P.ws.wordmask - (char*)P.ws.order_cnt)
+                                                                      : (size_t)((char*)P.ws.zbuf - (char*)P.ws.order_cnt) + P.ws.zbuf_bytes, stream);
     if (e != cudaSuccess) return (int)e;
     setup_meshes_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
     e = cudaGetLastError();
