@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define DIBR_ABI_VERSION 1
+#define DIBR_ABI_VERSION 2
 #define DIBR_MAX_ATTR 12 /* interpolated channels per pixel (the reference uses 4: rgb/xyz/normal + ones) */
 #define DIBR_MAX_OUTPUTS 6
 
@@ -201,8 +201,26 @@ typedef struct DibrStep {
     float *host_grad_pose;         /* pinned [num_instances, 12]: 9 of dL/dR then 3 of dL/dt per instance, or NULL */
     float *device_grad_pose;       /* [num_instances, 12] packed dL/dR | dL/dt on the device (always written when non-NULL);
                                       the D2H copy reads from it */
+    void *overlap;                 /* handle from dibr_overlap_create (a side stream + two events owned by the CALLER, one per
+                                      session / host thread), or NULL: both passes run one after the other in `stream` */
 } DibrStep;
 
+/* Side stream + fork/join events that let the teacher rasterisation run next to the student chain.  One handle per
+ * session (or per host thread that steps on a device): the library keeps no stream or event of its own, so two
+ * sessions stepping concurrently never share one.  Create and destroy with the session's device current. */
+int dibr_overlap_create(void **handle);
+int dibr_overlap_destroy(void *handle);
+
+/* The step in the two halves a training loop needs (the upstream gradients of the backward depend on the forward's
+ * images, self_engine_utils.py:541-558, 736-813):
+ *   dibr_render_forward   steps 1-3 above (H2D, student and teacher rasterisation, normal maps),
+ *   dibr_render_backward  steps 4-5 (backward of the student pass with student.grad_out[] / grad_improb, D2H of the
+ *                         pose gradients) on the forward's saved buffers; may be called again with other gradients.
+ * dibr_render_step = dibr_render_forward, then dibr_render_backward when run_backward != 0 (the student chain stays on
+ * the side stream throughout).  On every path, error returns included, `stream` has been made to wait for whatever was
+ * enqueued on the side stream. */
+int dibr_render_forward(const DibrStep *step, void *stream);
+int dibr_render_backward(const DibrStep *step, void *stream);
 int dibr_render_step(const DibrStep *step, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -29,3 +29,14 @@
 #undef EXP
 
 int dibr_oracle_abi_version(void) { return 1; }
+
+/* OpenMP threads the pixel loops use.  bench.py sets this explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers,
+ * which would silently turn the CPU arm into a single-thread run. */
+#ifdef _OPENMP
+#include <omp.h>
+void dibr_oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int dibr_oracle_get_threads(void) { return omp_get_max_threads(); }
+#else
+void dibr_oracle_set_threads(int n) { (void)n; }
+int dibr_oracle_get_threads(void) { return 1; }
+#endif

@@ -55,6 +55,7 @@ class DibrStep(ctypes.Structure):
         ("teacher_normal_in", _c_f32p), ("teacher_mask_in", _c_f32p), ("teacher_normal_out", _c_f32p),
         ("run_backward", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("host_grad_pose", _c_f32p), ("device_grad_pose", _c_f32p),
+        ("overlap", ctypes.c_void_p),
     ]
 
 
@@ -157,7 +158,7 @@ class DibrChamferReduce(ctypes.Structure):
 
 EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_device_count", "dibr_workspace_bytes",
            "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
-           "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_backproject_compact",
+           "dibr_backward_meshes", "dibr_normal_map", "dibr_render_step", "dibr_render_forward", "dibr_render_backward", "dibr_overlap_create", "dibr_overlap_destroy", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_backproject_compact",
            "dibr_backproject_compact_backward", "dibr_mask_loss_scratch_floats", "dibr_mask_loss_forward",
            "dibr_mask_loss_backward", "dibr_chamfer_reduce_forward", "dibr_chamfer_reduce_backward",
            "dibr_lab_loss_scratch_floats", "dibr_lab_loss_forward", "dibr_lab_loss_backward",
@@ -201,8 +202,13 @@ def load():
     lib.dibr_normal_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_longlong, ctypes.c_void_p]
     lib.dibr_normal_map.restype = ctypes.c_int
-    lib.dibr_render_step.argtypes = [ctypes.POINTER(DibrStep), ctypes.c_void_p]
-    lib.dibr_render_step.restype = ctypes.c_int
+    for fn in (lib.dibr_render_step, lib.dibr_render_forward, lib.dibr_render_backward):
+        fn.argtypes = [ctypes.POINTER(DibrStep), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    lib.dibr_overlap_create.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+    lib.dibr_overlap_create.restype = ctypes.c_int
+    lib.dibr_overlap_destroy.argtypes = [ctypes.c_void_p]
+    lib.dibr_overlap_destroy.restype = ctypes.c_int
     if lib.dibr_sizeof_step() != ctypes.sizeof(DibrStep):
         raise RuntimeError("DibrStep mirror out of date")
     for name in ("dibr_backproject_compact", "dibr_backproject_compact_backward"):
@@ -251,7 +257,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrNnd), ctypes.c_void_p]
         fn.restype = ctypes.c_int
-    if lib.dibr_abi_version() != 1:
+    if lib.dibr_abi_version() != 2:
         raise RuntimeError("libdibr_b200.so ABI version mismatch")
     if lib.dibr_sizeof_pass() != ctypes.sizeof(DibrPass):
         raise RuntimeError("DibrPass mirror out of date: C sizeof %d != ctypes %d"

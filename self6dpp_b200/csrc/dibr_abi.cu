@@ -5,7 +5,6 @@
 #include <cstring>
 
 #include "../../include/dibr_b200.h"
-#include <mutex>
 #include "dibr_internal.h"
 
 namespace {
@@ -655,57 +654,62 @@ int dibr_chamfer_reduce_backward(const DibrChamferReduce* p, void* stream) {
     return cuda_fail("dibr_chamfer_reduce_backward", dibr::launch_chamfer_reduce_backward(q, (cudaStream_t)stream));
 }
 
-// one side stream + fork/join events per device, created on first use and kept for the life of the process
-struct AuxStream { cudaStream_t stream; cudaEvent_t fork, join; };
-static AuxStream* aux_stream() {
-    static std::mutex mu;
-    static AuxStream slots[64];
-    static bool ready[64] = {false};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    if (!ready[dev]) {
-        AuxStream a;
-        int least = 0, greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        // the side stream carries the LONG chain (student forward + backward) at high priority; the short teacher chain stays on
-        // the caller's stream and fills in behind it
-        if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, greatest) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        slots[dev] = a;
-        ready[dev] = true;
-    }
-    return &slots[dev];
+// side stream + fork/join events of one session (dibr_overlap_create): owned by the caller, nothing process-global
+struct Overlap { cudaStream_t stream; cudaEvent_t fork, join; };
+
+int dibr_overlap_create(void** handle) {
+    if (!handle) return fail("overlap_create: null handle");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    Overlap* o = new Overlap();
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    // the side stream carries the LONG chain (student forward + backward) at high priority; the short teacher chain stays on
+    // the caller's stream and fills in behind it
+    cudaError_t e = cudaStreamCreateWithPriority(&o->stream, cudaStreamNonBlocking, greatest);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->join, cudaEventDisableTiming);
+    if (e != cudaSuccess) { delete o; return cuda_fail("overlap_create", (int)e); }
+    *handle = o;
+    return 0;
 }
 
-int dibr_render_step(const DibrStep* st, void* stream) {
-    if (!st) return fail("null DibrStep");
-    cudaStream_t cs = (cudaStream_t)stream;
-    if (st->staging_bytes > 0) {
-        if (!st->staging_host || !st->staging_device) return fail("render_step: staging buffers are null");
-        cudaError_t e = cudaMemcpyAsync(st->staging_device, st->staging_host, st->staging_bytes, cudaMemcpyHostToDevice, cs);
-        if (e != cudaSuccess) return cuda_fail("render_step H2D", (int)e);
+int dibr_overlap_destroy(void* handle) {
+    if (!handle) return 0;
+    Overlap* o = (Overlap*)handle;
+    cudaEventDestroy(o->fork); cudaEventDestroy(o->join); cudaStreamDestroy(o->stream);
+    delete o;
+    return 0;
+}
+
+namespace {
+// Fork the caller's stream into the session's side stream; the destructor joins again, so every return path of the entry
+// points below (errors included) leaves `cs` waiting for whatever was enqueued on the side stream.
+struct ForkJoin {
+    Overlap* o;
+    cudaStream_t cs;
+    int err;
+    ForkJoin(Overlap* o_, cudaStream_t cs_) : o(o_), cs(cs_), err(0) {
+        if (!o) return;
+        cudaError_t e = cudaEventRecord(o->fork, cs);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(o->stream, o->fork, 0);
+        if (e != cudaSuccess) { err = (int)e; o = nullptr; }
     }
+    ~ForkJoin() {
+        if (!o) return;
+        if (cudaEventRecord(o->join, o->stream) == cudaSuccess) cudaStreamWaitEvent(cs, o->join, 0);
+    }
+    void* side(void* fallback) const { return o ? (void*)o->stream : fallback; }
+};
+
+int render_forward_on(const DibrStep* st, void* stream, const ForkJoin& fj) {
     const DibrPass* passes[2] = {&st->student, &st->teacher};
     const float* nin[2] = {st->student_normal_in, st->teacher_normal_in};
     const float* nmask[2] = {st->student_mask_in, st->teacher_mask_in};
     float* nout[2] = {st->student_normal_out, st->teacher_normal_out};
-    // The teacher rasterisation depends on nothing the student pass or the backward produce (and vice versa).  The long
-    // chain (student set-up, forward, backward, pose-gradient read-back) goes to a high-priority side stream, forked
-    // after the staging copy; the teacher pass stays on the caller's stream and its CTAs fill the tails and stalls of the
-    // long chain.  The caller's stream waits for the side stream before the call returns, so for the caller everything
-    // is ordered in `stream` as before.
-    AuxStream* aux = (st->student.num_instances > 0 && st->teacher.num_instances > 0) ? aux_stream() : nullptr;
-    if (aux) {
-        cudaError_t e = cudaEventRecord(aux->fork, cs);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(aux->stream, aux->fork, 0);
-        if (e != cudaSuccess) return cuda_fail("render_step fork", (int)e);
-    }
     for (int k = 0; k < 2; k++) {
         const DibrPass* p = passes[k];
         if (p->num_instances <= 0) continue;
-        void* ks = (k == 0 && aux) ? (void*)aux->stream : stream;
+        void* ks = (k == 0) ? fj.side(stream) : stream;          // student chain on the side stream, teacher on the caller's
         if (int e = dibr_setup_meshes(p, ks)) return e;
         if (int e = dibr_forward(p, ks)) return e;
         if (nin[k]) {
@@ -713,27 +717,60 @@ int dibr_render_step(const DibrStep* st, void* stream) {
             if (int e = dibr_normal_map(nin[k], nmask[k], p->out_min_ordered, nout[k], (long long)p->batch * p->height * p->width, ks)) return e;
         }
     }
-    if (st->run_backward) {
-        const DibrPass* p = &st->student;
-        void* ls = aux ? (void*)aux->stream : stream;           // the student chain's stream
-        cudaStream_t lcs = (cudaStream_t)ls;
-        if (int e = dibr_backward_faces(p, ls)) return e;
-        if (st->device_grad_pose && (!p->grad_pose_R || !p->grad_pose_t)) return fail("render_step: pose-gradient buffers are null");
-        // the kernel's finalising block writes the [n,12] layout itself: no packing launch
-        if (int e = backward_meshes_impl(p, ls, st->device_grad_pose)) return e;
-        if (st->device_grad_pose) {
-            const int n = p->num_instances;
-            cudaError_t e = cudaSuccess;
-            if (st->host_grad_pose)
-                e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)n, cudaMemcpyDeviceToHost, lcs);
-            if (e != cudaSuccess) return cuda_fail("render_step pose gradients", (int)e);
-        }
+    return 0;
+}
+
+int render_backward_on(const DibrStep* st, void* ls) {
+    const DibrPass* p = &st->student;
+    if (int e = dibr_backward_faces(p, ls)) return e;
+    if (st->device_grad_pose && (!p->grad_pose_R || !p->grad_pose_t)) return fail("render_step: pose-gradient buffers are null");
+    // the kernel's finalising block writes the [n,12] layout itself: no packing launch
+    if (int e = backward_meshes_impl(p, ls, st->device_grad_pose)) return e;
+    if (st->device_grad_pose && st->host_grad_pose) {
+        cudaError_t e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)p->num_instances,
+                                        cudaMemcpyDeviceToHost, (cudaStream_t)ls);
+        if (e != cudaSuccess) return cuda_fail("render_step pose gradients", (int)e);
     }
-    if (aux) {
-        cudaError_t e = cudaEventRecord(aux->join, aux->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, aux->join, 0);
-        if (e != cudaSuccess) return cuda_fail("render_step join", (int)e);
+    return 0;
+}
+
+int render_upload(const DibrStep* st, cudaStream_t cs) {
+    if (st->staging_bytes > 0) {
+        if (!st->staging_host || !st->staging_device) return fail("render_step: staging buffers are null");
+        cudaError_t e = cudaMemcpyAsync(st->staging_device, st->staging_host, st->staging_bytes, cudaMemcpyHostToDevice, cs);
+        if (e != cudaSuccess) return cuda_fail("render_step H2D", (int)e);
     }
+    return 0;
+}
+}  // namespace
+
+// The teacher rasterisation depends on nothing the student pass or the backward produce (and vice versa).  The long
+// chain (student set-up, forward, backward, pose-gradient read-back) goes to the session's high-priority side stream,
+// forked after the staging copy; the teacher pass stays on the caller's stream and its CTAs fill the tails and stalls of
+// the long chain.  The caller's stream waits for the side stream before the call returns, so for the caller everything
+// is ordered in `stream` as before.
+int dibr_render_forward(const DibrStep* st, void* stream) {
+    if (!st) return fail("null DibrStep");
+    if (int e = render_upload(st, (cudaStream_t)stream)) return e;
+    const bool both = st->student.num_instances > 0 && st->teacher.num_instances > 0;
+    ForkJoin fj(both ? (Overlap*)st->overlap : nullptr, (cudaStream_t)stream);
+    if (fj.err) return cuda_fail("render_forward fork", fj.err);
+    return render_forward_on(st, stream, fj);
+}
+
+int dibr_render_backward(const DibrStep* st, void* stream) {
+    if (!st) return fail("null DibrStep");
+    return render_backward_on(st, stream);
+}
+
+int dibr_render_step(const DibrStep* st, void* stream) {
+    if (!st) return fail("null DibrStep");
+    if (int e = render_upload(st, (cudaStream_t)stream)) return e;
+    const bool both = st->student.num_instances > 0 && st->teacher.num_instances > 0;
+    ForkJoin fj(both ? (Overlap*)st->overlap : nullptr, (cudaStream_t)stream);
+    if (fj.err) return cuda_fail("render_step fork", fj.err);
+    if (int e = render_forward_on(st, stream, fj)) return e;
+    if (st->run_backward) return render_backward_on(st, fj.side(stream));       // the student chain's stream
     return 0;
 }
 

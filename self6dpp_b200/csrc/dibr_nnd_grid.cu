@@ -315,7 +315,15 @@ __global__ void __launch_bounds__(NND_T) nnd_query_kernel(NndParams P, const uns
 #ifdef DIBR_NND_STATS
     if (live && sub == 0) { atomicAdd(&g_nnd_stats[min(rr_stat, 7)], 1ull); atomicAdd(&g_nnd_stats[8], (unsigned long long)npts_stat); }
 #endif
-    if (live && sub == 0) { dist[j] = best; idx[j] = bi; }
+    if (live && sub == 0) {
+        // Non-finite input.  The exhaustive search (dibr_nnd.cu, nnd_cpu.cpp:17) starts from target 0 and replaces it only on
+        // 'd < best': when d(query, target 0) is NaN nothing ever replaces it, and when no distance is below 3.4e38 the
+        // loops above accepted nothing -- in both cases its answer is (d(query, target 0), 0).
+        const float* t0 = cloud_of(P, dir == 0 ? 1 : 0, b).xyz;
+        const float d0 = sqdist_exact(qx, qy, qz, t0[0], t0[1], t0[2]);
+        if (d0 != d0 || bi == 0x7fffffff) { best = d0; bi = 0; }
+        dist[j] = best; idx[j] = bi;
+    }
 }
 
 int launch_nnd_forward_grid(const NndParams& P, void* workspace, cudaStream_t stream)

@@ -254,16 +254,20 @@ def depth_bp_chamfer_loss(ren_depths, real_depths, Ks, distance_threshold=0.05, 
     if distance_threshold > 0:
         s1 = v1 & (dist1 < distance_threshold)
         s2 = v2 & (dist2 < distance_threshold)
-    mean1 = (dist1 * s1).sum(1) / s1.sum(1)                    # 0/0 = nan when nothing is selected, like torch.mean([])
-    mean2 = (dist2 * s2).sum(1) / s2.sum(1)
+    # A sample with an empty selection has mean = 0/0 = nan in the reference, which then skips it (:47-48).  Here the
+    # denominators are made safe BEFORE dividing and the skip is decided from the counts: a masked-out nan would still
+    # send 0 * inf = nan down the backward (into ren_depths, R, t and the network).
+    n1, n2 = s1.sum(1), s2.sum(1)
+    ok = (n1 > 0) & (n2 > 0)
+    mean1 = (dist1 * s1).sum(1) / n1.clamp(min=1)
+    mean2 = (dist2 * s2).sum(1) / n2.clamp(min=1)
     cur = mean1 + mean2
-    ok = ~torch.isnan(cur)                                     # the reference skips such samples (:47-48)
     num_valid = ok.sum().clamp(min=1)
     loss = torch.where(ok, cur, torch.zeros_like(cur)).sum() / num_valid
     loss_center = torch.zeros((), dtype=ren_depths.dtype, device=ren_depths.device)
     if center_lw > 0:
-        c_real = (real_pts * v1.unsqueeze(-1)).sum(1) / real_cnt.view(-1, 1)
-        c_rend = (rend_pts * v2.unsqueeze(-1)).sum(1) / rend_cnt.view(-1, 1)
+        c_real = (real_pts * v1.unsqueeze(-1)).sum(1) / real_cnt.view(-1, 1).clamp(min=1)
+        c_rend = (rend_pts * v2.unsqueeze(-1)).sum(1) / rend_cnt.view(-1, 1).clamp(min=1)
         per = (c_real - c_rend).abs().mean(1) * center_lw       # smooth_l1(beta=0, "mean") = mean |.|
         loss_center = torch.where(ok, per, torch.zeros_like(per)).sum() / num_valid
     return loss, loss_center

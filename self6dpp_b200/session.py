@@ -1,6 +1,8 @@
 """``RenderSession`` -- the render-and-compare step of Self6D++'s ``compute_self_loss_pose``
-(/root/reference/core/self6dpp/engine/self_engine_utils.py:426-447) behind ONE C-ABI call
-(``dibr_render_step``, include/dibr_b200.h) that takes HOST buffers.
+(/root/reference/core/self6dpp/engine/self_engine_utils.py:426-447) behind C-ABI calls that take HOST buffers
+(include/dibr_b200.h): ``forward()`` = ``dibr_render_forward`` (both rasterisations), then -- once the caller has
+turned the rendered images into upstream gradients (self_engine_utils.py:541-558, 736-813) -- ``backward()`` =
+``dibr_render_backward``; ``step()`` = both in one call (``dibr_render_step``) for gradients known beforehand.
 
 ``Renderer_dibr.render_batch`` is the drop-in for the reference's Python API; it pays ~0.4 ms of
 Python / torch.autograd bookkeeping per call, which is more than the kernels need.  A session
@@ -143,6 +145,11 @@ class RenderSession(object):
             st.teacher_mask_in = self.teacher.out["ones"].data_ptr()
             st.teacher_normal_out = self.teacher.normal_map.data_ptr()
         st.host_grad_pose, st.device_grad_pose = self.g_pose_host.data_ptr(), self.g_pose_dev.data_ptr()
+        # side stream + events for the student / teacher overlap: owned by THIS session (the library keeps none)
+        self._overlap = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dibr_overlap_create(ctypes.byref(self._overlap)), "dibr_overlap_create")
+        st.overlap = self._overlap
         self.st = st
         self._ar = np.arange(B)
         self._keep = None
@@ -153,11 +160,16 @@ class RenderSession(object):
         o, n = self.off[name]
         self._h_f32[o:o + n] = np.asarray(arr, dtype=np.float32).reshape(-1)
 
-    def step(self, Rs, ts, Ks, models, teacher_Rs=None, teacher_ts=None, grad_color=None, grad_prob=None,
-             grad_depth=None, backward=True, upload=True, download=True):
-        """Rs [B,3,3], ts [B,3], Ks [B,3,3] (+ teacher pose): HOST arrays.  grad_*: DEVICE tensors (dL/dcolor
-        [B,H,W,3], dL/dprob [B,H,W], dL/ddepth [B,H,W]) or None.  Returns the dict of persistent output tensors;
-        call ``synchronize()`` before reading ``grad_pose`` (pinned [B,12]: dL/dR then dL/dt)."""
+    def __del__(self):
+        try:
+            if getattr(self, "_overlap", None):
+                self.lib.dibr_overlap_destroy(self._overlap)
+                self._overlap = None
+        except Exception:
+            pass
+
+    def _stage_inputs(self, Rs, ts, Ks, models, teacher_Rs, teacher_ts, upload):
+        """poses / intrinsics / instance table -> pinned staging block; returns whether it must be uploaded"""
         B = self.B
         assert len(models) == B
         slots = np.fromiter((self.model_slot[id(m)] for m in models), dtype=np.int64, count=B)
@@ -193,7 +205,10 @@ class RenderSession(object):
         st = self.st
         st.student.total_faces = total
         st.teacher.total_faces = total
-        sp = st.student
+        return upload
+
+    def _set_grads(self, grad_color, grad_prob, grad_depth):
+        sp = self.st.student
         keep = []
         grads = {"color": grad_color, "depth": grad_depth}
         for g, key in enumerate(self.student.keys):
@@ -211,6 +226,35 @@ class RenderSession(object):
         else:
             sp.grad_improb = None
         self._keep = keep
+
+    def forward(self, Rs, ts, Ks, models, teacher_Rs=None, teacher_ts=None, upload=True):
+        """Rs [B,3,3], ts [B,3], Ks [B,3,3] (+ teacher pose): HOST arrays.  Renders the student and the teacher pass and
+        returns the dict of persistent output tensors; everything ``backward`` needs stays resident."""
+        st = self.st
+        upload = self._stage_inputs(Rs, ts, Ks, models, teacher_Rs, teacher_ts, upload)
+        st.staging_bytes = 4 * self.stage_words if upload else 0       # upload=False: inputs already resident
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dibr_render_forward(ctypes.byref(st), _stream(self.device)), "dibr_render_forward")
+        return self.outputs()
+
+    def backward(self, grad_color=None, grad_prob=None, grad_depth=None, download=True):
+        """grad_*: DEVICE tensors (dL/dcolor [B,H,W,3], dL/dprob [B,H,W], dL/ddepth [B,H,W]) or None, usually computed from
+        ``forward``'s images.  Runs the backward of the student pass; ``grad_pose`` (pinned [B,12]: dL/dR then dL/dt) is
+        valid after ``synchronize()``, ``g_pose_dev`` holds the same on the device.  May be called again with other gradients."""
+        st = self.st
+        self._set_grads(grad_color, grad_prob, grad_depth)
+        st.host_grad_pose = self.g_pose_host.data_ptr() if download else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dibr_render_backward(ctypes.byref(st), _stream(self.device)), "dibr_render_backward")
+        return self.g_pose_dev
+
+    def step(self, Rs, ts, Ks, models, teacher_Rs=None, teacher_ts=None, grad_color=None, grad_prob=None,
+             grad_depth=None, backward=True, upload=True, download=True):
+        """``forward`` and ``backward`` in ONE call (dibr_render_step), for upstream gradients that do not depend on this
+        step's images.  Returns the dict of persistent output tensors; call ``synchronize()`` before reading ``grad_pose``."""
+        st = self.st
+        upload = self._stage_inputs(Rs, ts, Ks, models, teacher_Rs, teacher_ts, upload)
+        self._set_grads(grad_color, grad_prob, grad_depth)
         st.run_backward = 1 if backward else 0
         st.staging_bytes = 4 * self.stage_words if upload else 0       # upload=False: inputs already resident
         st.host_grad_pose = self.g_pose_host.data_ptr() if download else None

@@ -26,7 +26,7 @@ def declared_symbols():
 def test_header_declares_something():
     names = declared_symbols()
     assert len(names) >= 16, names
-    for must in ("dibr_forward", "dibr_backward_meshes", "dibr_render_step", "dibr_nnd_forward"):
+    for must in ("dibr_forward", "dibr_backward_meshes", "dibr_render_step", "dibr_render_forward", "dibr_render_backward", "dibr_nnd_forward"):
         assert must in names
 
 
@@ -46,7 +46,7 @@ def test_no_undeclared_dibr_exports():
     path = _lib.lib_path() if hasattr(_lib, "lib_path") else os.path.join(ROOT, "self6dpp_b200", "lib", "libdibr_b200.so")
     out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("dibr_")}
-    extra = exported - set(declared_symbols()) - {"dibr_debug_phase_cycles"}
+    extra = exported - set(declared_symbols()) - {"dibr_debug_phase_cycles", "dibr_debug_item_cycles"}
     assert not extra, extra
 
 
@@ -54,7 +54,7 @@ def test_struct_size_handshake():
     lib = _lib.load()
     assert lib.dibr_sizeof_pass() == ctypes.sizeof(_lib.DibrPass)
     assert lib.dibr_sizeof_step() == ctypes.sizeof(_lib.DibrStep)
-    assert lib.dibr_abi_version() >= 1
+    assert lib.dibr_abi_version() == 2
 
 
 def test_validation_runs_before_any_cuda_call():

@@ -65,6 +65,21 @@ def test_depth_bp_chamfer_loss_matches_reference_golden():
     assert err < 1e-5, err
 
 
+def test_chamfer_loss_with_an_empty_sample_has_finite_gradients():
+    """A sample whose rendered depth is all zero has no points: the reference skips it (depth_bp_chamfer_loss.py:47-48) and so
+    it must contribute NO gradient -- in particular no 0 * inf = NaN from a masked-out mean (centre term on)."""
+    from self6dpp_b200.nndistance import depth_bp_chamfer_loss
+    d = np.load(GOLD)
+    ren0 = torch.tensor(d["ren"], device=DEV)
+    ren0[0] = 0.0                                  # sample 0 renders nothing
+    ren = ren0.clone().requires_grad_(True)
+    loss, loss_c = depth_bp_chamfer_loss(ren, torch.tensor(d["real"], device=DEV), torch.tensor(d["K"], device=DEV), 0.05, 0.5)
+    (loss + loss_c).backward()
+    assert torch.isfinite(loss) and torch.isfinite(loss_c)
+    assert torch.isfinite(ren.grad).all()
+    assert float(ren.grad[0].abs().max()) == 0.0 and float(ren.grad[1:].abs().max()) > 0.0
+
+
 def test_rendered_depth_feeds_the_chamfer_loss():
     """end of the chain the reference builds in compute_self_loss_pose: rendered depth -> chamfer loss -> dL/dR, dL/dt"""
     from self6dpp_b200 import Renderer_dibr, synth
@@ -111,7 +126,7 @@ def _both(x1, c1, x2, c2, g1, g2):
     return outs
 
 
-@pytest.mark.parametrize("case", ["surfaces", "far_apart", "duplicates_and_lines", "tiny_and_empty", "crowd"])
+@pytest.mark.parametrize("case", ["surfaces", "far_apart", "duplicates_and_lines", "tiny_and_empty", "crowd", "non_finite"])
 def test_grid_search_is_bit_identical_to_the_exhaustive_search(case):
     g = torch.Generator().manual_seed(hash(case) % 1000)
     B, S1, S2 = 3, 4000, 5000
@@ -135,13 +150,20 @@ def test_grid_search_is_bit_identical_to_the_exhaustive_search(case):
     elif case == "tiny_and_empty":
         c1 = torch.tensor([1, 0, 3], dtype=torch.int32)
         c2 = torch.tensor([2, 7, 0], dtype=torch.int32)
+    elif case == "non_finite":                    # nnd_cpu.cpp:17 starts from target 0 and only ever replaces it on 'd < best'
+        x1[0, 7] = float("nan")                   # a NaN query: every distance is NaN -> (NaN, 0)
+        x1[0, 9, 2] = float("inf")                # an infinite query: every distance is inf -> (inf, 0)
+        x2[1, 0, 0] = float("nan")                # target 0 is NaN: d(q, 0) = NaN sticks for every query of the sample
+        x2[2, 17] = float("nan")                  # a NaN target elsewhere is simply never the nearest
     elif case == "crowd":                         # thousands of queries share one nearest neighbour (backward fallback)
         x2[0, :, :] = x2[0, :, :] * 0.001 + torch.tensor([0.3, 0.3, 1.5])
         x2[1, 10:] = x2[1, 3]
     g1, g2 = torch.randn(B, S1, generator=g).to(DEV), torch.randn(B, S2, generator=g).to(DEV)
     a, e = _both(x1.to(DEV), c1.to(DEV), x2.to(DEV), c2.to(DEV), g1, g2)
     for k, name in enumerate(("dist1", "dist2", "idx1", "idx2", "grad1", "grad2")):
-        assert torch.equal(a[k], e[k]), f"{case}: {name} differs at {int((a[k] != e[k]).sum())} entries"
+        same = (a[k] == e[k]) | ((a[k] != a[k]) & (e[k] != e[k]))                 # NaN == NaN for this comparison
+        assert bool(same.all()), f"{case}: {name} differs at {int((~same).sum())} entries"
+    assert int(a[2].min()) >= 0 and int(a[2].max()) < S2 and int(a[3].min()) >= 0 and int(a[3].max()) < S1, "indices stay inside the clouds"
 
 
 def test_backproject_compact_equals_the_torch_expressions():
