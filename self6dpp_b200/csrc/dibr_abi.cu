@@ -39,7 +39,7 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
         w.tile_desc = (int4*)take(sizeof(int4) * dibr::ORDER_BUCKETS * ntiles);
         w.big_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
         w.big_cap = p->total_faces;
-        w.order_cnt = (int*)take(sizeof(int) * 2 * dibr::ORDER_BUCKETS);   // counters, then the bins, then the z-buffer: one memset clears all three
+        w.order_cnt = (int*)take(sizeof(int) * 4 * dibr::ORDER_BUCKETS);   // counters (+ the plan summary), then the bins, then the z-buffer: one memset clears all
         w.big_count = w.order_cnt ? w.order_cnt + dibr::ORDER_BUCKETS : nullptr;
         w.tile_blocks = (unsigned int*)take(sizeof(unsigned int) * ntiles);
     }
@@ -61,6 +61,7 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     w.face_flags = (unsigned int*)take(sizeof(unsigned int) * (size_t)p->total_faces);   // directly after list_counts: one memset
     w.color_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
     w.soft_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
+    w.open8 = (unsigned char*)take((size_t)p->batch * p->height * ((p->width + 7) / 8));
     w.bytes = off;
     return w;
 }
@@ -294,7 +295,7 @@ int dibr_forward(const DibrPass* p, void* stream) {
             if (((uintptr_t)f.out[g] & 15u) != 0 || (((long long)p->width * f.out_ch[g]) & 3) != 0) f.vec_out = 0;
     }
     f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
-    f.list_counts = w.list_counts; f.face_flags = w.face_flags; f.color_list = w.color_list; f.soft_list = w.soft_list;
+    f.list_counts = w.list_counts; f.face_flags = w.face_flags; f.color_list = w.color_list; f.soft_list = w.soft_list; f.open8 = w.open8;
     {
         const size_t nbytes = (size_t)((char*)w.color_list - (char*)w.list_counts);
         cudaError_t e = cudaMemsetAsync(w.list_counts, 0, nbytes, (cudaStream_t)stream);
@@ -327,7 +328,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     b.total_faces = p->total_faces; b.faces_per_image = p->faces_per_image; b.face_offsets = p->face_offsets;
     b.recs = w.recs; b.xs = w.xs; b.ys = w.ys; b.face_attr = p->face_attr;
     b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx;
-    b.list_counts = w.list_counts; b.face_flags = (const unsigned char*)w.face_flags; b.color_list = w.color_list; b.soft_list = w.soft_list;
+    b.list_counts = w.list_counts; b.face_flags = (const unsigned char*)w.face_flags; b.color_list = w.color_list; b.soft_list = w.soft_list; b.open8 = w.open8;
     if (p->num_outputs < 0 || p->num_outputs > DIBR_MAX_OUTPUTS) return fail("num_outputs=%d outside [0,%d]", p->num_outputs, DIBR_MAX_OUTPUTS);
     b.any_grad_im = 0;
     if (p->num_outputs == 0) {

@@ -21,7 +21,7 @@
 namespace dibr {
 
 #ifndef DIBR_COLOR_LANES
-#define DIBR_COLOR_LANES 4        // measured on cfg2 (faces win ~13 pixels): 16 lanes 126 us, 8: 116, 4: 112, 2: 110, 1: 144 for the launch
+#define DIBR_COLOR_LANES 8        // lanes per face (rows of its bbox per turn)
 #endif
 constexpr int GRP = DIBR_COLOR_LANES;     // lanes per face in the colour part
 
@@ -37,7 +37,8 @@ __device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
     const bool active = gi < nlist;
     const int D = P.num_attr;
     const int W = P.width, H = P.height;
-    const unsigned full = 0xffffffffu;
+    const int shift = (tid & 31) & ~(GRP - 1);                              // first lane of the group inside its warp
+    const unsigned full = (GRP == 32) ? 0xffffffffu : (((1u << GRP) - 1u) << shift);
 
     float acc[3 * DMAX];
 #pragma unroll
@@ -54,37 +55,72 @@ __device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
         // pixel centres inside the face's bbox: the ranges the set-up kernel left in the record
         const int c0 = (int)(rec.cols & 0xffffu), c1 = (int)(rec.cols >> 16);
         const int r0 = (int)(rec.rows & 0xffffu), r1 = (int)(rec.rows >> 16);
-        const int nc = c1 - c0, npx = nc * (r1 - r0);
-        if (nc > 0 && npx > 0 && P.any_grad_im) {
+        if (c1 > c0 && r1 > r0 && P.any_grad_im) {
             const FaceK fk = make_facek(rec);
-            const unsigned nc_magic = (unsigned)((0x100000000ull + (unsigned)nc - 1ull) / (unsigned)nc);   // ceil(2^32 / nc)
-            const bool magic_ok = (nc > 1) && ((unsigned long long)npx * (unsigned)nc < 0xffffffffull);
-            for (int i = gl; i < npx; i += GRP) {
-                const int rr = magic_ok ? (int)__umulhi((unsigned)i, nc_magic) : i / nc;
-                const int r = r0 + rr, c = c0 + (i - rr * nc);
-                const size_t pix = (size_t)r * W + c;
-                if (idx[pix] != f + 1) continue;
-                float w0, w1, w2;
-                bary(fk, P.xs[c], P.ys[r], w0, w1, w2);
+            // Lane = pixel row of the bbox: a mask of the pixels this face won (about a fifth of the bbox), then the
+            // (row, column) pairs of the group are numbered by a prefix sum and dealt out evenly, one per lane and turn:
+            // the per-pixel work (weights, gradient loads, 3 D fused multiply-adds) runs with every lane busy.  Which lane
+            // adds which pixel depends on the masks alone and the lanes are combined by a fixed tree: bit-reproducible.
+            for (int rb = r0; rb < r1; rb += GRP) {
+                const int r = rb + gl;
+                for (int cbase = c0; cbase < c1; cbase += 32) {
+                    unsigned m = 0u;
+                    if (r < r1) {
+                        const int32_t* __restrict__ ir = idx + (size_t)r * W + cbase;
+                        const int ncol = min(32, c1 - cbase);
+                        for (int k = 0; k < ncol; k++) m |= (ir[k] == f + 1) ? (1u << k) : 0u;
+                    }
+                    const int cnt = __popc(m);
+                    int incl = cnt;
 #pragma unroll
-                for (int d = 0; d < DMAX; d++) {
-                    if (d < D && P.chan_grad[d]) {
-                        const float gv = __ldg(P.chan_grad[d] + (img + pix) * (size_t)P.chan_stride[d]);
-                        acc[0 * DMAX + d] = fmaf(gv, w0, acc[0 * DMAX + d]);
-                        acc[1 * DMAX + d] = fmaf(gv, w1, acc[1 * DMAX + d]);
-                        acc[2 * DMAX + d] = fmaf(gv, w2, acc[2 * DMAX + d]);
+                    for (int o = 1; o < GRP; o <<= 1) {
+                        const int t = __shfl_up_sync(full, incl, o, GRP);
+                        if (gl >= o) incl += t;
+                    }
+                    const int total = __shfl_sync(full, incl, GRP - 1, GRP);
+                    for (int jb = 0; jb < total; jb += GRP) {
+                        const int jq = jb + gl;
+                        int src = 0;                            // lanes whose running count is <= jq: the lane that holds pair jq
+#pragma unroll
+                        for (int st = GRP / 2; st >= 1; st >>= 1) {
+                            const int v = __shfl_sync(full, incl, min(src + st - 1, GRP - 1), GRP);
+                            if (v <= jq) src += st;
+                        }
+                        src = min(src, GRP - 1);
+                        const unsigned ms = __shfl_sync(full, m, src, GRP);
+                        const int before = __shfl_sync(full, incl - cnt, src, GRP);
+                        if (jq < total) {
+                            const int rr = rb + src, c = cbase + (int)__fns(ms, 0u, jq - before + 1);
+                            const size_t pix = (size_t)rr * W + c;
+                            float w0, w1, w2;
+                            bary(fk, P.xs[c], P.ys[rr], w0, w1, w2);
+#pragma unroll
+                            for (int d = 0; d < DMAX; d++) {
+                                if (d < D && P.chan_grad[d]) {
+                                    const float gv = __ldg(P.chan_grad[d] + (img + pix) * (size_t)P.chan_stride[d]);
+                                    acc[0 * DMAX + d] = fmaf(gv, w0, acc[0 * DMAX + d]);
+                                    acc[1 * DMAX + d] = fmaf(gv, w1, acc[1 * DMAX + d]);
+                                    acc[2 * DMAX + d] = fmaf(gv, w2, acc[2 * DMAX + d]);
+                                }
+                            }
+                        }
                     }
                 }
             }
         }
     }
-    // fixed-tree reduction over the lanes of the face
+    // fixed-tree reduction over the lanes of the face (channels without an upstream gradient stay zero: skipped)
 #pragma unroll
-    for (int i = 0; i < 3 * DMAX; i++) {
-        float v = acc[i];
+    for (int d = 0; d < DMAX; d++) {
+        if (d < D && P.chan_grad[d]) {
 #pragma unroll
-        for (int o = GRP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
-        acc[i] = v;
+            for (int i = 0; i < 3; i++) {
+                float v = acc[i * DMAX + d];
+#pragma unroll
+                for (int o = GRP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o, GRP);
+                acc[i * DMAX + d] = v;
+            }
+        }
     }
     if (!active || gl != 0) return;
     // dL/dattr is acc itself; dL/dP follows from it (see the header comment)
@@ -121,17 +157,14 @@ __device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
             if (d < D) gao[i * D + d] = acc[i * DMAX + d];
 }
 
-// ---- soft part: one warp per face that entered at least one soft-silhouette product -------------------------------
-// The warp walks the pixel centres of the expanded bbox 32 at a time, keeps (ballot compaction, ascending pixel
-// order) the uncovered pixels that counted this face, and evaluates them 32 at a time with every lane busy.
-constexpr int SOFT_Q = 64;
+// ---- soft part: one group of lanes per face that entered at least one soft-silhouette product ----------------------
 #ifndef DIBR_SOFT_LANES
 #define DIBR_SOFT_LANES 16
 #endif
 constexpr int SOFT_LANES = DIBR_SOFT_LANES;          // lanes per face: a face has ~12 contributing pixels out of ~80 scanned,
 constexpr int SOFT_GROUPS = 256 / SOFT_LANES;        // so a full warp per face leaves most lanes idle in the evaluation
 static_assert(SOFT_LANES == 8 || SOFT_LANES == 16 || SOFT_LANES == 32, "a sub-warp group");
-__device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, int (*queue)[SOFT_Q])
+__device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid)
 {
     const int tid = threadIdx.x;
     const int grp = tid / SOFT_LANES, lane = tid % SOFT_LANES;          // lane = position inside the group
@@ -158,15 +191,7 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
     const float sentinel = 4.0f * mult * mult;
     const float px[3] = {rec.ax, rec.bx, rec.cx}, py[3] = {rec.ay, rec.by, rec.cy};
     float gp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int* q = queue[grp];
-    int qn = 0;
-
-    const unsigned nc_magic = (unsigned)((0x100000000ull + (unsigned)nc - 1ull) / (unsigned)nc);   // ceil(2^32 / nc)
-    const bool magic_ok = (nc > 1) && ((unsigned long long)npx * (unsigned)nc < 0xffffffffull);       // exact for i < 2^32 / nc
-    auto div_nc = [&](int i) { return magic_ok ? (int)__umulhi((unsigned)i, nc_magic) : i / nc; };
-    auto evaluate = [&](int i) {
-        const int rr = div_nc(i);
-        const int r = r0 + rr, c = c0 + (i - rr * nc);
+    auto evaluate = [&](int r, int c) {
         const size_t pix = (size_t)r * W + c;
         const float x0 = P.xs[c], y0 = P.ys[r];
         const SoftHit h = soft_distance(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, x0, y0, sentinel);
@@ -201,30 +226,53 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
         }
     };
 
-    for (int base = 0; base < npx; base += SOFT_LANES) {
-        const int i = base + lane;
-        bool take = false;
-        if (i < npx) {
-            const int rr = div_nc(i);
-            const int v = idx[(size_t)(r0 + rr) * W + c0 + (i - rr * nc)];
-            take = !(v > 0 || (v < 0 && f + 1 > -v));        // uncovered and this face is within the first K
-        }
-        const unsigned bal = __ballot_sync(full, take) >> shift;
-        if (take) q[qn + __popc(bal & ((1u << lane) - 1u))] = i;
-        qn += __popc(bal);
-        __syncwarp(full);
-        if (qn >= SOFT_LANES) {
-            evaluate(q[lane]);
-            __syncwarp(full);
-            const int rest = qn - SOFT_LANES;
-            const int moved = (lane < rest) ? q[SOFT_LANES + lane] : 0;
-            __syncwarp(full);
-            if (lane < rest) q[lane] = moved;
-            qn = rest;
-            __syncwarp(full);
+    // The forward left one bit per pixel ("uncovered").  Lane = pixel row of the expanded range: it reads its row 32 pixels
+    // per word and touches imidx only where the bit is set (a face has ~12 contributing pixels among the ~80 of its range).
+    // The surviving (row, column) pairs of the group are then numbered by a prefix sum and dealt out evenly, one per lane
+    // and turn.  Which lane adds which pixel is a function of the masks alone and the lanes are combined by a fixed tree:
+    // bit-reproducible.
+    const int wb = (W + 7) >> 3;
+    const unsigned char* __restrict__ orow = P.open8 + (size_t)b * H * wb;
+    for (int rb = r0; rb < r1; rb += SOFT_LANES) {
+        const int r = rb + lane;
+        for (int cbase = c0 & ~7; cbase < c1; cbase += 32) {
+            unsigned m = 0u;
+            if (r < r1) {
+                const unsigned char* __restrict__ ob = orow + (size_t)r * wb + (cbase >> 3);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (cbase + 8 * k < c1 && (cbase >> 3) + k < wb) m |= (unsigned)__ldg(ob + k) << (8 * k);
+                const int lo = max(c0 - cbase, 0), hi = min(c1 - cbase, 32);
+                m &= ((hi >= 32) ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                for (unsigned t = m; t; t &= t - 1) {             // uncovered: keep the pixels where this face is within the first K
+                    const int bit = __ffs(t) - 1;
+                    const int v = idx[(size_t)r * W + cbase + bit];
+                    if (!(v == 0 || f + 1 <= -v)) m &= ~(1u << bit);
+                }
+            }
+            const int cnt = __popc(m);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < SOFT_LANES; o <<= 1) {
+                const int t = __shfl_up_sync(full, incl, o, SOFT_LANES);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(full, incl, SOFT_LANES - 1, SOFT_LANES);
+            for (int jb = 0; jb < total; jb += SOFT_LANES) {
+                const int jq = jb + lane;
+                int src = 0;                                    // lanes whose running count is <= jq: the lane that holds pair jq
+#pragma unroll
+                for (int st = SOFT_LANES / 2; st >= 1; st >>= 1) {
+                    const int v = __shfl_sync(full, incl, min(src + st - 1, SOFT_LANES - 1), SOFT_LANES);
+                    if (v <= jq) src += st;
+                }
+                src = min(src, SOFT_LANES - 1);
+                const unsigned ms = __shfl_sync(full, m, src, SOFT_LANES);
+                const int before = __shfl_sync(full, incl - cnt, src, SOFT_LANES);
+                if (jq < total) evaluate(rb + src, cbase + (int)__fns(ms, 0u, jq - before + 1));
+            }
         }
     }
-    if (lane < qn) evaluate(q[lane]);
     // fixed-tree reduction over the group, then add to the face's six slots
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -253,13 +301,12 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid, 
 template <int DMAX>
 __global__ void __launch_bounds__(256, (DMAX <= 8) ? DIBR_BWD_MIN_CTAS : 2) backward_faces_kernel(const __grid_constant__ BwdParams P, int do_color, int do_soft)
 {
-    __shared__ int queue[SOFT_GROUPS][SOFT_Q];
     const int cbn = do_color ? (P.list_counts[0] + (256 / GRP) - 1) / (256 / GRP) : 0;
     const int sbn = do_soft ? (P.list_counts[1] + SOFT_GROUPS - 1) / SOFT_GROUPS : 0;
     for (int it = blockIdx.x; it < cbn + sbn; it += gridDim.x) {
         __syncwarp();                        // lanes leave the bodies at different points
         if (it < cbn) backward_color_body<DMAX>(P, it);
-        else backward_soft_body(P, it - cbn, queue);
+        else backward_soft_body(P, it - cbn);
     }
 }
 

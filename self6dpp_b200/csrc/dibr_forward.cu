@@ -724,6 +724,11 @@ __device__ __forceinline__ void block_item(const FwdParams& P, int4 desc, int bl
         const int prev = __shfl_up_sync(full, fw, 1);
         if (fw >= 0 && ((lane & 7) == 0 || prev != fw)) reinterpret_cast<unsigned char*>(P.face_flags)[f_lo + fw] = 1;
     }
+    {   // uncovered pixels of the block, one byte per row, for the backward's soft part
+        const unsigned ub = __ballot_sync(full, st.open);
+        if (lane < BH && (rowsel < 0 || lane == rowsel) && B.y0 + lane < H && B.x0 < W)
+            P.open8[((size_t)b * H + B.y0 + lane) * ((W + 7) >> 3) + (B.x0 >> 3)] = (unsigned char)((ub >> (8 * lane)) & 0xffu);
+    }
     // ---- soft silhouette of the uncovered pixels
     if (B.open32) {
         if (lane < BW) B.sxy[lane] = (B.x0 + lane < W) ? __ldg(P.xs + B.x0 + lane) : 0.f;

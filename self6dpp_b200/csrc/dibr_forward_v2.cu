@@ -86,6 +86,18 @@ __device__ __forceinline__ void mark_faces_warp(const FwdParams& P, bool want, i
     if (isnew) (bit == 1u ? P.color_list : P.soft_list)[base + __popc(bal & ((1u << lane) - 1u))] = g;
 }
 
+// rows = lanes, columns = bits: returns column `lane` of the 32x32 bit matrix as this lane's word
+__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
+    unsigned m = 0x0000ffffu;
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? (((y & ~m) >> j) | (x & ~m)) : ((x & m) | ((y & m) << j));
+        m ^= (m << (j >> 1));        // 0000ffff -> 00ff00ff -> 0f0f0f0f -> 33333333 -> 55555555
+    }
+    return x;
+}
+
 // first column c in [0,n] with xs[c] >= x (xs ascending, pitch 1/inv_dx): arithmetic guess + exact fix-up
 __device__ __forceinline__ int col_first_ge(const float* xs, int n, float x, float inv_dx) {
     int c = (int)fminf(fmaxf(ceilf((x - xs[0]) * inv_dx), 0.f), (float)n);
@@ -102,7 +114,7 @@ __device__ __forceinline__ int row_first_lt(const float* ys, int n, float y, flo
 }
 
 struct TileGeom {
-    int tw, th;
+    int tw, th, tx0, ty0;
     float inv_dx, inv_dy;
     const uint32_t* words;          // this tile's face bitmap (set-up kernel: bin_face)
     int nw;                         // its length in 32-face words
@@ -179,15 +191,19 @@ __device__ int fill_list(FwdSmem& s, const FwdParams& P, int f_lo, int wpos, con
         if (i < lcount) {
             const float4* rp = reinterpret_cast<const float4*>(recs + s.lid[i]);
             const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
-            // bbox of the 2D corners (the record now carries pixel ranges instead): xmin ymin xmax ymax
-            const float4 r3 = make_float4(fminf(r0.x, fminf(r0.z, r1.x)), fminf(r0.y, fminf(r0.w, r1.y)),
-                                          fmaxf(r0.x, fmaxf(r0.z, r1.x)), fmaxf(r0.y, fmaxf(r0.w, r1.y)));
+            // pixel ranges of the bbox and of the expanded bbox (exact, from the set-up kernel), clipped to the tile
+            const uint4 rg = __ldg(reinterpret_cast<const uint4*>(rp + 3));
             s.c0[i] = r0;
             s.c1[i] = make_float2(r1.x, r1.y);
+            {
+                const int e0 = min(max((int)(rg.z & 0xffffu) - T.tx0, 0), T.tw), e1 = min(max((int)(rg.z >> 16) - T.tx0, 0), T.tw);
+                const int q0 = min(max((int)(rg.w & 0xffffu) - T.ty0, 0), T.th), q1 = min(max((int)(rg.w >> 16) - T.ty0, 0), T.th);
+                s.smask[i] = (e1 > e0 && q1 > q0) ? (((1u << e1) - (1u << e0)) | (((1u << q1) - (1u << q0)) << 16)) : 0u;
+            }
             if (raster) { s.u.ab.z[0][i] = r1.z; s.u.ab.z[1][i] = r1.w; s.u.ab.z[2][i] = r2.x; }
             if (raster && r2.y >= 0.0f) {                       // front face (K1 culls normalz < 0)
-                const int c0 = col_first_ge(s.xs, T.tw, r3.x, T.inv_dx), c1 = col_first_ge(s.xs, T.tw, r3.z, T.inv_dx);
-                const int q0 = row_first_lt(s.ys, T.th, r3.w, T.inv_dy), q1 = row_first_lt(s.ys, T.th, r3.y, T.inv_dy);
+                const int c0 = min(max((int)(rg.x & 0xffffu) - T.tx0, 0), T.tw), c1 = min(max((int)(rg.x >> 16) - T.tx0, 0), T.tw);
+                const int q0 = min(max((int)(rg.y & 0xffffu) - T.ty0, 0), T.th), q1 = min(max((int)(rg.y >> 16) - T.ty0, 0), T.th);
                 if (c1 > c0 && q1 > q0) {
                     keep = true;
                     packed = (unsigned)i | ((unsigned)c0 << 9) | ((unsigned)(c1 - c0 - 1) << 13) |
@@ -359,32 +375,27 @@ dibr_forward_v2_kernel(const __grid_constant__ FwdParams P)
     const int ntiles = tiles_x * tiles_y * P.batch;
     int tile;
     {
-        static_assert(ORDER_BUCKETS == 32, "one bucket per lane");
-        const int n = __ldg(P.order_cnt + (ORDER_BUCKETS - 1 - lane));
-        int incl = n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(full_mask, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int touched = __shfl_sync(full_mask, incl, 30);                           // tiles of buckets 31..1
+        // the plan's summary (last CTA of plan_tiles_kernel): surplus CTAs of the grid leave after one load
+        if ((int)blockIdx.x >= __ldg(P.order_cnt + PLAN_WORK_CTAS)) return;
+        const int touched = __ldg(P.order_cnt + PLAN_TOUCHED);
         if ((int)blockIdx.x >= touched) {
-            // bucket 0 (empty bitmaps): one warp per tile, 8 tiles per CTA; the surplus CTAs of the grid leave at once
+            // bucket 0 (empty bitmaps): one warp per tile, 8 tiles per CTA
             const int j = ((int)blockIdx.x - touched) * NWARP + warp;
-            if (j < __shfl_sync(full_mask, n, 31)) fill_untouched_warp(P, __ldg(P.order_seg + j));
+            if (j < __ldg(P.order_cnt)) fill_untouched_warp(P, __ldg(P.order_seg + j));
             return;
         }
-        const unsigned past = __ballot_sync(full_mask, incl > (int)blockIdx.x);
-        const int src = __ffs(past) - 1;
-        const int before = __shfl_sync(full_mask, incl - n, src);
-        tile = __ldg(P.order_seg + (size_t)(ORDER_BUCKETS - 1 - src) * ntiles + ((int)blockIdx.x - before));
+        static_assert(ORDER_BUCKETS == 32, "one bucket per lane");
+        const int start = __ldg(P.order_cnt + PLAN_START + lane);                      // first position of bucket 31 - lane
+        const unsigned le = __ballot_sync(full_mask, start <= (int)blockIdx.x);       // lane 31 (bucket 0) starts at `touched`
+        const int src = 31 - __clz(le);
+        tile = __ldg(P.order_seg + (size_t)(ORDER_BUCKETS - 1 - src) * ntiles + ((int)blockIdx.x - __shfl_sync(full_mask, start, src)));
     }
     int b, tile_y, tile_x;
     unpack_tile(tile, b, tile_y, tile_x);
     const int tile_in = tile_y * tiles_x + tile_x;
     const int tx0 = tile_x * TILE, ty0 = tile_y * TILE;
     TileGeom T;
-    T.tw = min(TILE, P.width - tx0); T.th = min(TILE, P.height - ty0);
+    T.tw = min(TILE, P.width - tx0); T.th = min(TILE, P.height - ty0); T.tx0 = tx0; T.ty0 = ty0;
     const int tw = T.tw, th = T.th;
     const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
     const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
@@ -542,6 +553,14 @@ dibr_forward_v2_kernel(const __grid_constant__ FwdParams P)
             if (lane == 0 && ov != f2ord(3.0e38f)) atomicMin(P.out_min, ov);
         }
     }
+    {   // uncovered pixels of the tile, one byte per 8 pixels of a row, for the backward's soft part (a warp holds two tile rows)
+        const unsigned ub = __ballot_sync(full_mask, unc);
+        if ((lane & 7) == 0) {
+            const int row = ty0 + (tid >> 4), bytecol = (tx0 >> 3) + ((lane >> 3) & 1);
+            if (row < P.height && bytecol * 8 < P.width)
+                P.open8[((size_t)b * P.height + row) * ((P.width + 7) >> 3) + bytecol] = (unsigned char)((ub >> lane) & 0xffu);
+        }
+    }
     const int tile_unc = __syncthreads_or(unc ? 1 : 0);        // also: cnt[] complete, the z-buffer is dead
     PHASE_MARK(3);
     if (!tile_unc || P.knum <= 0) return;
@@ -566,18 +585,9 @@ dibr_forward_v2_kernel(const __grid_constant__ FwdParams P)
         }
         const int lcount = s.lcount;
         for (int i = tid; i < LCAP / 4; i += FWD_THREADS) reinterpret_cast<unsigned int*>(s.soft_used)[i] = 0u;
-        // per listed face: the tile's columns (bits 0-15) and rows (bits 16-31) whose pixel centres lie inside its
-        // expanded bbox
+        // per listed face s.smask holds the tile's columns (bits 0-15) and rows (bits 16-31) whose pixel centres lie inside
+        // its expanded bbox (rasterizer.py:54-57): written with the records by fill_list
         unsigned int* const smask = s.smask;
-        for (int li = tid; li < lcount; li += FWD_THREADS) {
-            const float4 a = s.c0[li];
-            const float2 d = s.c1[li];
-            const float xmin = fminf(a.x, fminf(a.z, d.x)) - ex, xmax = fmaxf(a.x, fmaxf(a.z, d.x)) + ex;   // rasterizer.py:49-57
-            const float ymin = fminf(a.y, fminf(a.w, d.y)) - ex, ymax = fmaxf(a.y, fmaxf(a.w, d.y)) + ex;
-            const int e0 = col_first_ge(s.xs, tw, xmin, T.inv_dx), e1 = col_first_ge(s.xs, tw, xmax, T.inv_dx);
-            const int q0 = row_first_lt(s.ys, th, ymax, T.inv_dy), q1 = row_first_lt(s.ys, th, ymin, T.inv_dy);
-            smask[li] = (e1 > e0 && q1 > q0) ? (((1u << e1) - (1u << e0)) | (((1u << q1) - (1u << q0)) << 16)) : 0u;
-        }
         __syncthreads();
         const int c_start = c;
         // passes of HITCAP hits per pixel (one pass unless K > HITCAP)
@@ -597,28 +607,36 @@ dibr_forward_v2_kernel(const __grid_constant__ FwdParams P)
                         m32 = (cm * 0x01010101u) & (((rm * 0x00204081u) & 0x01010101u) * 0xffu) & open32;
                     }
                     unsigned bal = __ballot_sync(full_mask, m32 != 0u);
-                    while (bal) {
-                        const int src = __ffs(bal) - 1;
-                        bal &= bal - 1;
-                        const unsigned m = __shfl_sync(full_mask, m32, src);
-                        if (open && ((m >> lane) & 1u)) {
-                            if (seen >= skip) {
-                                if (nh < HITCAP) {
-                                    s.u.hits[nh][tid] = (unsigned)(i0 + src);
-                                    nh++;
-                                    if (c_start + seen + 1 >= knum) {      // the K-th accepted face closes the pixel
-                                        open = false;
-                                        imidx[gpix] = -(s.lid[i0 + src] + 1);
-                                    }
-                                } else {
-                                    more = true;
-                                    open = false;               // nothing more to store in this pass
+                    // one accepted (pixel, face) pair of this lane's pixel: list entry i0 + src
+                    auto accept = [&](int src) {
+                        if (seen >= skip) {
+                            if (nh < HITCAP) {
+                                s.u.hits[nh][tid] = (unsigned)(i0 + src);
+                                nh++;
+                                if (c_start + seen + 1 >= knum) {      // the K-th accepted face closes the pixel
+                                    open = false;
+                                    imidx[gpix] = -(s.lid[i0 + src] + 1);
                                 }
-                            } else if (c_start + seen + 1 >= knum) {
-                                open = false;
+                            } else {
+                                more = true;
+                                open = false;               // nothing more to store in this pass
                             }
-                            if (!more) seen++;
+                        } else if (c_start + seen + 1 >= knum) {
+                            open = false;
                         }
+                        if (!more) seen++;
+                    };
+                    if (__popc(bal) <= 4) {
+                        // few faces of this chunk reach the block: hand their masks round one at a time
+                        while (bal) {
+                            const int src = __ffs(bal) - 1;
+                            bal &= bal - 1;
+                            const unsigned m = __shfl_sync(full_mask, m32, src);
+                            if (open && ((m >> lane) & 1u)) accept(src);
+                        }
+                    } else {
+                        // many: transpose the 32 x 32 bit matrix (5 shuffles), every pixel then walks its own faces only
+                        for (unsigned t = transpose32(m32, lane); t && open; t &= t - 1) accept(__ffs(t) - 1);
                     }
                     if (!__any_sync(full_mask, open)) break;
                 }

@@ -36,6 +36,8 @@ struct Workspace {
     int* list_counts;   // [2] entries in color_list / soft_list (+ padding), zeroed by dibr_forward
     unsigned int* pose_done;    // [num_instances] vertex blocks that have delivered their pose sums (zeroed by dibr_forward with the lists)
     unsigned int* face_flags;   // zeroed by dibr_forward.  Read as bytes: [0, F) face won a pixel, [F, 2F) face entered a soft product
+    unsigned char* open8;       // [batch, H, ceil(W/8)] bit x%8 of byte x/8: pixel (y, x) is uncovered.  Written by the forward for every
+                                // touched tile (the only ones a face's expanded pixel range can reach), read by the backward's soft part
     int* color_list;    // [total_faces] global face ids that won at least one pixel (built from the flags by the backward, arbitrary order)
     int* soft_list;     // [total_faces] global face ids that entered at least one soft-silhouette product
     size_t bytes;
@@ -111,6 +113,7 @@ struct FwdParams {
     unsigned int* face_flags;
     int* color_list;
     int* soft_list;
+    unsigned char* open8;
     int min_group;             // output group whose batch-global minimum is accumulated, or -1
     unsigned int* out_min;     // ordered-uint encoding
 };
@@ -127,6 +130,7 @@ struct BwdParams {
     const float* improb;
     const float* imcomp;
     const int32_t* imidx;
+    const unsigned char* open8;
     int* list_counts;          // [0] colour list length, [1] soft list length
     const unsigned char* face_flags;
     int* color_list;
@@ -170,6 +174,11 @@ struct MeshBwdParams {
 // tiles * ((f_lo >> 5) + b) (images never overlap: consecutive images share at most one boundary word, and the "+ b"
 // pays for it), one run of nw words per tile.  Total: tiles * (ceil(total_faces / 32) + batch + 1) words.
 constexpr int ORDER_BUCKETS = 32;
+// plan summary, written by the last CTA of plan_tiles_kernel behind the 32 bucket counters (order_cnt[32] is big_count):
+constexpr int PLAN_TOUCHED = 64;        // order_cnt[64]: tiles with a non-empty bitmap
+constexpr int PLAN_WORK_CTAS = 65;      // order_cnt[65]: CTAs of the tile-CTA forward that have work (touched tiles + ceil(untouched / 8))
+constexpr int PLAN_TICKET = 66;         // order_cnt[66]: CTAs of the plan kernel that are done
+constexpr int PLAN_START = 96;          // order_cnt[96 + l]: first heaviest-first position of bucket 31 - l
 __host__ __device__ inline size_t bin_total_words(int width, int height, int batch, int total_faces) {
     const size_t tiles = (size_t)((width + TILE - 1) / TILE) * (size_t)((height + TILE - 1) / TILE);
     return tiles * ((size_t)((total_faces + 31) / 32) + (size_t)batch + 1);

@@ -310,6 +310,28 @@ __global__ void __launch_bounds__(32 * PLAN_TILES_PER_CTA) plan_tiles_kernel(Set
         P.ws.order_seg[(size_t)kb * ntiles + base[kb] + pos] = id;
         P.ws.tile_desc[(size_t)kb * ntiles + base[kb] + pos] = desc;
     }
+    // ---- the CTA that finishes last sums the plan up, so that the forward's CTAs find their tile with one ballot and its
+    //      surplus CTAs leave after one load
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&P.ws.order_cnt[PLAN_TICKET], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (s_last && warp == 0) {
+        const int n = __ldcg(P.ws.order_cnt + (ORDER_BUCKETS - 1 - lane));
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        P.ws.order_cnt[PLAN_START + lane] = incl - n;
+        if (lane == 31) {
+            const int touched = incl - n;                       // bucket 0 (lane 31) comes last
+            P.ws.order_cnt[PLAN_TOUCHED] = touched;
+            P.ws.order_cnt[PLAN_WORK_CTAS] = touched + (n + 7) / 8;
+        }
+    }
 }
 
 static inline int launch_plan(const SetupParams& P, cudaStream_t stream) {
