@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define DIBR_ABI_VERSION 2
+#define DIBR_ABI_VERSION 3
 #define DIBR_MAX_ATTR 12 /* interpolated channels per pixel (the reference uses 4: rgb/xyz/normal + ones) */
 #define DIBR_MAX_OUTPUTS 6
 

@@ -257,7 +257,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrNnd), ctypes.c_void_p]
         fn.restype = ctypes.c_int
-    if lib.dibr_abi_version() != 2:
+    if lib.dibr_abi_version() != 3:
         raise RuntimeError("libdibr_b200.so ABI version mismatch")
     if lib.dibr_sizeof_pass() != ctypes.sizeof(DibrPass):
         raise RuntimeError("DibrPass mirror out of date: C sizeof %d != ctypes %d"

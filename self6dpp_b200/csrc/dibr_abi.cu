@@ -33,22 +33,17 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     char* b = (char*)base;
     auto take = [&](size_t bytes) { void* r = b ? (void*)(b + off) : nullptr; off += align_up(bytes, 256); return r; };
     w.recs = (dibr::FaceRec*)take(sizeof(dibr::FaceRec) * (size_t)p->total_faces);
+    w.fvid = (int4*)take(sizeof(int4) * (size_t)p->total_faces);
     {
         const size_t ntiles = (size_t)p->batch * ((p->height + dibr::TILE - 1) / dibr::TILE) * ((p->width + dibr::TILE - 1) / dibr::TILE);
         w.order_seg = (int*)take(sizeof(int) * dibr::ORDER_BUCKETS * ntiles);
-        w.tile_desc = (int4*)take(sizeof(int4) * dibr::ORDER_BUCKETS * ntiles);
-        w.big_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
-        w.big_cap = p->total_faces;
-        w.order_cnt = (int*)take(sizeof(int) * 4 * dibr::ORDER_BUCKETS);   // counters (+ the plan summary), then the bins, then the z-buffer: one memset clears all
-        w.big_count = w.order_cnt ? w.order_cnt + dibr::ORDER_BUCKETS : nullptr;
-        w.tile_blocks = (unsigned int*)take(sizeof(unsigned int) * ntiles);
+        // counters (+ the plan summary), per-tile face counters, per-image progress, then the bins: one memset clears all
+        w.order_cnt = (int*)take(sizeof(int) * 4 * dibr::ORDER_BUCKETS);
+        w.tile_count = (int*)take(sizeof(int) * ntiles);
+        w.img_done = (int*)take(sizeof(int) * (size_t)p->batch);
     }
     w.bins_bytes = sizeof(uint32_t) * dibr::bin_total_words(p->width, p->height, p->batch, p->total_faces);
     w.bins = (uint32_t*)take(w.bins_bytes);
-    w.wordmask = (unsigned char*)take(w.bins_bytes / sizeof(uint32_t));
-    w.zbuf_bytes = sizeof(unsigned long long) * (size_t)p->batch * (size_t)p->height * (size_t)p->width;
-    w.zbuf = (unsigned long long*)take(w.zbuf_bytes);
-    w.fbox = (uint2*)take(sizeof(uint2) * (size_t)p->total_faces);
     w.xs = (float*)take(sizeof(float) * (size_t)p->width);
     w.ys = (float*)take(sizeof(float) * (size_t)p->height);
     w.pose_part = (float*)take(sizeof(float) * 12 * dibr::POSE_BLOCKS * (size_t)(p->num_instances > 0 ? p->num_instances : 0));
@@ -99,6 +94,18 @@ int check_outputs(const DibrPass* p) {
     return d == p->num_attr ? 0 : fail("out_channels sum %d != num_attr %d", d, p->num_attr);
 }
 
+// a pass set up by dibr_setup_meshes: the corner attributes are gathered from the vertex table, face_attr is not used
+bool is_fused(const DibrPass* p) { return p->num_instances > 0 && p->inst_desc && p->verts && p->mesh_faces; }
+
+void set_vertex_attr(dibr::VertexAttr& va, const DibrPass* p, const dibr::Workspace& w) {
+    va.fvid = w.fvid;
+    va.table = p->vert_attr;
+    va.dim = p->vert_attr_dim;
+    va.stride = p->vert_attr_stride > 0 ? p->vert_attr_stride : p->vert_attr_dim;
+    va.flags = p->attr_flags;
+    va.vec = va.dim > 0 && (va.stride & 3) == 0 && (((uintptr_t)va.table & 15u) == 0);
+}
+
 dibr::SetupParams setup_params(const DibrPass* p) {
     dibr::SetupParams s;
     memset(&s, 0, sizeof(s));
@@ -115,7 +122,6 @@ dibr::SetupParams setup_params(const DibrPass* p) {
     s.pose_R = p->pose_R; s.pose_t = p->pose_t; s.pose_K = p->pose_K; s.num_K = p->num_K;
     const double nc = p->znear, fc = p->zfar;
     s.expand_mul = (float)((double)p->expand * (double)p->multiplier);
-    s.fwd_impl = dibr::forward_impl();
     s.q = (float)(-(fc + nc) / (fc - nc));
     s.qn = (float)(-2.0 * (fc * nc) / (fc - nc));
     return s;
@@ -245,7 +251,7 @@ int dibr_setup_faces(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
     if (p->total_faces > 0 && (!p->points3d || !p->points2d || !p->normalz)) return fail("setup_faces: points3d/points2d/normalz required");
     const dibr::SetupParams s = setup_params(p);
-    g_launches += 2;
+    g_launches += 1;
     return cuda_fail("dibr_setup_faces", dibr::launch_setup_faces(s, (cudaStream_t)stream));
 }
 
@@ -255,20 +261,21 @@ int dibr_setup_meshes(const DibrPass* p, void* stream) {
     if (p->pose_R) {
         if (!p->pose_t || !p->pose_K || p->num_K <= 0 || !(p->zfar > p->znear)) return fail("setup_meshes: pose mode needs pose_t, pose_K, num_K > 0 and zfar > znear");
     } else if (!p->cam_rot || !p->cam_pos || !p->cam_proj) return fail("setup_meshes: cameras required");
-    if (!p->face_attr) return fail("setup_meshes: face_attr output required");
     const int d = p->vert_attr_dim + ((p->attr_flags & 1) ? 1 : 0) + ((p->attr_flags & 2) ? 1 : 0);
     if (d != p->num_attr) return fail("setup_meshes: vert_attr_dim + flags = %d but num_attr = %d", d, p->num_attr);
     if (p->vert_attr_dim > 0 && !p->vert_attr) return fail("setup_meshes: vert_attr is null");
     if (p->verts_stride != 0 && p->verts_stride < 3) return fail("setup_meshes: verts_stride %d < 3", p->verts_stride);
     if (p->vert_attr_stride != 0 && p->vert_attr_stride < p->vert_attr_dim) return fail("setup_meshes: vert_attr_stride %d < vert_attr_dim %d", p->vert_attr_stride, p->vert_attr_dim);
     const dibr::SetupParams s = setup_params(p);
-    g_launches += 2;
+    g_launches += 1;
     return cuda_fail("dibr_setup_meshes", dibr::launch_setup_meshes(s, (cudaStream_t)stream));
 }
 
 int dibr_forward(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
-    if ((p->total_faces > 0 && !p->face_attr) || !p->improb || !p->imidx || !p->imcomp) return fail("forward: face_attr/improb/imidx/imcomp required");
+    const bool fused = is_fused(p);
+    if ((p->total_faces > 0 && !fused && !p->face_attr) || !p->improb || !p->imidx || !p->imcomp) return fail("forward: face_attr/improb/imidx/imcomp required");
+    if (fused && p->vert_attr_dim > 0 && !p->vert_attr) return fail("forward: vert_attr is null");
     if (int e = check_outputs(p)) return e;
     const dibr::Workspace w = carve(p, p->workspace);
     dibr::FwdParams f;
@@ -277,8 +284,9 @@ int dibr_forward(const DibrPass* p, void* stream) {
     f.multiplier = p->multiplier; f.delta = p->delta;
     f.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     f.faces_per_image = p->faces_per_image; f.face_offsets = p->face_offsets;
-    f.total_faces = p->total_faces; f.zbuf = w.zbuf; f.big_count = w.big_count; f.big_list = w.big_list; f.tile_blocks = w.tile_blocks; f.wordmask = w.wordmask; f.fbox = w.fbox;
-    f.recs = w.recs; f.bins = w.bins; f.order_cnt = w.order_cnt; f.order_seg = w.order_seg; f.tile_desc = w.tile_desc; f.xs = w.xs; f.ys = w.ys; f.face_attr = p->face_attr;
+    f.total_faces = p->total_faces;
+    f.recs = w.recs; f.bins = w.bins; f.order_cnt = w.order_cnt; f.order_seg = w.order_seg; f.xs = w.xs; f.ys = w.ys; f.face_attr = p->face_attr;
+    if (fused) set_vertex_attr(f.va, p, w);
     if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
     else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }
     {
@@ -310,14 +318,16 @@ int dibr_forward(const DibrPass* p, void* stream) {
         cudaError_t e = cudaMemsetAsync(p->out_min_ordered, 0xff, sizeof(uint32_t), (cudaStream_t)stream);
         if (e != cudaSuccess) return cuda_fail("dibr_forward (reset min)", (int)e);
     }
-    g_launches += 2;           // coverage + tiles
+    g_launches += 1;
     return cuda_fail("dibr_forward", dibr::launch_forward(f, (cudaStream_t)stream));
 }
 
 int dibr_backward_faces(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
     if (p->total_faces == 0) return 0;                      // nothing to differentiate
-    if (!p->face_attr || !p->improb || !p->imidx || !p->imcomp) return fail("backward_faces: saved forward buffers required");
+    const bool fused = is_fused(p);
+    if ((!fused && !p->face_attr) || !p->improb || !p->imidx || !p->imcomp) return fail("backward_faces: saved forward buffers required");
+    if (fused && p->vert_attr_dim > 0 && !p->vert_attr) return fail("backward_faces: vert_attr is null");
     if (!p->grad_points2d || !p->grad_face_attr) return fail("backward_faces: grad outputs required");
     const dibr::Workspace w = carve(p, p->workspace);
     dibr::BwdParams b;
@@ -327,6 +337,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     b.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     b.total_faces = p->total_faces; b.faces_per_image = p->faces_per_image; b.face_offsets = p->face_offsets;
     b.recs = w.recs; b.xs = w.xs; b.ys = w.ys; b.face_attr = p->face_attr;
+    if (fused) set_vertex_attr(b.va, p, w);
     b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx;
     b.list_counts = w.list_counts; b.face_flags = (const unsigned char*)w.face_flags; b.color_list = w.color_list; b.soft_list = w.soft_list; b.open8 = w.open8;
     if (p->num_outputs < 0 || p->num_outputs > DIBR_MAX_OUTPUTS) return fail("num_outputs=%d outside [0,%d]", p->num_outputs, DIBR_MAX_OUTPUTS);
@@ -348,7 +359,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     }
     b.grad_improb = p->grad_improb;
     b.grad_points2d = p->grad_points2d; b.grad_face_attr = p->grad_face_attr;
-    g_launches += 2;           // work lists + faces
+    g_launches += 1;
     return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream));
 }
 

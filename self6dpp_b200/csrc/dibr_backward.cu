@@ -125,12 +125,24 @@ __device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
     if (!active || gl != 0) return;
     // dL/dattr is acc itself; dL/dP follows from it (see the header comment)
     const FaceK fk = make_facek(rec);
-    const float* __restrict__ a = P.face_attr + (size_t)g * 3 * D;
+    // corner attributes: seam mode from face_attr; fused mode [row of the vertex table | 1 | -view z] through the face's row ids
+    const bool fusedm = P.va.fvid != nullptr;
+    const float* __restrict__ a = fusedm ? nullptr : P.face_attr + (size_t)g * 3 * D;
+    int4 vid = make_int4(0, 0, 0, 0);
+    if (fusedm) vid = __ldg(P.va.fvid + g);
+    const float* __restrict__ a0 = P.va.table + (size_t)vid.x * P.va.stride;
+    const float* __restrict__ a1 = P.va.table + (size_t)vid.y * P.va.stride;
+    const float* __restrict__ a2 = P.va.table + (size_t)vid.z * P.va.stride;
+    const int nA = P.va.dim, ones = P.va.flags & 1, dep = (P.va.flags >> 1) & 1;
     float A[3] = {0.f, 0.f, 0.f}, Bv[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int d = 0; d < DMAX; d++) {
         if (d < D) {
-            const float c0v = a[d], e1 = a[D + d] - c0v, e2 = a[2 * D + d] - c0v;
+            float c0v, e1, e2;
+            if (!fusedm) { c0v = a[d]; e1 = a[D + d] - c0v; e2 = a[2 * D + d] - c0v; }
+            else if (d < nA) { c0v = __ldg(a0 + d); e1 = __ldg(a1 + d) - c0v; e2 = __ldg(a2 + d) - c0v; }
+            else if (dep && d == nA + ones) { c0v = -rec.az; e1 = -rec.bz - c0v; e2 = -rec.cz - c0v; }
+            else { c0v = 1.0f; e1 = 0.f; e2 = 0.f; }        // the ones channel: constant over the face
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 A[i] = fmaf(e1, acc[i * DMAX + d], A[i]);
@@ -310,32 +322,6 @@ __global__ void __launch_bounds__(256, (DMAX <= 8) ? DIBR_BWD_MIN_CTAS : 2) back
     }
 }
 
-// The work lists of the two bodies, compacted from the byte flags the forward left (faces that won a pixel / faces that
-// entered a soft product).  One counter atomic per CTA and list; the order of a list is arbitrary and no result depends
-// on it.
-__global__ void __launch_bounds__(256) build_lists_kernel(const BwdParams P)
-{
-    __shared__ int s_cnt[2][8], s_base[2];
-    const int g = blockIdx.x * 256 + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool fc = g < P.total_faces && P.face_flags[g] != 0;
-    const bool fs = g < P.total_faces && P.face_flags[(size_t)P.total_faces + g] != 0;
-    const unsigned bc = __ballot_sync(0xffffffffu, fc), bs = __ballot_sync(0xffffffffu, fs);
-    if (lane == 0) { s_cnt[0][warp] = __popc(bc); s_cnt[1][warp] = __popc(bs); }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        int tot = 0;
-        for (int w = 0; w < 8; w++) tot += s_cnt[threadIdx.x][w];
-        s_base[threadIdx.x] = tot ? atomicAdd(&P.list_counts[threadIdx.x], tot) : 0;
-    }
-    __syncthreads();
-    int oc = s_base[0], os = s_base[1];
-    for (int w = 0; w < warp; w++) { oc += s_cnt[0][w]; os += s_cnt[1][w]; }
-    const unsigned lt = (1u << lane) - 1u;
-    if (fc) P.color_list[oc + __popc(bc & lt)] = g;
-    if (fs) P.soft_list[os + __popc(bs & lt)] = g;
-}
-
 int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
 {
     if (P.total_faces <= 0) return 0;
@@ -346,13 +332,6 @@ int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
     if (e != cudaSuccess) return (int)e;
     const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
     if (!do_color && !do_soft) return 0;
-    if (forward_impl() != 2) {
-        e = cudaMemsetAsync(P.list_counts, 0, 2 * sizeof(int), stream);
-        if (e != cudaSuccess) return (int)e;
-        build_lists_kernel<<<(P.total_faces + 255) / 256, 256, 0, stream>>>(P);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-    }
     const int worst = (do_color ? (P.total_faces + (256 / GRP) - 1) / (256 / GRP) : 0) + (do_soft ? (P.total_faces + SOFT_GROUPS - 1) / SOFT_GROUPS : 0);
     const int grid = min(worst, DIBR_BWD_GRID);
     if (P.num_attr <= 4) backward_faces_kernel<4><<<grid, 256, 0, stream>>>(P, do_color, do_soft);

@@ -12,21 +12,14 @@ namespace dibr {
 // workspace carved out of DibrPass::workspace by dibr_abi.cu
 struct Workspace {
     FaceRec* recs;      // [total_faces]
+    int4* fvid;         // fused mode: [total_faces] rows of the three corners in vert_attr (attr_base + vertex id); the forward and the
+                        // backward gather the corner attributes through it instead of a materialised [F, 3, D] array
     uint32_t* bins;     // per image, per 16x16 tile: bitmap over the image's faces (bit = face may reach the tile); layout in bin_words()
     size_t bins_bytes;
-    unsigned long long* zbuf;   // [batch*H*W] z-buffer of the forward: (orderable z << 32) | ~face, 0 = uncovered.  Directly after
-                                // the bins (one memset at set-up clears both); the forward leaves it all-zero again
-    size_t zbuf_bytes;
-    int* big_count;     // [1] faces on big_list (directly after order_cnt: same memset)
-    unsigned int* tile_blocks;  // [batch * tiles] bit k: some face's expanded pixel range meets 8x4 block k of the tile (after order_cnt: same memset)
-    unsigned char* wordmask;    // one byte per bitmap word (same layout as bins): bit k = some face of the word meets block k of the tile; directly
-                                // after the bins and before the z-buffer (same memset)
-    uint2* fbox;        // [total_faces] expanded pixel ranges (ecols, erows) of the records, packed for the soft phase's gathers
-    int* big_list;      // [total_faces] front faces with more than BIG_FACE_PIXELS pixel centres in their bbox
-    int big_cap;
-    int* order_cnt;     // [ORDER_BUCKETS] tiles per cost bucket (bucket = ceil(listed faces / 32), capped)
+    int* order_cnt;     // [4 * ORDER_BUCKETS] tiles per cost bucket (bucket = ceil(listed faces / 32), capped) + the plan summary
+    int* tile_count;    // [batch * tiles] faces listed in the tile's bitmap (bumped by the binning; directly after order_cnt: same memset)
+    int* img_done;      // [batch] faces of the image that are binned (the CTA that completes an image plans its tiles; same memset)
     int* order_seg;     // [ORDER_BUCKETS, batch * tiles] tile ids of each bucket: the forward kernel works heaviest bucket first
-    int4* tile_desc;    // same shape: {tile id, first face of the image, bitmap words per tile, offset of the tile's words in bins}
     float* xs;          // [width]  pixel-centre x
     float* ys;          // [height] pixel-centre y
     float* pose_part;   // [num_instances * POSE_BLOCKS * 12] partial pose-gradient sums
@@ -35,10 +28,10 @@ struct Workspace {
     float* cam_proj;    // pose mode: [num_K, 16]
     int* list_counts;   // [2] entries in color_list / soft_list (+ padding), zeroed by dibr_forward
     unsigned int* pose_done;    // [num_instances] vertex blocks that have delivered their pose sums (zeroed by dibr_forward with the lists)
-    unsigned int* face_flags;   // zeroed by dibr_forward.  Read as bytes: [0, F) face won a pixel, [F, 2F) face entered a soft product
+    unsigned int* face_flags;   // [total_faces] zeroed by dibr_forward.  bit 0: the face won a pixel, bit 1: it entered a soft product
     unsigned char* open8;       // [batch, H, ceil(W/8)] bit x%8 of byte x/8: pixel (y, x) is uncovered.  Written by the forward for every
                                 // touched tile (the only ones a face's expanded pixel range can reach), read by the backward's soft part
-    int* color_list;    // [total_faces] global face ids that won at least one pixel (built from the flags by the backward, arbitrary order)
+    int* color_list;    // [total_faces] global face ids that won at least one pixel (appended by the forward, arbitrary order)
     int* soft_list;     // [total_faces] global face ids that entered at least one soft-silhouette product
     size_t bytes;
 };
@@ -73,8 +66,15 @@ struct SetupParams {
     int num_K;
     float q, qn;             // -(f+n)/(f-n), -2fn/(f-n)
     float expand_mul;        // expand * multiplier: the bins cover the EXPANDED bboxes
-    int fwd_impl;            // forward_impl(): the v4 forward needs the z-buffer cleared, block masks, packed ranges and the big-face list
     Workspace ws;
+};
+
+// fused mode: the per-corner attributes of a face are [row of vert_attr | 1 (flags & 1) | -view z (flags & 2)]
+// (vcrender_batch.py:84-88, renderer_dibr.py:296-301), gathered through the face's three row ids
+struct VertexAttr {
+    const int4* fvid;          // [total_faces] rows of the three corners, or null: seam mode, attributes come from face_attr
+    const float* table;
+    int dim, stride, flags, vec;
 };
 
 struct FwdParams {
@@ -85,18 +85,12 @@ struct FwdParams {
     int total_faces;
     const FaceRec* recs;
     const uint32_t* bins;
-    unsigned long long* zbuf;  // all-zero on entry and on exit
-    const int* big_count;
-    const int* big_list;
-    const unsigned int* tile_blocks;
-    const unsigned char* wordmask;
-    const uint2* fbox;
     const int* order_cnt;
     const int* order_seg;
-    const int4* tile_desc;
     const float* xs;           // [width], [height] pixel-centre tables
     const float* ys;
     const float* face_attr;
+    VertexAttr va;
     int n_out;                 // channel groups (>= 1)
     int out_ch[6];
     float* out[6];             // [batch,H,W,out_ch[g]]
@@ -127,6 +121,7 @@ struct BwdParams {
     const float* xs;
     const float* ys;
     const float* face_attr;
+    VertexAttr va;
     const float* improb;
     const float* imcomp;
     const int32_t* imidx;
@@ -174,10 +169,10 @@ struct MeshBwdParams {
 // tiles * ((f_lo >> 5) + b) (images never overlap: consecutive images share at most one boundary word, and the "+ b"
 // pays for it), one run of nw words per tile.  Total: tiles * (ceil(total_faces / 32) + batch + 1) words.
 constexpr int ORDER_BUCKETS = 32;
-// plan summary, written by the last CTA of plan_tiles_kernel behind the 32 bucket counters (order_cnt[32] is big_count):
+// plan summary, written behind the 32 bucket counters by the set-up CTA that plans the last image:
 constexpr int PLAN_TOUCHED = 64;        // order_cnt[64]: tiles with a non-empty bitmap
 constexpr int PLAN_WORK_CTAS = 65;      // order_cnt[65]: CTAs of the tile-CTA forward that have work (touched tiles + ceil(untouched / 8))
-constexpr int PLAN_TICKET = 66;         // order_cnt[66]: CTAs of the plan kernel that are done
+constexpr int PLAN_TICKET = 66;         // order_cnt[66]: images whose tiles are planned
 constexpr int PLAN_START = 96;          // order_cnt[96 + l]: first heaviest-first position of bucket 31 - l
 __host__ __device__ inline size_t bin_total_words(int width, int height, int batch, int total_faces) {
     const size_t tiles = (size_t)((width + TILE - 1) / TILE) * (size_t)((height + TILE - 1) / TILE);
@@ -357,8 +352,6 @@ int launch_nnd_backward(const NndParams& P, cudaStream_t stream);
 int launch_setup_faces(const SetupParams& P, cudaStream_t stream);
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream);
 int launch_forward(const FwdParams& P, cudaStream_t stream);
-int launch_forward_v2(const FwdParams& P, cudaStream_t stream);
-int forward_impl();               // 4 (current) or 2 (DIBR_FWD_IMPL=2: the round-1 kernel, which appends the work lists itself)      // previous design, kept for the A/B (DIBR_FWD_IMPL=2)
 int launch_backward_faces(const BwdParams& P, cudaStream_t stream);
 int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream);
 int launch_normal_map(const float* n, const float* mask, const unsigned int* min_ordered, float* out, long long npix, cudaStream_t stream);

@@ -1,14 +1,24 @@
-// Face set-up kernels: build the 64 B face records and the per-tile face bitmaps the forward/backward kernels read.
+// Set-up kernels: build the 64 B face records, the per-tile face bitmaps and the heaviest-first tile plan the
+// forward/backward kernels read.
 //
 //   setup_faces_kernel   operator-seam mode: inputs are the reference's points3d_bxfx9 /
 //                        points2d_bxfx6 / normalz_bxfx1; replaces prepare_tfpoints
 //                        (/root/reference/lib/dr_utils/dib_renderer_x/rasterizer/rasterizer.py:36-70).
-//   setup_meshes_kernel  fused mode: object-space vertices + per-instance camera; replaces the
-//                        per-sample Python loop of renderer/vcrender_batch.py:49-102 and
-//                        renderer/vertex_shaders/perpsective.py:71-111 (view transform, 4x4
-//                        projection, divide, per-face gather, face normal, attribute gather with
-//                        the ones channel) for the whole ragged batch in ONE launch.  The fp32
-//                        operation order is the one frozen in oracle dibr_oracle_project.
+//   setup_meshes_kernel  fused mode: object-space vertices + per-instance camera; replaces the per-sample Python loop
+//                        of renderer/vcrender_batch.py:49-102 and renderer/vertex_shaders/perpsective.py:71-111 (view
+//                        transform, 4x4 projection, divide, per-face gather, face normal) + prepare_tfpoints for the
+//                        whole ragged batch in ONE launch.  Pose mode derives the camera from (R, t, K) first
+//                        (renderer/base.py:131-191, utils/perspective.py:95-130).  The fp32 operation order is the one
+//                        frozen in oracle dibr_oracle_project / dibr_oracle_camera.  The per-face attribute gather of
+//                        vcrender_batch.py:84-88 is NOT materialised: the kernel leaves the three attribute rows of
+//                        every face (16 B) and the forward / backward kernels read the vertex table through them.
+//                        (The kernel is bound by L1 wavefronts -- distinct 128 B lines per load/store instruction --
+//                        not by arithmetic: one 16 B vertex gather per corner plus the redundant transform is cheaper
+//                        than a projected-vertex table with 32 B rows, measured in profiles/r02_setup.md.)
+//
+// Both face kernels end with the tile plan: the binning bumps a per-tile face counter, the CTA that bins the last face
+// of an image buckets that image's tiles by cost, and the CTA that plans the last image writes the summary the forward
+// kernel's CTAs index with one ballot (no separate plan kernel, no pass over the bitmaps).
 #include "dibr_internal.h"
 
 namespace dibr {
@@ -26,9 +36,12 @@ __device__ __forceinline__ void write_tables(const SetupParams& P, int gtid) {
 }
 
 // Tile binning: set the face's bit in the bitmap of every 16x16 tile that holds a pixel centre of its EXPANDED bbox
-// (exact: the pixel ranges come from first_col_ge / first_row_lt).  Bitmaps instead of lists: OR is order independent,
-// so the forward kernel reads the faces of a tile in ascending order without any sort, and the result is the same run
-// to run.
+// (exact: the pixel ranges come from first_col_ge / first_row_lt) and count it in the tile's plan counter.  Bitmaps
+// instead of lists: OR is order independent, so the forward kernel reads the faces of a tile in ascending order without
+// any sort, and the result is the same run to run.
+//
+// (A warp-level vote that merges the atomics of faces in the same tile was measured 3x slower: the faces of a warp
+// are consecutive in the mesh, not on the screen, and land in ~80 different tiles.)
 __device__ __forceinline__ void bin_face(const SetupParams& P, int g, int b, int e0, int e1, int q0, int q1) {
     if (e1 <= e0 || q1 <= q0) return;
     const int tiles_x = (P.width + TILE - 1) / TILE, tiles_y = (P.height + TILE - 1) / TILE;
@@ -38,62 +51,147 @@ __device__ __forceinline__ void bin_face(const SetupParams& P, int g, int b, int
     const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
     const int w0 = f_lo >> 5, nw = ((f_hi - 1) >> 5) - w0 + 1;
     uint32_t* img = P.ws.bins + (size_t)tiles_x * tiles_y * ((size_t)w0 + b) + ((g >> 5) - w0);
+    int* cnt = P.ws.tile_count + (size_t)b * tiles_x * tiles_y;
     const uint32_t bit = 1u << (g & 31);
-    if (P.fwd_impl == 2) {                           // the round-1 forward only reads the bitmaps
-        for (int ty = ty0; ty <= ty1; ty++)
-            for (int tx = tx0; tx <= tx1; tx++) atomicOr(img + (size_t)(ty * tiles_x + tx) * nw, bit);
-        return;
-    }
-    unsigned int* tb = P.ws.tile_blocks + (size_t)b * tiles_x * tiles_y;
-    // per-word block masks: byte (word index) of the same layout as the bins, updated with 32-bit atomics
-    unsigned int* wm4 = reinterpret_cast<unsigned int*>(P.ws.wordmask);
-    const size_t wbase = (size_t)tiles_x * tiles_y * ((size_t)w0 + b) + ((g >> 5) - w0);
-    for (int ty = ty0; ty <= ty1; ty++) {
-        // 8x4 blocks of the tile the range meets: rows of blocks (4 pixel rows each) x two halves (8 pixel columns each)
-        const int rlo = max(q0 - ty * TILE, 0) >> 2, rhi = (min(q1 - ty * TILE, TILE) - 1) >> 2;
-        const unsigned rowbits = ((2u << (2 * rhi + 1)) - 1u) & ~((1u << (2 * rlo)) - 1u);         // both halves of block rows rlo..rhi
+    for (int ty = ty0; ty <= ty1; ty++)
         for (int tx = tx0; tx <= tx1; tx++) {
             atomicOr(img + (size_t)(ty * tiles_x + tx) * nw, bit);
-            const unsigned halves = ((e0 < tx * TILE + 8) ? 0x55u : 0u) | ((e1 > tx * TILE + 8) ? 0xaau : 0u);
-            const unsigned m = rowbits & halves;
-            if ((__ldcg(tb + ty * tiles_x + tx) & m) != m) atomicOr(tb + ty * tiles_x + tx, m);
-            const size_t wi = wbase + (size_t)(ty * tiles_x + tx) * nw;
-            atomicOr(wm4 + (wi >> 2), m << ((wi & 3) * 8));
+            atomicAdd(cnt + ty * tiles_x + tx, 1);
         }
-    }
 }
 
-__device__ __forceinline__ void store_face(const SetupParams& P, int g, int b, float ax, float ay, float bx, float by,
+// The CTA's records are staged in shared memory and written out as whole 512 B rows per warp instruction (a thread's
+// own 64 B at a stride touches 16 lines per store instruction instead of 4).
+struct StageSmem {
+    float4 rec[256 * 4];                // 16 KB, 16 B chunks swizzled by (thread >> 1) & 3 against bank conflicts
+};
+__device__ __forceinline__ int rec_slot(int t, int c) { return t * 4 + (c ^ ((t >> 1) & 3)); }
+
+__device__ __forceinline__ void store_face(const SetupParams& P, StageSmem& st, int g, int b, float ax, float ay, float bx, float by,
                                            float cx, float cy, float az, float bz, float cz, float nz, bool active)
 {
-    if (!active) return;
-    FaceRec r;
-    r.ax = ax; r.ay = ay; r.bx = bx; r.by = by; r.cx = cx; r.cy = cy;
-    r.az = az; r.bz = bz; r.cz = cz; r.nz = nz; r.image = __int_as_float(b); r.pad1 = 0.f;
-    r.cols = r.rows = r.ecols = r.erows = 0u;
     // non-finite corners make the face invisible (torch.min/max would propagate the NaN)
-    const bool ok = isfinite(ax) && isfinite(ay) && isfinite(bx) && isfinite(by) && isfinite(cx) && isfinite(cy);
-    int e0 = 0, e1 = 0, q0 = 0, q1 = 0;
+    const bool ok = active && isfinite(ax) && isfinite(ay) && isfinite(bx) && isfinite(by) && isfinite(cx) && isfinite(cy);
+    int c0 = 0, c1 = 0, r0 = 0, r1 = 0, e0 = 0, e1 = 0, q0 = 0, q1 = 0;
     if (ok) {
         const float xmin = fminf(ax, fminf(bx, cx)), xmax = fmaxf(ax, fmaxf(bx, cx));     // rasterizer.py:49-52
         const float ymin = fminf(ay, fminf(by, cy)), ymax = fmaxf(ay, fmaxf(by, cy));
         const float ex = P.expand_mul;
         const int W = P.width, H = P.height, M = P.multiplier;
-        const int c0 = first_col_ge(xmin, W, M), c1 = first_col_ge(xmax, W, M);
-        const int r0 = first_row_lt(ymax, H, M), r1 = first_row_lt(ymin, H, M);
+        c0 = first_col_ge(xmin, W, M); c1 = first_col_ge(xmax, W, M);
+        r0 = first_row_lt(ymax, H, M); r1 = first_row_lt(ymin, H, M);
         e0 = first_col_ge(xmin - ex, W, M); e1 = first_col_ge(xmax + ex, W, M);            // rasterizer.py:54-57
         q0 = first_row_lt(ymax + ex, H, M); q1 = first_row_lt(ymin - ex, H, M);
-        r.cols = (unsigned)c0 | ((unsigned)c1 << 16); r.rows = (unsigned)r0 | ((unsigned)r1 << 16);
-        r.ecols = (unsigned)e0 | ((unsigned)e1 << 16); r.erows = (unsigned)q0 | ((unsigned)q1 << 16);
-        // front faces with many pixel centres in their bbox are rasterised by the whole grid (coverage kernel, phase 2)
-        if (P.fwd_impl != 2 && nz >= 0.0f && (long long)(c1 - c0) * (r1 - r0) > BIG_FACE_PIXELS) {
-            const int slot = atomicAdd(P.ws.big_count, 1);
-            if (slot < P.ws.big_cap) P.ws.big_list[slot] = g;
+    }
+    const int t = threadIdx.x;
+    st.rec[rec_slot(t, 0)] = make_float4(ax, ay, bx, by);
+    st.rec[rec_slot(t, 1)] = make_float4(cx, cy, az, bz);
+    st.rec[rec_slot(t, 2)] = make_float4(cz, nz, __int_as_float(b), 0.f);
+    st.rec[rec_slot(t, 3)] = make_float4(__uint_as_float((unsigned)c0 | ((unsigned)c1 << 16)), __uint_as_float((unsigned)r0 | ((unsigned)r1 << 16)),
+                                         __uint_as_float((unsigned)e0 | ((unsigned)e1 << 16)), __uint_as_float((unsigned)q0 | ((unsigned)q1 << 16)));
+    if (ok) bin_face(P, g, b, e0, e1, q0, q1);
+    __syncthreads();
+    // the CTA's 256 records are contiguous in global memory: 1024 16 B chunks, four per thread, fully coalesced
+    const int g0 = blockIdx.x * blockDim.x;
+    const int nrec = min((int)blockDim.x, P.total_faces - g0);
+    float4* out = reinterpret_cast<float4*>(P.ws.recs + g0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = k * 256 + t;
+        if (i < nrec * 4) out[i] = st.rec[rec_slot(i >> 2, i & 3)];
+    }
+}
+
+// ---- tile plan -----------------------------------------------------------------------------------------------------
+// tile ids of the plan: image | tile row | tile column (forward: unpack_tile)
+__device__ __forceinline__ int pack_tile(int b, int ty, int tx) { return (int)(((unsigned)b << 20) | ((unsigned)ty << 10) | (unsigned)tx); }
+
+struct PlanSmem {
+    int hist[ORDER_BUCKETS], base[ORDER_BUCKETS], fill[ORDER_BUCKETS];
+    int fin[256];           // images this CTA completed
+    int nfin, last;
+};
+
+// The whole CTA buckets the tiles of image b by cost (faces listed in the tile's bitmap, 32 per bucket step) and appends
+// them to the global buckets.  The order inside a bucket is arbitrary; it only decides which CTA of the forward grid gets
+// which tile.
+__device__ void plan_image(const SetupParams& P, PlanSmem& s, int b)
+{
+    const int tiles_x = (P.width + TILE - 1) / TILE;
+    const int tiles = tiles_x * ((P.height + TILE - 1) / TILE);
+    const int ntiles = tiles * P.batch;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int* __restrict__ cnt = P.ws.tile_count + (size_t)b * tiles;
+    if (tid < ORDER_BUCKETS) { s.hist[tid] = 0; s.fill[tid] = 0; }
+    __syncthreads();
+    for (int t = tid; t < tiles; t += nthr) atomicAdd(&s.hist[min((__ldcg(cnt + t) + 31) >> 5, ORDER_BUCKETS - 1)], 1);
+    __syncthreads();
+    if (tid < ORDER_BUCKETS) s.base[tid] = s.hist[tid] > 0 ? atomicAdd(&P.ws.order_cnt[tid], s.hist[tid]) : 0;
+    __syncthreads();
+    for (int t = tid; t < tiles; t += nthr) {
+        const int kb = min((__ldcg(cnt + t) + 31) >> 5, ORDER_BUCKETS - 1);
+        const int pos = s.base[kb] + atomicAdd(&s.fill[kb], 1);
+        const int ty = t / tiles_x;
+        P.ws.order_seg[(size_t)kb * ntiles + pos] = pack_tile(b, ty, t - ty * tiles_x);
+    }
+    __syncthreads();
+}
+
+// End of a face kernel.  `g`: this thread's face, `b`: its image (when active).  Every thread of the CTA must call.
+__device__ void plan_epilogue(const SetupParams& P, int g, int b, bool active)
+{
+    __shared__ PlanSmem s;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s.nfin = 0; s.last = 0; }
+    __syncthreads();
+    // the CTA's binning atomics before the image counters.  One thread fences for the CTA (fences are cumulative over
+    // the barrier): a gpu-scope fence also drops the SM's L1, which the other CTAs of the SM are gathering through.
+    if (tid == 0) __threadfence();
+    __syncthreads();
+    if (active) {
+        const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
+        const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
+        // the last face of image b inside this CTA reports how many of the image's faces the CTA has binned
+        if (tid == (int)blockDim.x - 1 || g + 1 == f_hi) {
+            const int first = max((int)(blockIdx.x * blockDim.x), f_lo);
+            const int n = g - first + 1;
+            if (atomicAdd(&P.ws.img_done[b], n) + n == f_hi - f_lo) s.fin[atomicAdd(&s.nfin, 1)] = b;
         }
     }
-    P.ws.recs[g] = r;
-    if (P.fwd_impl != 2) P.ws.fbox[g] = make_uint2(r.ecols, r.erows);
-    if (ok) bin_face(P, g, b, e0, e1, q0, q1);
+    __syncthreads();
+    int planned = 0;
+    // images without faces are nobody's: the first CTA plans them (all their tiles go to bucket 0)
+    if (blockIdx.x == 0) {
+        for (int i = 0; i < P.batch; i++) {
+            const int lo = P.face_offsets ? P.face_offsets[i] : i * P.faces_per_image;
+            const int hi = P.face_offsets ? P.face_offsets[i + 1] : lo + P.faces_per_image;
+            if (hi <= lo) { plan_image(P, s, i); planned++; }
+        }
+    }
+    const int nfin = s.nfin;
+    for (int i = 0; i < nfin; i++) { plan_image(P, s, s.fin[i]); planned++; }
+    if (planned == 0) return;
+    // ---- the CTA that plans the last image sums the plan up, so that the forward's CTAs find their tile with one
+    //      ballot and its surplus CTAs leave after one load
+    __syncthreads();
+    if (tid == 0) { __threadfence(); s.last = (atomicAdd(&P.ws.order_cnt[PLAN_TICKET], planned) + planned == P.batch); }
+    __syncthreads();
+    if (s.last && tid < 32) {
+        const int lane = tid;
+        const int n = __ldcg(P.ws.order_cnt + (ORDER_BUCKETS - 1 - lane));
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        P.ws.order_cnt[PLAN_START + lane] = incl - n;
+        if (lane == 31) {
+            const int touched = incl - n;                       // bucket 0 (lane 31) comes last
+            P.ws.order_cnt[PLAN_TOUCHED] = touched;
+            P.ws.order_cnt[PLAN_WORK_CTAS] = touched + (n + 7) / 8;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) setup_faces_kernel(SetupParams P)
@@ -114,14 +212,18 @@ __global__ void __launch_bounds__(256) setup_faces_kernel(SetupParams P)
         nz = P.normalz[g];
         b = image_of_face(g, P.batch, P.faces_per_image, P.face_offsets);
     }
-    store_face(P, g, b, ax, ay, bx, by, cx, cy, az, bz, cz, nz, active);
+    __shared__ StageSmem st;
+    store_face(P, st, g, b, ax, ay, bx, by, cx, cy, az, bz, cz, nz, active);
+    plan_epilogue(P, g, b, active);
 }
 
+// ---- fused mode: one thread per face of the ragged batch ----------------------------------------------------------
 #ifndef DIBR_SETUP_MIN_CTAS
 #define DIBR_SETUP_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(256, DIBR_SETUP_MIN_CTAS) setup_meshes_kernel(SetupParams P)
 {
+    __shared__ StageSmem st;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     write_tables(P, g);
     const bool active = g < P.total_faces;
@@ -197,10 +299,10 @@ __global__ void __launch_bounds__(256, DIBR_SETUP_MIN_CTAS) setup_meshes_kernel(
             for (int k = 0; k < 16; k++) Pm[k] = Pg[k];
         }
         const float m = (float)P.multiplier;
-        const int A = P.vert_attr_dim, D = P.num_attr;
         const bool vec_verts = (P.verts_stride == 4) && ((reinterpret_cast<uintptr_t>(P.verts) & 15) == 0);
-        const bool vec_attr = A > 0 && (P.vert_attr_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.vert_attr) & 15) == 0);
         float pc[3][3];
+        // rows of the three corners in the vertex-attribute table: the forward / backward gather through them
+        P.ws.fvid[g] = make_int4(de[I_ATTR_BASE] + fv[0], de[I_ATTR_BASE] + fv[1], de[I_ATTR_BASE] + fv[2], 0);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const int vid = fv[c];
@@ -223,40 +325,6 @@ __global__ void __launch_bounds__(256, DIBR_SETUP_MIN_CTAS) setup_meshes_kernel(
             const float xn = __fdiv_rn(clip[0], clip[3]), yn = __fdiv_rn(clip[1], clip[3]);
             x2[c] = __fmul_rn(m, xn); y2[c] = __fmul_rn(m, yn);
             zc[c] = pc[c][2];
-            // per-face corner attributes: [vertex attrs | ones | view depth], 128-bit stores when D % 4 == 0
-            float* fa = P.face_attr + ((size_t)g * 3 + c) * D;
-            const float* va = P.vert_attr + (size_t)(de[I_ATTR_BASE] + vid) * P.vert_attr_stride;
-            float raw[DIBR_MAX_ATTR_INTERNAL];
-            if (vec_attr) {                                      // rows padded to a multiple of 16 B
-#pragma unroll
-                for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d += 4) {
-                    if (d < A) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(va + d));
-                        raw[d] = t.x; raw[d + 1] = t.y; raw[d + 2] = t.z; raw[d + 3] = t.w;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) if (d < A) raw[d] = __ldg(va + d);
-            }
-            float av[DIBR_MAX_ATTR_INTERNAL];
-#pragma unroll
-            for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++) {
-                float x = 0.f;
-                if (d < A) x = raw[d];
-                else if (d == A && (P.attr_flags & 1)) x = 1.0f;
-                else if (d == A + (P.attr_flags & 1) && (P.attr_flags & 2)) x = -pc[c][2];
-                av[d] = x;
-            }
-            if ((D & 3) == 0) {
-#pragma unroll
-                for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d += 4)
-                    if (d < D) reinterpret_cast<float4*>(fa)[d >> 2] = make_float4(av[d], av[d + 1], av[d + 2], av[d + 3]);
-            } else {
-#pragma unroll
-                for (int d = 0; d < DIBR_MAX_ATTR_INTERNAL; d++)
-                    if (d < D) fa[d] = av[d];
-            }
         }
         const float e1x = __fsub_rn(pc[1][0], pc[0][0]), e1y = __fsub_rn(pc[1][1], pc[0][1]), e1z = __fsub_rn(pc[1][2], pc[0][2]);
         const float e2x = __fsub_rn(pc[2][0], pc[0][0]), e2y = __fsub_rn(pc[2][1], pc[0][1]), e2z = __fsub_rn(pc[2][2], pc[0][2]);
@@ -270,103 +338,36 @@ __global__ void __launch_bounds__(256, DIBR_SETUP_MIN_CTAS) setup_meshes_kernel(
             P.face_normal[(size_t)g * 3 + 2] = nz / len;
         }
     }
-    store_face(P, g, b, x2[0], y2[0], x2[1], y2[1], x2[2], y2[2], zc[0], zc[1], zc[2], nz, active);
+    store_face(P, st, g, b, x2[0], y2[0], x2[1], y2[1], x2[2], y2[2], zc[0], zc[1], zc[2], nz, active);
+    plan_epilogue(P, g, b, active);
 }
 
-// Work plan of the forward kernel: tiles bucketed by how many faces their bitmap lists (one warp per tile).  The
-// forward kernel takes the buckets heaviest first, so the long tiles start early and the short ones fill the tail.
-constexpr int PLAN_TILES_PER_CTA = 32;          // one warp per tile, 1024 threads: the bucket counters are bumped once per CTA
-__global__ void __launch_bounds__(32 * PLAN_TILES_PER_CTA) plan_tiles_kernel(SetupParams P)
-{
-    __shared__ int hist[ORDER_BUCKETS], base[ORDER_BUCKETS];
-    const int tiles_x = (P.width + TILE - 1) / TILE;
-    const int tiles = tiles_x * ((P.height + TILE - 1) / TILE);
-    const int ntiles = tiles * P.batch;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < ORDER_BUCKETS) hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int t = blockIdx.x * PLAN_TILES_PER_CTA + warp;
-    int kb = -1, pos = 0, id = 0;
-    int4 desc = make_int4(0, 0, 0, 0);
-    if (t < ntiles) {
-        const int b = t / tiles, tl = t - b * tiles;
-        const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
-        const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
-        const int w0 = f_lo >> 5, nw = ((f_hi - 1) >> 5) - w0 + 1;
-        const uint32_t* words = P.ws.bins + (size_t)tiles * ((size_t)w0 + b) + (size_t)tl * nw;
-        int cost = 0;
-        for (int w = lane; w < nw; w += 32) cost += __popc(__ldg(words + w));
-        cost = __reduce_add_sync(0xffffffffu, cost);
-        kb = min((cost + 31) >> 5, ORDER_BUCKETS - 1);
-        const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
-        id = (int)(((unsigned)b << 20) | ((unsigned)ty << 10) | (unsigned)tx);                 // forward: unpack_tile
-        desc = make_int4(id, f_lo, nw, (int)(words - P.ws.bins));
-        if (lane == 0) pos = atomicAdd(&hist[kb], 1);
-    }
-    __syncthreads();
-    if (threadIdx.x < ORDER_BUCKETS && hist[threadIdx.x] > 0) base[threadIdx.x] = atomicAdd(&P.ws.order_cnt[threadIdx.x], hist[threadIdx.x]);
-    __syncthreads();
-    if (lane == 0 && kb >= 0) {
-        P.ws.order_seg[(size_t)kb * ntiles + base[kb] + pos] = id;
-        P.ws.tile_desc[(size_t)kb * ntiles + base[kb] + pos] = desc;
-    }
-    // ---- the CTA that finishes last sums the plan up, so that the forward's CTAs find their tile with one ballot and its
-    //      surplus CTAs leave after one load
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&P.ws.order_cnt[PLAN_TICKET], 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (s_last && warp == 0) {
-        const int n = __ldcg(P.ws.order_cnt + (ORDER_BUCKETS - 1 - lane));
-        int incl = n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        P.ws.order_cnt[PLAN_START + lane] = incl - n;
-        if (lane == 31) {
-            const int touched = incl - n;                       // bucket 0 (lane 31) comes last
-            P.ws.order_cnt[PLAN_TOUCHED] = touched;
-            P.ws.order_cnt[PLAN_WORK_CTAS] = touched + (n + 7) / 8;
-        }
-    }
-}
-
-static inline int launch_plan(const SetupParams& P, cudaStream_t stream) {
-    const int ntiles = ((P.width + TILE - 1) / TILE) * ((P.height + TILE - 1) / TILE) * P.batch;
-    plan_tiles_kernel<<<(ntiles + PLAN_TILES_PER_CTA - 1) / PLAN_TILES_PER_CTA, 32 * PLAN_TILES_PER_CTA, 0, stream>>>(P);
-    return (int)cudaGetLastError();
-}
 
 static inline int setup_grid(const SetupParams& P) {
     const int n = max(P.total_faces, P.width + P.height);
     return (n + 255) / 256;
 }
 
+// plan counters, per-tile face counters, per-image progress counters and the tile bitmaps are adjacent in the workspace:
+// one memset
+static inline cudaError_t clear_plan(const SetupParams& P, cudaStream_t stream) {
+    return cudaMemsetAsync(P.ws.order_cnt, 0, (size_t)((char*)P.ws.bins - (char*)P.ws.order_cnt) + P.ws.bins_bytes, stream);
+}
+
 int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
 {
-    // plan counters, tile bitmaps and the z-buffer are adjacent in the workspace
-    cudaError_t e = cudaMemsetAsync(P.ws.order_cnt, 0, P.fwd_impl == 2 ? (size_t)((char*)P.ws.wordmask - (char*)P.ws.order_cnt)
-                                                                      : (size_t)((char*)P.ws.zbuf - (char*)P.ws.order_cnt) + P.ws.zbuf_bytes, stream);
+    cudaError_t e = clear_plan(P, stream);
     if (e != cudaSuccess) return (int)e;
     setup_faces_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    return launch_plan(P, stream);
+    return (int)cudaGetLastError();
 }
 
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
 {
-    // plan counters, tile bitmaps and the z-buffer are adjacent in the workspace
-    cudaError_t e = cudaMemsetAsync(P.ws.order_cnt, 0, P.fwd_impl == 2 ? (size_t)((char*)P.ws.wordmask - (char*)P.ws.order_cnt)
-                                                                      : (size_t)((char*)P.ws.zbuf - (char*)P.ws.order_cnt) + P.ws.zbuf_bytes, stream);
+    cudaError_t e = clear_plan(P, stream);
     if (e != cudaSuccess) return (int)e;
     setup_meshes_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    return launch_plan(P, stream);
+    return (int)cudaGetLastError();
 }
 
 }  // namespace dibr

@@ -118,7 +118,7 @@ class RenderMeshes(Function):
             if meta.get("pose_mode"):
                 p.num_K = int(proj_c.shape[0])          # the workspace holds the derived cameras
             ws = _alloc_workspace(p, device)
-            face_attr = torch.empty(max(TF, 1), 3, D, dtype=torch.float32, device=device)
+            # (no [F, 3, D] corner-attribute array: the kernels gather from the vertex table through the faces' row ids)
             face_normal = torch.empty(TF, 3, dtype=torch.float32, device=device) if meta["want_normals"] else None
             split = meta.get("out_split") or [D]
             assert sum(split) == D and len(split) <= 6, (split, D)
@@ -137,7 +137,7 @@ class RenderMeshes(Function):
                 p.znear, p.zfar = float(meta["znear"]), float(meta["zfar"])
             else:
                 p.cam_rot, p.cam_pos, p.cam_proj = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
-            p.face_attr, p.face_normal = _lib.ptr(face_attr), _lib.ptr(face_normal)
+            p.face_normal = _lib.ptr(face_normal)
             p.improb, p.imidx, p.imcomp = _lib.ptr(improb), _lib.ptr(imidx), _lib.ptr(imcomp)
             p.num_outputs = len(split)
             for g, (c, o) in enumerate(zip(split, outs)):
@@ -153,8 +153,8 @@ class RenderMeshes(Function):
             _lib.check(lib.dibr_setup_meshes(ctypes.byref(p), st), "dibr_setup_meshes")
             _lib.check(lib.dibr_forward(ctypes.byref(p), st), "dibr_forward")
         if meta.get("keep_pass"):      # bench_util.time_forward_kernel re-launches dibr_forward on these buffers
-            meta["_last_pass"] = (p, [verts_c, vattr_c, rot_c, pos_c, proj_c, face_attr, face_normal, outs, improb, imcomp, imidx, ws])
-        ctx.save_for_backward(verts_c, rot_c, pos_c, proj_c, face_attr, improb, imcomp, imidx, ws)
+            meta["_last_pass"] = (p, [verts_c, vattr_c, rot_c, pos_c, proj_c, face_normal, outs, improb, imcomp, imidx, ws])
+        ctx.save_for_backward(verts_c, rot_c, pos_c, proj_c, vattr_c if A > 0 else None, improb, imcomp, imidx, ws)
         ctx.meta = meta
         ctx.dims = (D, A, flags)
         ctx.split = list(split)
@@ -169,7 +169,7 @@ class RenderMeshes(Function):
     @staticmethod
     def backward(ctx, *grads):
         g_outs, g_prob = grads[:-2], grads[-2]
-        verts_c, rot_c, pos_c, proj_c, face_attr, improb, imcomp, imidx, ws = ctx.saved_tensors
+        verts_c, rot_c, pos_c, proj_c, vattr_c, improb, imcomp, imidx, ws = ctx.saved_tensors
         meta = ctx.meta
         D, A, flags = ctx.dims
         need_verts, need_vattr = ctx.needs
@@ -185,8 +185,8 @@ class RenderMeshes(Function):
             p.workspace = ctypes.c_void_p(ws.data_ptr())
             p.workspace_bytes = ws.numel()
             p.inst_desc = _lib.ptr(meta["inst_desc"])
-            p.verts = _lib.ptr(verts_c)
-            p.vert_attr_dim, p.attr_flags = A, flags
+            p.verts, p.mesh_faces = _lib.ptr(verts_c), _lib.ptr(pack.faces)
+            p.vert_attr, p.vert_attr_dim, p.attr_flags = _lib.ptr(vattr_c), A, flags
             p.verts_stride, p.vert_attr_stride = int(meta.get("verts_stride", 0)), int(meta.get("vert_attr_stride", 0))
             pose_mode = bool(meta.get("pose_mode"))
             if pose_mode:
@@ -195,7 +195,6 @@ class RenderMeshes(Function):
                 p.znear, p.zfar = float(meta["znear"]), float(meta["zfar"])
             else:
                 p.cam_rot, p.cam_pos, p.cam_proj = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
-            p.face_attr = _lib.ptr(face_attr)
             p.improb, p.imidx, p.imcomp = _lib.ptr(improb), _lib.ptr(imidx), _lib.ptr(imcomp)
             p.grad_improb = _lib.ptr(gP)
             p.num_outputs = len(ctx.split)

@@ -44,7 +44,6 @@ class _PassBuffers(object):
         self.improb = torch.empty(batch, height, width, 1, **f32)
         self.imcomp = torch.empty(batch, height, width, **f32)
         self.imidx = torch.empty(batch, height, width, dtype=torch.int32, device=device)
-        self.face_attr = torch.empty(max_faces, 3, self.D, **f32)
         self.out_min = torch.empty(1, dtype=torch.int32, device=device)
         self.normal_map = torch.empty(batch, height, width, 3, **f32) if "norm" in mode else None
         p = _lib.DibrPass()
@@ -61,7 +60,6 @@ class _PassBuffers(object):
         p.vert_attr = self.vattr.data_ptr() if self.A else None
         p.vert_attr_dim, p.attr_flags = self.A, self.flags
         p.verts_stride, p.vert_attr_stride = 4, int(self.vattr.shape[1]) if self.A else 0
-        p.face_attr = self.face_attr.data_ptr()
         p.improb, p.imidx, p.imcomp = self.improb.data_ptr(), self.imidx.data_ptr(), self.imcomp.data_ptr()
         p.num_outputs = len(self.split)
         for g, (c, o) in enumerate(zip(self.split, self.outs)):

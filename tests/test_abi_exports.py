@@ -54,7 +54,7 @@ def test_struct_size_handshake():
     lib = _lib.load()
     assert lib.dibr_sizeof_pass() == ctypes.sizeof(_lib.DibrPass)
     assert lib.dibr_sizeof_step() == ctypes.sizeof(_lib.DibrStep)
-    assert lib.dibr_abi_version() == 2
+    assert lib.dibr_abi_version() == 3
 
 
 def test_validation_runs_before_any_cuda_call():

@@ -1,8 +1,7 @@
 #!/usr/bin/env python
 """Debug/profiling driver: set up the cfg2 student pass once, then launch dibr_forward N times (L2 flushed between
-launches) and print the mean kernel time.  Used under ncu (-k regex:dibr_forward) and for the v2/v3 A/B:
-    DIBR_FWD_IMPL=4 python tools/fwd_only.py        # barrier-free design (dibr_forward.cu)
-    python tools/fwd_only.py [reps] [teacher]       # default design (dibr_forward_v2.cu); 'teacher' = the norm-only pass (D = 3)"""
+launches) and print the mean kernel time.  Used under ncu (-k regex:dibr_forward):
+    python tools/fwd_only.py [reps] [teacher]       # 'teacher' = the norm-only pass (D = 4)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
@@ -19,4 +18,4 @@ ren = Renderer_dibr(256, 256, "VertexColorBatch")
 dev_in = {k: torch.tensor(student[k], device=dev) for k in ("Rs", "ts", "Ks")}
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 ms = time_forward_kernel(ren, dev_in, cur, mode, 256, flush, reps=reps)
-print("forward kernel (impl %s, %s) %.1f us" % (os.environ.get("DIBR_FWD_IMPL", "2"), "+".join(mode), ms * 1e3), flush=True)
+print("forward kernel (%s) %.1f us" % ("+".join(mode), ms * 1e3), flush=True)
