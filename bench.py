@@ -213,15 +213,21 @@ def main_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def parity_check(sess, meshes, student, n_samples):
+def parity_check(sess, chk, meshes, student, n_samples):
     """The rendered cfg2 batch against the CPU oracle on the first ``n_samples`` samples: face ids and interpolated attributes
-    bit for bit (fp32 operation-order oracle), soft mask against float64."""
+    bit for bit (fp32 operation-order oracle), soft mask against float64.  ``sess`` is the timed session, which turns the
+    interpolated normals into the normal map IN PLACE; ``chk`` rendered the same inputs with raw_normals=True (same kernels,
+    the map goes to its own tensor), so the raw normals can be compared with the oracle -- and every output of the timed
+    session, its normal map included, must equal the checked session's bit for bit."""
     import torch
     from oracle import dibr_oracle as O
-    s = sess.student
+    s = chk.student
     im_all = torch.cat([s.out[k] for k in s.keys], -1).cpu()
     idx_all, prob_all = s.imidx.cpu(), s.improb.cpu()
-    res = {"samples": n_samples, "imidx_mismatch_pixels": 0, "im_mismatch_values": 0, "prob_err_over_tol": 0.0,
+    same_out = bool(torch.equal(sess.student.imidx, s.imidx) and torch.equal(sess.student.improb, s.improb)
+                    and torch.equal(sess.student.normal_map, s.normal_map) and torch.equal(sess.teacher.normal_map, chk.teacher.normal_map)
+                    and all(torch.equal(sess.student.out[k], s.out[k]) for k in s.keys if k != "norm"))
+    res = {"samples": n_samples, "timed_session_equals_checked_session": same_out, "imidx_mismatch_pixels": 0, "im_mismatch_values": 0, "prob_err_over_tol": 0.0,
            "tolerance_prob": "1e-5 * |ref| + 1e-5 vs the float64 oracle on identical fp32 corners"}
     for i in range(n_samples):
         m = meshes[int(student["ids"][i])]
@@ -236,7 +242,7 @@ def parity_check(sess, meshes, student, n_samples):
         same = fw32["imidx"].double() == fw64["imidx"]
         err = ((prob_all[i:i + 1].double() - fw64["improb"]).abs() / (1e-5 * fw64["improb"].abs() + 1e-5))[same]
         res["prob_err_over_tol"] = max(res["prob_err_over_tol"], float(err.max()) if err.numel() else 0.0)
-    res["ok"] = res["imidx_mismatch_pixels"] == 0 and res["im_mismatch_values"] == 0 and res["prob_err_over_tol"] <= 1.0
+    res["ok"] = same_out and res["imidx_mismatch_pixels"] == 0 and res["im_mismatch_values"] == 0 and res["prob_err_over_tol"] <= 1.0
     return res
 
 
@@ -541,7 +547,11 @@ def main_b200(args):
                 roof["fp32"]["frac"] = roof["fp32"]["achieved_tflops"] / roof["fp32"]["peak_tflops_measured"]
         sess_e2e()
         sess.synchronize()
-        par = parity_check(sess, meshes, student, min(4, args.cpu_samples))
+        chk = RenderSession(models, BATCH, RES, RES, student_mode=tuple(stu_mode), teacher_mode=("norm",), device=dev, raw_normals=True)
+        chk.forward(student["Rs"], student["ts"], student["Ks"], cur_models, teacher["Rs"], teacher["ts"])
+        chk.synchronize()
+        par = parity_check(sess, chk, meshes, student, min(4, args.cpu_samples))
+        del chk
         try:
             ks = kaolin_structure_gpu(meshes, student, teacher, dev, 4, flush)
         except Exception as exc:

@@ -174,6 +174,10 @@ int dibr_backward_meshes(const DibrPass *pass, void *stream);
  * min = the batch-global minimum accumulated by dibr_forward into min_ordered. */
 int dibr_normal_map(const float *normals_nx3, const float *mask_n, const uint32_t *min_ordered, float *out_nx3,
                     long long num_pixels, void *stream);
+/* The same map over a pass that dibr_forward has rasterised: only the tiles some face reaches are read and normalised (the
+ * plan of the pass lists them), the others are zero-filled -- or left alone when out_nx3 == normals_nx3 (in place over the
+ * forward's own zero fill).  normals / mask are output groups of the pass, the minimum is pass->out_min_ordered. */
+int dibr_normal_map_pass(const DibrPass *pass, const float *normals_nx3, const float *mask_n, float *out_nx3, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * One render-and-compare step of Self6D++'s compute_self_loss_pose (core/self6dpp/engine/self_engine_utils.py:426-447)

@@ -397,6 +397,15 @@ int dibr_normal_map(const float* normals, const float* mask, const uint32_t* min
     return cuda_fail("dibr_normal_map", dibr::launch_normal_map(normals, mask, min_ordered, out, npix, (cudaStream_t)stream));
 }
 
+int dibr_normal_map_pass(const DibrPass* p, const float* normals, const float* mask, float* out, void* stream) {
+    if (int e = check_common(p, true)) return e;
+    if (!normals || !mask || !out || !p->out_min_ordered) return fail("normal_map_pass: null argument (the pass needs out_min_ordered)");
+    const dibr::Workspace w = carve(p, p->workspace);
+    g_launches += 1;
+    return cuda_fail("dibr_normal_map_pass", dibr::launch_normal_map_tiles(p->batch, p->height, p->width, w.order_cnt, w.order_seg, normals, mask,
+                                                                           p->out_min_ordered, out, (cudaStream_t)stream));
+}
+
 static int nnd_params(const DibrNnd* p, dibr::NndParams& n, bool backward) {
     if (!p) return fail("null DibrNnd");
     if (p->batch < 0 || p->stride1 < 0 || p->stride2 < 0) return fail("nnd: negative sizes");
@@ -726,7 +735,7 @@ int render_forward_on(const DibrStep* st, void* stream, const ForkJoin& fj) {
         if (int e = dibr_forward(p, ks)) return e;
         if (nin[k]) {
             if (!p->out_min_ordered || p->min_output < 0) return fail("render_step: normal map needs min_output/out_min_ordered");
-            if (int e = dibr_normal_map(nin[k], nmask[k], p->out_min_ordered, nout[k], (long long)p->batch * p->height * p->width, ks)) return e;
+            if (int e = dibr_normal_map_pass(p, nin[k], nmask[k], nout[k], ks)) return e;
         }
     }
     return 0;

@@ -354,6 +354,8 @@ int launch_setup_meshes(const SetupParams& P, cudaStream_t stream);
 int launch_forward(const FwdParams& P, cudaStream_t stream);
 int launch_backward_faces(const BwdParams& P, cudaStream_t stream);
 int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream);
+int launch_normal_map_tiles(int batch, int height, int width, const int* order_cnt, const int* order_seg, const float* n, const float* mask,
+                            const unsigned int* min_ordered, float* out, cudaStream_t stream);
 int launch_normal_map(const float* n, const float* mask, const unsigned int* min_ordered, float* out, long long npix, cudaStream_t stream);
 
 }  // namespace dibr

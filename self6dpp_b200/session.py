@@ -30,7 +30,7 @@ _MODE_ATTR = (("color", "colors"), ("norm", "normals"), ("xyz", "vertices"))
 
 
 class _PassBuffers(object):
-    def __init__(self, reg, mode, batch, height, width, max_faces, device, znear, zfar, knum=None):
+    def __init__(self, reg, mode, batch, height, width, max_faces, device, znear, zfar, knum=None, raw_normals=False):
         self.names = [a for k, a in _MODE_ATTR if k in mode]
         self.keys = [k for k, a in _MODE_ATTR if k in mode] + ["ones"] + (["depth"] if "depth" in mode else [])
         self.split = [3] * len(self.names) + [1] + ([1] if "depth" in mode else [])
@@ -45,7 +45,12 @@ class _PassBuffers(object):
         self.imcomp = torch.empty(batch, height, width, **f32)
         self.imidx = torch.empty(batch, height, width, dtype=torch.int32, device=device)
         self.out_min = torch.empty(1, dtype=torch.int32, device=device)
-        self.normal_map = torch.empty(batch, height, width, 3, **f32) if "norm" in mode else None
+        # the normal map is computed in place over the pass's "norm" output group (dibr_normal_map_pass touches only the
+        # tiles some face reaches; the forward's zero fill of the others already is the map)
+        # (raw_normals=True keeps the interpolated normals in out["norm"] and writes the map to its own tensor.)
+        self.normal_map = None
+        if "norm" in mode:
+            self.normal_map = torch.empty(batch, height, width, 3, **f32) if raw_normals else self.out["norm"]
         p = _lib.DibrPass()
         p.batch, p.height, p.width = batch, height, width
         p.num_attr, p.knum = self.D, fused.DEFAULT_KNUM if knum is None else int(knum)
@@ -76,7 +81,7 @@ class _PassBuffers(object):
 
 class RenderSession(object):
     def __init__(self, models, batch, height, width, student_mode=("color", "depth", "mask", "norm", "prob"),
-                 teacher_mode=("norm",), device="cuda:0", znear=0.01, zfar=100.0, teacher_soft_mask=True):
+                 teacher_mode=("norm",), device="cuda:0", znear=0.01, zfar=100.0, teacher_soft_mask=True, raw_normals=False):
         """``teacher_soft_mask=False`` skips the soft-silhouette phase of the teacher rasterisation (K = 0).  The reference
         always computes it (kaolin's forward does) and then drops it when ``mode`` has no "color"
         (renderer_dibr.py:273-286), so nothing a caller can observe changes; the default keeps the reference's work."""
@@ -92,8 +97,8 @@ class RenderSession(object):
         B = self.B
         max_faces = B * int(reg.table[:, 3].max())
         with torch.cuda.device(self.device):
-            self.student = _PassBuffers(reg, student_mode, B, self.H, self.W, max_faces, self.device, znear, zfar)
-            self.teacher = _PassBuffers(reg, teacher_mode, B, self.H, self.W, max_faces, self.device, znear, zfar,
+            self.student = _PassBuffers(reg, student_mode, B, self.H, self.W, max_faces, self.device, znear, zfar, raw_normals=raw_normals)
+            self.teacher = _PassBuffers(reg, teacher_mode, B, self.H, self.W, max_faces, self.device, znear, zfar, raw_normals=raw_normals,
                                         knum=None if teacher_soft_mask else 0) if teacher_mode else None
             f32 = dict(dtype=torch.float32, device=self.device)
             self.g_p2d = torch.empty(max_faces, 6, **f32)

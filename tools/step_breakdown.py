@@ -27,10 +27,10 @@ sp, tp = st.student, st.teacher
 calls = [
     ("student setup_meshes", lambda: lib.dibr_setup_meshes(ctypes.byref(sp), stream)),
     ("student forward", lambda: lib.dibr_forward(ctypes.byref(sp), stream)),
-    ("student normal_map", lambda: lib.dibr_normal_map(ctypes.c_void_p(st.student_normal_in), ctypes.c_void_p(st.student_mask_in), ctypes.c_void_p(sp.out_min_ordered), ctypes.c_void_p(st.student_normal_out), ctypes.c_longlong(npix), stream)),
+    ("student normal_map", lambda: lib.dibr_normal_map_pass(ctypes.byref(sp), ctypes.c_void_p(st.student_normal_in), ctypes.c_void_p(st.student_mask_in), ctypes.c_void_p(st.student_normal_out), stream)),
     ("teacher setup_meshes", lambda: lib.dibr_setup_meshes(ctypes.byref(tp), stream)),
     ("teacher forward", lambda: lib.dibr_forward(ctypes.byref(tp), stream)),
-    ("teacher normal_map", lambda: lib.dibr_normal_map(ctypes.c_void_p(st.teacher_normal_in), ctypes.c_void_p(st.teacher_mask_in), ctypes.c_void_p(tp.out_min_ordered), ctypes.c_void_p(st.teacher_normal_out), ctypes.c_longlong(npix), stream)),
+    ("teacher normal_map", lambda: lib.dibr_normal_map_pass(ctypes.byref(tp), ctypes.c_void_p(st.teacher_normal_in), ctypes.c_void_p(st.teacher_mask_in), ctypes.c_void_p(st.teacher_normal_out), stream)),
     ("backward_faces", lambda: lib.dibr_backward_faces(ctypes.byref(sp), stream)),
     ("backward_meshes", lambda: lib.dibr_backward_meshes(ctypes.byref(sp), stream)),
 ]
