@@ -59,6 +59,7 @@ struct FwdSmem {
             float z[3][LCAP];                   //        view-space depth of the corners (coverage only)
             unsigned int wf[TILE * TILE];       //        winner's face id, committed per batch when a tile needs several
             int big[BIGCAP];
+            unsigned int cq[FWD_THREADS / 32][64];  //    per-warp queue of (face, pixel) pairs that passed the cheap inside test (phase B)
             int4 vid[LCAP];                     //        fused mode: attribute rows of the raster candidates' corners (fetched with the records,
                                                 //        so the resolve does not chain two gathers)
         } ab;
@@ -258,30 +259,89 @@ __device__ __forceinline__ void raster_pixel(FwdSmem& s, const FaceK& fk, unsign
 }
 
 // Phase B.  `nprev`: faces listed by earlier batches of this tile (ranks keep ascending across batches).
+//
+// Four in five pixel centres of a face's bbox lie outside the face.  They are turned away by a CHEAP conservative test --
+// the signs of the two edge functions and of their sum against k3, no division, with margins far above the rounding of
+// the exact solve -- and only the survivors, queued per warp and taken 32 at a time with every lane busy, get the exact
+// barycentric solve in the frozen fp32 order (two IEEE divisions) that decides coverage and depth.  A pixel the cheap
+// test rejects is one the exact test rejects too (proof in the comments below), so the face ids stay bit-exact.
+__device__ __forceinline__ void raster_queued(FwdSmem& s, unsigned entry, int nprev) {
+    const int li = (int)(entry & 511u);
+    const FaceK fk = facek_from_list(s, li);
+    raster_pixel(s, fk, (unsigned)(nprev + li), (int)((entry >> 9) & 15u), (int)(entry >> 13));
+}
+
 __device__ void raster_list(FwdSmem& s, int nprev)
 {
-    const int tid = threadIdx.x;
+    const unsigned full_mask = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rcount = s.rcount;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned int* const cq = s.u.ab.cq[warp];
+    int qn = 0;                                                         // queued candidates of this warp (< 32 between turns)
     // ---- RASTER_LANES lanes per face; faces with many pixels in the tile are deferred to the whole CTA
-    const int q = tid / RASTER_LANES, ql = tid % RASTER_LANES;
-    for (int e = q; e < rcount; e += FWD_THREADS / RASTER_LANES) {
-        const unsigned int packed = s.u.ab.rlist[e];
-        const RasterEntry en = unpack_entry(packed);
-        const int npx = en.nc * en.nr;
-        if (npx > BIG_AREA) {
-            if (ql == 0) {
-                const int slot = atomicAdd(&s.nbig, 1);
-                if (slot < BIGCAP) s.u.ab.big[slot] = (int)packed;     // beyond BIGCAP: picked up by the rescan below
+    const int ql = tid % RASTER_LANES;
+    for (int e0 = warp * (32 / RASTER_LANES); e0 < rcount; e0 += FWD_THREADS / RASTER_LANES) {
+        const int e = e0 + lane / RASTER_LANES;
+        int npx = 0, li = 0, c0 = 0, r0 = 0, nc = 1;
+        float ax = 0.f, ay = 0.f, em = 0.f, ep = 0.f, en_ = 0.f, eq = 0.f, sg = 1.f, lim = 0.f;
+        bool cheap_ok = false;
+        if (e < rcount) {
+            const unsigned int packed = s.u.ab.rlist[e];
+            const RasterEntry en = unpack_entry(packed);
+            npx = en.nc * en.nr;
+            if (npx > BIG_AREA) {
+                if (ql == 0) {
+                    const int slot = atomicAdd(&s.nbig, 1);
+                    if (slot < BIGCAP) s.u.ab.big[slot] = (int)packed;     // beyond BIGCAP: picked up by the rescan below
+                }
+                npx = 0;
+            } else {
+                li = en.li; c0 = en.c0; r0 = en.r0; nc = en.nc;
+                const float4 a = s.c0[li];
+                const float2 b = s.c1[li];
+                ax = a.x; ay = a.y;
+                em = __fsub_rn(a.z, a.x); ep = __fsub_rn(a.w, a.y);         // make_facek's m, p, n, q, k3
+                en_ = __fsub_rn(b.x, a.x); eq = __fsub_rn(b.y, a.y);
+                const float k3 = __fmaf_rn(em, eq, -__fmul_rn(en_, ep));
+                // the margins below hold while the quotients k / k3 of the exact solve are ordinary fp32 divisions (|k3| >= 32,
+                // div_eps) that can neither overflow nor flush to zero
+                cheap_ok = fabsf(k3) >= 32.0f && fabsf(k3) <= 1.0e15f;
+                sg = copysignf(1.0f, k3);
+                lim = fabsf(k3) * 1.0001f;
             }
-            continue;
         }
-        const FaceK fk = facek_from_list(s, en.li);
-        const unsigned inv = c_inv16[en.nc];                           // 65536 / nc + 1: exact i / nc for i < 256
-        for (int i = ql; i < npx; i += RASTER_LANES) {
-            const int row = (int)(((unsigned)i * inv) >> 16);
-            raster_pixel(s, fk, (unsigned)(nprev + en.li), en.c0 + (i - row * en.nc), en.r0 + row);
+        const int maxn = __reduce_max_sync(full_mask, npx);
+        const unsigned inv = c_inv16[nc];                                  // 65536 / nc + 1: exact i / nc for i < 256
+        for (int i0 = 0; i0 < maxn; i0 += RASTER_LANES) {
+            const int i = i0 + ql;
+            bool cand = false;
+            unsigned entry = 0u;
+            if (i < npx) {
+                const int row = (int)(((unsigned)i * inv) >> 16);
+                const int lx = c0 + (i - row * nc), ly = r0 + row;
+                const float sx = __fsub_rn(s.xs[lx], ax), ty = __fsub_rn(s.ys[ly], ay);
+                const float k1 = __fmaf_rn(sx, eq, -__fmul_rn(en_, ty)) * sg;      // w1 = k1 / k3, w2 = k2 / k3 (bary)
+                const float k2 = __fmaf_rn(em, ty, -__fmul_rn(sx, ep)) * sg;
+                // k1 sg < -1e-12: w1 = -|k1| / |k3| <= -1e-27 is an ordinary negative number -> bary() says outside.  Same for
+                // w2.  Otherwise both are >= -3e-14, and (k1 + k2) sg > 1.0001 |k3| puts w1 + w2 above 1 by 1e-4, four hundred
+                // times the rounding of w0 = (1 - w1) - w2 -> w0 < 0.  NaNs fail every comparison and stay candidates.
+                cand = !cheap_ok || !(k1 < -1.0e-12f || k2 < -1.0e-12f || (k1 + k2) > lim);
+                entry = (unsigned)li | ((unsigned)lx << 9) | ((unsigned)ly << 13);
+            }
+            const unsigned bal = __ballot_sync(full_mask, cand);
+            if (cand) cq[qn + __popc(bal & lt)] = entry;
+            qn += __popc(bal);
+            if (qn >= 32) {
+                __syncwarp();
+                raster_queued(s, cq[qn - 32 + lane], nprev);
+                qn -= 32;
+                __syncwarp();
+            }
         }
     }
+    __syncwarp();
+    if (lane < qn) raster_queued(s, cq[lane], nprev);
     __syncthreads();
     // ---- large faces: one pixel per thread
     const int nbig_all = s.nbig;
