@@ -95,10 +95,10 @@ def torch_project(verts, faces, cam_rot, cam_pos, proj):
     return p3, p2, n[:, 2:3], p
 
 
-def oracle_render_batch64(meshes, ids, Rs, ts, Ks, H, W, attr_names, with_depth, grads, imidx_override=None):
+def oracle_render_batch64(meshes, ids, Rs, ts, Ks, H, W, attr_names, with_depth, grads, imidx_override=None, dt=torch.float64):
     """float64: every sample rendered with attributes [attr_names..., ones, (depth)]; returns images and
-    dL/dRs, dL/dts for loss = sum(im * grads['im']) + sum(prob * grads['prob'])."""
-    dt = torch.float64
+    dL/dRs, dL/dts for loss = sum(im * grads['im']) + sum(prob * grads['prob']).  ``dt=torch.float32`` runs the same
+    pipeline in fp32 (profiles/r02_parity.md: what ANY fp32 evaluation is away from float64)."""
     Rs = torch.tensor(Rs, dtype=dt, requires_grad=True)
     ts = torch.tensor(ts, dtype=dt, requires_grad=True)
     cams = O.camera_params_from_RT_K(Rs, ts, torch.tensor(Ks, dtype=dt), H, W, near=0.01, far=100.0)
@@ -121,7 +121,7 @@ def oracle_render_batch64(meshes, ids, Rs, ts, Ks, H, W, attr_names, with_depth,
         probs.append(fw["improb"])
         idxs.append(fw["imidx"])
         if grads is not None:
-            dp2, dat = O.rasterize_backward(fw, grads["im"][i:i + 1], grads["prob"][i:i + 1])
+            dp2, dat = O.rasterize_backward(fw, grads["im"][i:i + 1].to(dt), grads["prob"][i:i + 1].to(dt))
             proxy = proxy + (p2 * dp2[0]).sum() + (at * dat[0]).sum()
     out = {"im": torch.cat(ims), "prob": torch.cat(probs), "imidx": torch.cat(idxs)}
     if grads is not None:

@@ -103,13 +103,15 @@ def test_render_batch_pose_gradients_vs_float64():
     same = (cov64 == cov32)
     assert same.float().mean() > 0.999
     # full float64 pipeline (float64 vertex shader too): bounded by the fp32 quantisation of projected coordinates
-    Hh.assert_close("im", got_im, ref["im"], mask=same.expand_as(ref["im"]), rtol=1e-4, atol_rel=1e-4)
-    Hh.assert_close("prob", ret["prob"].unsqueeze(-1), ref["prob"], mask=same, rtol=1e-4, atol_rel=1e-4)
+    # gates = 2x the achieved error of profiles/r02_parity.md (3.2e-5 / 2.7e-5, equal to a plain fp32 pipeline's own error)
+    Hh.assert_close("im", got_im, ref["im"], mask=same.expand_as(ref["im"]), rtol=7e-5, atol_rel=7e-5)
+    Hh.assert_close("prob", ret["prob"].unsqueeze(-1), ref["prob"], mask=same, rtol=7e-5, atol_rel=7e-5)
     loss = (ret["color"] * g_color.float().to(DEV)).sum() + (ret["prob"] * g_prob[..., 0].float().to(DEV)).sum() \
         + (ret["depth"] * g_depth[..., 0].float().to(DEV)).sum()
     loss.backward()
-    e_R = Hh.assert_close("dL/dR", Rs.grad, ref["grad_Rs"], rtol=2e-4, atol_rel=2e-4)
-    e_t = Hh.assert_close("dL/dt", ts.grad, ref["grad_ts"], rtol=2e-4, atol_rel=2e-4)
+    # achieved 2.2e-5 / 3.0e-5 (a plain fp32 pipeline: 3.1e-5 / 4.8e-5), profiles/r02_parity.md
+    e_R = Hh.assert_close("dL/dR", Rs.grad, ref["grad_Rs"], rtol=6e-5, atol_rel=6e-5)
+    e_t = Hh.assert_close("dL/dt", ts.grad, ref["grad_ts"], rtol=6e-5, atol_rel=6e-5)
     print({"e_R": e_R, "e_t": e_t})
     # deterministic
     Rs2 = torch.tensor(batch["Rs"], device=DEV, requires_grad=True)
