@@ -37,6 +37,7 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     {
         const size_t ntiles = (size_t)p->batch * ((p->height + dibr::TILE - 1) / dibr::TILE) * ((p->width + dibr::TILE - 1) / dibr::TILE);
         w.order_seg = (int*)take(sizeof(int) * dibr::ORDER_BUCKETS * ntiles);
+        w.order_desc = (int4*)take(sizeof(int4) * dibr::ORDER_BUCKETS * ntiles);
         // counters (+ the plan summary), per-tile face counters, per-image progress, then the bins: one memset clears all
         w.order_cnt = (int*)take(sizeof(int) * 4 * dibr::ORDER_BUCKETS);
         w.tile_count = (int*)take(sizeof(int) * ntiles);
@@ -73,6 +74,7 @@ int check_common(const DibrPass* p, bool need_ws) {
     if (!p->face_offsets && (long long)p->faces_per_image * p->batch != (long long)p->total_faces)
         return fail("faces_per_image*batch != total_faces and no face_offsets given");
     if ((long long)p->batch * p->height * p->width >= (1ll << 31)) return fail("image batch too large for 32-bit pixel ids");
+    if (dibr::bin_total_words(p->width, p->height, p->batch, p->total_faces) >= (1ull << 31)) return fail("tiles x faces too large: the tile bitmaps exceed 2^31 words");
     if (need_ws) {
         if (!p->workspace) return fail("workspace is null");
         if (((uintptr_t)p->workspace & 255u) != 0) return fail("workspace must be 256-byte aligned");
@@ -285,7 +287,7 @@ int dibr_forward(const DibrPass* p, void* stream) {
     f.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     f.faces_per_image = p->faces_per_image; f.face_offsets = p->face_offsets;
     f.total_faces = p->total_faces;
-    f.recs = w.recs; f.bins = w.bins; f.order_cnt = w.order_cnt; f.order_seg = w.order_seg; f.xs = w.xs; f.ys = w.ys; f.face_attr = p->face_attr;
+    f.recs = w.recs; f.bins = w.bins; f.order_cnt = w.order_cnt; f.order_seg = w.order_seg; f.order_desc = w.order_desc; f.xs = w.xs; f.ys = w.ys; f.face_attr = p->face_attr;
     if (fused) set_vertex_attr(f.va, p, w);
     if (p->num_outputs == 0) { f.n_out = 1; f.out_ch[0] = p->num_attr; f.out[0] = p->im; }
     else { f.n_out = p->num_outputs; for (int g = 0; g < f.n_out; g++) { f.out_ch[g] = p->out_channels[g]; f.out[g] = p->out[g]; } }

@@ -438,6 +438,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
     const int tiles_x = (P.width + TILE - 1) / TILE, tiles_y = (P.height + TILE - 1) / TILE;
     const int ntiles = tiles_x * tiles_y * P.batch;
     int tile;
+    int4 desc;               // plan entry: tile id, the image's face range, offset of the tile's bitmap
     {
         // the plan's summary (last CTA of plan_tiles_kernel): surplus CTAs of the grid leave after one load
         if ((int)blockIdx.x >= __ldg(P.order_cnt + PLAN_WORK_CTAS)) return;
@@ -454,26 +455,24 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         const int start = __ldg(P.order_cnt + PLAN_START + lane);                      // first position of bucket 31 - lane
         const unsigned le = __ballot_sync(full_mask, start <= (int)blockIdx.x);       // lane 31 (bucket 0) starts at `touched`
         const int src = 31 - __clz(le);
-        tile = __ldg(P.order_seg + (size_t)(ORDER_BUCKETS - 1 - src) * ntiles + ((int)blockIdx.x - __shfl_sync(full_mask, start, src)));
+        desc = __ldg(P.order_desc + (size_t)(ORDER_BUCKETS - 1 - src) * ntiles + ((int)blockIdx.x - __shfl_sync(full_mask, start, src)));
+        tile = desc.x;
     }
 #ifdef DIBR_EXP_ONLYFILL
     return;
 #endif
     int b, tile_y, tile_x;
     unpack_tile(tile, b, tile_y, tile_x);
-    const int tile_in = tile_y * tiles_x + tile_x;
     const int tx0 = tile_x * TILE, ty0 = tile_y * TILE;
     TileGeom T;
     T.tw = min(TILE, P.width - tx0); T.th = min(TILE, P.height - ty0); T.tx0 = tx0; T.ty0 = ty0;
     const int tw = T.tw, th = T.th;
-    const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
-    const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
+    const int f_lo = desc.y, f_hi = desc.z;
     const int D = P.num_attr;
     const size_t img_pix = (size_t)b * P.height * P.width;
     float* __restrict__ improb = P.improb + img_pix;
     float* __restrict__ imcomp = P.imcomp + img_pix;
     int* __restrict__ imidx = P.imidx + img_pix;
-    const float ex = P.expand_mul;
 
 
     // ---- tile set-up ----------------------------------------------------------------------------
@@ -492,7 +491,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         const int w0 = f_lo >> 5;
         T.nw = ((f_hi - 1) >> 5) - w0 + 1;
         T.id0 = (w0 << 5) - f_lo;
-        T.words = P.bins + (size_t)tiles_x * tiles_y * ((size_t)w0 + b) + (size_t)tile_in * T.nw;
+        T.words = P.bins + (size_t)(unsigned)desc.w;
     }
     __syncthreads();
 

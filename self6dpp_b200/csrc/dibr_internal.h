@@ -20,6 +20,8 @@ struct Workspace {
     int* tile_count;    // [batch * tiles] faces listed in the tile's bitmap (bumped by the binning; directly after order_cnt: same memset)
     int* img_done;      // [batch] faces of the image that are binned (the CTA that completes an image plans its tiles; same memset)
     int* order_seg;     // [ORDER_BUCKETS, batch * tiles] tile ids of each bucket: the forward kernel works heaviest bucket first
+    int4* order_desc;   // same shape: {tile id, first face of the image, one past its last face, offset of the tile's bitmap in bins (words)}:
+                        // everything a tile CTA needs to start reading its bitmap, in one load
     float* xs;          // [width]  pixel-centre x
     float* ys;          // [height] pixel-centre y
     float* pose_part;   // [num_instances * POSE_BLOCKS * 12] partial pose-gradient sums
@@ -87,6 +89,7 @@ struct FwdParams {
     const uint32_t* bins;
     const int* order_cnt;
     const int* order_seg;
+    const int4* order_desc;
     const float* xs;           // [width], [height] pixel-centre tables
     const float* ys;
     const float* face_attr;

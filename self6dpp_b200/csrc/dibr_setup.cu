@@ -122,6 +122,9 @@ __device__ void plan_image(const SetupParams& P, PlanSmem& s, int b)
     const int ntiles = tiles * P.batch;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int* __restrict__ cnt = P.ws.tile_count + (size_t)b * tiles;
+    const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
+    const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
+    const int w0 = f_lo >> 5, nw = ((f_hi - 1) >> 5) - w0 + 1;          // bitmap words per tile (bin_face)
     if (tid < ORDER_BUCKETS) { s.hist[tid] = 0; s.fill[tid] = 0; }
     __syncthreads();
     for (int t = tid; t < tiles; t += nthr) atomicAdd(&s.hist[min((__ldcg(cnt + t) + 31) >> 5, ORDER_BUCKETS - 1)], 1);
@@ -132,7 +135,9 @@ __device__ void plan_image(const SetupParams& P, PlanSmem& s, int b)
         const int kb = min((__ldcg(cnt + t) + 31) >> 5, ORDER_BUCKETS - 1);
         const int pos = s.base[kb] + atomicAdd(&s.fill[kb], 1);
         const int ty = t / tiles_x;
-        P.ws.order_seg[(size_t)kb * ntiles + pos] = pack_tile(b, ty, t - ty * tiles_x);
+        const int id = pack_tile(b, ty, t - ty * tiles_x);
+        P.ws.order_seg[(size_t)kb * ntiles + pos] = id;
+        P.ws.order_desc[(size_t)kb * ntiles + pos] = make_int4(id, f_lo, f_hi, (int)((size_t)tiles * ((size_t)w0 + b) + (size_t)t * nw));
     }
     __syncthreads();
 }

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Turn gpurun_out/r01_launches.csv (+ r01_top.ncu-rep) into the tracked summaries under profiles/."""
+"""Turn gpurun_out/<tag>_launches.csv (+ <tag>_top.ncu-rep) into the tracked summaries under profiles/ (usage: summarize_profiles.py r02)."""
 import csv, collections, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(ROOT, "profiles")
