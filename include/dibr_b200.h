@@ -339,7 +339,8 @@ int dibr_lab_loss_backward(const DibrLabLoss *p, void *stream);
  * when want_grad, the per-level coefficient maps; the backward must be given the same workspace untouched and writes
  * d L / d y for grad_out = d L / d out ([n_img]).  x is data on this path (no gradient). */
 typedef struct DibrMsSsim {
-    int32_t n_img, channels, height, width, levels, normalize, want_grad, reserved0;
+    int32_t n_img, channels, height, width, levels, normalize, want_grad;
+    int32_t use_padding;                     /* ssim.py:42-55: zero-pad the 11-tap windows (maps of the input's size) instead of valid windows */
     float data_range;
     float window[11];
     float weights[8];
@@ -414,6 +415,24 @@ typedef struct DibrRoiAlign {
 } DibrRoiAlign;
 int dibr_roi_align_forward(const DibrRoiAlign *p, void *stream);
 int dibr_roi_align_backward(const DibrRoiAlign *p, void *stream);
+
+/* batch_crop_resize(interpolation="nearest") (core/utils/zoom_utils.py:91-92) = torchvision.ops.RoIPool(output_size,
+ * spatial_scale): maximum over quantised bins.  Same addressing as DibrRoiAlign; argmax: [num_rois, channels, pooled_h,
+ * pooled_w] int32 scratch the forward fills (position h * width + w of the maximum, -1 for an empty bin) and the backward
+ * reads.  The backward writes EVERY element of grad_input by a fixed-order gather (torchvision scatters with atomicAdd). */
+typedef struct DibrRoiPool {
+    int32_t num_rois, num_images, channels, height, width, pooled_h, pooled_w, reserved0;
+    float spatial_scale, reserved1;
+    int64_t stride_n, stride_c, stride_h, stride_w;
+    const float *input;
+    const float *rois;
+    float *output;
+    int32_t *argmax;
+    const float *grad_output;                /* backward in */
+    float *grad_input;                       /* backward out */
+} DibrRoiPool;
+int dibr_roi_pool_forward(const DibrRoiPool *p, void *stream);
+int dibr_roi_pool_backward(const DibrRoiPool *p, void *stream);
 
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);

@@ -66,7 +66,7 @@ def lab_l1_loss(gt, ren, mask=None, no_l=False, bgr=True):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# MS-SSIM: core/self6dpp/losses/ssim.py:13-160 (create_window, _gaussian_filter, ssim, ms_ssim; use_padding=False)
+# MS-SSIM: core/self6dpp/losses/ssim.py:13-160 (create_window, _gaussian_filter, ssim, ms_ssim; use_padding False or True)
 # ------------------------------------------------------------------------------------------------------------------
 def create_window(window_size=11, sigma=1.5):
     """ssim.py:13-30 (float32 arithmetic like torch's, then promoted)"""
@@ -76,9 +76,11 @@ def create_window(window_size=11, sigma=1.5):
     return g.astype(np.float64)
 
 
-def _filt(img, win):
-    """valid separable correlation over the last two axes (ssim.py:33-55)"""
+def _filt(img, win, pad=0):
+    """separable correlation over the last two axes, valid or zero padded by `pad` on every side (ssim.py:33-55)"""
     k = len(win)
+    if pad:
+        img = np.pad(img, [(0, 0)] * (img.ndim - 2) + [(pad, pad), (pad, pad)])
     H, W = img.shape[-2:]
     out = np.zeros(img.shape[:-1] + (W - k + 1,))
     for i in range(k):
@@ -89,8 +91,11 @@ def _filt(img, win):
     return out2
 
 
-def _filt_T(m, win):
-    """adjoint of _filt: (.., H-k+1, W-k+1) -> (.., H, W)"""
+def _filt_T(m, win, pad=0):
+    """adjoint of _filt: (.., H-k+1+2 pad, W-k+1+2 pad) -> (.., H, W)"""
+    if pad:
+        full = _filt_T(m, win)
+        return full[..., pad:full.shape[-2] - pad, pad:full.shape[-1] - pad]
     k = len(win)
     Ho, Wo = m.shape[-2:]
     mid = np.zeros(m.shape[:-2] + (Ho + k - 1, Wo))
@@ -126,11 +131,12 @@ def _pool_T(g, H, W):
 
 
 def ms_ssim(X, Y, data_range=1.0, weights=(0.0448, 0.2856, 0.3001, 0.2363, 0.1333), normalize=False, window=None,
-            grad_out=None):
+            grad_out=None, use_padding=False):
     """returns (ms [N], d sum(grad_out * ms) / d Y or None)"""
     X = np.asarray(X, dtype=np.float64)
     Y = np.asarray(Y, dtype=np.float64)
     win = create_window() if window is None else np.asarray(window, dtype=np.float64)
+    pad = len(win) // 2 if use_padding else 0                                                     # ssim.py:42-45
     w = np.asarray(np.asarray(weights, dtype=np.float32), dtype=np.float64)
     L = len(w)
     C1, C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
@@ -138,8 +144,8 @@ def ms_ssim(X, Y, data_range=1.0, weights=(0.0448, 0.2856, 0.3001, 0.2363, 0.133
     cs_vals, ssim_vals = [], []
     for l in range(L):
         x, y = xs[-1], ys[-1]
-        mu1, mu2 = _filt(x, win), _filt(y, win)
-        e11, e22, e12 = _filt(x * x, win), _filt(y * y, win), _filt(x * y, win)
+        mu1, mu2 = _filt(x, win, pad), _filt(y, win, pad)
+        e11, e22, e12 = _filt(x * x, win, pad), _filt(y * y, win, pad), _filt(x * y, win, pad)
         s11, s22, s12 = e11 - mu1 ** 2, e22 - mu2 ** 2, e12 - mu1 * mu2
         dcs, dl = s11 + s22 + C2, mu1 ** 2 + mu2 ** 2 + C1
         cs = (2 * s12 + C2) / dcs
@@ -177,7 +183,7 @@ def ms_ssim(X, Y, data_range=1.0, weights=(0.0448, 0.2856, 0.3001, 0.2363, 0.133
         else:
             s = ms * w[l] / cs_vals[l] * half / npx
         s = (s * go).reshape(-1, 1, 1, 1)
-        g = s * (_filt_T(g_mu, win) + 2 * y * _filt_T(g_22, win) + x * _filt_T(g_12, win))
+        g = s * (_filt_T(g_mu, win, pad) + 2 * y * _filt_T(g_22, win, pad) + x * _filt_T(g_12, win, pad))
         if g_next is not None:
             g = g + _pool_T(g_next, x.shape[-2], x.shape[-1])
         g_next = g

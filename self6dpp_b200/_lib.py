@@ -105,7 +105,7 @@ class DibrMsSsim(ctypes.Structure):
 
     _fields_ = [
         ("n_img", ctypes.c_int32), ("channels", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
-        ("levels", ctypes.c_int32), ("normalize", ctypes.c_int32), ("want_grad", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("levels", ctypes.c_int32), ("normalize", ctypes.c_int32), ("want_grad", ctypes.c_int32), ("use_padding", ctypes.c_int32),
         ("data_range", ctypes.c_float), ("window", ctypes.c_float * 11), ("weights", ctypes.c_float * 8),
         ("x", _c_f32p), ("y", _c_f32p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("out", _c_f32p), ("grad_out", _c_f32p), ("grad_y", _c_f32p),
@@ -130,6 +130,18 @@ class DibrNormLoss(ctypes.Structure):
         ("n_img", ctypes.c_int32), ("hw", ctypes.c_int32), ("with_l1", ctypes.c_int32), ("with_cs", ctypes.c_int32),
         ("out_norm", _c_f32p), ("gt_norm", _c_f32p), ("mask", _c_f32p),
         ("scratch", _c_f32p), ("out", _c_f32p), ("grad_out", _c_f32p), ("grad_out_norm", _c_f32p),
+    ]
+
+
+class DibrRoiPool(ctypes.Structure):
+    """Mirror of ``struct DibrRoiPool`` (include/dibr_b200.h)."""
+
+    _fields_ = [
+        ("num_rois", ctypes.c_int32), ("num_images", ctypes.c_int32), ("channels", ctypes.c_int32), ("height", ctypes.c_int32),
+        ("width", ctypes.c_int32), ("pooled_h", ctypes.c_int32), ("pooled_w", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("spatial_scale", ctypes.c_float), ("reserved1", ctypes.c_float),
+        ("stride_n", ctypes.c_int64), ("stride_c", ctypes.c_int64), ("stride_h", ctypes.c_int64), ("stride_w", ctypes.c_int64),
+        ("input", _c_f32p), ("rois", _c_f32p), ("output", _c_f32p), ("argmax", _c_i32p), ("grad_output", _c_f32p), ("grad_input", _c_f32p),
     ]
 
 
@@ -163,7 +175,7 @@ EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_devi
            "dibr_mask_loss_backward", "dibr_chamfer_reduce_forward", "dibr_chamfer_reduce_backward",
            "dibr_lab_loss_scratch_floats", "dibr_lab_loss_forward", "dibr_lab_loss_backward",
            "dibr_ms_ssim_workspace_bytes", "dibr_ms_ssim_forward", "dibr_ms_ssim_backward",
-           "dibr_roi_align_forward", "dibr_roi_align_backward", "dibr_dice_loss_forward", "dibr_dice_loss_backward",
+           "dibr_roi_align_forward", "dibr_roi_align_backward", "dibr_roi_pool_forward", "dibr_roi_pool_backward", "dibr_dice_loss_forward", "dibr_dice_loss_backward",
            "dibr_norm_loss_scratch_floats", "dibr_norm_loss_forward", "dibr_norm_loss_backward",
            "dibr_launch_count"]
 
@@ -248,6 +260,10 @@ def load():
     for name in ("dibr_dice_loss_forward", "dibr_dice_loss_backward"):
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(DibrDiceLoss), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    for name in ("dibr_roi_pool_forward", "dibr_roi_pool_backward"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(DibrRoiPool), ctypes.c_void_p]
         fn.restype = ctypes.c_int
     for name in ("dibr_roi_align_forward", "dibr_roi_align_backward"):
         fn = getattr(lib, name)

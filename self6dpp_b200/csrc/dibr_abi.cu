@@ -236,6 +236,35 @@ int dibr_roi_align_backward(const DibrRoiAlign* p, void* stream) {
     return cuda_fail("dibr_roi_align_backward", dibr::launch_roi_align_backward(q, (cudaStream_t)stream));
 }
 
+static int rp_params(const DibrRoiPool* p, dibr::RoiPoolParams& q, bool backward) {
+    if (!p) return fail("null DibrRoiPool");
+    if (p->num_rois < 0 || p->num_images < 0 || p->channels < 0) return fail("roi_pool: negative size");
+    if (p->height <= 0 || p->width <= 0 || p->pooled_h <= 0 || p->pooled_w <= 0) return fail("roi_pool: bad image / output size");
+    if ((long long)p->height * p->width >= (1ll << 31)) return fail("roi_pool: image too large for 32-bit positions");
+    if (p->num_rois > 0 && (!p->rois || !p->argmax)) return fail("roi_pool: rois / argmax required");
+    if (!backward && p->num_rois > 0 && p->channels > 0 && (!p->input || !p->output)) return fail("roi_pool: input / output required");
+    if (backward && p->num_images > 0 && p->channels > 0 && (!p->grad_input || (p->num_rois > 0 && !p->grad_output)))
+        return fail("roi_pool backward: grad_output / grad_input required");
+    if (dibr_device_count() <= 0) return fail("no CUDA device: libdibr_b200 has no CPU fallback");
+    q.input = p->input; q.rois = p->rois; q.output = p->output; q.argmax = p->argmax; q.grad_output = p->grad_output; q.grad_input = p->grad_input;
+    q.num_rois = p->num_rois; q.num_images = p->num_images; q.channels = p->channels; q.height = p->height; q.width = p->width;
+    q.pooled_h = p->pooled_h; q.pooled_w = p->pooled_w; q.spatial_scale = p->spatial_scale;
+    q.stride_n = p->stride_n; q.stride_c = p->stride_c; q.stride_h = p->stride_h; q.stride_w = p->stride_w;
+    return 0;
+}
+int dibr_roi_pool_forward(const DibrRoiPool* p, void* stream) {
+    dibr::RoiPoolParams q;
+    if (int e = rp_params(p, q, false)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_roi_pool_forward", dibr::launch_roi_pool_forward(q, (cudaStream_t)stream));
+}
+int dibr_roi_pool_backward(const DibrRoiPool* p, void* stream) {
+    dibr::RoiPoolParams q;
+    if (int e = rp_params(p, q, true)) return e;
+    g_launches += 1;
+    return cuda_fail("dibr_roi_pool_backward", dibr::launch_roi_pool_backward(q, (cudaStream_t)stream));
+}
+
 long long dibr_launch_count(int reset) {
     const long long v = g_launches;
     if (reset) g_launches = 0;
@@ -546,7 +575,7 @@ int dibr_lab_loss_backward(const DibrLabLoss* p, void* stream) {
 
 namespace {
 struct SsimPlan {
-    int levels, planes;
+    int levels, planes, pad;
     int H[dibr::SSIM_MAX_LEVELS], W[dibr::SSIM_MAX_LEVELS], tiles[dibr::SSIM_MAX_LEVELS];
     size_t px[dibr::SSIM_MAX_LEVELS], py[dibr::SSIM_MAX_LEVELS], gp[dibr::SSIM_MAX_LEVELS];      // float offsets (level 0 unused)
     size_t maps[dibr::SSIM_MAX_LEVELS], partial[dibr::SSIM_MAX_LEVELS], scale;
@@ -561,15 +590,18 @@ static int ssim_plan(const DibrMsSsim* p, SsimPlan& s) {
     if ((long long)p->n_img * p->channels > 65535) return fail("ms_ssim: n_img * channels must be <= 65535");
     s.levels = p->levels; s.planes = p->n_img * p->channels;
     int h = p->height, w = p->width;
+    const int pad = p->use_padding ? 5 : 0;               // ssim.py:42-45: window_size // 2
+    s.pad = pad;
     size_t off = 0;
     for (int l = 0; l < s.levels; l++) {
-        if (h < 11 || w < 11) return fail("ms_ssim: every level must keep at least 11x11 pixels (ssim.py valid convolution)");
-        s.H[l] = h; s.W[l] = w; s.tiles[l] = dibr::ssim_forward_tiles(h, w);
+        if (!pad && (h < 11 || w < 11)) return fail("ms_ssim: every level must keep at least 11x11 pixels (ssim.py valid convolution)");
+        if (h < 1 || w < 1) return fail("ms_ssim: a level has no pixels");
+        s.H[l] = h; s.W[l] = w; s.tiles[l] = dibr::ssim_forward_tiles(h, w, pad);
         const size_t img = (size_t)s.planes * h * w;
         s.px[l] = off; if (l) off += img;
         s.py[l] = off; if (l) off += img;
         s.gp[l] = off; if (l && p->want_grad) off += img;
-        s.maps[l] = off; if (p->want_grad) off += (size_t)s.planes * 3 * (h - 10) * (w - 10);
+        s.maps[l] = off; if (p->want_grad) off += (size_t)s.planes * 3 * (h - 10 + 2 * pad) * (w - 10 + 2 * pad);
         off = (off + 3) & ~(size_t)3;                // the combine kernel reads the partials as float2
         s.partial[l] = off; off += (size_t)s.planes * s.tiles[l] * 2;
         h = (h + 2 * (h & 1) - 2) / 2 + 1;          // avg_pool2d(kernel 2, stride 2, padding h % 2)
@@ -589,7 +621,7 @@ int dibr_ms_ssim_workspace_bytes(const DibrMsSsim* p, size_t* bytes) {
 static void ssim_level(const DibrMsSsim* p, const SsimPlan& s, int l, dibr::SsimLevelParams& q) {
     float* ws = (float*)p->workspace;
     q = dibr::SsimLevelParams{};
-    q.H = s.H[l]; q.W = s.W[l]; q.channels = p->channels; q.use_ssim = (l == s.levels - 1);
+    q.H = s.H[l]; q.W = s.W[l]; q.channels = p->channels; q.use_ssim = (l == s.levels - 1); q.pad = s.pad;
     const double k1 = 0.01 * (double)p->data_range, k2 = 0.03 * (double)p->data_range;      // ssim.py:72-73, python doubles
     q.C1 = (float)(k1 * k1);
     q.C2 = (float)(k2 * k2);
@@ -622,7 +654,7 @@ int dibr_ms_ssim_forward(const DibrMsSsim* p, void* stream) {
         }
         g_launches += 1;
         if (int e = cuda_fail("dibr_ms_ssim_forward(level)", dibr::launch_ssim_level_forward(q, s.planes, st))) return e;
-        c.weights[l] = p->weights[l]; c.tiles[l] = s.tiles[l]; c.map_pixels[l] = (s.H[l] - 10) * (s.W[l] - 10);
+        c.weights[l] = p->weights[l]; c.tiles[l] = s.tiles[l]; c.map_pixels[l] = (s.H[l] - 10 + 2 * s.pad) * (s.W[l] - 10 + 2 * s.pad);
         c.partial_off[l] = (long long)s.partial[l];
     }
     c.partial = ws; c.out = p->out; c.scale = p->want_grad ? ws + s.scale : nullptr;

@@ -265,6 +265,20 @@ struct RoiAlignParams {
 };
 int launch_roi_align_forward(const RoiAlignParams& P, cudaStream_t stream);
 int launch_roi_align_backward(const RoiAlignParams& P, cudaStream_t stream);
+// RoIPool (max over quantised bins), the 'nearest' mode of batch_crop_resize
+struct RoiPoolParams {
+    const float* input;        // [num_images, channels, height, width] through element strides
+    const float* rois;         // [num_rois, 5]
+    float* output;             // [num_rois, channels, pooled_h, pooled_w]
+    int* argmax;               // same shape: h * width + w of the maximum, -1 for an empty bin
+    const float* grad_output;
+    float* grad_input;         // same strides as input; every element is written
+    int num_rois, num_images, channels, height, width, pooled_h, pooled_w;
+    float spatial_scale;
+    long long stride_n, stride_c, stride_h, stride_w;
+};
+int launch_roi_pool_forward(const RoiPoolParams& P, cudaStream_t stream);
+int launch_roi_pool_backward(const RoiPoolParams& P, cudaStream_t stream);
 // L1 in normalised CIE-Lab between the real and the rendered crop (dibr_photometric.cu)
 struct LabLossParams {
     int n_img;                 // images
@@ -289,6 +303,7 @@ struct SsimLevelParams {
     int H, W;                  // this level's image size
     int channels;
     int use_ssim;              // last level: the maps are d ssim, otherwise d cs
+    int pad;                   // 0: valid windows; 5: zero padding (ssim.py use_padding)
     float C1, C2;
     float win[11];
     const float* x;            // [planes, H, W]
@@ -312,7 +327,7 @@ struct SsimCombineParams {
     float* scale;              // [levels, n_img] or null
 };
 int launch_ssim_pool(const float* x, const float* y, float* px, float* py, int planes, int H, int W, int Ho, int Wo, cudaStream_t stream);
-int ssim_forward_tiles(int H, int W);
+int ssim_forward_tiles(int H, int W, int pad);
 int launch_ssim_level_forward(const SsimLevelParams& P, int planes, cudaStream_t stream);
 int launch_ssim_combine(const SsimCombineParams& P, cudaStream_t stream);
 int launch_ssim_level_backward(const SsimLevelParams& P, int planes, cudaStream_t stream);

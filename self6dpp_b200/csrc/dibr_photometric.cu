@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(256) ssim_level_forward_kernel(SsimLevelParams
     __shared__ float sy[SS_IN][SS_IN + 1];
     __shared__ float hz[5][SS_IN][SS_TILE + 1];
     __shared__ float red[8][2];
-    const int Ho = P.H - (SS_WIN - 1), Wo = P.W - (SS_WIN - 1);
+    // pad = 0: valid windows; pad = 5: zero padding on every side (ssim.py:42-55, use_padding), map of the input's size
+    const int Ho = P.H - (SS_WIN - 1) + 2 * P.pad, Wo = P.W - (SS_WIN - 1) + 2 * P.pad;
     const int tiles_x = (Wo + SS_TILE - 1) / SS_TILE;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     const int plane = blockIdx.y;
@@ -252,8 +253,8 @@ __global__ void __launch_bounds__(256) ssim_level_forward_kernel(SsimLevelParams
     const float* Y = P.y + (size_t)plane * P.H * P.W;
     for (int i = threadIdx.x; i < SS_IN * SS_IN; i += 256) {
         const int r = i / SS_IN, c = i - r * SS_IN;
-        const int gr = r0 + r, gc = c0 + c;
-        const bool in = gr < P.H && gc < P.W;
+        const int gr = r0 + r - P.pad, gc = c0 + c - P.pad;
+        const bool in = gr >= 0 && gc >= 0 && gr < P.H && gc < P.W;
         sx[r][c] = in ? X[(size_t)gr * P.W + gc] : 0.f;
         sy[r][c] = in ? Y[(size_t)gr * P.W + gc] : 0.f;
     }
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(256) ssim_level_backward_kernel(SsimLevelParam
 {
     __shared__ float sm[3][SS_IN][SS_IN + 1];
     __shared__ float hz[3][SS_IN][SS_TILE + 1];
-    const int Ho = P.H - (SS_WIN - 1), Wo = P.W - (SS_WIN - 1);
+    const int Ho = P.H - (SS_WIN - 1) + 2 * P.pad, Wo = P.W - (SS_WIN - 1) + 2 * P.pad;
     const int tiles_x = (P.W + SS_TILE - 1) / SS_TILE;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     const int plane = blockIdx.y;
@@ -389,10 +390,11 @@ __global__ void __launch_bounds__(256) ssim_level_backward_kernel(SsimLevelParam
     const int r0 = ty * SS_TILE, c0 = tx * SS_TILE;
     const size_t msz = (size_t)Ho * Wo;
     const float* M = P.maps + (size_t)plane * 3 * msz;
-    // map pixel (u, v) feeds input pixels (u .. u+10, v .. v+10): this tile needs u in [r0 - 10, r0 + 31]
+    // map pixel (u, v) feeds input pixels (u - pad .. u - pad + 10, v - pad .. v - pad + 10): this tile needs
+    // u in [r0 + pad - 10, r0 + pad + 31]
     for (int i = threadIdx.x; i < SS_IN * SS_IN; i += 256) {
         const int r = i / SS_IN, c = i - r * SS_IN;
-        const int u = r0 - (SS_WIN - 1) + r, v = c0 - (SS_WIN - 1) + c;
+        const int u = r0 + P.pad - (SS_WIN - 1) + r, v = c0 + P.pad - (SS_WIN - 1) + c;
         const bool in = u >= 0 && u < Ho && v >= 0 && v < Wo;
         const size_t o = (size_t)u * Wo + v;
         sm[0][r][c] = in ? M[o] : 0.f; sm[1][r][c] = in ? M[msz + o] : 0.f; sm[2][r][c] = in ? M[2 * msz + o] : 0.f;
@@ -459,14 +461,14 @@ int launch_ssim_pool(const float* x, const float* y, float* px, float* py, int p
     ssim_pool_kernel<<<ph_grid(total), 256, 0, stream>>>(x, y, px, py, planes, H, W, Ho, Wo);
     return (int)cudaGetLastError();
 }
-int ssim_forward_tiles(int H, int W)
+int ssim_forward_tiles(int H, int W, int pad)
 {
-    const int Ho = H - (SS_WIN - 1), Wo = W - (SS_WIN - 1);
+    const int Ho = H - (SS_WIN - 1) + 2 * pad, Wo = W - (SS_WIN - 1) + 2 * pad;
     return ((Ho + SS_TILE - 1) / SS_TILE) * ((Wo + SS_TILE - 1) / SS_TILE);
 }
 int launch_ssim_level_forward(const SsimLevelParams& P, int planes, cudaStream_t stream)
 {
-    dim3 grid(ssim_forward_tiles(P.H, P.W), planes);
+    dim3 grid(ssim_forward_tiles(P.H, P.W, P.pad), planes);
     ssim_level_forward_kernel<<<grid, 256, 0, stream>>>(P);
     return (int)cudaGetLastError();
 }

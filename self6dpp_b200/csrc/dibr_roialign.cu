@@ -327,7 +327,102 @@ __global__ void __launch_bounds__(RA_T, DIBR_RA_MIN_CTAS) roi_align_backward_ker
     }
 }
 
+// ---- RoIPool: batch_crop_resize(interpolation="nearest") = torchvision.ops.RoIPool(output_size, 1.0)
+//      (/root/reference/core/utils/zoom_utils.py:91-92).  Quantised roi (roundf of the scaled corners, width / height
+//      >= 1), bin (ph, pw) = rows floor(ph * bin_h) .. ceil((ph + 1) * bin_h) (shifted by the roi start, clipped to the
+//      image), maximum and its first position in row-major order; an empty bin gives 0 and no gradient.
+struct PoolBox { int b, sw, sh; float bin_h, bin_w; };
+__device__ __forceinline__ PoolBox pool_box(const RoiPoolParams& P, int r) {
+    const float* roi = P.rois + (size_t)r * 5;
+    PoolBox B;
+    B.b = (int)roi[0];
+    B.sw = (int)roundf(roi[1] * P.spatial_scale); B.sh = (int)roundf(roi[2] * P.spatial_scale);
+    const int ew = (int)roundf(roi[3] * P.spatial_scale), eh = (int)roundf(roi[4] * P.spatial_scale);
+    const int rw = max(ew - B.sw + 1, 1), rh = max(eh - B.sh + 1, 1);               // malformed rois become 1 x 1
+    B.bin_h = (float)rh / (float)P.pooled_h; B.bin_w = (float)rw / (float)P.pooled_w;
+    return B;
+}
+__device__ __forceinline__ void pool_bin(const RoiPoolParams& P, const PoolBox& B, int ph, int pw, int& h0, int& h1, int& w0, int& w1) {
+    h0 = min(max((int)floorf((float)ph * B.bin_h) + B.sh, 0), P.height);
+    h1 = min(max((int)ceilf((float)(ph + 1) * B.bin_h) + B.sh, 0), P.height);
+    w0 = min(max((int)floorf((float)pw * B.bin_w) + B.sw, 0), P.width);
+    w1 = min(max((int)ceilf((float)(pw + 1) * B.bin_w) + B.sw, 0), P.width);
+}
+
+__global__ void __launch_bounds__(256) roi_pool_forward_kernel(const RoiPoolParams P)
+{
+    const long long total = (long long)P.num_rois * P.channels * P.pooled_h * P.pooled_w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int pw = (int)(i % P.pooled_w), ph = (int)((i / P.pooled_w) % P.pooled_h);
+        const int c = (int)((i / ((long long)P.pooled_w * P.pooled_h)) % P.channels);
+        const int r = (int)(i / ((long long)P.pooled_w * P.pooled_h * P.channels));
+        const PoolBox B = pool_box(P, r);
+        int h0, h1, w0, w1;
+        pool_bin(P, B, ph, pw, h0, h1, w0, w1);
+        const bool empty = (h1 <= h0) || (w1 <= w0) || B.b < 0 || B.b >= P.num_images;
+        float best = empty ? 0.f : -3.402823466e+38f;
+        int arg = -1;
+        if (!empty) {
+            const float* img = P.input + (long long)B.b * P.stride_n + (long long)c * P.stride_c;
+            for (int h = h0; h < h1; h++)
+                for (int w = w0; w < w1; w++) {
+                    const float v = img[(long long)h * P.stride_h + (long long)w * P.stride_w];
+                    if (v > best) { best = v; arg = h * P.width + w; }
+                }
+        }
+        P.output[i] = best;
+        P.argmax[i] = arg;
+    }
+}
+
+// Gradient by gather, one thread per input element: the bins of every roi of its image that can hold the pixel are
+// visited in (roi, ph, pw) order and those whose recorded maximum IS the pixel add their gradient -- no atomics, every
+// element written once, bit-reproducible (torchvision scatters with atomicAdd).
+__global__ void __launch_bounds__(256) roi_pool_backward_kernel(const RoiPoolParams P)
+{
+    const long long total = (long long)P.num_images * P.channels * P.height * P.width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % P.width), h = (int)((i / P.width) % P.height);
+        const int c = (int)((i / ((long long)P.width * P.height)) % P.channels);
+        const int b = (int)(i / ((long long)P.width * P.height * P.channels));
+        float g = 0.f;
+        for (int r = 0; r < P.num_rois; r++) {
+            const PoolBox B = pool_box(P, r);
+            if (B.b != b) continue;
+            // candidate bins: bin ph holds row h' = h - start iff floor(ph bin) <= h' < ceil((ph + 1) bin), which puts ph strictly
+            // between (h' - 1) / bin - 1 and (h' + 1) / bin; the recorded argmax decides membership exactly
+            const float hr = (float)(h - B.sh), wr = (float)(w - B.sw);
+            const int p0 = max((int)floorf((hr - 1.f) / B.bin_h) - 1, 0), p1 = min((int)floorf((hr + 1.f) / B.bin_h) + 1, P.pooled_h - 1);
+            const int q0 = max((int)floorf((wr - 1.f) / B.bin_w) - 1, 0), q1 = min((int)floorf((wr + 1.f) / B.bin_w) + 1, P.pooled_w - 1);
+            for (int ph = p0; ph <= p1; ph++)
+                for (int pw = q0; pw <= q1; pw++) {
+                    const size_t o = (((size_t)r * P.channels + c) * P.pooled_h + ph) * P.pooled_w + pw;
+                    if (P.argmax[o] == h * P.width + w) g += P.grad_output[o];
+                }
+        }
+        P.grad_input[(long long)b * P.stride_n + (long long)c * P.stride_c + (long long)h * P.stride_h + (long long)w * P.stride_w] = g;
+    }
+}
+
 }  // namespace
+
+int launch_roi_pool_forward(const RoiPoolParams& P, cudaStream_t stream)
+{
+    const long long total = (long long)P.num_rois * P.channels * P.pooled_h * P.pooled_w;
+    if (total <= 0) return 0;
+    const long long want = (total + 255) / 256;
+    roi_pool_forward_kernel<<<(int)(want < 148ll * 32 ? want : 148ll * 32), 256, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+int launch_roi_pool_backward(const RoiPoolParams& P, cudaStream_t stream)
+{
+    const long long total = (long long)P.num_images * P.channels * P.height * P.width;
+    if (total <= 0) return 0;
+    const long long want = (total + 255) / 256;
+    roi_pool_backward_kernel<<<(int)(want < 148ll * 32 ? want : 148ll * 32), 256, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
 
 int launch_roi_align_forward(const RoiAlignParams& P, cudaStream_t stream)
 {

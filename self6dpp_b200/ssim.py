@@ -28,10 +28,11 @@ def create_window(window_size, sigma):
     return g
 
 
-def _fill(q, X, Y, window, weights, data_range, normalize, want_grad):
+def _fill(q, X, Y, window, weights, data_range, normalize, want_grad, use_padding=False):
     n, c, h, w = Y.shape
     q.n_img, q.channels, q.height, q.width = n, c, h, w
     q.levels, q.normalize, q.want_grad = len(weights), int(bool(normalize)), int(bool(want_grad))
+    q.use_padding = int(bool(use_padding))
     q.data_range = float(data_range)
     for i, v in enumerate(window):
         q.window[i] = v
@@ -42,7 +43,7 @@ def _fill(q, X, Y, window, weights, data_range, normalize, want_grad):
 
 class _MsSsim(Function):
     @staticmethod
-    def forward(ctx, X, Y, window, weights, data_range, normalize):
+    def forward(ctx, X, Y, window, weights, data_range, normalize, use_padding=False):
         _require_cuda_f32("X", X)
         _require_cuda_f32("Y", Y)
         if X.dim() != 4 or X.shape != Y.shape:
@@ -54,7 +55,7 @@ class _MsSsim(Function):
         want_grad = Y.requires_grad
         lib = _lib.load()
         q = _lib.DibrMsSsim()
-        _fill(q, x_c, y_c, window, weights, data_range, normalize, want_grad)
+        _fill(q, x_c, y_c, window, weights, data_range, normalize, want_grad, use_padding)
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.dibr_ms_ssim_workspace_bytes(ctypes.byref(q), ctypes.byref(nbytes)), "dibr_ms_ssim_workspace_bytes")
         ws = torch.empty((nbytes.value + 3) // 4, dtype=torch.float32, device=device)
@@ -64,23 +65,23 @@ class _MsSsim(Function):
             _lib.check(lib.dibr_ms_ssim_forward(ctypes.byref(q), _stream(device)), "dibr_ms_ssim_forward")
         if want_grad:
             ctx.save_for_backward(x_c, y_c, ws)
-            ctx.cfg = (window, weights, data_range, normalize)
+            ctx.cfg = (window, weights, data_range, normalize, use_padding)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         x_c, y_c, ws = ctx.saved_tensors
-        window, weights, data_range, normalize = ctx.cfg
+        window, weights, data_range, normalize, use_padding = ctx.cfg
         device = y_c.device
         go = grad_out.detach().to(torch.float32).contiguous()
         gy = torch.empty_like(y_c)
         q = _lib.DibrMsSsim()
-        _fill(q, x_c, y_c, window, weights, data_range, normalize, True)
+        _fill(q, x_c, y_c, window, weights, data_range, normalize, True, use_padding)
         q.workspace, q.workspace_bytes = ws.data_ptr(), ws.numel() * 4
         q.grad_out, q.grad_y = _lib.ptr(go), _lib.ptr(gy)
         with torch.cuda.device(device):
             _lib.check(_lib.load().dibr_ms_ssim_backward(ctypes.byref(q), _stream(device)), "dibr_ms_ssim_backward")
-        return None, gy, None, None, None, None
+        return None, gy, None, None, None, None, None
 
 
 class MS_SSIM(torch.nn.Module):
@@ -92,8 +93,6 @@ class MS_SSIM(torch.nn.Module):
         assert window_size % 2 == 1, "Window size must be odd."
         if window_size != 11:
             raise NotImplementedError("self6dpp_b200 MS_SSIM: window_size must be 11 (the reference's default)")
-        if use_padding:
-            raise NotImplementedError("self6dpp_b200 MS_SSIM: use_padding=True is not built (the reference's default is False)")
         self.data_range = data_range
         self.use_padding = use_padding
         self.normalize = normalize
@@ -109,4 +108,4 @@ class MS_SSIM(torch.nn.Module):
         self._weights = tuple(float(v) for v in weights)
 
     def forward(self, X, Y):
-        return _MsSsim.apply(X, Y, self._window, self._weights, self.data_range, self.normalize)
+        return _MsSsim.apply(X, Y, self._window, self._weights, self.data_range, self.normalize, self.use_padding)

@@ -8,7 +8,8 @@ contiguous BCHW input -- the rendered image arrives as a permuted BHWC view, so 
 gradient with fp32 atomics.  Here ``x`` is read through its strides (no copy for any dense layout), and the backward is a
 fixed-order gather that writes the dense gradient once, in ``x``'s own layout: bit-reproducible.  No CPU fallback.
 
-``interpolation="nearest"`` (torchvision ``RoIPool``) has no call site in the reference's ``core/`` and is refused.
+``interpolation="nearest"`` is torchvision's ``RoIPool`` (maximum over quantised bins; no call site in the reference's
+``core/`` uses it): its own pair of kernels, gradient by a fixed-order gather.
 """
 import ctypes
 
@@ -83,6 +84,61 @@ class _RoiAlign(Function):
         return grad_x, None, None, None, None, None, None
 
 
+class _RoiPool(Function):
+    @staticmethod
+    def forward(ctx, x, rois, out_h, out_w, spatial_scale):
+        _require_cuda_f32("x", x)
+        _require_cuda_f32("rois", rois)
+        if x.dim() != 4:
+            raise RuntimeError("batch_crop_resize: x must be BCHW")
+        if rois.dim() != 2 or rois.shape[1] != 5:
+            raise RuntimeError("batch_crop_resize: rois must be Bx5 (index into x, x1, y1, x2, y2)")
+        if rois.device != x.device:
+            raise RuntimeError("batch_crop_resize: x and rois must be on the same device")
+        xd = x.detach()
+        if _dense_strides(xd) is None:
+            xd = xd.contiguous()
+        r_c = rois.detach().contiguous()
+        out = torch.empty(r_c.shape[0], x.shape[1], int(out_h), int(out_w), dtype=torch.float32, device=x.device)
+        arg = torch.empty(out.shape, dtype=torch.int32, device=x.device)
+        q = _lib.DibrRoiPool()
+        _fill_pool(q, xd, r_c, out_h, out_w, spatial_scale)
+        q.input, q.output, q.argmax = _lib.ptr(xd), _lib.ptr(out), _lib.ptr(arg)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().dibr_roi_pool_forward(ctypes.byref(q), _stream(x.device)), "dibr_roi_pool_forward")
+        ctx.save_for_backward(r_c, arg)
+        ctx.meta = (tuple(x.shape), tuple(xd.stride()), int(out_h), int(out_w), float(spatial_scale))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        r_c, arg = ctx.saved_tensors
+        shape, strides, out_h, out_w, spatial_scale = ctx.meta
+        g = grad_out.contiguous()
+        grad_x = torch.empty_strided(shape, strides, dtype=torch.float32, device=g.device)     # every element is written
+        if grad_x.numel() > 0:
+            q = _lib.DibrRoiPool()
+            _fill_pool(q, grad_x, r_c, out_h, out_w, spatial_scale)
+            q.argmax, q.grad_output, q.grad_input = _lib.ptr(arg), _lib.ptr(g), _lib.ptr(grad_x)
+            with torch.cuda.device(g.device):
+                _lib.check(_lib.load().dibr_roi_pool_backward(ctypes.byref(q), _stream(g.device)), "dibr_roi_pool_backward")
+        return grad_x, None, None, None, None
+
+
+def _fill_pool(q, x_like, rois, out_h, out_w, spatial_scale):
+    n, c, h, w = x_like.shape
+    q.num_rois, q.num_images, q.channels, q.height, q.width = rois.shape[0], n, c, h, w
+    q.pooled_h, q.pooled_w, q.spatial_scale = int(out_h), int(out_w), float(spatial_scale)
+    q.stride_n, q.stride_c, q.stride_h, q.stride_w = (int(s) for s in x_like.stride())
+    q.rois = _lib.ptr(rois)
+
+
+def roi_pool(x, rois, output_size, spatial_scale=1.0):
+    """``torchvision.ops.RoIPool(output_size, spatial_scale)(x, rois)``."""
+    out_h, out_w = (output_size, output_size) if isinstance(output_size, int) else output_size
+    return _RoiPool.apply(x, rois, out_h, out_w, spatial_scale)
+
+
 def roi_align(x, rois, output_size, spatial_scale=1.0, sampling_ratio=0, aligned=True):
     """``ROIAlign(output_size, spatial_scale, sampling_ratio, aligned)(x, rois)`` (detectron2.layers.roi_align)."""
     out_h, out_w = (output_size, output_size) if isinstance(output_size, int) else output_size
@@ -101,7 +157,7 @@ def batch_crop_resize(x, rois, out_H, out_W, aligned=True, interpolation="biline
     if interpolation == "bilinear":
         return roi_align(x, rois, (out_H, out_W), 1.0, 0, aligned)
     if interpolation == "nearest":
-        raise NotImplementedError("interpolation='nearest' (RoIPool) is not provided: no call site in the reference uses it")
+        return roi_pool(x, rois, (out_H, out_W), 1.0)              # RoIPool(output_size, 1.0), zoom_utils.py:91-92
     raise ValueError(f"Wrong interpolation type: {interpolation}")
 
 

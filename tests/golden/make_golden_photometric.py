@@ -64,7 +64,9 @@ def golden_ms_ssim():
     out = {}
     cases = (("a", (2, 3, 192, 208), dict(data_range=1.0, normalize=True), None),         # the loop's configuration, 5 levels
              ("b", (1, 3, 97, 113), dict(data_range=1.0, normalize=True, levels=3), None),  # odd sizes: padded pooling
-             ("c", (2, 1, 64, 48), dict(data_range=1.0, normalize=False, levels=2, channel=1), None))
+             ("c", (2, 1, 64, 48), dict(data_range=1.0, normalize=False, levels=2, channel=1), None),
+             ("d", (2, 3, 96, 80), dict(data_range=1.0, normalize=True, use_padding=True), None),     # zero-padded windows, 5 levels
+             ("e", (1, 3, 45, 37), dict(data_range=1.0, normalize=False, use_padding=True, levels=3), None))   # odd sizes, levels below 11 px
     for tag, shape, kw, _ in cases:
         n, c, h, w = shape
         gt, ren, mask = crops(g, n, h, w, black=True)
@@ -77,7 +79,7 @@ def golden_ms_ssim():
         (val * go).sum().backward()
         out.update({f"ssim_{tag}_x": X.numpy(), f"ssim_{tag}_ren": ren.detach().numpy(), f"ssim_{tag}_mask": mask.numpy(),
                     f"ssim_{tag}_levels": np.array(len(m.weights)), f"ssim_{tag}_weights": m.weights.numpy(),
-                    f"ssim_{tag}_normalize": np.array(int(kw["normalize"])), f"ssim_{tag}_window": m.window[0, 0, 0].numpy(),
+                    f"ssim_{tag}_normalize": np.array(int(kw["normalize"])), f"ssim_{tag}_pad": np.array(int(kw.get("use_padding", False))), f"ssim_{tag}_window": m.window[0, 0, 0].numpy(),
                     f"ssim_{tag}_val": val.detach().numpy(), f"ssim_{tag}_go": go.numpy(), f"ssim_{tag}_grad": ren.grad.numpy()})
         print("ms_ssim", tag, val.detach().numpy())
     return out

@@ -83,7 +83,7 @@ def test_lab_cpu_tensor_raises():
 # entry against the reference's fp32 autograd (whose own conv / cancellation noise is of that order: the float64 oracle
 # agrees with it only to ~1e-5..1e-4) and 2e-5 against the float64 oracle.
 # ------------------------------------------------------------------------------------------------------------------
-SSIM_TAGS = "abc"
+SSIM_TAGS = "abcde"         # d, e: use_padding=True (zero-padded windows)
 
 
 def test_ms_ssim_oracle_matches_reference_golden():
@@ -93,7 +93,8 @@ def test_ms_ssim_oracle_matches_reference_golden():
         y = d[f"ssim_{tag}_ren"] * d[f"ssim_{tag}_mask"]
         np.testing.assert_allclose(P.create_window(), d[f"ssim_{tag}_window"], rtol=1e-6)
         ms, g_y = P.ms_ssim(d[f"ssim_{tag}_x"], y, data_range=1.0, weights=d[f"ssim_{tag}_weights"],
-                            normalize=bool(d[f"ssim_{tag}_normalize"]), window=d[f"ssim_{tag}_window"], grad_out=d[f"ssim_{tag}_go"])
+                            normalize=bool(d[f"ssim_{tag}_normalize"]), window=d[f"ssim_{tag}_window"], grad_out=d[f"ssim_{tag}_go"],
+                            use_padding=bool(d[f"ssim_{tag}_pad"]))
         np.testing.assert_allclose(ms, d[f"ssim_{tag}_val"], rtol=1e-5)
         ref = d[f"ssim_{tag}_grad"]
         got = g_y * d[f"ssim_{tag}_mask"]                 # chain through ren * mask
@@ -102,8 +103,7 @@ def test_ms_ssim_oracle_matches_reference_golden():
 
 def test_ms_ssim_module_rejects_unbuilt_options():
     from self6dpp_b200.ssim import MS_SSIM, create_window
-    with pytest.raises(NotImplementedError):
-        MS_SSIM(use_padding=True)
+    assert MS_SSIM(use_padding=True).use_padding
     with pytest.raises(NotImplementedError):
         MS_SSIM(window_size=7)
     m = MS_SSIM(data_range=1.0, normalize=True, levels=3)
@@ -121,7 +121,8 @@ def test_ms_ssim_gpu_matches_reference_golden_and_is_reproducible():
     d = np.load(GOLD)
     for tag in SSIM_TAGS:
         levels = int(d[f"ssim_{tag}_levels"])
-        m = MS_SSIM(data_range=1.0, normalize=bool(d[f"ssim_{tag}_normalize"]), levels=levels if levels != 5 else None).to(dev)
+        m = MS_SSIM(data_range=1.0, normalize=bool(d[f"ssim_{tag}_normalize"]), levels=levels if levels != 5 else None,
+                    use_padding=bool(d[f"ssim_{tag}_pad"])).to(dev)
         np.testing.assert_allclose(m.weights.cpu().numpy(), d[f"ssim_{tag}_weights"], rtol=1e-6)
         mask = torch.tensor(d[f"ssim_{tag}_mask"], device=dev)
         outs = []

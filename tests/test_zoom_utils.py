@@ -54,8 +54,8 @@ def test_batch_crop_resize_refuses_cpu_and_unknown_modes():
         batch_crop_resize(x, r, 4, 4)
     with pytest.raises(ValueError):
         batch_crop_resize(x, r, 4, 4, interpolation="cubic")
-    with pytest.raises(NotImplementedError):
-        batch_crop_resize(x, r, 4, 4, interpolation="nearest")
+    with pytest.raises(Exception):
+        batch_crop_resize(x, r, 4, 4, interpolation="nearest")      # CPU tensors: no fallback for RoIPool either
 
 
 @pytest.mark.gpu
@@ -188,3 +188,47 @@ def test_roialign_gpu_random_rois_against_oracle(seed):
         ry, rgx = O.roi_align(xs.numpy(), rois.numpy(), oh, ow, 1.0, sr, aligned, grad_out=go.numpy())
         _close(f"y aligned={aligned} sr={sr}", y.detach().cpu().numpy(), ry)
         _close(f"gx aligned={aligned} sr={sr}", x.grad.cpu().numpy(), rgx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1])
+def test_roipool_nearest_against_torchvision(seed):
+    """batch_crop_resize(interpolation="nearest") = torchvision.ops.RoIPool(output_size, 1.0) (zoom_utils.py:91-92), against
+    torchvision's own CPU op on random rois (inside, straddling the border, outside, malformed, smaller than the output grid):
+    the forward bit for bit (a maximum is a selection), the gradient to 1e-6 (torchvision adds with atomics in arbitrary order,
+    ours is a fixed-order gather) and bit-reproducible, in both memory layouts."""
+    from torchvision.ops import roi_pool as tv_roi_pool
+    from self6dpp_b200.zoom_utils import batch_crop_resize
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(40 + seed)
+    B, C, H, W, R = 3, 4, 37, 45, 60
+    x = torch.randn(B, C, H, W, generator=g)
+    c = torch.rand(R, 2, generator=g) * torch.tensor([W + 10.0, H + 10.0]) - 5.0
+    s = torch.rand(R, 2, generator=g) * 14 + 0.3
+    rois = torch.cat([torch.randint(0, B, (R, 1), generator=g).float(), c - s, c + s], dim=1)
+    rois[3, 1:] = torch.tensor([20.0, 20.0, 10.0, 5.0])             # x2 < x1, y2 < y1: becomes 1 x 1
+    rois[4, 1:] = torch.tensor([-30.0, -30.0, -20.0, -25.0])        # outside: empty bins, zeros, no gradient
+    rois[5, 1:] = torch.tensor([10.2, 11.7, 12.4, 13.1])            # smaller than the 6 x 5 output grid
+    oh, ow = 6, 5
+    go = torch.randn(R, C, oh, ow, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = tv_roi_pool(xr, rois, (oh, ow), 1.0)
+    (yr * go).sum().backward()
+    outs = []
+    for layout in ("bchw", "bhwc", "bchw"):
+        xd = x.to(dev)
+        if layout == "bhwc":
+            xd = xd.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        xd.requires_grad_(True)
+        y = batch_crop_resize(xd, rois.to(dev), oh, ow, interpolation="nearest")
+        (y * go.to(dev)).sum().backward()
+        assert xd.grad.stride() == xd.stride()
+        assert torch.equal(y.detach().cpu(), yr.detach()), layout
+        _close("roipool gx " + layout, xd.grad.cpu().numpy(), xr.grad.numpy(), 1e-6)
+        outs.append((y.detach().clone(), xd.grad.clone()))
+    for a, b in zip(outs[0], outs[2]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    y0 = batch_crop_resize(x.to(dev), torch.zeros(0, 5, device=dev), oh, ow, interpolation="nearest")
+    assert y0.shape == (0, C, oh, ow)
