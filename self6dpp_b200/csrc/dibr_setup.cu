@@ -62,8 +62,15 @@ __device__ __forceinline__ void bin_face(const SetupParams& P, int g, int b, int
 
 // The CTA's records are staged in shared memory and written out as whole 512 B rows per warp instruction (a thread's
 // own 64 B at a stride touches 16 lines per store instruction instead of 4).
+// Threads per set-up CTA.  157 k faces are ONE wave of work: with 128 threads (56 registers, 10 KB of shared memory) nine CTAs
+// fit an SM and the whole grid is resident at once; 256-thread CTAs left 21 of 613 CTAs for a second wave that doubled the
+// kernel's time.
+#ifndef DIBR_SETUP_THREADS
+#define DIBR_SETUP_THREADS 128
+#endif
+constexpr int SETUP_T = DIBR_SETUP_THREADS;
 struct StageSmem {
-    float4 rec[256 * 4];                // 16 KB, 16 B chunks swizzled by (thread >> 1) & 3 against bank conflicts
+    float4 rec[SETUP_T * 4];            // 64 B per thread, 16 B chunks swizzled by (thread >> 1) & 3 against bank conflicts
 };
 __device__ __forceinline__ int rec_slot(int t, int c) { return t * 4 + (c ^ ((t >> 1) & 3)); }
 
@@ -91,13 +98,13 @@ __device__ __forceinline__ void store_face(const SetupParams& P, StageSmem& st, 
                                          __uint_as_float((unsigned)e0 | ((unsigned)e1 << 16)), __uint_as_float((unsigned)q0 | ((unsigned)q1 << 16)));
     if (ok) bin_face(P, g, b, e0, e1, q0, q1);
     __syncthreads();
-    // the CTA's 256 records are contiguous in global memory: 1024 16 B chunks, four per thread, fully coalesced
+    // the CTA's records are contiguous in global memory: 16 B chunks, four per thread, fully coalesced
     const int g0 = blockIdx.x * blockDim.x;
     const int nrec = min((int)blockDim.x, P.total_faces - g0);
     float4* out = reinterpret_cast<float4*>(P.ws.recs + g0);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int i = k * 256 + t;
+        const int i = k * SETUP_T + t;
         if (i < nrec * 4) out[i] = st.rec[rec_slot(i >> 2, i & 3)];
     }
 }
@@ -108,7 +115,7 @@ __device__ __forceinline__ int pack_tile(int b, int ty, int tx) { return (int)((
 
 struct PlanSmem {
     int hist[ORDER_BUCKETS], base[ORDER_BUCKETS], fill[ORDER_BUCKETS];
-    int fin[256];           // images this CTA completed
+    int fin[SETUP_T];       // images this CTA completed
     int nfin, last;
 };
 
@@ -199,7 +206,7 @@ __device__ void plan_epilogue(const SetupParams& P, int g, int b, bool active)
     }
 }
 
-__global__ void __launch_bounds__(256) setup_faces_kernel(SetupParams P)
+__global__ void __launch_bounds__(SETUP_T) setup_faces_kernel(SetupParams P)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     write_tables(P, g);
@@ -223,10 +230,7 @@ __global__ void __launch_bounds__(256) setup_faces_kernel(SetupParams P)
 }
 
 // ---- fused mode: one thread per face of the ragged batch ----------------------------------------------------------
-#ifndef DIBR_SETUP_MIN_CTAS
-#define DIBR_SETUP_MIN_CTAS 4
-#endif
-__global__ void __launch_bounds__(256, DIBR_SETUP_MIN_CTAS) setup_meshes_kernel(SetupParams P)
+__global__ void __launch_bounds__(SETUP_T) setup_meshes_kernel(SetupParams P)
 {
     __shared__ StageSmem st;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(256, DIBR_SETUP_MIN_CTAS) setup_meshes_kernel(
 
 static inline int setup_grid(const SetupParams& P) {
     const int n = max(P.total_faces, P.width + P.height);
-    return (n + 255) / 256;
+    return (n + SETUP_T - 1) / SETUP_T;
 }
 
 // plan counters, per-tile face counters, per-image progress counters and the tile bitmaps are adjacent in the workspace:
@@ -363,7 +367,7 @@ int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
 {
     cudaError_t e = clear_plan(P, stream);
     if (e != cudaSuccess) return (int)e;
-    setup_faces_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
+    setup_faces_kernel<<<setup_grid(P), SETUP_T, 0, stream>>>(P);
     return (int)cudaGetLastError();
 }
 
@@ -371,7 +375,7 @@ int launch_setup_meshes(const SetupParams& P, cudaStream_t stream)
 {
     cudaError_t e = clear_plan(P, stream);
     if (e != cudaSuccess) return (int)e;
-    setup_meshes_kernel<<<setup_grid(P), 256, 0, stream>>>(P);
+    setup_meshes_kernel<<<setup_grid(P), SETUP_T, 0, stream>>>(P);
     return (int)cudaGetLastError();
 }
 
