@@ -571,12 +571,13 @@ def main_b200(args):
                            "batch_per_gpu": BATCH, "faces_in_batch": faces_total, "l2": "flushed between steps (256 MiB memset)",
                            "passes": "2 fused rasterisations + 1 backward per step (reference: 4 fwd + 2 bwd per sample); inside the forward call the teacher rasterisation runs on the session's side stream next to the student chain",
                            "api": "value/e2e: RenderSession.forward -> dibr_render_forward, then RenderSession.backward -> dibr_render_backward "
-                                  "(two C-ABI calls per step, gradients handed over after the forward); one_call_step: dibr_render_step; "
+                                  "(two C-ABI calls per step, gradients handed over after the forward; the session captures the launches of "
+                                  "each call into a CUDA graph the second time it is made and replays it afterwards); one_call_step: dibr_render_step; "
                                   "python_api: Renderer_dibr.render_batch x2 + torch.autograd.backward (drop-in reference API)"},
                 "one_call_step": {"value": BATCH * n * args.steps / (one_ms * 1e-3), "unit": UNIT, "ms_per_step": one_ms / args.steps,
                                   "note": "dibr_render_step: forward + backward in one call, student chain on the side stream throughout"},
                 "cuda_graph": ({"value": BATCH * n * args.steps / (graph_ms * 1e-3), "unit": UNIT, "ms_per_step": graph_ms / args.steps,
-                                "note": "the forward + backward calls of `value` captured once and replayed as one CUDA graph"}
+                                "note": "the forward AND backward calls captured together and replayed as ONE CUDA graph (`value` replays one graph per call: RenderSession captures each call the second time it is made)"}
                                if graph_ms else {"value": None, "error": locals().get("graph_err")}),
                 "option_teacher_without_soft_mask": {"value": BATCH * n * args.steps / (lean_ms * 1e-3), "unit": UNIT,
                                                      "ms_per_step": lean_ms / args.steps,

@@ -63,7 +63,8 @@ typedef struct DibrPass {
     int32_t multiplier;      /* reference default 1000 (passed as a C int, rasterizer.py:170) */
     int32_t delta;           /* reference default 7000 ("sigmainv") */
     float expand;            /* reference default 0.02 */
-    int32_t total_faces;     /* faces over all images */
+    int32_t total_faces;     /* faces over all images.  With face_offsets this is the CAPACITY of the per-face arrays (and fixes the
+                                workspace layout); the faces in use are face_offsets[batch] <= total_faces, read on the device */
     int32_t faces_per_image; /* used when face_offsets == NULL */
     const int32_t *face_offsets; /* [batch+1] or NULL */
 
@@ -436,6 +437,9 @@ int dibr_roi_pool_backward(const DibrRoiPool *p, void *stream);
 
 /* how many kernels the library has launched on this thread since the last reset (bench evidence) */
 long long dibr_launch_count(int reset);
+/* a caller that replays a captured CUDA graph of library calls adds the kernels of the replay here (the count above only sees
+ * the launches of the capture) */
+void dibr_launch_count_add(long long n);
 
 #ifdef __cplusplus
 }

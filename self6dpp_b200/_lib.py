@@ -170,7 +170,7 @@ class DibrChamferReduce(ctypes.Structure):
 
 EXPORTS = ["dibr_abi_version", "dibr_sizeof_pass", "dibr_last_error", "dibr_device_count", "dibr_workspace_bytes",
            "dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces",
-           "dibr_backward_meshes", "dibr_normal_map", "dibr_normal_map_pass", "dibr_render_step", "dibr_render_forward", "dibr_render_backward", "dibr_overlap_create", "dibr_overlap_destroy", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_backproject_compact",
+           "dibr_backward_meshes", "dibr_normal_map", "dibr_normal_map_pass", "dibr_launch_count_add", "dibr_render_step", "dibr_render_forward", "dibr_render_backward", "dibr_overlap_create", "dibr_overlap_destroy", "dibr_sizeof_step", "dibr_nnd_forward", "dibr_nnd_backward", "dibr_nnd_workspace_bytes", "dibr_backproject_compact",
            "dibr_backproject_compact_backward", "dibr_mask_loss_scratch_floats", "dibr_mask_loss_forward",
            "dibr_mask_loss_backward", "dibr_chamfer_reduce_forward", "dibr_chamfer_reduce_backward",
            "dibr_lab_loss_scratch_floats", "dibr_lab_loss_forward", "dibr_lab_loss_backward",
@@ -206,6 +206,8 @@ def load():
     lib.dibr_device_count.restype = ctypes.c_int
     lib.dibr_launch_count.restype = ctypes.c_longlong
     lib.dibr_launch_count.argtypes = [ctypes.c_int]
+    lib.dibr_launch_count_add.restype = None
+    lib.dibr_launch_count_add.argtypes = [ctypes.c_longlong]
     lib.dibr_workspace_bytes.argtypes = [ctypes.POINTER(DibrPass), ctypes.POINTER(ctypes.c_size_t)]
     for name in ("dibr_setup_faces", "dibr_setup_meshes", "dibr_forward", "dibr_backward_faces", "dibr_backward_meshes"):
         fn = getattr(lib, name)

@@ -265,6 +265,8 @@ int dibr_roi_pool_backward(const DibrRoiPool* p, void* stream) {
     return cuda_fail("dibr_roi_pool_backward", dibr::launch_roi_pool_backward(q, (cudaStream_t)stream));
 }
 
+void dibr_launch_count_add(long long n) { g_launches += n; }
+
 long long dibr_launch_count(int reset) {
     const long long v = g_launches;
     if (reset) g_launches = 0;

@@ -206,11 +206,18 @@ __device__ void plan_epilogue(const SetupParams& P, int g, int b, bool active)
     }
 }
 
+// faces in use: with face_offsets the count lives on the device (P.total_faces is then the CAPACITY of the face arrays, which
+// keeps the workspace layout and the grid the same from step to step -- a captured CUDA graph stays valid when the batch
+// composition changes)
+__device__ __forceinline__ int faces_in_use(const SetupParams& P) {
+    return P.face_offsets ? min(__ldg(P.face_offsets + P.batch), P.total_faces) : P.total_faces;
+}
+
 __global__ void __launch_bounds__(SETUP_T) setup_faces_kernel(SetupParams P)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     write_tables(P, g);
-    const bool active = g < P.total_faces;
+    const bool active = g < faces_in_use(P);
     float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0, az = 0, bz = 0, cz = 0, nz = 0;
     int b = -1;
     if (active) {
@@ -235,7 +242,8 @@ __global__ void __launch_bounds__(SETUP_T) setup_meshes_kernel(SetupParams P)
     __shared__ StageSmem st;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     write_tables(P, g);
-    const bool active = g < P.total_faces;
+    const int nfaces = faces_in_use(P);
+    const bool active = g < nfaces;
     float x2[3] = {0, 0, 0}, y2[3] = {0, 0, 0}, zc[3] = {0, 0, 0};
     float nz = 0.f;
     int b = -1;
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(SETUP_T) setup_meshes_kernel(SetupParams P)
     // contiguous, so lanes then only ever step forward a little)
     int inst0 = 0;
     {
-        const int gw = min(blockIdx.x * blockDim.x + (threadIdx.x & ~31), max(P.total_faces - 1, 0));
+        const int gw = min(blockIdx.x * blockDim.x + (threadIdx.x & ~31), max(nfaces - 1, 0));
         int below = 0;
         for (int i0 = 0; i0 < P.num_instances; i0 += 32) {
             const int i = i0 + (threadIdx.x & 31);

@@ -81,7 +81,8 @@ class _PassBuffers(object):
 
 class RenderSession(object):
     def __init__(self, models, batch, height, width, student_mode=("color", "depth", "mask", "norm", "prob"),
-                 teacher_mode=("norm",), device="cuda:0", znear=0.01, zfar=100.0, teacher_soft_mask=True, raw_normals=False):
+                 teacher_mode=("norm",), device="cuda:0", znear=0.01, zfar=100.0, teacher_soft_mask=True, raw_normals=False,
+                 cuda_graphs=True):
         """``teacher_soft_mask=False`` skips the soft-silhouette phase of the teacher rasterisation (K = 0).  The reference
         always computes it (kaolin's forward does) and then drops it when ``mode`` has no "color"
         (renderer_dibr.py:273-286), so nothing a caller can observe changes; the default keeps the reference's work."""
@@ -156,6 +157,11 @@ class RenderSession(object):
         self.st = st
         self._ar = np.arange(B)
         self._keep = None
+        # The launches of a forward / backward call (2 + 1 memsets, kernels, copies on two streams) are captured into a CUDA
+        # graph the second time the call is made with the same arguments and replayed from then on: every pointer in them
+        # is owned by the session (or, for the backward, is the caller's gradient tensor: another tensor -> another graph).
+        self.cuda_graphs = bool(cuda_graphs)
+        self._graphs = {}          # key -> [calls seen, CUDAGraph or None, kernels launched per replay]
         self._last_slots, self._last_total = None, 0
 
     # ------------------------------------------------------------------------------------------
@@ -204,31 +210,40 @@ class RenderSession(object):
             self._last_total = int(cf[-1])
             self._last_slots = slots
             upload = True                 # a new instance table must reach the device even if the caller says the inputs are resident
-        total = self._last_total
-        st = self.st
-        st.student.total_faces = total
-        st.teacher.total_faces = total
+        # (total_faces of both passes stays at the session's capacity: the kernels read the faces in use from
+        # face_offsets[B] on the device, so the workspace layout, the grids -- and a captured graph -- survive a new composition)
         return upload
 
     def _set_grads(self, grad_color, grad_prob, grad_depth):
+        """point the student pass at the caller's gradient tensors; returns their addresses (the identity of a captured graph)"""
         sp = self.st.student
-        keep = []
+        keep, key = [], []
         grads = {"color": grad_color, "depth": grad_depth}
-        for g, key in enumerate(self.student.keys):
-            t = grads.get(key)
+        npix = self.B * self.H * self.W
+        for g, key_name in enumerate(self.student.keys):
+            t = grads.get(key_name)
             if t is not None:
+                if not t.is_cuda or t.dtype != torch.float32 or t.numel() != npix * self.student.split[g]:
+                    raise RuntimeError("RenderSession.backward: grad_%s must be a float32 CUDA tensor with %d elements" % (key_name, npix * self.student.split[g]))
                 t = t.contiguous()
                 keep.append(t)
                 sp.grad_out[g] = t.data_ptr()
+                key.append(t.data_ptr())
             else:
                 sp.grad_out[g] = None
+                key.append(0)
         if grad_prob is not None:
+            if not grad_prob.is_cuda or grad_prob.dtype != torch.float32 or grad_prob.numel() != npix:
+                raise RuntimeError("RenderSession.backward: grad_prob must be a float32 CUDA tensor with %d elements" % npix)
             gp = grad_prob.contiguous()
             keep.append(gp)
             sp.grad_improb = gp.data_ptr()
+            key.append(gp.data_ptr())
         else:
             sp.grad_improb = None
+            key.append(0)
         self._keep = keep
+        return tuple(key)
 
     def forward(self, Rs, ts, Ks, models, teacher_Rs=None, teacher_ts=None, upload=True):
         """Rs [B,3,3], ts [B,3], Ks [B,3,3] (+ teacher pose): HOST arrays.  Renders the student and the teacher pass and
@@ -236,19 +251,54 @@ class RenderSession(object):
         st = self.st
         upload = self._stage_inputs(Rs, ts, Ks, models, teacher_Rs, teacher_ts, upload)
         st.staging_bytes = 4 * self.stage_words if upload else 0       # upload=False: inputs already resident
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.dibr_render_forward(ctypes.byref(st), _stream(self.device)), "dibr_render_forward")
+        self._run(("forward", bool(upload)), self.lib.dibr_render_forward, "dibr_render_forward")
         return self.outputs()
+
+    def _run(self, key, fn, what):
+        """call ``fn(step, stream)`` eagerly the first time ``key`` is seen, capture it into a CUDA graph the second time,
+        replay the graph afterwards"""
+        st = self.st
+        with torch.cuda.device(self.device):
+            if torch.cuda.is_current_stream_capturing():                # the caller is capturing a graph of its own: plain launches
+                _lib.check(fn(ctypes.byref(st), _stream(self.device)), what)
+                return
+            ent = self._graphs.get(key) if self.cuda_graphs else None
+            if ent is not None and ent[1] is not None:
+                ent[1].replay()
+                self.lib.dibr_launch_count_add(ent[2])
+                return
+            if self.cuda_graphs:
+                if ent is None:
+                    if len(self._graphs) > 8:                           # callers that hand over fresh gradient tensors every step
+                        self._graphs = {k: v for k, v in self._graphs.items() if v[1] is not None and k[0] == "forward"}
+                    ent = self._graphs[key] = [0, None, 0]
+                ent[0] += 1
+                if ent[0] == 2:
+                    try:
+                        torch.cuda.current_stream(self.device).synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        before = self.lib.dibr_launch_count(0)
+                        with torch.cuda.graph(g):
+                            _lib.check(fn(ctypes.byref(st), _stream(self.device)), what)
+                        ent[1], ent[2] = g, int(self.lib.dibr_launch_count(0) - before)
+                        self.lib.dibr_launch_count_add(-ent[2])         # the capture launched nothing
+                        g.replay()
+                        self.lib.dibr_launch_count_add(ent[2])
+                        return
+                    except Exception:
+                        ent[1] = None
+                        ent[0] = 3                                      # never try again for this key
+                        torch.cuda.synchronize(self.device)
+            _lib.check(fn(ctypes.byref(st), _stream(self.device)), what)
 
     def backward(self, grad_color=None, grad_prob=None, grad_depth=None, download=True):
         """grad_*: DEVICE tensors (dL/dcolor [B,H,W,3], dL/dprob [B,H,W], dL/ddepth [B,H,W]) or None, usually computed from
         ``forward``'s images.  Runs the backward of the student pass; ``grad_pose`` (pinned [B,12]: dL/dR then dL/dt) is
         valid after ``synchronize()``, ``g_pose_dev`` holds the same on the device.  May be called again with other gradients."""
         st = self.st
-        self._set_grads(grad_color, grad_prob, grad_depth)
+        ptrs = self._set_grads(grad_color, grad_prob, grad_depth)
         st.host_grad_pose = self.g_pose_host.data_ptr() if download else None
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.dibr_render_backward(ctypes.byref(st), _stream(self.device)), "dibr_render_backward")
+        self._run(("backward", bool(download)) + ptrs, self.lib.dibr_render_backward, "dibr_render_backward")
         return self.g_pose_dev
 
     def step(self, Rs, ts, Ks, models, teacher_Rs=None, teacher_ts=None, grad_color=None, grad_prob=None,
