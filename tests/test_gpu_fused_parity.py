@@ -354,3 +354,40 @@ def test_render_session_composition_change_and_lean_teacher():
     for k in ref_out:
         assert torch.equal(out_l[k], ref_out[k]), k
     assert torch.equal(grad_l, ref_grad)
+
+
+def test_render_session_graph_replay_equals_plain_launches():
+    """RenderSession captures each forward / backward call into a CUDA graph the second time it is made and replays it from
+    then on.  Over five steps with changing batch compositions and poses (the graph was captured on ANOTHER composition:
+    the face arrays stay at capacity and the kernels read the faces in use from the device) every output and the pose
+    gradients must equal a session that launches plainly, bit for bit; fresh gradient tensors fall back to plain launches."""
+    from self6dpp_b200 import synth
+    from self6dpp_b200.session import RenderSession
+    from tests.golden.make_golden import small_meshes
+    meshes = small_meshes()
+    H = W = 64
+    B = 4
+    models = to_dev_models(meshes)
+    for m in models:
+        m["faces"] = m["faces"].to(torch.int32)
+    g = torch.Generator().manual_seed(15)
+    gc, gp, gd = torch.randn(B, H, W, 3, generator=g).to(DEV), torch.randn(B, H, W, generator=g).to(DEV), torch.randn(B, H, W, generator=g).to(DEV)
+    graph, plain = RenderSession(models, B, H, W), RenderSession(models, B, H, W, cuda_graphs=False)
+    comps = [[2, 0, 1, 1], [0, 0, 2, 1], [1, 2, 2, 0], [2, 0, 1, 1], [0, 1, 0, 1]]
+    for step, ids in enumerate(comps):
+        batch = synth.roi_batch([meshes[i] for i in ids], B, res=W, seed=60 + step, fill=(0.45, 0.7))
+        tea = synth.roi_batch([meshes[i] for i in ids], B, res=W, seed=80 + step, fill=(0.45, 0.7))
+        res = []
+        for sess in (graph, plain):
+            out = sess.forward(batch["Rs"], batch["ts"], batch["Ks"], [models[i] for i in ids], tea["Rs"], tea["ts"])
+            out = {k: v.clone() for k, v in out.items()}
+            grads = (gc, gp, gd) if step != 3 else (gc.clone(), gp.clone(), gd.clone())      # step 3: other tensors, no graph for them
+            sess.backward(*grads)
+            sess.synchronize()
+            res.append((out, sess.grad_pose.clone()))
+        for k in res[0][0]:
+            assert torch.equal(res[0][0][k], res[1][0][k]), (step, k)
+        assert torch.equal(res[0][1], res[1][1]), step
+    assert any(e[1] is not None for k, e in graph._graphs.items() if k[0] == "forward")
+    assert any(e[1] is not None for k, e in graph._graphs.items() if k[0] == "backward")
+    assert not plain._graphs
