@@ -211,7 +211,7 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid)
         soft_prob(h.d2 * zscale, p, om);
         // d improb / d p_k = prod_{j != k}(1 - p_j) = comp / (1 - p_k);  dp/dz = -p;  z = zscale * d2;
         // the gradient w.r.t. UN-multiplied coordinates carries one more 'mult'
-        const float coef = -__ldg(gpr + pix) * __ldg(comp + pix) / (om + 1e-15f) * p * zscale * mult;
+        const float coef = __fdividef(-__ldg(gpr + pix) * __ldg(comp + pix), om + 1e-15f) * p * zscale * mult;     // 2 ulp division: gradients are gated at 1e-5
         if (h.kase >= 3) {
             const int k = h.kase - 3;
             const float vx = (k == 0) ? px[0] : ((k == 1) ? px[1] : px[2]);
@@ -227,7 +227,7 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid)
             const float x2 = (k2 == 0) ? px[0] : ((k2 == 1) ? px[1] : px[2]);
             const float y2 = (k2 == 0) ? py[0] : ((k2 == 1) ? py[1] : py[2]);
             const float exx = x2 - x1, eyy = y2 - y1;
-            const float s2 = 2.0f * coef / h.len2;
+            const float s2 = __fdividef(2.0f * coef, h.len2);
             const float gx1 = s2 * ((y0 - y2) * h.cr + h.d2 * exx);
             const float gy1 = s2 * (-(x0 - x2) * h.cr + h.d2 * eyy);
             const float gx2 = s2 * (-(y0 - y1) * h.cr - h.d2 * exx);
@@ -313,6 +313,27 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid)
 template <int DMAX>
 __global__ void __launch_bounds__(256, (DMAX <= 8) ? DIBR_BWD_MIN_CTAS : 2) backward_faces_kernel(const __grid_constant__ BwdParams P, int do_color, int do_soft)
 {
+    // dL/dattr of the faces that won no pixel is zero.  The colour body writes the whole row of every face on its list, so
+    // only the OTHER rows are cleared here (about half of them, inside this launch) instead of a memset of the whole array.
+    {
+        const unsigned int* __restrict__ flags = reinterpret_cast<const unsigned int*>(P.face_flags);
+        const int row = 3 * P.num_attr;                                     // floats per face
+        const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+        if ((row & 3) == 0 && (reinterpret_cast<uintptr_t>(P.grad_face_attr) & 15) == 0) {
+            const int r4 = row >> 2;
+            const long long n4 = (long long)P.total_faces * r4;
+            for (long long i = t0; i < n4; i += stride) {
+                const int g = (int)(i / r4);
+                if (!do_color || !(__ldg(flags + g) & 1u)) reinterpret_cast<float4*>(P.grad_face_attr)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            const long long n = (long long)P.total_faces * row;
+            for (long long i = t0; i < n; i += stride) {
+                const int g = (int)(i / row);
+                if (!do_color || !(__ldg(flags + g) & 1u)) P.grad_face_attr[i] = 0.f;
+            }
+        }
+    }
     const int cbn = do_color ? (P.list_counts[0] + (256 / GRP) - 1) / (256 / GRP) : 0;
     const int sbn = do_soft ? (P.list_counts[1] + SOFT_GROUPS - 1) / SOFT_GROUPS : 0;
     for (int it = blockIdx.x; it < cbn + sbn; it += gridDim.x) {
@@ -328,10 +349,11 @@ int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
     // faces on neither work list keep a zero gradient
     cudaError_t e = cudaMemsetAsync(P.grad_points2d, 0, sizeof(float) * 6 * (size_t)P.total_faces, stream);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(P.grad_face_attr, 0, sizeof(float) * 3 * (size_t)P.num_attr * (size_t)P.total_faces, stream);
-    if (e != cudaSuccess) return (int)e;
     const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
-    if (!do_color && !do_soft) return 0;
+    if (!do_color && !do_soft) {                     // no upstream gradient at all: everything is zero
+        e = cudaMemsetAsync(P.grad_face_attr, 0, sizeof(float) * 3 * (size_t)P.num_attr * (size_t)P.total_faces, stream);
+        return (int)e;
+    }
     const int worst = (do_color ? (P.total_faces + (256 / GRP) - 1) / (256 / GRP) : 0) + (do_soft ? (P.total_faces + SOFT_GROUPS - 1) / SOFT_GROUPS : 0);
     const int grid = min(worst, DIBR_BWD_GRID);
     if (P.num_attr <= 4) backward_faces_kernel<4><<<grid, 256, 0, stream>>>(P, do_color, do_soft);
