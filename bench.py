@@ -517,11 +517,31 @@ def main_b200(args):
             if fresh:                                        # a capture of other kernel sources says nothing about this build
                 traffic = cap.get("dibr_forward_kernel_bytes_per_launch")
                 ncu.update({k: v for k, v in cap.items() if k not in ("dibr_forward_kernel_bytes_per_launch", "csrc_hash")})
-        roof = {"bound": "hbm", "kernel": "dibr_forward_v2_kernel (student pass, D=8; with the list-reset memset of dibr_forward)",
+        # pure-write bandwidth of this GPU (a device fill): 109 of the kernel's 134 MB are writes, and a write stream tops out
+        # well below the copy figure (read + write bytes) of MEASURED_PEAKS.json
+        wbuf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            wbuf.zero_()
+        torch.cuda.synchronize()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(5):
+            wbuf.zero_()
+        w1.record()
+        torch.cuda.synchronize()
+        write_peak = 5 * wbuf.numel() / (w0.elapsed_time(w1) * 1e-3) / 1e9
+        del wbuf
+        bytes_written = 4.0 * (D + 5) * RES * RES * BATCH
+        roof = {"bound": "hbm", "kernel": "dibr_forward_kernel<FUSED> (student pass, D=8; with the list-reset memset of dibr_forward)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "kernel_ms": k_ms,
                 "algorithmic_bytes": alg, "peak_source": peak_src,
-                "limiter": "instruction issue and barrier latency, not HBM (DESIGN.md 6): the HBM roofline is the binding one only "
-                           "because the FP32 work is tiny -- see fp32",
+                "limiter": "latency of short dependent phases between CTA barriers at half occupancy, not HBM (DESIGN.md 6): the HBM "
+                           "roofline is the binding one only because the FP32 work is tiny -- see fp32",
+                "write_floor": {"bytes_written": bytes_written, "fill_peak_gbs_measured": write_peak,
+                                "floor_ms": bytes_written / (write_peak * 1e9) * 1e3,
+                                "frac_of_floor": bytes_written / (write_peak * 1e9) * 1e3 / k_ms,
+                                "note": "81 % of the algorithmic bytes are stores; a store-only stream (torch fill, 512 MiB x 5) reaches "
+                                        "this rate on the same GPU, so the kernel cannot be faster than floor_ms whatever it computes"},
                 "ncu": ncu}
         try:
             from oracle import kaolin_structure as KS

@@ -55,7 +55,10 @@ if os.path.exists(rep):
             t = mb(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + mb(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
             def num(m):
                 return float(r[idx[m]].replace(",", "")) if m in idx and r[idx[m]] not in ("", "n/a") else None
-            json.dump({"dibr_forward_kernel_bytes_per_launch": t,
+            sys.path.insert(0, ROOT)
+            import bench
+            json.dump({"csrc_hash": bench.csrc_hash(),        # of the tree the capture was made on (run this right after the capture)
+                       "dibr_forward_kernel_bytes_per_launch": t,
                        "warp_instructions_per_launch": num("smsp__inst_executed.sum"),
                        "issue_slots_busy_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                        "warp_slots_occupied_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active"),
