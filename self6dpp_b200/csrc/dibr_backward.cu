@@ -482,9 +482,11 @@ __global__ void __launch_bounds__(MV_T) mesh_vertex_grad_kernel(MeshBwdParams P)
     //      cam_view_pos = -(R^T t) down to R and t:
     //        dL/dR[j][k] = F_jj dL/dcamR[j][k] - t[j] dL/dpos[k],   dL/dt[j] = -sum_k R[j][k] dL/dpos[k]
     __shared__ unsigned int ticket;
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) ticket = atomicAdd(&P.pose_done[inst], 1u);
+    if (threadIdx.x == 0) {
+        __threadfence();            // one fence for the block (cumulative over the barrier): the partial sums before the ticket
+        ticket = atomicAdd(&P.pose_done[inst], 1u);
+    }
     __syncthreads();
     if (ticket != gridDim.x - 1) return;
     if (threadIdx.x == 0) P.pose_done[inst] = 0u;          // ready for another backward over the same forward

@@ -38,7 +38,10 @@ struct Workspace {
     size_t bytes;
 };
 
-constexpr int POSE_BLOCKS = 16;   // vertex blocks per instance in the pose-gradient reduction
+#ifndef DIBR_POSE_BLOCKS
+#define DIBR_POSE_BLOCKS 12
+#endif
+constexpr int POSE_BLOCKS = DIBR_POSE_BLOCKS;   // vertex blocks per instance in the pose-gradient reduction (12 x 32 instances of 256 threads x 80 registers = one wave)
 
 struct SetupParams {
     int batch, height, width, multiplier;
