@@ -119,7 +119,9 @@ typedef struct DibrPass {
                                                  (the K-th accepted face: first-K-in-index-order rule) */
     float *imcomp;           /* [batch, H, W]    prod_k (1 - p_k) over the accepted faces of an uncovered pixel
                                                  (= 1 - improb, kept separately at full relative precision;
-                                                 saved for the backward, 0 where covered) */
+                                                 saved for the backward, 0 where covered).  Written on the 16x16 tiles
+                                                 some face's expanded bbox reaches -- the only pixels the backward reads;
+                                                 NOT written elsewhere (where the empty product would be 1) */
 
     /* ---- backward inputs / outputs --------------------------------------------------------- */
     const float *grad_im;     /* [batch, H, W, D] or NULL */

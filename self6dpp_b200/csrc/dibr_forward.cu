@@ -407,7 +407,7 @@ __device__ __forceinline__ void unpack_tile(int packed, int& b, int& ty, int& tx
     b = (int)((unsigned)packed >> 20); ty = (packed >> 10) & 1023; tx = packed & 1023;
 }
 
-// nothing near this tile: zeros everywhere (imcomp = 1: empty product).  One warp per tile.
+// nothing near this tile: zeros everywhere.  One warp per tile.
 __device__ __noinline__ void fill_untouched_warp(const FwdParams& P, int packed_tile)
 {
     int b, ty, tx;
@@ -419,7 +419,7 @@ __device__ __noinline__ void fill_untouched_warp(const FwdParams& P, int packed_
     for (int g = 0; g < P.n_out; g++) fill_tile_warp(P.out[g] + img_pix * P.out_ch[g], P.width, P.out_ch[g], tx0, ty0, tw, th, 0.0f);
     fill_tile_warp(P.improb + img_pix, P.width, 1, tx0, ty0, tw, th, 0.0f);
     fill_tile_warp(reinterpret_cast<float*>(P.imidx + img_pix), P.width, 1, tx0, ty0, tw, th, 0.0f);
-    fill_tile_warp(P.imcomp + img_pix, P.width, 1, tx0, ty0, tw, th, 1.0f);
+    // imcomp is NOT written here: the backward reads it only at uncovered pixels inside some face's expanded range, i.e. on touched tiles
 }
 
 #ifndef DIBR_FWD_MIN_CTAS
