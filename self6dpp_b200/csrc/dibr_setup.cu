@@ -134,13 +134,28 @@ __device__ void plan_image(const SetupParams& P, PlanSmem& s, int b)
     const int w0 = f_lo >> 5, nw = ((f_hi - 1) >> 5) - w0 + 1;          // bitmap words per tile (bin_face)
     if (tid < ORDER_BUCKETS) { s.hist[tid] = 0; s.fill[tid] = 0; }
     __syncthreads();
-    for (int t = tid; t < tiles; t += nthr) atomicAdd(&s.hist[min((__ldcg(cnt + t) + 31) >> 5, ORDER_BUCKETS - 1)], 1);
+    // most tiles of an image share a bucket (the empty one): the lanes of a warp that agree on the bucket send ONE shared-memory
+    // atomic between them (1,200 tiles of a 480x640 image on one counter cost 18 us otherwise)
+    const int lane = tid & 31;
+    for (int t0 = 0; t0 < tiles; t0 += nthr) {
+        const int t = t0 + tid;
+        const int kb = t < tiles ? min((__ldcg(cnt + t) + 31) >> 5, ORDER_BUCKETS - 1) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, kb);
+        if (kb >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s.hist[kb], __popc(peers));
+    }
     __syncthreads();
     if (tid < ORDER_BUCKETS) s.base[tid] = s.hist[tid] > 0 ? atomicAdd(&P.ws.order_cnt[tid], s.hist[tid]) : 0;
     __syncthreads();
-    for (int t = tid; t < tiles; t += nthr) {
-        const int kb = min((__ldcg(cnt + t) + 31) >> 5, ORDER_BUCKETS - 1);
-        const int pos = s.base[kb] + atomicAdd(&s.fill[kb], 1);
+    for (int t0 = 0; t0 < tiles; t0 += nthr) {
+        const int t = t0 + tid;
+        const int kb = t < tiles ? min((__ldcg(cnt + t) + 31) >> 5, ORDER_BUCKETS - 1) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, kb);
+        const int leader = __ffs(peers) - 1;
+        int pos = 0;
+        if (kb >= 0 && lane == leader) pos = atomicAdd(&s.fill[kb], __popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+        if (kb < 0) continue;
+        pos += s.base[kb];
         const int ty = t / tiles_x;
         const int id = pack_tile(b, ty, t - ty * tiles_x);
         P.ws.order_seg[(size_t)kb * ntiles + pos] = id;
