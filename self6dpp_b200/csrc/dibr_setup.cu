@@ -40,28 +40,46 @@ __device__ __forceinline__ void write_tables(const SetupParams& P, int gtid) {
 // instead of lists: OR is order independent, so the forward kernel reads the faces of a tile in ascending order without
 // any sort, and the result is the same run to run.
 //
-// (A warp-level vote that merges the atomics of faces in the same tile was measured 3x slower: the faces of a warp
-// are consecutive in the mesh, not on the screen, and land in ~80 different tiles.)
-__device__ __forceinline__ void bin_face(const SetupParams& P, int g, int b, int e0, int e1, int q0, int q1) {
-    if (e1 <= e0 || q1 <= q0) return;
-    const int tiles_x = (P.width + TILE - 1) / TILE, tiles_y = (P.height + TILE - 1) / TILE;
-    const int tx0 = e0 / TILE, tx1 = (e1 - 1) / TILE;
-    const int ty0 = q0 / TILE, ty1 = (q1 - 1) / TILE;
-    const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
-    const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
-    const int w0 = f_lo >> 5, nw = ((f_hi - 1) >> 5) - w0 + 1;
-    uint32_t* img = P.ws.bins + (size_t)tiles_x * tiles_y * ((size_t)w0 + b) + ((g >> 5) - w0);
-    int* cnt = P.ws.tile_count + (size_t)b * tiles_x * tiles_y;
-    const uint32_t bit = 1u << (g & 31);
-    for (int ty = ty0; ty <= ty1; ty++)
-        for (int tx = tx0; tx <= tx1; tx++) {
-            atomicOr(img + (size_t)(ty * tiles_x + tx) * nw, bit);
-            atomicAdd(cnt + ty * tiles_x + tx, 1);
+// The 32 faces of a warp are consecutive, so they share ONE bitmap word per tile; where the mesh has locality (neighbouring
+// faces land in the same tile) they would send 32 atomics to the same address, which the L2 serialises (a 100k-face mesh:
+// set-up 519 us).  So the warp walks its faces' tile rectangles slot by slot (slot j = the j-th tile of every lane's
+// rectangle, at most 4 slots), `__match_any_sync` groups the lanes whose slot is the same tile, and one lane per group sends
+// a single atomicOr (the group's bits) and a single atomicAdd (its size).  Without locality every lane is its own group
+// and the cost is that of the per-face atomics.  (A loop over the DISTINCT tiles of the warp instead of over slots was
+// measured 3x slower on meshes without locality: ~80 distinct tiles per warp.)  Every lane of the warp must call.
+__device__ __forceinline__ void bin_face_warp(const SetupParams& P, int g, int b, bool ok, int e0, int e1, int q0, int q1) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    ok = ok && e1 > e0 && q1 > q0;
+    const int tiles_x = (P.width + TILE - 1) / TILE, tiles = tiles_x * ((P.height + TILE - 1) / TILE);
+    int tx0 = 0, ty0 = 0, ntx = 0, n = 0, w0 = 0, nw = 1;
+    if (ok) {
+        tx0 = e0 / TILE; ty0 = q0 / TILE;
+        ntx = (e1 - 1) / TILE - tx0 + 1;
+        n = ntx * ((q1 - 1) / TILE - ty0 + 1);
+        const int f_lo = P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image;
+        const int f_hi = P.face_offsets ? P.face_offsets[b + 1] : f_lo + P.faces_per_image;
+        w0 = f_lo >> 5; nw = ((f_hi - 1) >> 5) - w0 + 1;
+    }
+    const int nmax = __reduce_max_sync(full, n);
+    for (int j = 0; j < min(nmax, 4); j++) {
+        int t = -1;                                              // tile of this lane's slot j, unique over the batch with b
+        if (j < n) { const int ry = j / ntx; t = (ty0 + ry) * tiles_x + tx0 + (j - ry * ntx); }
+        const int key = t < 0 ? -1 : b * tiles + t;
+        const unsigned peers = __match_any_sync(full, key);
+        if (t >= 0 && lane == __ffs(peers) - 1) {                // bit = lane = g & 31: the CTA starts on a multiple of 32
+            atomicOr(P.ws.bins + (size_t)tiles * ((size_t)w0 + b) + (size_t)t * nw + ((g >> 5) - w0), peers);
+            atomicAdd(P.ws.tile_count + (size_t)b * tiles + t, __popc(peers));
         }
+    }
+    // faces that reach more than four tiles are rare: the rest of their rectangle on their own
+    for (int j = 4; j < n; j++) {
+        const int ry = j / ntx, t = (ty0 + ry) * tiles_x + tx0 + (j - ry * ntx);
+        atomicOr(P.ws.bins + (size_t)tiles * ((size_t)w0 + b) + (size_t)t * nw + ((g >> 5) - w0), 1u << (g & 31));
+        atomicAdd(P.ws.tile_count + (size_t)b * tiles + t, 1);
+    }
 }
 
-// The CTA's records are staged in shared memory and written out as whole 512 B rows per warp instruction (a thread's
-// own 64 B at a stride touches 16 lines per store instruction instead of 4).
 // Threads per set-up CTA.  157 k faces are ONE wave of work: with 128 threads (56 registers, 10 KB of shared memory) nine CTAs
 // fit an SM and the whole grid is resident at once; 256-thread CTAs left 21 of 613 CTAs for a second wave that doubled the
 // kernel's time.
@@ -96,7 +114,7 @@ __device__ __forceinline__ void store_face(const SetupParams& P, StageSmem& st, 
     st.rec[rec_slot(t, 2)] = make_float4(cz, nz, __int_as_float(b), 0.f);
     st.rec[rec_slot(t, 3)] = make_float4(__uint_as_float((unsigned)c0 | ((unsigned)c1 << 16)), __uint_as_float((unsigned)r0 | ((unsigned)r1 << 16)),
                                          __uint_as_float((unsigned)e0 | ((unsigned)e1 << 16)), __uint_as_float((unsigned)q0 | ((unsigned)q1 << 16)));
-    if (ok) bin_face(P, g, b, e0, e1, q0, q1);
+    bin_face_warp(P, g, b, ok, e0, e1, q0, q1);
     __syncthreads();
     // the CTA's records are contiguous in global memory: 16 B chunks, four per thread, fully coalesced
     const int g0 = blockIdx.x * blockDim.x;
