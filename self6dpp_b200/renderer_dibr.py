@@ -76,6 +76,10 @@ class _ModelRegistry(object):
         """slot per sample, or None when a model cannot be cached (requires grad)."""
         out = np.empty(len(models), dtype=np.int64)
         dirty = False
+        if len(self.models) > 128 and any(id(m) not in self.index for m in models):
+            # callers that build fresh model dicts every call would grow the registry (and every rebuild) without bound:
+            # start over with the models of this call
+            self.index, self.models, self.sigs = {}, [], []
         for i, m in enumerate(models):
             slot = self.index.get(id(m))
             if slot is None:
@@ -112,8 +116,14 @@ class _ModelRegistry(object):
         self.generation += 1
 
     def attr_matrix(self, names):
+        """[sum verts, 3 * len(names)] (rows padded to 16 B) of every resident model, or None when an attribute requires grad.
+        The cached copy is tied to the identity AND version of every source tensor: an attribute modified in place, replaced
+        or switched to requires_grad is picked up on the next call."""
         key = tuple(names)
+        sig = tuple((m[n].data_ptr(), m[n]._version, m[n].requires_grad) for m in self.models for n in names)
         hit = self.attrs.get(key)
+        if hit is not None and hit[1] != sig:
+            hit = None
         if hit is None:
             if any(m[n].requires_grad for m in self.models for n in names):
                 return None
@@ -123,8 +133,9 @@ class _ModelRegistry(object):
             pad = (-hit.shape[1]) % 4                                  # rows padded to a multiple of 16 B, same reason
             if pad:
                 hit = torch.cat((hit, hit.new_zeros(hit.shape[0], pad)), dim=1).contiguous()
+            hit = (hit, sig)
             self.attrs[key] = hit
-        return hit
+        return hit[0]
 
 
 class Renderer_dibr(object):

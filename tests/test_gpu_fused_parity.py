@@ -391,3 +391,27 @@ def test_render_session_graph_replay_equals_plain_launches():
     assert any(e[1] is not None for k, e in graph._graphs.items() if k[0] == "forward")
     assert any(e[1] is not None for k, e in graph._graphs.items() if k[0] == "backward")
     assert not plain._graphs
+
+
+def test_renderer_picks_up_modified_attributes_and_bounds_its_registry():
+    """ the cached per-vertex attribute matrix follows the source tensors: colours modified in place or replaced
+    show up in the next render; a caller that builds fresh model dicts every call does not grow the registry without bound."""
+    from self6dpp_b200 import Renderer_dibr, synth
+    from tests.golden.make_golden import small_meshes
+    meshes = small_meshes()
+    H = W = 48
+    models = to_dev_models(meshes)
+    batch = synth.roi_batch([meshes[0]], 1, res=W, seed=3, fill=(0.5, 0.7))
+    ren = Renderer_dibr(H, W, "VertexColorBatch")
+    args = dict(Ks=torch.tensor(batch["Ks"], device=DEV), width=W, height=H, mode=["color", "mask"])
+    Rs, ts = torch.tensor(batch["Rs"], device=DEV), torch.tensor(batch["ts"], device=DEV)
+    a = ren.render_batch(Rs, ts, [models[0]], **args)["color"].clone()
+    models[0]["colors"].mul_(0.5)                                  # in place: same storage, new version
+    b = ren.render_batch(Rs, ts, [models[0]], **args)["color"].clone()
+    assert torch.allclose(b, 0.5 * a, atol=1e-6) and float(a.abs().max()) > 0
+    models[0]["colors"] = torch.zeros_like(models[0]["colors"])    # replaced
+    c = ren.render_batch(Rs, ts, [models[0]], **args)["color"]
+    assert float(c.abs().max()) == 0
+    for _ in range(140):                                           # fresh dicts (same tensors) every call
+        ren.render_batch(Rs, ts, [dict(models[1])], Ks=torch.tensor(batch["Ks"], device=DEV), width=W, height=H, mode=["mask"])
+    assert len(ren._registry.models) <= 130
