@@ -204,7 +204,9 @@ typedef struct DibrStep {
     const float *student_normal_in, *student_mask_in; float *student_normal_out;
     const float *teacher_normal_in, *teacher_mask_in; float *teacher_normal_out;
     int32_t run_backward;
-    int32_t reserved;
+    int32_t grad_pose_sum;         /* != 0: device_grad_pose has num_instances + 1 rows and the last one receives the column sums
+                                      of the others (added in instance order by the backward itself): the 12-float vector a
+                                      data-parallel step all-reduces over NCCL, ready without another launch */
     float *host_grad_pose;         /* pinned [num_instances, 12]: 9 of dL/dR then 3 of dL/dt per instance, or NULL */
     float *device_grad_pose;       /* [num_instances, 12] packed dL/dR | dL/dt on the device (always written when non-NULL);
                                       the D2H copy reads from it */

@@ -53,7 +53,7 @@ class DibrStep(ctypes.Structure):
         ("staging_host", ctypes.c_void_p), ("staging_device", ctypes.c_void_p), ("staging_bytes", ctypes.c_size_t),
         ("student_normal_in", _c_f32p), ("student_mask_in", _c_f32p), ("student_normal_out", _c_f32p),
         ("teacher_normal_in", _c_f32p), ("teacher_mask_in", _c_f32p), ("teacher_normal_out", _c_f32p),
-        ("run_backward", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("run_backward", ctypes.c_int32), ("grad_pose_sum", ctypes.c_int32),
         ("host_grad_pose", _c_f32p), ("device_grad_pose", _c_f32p),
         ("overlap", ctypes.c_void_p),
     ]

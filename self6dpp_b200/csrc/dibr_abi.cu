@@ -53,7 +53,7 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     w.cam_pos = (float*)take(sizeof(float) * 3 * ni);
     w.cam_proj = (float*)take(sizeof(float) * 16 * (size_t)(p->num_K > 0 ? p->num_K : 0));
     w.list_counts = (int*)take(sizeof(int) * 64);
-    w.pose_done = (unsigned int*)take(sizeof(unsigned int) * ni);          // between the counters and the flags: same memset
+    w.pose_done = (unsigned int*)take(sizeof(unsigned int) * (ni + 1));          // between the counters and the flags: same memset
     w.face_flags = (unsigned int*)take(sizeof(unsigned int) * (size_t)p->total_faces);   // directly after list_counts: one memset
     w.color_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
     w.soft_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
@@ -396,7 +396,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream));
 }
 
-static int backward_meshes_impl(const DibrPass* p, void* stream, float* packed) {
+static int backward_meshes_impl(const DibrPass* p, void* stream, float* packed, int pose_sum = 0) {
     if (int e = check_common(p, true)) return e;
     if (p->num_instances <= 0 || !p->inst_desc || !p->verts) return fail("backward_meshes: instances and verts required");
     if (!p->pose_R && (!p->cam_rot || !p->cam_pos || !p->cam_proj)) return fail("backward_meshes: cameras required");
@@ -417,6 +417,7 @@ static int backward_meshes_impl(const DibrPass* p, void* stream, float* packed) 
     m.grad_verts = p->grad_verts; m.grad_vert_attr = p->grad_vert_attr;
     m.grad_cam_rot = p->grad_cam_rot; m.grad_cam_pos = p->grad_cam_pos; m.pose_part = w.pose_part; m.pose_done = w.pose_done;
     m.grad_pose_packed = p->pose_R ? packed : nullptr;
+    m.pose_sum = pose_sum;
     g_launches += 1;
     return cuda_fail("dibr_backward_meshes", dibr::launch_backward_meshes(m, (cudaStream_t)stream));
 }
@@ -782,7 +783,7 @@ int render_backward_on(const DibrStep* st, void* ls) {
     if (int e = dibr_backward_faces(p, ls)) return e;
     if (st->device_grad_pose && (!p->grad_pose_R || !p->grad_pose_t)) return fail("render_step: pose-gradient buffers are null");
     // the kernel's finalising block writes the [n,12] layout itself: no packing launch
-    if (int e = backward_meshes_impl(p, ls, st->device_grad_pose)) return e;
+    if (int e = backward_meshes_impl(p, ls, st->device_grad_pose, st->grad_pose_sum)) return e;
     if (st->device_grad_pose && st->host_grad_pose) {
         cudaError_t e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)p->num_instances,
                                         cudaMemcpyDeviceToHost, (cudaStream_t)ls);

@@ -525,6 +525,22 @@ __global__ void __launch_bounds__(MV_T) mesh_vertex_grad_kernel(MeshBwdParams P)
             if (P.grad_pose_packed) P.grad_pose_packed[(size_t)inst * 12 + 9 + j] = gt;
         }
     }
+    // ---- optional row num_instances of the packed gradients: their column sums, added in instance order by the block that
+    //      finalises the LAST instance -- the 12-float vector a data-parallel step all-reduces, ready without another launch
+    if (P.pose_sum && P.grad_pose_packed && P.pose_R) {
+        __shared__ unsigned int t2;
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); t2 = atomicAdd(&P.pose_done[P.num_instances], 1u); }
+        __syncthreads();
+        if (t2 != (unsigned)P.num_instances - 1u) return;
+        if (threadIdx.x == 0) P.pose_done[P.num_instances] = 0u;
+        __threadfence();
+        if (threadIdx.x < 12) {
+            float v = 0.f;
+            for (int i = 0; i < P.num_instances; i++) v += __ldcg(P.grad_pose_packed + (size_t)i * 12 + threadIdx.x);
+            P.grad_pose_packed[(size_t)P.num_instances * 12 + threadIdx.x] = v;
+        }
+    }
 }
 
 int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream)

@@ -29,7 +29,8 @@ struct Workspace {
     float* cam_pos;     // pose mode: [num_instances, 3]
     float* cam_proj;    // pose mode: [num_K, 16]
     int* list_counts;   // [2] entries in color_list / soft_list (+ padding), zeroed by dibr_forward
-    unsigned int* pose_done;    // [num_instances] vertex blocks that have delivered their pose sums (zeroed by dibr_forward with the lists)
+    unsigned int* pose_done;    // [num_instances + 1] vertex blocks that have delivered their pose sums (zeroed by dibr_forward with the lists);
+                                // last entry: instances that are final
     unsigned int* face_flags;   // [total_faces] zeroed by dibr_forward.  bit 0: the face won a pixel, bit 1: it entered a soft product
     unsigned char* open8;       // [batch, H, ceil(W/8)] bit x%8 of byte x/8: pixel (y, x) is uncovered.  Written by the forward for every
                                 // touched tile (the only ones a face's expanded pixel range can reach), read by the backward's soft part
@@ -169,6 +170,7 @@ struct MeshBwdParams {
     float* grad_pose_R;
     float* grad_pose_t;
     float* grad_pose_packed;   // optional [num_instances, 12]: dL/dR then dL/dt, the layout dibr_render_step copies back to the host
+    int pose_sum;              // the packed buffer has one more row that receives the column sums
 };
 
 // Tile bins.  Image b owns the global 32-face words [f_lo >> 5, (f_hi - 1) >> 5]; its bitmaps start at word

@@ -106,7 +106,9 @@ class RenderSession(object):
             self.g_fattr = torch.empty(max_faces, 3, self.student.D, **f32)
             self.g_pose_R = torch.empty(B, 9, **f32)
             self.g_pose_t = torch.empty(B, 3, **f32)
-            self.g_pose_dev = torch.empty(B, 12, **f32)
+            self._g_pose_all = torch.zeros(B + 1, 12, **f32)       # rows 0..B-1: dL/dR | dL/dt per sample; row B: their column sums
+            self.g_pose_dev = self._g_pose_all[:B]
+            self.g_pose_sum = self._g_pose_all[B]                  # written by the backward kernel: what a data-parallel step all-reduces
             self.g_pose_host = torch.empty(B, 12, dtype=torch.float32, pin_memory=True)
             # staging block, 4-byte words: sR[9B] st[3B] K[9B] tR[9B] tt[3B] desc[12B] face_off[B+1]
             self.off = {}
@@ -148,7 +150,8 @@ class RenderSession(object):
             st.teacher_normal_in = self.teacher.out["norm"].data_ptr()
             st.teacher_mask_in = self.teacher.out["ones"].data_ptr()
             st.teacher_normal_out = self.teacher.normal_map.data_ptr()
-        st.host_grad_pose, st.device_grad_pose = self.g_pose_host.data_ptr(), self.g_pose_dev.data_ptr()
+        st.host_grad_pose, st.device_grad_pose = self.g_pose_host.data_ptr(), self._g_pose_all.data_ptr()
+        st.grad_pose_sum = 1
         # side stream + events for the student / teacher overlap: owned by THIS session (the library keeps none)
         self._overlap = ctypes.c_void_p()
         with torch.cuda.device(self.device):

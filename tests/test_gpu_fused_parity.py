@@ -388,6 +388,11 @@ def test_render_session_graph_replay_equals_plain_launches():
         for k in res[0][0]:
             assert torch.equal(res[0][0][k], res[1][0][k]), (step, k)
         assert torch.equal(res[0][1], res[1][1]), step
+        # the check-sum row the backward kernel leaves for a data-parallel all-reduce: the rows added in instance order
+        acc = torch.zeros(12, device=DEV)
+        for i in range(B):
+            acc = acc + graph.g_pose_dev[i]
+        assert torch.equal(graph.g_pose_sum, acc) and torch.equal(plain.g_pose_sum, acc), step
     assert any(e[1] is not None for k, e in graph._graphs.items() if k[0] == "forward")
     assert any(e[1] is not None for k, e in graph._graphs.items() if k[0] == "backward")
     assert not plain._graphs
