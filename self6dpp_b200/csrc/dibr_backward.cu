@@ -21,7 +21,7 @@
 namespace dibr {
 
 #ifndef DIBR_COLOR_LANES
-#define DIBR_COLOR_LANES 8        // lanes per face (rows of its bbox per turn)
+#define DIBR_COLOR_LANES 4        // lanes per face (rows of its bbox per turn): 4 measured best (8: +6 us, 2: +2 us, 16: +16 us)
 #endif
 constexpr int GRP = DIBR_COLOR_LANES;     // lanes per face in the colour part
 
