@@ -420,3 +420,37 @@ def test_renderer_picks_up_modified_attributes_and_bounds_its_registry():
     for _ in range(140):                                           # fresh dicts (same tensors) every call
         ren.render_batch(Rs, ts, [dict(models[1])], Ks=torch.tensor(batch["Ks"], device=DEV), width=W, height=H, mode=["mask"])
     assert len(ren._registry.models) <= 130
+
+
+@pytest.mark.parametrize("hw", [(72, 100), (50, 62)])
+def test_normal_map_over_the_tiles_of_a_pass(hw):
+    """dibr_normal_map_pass (plan-driven: touched tiles normalised, the others zero) in place and into a separate tensor,
+    on images with partial tiles (and, for 62 columns, without the 16 B row alignment of the vector path), against the
+    torch expression of renderer_dibr.py:284-285 on the raw normals."""
+    from self6dpp_b200 import synth
+    from self6dpp_b200.session import RenderSession
+    from tests.golden.make_golden import small_meshes
+    meshes = small_meshes()
+    H, W = hw
+    ids = [2, 0, 1]
+    B = len(ids)
+    models = to_dev_models(meshes)
+    for m in models:
+        m["faces"] = m["faces"].to(torch.int32)
+    batch = synth.roi_batch([meshes[i] for i in ids], B, res=min(H, W), seed=21, fill=(0.4, 0.6))
+    tea = synth.roi_batch([meshes[i] for i in ids], B, res=min(H, W), seed=22, fill=(0.4, 0.6))
+    outs = {}
+    for raw in (False, True):
+        sess = RenderSession(models, B, H, W, raw_normals=raw, cuda_graphs=False)
+        out = sess.forward(batch["Rs"], batch["ts"], batch["Ks"], [models[i] for i in ids], tea["Rs"], tea["ts"])
+        sess.synchronize()
+        outs[raw] = ({k: v.clone() for k, v in out.items()}, sess)
+    for k in ("norm", "teacher_norm", "color", "prob", "mask"):
+        assert torch.equal(outs[False][0][k], outs[True][0][k]), k
+    for name, pb in (("norm", outs[True][1].student), ("teacher_norm", outs[True][1].teacher)):
+        n, m = pb.out["norm"], pb.out["ones"]
+        shift = n - n.min()
+        ref = shift / (torch.norm(shift, dim=-1, keepdim=True) + 1e-5) * m
+        got = outs[True][0][name]
+        assert float((got - ref).abs().max()) <= 2e-6, name
+        assert float(got[m.expand_as(got) == 0].abs().max()) == 0
