@@ -45,16 +45,19 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     }
     w.bins_bytes = sizeof(uint32_t) * dibr::bin_total_words(p->width, p->height, p->batch, p->total_faces);
     w.bins = (uint32_t*)take(w.bins_bytes);
+    const size_t ni = (size_t)(p->num_instances > 0 ? p->num_instances : 0);
+    // the backward's list counters, ticket counters and face flags sit directly behind the bitmaps: the set-up call clears
+    // plan + bitmaps + lists with ONE memset (dibr_forward clears the lists again when it is called on its own)
+    w.list_counts = (int*)take(sizeof(int) * 64);
+    w.pose_done = (unsigned int*)take(sizeof(unsigned int) * (ni + 1));
+    w.face_flags = (unsigned int*)take(sizeof(unsigned int) * (size_t)p->total_faces);
+    w.clear_bytes = w.order_cnt ? (size_t)((char*)w.face_flags - (char*)w.order_cnt) + sizeof(unsigned int) * (size_t)p->total_faces : 0;
     w.xs = (float*)take(sizeof(float) * (size_t)p->width);
     w.ys = (float*)take(sizeof(float) * (size_t)p->height);
     w.pose_part = (float*)take(sizeof(float) * 12 * dibr::POSE_BLOCKS * (size_t)(p->num_instances > 0 ? p->num_instances : 0));
-    const size_t ni = (size_t)(p->num_instances > 0 ? p->num_instances : 0);
     w.cam_rot = (float*)take(sizeof(float) * 9 * ni);
     w.cam_pos = (float*)take(sizeof(float) * 3 * ni);
     w.cam_proj = (float*)take(sizeof(float) * 16 * (size_t)(p->num_K > 0 ? p->num_K : 0));
-    w.list_counts = (int*)take(sizeof(int) * 64);
-    w.pose_done = (unsigned int*)take(sizeof(unsigned int) * (ni + 1));          // between the counters and the flags: same memset
-    w.face_flags = (unsigned int*)take(sizeof(unsigned int) * (size_t)p->total_faces);   // directly after list_counts: one memset
     w.color_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
     w.soft_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
     w.open8 = (unsigned char*)take((size_t)p->batch * p->height * ((p->width + 7) / 8));
@@ -122,6 +125,7 @@ dibr::SetupParams setup_params(const DibrPass* p) {
     s.face_attr = p->face_attr; s.face_normal = p->face_normal;
     s.ws = carve(p, p->workspace);
     s.pose_R = p->pose_R; s.pose_t = p->pose_t; s.pose_K = p->pose_K; s.num_K = p->num_K;
+    s.out_min = (p->min_output >= 0) ? p->out_min_ordered : nullptr;
     const double nc = p->znear, fc = p->zfar;
     s.expand_mul = (float)((double)p->expand * (double)p->multiplier);
     s.q = (float)(-(fc + nc) / (fc - nc));
@@ -304,7 +308,9 @@ int dibr_setup_meshes(const DibrPass* p, void* stream) {
     return cuda_fail("dibr_setup_meshes", dibr::launch_setup_meshes(s, (cudaStream_t)stream));
 }
 
-int dibr_forward(const DibrPass* p, void* stream) {
+// lists_clean: the set-up call of this pass has just run on the same stream (it cleared the work lists and reset the
+// minimum): the resets below are skipped (dibr_render_forward; two graph nodes less per pass)
+static int forward_impl(const DibrPass* p, void* stream, bool lists_clean) {
     if (int e = check_common(p, true)) return e;
     const bool fused = is_fused(p);
     if ((p->total_faces > 0 && !fused && !p->face_attr) || !p->improb || !p->imidx || !p->imcomp) return fail("forward: face_attr/improb/imidx/imcomp required");
@@ -337,8 +343,8 @@ int dibr_forward(const DibrPass* p, void* stream) {
     }
     f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
     f.list_counts = w.list_counts; f.face_flags = w.face_flags; f.color_list = w.color_list; f.soft_list = w.soft_list; f.open8 = w.open8;
-    {
-        const size_t nbytes = (size_t)((char*)w.color_list - (char*)w.list_counts);
+    if (!lists_clean) {
+        const size_t nbytes = (size_t)((char*)w.face_flags - (char*)w.list_counts) + sizeof(unsigned int) * (size_t)p->total_faces;
         cudaError_t e = cudaMemsetAsync(w.list_counts, 0, nbytes, (cudaStream_t)stream);
         if (e != cudaSuccess) return cuda_fail("dibr_forward (reset face lists)", (int)e);
     }
@@ -348,12 +354,16 @@ int dibr_forward(const DibrPass* p, void* stream) {
         f.min_group = p->min_output; f.out_min = p->out_min_ordered;
         for (int g = 0, d = 0; g < f.n_out; d += f.out_ch[g], g++)
             if (g == f.min_group) f.min_mask = ((1u << f.out_ch[g]) - 1u) << d;
-        cudaError_t e = cudaMemsetAsync(p->out_min_ordered, 0xff, sizeof(uint32_t), (cudaStream_t)stream);
-        if (e != cudaSuccess) return cuda_fail("dibr_forward (reset min)", (int)e);
+        if (!lists_clean) {
+            cudaError_t e = cudaMemsetAsync(p->out_min_ordered, 0xff, sizeof(uint32_t), (cudaStream_t)stream);
+            if (e != cudaSuccess) return cuda_fail("dibr_forward (reset min)", (int)e);
+        }
     }
     g_launches += 1;
     return cuda_fail("dibr_forward", dibr::launch_forward(f, (cudaStream_t)stream));
 }
+
+int dibr_forward(const DibrPass* p, void* stream) { return forward_impl(p, stream, false); }
 
 int dibr_backward_faces(const DibrPass* p, void* stream) {
     if (int e = check_common(p, true)) return e;
@@ -769,7 +779,7 @@ int render_forward_on(const DibrStep* st, void* stream, const ForkJoin& fj) {
         if (p->num_instances <= 0) continue;
         void* ks = (k == 0) ? fj.side(stream) : stream;          // student chain on the side stream, teacher on the caller's
         if (int e = dibr_setup_meshes(p, ks)) return e;
-        if (int e = dibr_forward(p, ks)) return e;
+        if (int e = forward_impl(p, ks, true)) return e;          // the set-up call above cleared the lists and the minimum
         if (nin[k]) {
             if (!p->out_min_ordered || p->min_output < 0) return fail("render_step: normal map needs min_output/out_min_ordered");
             if (int e = dibr_normal_map_pass(p, nin[k], nmask[k], nout[k], ks)) return e;

@@ -16,6 +16,7 @@ struct Workspace {
                         // backward gather the corner attributes through it instead of a materialised [F, 3, D] array
     uint32_t* bins;     // per image, per 16x16 tile: bitmap over the image's faces (bit = face may reach the tile); layout in bin_words()
     size_t bins_bytes;
+    size_t clear_bytes;  // from order_cnt to the end of face_flags: what the set-up call clears with one memset
     int* order_cnt;     // [4 * ORDER_BUCKETS] tiles per cost bucket (bucket = ceil(listed faces / 32), capped) + the plan summary
     int* tile_count;    // [batch * tiles] faces listed in the tile's bitmap (bumped by the binning; directly after order_cnt: same memset)
     int* img_done;      // [batch] faces of the image that are binned (the CTA that completes an image plans its tiles; same memset)
@@ -72,6 +73,7 @@ struct SetupParams {
     int num_K;
     float q, qn;             // -(f+n)/(f-n), -2fn/(f-n)
     float expand_mul;        // expand * multiplier: the bins cover the EXPANDED bboxes
+    unsigned int* out_min;   // the pass's batch-global minimum (ordered-uint encoding), reset to 'nothing seen' by the set-up kernel; or null
     Workspace ws;
 };
 

@@ -31,6 +31,7 @@ __device__ __forceinline__ int image_of_face(int g, int batch, int faces_per_ima
 }
 
 __device__ __forceinline__ void write_tables(const SetupParams& P, int gtid) {
+    if (gtid == 0 && P.out_min) *P.out_min = 0xffffffffu;          // batch-global minimum of the pass: nothing seen yet
     if (gtid < P.width) P.ws.xs[gtid] = pix_x(gtid, P.width, P.multiplier);
     else if (gtid < P.width + P.height) P.ws.ys[gtid - P.width] = pix_y(gtid - P.width, P.height, P.multiplier);
 }
@@ -398,10 +399,10 @@ static inline int setup_grid(const SetupParams& P) {
     return (n + SETUP_T - 1) / SETUP_T;
 }
 
-// plan counters, per-tile face counters, per-image progress counters and the tile bitmaps are adjacent in the workspace:
-// one memset
+// plan counters, per-tile face counters, per-image progress counters, the tile bitmaps and the backward's list counters /
+// face flags are adjacent in the workspace: one memset
 static inline cudaError_t clear_plan(const SetupParams& P, cudaStream_t stream) {
-    return cudaMemsetAsync(P.ws.order_cnt, 0, (size_t)((char*)P.ws.bins - (char*)P.ws.order_cnt) + P.ws.bins_bytes, stream);
+    return cudaMemsetAsync(P.ws.order_cnt, 0, P.ws.clear_bytes, stream);
 }
 
 int launch_setup_faces(const SetupParams& P, cudaStream_t stream)
