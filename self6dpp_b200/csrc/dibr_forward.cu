@@ -794,8 +794,9 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
                     int pa = 0, pb = FWD_THREADS;               // last pixel pp with E[pp] <= lo
                     while (pb - pa > 1) { const int mid = (pa + pb) >> 1; if ((int)s.E[mid] <= lo) pa = mid; else pb = mid; }
                     int pp = pa, k = lo - (int)s.E[pa];
+                    int npp = (int)s.E[pp + 1] - (int)s.E[pp];           // hits of pixel pp
                     for (int j = lo; j < hi; j++) {
-                        while (k >= (int)s.E[pp + 1] - (int)s.E[pp]) { pp++; k = 0; }
+                        while (k >= npp) { pp++; k = 0; npp = (int)s.E[pp + 1] - (int)s.E[pp]; }
                         const int lj = (int)s.u.hits[k][pp];
                         s.soft_used[lj] = 1;                    // benign race: everybody writes 1
                         const float4 a = s.c0[lj];
