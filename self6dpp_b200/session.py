@@ -165,7 +165,8 @@ class RenderSession(object):
         # is owned by the session (or, for the backward, is the caller's gradient tensor: another tensor -> another graph).
         self.cuda_graphs = bool(cuda_graphs)
         self._graphs = {}          # key -> [calls seen, CUDAGraph or None, kernels launched per replay]
-        self._last_slots, self._last_total = None, 0
+        self._last_slots, self._last_total, self._last_ids = None, 0, None
+        self._views = {name: self._h_f32[o:o + n].reshape(B, -1) for name, (o, n) in self.off.items() if name in ("sR", "st", "K", "tR", "tt")}
 
     # ------------------------------------------------------------------------------------------
     def _fill(self, name, arr):
@@ -184,15 +185,17 @@ class RenderSession(object):
         """poses / intrinsics / instance table -> pinned staging block; returns whether it must be uploaded"""
         B = self.B
         assert len(models) == B
-        slots = np.fromiter((self.model_slot[id(m)] for m in models), dtype=np.int64, count=B)
-        self._fill("sR", Rs)
-        self._fill("st", ts)
-        K = np.asarray(Ks, dtype=np.float32)
-        self._fill("K", np.broadcast_to(K.reshape(-1, 3, 3), (B, 3, 3)))
+        v = self._views                                        # float32 views of the staging block's sections, shaped like the inputs
+        np.copyto(v["sR"], np.asarray(Rs, dtype=np.float32).reshape(B, 9))
+        np.copyto(v["st"], np.asarray(ts, dtype=np.float32).reshape(B, 3))
+        np.copyto(v["K"], np.asarray(Ks, dtype=np.float32).reshape(-1, 9))          # one K broadcasts over the batch
         if self.teacher is not None:
-            self._fill("tR", teacher_Rs)
-            self._fill("tt", teacher_ts)
-        if self._last_slots is None or not np.array_equal(slots, self._last_slots):
+            np.copyto(v["tR"], np.asarray(teacher_Rs, dtype=np.float32).reshape(B, 9))
+            np.copyto(v["tt"], np.asarray(teacher_ts, dtype=np.float32).reshape(B, 3))
+        ids = tuple(map(id, models))                           # the composition: which resident model sits in which sample
+        if ids != self._last_ids:
+            self._last_ids = ids
+            slots = np.fromiter((self.model_slot[i] for i in ids), dtype=np.int64, count=B)
             # the instance table depends on WHICH models sit in the batch only: rebuilt when the composition changes
             tab = self.reg.table[slots]
             nf, nv = tab[:, 3], tab[:, 1]
