@@ -65,7 +65,8 @@ struct FwdSmem {
         } ab;
         unsigned int hits[HITCAP][FWD_THREADS]; //        phase D: list index of the k-th face of a pixel, then its result
     } u;
-    unsigned short E[FWD_THREADS + 2];          // phase D: exclusive scan of the pixels' hit counts
+    unsigned short E[FWD_THREADS];              // phase D: exclusive scan of the pixels' hit counts inside their warp
+    unsigned char nhc[FWD_THREADS];             // phase D: hit count of each pixel in the current pass
     unsigned char cnt[TILE * TILE];             // accepted faces per pixel (255 = covered)
     unsigned char soft_used[LCAP];              // listed faces that entered some pixel's soft product
     unsigned int smask[LCAP];                   //  2 KB  phase D: tile columns (bits 0-15) / rows (16-31) inside the face's expanded bbox
@@ -78,7 +79,7 @@ struct FwdSmem {
 // to the matching work list of the backward.  Warp-aggregated: one counter atomic per warp, every lane must call.
 __device__ __forceinline__ void mark_faces_warp(const FwdParams& P, bool want, int g, unsigned bit) {
     bool isnew = false;
-    if (want && (__ldcg(&P.face_flags[g]) & bit) == 0u) isnew = (atomicOr(&P.face_flags[g], bit) & bit) == 0u;
+    if (want) isnew = (atomicOr(&P.face_flags[g], bit) & bit) == 0u;
     const unsigned bal = __ballot_sync(0xffffffffu, isnew);
     if (bal == 0u) return;
     const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
@@ -132,6 +133,7 @@ __device__ int fill_list(FwdSmem& s, const FwdParams& P, int f_lo, int wpos, con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     int lcount = 0;
+    if (tid == 0) s.rcount = 0;         // ordered before the gather's atomicAdds by the barriers below; its last readers are past raster_list's barrier
     while (wpos < T.nw) {
         const int w = wpos + tid;
         uint32_t word = (w < T.nw) ? __ldg(T.words + w) : 0u;
@@ -181,8 +183,7 @@ __device__ int fill_list(FwdSmem& s, const FwdParams& P, int f_lo, int wpos, con
         wpos += FWD_THREADS;
     }
     wpos = min(wpos, T.nw);
-    __syncthreads();
-    if (tid == 0) { s.lcount = lcount; s.rcount = 0; }
+    if (tid == 0) s.lcount = lcount;    // uniform across the CTA: published for the phases after this call
     __syncthreads();
     // ---- gather the listed faces' records (the one L2 round trip of the list) and build the raster list:
     //      front faces with a non-empty pixel range (packed: list index | c0 | nc-1 | r0 | nr-1), any order
@@ -363,9 +364,8 @@ __device__ void raster_list(FwdSmem& s, int nprev)
             }
         }
         __syncthreads();
-        if (tid == 0) s.nbig = 0;
+        if (tid == 0) s.nbig = 0;           // everybody read it before the barrier; the next user sits behind fill_list's barriers
     }
-    __syncthreads();
 }
 
 // One WARP fills a 16x16 tile of one [H,W,CH] image: 128-bit stores, 2*CH per lane
@@ -440,20 +440,23 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
     int tile;
     int4 desc;               // plan entry: tile id, the image's face range, offset of the tile's bitmap
     {
-        // the plan's summary (last CTA of plan_tiles_kernel): surplus CTAs of the grid leave after one load
-        if ((int)blockIdx.x >= __ldg(P.order_cnt + PLAN_WORK_CTAS)) return;
-        const int touched = __ldg(P.order_cnt + PLAN_TOUCHED);
+        // the plan's summary (written by the set-up CTA that planned the last image): lane l reads the first position of
+        // bucket 31 - l, every lane the size of bucket 0 (untouched tiles) -- two independent loads, ONE trip to L2 before the
+        // tile's plan entry can be fetched.  Surplus CTAs of the grid leave here.
+        static_assert(ORDER_BUCKETS == 32, "one bucket per lane");
+        const int start = __ldg(P.order_cnt + PLAN_START + lane);                      // first position of bucket 31 - lane
+        const int n_untouched = __ldg(P.order_cnt);
+        const int touched = __shfl_sync(full_mask, start, 31);                        // bucket 0 comes last
+        if ((int)blockIdx.x >= touched + ((n_untouched + NWARP - 1) / NWARP)) return;
         if ((int)blockIdx.x >= touched) {
             // bucket 0 (empty bitmaps): one warp per tile, 8 tiles per CTA
             const int j = ((int)blockIdx.x - touched) * NWARP + warp;
 #ifndef DIBR_EXP_NOFILL
-            if (j < __ldg(P.order_cnt)) fill_untouched_warp(P, __ldg(P.order_seg + j));
+            if (j < n_untouched) fill_untouched_warp(P, __ldg(P.order_seg + j));
 #endif
             return;
         }
-        static_assert(ORDER_BUCKETS == 32, "one bucket per lane");
-        const int start = __ldg(P.order_cnt + PLAN_START + lane);                      // first position of bucket 31 - lane
-        const unsigned le = __ballot_sync(full_mask, start <= (int)blockIdx.x);       // lane 31 (bucket 0) starts at `touched`
+        const unsigned le = __ballot_sync(full_mask, start <= (int)blockIdx.x);
         const int src = 31 - __clz(le);
         desc = __ldg(P.order_desc + (size_t)(ORDER_BUCKETS - 1 - src) * ntiles + ((int)blockIdx.x - __shfl_sync(full_mask, start, src)));
         tile = desc.x;
@@ -493,7 +496,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         T.id0 = (w0 << 5) - f_lo;
         T.words = P.bins + (size_t)(unsigned)desc.w;
     }
-    __syncthreads();
+    // no barrier here: nothing reads these before fill_list's first barrier
 
     int nbatch = 0, parity = 0;
     {
@@ -553,7 +556,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         // winners go on the backward's colour work list (run-length de-duplicated along the row)
         const int prev = __shfl_up_sync(full_mask, fw, 1);
         const bool lead = fw >= 0 && (lx == 0 || prev != fw);
-        const unsigned fl = lead ? __ldcg(&P.face_flags[f_lo + fw]) : 1u;
+        const unsigned fl = lead ? atomicOr(&P.face_flags[f_lo + fw], 1u) : 1u;     // issued here, consumed behind the attribute work
         float vmin = 3.0e38f;                        // minimum of output group P.min_group
         if (val) {
             const size_t gp = (size_t)(ty0 + ly) * P.width + (tx0 + lx);
@@ -661,7 +664,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         {
             bool isnew = false;
             const int g = f_lo + max(fw, 0);
-            if (lead && (fl & 1u) == 0u) isnew = (atomicOr(&P.face_flags[g], 1u) & 1u) == 0u;
+            isnew = lead && (fl & 1u) == 0u;
             const unsigned nb = __ballot_sync(full_mask, isnew);
             if (nb) {
                 const int leader = __ffs(nb) - 1;
@@ -714,7 +717,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         // per listed face s.smask holds the tile's columns (bits 0-15) and rows (bits 16-31) whose pixel centres lie inside
         // its expanded bbox (rasterizer.py:54-57): written with the records by fill_list
         unsigned int* const smask = s.smask;
-        __syncthreads();
+        // (no barrier: soft_used is first written behind the collect step's barrier, the lists are stable since fill_list's last one)
         const int c_start = c;
         // passes of HITCAP hits per pixel (one pass unless K > HITCAP)
         for (int skip = 0;; skip += HITCAP) {
@@ -762,41 +765,59 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
                         }
                     } else {
                         // many: transpose the 32 x 32 bit matrix (5 shuffles), every pixel then walks its own faces only
-                        for (unsigned t = transpose32(m32, lane); t && open; t &= t - 1) accept(__ffs(t) - 1);
+                        unsigned t = transpose32(m32, lane);
+                        if (!open) t = 0u;
+                        const int n = __popc(t);
+                        // the common chunk: first pass, and no pixel of the block reaches its K-th face or the end of its hit
+                        // row inside it -> plain appends, none of accept()'s bookkeeping
+                        const bool easy = (skip == 0) && (c_start + seen + n < knum) && (nh + n <= HITCAP);
+                        if (__all_sync(full_mask, easy)) {
+                            seen += n;
+                            for (; t; t &= t - 1) s.u.hits[nh++][tid] = (unsigned)(i0 + __ffs(t) - 1);
+                        } else {
+                            for (; t && open; t &= t - 1) accept(__ffs(t) - 1);
+                        }
                     }
                     if (!__any_sync(full_mask, open)) break;
                 }
             }
-            // (2) all pairs of the tile, dealt out evenly: exclusive scan of the hit counts ...
+            // (2) all pairs of the tile, dealt out evenly: every warp publishes the exclusive scan of its pixels' hit counts and
+            //     its total BEFORE the barrier that ends the collect step, so no second barrier is needed to find the pairs
             int incl = nh;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(full_mask, incl, o);
                 if (lane >= o) incl += t;
             }
+            s.E[tid] = (unsigned short)(incl - nh);
+            s.nhc[tid] = (unsigned char)nh;
             if (lane == 31) s.warp_tot[parity][warp] = incl;
-            const int any_more = __syncthreads_or(more ? 1 : 0);        // hit lists + warp totals visible
-            int wbase = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < NWARP; w++) {
-                const int t = s.warp_tot[parity][w];
-                if (w < warp) wbase += t;
-                total += t;
-            }
+            const int any_more = __syncthreads_or(more ? 1 : 0);        // hit lists, scans and warp totals visible
+            const int par = parity;
             parity ^= 1;
+            int total = 0;
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) total += s.warp_tot[par][w];
             if (total > 0) {
-                s.E[tid] = (unsigned short)(wbase + incl - nh);
-                if (tid == 0) s.E[FWD_THREADS] = (unsigned short)total;
-                __syncthreads();
                 // ... thread t evaluates the flat range [t*total/256, (t+1)*total/256)
                 const int lo = (int)(((long long)tid * total) / FWD_THREADS), hi = (int)(((long long)(tid + 1) * total) / FWD_THREADS);
                 if (hi > lo) {
-                    int pa = 0, pb = FWD_THREADS;               // last pixel pp with E[pp] <= lo
-                    while (pb - pa > 1) { const int mid = (pa + pb) >> 1; if ((int)s.E[mid] <= lo) pa = mid; else pb = mid; }
-                    int pp = pa, k = lo - (int)s.E[pa];
-                    int npp = (int)s.E[pp + 1] - (int)s.E[pp];           // hits of pixel pp
+                    // the warp that holds pair `lo` (the last one starting at or before it), then the pixel inside that warp
+                    int wq0 = 0, ws = 0;
+#pragma unroll
+                    for (int w = 0; w < NWARP - 1; w++) {
+                        const int t = s.warp_tot[par][w];
+                        if (wq0 == w && ws + t <= lo) { ws += t; wq0 = w + 1; }
+                    }
+                    const int rel = lo - ws;
+                    const unsigned short* Ew = s.E + wq0 * 32;
+                    int pa = 0;                                 // last lane with Ew[lane] <= rel
+#pragma unroll
+                    for (int stp = 16; stp >= 1; stp >>= 1) if ((int)Ew[pa + stp] <= rel) pa += stp;
+                    int pp = wq0 * 32 + pa, k = rel - (int)Ew[pa];
+                    int npp = (int)s.nhc[pp];                   // hits of pixel pp
                     for (int j = lo; j < hi; j++) {
-                        while (k >= npp) { pp++; k = 0; npp = (int)s.E[pp + 1] - (int)s.E[pp]; }
+                        while (k >= npp) { pp++; k = 0; npp = (int)s.nhc[pp]; }
                         const int lj = (int)s.u.hits[k][pp];
                         s.soft_used[lj] = 1;                    // benign race: everybody writes 1
                         const float4 a = s.c0[lj];
@@ -808,7 +829,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
                         k++;
                     }
                 }
-                __syncthreads();
+                __syncthreads();                                // results (and soft_used) of this pass complete
                 // (3) each pixel folds its own results in ascending face order
                 for (int k = 0; k < nh; k++) {
                     float p, om;
@@ -821,7 +842,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
             if (!any_more) break;
             __syncthreads();                                    // the hit lists are rewritten by the next pass
         }
-        __syncthreads();                                        // soft_used complete
+        // soft_used is complete: its writers sit in front of the barrier above the last fold
         // hand the faces that contributed to the backward's work list
         for (int li0 = 0; li0 < lcount; li0 += FWD_THREADS) {
             const int li = li0 + tid;
