@@ -402,7 +402,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     }
     b.grad_improb = p->grad_improb;
     b.grad_points2d = p->grad_points2d; b.grad_face_attr = p->grad_face_attr;
-    g_launches += 1;
+    g_launches += 2;     // prepare_backward_kernel + backward_faces_kernel
     return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream));
 }
 

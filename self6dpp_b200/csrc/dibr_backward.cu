@@ -343,11 +343,63 @@ __global__ void __launch_bounds__(256, (DMAX <= 8) ? DIBR_BWD_MIN_CTAS : 2) back
     }
 }
 
+// Ahead of the face kernel, in the launch that used to be the memset of dL/dpoints2d: (1) zero dL/dpoints2d (faces on neither
+// work list keep a zero gradient, the two bodies add into it); (2) compact the flags the forward left (bit 0: won a pixel,
+// bit 1: entered a soft product) into the colour and the soft work list -- one counter atomic per CTA and list.  A face that
+// has been listed gets bit 2 / bit 3, so a second backward over the same forward appends nothing and finds the lists as they are.
+constexpr int PREP_THREADS = 1024;
+__global__ void __launch_bounds__(PREP_THREADS) prepare_backward_kernel(const BwdParams P)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const long long n = 6ll * P.total_faces;
+        const long long t0 = (long long)blockIdx.x * PREP_THREADS + tid, stride = (long long)gridDim.x * PREP_THREADS;
+        if ((reinterpret_cast<uintptr_t>(P.grad_points2d) & 15) == 0) {
+            const long long n4 = n >> 2;
+            for (long long i = t0; i < n4; i += stride) reinterpret_cast<float4*>(P.grad_points2d)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (long long i = (n4 << 2) + t0; i < n; i += stride) P.grad_points2d[i] = 0.f;
+        } else {
+            for (long long i = t0; i < n; i += stride) P.grad_points2d[i] = 0.f;
+        }
+    }
+    __shared__ int wcnt[2][PREP_THREADS / 32];
+    unsigned int* __restrict__ flags = reinterpret_cast<unsigned int*>(const_cast<unsigned char*>(P.face_flags));
+    for (int g0 = blockIdx.x * PREP_THREADS; g0 < P.total_faces; g0 += gridDim.x * PREP_THREADS) {     // uniform across the CTA
+        const int g = g0 + tid;
+        const unsigned f = (g < P.total_faces) ? flags[g] : 0u;
+        const bool nc = (f & 5u) == 1u, ns = (f & 10u) == 2u;
+        const unsigned bc = __ballot_sync(0xffffffffu, nc), bs = __ballot_sync(0xffffffffu, ns);
+        if (lane == 0) { wcnt[0][warp] = __popc(bc); wcnt[1][warp] = __popc(bs); }
+        __syncthreads();
+        if (warp < 2) {                                     // warp 0: colour list, warp 1: soft list
+            const int c = wcnt[warp][lane];
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            int b0 = 0;
+            if (lane == 0 && total > 0) b0 = atomicAdd(&P.list_counts[warp], total);
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+            wcnt[warp][lane] = b0 + incl - c;               // where this warp's entries start
+        }
+        __syncthreads();
+        const unsigned lt = (1u << lane) - 1u;
+        if (nc) P.color_list[wcnt[0][warp] + __popc(bc & lt)] = g;
+        if (ns) P.soft_list[wcnt[1][warp] + __popc(bs & lt)] = g;
+        if (nc || ns) flags[g] = f | (nc ? 4u : 0u) | (ns ? 8u : 0u);
+        __syncthreads();                                    // wcnt is rewritten by the next round
+    }
+}
+
 int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
 {
     if (P.total_faces <= 0) return 0;
-    // faces on neither work list keep a zero gradient
-    cudaError_t e = cudaMemsetAsync(P.grad_points2d, 0, sizeof(float) * 6 * (size_t)P.total_faces, stream);
+    static_assert(PREP_THREADS / 32 == 32, "one warp scans the 32 warp counts of a list");
+    prepare_backward_kernel<<<min((P.total_faces + PREP_THREADS - 1) / PREP_THREADS, 148 * 2), PREP_THREADS, 0, stream>>>(P);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
     if (!do_color && !do_soft) {                     // no upstream gradient at all: everything is zero

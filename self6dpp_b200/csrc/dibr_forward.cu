@@ -75,18 +75,11 @@ struct FwdSmem {
     int nbig, lcount, rcount, pad0;
 };
 
-// The first time a face is seen doing `bit`-type work (1: won a pixel, 2: entered a soft product) it is appended
-// to the matching work list of the backward.  Warp-aggregated: one counter atomic per warp, every lane must call.
-__device__ __forceinline__ void mark_faces_warp(const FwdParams& P, bool want, int g, unsigned bit) {
-    bool isnew = false;
-    if (want) isnew = (atomicOr(&P.face_flags[g], bit) & bit) == 0u;
-    const unsigned bal = __ballot_sync(0xffffffffu, isnew);
-    if (bal == 0u) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&P.list_counts[bit == 1u ? 0 : 1], __popc(bal));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (isnew) (bit == 1u ? P.color_list : P.soft_list)[base + __popc(bal & ((1u << lane) - 1u))] = g;
+// Faces that did `bit`-type work (1: won a pixel, 2: entered a soft product) are flagged with a fire-and-forget atomic (RED):
+// the backward compacts the flags into its two work lists before it starts (prepare_backward_kernel), so no tile waits
+// for a returning atomic on a list counter that every CTA of the grid is hammering.
+__device__ __forceinline__ void mark_face(const FwdParams& P, int g, unsigned bit) {
+    atomicOr(&P.face_flags[g], bit);
 }
 
 // rows = lanes, columns = bits: returns column `lane` of the 32x32 bit matrix as this lane's word
@@ -553,10 +546,10 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
                 }
             }
         }
-        // winners go on the backward's colour work list (run-length de-duplicated along the row)
+        // winners are flagged for the backward's colour work list (run-length de-duplicated along the row)
         const int prev = __shfl_up_sync(full_mask, fw, 1);
         const bool lead = fw >= 0 && (lx == 0 || prev != fw);
-        const unsigned fl = lead ? atomicOr(&P.face_flags[f_lo + fw], 1u) : 1u;     // issued here, consumed behind the attribute work
+        if (lead) mark_face(P, f_lo + fw, 1u);
         float vmin = 3.0e38f;                        // minimum of output group P.min_group
         if (val) {
             const size_t gp = (size_t)(ty0 + ly) * P.width + (tx0 + lx);
@@ -658,20 +651,6 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
                     P.chan_out[d][px * P.chan_stride[d]] = vdep;
                     if ((P.min_mask >> d) & 1u) vmin = fminf(vmin, vdep);
                 }
-            }
-        }
-        // append first-time winners to the colour list: one counter atomic per warp
-        {
-            bool isnew = false;
-            const int g = f_lo + max(fw, 0);
-            isnew = lead && (fl & 1u) == 0u;
-            const unsigned nb = __ballot_sync(full_mask, isnew);
-            if (nb) {
-                const int leader = __ffs(nb) - 1;
-                int lb = 0;
-                if (lane == leader) lb = atomicAdd(&P.list_counts[0], __popc(nb));
-                lb = __shfl_sync(full_mask, lb, leader);
-                if (isnew) P.color_list[lb + __popc(nb & ((1u << lane) - 1u))] = g;
             }
         }
         if (P.min_group >= 0) {
@@ -846,8 +825,7 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         // hand the faces that contributed to the backward's work list
         for (int li0 = 0; li0 < lcount; li0 += FWD_THREADS) {
             const int li = li0 + tid;
-            const bool used = (li < lcount) && s.soft_used[li];
-            mark_faces_warp(P, used, used ? f_lo + s.lid[li] : 0, 2u);
+            if (li < lcount && s.soft_used[li]) mark_face(P, f_lo + s.lid[li], 2u);
         }
         if (single) break;
         // stop early once every uncovered pixel has its K faces

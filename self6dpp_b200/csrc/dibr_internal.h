@@ -29,13 +29,13 @@ struct Workspace {
     float* cam_rot;     // pose mode: [num_instances, 9]
     float* cam_pos;     // pose mode: [num_instances, 3]
     float* cam_proj;    // pose mode: [num_K, 16]
-    int* list_counts;   // [2] entries in color_list / soft_list (+ padding), zeroed by dibr_forward
+    int* list_counts;   // [2] entries in color_list / soft_list (+ padding), zeroed ahead of the forward, filled by the backward
     unsigned int* pose_done;    // [num_instances + 1] vertex blocks that have delivered their pose sums (zeroed by dibr_forward with the lists);
                                 // last entry: instances that are final
-    unsigned int* face_flags;   // [total_faces] zeroed by dibr_forward.  bit 0: the face won a pixel, bit 1: it entered a soft product
+    unsigned int* face_flags;   // [total_faces] zeroed by dibr_forward.  bit 0: the face won a pixel, bit 1: it entered a soft product (set by the forward); bits 2, 3: listed (set by the backward)
     unsigned char* open8;       // [batch, H, ceil(W/8)] bit x%8 of byte x/8: pixel (y, x) is uncovered.  Written by the forward for every
                                 // touched tile (the only ones a face's expanded pixel range can reach), read by the backward's soft part
-    int* color_list;    // [total_faces] global face ids that won at least one pixel (appended by the forward, arbitrary order)
+    int* color_list;    // [total_faces] global face ids that won at least one pixel (compacted from face_flags by the backward, arbitrary order)
     int* soft_list;     // [total_faces] global face ids that entered at least one soft-silhouette product
     size_t bytes;
 };
