@@ -85,7 +85,10 @@ typedef struct DibrPass {
     int32_t vert_attr_dim;          /* channels read per vertex */
     int32_t attr_flags;             /* bit0: append a ones channel (vcrender_batch.py:87-88);
                                        bit1: append view depth -z_view (= z of R v + t,
-                                       renderer_dibr.py:296-301) as one more channel */
+                                       renderer_dibr.py:296-301) as one more channel;
+                                       bit2: grad_face_attr is SCRATCH between dibr_backward_faces and dibr_backward_meshes
+                                       (the caller never reads it; ignored when grad_vert_attr is set): only the depth
+                                       channel's corner gradients are kept, as [total_faces, 3] at the start of the buffer */
     const float *cam_rot;           /* [ncam, 9]  cam_view_R = diag(1,-1,-1) R   (base.py:169) */
     const float *cam_pos;           /* [ncam, 3]  cam_view_pos = -(R^T t)        (base.py:170) */
     const float *cam_proj;          /* [nproj, 16] row-major 4x4 used as [p,1] @ proj (perspective.py:122-129) */

@@ -101,6 +101,9 @@ int check_outputs(const DibrPass* p) {
 
 // a pass set up by dibr_setup_meshes: the corner attributes are gathered from the vertex table, face_attr is not used
 bool is_fused(const DibrPass* p) { return p->num_instances > 0 && p->inst_desc && p->verts && p->mesh_faces; }
+// attr_flags bit 2 (fused passes): the caller never reads grad_face_attr -- it is scratch between dibr_backward_faces and
+// dibr_backward_meshes, which needs the depth channel alone.  Ignored when the per-vertex attribute gradient is asked for.
+bool attr_compact(const DibrPass* p) { return is_fused(p) && (p->attr_flags & 4) != 0 && !p->grad_vert_attr; }
 
 void set_vertex_attr(dibr::VertexAttr& va, const DibrPass* p, const dibr::Workspace& w) {
     va.fvid = w.fvid;
@@ -402,6 +405,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     }
     b.grad_improb = p->grad_improb;
     b.grad_points2d = p->grad_points2d; b.grad_face_attr = p->grad_face_attr;
+    b.attr_compact = attr_compact(p) ? 1 : 0;
     g_launches += 2;     // prepare_backward_kernel + backward_faces_kernel
     return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream));
 }
@@ -422,7 +426,7 @@ static int backward_meshes_impl(const DibrPass* p, void* stream, float* packed, 
     m.cam_proj = p->pose_R ? w.cam_proj : p->cam_proj;
     m.pose_R = p->pose_R; m.pose_t = p->pose_t; m.grad_pose_R = p->grad_pose_R; m.grad_pose_t = p->grad_pose_t;
     m.vert_attr_dim = p->vert_attr_dim; m.attr_flags = p->attr_flags; m.num_attr = p->num_attr;
-    m.grad_points2d = p->grad_points2d; m.grad_face_attr = p->grad_face_attr;
+    m.grad_points2d = p->grad_points2d; m.grad_face_attr = p->grad_face_attr; m.attr_compact = attr_compact(p) ? 1 : 0;
     m.vert_face_ptr = p->vert_face_ptr; m.vert_face_idx = p->vert_face_idx;
     m.grad_verts = p->grad_verts; m.grad_vert_attr = p->grad_vert_attr;
     m.grad_cam_rot = p->grad_cam_rot; m.grad_cam_pos = p->grad_cam_pos; m.pose_part = w.pose_part; m.pose_done = w.pose_done;

@@ -162,6 +162,16 @@ __device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
         atomicAdd(gpo + 2 * i + 0, inv * (-fk.q * A[i] + fk.p * Bv[i]));
         atomicAdd(gpo + 2 * i + 1, inv * (fk.n * A[i] - fk.m * Bv[i]));
     }
+    if (P.attr_compact) {
+        // nobody but dibr_backward_meshes reads dL/dattr, and it reads the depth channel alone: three floats per face
+        if (dep) {
+            float* __restrict__ g3 = P.grad_face_attr + (size_t)g * 3;
+#pragma unroll
+            for (int d = 0; d < DMAX; d++)
+                if (d == nA + ones) { g3[0] = acc[0 * DMAX + d]; g3[1] = acc[1 * DMAX + d]; g3[2] = acc[2 * DMAX + d]; }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(256, (DMAX <= 8) ? DIBR_BWD_MIN_CTAS : 2) back
 {
     // dL/dattr of the faces that won no pixel is zero.  The colour body writes the whole row of every face on its list, so
     // only the OTHER rows are cleared here (about half of them, inside this launch) instead of a memset of the whole array.
-    {
+    if (!P.attr_compact) {           // (compact mode: prepare_backward_kernel has zeroed the [total_faces, 3] depth column)
         const unsigned int* __restrict__ flags = reinterpret_cast<const unsigned int*>(P.face_flags);
         const int row = 3 * P.num_attr;                                     // floats per face
         const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
@@ -362,6 +372,10 @@ __global__ void __launch_bounds__(PREP_THREADS) prepare_backward_kernel(const Bw
             for (long long i = t0; i < n; i += stride) P.grad_points2d[i] = 0.f;
         }
     }
+    if (P.attr_compact && (P.va.flags & 2)) {               // the compact depth column of dL/dattr: rows of unlisted faces stay zero
+        const long long n = 3ll * P.total_faces;
+        for (long long i = (long long)blockIdx.x * PREP_THREADS + tid; i < n; i += (long long)gridDim.x * PREP_THREADS) P.grad_face_attr[i] = 0.f;
+    }
     __shared__ int wcnt[2][PREP_THREADS / 32];
     unsigned int* __restrict__ flags = reinterpret_cast<unsigned int*>(const_cast<unsigned char*>(P.face_flags));
     for (int g0 = blockIdx.x * PREP_THREADS; g0 < P.total_faces; g0 += gridDim.x * PREP_THREADS) {     // uniform across the CTA
@@ -403,6 +417,7 @@ int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
     if (e != cudaSuccess) return (int)e;
     const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
     if (!do_color && !do_soft) {                     // no upstream gradient at all: everything is zero
+        if (P.attr_compact) return 0;                // (the prepare kernel has zeroed the compact column)
         e = cudaMemsetAsync(P.grad_face_attr, 0, sizeof(float) * 3 * (size_t)P.num_attr * (size_t)P.total_faces, stream);
         return (int)e;
     }
@@ -462,7 +477,7 @@ __global__ void __launch_bounds__(MV_T) mesh_vertex_grad_kernel(MeshBwdParams P)
                 if (fcs[k] >= 0) {
                     const int gf = fbase + fcs[k] / 3, c = fcs[k] % 3;
                     g2[k] = *reinterpret_cast<const float2*>(P.grad_points2d + (size_t)gf * 6 + c * 2);
-                    if (depth_ch >= 0) gdk[k] = P.grad_face_attr[((size_t)gf * 3 + c) * D + depth_ch];
+                    if (depth_ch >= 0) gdk[k] = P.attr_compact ? P.grad_face_attr[(size_t)gf * 3 + c] : P.grad_face_attr[((size_t)gf * 3 + c) * D + depth_ch];
                 }
             }
 #pragma unroll

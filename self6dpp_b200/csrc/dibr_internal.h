@@ -145,6 +145,8 @@ struct BwdParams {
     const float* grad_improb;
     float* grad_points2d;
     float* grad_face_attr;
+    int attr_compact;          // attr_flags bit 2: grad_face_attr is scratch for dibr_backward_meshes alone -- only the depth channel's
+                               // corner gradients are kept, as a [total_faces, 3] array at its start (nothing when there is no depth channel)
 };
 
 struct MeshBwdParams {
@@ -173,6 +175,7 @@ struct MeshBwdParams {
     float* grad_pose_t;
     float* grad_pose_packed;   // optional [num_instances, 12]: dL/dR then dL/dt, the layout dibr_render_step copies back to the host
     int pose_sum;              // the packed buffer has one more row that receives the column sums
+    int attr_compact;          // grad_face_attr holds the depth channel alone, [total_faces, 3] (see BwdParams)
 };
 
 // Tile bins.  Image b owns the global 32-face words [f_lo >> 5, (f_hi - 1) >> 5]; its bitmaps start at word

@@ -23,6 +23,7 @@ from .rasterizer import (DEFAULT_DELTA, DEFAULT_EXPAND, DEFAULT_KNUM, DEFAULT_MU
 INST_STRIDE = 12
 FLAG_ONES = 1
 FLAG_DEPTH = 2
+FLAG_ATTR_GRAD_SCRATCH = 4      # include/dibr_b200.h attr_flags bit 2: grad_face_attr is scratch (depth column only, [F, 3])
 
 
 class MeshPack(object):

@@ -30,11 +30,11 @@ _MODE_ATTR = (("color", "colors"), ("norm", "normals"), ("xyz", "vertices"))
 
 
 class _PassBuffers(object):
-    def __init__(self, reg, mode, batch, height, width, max_faces, device, znear, zfar, knum=None, raw_normals=False):
+    def __init__(self, reg, mode, batch, height, width, max_faces, device, znear, zfar, knum=None, raw_normals=False, face_attr_grad=True):
         self.names = [a for k, a in _MODE_ATTR if k in mode]
         self.keys = [k for k, a in _MODE_ATTR if k in mode] + ["ones"] + (["depth"] if "depth" in mode else [])
         self.split = [3] * len(self.names) + [1] + ([1] if "depth" in mode else [])
-        self.flags = fused.FLAG_ONES | (fused.FLAG_DEPTH if "depth" in mode else 0)
+        self.flags = fused.FLAG_ONES | (fused.FLAG_DEPTH if "depth" in mode else 0) | (0 if face_attr_grad else fused.FLAG_ATTR_GRAD_SCRATCH)
         self.A = 3 * len(self.names)
         self.D = sum(self.split)
         self.vattr = reg.attr_matrix(self.names) if self.names else torch.zeros(0, 4, dtype=torch.float32, device=device)
@@ -82,7 +82,7 @@ class _PassBuffers(object):
 class RenderSession(object):
     def __init__(self, models, batch, height, width, student_mode=("color", "depth", "mask", "norm", "prob"),
                  teacher_mode=("norm",), device="cuda:0", znear=0.01, zfar=100.0, teacher_soft_mask=True, raw_normals=False,
-                 cuda_graphs=True):
+                 cuda_graphs=True, face_attr_grad=False):
         """``teacher_soft_mask=False`` skips the soft-silhouette phase of the teacher rasterisation (K = 0).  The reference
         always computes it (kaolin's forward does) and then drops it when ``mode`` has no "color"
         (renderer_dibr.py:273-286), so nothing a caller can observe changes; the default keeps the reference's work."""
@@ -98,12 +98,14 @@ class RenderSession(object):
         B = self.B
         max_faces = B * int(reg.table[:, 3].max())
         with torch.cuda.device(self.device):
-            self.student = _PassBuffers(reg, student_mode, B, self.H, self.W, max_faces, self.device, znear, zfar, raw_normals=raw_normals)
+            self.student = _PassBuffers(reg, student_mode, B, self.H, self.W, max_faces, self.device, znear, zfar, raw_normals=raw_normals, face_attr_grad=face_attr_grad)
             self.teacher = _PassBuffers(reg, teacher_mode, B, self.H, self.W, max_faces, self.device, znear, zfar, raw_normals=raw_normals,
                                         knum=None if teacher_soft_mask else 0) if teacher_mode else None
             f32 = dict(dtype=torch.float32, device=self.device)
             self.g_p2d = torch.empty(max_faces, 6, **f32)
-            self.g_fattr = torch.empty(max_faces, 3, self.student.D, **f32)
+            # dL/d(corner attributes): between the two backward kernels only.  The resident models take no gradient, so the
+            # vertex stage reads its depth column alone -- kept as [F, 3] unless face_attr_grad=True asks for the full array
+            self.g_fattr = torch.empty(max_faces, 3, self.student.D, **f32) if face_attr_grad else torch.empty(max_faces, 3, **f32)
             self.g_pose_R = torch.empty(B, 9, **f32)
             self.g_pose_t = torch.empty(B, 3, **f32)
             self._g_pose_all = torch.zeros(B + 1, 12, **f32)       # rows 0..B-1: dL/dR | dL/dt per sample; row B: their column sums

@@ -61,7 +61,7 @@ def cfg2():
     models = dev_models(meshes)
     cur = [models[int(i)] for i in student["ids"]]
     B, RES = bench.BATCH, bench.RES
-    sess = RenderSession(models, B, RES, RES, device=DEV, raw_normals=True)    # the oracle comparison reads the interpolated normals
+    sess = RenderSession(models, B, RES, RES, device=DEV, raw_normals=True, face_attr_grad=True)    # the oracle comparison reads the interpolated normals and the full dL/dattr
     out = sess.forward(student["Rs"], student["ts"], student["Ks"], cur, teacher["Rs"], teacher["ts"])
     sess.synchronize()
     return dict(meshes=meshes, student=student, teacher=teacher, sess=sess, out=out, cur=cur, B=B, RES=RES)

@@ -354,6 +354,19 @@ def test_render_session_composition_change_and_lean_teacher():
     for k in ref_out:
         assert torch.equal(out_l[k], ref_out[k]), k
     assert torch.equal(grad_l, ref_grad)
+    # (3) face_attr_grad=True keeps the full dL/d(corner attributes) array between the two backward kernels instead of the
+    # [F, 3] depth column the vertex stage reads (attr_flags bit 2): same pose gradients, and the depth column is the same
+    full = RenderSession(models, B, H, W, face_attr_grad=True)
+    out_f, grad_f = run(full, ids_b)
+    for k in ref_out:
+        assert torch.equal(out_f[k], ref_out[k]), k
+    assert torch.equal(grad_f, ref_grad)
+    nf = sum(int(models[i]["faces"].shape[0]) for i in ids_b)
+    dcol = full.student.keys.index("depth") if "depth" in full.student.keys else None
+    assert full.g_fattr.dim() == 3 and ref_sess.g_fattr.dim() == 2
+    ch = sum(full.student.split[:dcol])
+    assert torch.equal(full.g_fattr[:nf, :, ch], ref_sess.g_fattr[:nf])
+    assert float(ref_sess.g_fattr[:nf].abs().max()) > 0
 
 
 def test_render_session_graph_replay_equals_plain_launches():

@@ -19,14 +19,22 @@ sess.synchronize()
 lib = _lib.load()
 stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-ts = []
-for it in range(23):
-    flush.zero_()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    assert lib.dibr_backward_faces(ctypes.byref(sess.st.student), stream) == 0
-    b.record()
-    torch.cuda.synchronize()
-    if it >= 3:
-        ts.append(a.elapsed_time(b) * 1e3)
-print("backward_faces call %.1f us (median of %d)" % (statistics.median(ts), len(ts)), flush=True)
+def timed(label):
+    ts = []
+    for it in range(23):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        assert lib.dibr_backward_faces(ctypes.byref(sess.st.student), stream) == 0
+        b.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(a.elapsed_time(b) * 1e3)
+    print("backward_faces call (%s) %.1f us (median of %d)" % (label, statistics.median(ts), len(ts)), flush=True)
+timed("colour + soft")
+if "split" in sys.argv:
+    sess._set_grads(gc, None, gd)
+    timed("colour part only")
+    sess._set_grads(None, gp, None)
+    timed("soft part only")
+    sess._set_grads(gc, gp, gd)
