@@ -137,7 +137,7 @@ __device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
     float A[3] = {0.f, 0.f, 0.f}, Bv[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int d = 0; d < DMAX; d++) {
-        if (d < D) {
+        if (d < D && P.chan_grad[d]) {                  // (a channel without an upstream gradient has acc == 0: it adds nothing)
             float c0v, e1, e2;
             if (!fusedm) { c0v = a[d]; e1 = a[D + d] - c0v; e2 = a[2 * D + d] - c0v; }
             else if (d < nA) { c0v = __ldg(a0 + d); e1 = __ldg(a1 + d) - c0v; e2 = __ldg(a2 + d) - c0v; }
@@ -357,62 +357,78 @@ __global__ void __launch_bounds__(256, (DMAX <= 8) ? DIBR_BWD_MIN_CTAS : 2) back
 // work list keep a zero gradient, the two bodies add into it); (2) compact the flags the forward left (bit 0: won a pixel,
 // bit 1: entered a soft product) into the colour and the soft work list -- one counter atomic per CTA and list.  A face that
 // has been listed gets bit 2 / bit 3, so a second backward over the same forward appends nothing and finds the lists as they are.
-constexpr int PREP_THREADS = 1024;
+constexpr int PREP_THREADS = 256, PREP_FACES = 4 * PREP_THREADS;       // four faces per thread: one 16 B load of their flags
 __global__ void __launch_bounds__(PREP_THREADS) prepare_backward_kernel(const BwdParams P)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = gridDim.x * PREP_THREADS, t0 = blockIdx.x * PREP_THREADS + tid;
     {
-        const long long n = 6ll * P.total_faces;
-        const long long t0 = (long long)blockIdx.x * PREP_THREADS + tid, stride = (long long)gridDim.x * PREP_THREADS;
+        const int n = 6 * P.total_faces;                    // (total_faces < 2^31 / 6: the ABI caps batch x faces well below)
         if ((reinterpret_cast<uintptr_t>(P.grad_points2d) & 15) == 0) {
-            const long long n4 = n >> 2;
-            for (long long i = t0; i < n4; i += stride) reinterpret_cast<float4*>(P.grad_points2d)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (long long i = (n4 << 2) + t0; i < n; i += stride) P.grad_points2d[i] = 0.f;
+            const int n4 = n >> 2;
+            float4* __restrict__ o = reinterpret_cast<float4*>(P.grad_points2d);
+            for (int i = t0; i < n4; i += nthreads) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = (n4 << 2) + t0; i < n; i += nthreads) P.grad_points2d[i] = 0.f;
         } else {
-            for (long long i = t0; i < n; i += stride) P.grad_points2d[i] = 0.f;
+            for (int i = t0; i < n; i += nthreads) P.grad_points2d[i] = 0.f;
         }
     }
     if (P.attr_compact && (P.va.flags & 2)) {               // the compact depth column of dL/dattr: rows of unlisted faces stay zero
-        const long long n = 3ll * P.total_faces;
-        for (long long i = (long long)blockIdx.x * PREP_THREADS + tid; i < n; i += (long long)gridDim.x * PREP_THREADS) P.grad_face_attr[i] = 0.f;
+        const int n = 3 * P.total_faces;
+        for (int i = t0; i < n; i += nthreads) P.grad_face_attr[i] = 0.f;
     }
     __shared__ int wcnt[2][PREP_THREADS / 32];
+    __shared__ int cta_base[2];
     unsigned int* __restrict__ flags = reinterpret_cast<unsigned int*>(const_cast<unsigned char*>(P.face_flags));
-    for (int g0 = blockIdx.x * PREP_THREADS; g0 < P.total_faces; g0 += gridDim.x * PREP_THREADS) {     // uniform across the CTA
-        const int g = g0 + tid;
-        const unsigned f = (g < P.total_faces) ? flags[g] : 0u;
-        const bool nc = (f & 5u) == 1u, ns = (f & 10u) == 2u;
-        const unsigned bc = __ballot_sync(0xffffffffu, nc), bs = __ballot_sync(0xffffffffu, ns);
-        if (lane == 0) { wcnt[0][warp] = __popc(bc); wcnt[1][warp] = __popc(bs); }
-        __syncthreads();
-        if (warp < 2) {                                     // warp 0: colour list, warp 1: soft list
-            const int c = wcnt[warp][lane];
-            int incl = c;
+    const bool vec = (reinterpret_cast<uintptr_t>(flags) & 15) == 0;
+    for (int g0 = blockIdx.x * PREP_FACES; g0 < P.total_faces; g0 += gridDim.x * PREP_FACES) {          // uniform across the CTA
+        const int g = g0 + 4 * tid;
+        unsigned f[4] = {0u, 0u, 0u, 0u};
+        if (vec && g + 3 < P.total_faces) {
+            const uint4 v = *reinterpret_cast<const uint4*>(flags + g);
+            f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+        } else {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            int b0 = 0;
-            if (lane == 0 && total > 0) b0 = atomicAdd(&P.list_counts[warp], total);
-            b0 = __shfl_sync(0xffffffffu, b0, 0);
-            wcnt[warp][lane] = b0 + incl - c;               // where this warp's entries start
+            for (int k = 0; k < 4; k++) if (g + k < P.total_faces) f[k] = flags[g + k];
+        }
+        int nc = 0, ns = 0;                                 // this thread's new entries of the colour / soft list
+#pragma unroll
+        for (int k = 0; k < 4; k++) { nc += ((f[k] & 5u) == 1u) ? 1 : 0; ns += ((f[k] & 10u) == 2u) ? 1 : 0; }
+        int ic = nc, is = ns;                               // inclusive scans over the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, ic, o), b2 = __shfl_up_sync(0xffffffffu, is, o);
+            if (lane >= o) { ic += a; is += b2; }
+        }
+        if (lane == 31) { wcnt[0][warp] = ic; wcnt[1][warp] = is; }
+        __syncthreads();
+        if (tid < 2) {                                      // one counter atomic per CTA and list
+            int total = 0;
+#pragma unroll
+            for (int w = 0; w < PREP_THREADS / 32; w++) total += wcnt[tid][w];
+            cta_base[tid] = total > 0 ? atomicAdd(&P.list_counts[tid], total) : 0;
         }
         __syncthreads();
-        const unsigned lt = (1u << lane) - 1u;
-        if (nc) P.color_list[wcnt[0][warp] + __popc(bc & lt)] = g;
-        if (ns) P.soft_list[wcnt[1][warp] + __popc(bs & lt)] = g;
-        if (nc || ns) flags[g] = f | (nc ? 4u : 0u) | (ns ? 8u : 0u);
-        __syncthreads();                                    // wcnt is rewritten by the next round
+        int oc = cta_base[0] + ic - nc, os = cta_base[1] + is - ns;
+        for (int w = 0; w < warp; w++) { oc += wcnt[0][w]; os += wcnt[1][w]; }
+        if (nc | ns) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool c = (f[k] & 5u) == 1u, s2 = (f[k] & 10u) == 2u;
+                if (c) P.color_list[oc++] = g + k;
+                if (s2) P.soft_list[os++] = g + k;
+                if (c || s2) flags[g + k] = f[k] | (c ? 4u : 0u) | (s2 ? 8u : 0u);
+            }
+        }
+        __syncthreads();                                    // wcnt / cta_base are rewritten by the next round
     }
 }
 
 int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
 {
     if (P.total_faces <= 0) return 0;
-    static_assert(PREP_THREADS / 32 == 32, "one warp scans the 32 warp counts of a list");
-    prepare_backward_kernel<<<min((P.total_faces + PREP_THREADS - 1) / PREP_THREADS, 148 * 2), PREP_THREADS, 0, stream>>>(P);
+    if (P.total_faces > (1 << 28)) return (int)cudaErrorInvalidValue;       // 6 * total_faces is indexed with int
+    prepare_backward_kernel<<<min((P.total_faces + PREP_FACES - 1) / PREP_FACES, 148 * 8), PREP_THREADS, 0, stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;

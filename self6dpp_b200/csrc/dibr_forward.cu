@@ -72,7 +72,7 @@ struct FwdSmem {
     unsigned int smask[LCAP];                   //  2 KB  phase D: tile columns (bits 0-15) / rows (16-31) inside the face's expanded bbox
     float xs[TILE], ys[TILE];
     int warp_tot[2][NWARP];
-    int nbig, lcount, rcount, pad0;
+    int nbig, lcount, rcount, rnext;            // rnext: next unclaimed entry of the raster list (warps draw four faces at a time)
 };
 
 // Faces that did `bit`-type work (1: won a pixel, 2: entered a soft product) are flagged with a fire-and-forget atomic (RED):
@@ -126,7 +126,7 @@ __device__ int fill_list(FwdSmem& s, const FwdParams& P, int f_lo, int wpos, con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     int lcount = 0;
-    if (tid == 0) s.rcount = 0;         // ordered before the gather's atomicAdds by the barriers below; its last readers are past raster_list's barrier
+    if (tid == 0) { s.rcount = 0; s.rnext = 0; }         // ordered before the gather's atomicAdds by the barriers below; its last readers are past raster_list's barrier
     while (wpos < T.nw) {
         const int w = wpos + tid;
         uint32_t word = (w < T.nw) ? __ldg(T.words + w) : 0u;
@@ -275,7 +275,11 @@ __device__ void raster_list(FwdSmem& s, int nprev)
     int qn = 0;                                                         // queued candidates of this warp (< 32 between turns)
     // ---- RASTER_LANES lanes per face; faces with many pixels in the tile are deferred to the whole CTA
     const int ql = tid % RASTER_LANES;
-    for (int e0 = warp * (32 / RASTER_LANES); e0 < rcount; e0 += FWD_THREADS / RASTER_LANES) {
+    for (;;) {
+        int e0 = 0;
+        if (lane == 0) e0 = atomicAdd(&s.rnext, 32 / RASTER_LANES);     // the faces' pixel counts differ: warps draw work instead of striding (-1.5 us)
+        e0 = __shfl_sync(full_mask, e0, 0);
+        if (e0 >= rcount) break;
         const int e = e0 + lane / RASTER_LANES;
         int npx = 0, li = 0, c0 = 0, r0 = 0, nc = 1;
         float ax = 0.f, ay = 0.f, em = 0.f, ep = 0.f, en_ = 0.f, eq = 0.f, sg = 1.f, lim = 0.f;

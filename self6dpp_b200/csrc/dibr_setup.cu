@@ -65,7 +65,10 @@ __device__ __forceinline__ void bin_face_warp(const SetupParams& P, int g, int b
     const int nmax = __reduce_max_sync(full, n);
     for (int j = 0; j < min(nmax, 4); j++) {
         int t = -1;                                              // tile of this lane's slot j, unique over the batch with b
-        if (j < n) { const int ry = j / ntx; t = (ty0 + ry) * tiles_x + tx0 + (j - ry * ntx); }
+        if (j < n) {                                             // j < 4: the row of slot j without an integer division
+            const int ry = (j >= ntx ? 1 : 0) + (j >= 2 * ntx ? 1 : 0) + (j >= 3 * ntx ? 1 : 0);
+            t = (ty0 + ry) * tiles_x + tx0 + (j - ry * ntx);
+        }
         const int key = t < 0 ? -1 : b * tiles + t;
         const unsigned peers = __match_any_sync(full, key);
         if (t >= 0 && lane == __ffs(peers) - 1) {                // bit = lane = g & 31: the CTA starts on a multiple of 32

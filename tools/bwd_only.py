@@ -21,7 +21,7 @@ stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 def timed(label):
     ts = []
-    for it in range(23):
+    for it in range(5 if "short" in sys.argv else 23):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -31,6 +31,12 @@ def timed(label):
         if it >= 3:
             ts.append(a.elapsed_time(b) * 1e3)
     print("backward_faces call (%s) %.1f us (median of %d)" % (label, statistics.median(ts), len(ts)), flush=True)
+al = lambda x: (x + 255) // 256 * 256
+_p = sess.student.p
+_nt = B * ((RES + 15) // 16) ** 2
+_F = _p.total_faces
+_off = al(64 * _F) + al(16 * _F) + al(4 * 32 * _nt) + al(16 * 32 * _nt) + al(4 * 4 * 32) + al(4 * _nt) + al(4 * B) + al(4 * (_nt // B) * ((_F + 31) // 32 + B + 1))
+print("work lists (colour, soft):", sess.student.ws[_off:_off + 8].view(torch.int32).cpu().tolist(), "of", int(sess._last_total), "faces in use")
 timed("colour + soft")
 if "split" in sys.argv:
     sess._set_grads(gc, None, gd)
