@@ -61,6 +61,7 @@ dibr::Workspace carve(const DibrPass* p, void* base) {
     w.color_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
     w.soft_list = (int*)take(sizeof(int) * (size_t)p->total_faces);
     w.open8 = (unsigned char*)take((size_t)p->batch * p->height * ((p->width + 7) / 8));
+    w.closed8 = (unsigned char*)take((size_t)p->batch * p->height * ((p->width + 7) / 8));
     w.bytes = off;
     return w;
 }
@@ -345,7 +346,7 @@ static int forward_impl(const DibrPass* p, void* stream, bool lists_clean) {
             if (((uintptr_t)f.out[g] & 15u) != 0 || (((long long)p->width * f.out_ch[g]) & 3) != 0) f.vec_out = 0;
     }
     f.improb = p->improb; f.imcomp = p->imcomp; f.imidx = p->imidx;
-    f.list_counts = w.list_counts; f.face_flags = w.face_flags; f.color_list = w.color_list; f.soft_list = w.soft_list; f.open8 = w.open8;
+    f.list_counts = w.list_counts; f.face_flags = w.face_flags; f.color_list = w.color_list; f.soft_list = w.soft_list; f.open8 = w.open8; f.closed8 = w.closed8;
     if (!lists_clean) {
         const size_t nbytes = (size_t)((char*)w.face_flags - (char*)w.list_counts) + sizeof(unsigned int) * (size_t)p->total_faces;
         cudaError_t e = cudaMemsetAsync(w.list_counts, 0, nbytes, (cudaStream_t)stream);
@@ -385,7 +386,7 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     b.recs = w.recs; b.xs = w.xs; b.ys = w.ys; b.face_attr = p->face_attr;
     if (fused) set_vertex_attr(b.va, p, w);
     b.improb = p->improb; b.imcomp = p->imcomp; b.imidx = p->imidx;
-    b.list_counts = w.list_counts; b.face_flags = (const unsigned char*)w.face_flags; b.color_list = w.color_list; b.soft_list = w.soft_list; b.open8 = w.open8;
+    b.list_counts = w.list_counts; b.face_flags = (const unsigned char*)w.face_flags; b.color_list = w.color_list; b.soft_list = w.soft_list; b.open8 = w.open8; b.closed8 = w.closed8;
     if (p->num_outputs < 0 || p->num_outputs > DIBR_MAX_OUTPUTS) return fail("num_outputs=%d outside [0,%d]", p->num_outputs, DIBR_MAX_OUTPUTS);
     b.any_grad_im = 0;
     if (p->num_outputs == 0) {

@@ -49,7 +49,7 @@ __device__ __forceinline__ void backward_color_body(const BwdParams& P, int bid)
         g = P.color_list[gi];
         rec = P.recs[g];
         const int b = __float_as_int(rec.image);
-        const int f = g - (P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image);
+        const int f = __float_as_int(rec.local_id);
         const size_t img = (size_t)b * H * W;
         const int32_t* __restrict__ idx = P.imidx + img;
         // pixel centres inside the face's bbox: the ranges the set-up kernel left in the record
@@ -198,7 +198,7 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid)
     const int g = P.soft_list[wi];
     const FaceRec rec = P.recs[g];
     const int b = __float_as_int(rec.image);
-    const int f = g - (P.face_offsets ? P.face_offsets[b] : b * P.faces_per_image);
+    const int f = __float_as_int(rec.local_id);
     const size_t img = (size_t)b * H * W;
     const int32_t* __restrict__ idx = P.imidx + img;
     const float* __restrict__ gpr = P.grad_improb + img;
@@ -255,18 +255,25 @@ __device__ __forceinline__ void backward_soft_body(const BwdParams& P, int bid)
     // bit-reproducible.
     const int wb = (W + 7) >> 3;
     const unsigned char* __restrict__ orow = P.open8 + (size_t)b * H * wb;
+    const unsigned char* __restrict__ crow = P.closed8 + (size_t)b * H * wb;
     for (int rb = r0; rb < r1; rb += SOFT_LANES) {
         const int r = rb + lane;
         for (int cbase = c0 & ~7; cbase < c1; cbase += 32) {
             unsigned m = 0u;
             if (r < r1) {
-                const unsigned char* __restrict__ ob = orow + (size_t)r * wb + (cbase >> 3);
+                const size_t o8 = (size_t)r * wb + (cbase >> 3);
+                unsigned mc = 0u;                               // uncovered pixels closed by their K-th face: imidx = -(that face + 1)
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    if (cbase + 8 * k < c1 && (cbase >> 3) + k < wb) m |= (unsigned)__ldg(ob + k) << (8 * k);
+                    if (cbase + 8 * k < c1 && (cbase >> 3) + k < wb) {
+                        m |= (unsigned)__ldg(orow + o8 + k) << (8 * k);
+                        mc |= (unsigned)__ldg(crow + o8 + k) << (8 * k);
+                    }
                 const int lo = max(c0 - cbase, 0), hi = min(c1 - cbase, 32);
                 m &= ((hi >= 32) ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-                for (unsigned t = m; t; t &= t - 1) {             // uncovered: keep the pixels where this face is within the first K
+                // an uncovered pixel that never reached K faces counted every near face; a closed one (about one in eight)
+                // only the faces up to its K-th: imidx is read there alone
+                for (unsigned t = m & mc; t; t &= t - 1) {
                     const int bit = __ffs(t) - 1;
                     const int v = idx[(size_t)r * W + cbase + bit];
                     if (!(v == 0 || f + 1 <= -v)) m &= ~(1u << bit);

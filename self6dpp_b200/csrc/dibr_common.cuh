@@ -31,7 +31,7 @@ constexpr int BIG_FACE_PIXELS = 512;            // bbox pixel centres above whic
 struct __align__(16) FaceRec {
     float ax, ay, bx, by;           // 2D corners, already x multiplier
     float cx, cy, az, bz;           // third corner, view-space z of a and b
-    float cz, nz, image, pad1;      // view-space z of c, z of the face normal (< 0: back face), image index (int bits)
+    float cz, nz, image, local_id;  // view-space z of c, z of the face normal (< 0: back face), image index and the face's id inside its image (int bits)
     // pixel ranges, lo | hi << 16 (hi exclusive, both clamped to the image): the pixel centres inside the bbox of the 2D
     // corners (rasterizer.py:49-52, half-open) and inside the expanded bbox (rasterizer.py:54-57).  All four are 0
     // (empty) for a face with a non-finite corner.

@@ -666,8 +666,11 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         const unsigned ub = __ballot_sync(full_mask, unc);
         if ((lane & 7) == 0) {
             const int row = ty0 + (tid >> 4), bytecol = (tx0 >> 3) + ((lane >> 3) & 1);
-            if (row < P.height && bytecol * 8 < P.width)
-                P.open8[((size_t)b * P.height + row) * ((P.width + 7) >> 3) + bytecol] = (unsigned char)((ub >> lane) & 0xffu);
+            if (row < P.height && bytecol * 8 < P.width) {
+                const size_t o8 = ((size_t)b * P.height + row) * ((P.width + 7) >> 3) + bytecol;
+                P.open8[o8] = (unsigned char)((ub >> lane) & 0xffu);
+                P.closed8[o8] = 0;                           // phase D overwrites it where a pixel gets its K-th face
+            }
         }
     }
     const int tile_unc = __syncthreads_or(unc ? 1 : 0);        // also: cnt[] complete, the z-buffer is dead
@@ -836,6 +839,14 @@ dibr_forward_kernel(const __grid_constant__ FwdParams P)
         if (!__syncthreads_or((c < knum) ? 1 : 0)) break;
     }
     if (had) { improb[gpix] = fminf(q, 1.0f); imcomp[gpix] = cc; }     // the recurrence can overshoot 1 by an ulp
+    {   // pixels closed by their K-th face (imidx < 0), one byte per row of the block: the backward reads imidx there alone
+        const unsigned cb = __ballot_sync(full_mask, had && c >= knum);
+        if ((lane & 7) == 0 && cb) {
+            const int row = ty0 + ly, bytecol = (tx0 + bx) >> 3;
+            if (row < P.height && bytecol * 8 < P.width)
+                P.closed8[((size_t)b * P.height + row) * ((P.width + 7) >> 3) + bytecol] = (unsigned char)((cb >> lane) & 0xffu);
+        }
+    }
     PHASE_MARK(4);
 }
 

@@ -35,6 +35,8 @@ struct Workspace {
     unsigned int* face_flags;   // [total_faces] zeroed by dibr_forward.  bit 0: the face won a pixel, bit 1: it entered a soft product (set by the forward); bits 2, 3: listed (set by the backward)
     unsigned char* open8;       // [batch, H, ceil(W/8)] bit x%8 of byte x/8: pixel (y, x) is uncovered.  Written by the forward for every
                                 // touched tile (the only ones a face's expanded pixel range can reach), read by the backward's soft part
+    unsigned char* closed8;     // same layout: the uncovered pixel was closed by its K-th face (imidx < 0): the only uncovered pixels
+                                // where the backward has to look at imidx
     int* color_list;    // [total_faces] global face ids that won at least one pixel (compacted from face_flags by the backward, arbitrary order)
     int* soft_list;     // [total_faces] global face ids that entered at least one soft-silhouette product
     size_t bytes;
@@ -117,6 +119,7 @@ struct FwdParams {
     int* color_list;
     int* soft_list;
     unsigned char* open8;
+    unsigned char* closed8;
     int min_group;             // output group whose batch-global minimum is accumulated, or -1
     unsigned int* out_min;     // ordered-uint encoding
 };
@@ -135,6 +138,7 @@ struct BwdParams {
     const float* imcomp;
     const int32_t* imidx;
     const unsigned char* open8;
+    const unsigned char* closed8;
     int* list_counts;          // [0] colour list length, [1] soft list length
     const unsigned char* face_flags;
     int* color_list;

@@ -115,7 +115,9 @@ __device__ __forceinline__ void store_face(const SetupParams& P, StageSmem& st, 
     const int t = threadIdx.x;
     st.rec[rec_slot(t, 0)] = make_float4(ax, ay, bx, by);
     st.rec[rec_slot(t, 1)] = make_float4(cx, cy, az, bz);
-    st.rec[rec_slot(t, 2)] = make_float4(cz, nz, __int_as_float(b), 0.f);
+    // (the face's id inside its image rides along: the backward needs it against imidx and would otherwise chain a load of face_offsets[b])
+    const int f_lo = (active && b >= 0) ? (P.face_offsets ? __ldg(P.face_offsets + b) : b * P.faces_per_image) : 0;
+    st.rec[rec_slot(t, 2)] = make_float4(cz, nz, __int_as_float(b), __int_as_float(g - f_lo));
     st.rec[rec_slot(t, 3)] = make_float4(__uint_as_float((unsigned)c0 | ((unsigned)c1 << 16)), __uint_as_float((unsigned)r0 | ((unsigned)r1 << 16)),
                                          __uint_as_float((unsigned)e0 | ((unsigned)e1 << 16)), __uint_as_float((unsigned)q0 | ((unsigned)q1 << 16)));
     bin_face_warp(P, g, b, ok, e0, e1, q0, q1);
