@@ -17,7 +17,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from .rasterizer import (DEFAULT_DELTA, DEFAULT_EXPAND, DEFAULT_KNUM, DEFAULT_MULTIPLIER, _alloc_workspace,
+from .rasterizer import (DEFAULT_DELTA, DEFAULT_EXPAND, DEFAULT_KNUM, DEFAULT_MULTIPLIER, _alloc_workspace, _on_device,
                          _base_pass, _require_cuda_f32, _stream)
 
 INST_STRIDE = 12
@@ -88,6 +88,22 @@ def dedup(tensors):
     return distinct, ids
 
 
+_PASS_TEMPLATES = {}     # signature of a fused pass -> (bytes of the filled DibrPass, workspace bytes)
+
+
+def _pass_from_template(key, build):
+    """A DibrPass whose size / option fields are already filled: ~60 ctypes field stores and the workspace-size call are paid
+    once per configuration, every later call copies the struct (one memmove) and sets its pointers."""
+    hit = _PASS_TEMPLATES.get(key)
+    if hit is None:
+        p = build()
+        nbytes = _lib.workspace_bytes(p)
+        if len(_PASS_TEMPLATES) > 256:
+            _PASS_TEMPLATES.clear()
+        hit = _PASS_TEMPLATES[key] = (bytes(p), nbytes)
+    return _lib.DibrPass.from_buffer_copy(hit[0]), hit[1]
+
+
 class RenderMeshes(Function):
     """forward(verts_packed [SV,3], vattr_packed [SA,A], cam_rot [I,3,3], cam_pos [I,3], cam_proj [P,4,4], meta)
     -> (out_0 [B,H,W,c0], ..., out_n [B,H,W,cn], improb [B,H,W,1], face_normal [TF,3] or empty).
@@ -105,57 +121,89 @@ class RenderMeshes(Function):
         A, flags = meta["attr_dim"], meta["attr_flags"]
         D = A + (1 if flags & FLAG_ONES else 0) + (1 if flags & FLAG_DEPTH else 0)
         TF = meta["total_faces"]
-        verts_c = verts.detach().contiguous()
-        vattr_c = vattr.detach().contiguous() if A > 0 else None
+        # (inside Function.forward autograd is off: a contiguous input is used as it is, no detach() alias per call)
+        verts_c = verts if verts.is_contiguous() else verts.contiguous()
+        vattr_c = (vattr if vattr.is_contiguous() else vattr.contiguous()) if A > 0 else None
         if A > 0:
             _require_cuda_f32("vertex attributes", vattr)
-        rot_c = cam_rot.detach().contiguous()
-        pos_c = cam_pos.detach().contiguous()
-        proj_c = cam_proj.detach().contiguous()
-        with torch.cuda.device(device):
-            p = _base_pass(B, H, W, D, meta["knum"], meta["multiplier"], meta["delta"], meta["expand"], TF, 0)
-            p.face_offsets = _lib.ptr(meta["face_offsets"])
-            p.num_instances = meta["num_instances"]
-            if meta.get("pose_mode"):
-                p.num_K = int(proj_c.shape[0])          # the workspace holds the derived cameras
-            ws = _alloc_workspace(p, device)
+        rot_c = cam_rot if cam_rot.is_contiguous() else cam_rot.contiguous()
+        pos_c = cam_pos if cam_pos.is_contiguous() else cam_pos.contiguous()
+        proj_c = cam_proj if cam_proj.is_contiguous() else cam_proj.contiguous()
+        pose_mode = bool(meta.get("pose_mode"))
+        split = meta.get("out_split") or [D]
+        assert sum(split) == D and len(split) <= 6, (split, D)
+        min_output = meta.get("min_output")
+        nmap_spec = meta.get("normal_map")          # (normals group, mask group): the normal map comes out of this call too
+        num_K = int(proj_c.shape[0]) if pose_mode else 0
+        vs, vas = int(meta.get("verts_stride", 0)), int(meta.get("vert_attr_stride", 0))
+        key = (B, H, W, D, meta["knum"], meta["multiplier"], meta["delta"], meta["expand"], TF, meta["num_instances"], A, flags,
+               vs, vas, pose_mode, num_K, float(meta.get("znear", 0.0)), float(meta.get("zfar", 0.0)), tuple(split), min_output)
+
+        def build():
+            q = _base_pass(B, H, W, D, meta["knum"], meta["multiplier"], meta["delta"], meta["expand"], TF, 0)
+            q.num_instances = meta["num_instances"]
+            q.vert_attr_dim, q.attr_flags = A, flags
+            q.verts_stride, q.vert_attr_stride = vs, vas
+            if pose_mode:
+                q.num_K = num_K                          # the workspace holds the derived cameras
+                q.znear, q.zfar = float(meta["znear"]), float(meta["zfar"])
+            q.num_outputs = len(split)
+            for g, c in enumerate(split):
+                q.out_channels[g] = c
+            if min_output is not None:
+                q.min_output = int(min_output)
+            return q
+        with _on_device(device):
+            p, nbytes = _pass_from_template(key, build)
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+            p.face_offsets = meta["face_offsets"].data_ptr()
             # (no [F, 3, D] corner-attribute array: the kernels gather from the vertex table through the faces' row ids)
             face_normal = torch.empty(TF, 3, dtype=torch.float32, device=device) if meta["want_normals"] else None
-            split = meta.get("out_split") or [D]
-            assert sum(split) == D and len(split) <= 6, (split, D)
             outs = [torch.empty(B, H, W, c, dtype=torch.float32, device=device) for c in split]
             improb = torch.empty(B, H, W, 1, dtype=torch.float32, device=device)
             imcomp = torch.empty(B, H, W, dtype=torch.float32, device=device)
             imidx = torch.empty(B, H, W, dtype=torch.int32, device=device)
             pack = meta["pack"]
-            p.inst_desc = _lib.ptr(meta["inst_desc"])
-            p.verts, p.mesh_faces = _lib.ptr(verts_c), _lib.ptr(pack.faces)
-            p.vert_attr, p.vert_attr_dim, p.attr_flags = _lib.ptr(vattr_c), A, flags
-            p.verts_stride, p.vert_attr_stride = int(meta.get("verts_stride", 0)), int(meta.get("vert_attr_stride", 0))
-            if meta.get("pose_mode"):      # cam_rot / cam_pos / cam_proj carry R [I,3,3], t [I,3], K [nK,3,3]
-                p.pose_R, p.pose_t, p.pose_K = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
-                p.num_K = int(proj_c.shape[0])
-                p.znear, p.zfar = float(meta["znear"]), float(meta["zfar"])
+            p.inst_desc = meta["inst_desc"].data_ptr()
+            p.verts, p.mesh_faces = verts_c.data_ptr(), pack.faces.data_ptr()
+            p.vert_attr = vattr_c.data_ptr() if vattr_c is not None else None
+            if pose_mode:      # cam_rot / cam_pos / cam_proj carry R [I,3,3], t [I,3], K [nK,3,3]
+                p.pose_R, p.pose_t, p.pose_K = rot_c.data_ptr(), pos_c.data_ptr(), proj_c.data_ptr()
             else:
-                p.cam_rot, p.cam_pos, p.cam_proj = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
+                p.cam_rot, p.cam_pos, p.cam_proj = rot_c.data_ptr(), pos_c.data_ptr(), proj_c.data_ptr()
             p.face_normal = _lib.ptr(face_normal)
-            p.improb, p.imidx, p.imcomp = _lib.ptr(improb), _lib.ptr(imidx), _lib.ptr(imcomp)
-            p.num_outputs = len(split)
-            for g, (c, o) in enumerate(zip(split, outs)):
-                p.out_channels[g] = c
+            p.improb, p.imidx, p.imcomp = improb.data_ptr(), imidx.data_ptr(), imcomp.data_ptr()
+            for g, o in enumerate(outs):
                 p.out[g] = o.data_ptr()
-            if meta.get("min_output") is not None:      # batch-global minimum of one output group (normal maps)
+            out_min = None
+            if min_output is not None:      # batch-global minimum of one output group (normal maps)
                 out_min = torch.empty(1, dtype=torch.int32, device=device)
-                p.min_output = int(meta["min_output"])
-                p.out_min_ordered = ctypes.c_void_p(out_min.data_ptr())
+                p.out_min_ordered = out_min.data_ptr()
                 meta["out_min"] = out_min
             lib = _lib.load()
             st = _stream(device)
             _lib.check(lib.dibr_setup_meshes(ctypes.byref(p), st), "dibr_setup_meshes")
             _lib.check(lib.dibr_forward(ctypes.byref(p), st), "dibr_forward")
+            nmap = None
+            if nmap_spec is not None and out_min is not None:
+                # renderer_dibr.py:281-286 over the tiles of the pass some face reaches, the others zero-filled: same values as
+                # dibr_normal_map over every pixel (tests/test_gpu_fused_parity.py), a fraction of the traffic
+                nmap = torch.empty_like(outs[nmap_spec[0]])
+                _lib.check(lib.dibr_normal_map_pass(ctypes.byref(p), ctypes.c_void_p(outs[nmap_spec[0]].data_ptr()),
+                                                    ctypes.c_void_p(outs[nmap_spec[1]].data_ptr()), ctypes.c_void_p(nmap.data_ptr()), st),
+                           "dibr_normal_map_pass")
         if meta.get("keep_pass"):      # bench_util.time_forward_kernel re-launches dibr_forward on these buffers
             meta["_last_pass"] = (p, [verts_c, vattr_c, rot_c, pos_c, proj_c, face_normal, outs, improb, imcomp, imidx, ws])
-        ctx.save_for_backward(verts_c, rot_c, pos_c, proj_c, vattr_c if A > 0 else None, improb, imcomp, imidx, ws)
+        # (outputs go through save_for_backward, never onto ctx directly: an output held by its own node is a reference cycle,
+        # and 200 MB of images per call would wait for the cyclic collector)
+        if nmap is not None:
+            ctx.save_for_backward(verts_c, rot_c, pos_c, proj_c, vattr_c if A > 0 else None, improb, imcomp, imidx, ws,
+                                  outs[nmap_spec[0]], outs[nmap_spec[1]])
+        else:
+            ctx.save_for_backward(verts_c, rot_c, pos_c, proj_c, vattr_c if A > 0 else None, improb, imcomp, imidx, ws)
+        ctx.pass_struct = p          # the backward completes this struct (its pointers stay valid: the tensors are saved above / in meta)
+        ctx.nmap_spec = nmap_spec if nmap is not None else None
         ctx.meta = meta
         ctx.dims = (D, A, flags)
         ctx.split = list(split)
@@ -165,45 +213,47 @@ class RenderMeshes(Function):
             face_normal = torch.empty(0, 3, dtype=torch.float32, device=device)
         ctx.mark_non_differentiable(face_normal)
         ctx.set_materialize_grads(False)
+        if nmap is not None:
+            return (*outs, improb, face_normal, nmap)
         return (*outs, improb, face_normal)
 
     @staticmethod
     def backward(ctx, *grads):
+        g_nmap = None
+        saved = ctx.saved_tensors
+        if ctx.nmap_spec is not None:
+            grads, g_nmap = grads[:-1], grads[-1]
         g_outs, g_prob = grads[:-2], grads[-2]
-        verts_c, rot_c, pos_c, proj_c, vattr_c, improb, imcomp, imidx, ws = ctx.saved_tensors
+        verts_c, rot_c, pos_c, proj_c, vattr_c, improb, imcomp, imidx, ws = saved[:9]
         meta = ctx.meta
         D, A, flags = ctx.dims
         need_verts, need_vattr = ctx.needs
         device = verts_c.device
         B, H, W, TF, I = meta["batch"], meta["height"], meta["width"], meta["total_faces"], meta["num_instances"]
         g_outs = [g.contiguous() if g is not None else None for g in g_outs]
+        if g_nmap is not None:      # rare (nobody in Self6D++ differentiates the normal map): the torch expression under autograd
+            n_src, m_src, (ni, mi) = saved[9], saved[10], ctx.nmap_spec
+            with torch.enable_grad():
+                n = n_src.detach().requires_grad_(True)
+                m = m_src.detach().requires_grad_(True)
+                shift = n - n.min()
+                y = shift / (torch.norm(shift, dim=-1, keepdim=True) + 1e-5) * m
+                gn, gm = torch.autograd.grad(y, [n, m], g_nmap)
+            g_outs[ni] = gn if g_outs[ni] is None else g_outs[ni] + gn
+            g_outs[mi] = gm if g_outs[mi] is None else g_outs[mi] + gm
         gP = g_prob.contiguous() if g_prob is not None else None
         pack = meta["pack"]
-        with torch.cuda.device(device):
-            p = _base_pass(B, H, W, D, meta["knum"], meta["multiplier"], meta["delta"], meta["expand"], TF, 0)
-            p.face_offsets = _lib.ptr(meta["face_offsets"])
-            p.num_instances = I
-            p.workspace = ctypes.c_void_p(ws.data_ptr())
-            p.workspace_bytes = ws.numel()
-            p.inst_desc = _lib.ptr(meta["inst_desc"])
-            p.verts, p.mesh_faces = _lib.ptr(verts_c), _lib.ptr(pack.faces)
-            p.vert_attr, p.vert_attr_dim, p.attr_flags = _lib.ptr(vattr_c), A, flags
-            p.verts_stride, p.vert_attr_stride = int(meta.get("verts_stride", 0)), int(meta.get("vert_attr_stride", 0))
-            pose_mode = bool(meta.get("pose_mode"))
-            if pose_mode:
-                p.pose_R, p.pose_t, p.pose_K = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
-                p.num_K = int(proj_c.shape[0])
-                p.znear, p.zfar = float(meta["znear"]), float(meta["zfar"])
-            else:
-                p.cam_rot, p.cam_pos, p.cam_proj = _lib.ptr(rot_c), _lib.ptr(pos_c), _lib.ptr(proj_c)
-            p.improb, p.imidx, p.imcomp = _lib.ptr(improb), _lib.ptr(imidx), _lib.ptr(imcomp)
+        pose_mode = bool(meta.get("pose_mode"))
+        with _on_device(device):
+            p = ctx.pass_struct
             p.grad_improb = _lib.ptr(gP)
-            p.num_outputs = len(ctx.split)
-            for g, (c, go) in enumerate(zip(ctx.split, g_outs)):
-                p.out_channels[g] = c
+            for g, go in enumerate(g_outs):
                 p.grad_out[g] = go.data_ptr() if go is not None else None
             g_p2d = torch.empty(max(TF, 1), 6, dtype=torch.float32, device=device)
-            g_fattr = torch.empty(max(TF, 1), 3, D, dtype=torch.float32, device=device)
+            # nobody reads dL/d(corner attributes) unless the vertex attributes take a gradient: attr_flags bit 2 keeps only the
+            # depth column the vertex stage needs ([F, 3] instead of [F, 3, D])
+            p.attr_flags = flags if need_vattr else (flags | FLAG_ATTR_GRAD_SCRATCH)
+            g_fattr = torch.empty(max(TF, 1), 3, D if need_vattr else 1, dtype=torch.float32, device=device)
             g_rot = torch.empty(I, 3, 3, dtype=torch.float32, device=device)
             g_pos = torch.empty(I, 3, dtype=torch.float32, device=device)
             n_rows = meta["num_inst_verts"]

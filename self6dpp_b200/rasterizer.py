@@ -42,6 +42,26 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _NoSwitch(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on_device(device):
+    """``torch.cuda.device(device)`` only when that is not the current device already (the context manager costs ~6 us of
+    host time per use; the training loop sits on one device)"""
+    index = device.index
+    if index is None or index == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(device)
+
+
 def _alloc_workspace(p, device):
     nbytes = _lib.workspace_bytes(p)
     ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)

@@ -67,8 +67,9 @@ class Renderer(nn.Module):
 
     def set_camera_parameters_lazy(self, Rs, ts, Ks, height, width, near, far, rot_type):
         """same result as set_camera_parameters_from_RT_K, computed only if somebody reads .camera_params"""
-        self._camera_params = None
-        self._camera_pending = (Rs, ts, Ks, height, width, near, far, rot_type)
+        d = self.__dict__             # plain attributes: nn.Module.__setattr__ costs ~6 us per store on this per-call path
+        d["_camera_params"] = None
+        d["_camera_pending"] = (Rs, ts, Ks, height, width, near, far, rot_type)
 
     def forward(self, points, *args, **kwargs):
         if self.camera_params is None:

@@ -67,19 +67,37 @@ class _ModelRegistry(object):
         self.table = None        # [n, 4] vert_base, num_verts, face_base, num_faces
         self.attrs = {}          # tuple(attr names) -> [sum verts, 3*len] tensor
         self.generation = 0      # bumped whenever the packed tables are rebuilt
+        self._last_ids, self._last_out, self._last_distinct = None, None, ()
 
     @staticmethod
     def _sig(model):
-        return tuple((model[k].data_ptr(), model[k]._version) for k in ("vertices", "faces"))
+        """identity and version counter of the two geometry tensors: a replaced tensor is another object, one modified in
+        place has another version (the tensors themselves are kept, so an id cannot be recycled)"""
+        v, f = model["vertices"], model["faces"]
+        return (v, v._version, f, f._version)
+
+    @staticmethod
+    def _same(sig, model):
+        v, f = model["vertices"], model["faces"]
+        return v is sig[0] and f is sig[2] and v._version == sig[1] and f._version == sig[3]
 
     def slots(self, models):
         """slot per sample, or None when a model cannot be cached (requires grad)."""
+        ids = tuple(map(id, models))
+        if ids == self._last_ids:                # the same model dicts as last time: only their tensors need another look
+            for slot in self._last_distinct:
+                m = self.models[slot]
+                if m["vertices"].requires_grad or not self._same(self.sigs[slot], m):
+                    break
+            else:
+                return self._last_out
         out = np.empty(len(models), dtype=np.int64)
         dirty = False
         if len(self.models) > 128 and any(id(m) not in self.index for m in models):
             # callers that build fresh model dicts every call would grow the registry (and every rebuild) without bound:
             # start over with the models of this call
             self.index, self.models, self.sigs = {}, [], []
+            self._last_ids = None
         for i, m in enumerate(models):
             slot = self.index.get(id(m))
             if slot is None:
@@ -95,11 +113,12 @@ class _ModelRegistry(object):
             m = self.models[slot]
             if m["vertices"].requires_grad:
                 return None
-            if self._sig(m) != self.sigs[slot]:          # tensors replaced or modified in place
+            if not self._same(self.sigs[slot], m):       # tensors replaced or modified in place
                 self.sigs[slot] = self._sig(m)
                 dirty = True
         if dirty:
             self._rebuild()
+        self._last_ids, self._last_out, self._last_distinct = ids, out, sorted(set(out.tolist()))
         return out
 
     def _rebuild(self):
@@ -220,10 +239,15 @@ class Renderer_dibr(object):
                     out_split=split, inst_desc=dev[:B * fused.INST_STRIDE],
                     face_offsets=dev[B * fused.INST_STRIDE:B * fused.INST_STRIDE + nimg + 1],
                     pose_mode=True, znear=float(znear), zfar=float(zfar), min_output=min_output)
+        if min_output is not None:
+            meta["normal_map"] = (int(min_output), len(names))        # (normals group, ones group): the map comes with the render
         meta["verts_stride"] = 4
         meta["vert_attr_stride"] = int(vattr.shape[1]) if names else 0
         res = fused.render_meshes(reg.verts4, vattr, R, ts.reshape(B, 3), K, meta)
-        return list(res[:-2]), res[-2], meta
+        nmap = None
+        if min_output is not None:           # (handed back beside meta, never inside it: meta hangs on the autograd node, and an
+            nmap, res = res[-1], res[:-1]    #  output reachable from its own node is a reference cycle)
+        return list(res[:-2]), res[-2], meta, nmap
 
     # ------------------------------------------------------------------------------------------
     def render_batch(self, Rs, ts, models, *, Ks, width, height, znear=0.01, zfar=100, rot_type="mat",
@@ -257,7 +281,7 @@ class Renderer_dibr(object):
         fast = self._render_batch_fast(Rs, ts, models, Ks, width, height, znear, zfar, rot_type, names, split, flags,
                                        min_output=min_output)
         if fast is not None:
-            outs, improb, meta = fast
+            outs, improb, meta, nmap = fast
             # the reference sets the camera as a side effect (renderer_dibr.py:261); keep that, lazily
             self.dib_ren.set_camera_parameters_lazy(Rs, ts, Ks, height, width, znear, zfar, rot_type)
         else:       # models that require grad, list-of-tensor poses, ...: generic path
@@ -274,7 +298,9 @@ class Renderer_dibr(object):
             ret["mask"] = im_mask.squeeze(-1)
         if "norm" in mode:
             _ren_norms = out["norm"]
-            if meta.get("out_min") is not None:                      # one fused kernel, min came with the rasterisation
+            if fast is not None and nmap is not None:                # came out of the render call itself (one autograd node)
+                ret["norm"] = nmap
+            elif meta.get("out_min") is not None:                    # one fused kernel, min came with the rasterisation
                 ret["norm"] = fused.NormalMap.apply(_ren_norms, im_mask, meta["out_min"])
             else:
                 ren_norms_shift = _ren_norms - _ren_norms.min()      # batch-global shift, renderer_dibr.py:284
@@ -303,7 +329,7 @@ class Renderer_dibr(object):
         fast = self._render_batch_fast(Rs, ts, models, K, width, height, znear, zfar, rot_type, ["colors"], split, flags,
                                        multi=True)
         if fast is not None:
-            outs, improb, meta = fast
+            outs, improb, meta, nmap = fast
             self.scene_ren.set_camera_parameters_lazy(Rs, ts, K, height, width, znear, zfar, rot_type)
         else:
             self.scene_ren.set_camera_parameters_from_RT_K(Rs, ts, K, height, width, near=znear, far=zfar, rot_type=rot_type)
@@ -377,7 +403,7 @@ class Renderer_dibr(object):
             fast = self._render_batch_fast(Rs, ts, models, Ks, width, height, znear, zfar, rot_type, ["vertex_uvs"], split, flags)
             if fast is not None:
                 from .renderer.tex import shade_tex
-                outs, improb, meta = fast
+                outs, improb, meta, _ = fast
                 self.dib_ren.set_camera_parameters_lazy(Rs, ts, Ks, height, width, znear, zfar, rot_type)
                 uvimg, mask = outs[0], outs[1]
                 shapes = {tuple(m["texture"].shape) for m in models}
