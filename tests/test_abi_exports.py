@@ -54,7 +54,12 @@ def test_struct_size_handshake():
     lib = _lib.load()
     assert lib.dibr_sizeof_pass() == ctypes.sizeof(_lib.DibrPass)
     assert lib.dibr_sizeof_step() == ctypes.sizeof(_lib.DibrStep)
-    assert lib.dibr_abi_version() == 3
+    import re
+    want = int(re.search(r"#define\s+DIBR_ABI_VERSION\s+(\d+)", open(os.path.join(ROOT, "include", "dibr_b200.h")).read()).group(1))
+    assert lib.dibr_abi_version() == want == 3
+    # the driver's build check must expect what the header says (it once kept a stale literal)
+    src = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    assert "DIBR_ABI_VERSION" in src and not re.search(r"dibr_abi_version\(\)\s*==\s*\d", src)
 
 
 def test_validation_runs_before_any_cuda_call():
