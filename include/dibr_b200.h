@@ -206,7 +206,12 @@ typedef struct DibrStep {
     /* optional normal-map post-processing (renderer_dibr.py:281-286); inputs are output groups of the pass */
     const float *student_normal_in, *student_mask_in; float *student_normal_out;
     const float *teacher_normal_in, *teacher_mask_in; float *teacher_normal_out;
-    int32_t run_backward;
+    int32_t run_backward;          /* bit 0 (dibr_render_step): run the backward after the forward.
+                                      bit 1: the forward call also PREPARES the backward of the student pass (zeroes
+                                      grad_points2d / the scratch grad_face_attr and builds the work lists, in the shadow of the
+                                      teacher rasterisation); dibr_render_backward / the backward half of dibr_render_step with
+                                      bit 1 set rely on that and must be the FIRST backward after such a forward -- clear the bit
+                                      for a repeated backward over the same forward (it then prepares itself) */
     int32_t grad_pose_sum;         /* != 0: device_grad_pose has num_instances + 1 rows and the last one receives the column sums
                                       of the others (added in instance order by the backward itself): the 12-float vector a
                                       data-parallel step all-reduces over NCCL, ready without another launch */

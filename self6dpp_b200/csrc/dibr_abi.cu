@@ -369,7 +369,10 @@ static int forward_impl(const DibrPass* p, void* stream, bool lists_clean) {
 
 int dibr_forward(const DibrPass* p, void* stream) { return forward_impl(p, stream, false); }
 
-int dibr_backward_faces(const DibrPass* p, void* stream) {
+// parts: bit 0 = the prepare kernel (zero dL/dpoints2d, work lists from the forward's flags), bit 1 = the face kernel.
+// dibr_render_forward runs the first part behind the student rasterisation when DibrStep.run_backward has bit 1 set, the
+// backward entry points then run the second part alone.
+static int backward_faces_impl(const DibrPass* p, void* stream, int parts) {
     if (int e = check_common(p, true)) return e;
     if (p->total_faces == 0) return 0;                      // nothing to differentiate
     const bool fused = is_fused(p);
@@ -407,9 +410,11 @@ int dibr_backward_faces(const DibrPass* p, void* stream) {
     b.grad_improb = p->grad_improb;
     b.grad_points2d = p->grad_points2d; b.grad_face_attr = p->grad_face_attr;
     b.attr_compact = attr_compact(p) ? 1 : 0;
-    g_launches += 2;     // prepare_backward_kernel + backward_faces_kernel
-    return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream));
+    g_launches += ((parts & 1) ? 1 : 0) + ((parts & 2) ? 1 : 0);     // prepare_backward_kernel, backward_faces_kernel
+    return cuda_fail("dibr_backward_faces", dibr::launch_backward_faces(b, (cudaStream_t)stream, parts));
 }
+
+int dibr_backward_faces(const DibrPass* p, void* stream) { return backward_faces_impl(p, stream, 3); }
 
 static int backward_meshes_impl(const DibrPass* p, void* stream, float* packed, int pose_sum = 0) {
     if (int e = check_common(p, true)) return e;
@@ -785,6 +790,10 @@ int render_forward_on(const DibrStep* st, void* stream, const ForkJoin& fj) {
         void* ks = (k == 0) ? fj.side(stream) : stream;          // student chain on the side stream, teacher on the caller's
         if (int e = dibr_setup_meshes(p, ks)) return e;
         if (int e = forward_impl(p, ks, true)) return e;          // the set-up call above cleared the lists and the minimum
+        // the backward's preparation (zeroed gradients, work lists from the flags the forward just set) depends on no upstream
+        // gradient: here it runs in the shadow of the teacher rasterisation instead of at the head of the backward call
+        if (k == 0 && (st->run_backward & 2))
+            if (int e = backward_faces_impl(p, ks, 1)) return e;
         if (nin[k]) {
             if (!p->out_min_ordered || p->min_output < 0) return fail("render_step: normal map needs min_output/out_min_ordered");
             if (int e = dibr_normal_map_pass(p, nin[k], nmask[k], nout[k], ks)) return e;
@@ -795,7 +804,7 @@ int render_forward_on(const DibrStep* st, void* stream, const ForkJoin& fj) {
 
 int render_backward_on(const DibrStep* st, void* ls) {
     const DibrPass* p = &st->student;
-    if (int e = dibr_backward_faces(p, ls)) return e;
+    if (int e = backward_faces_impl(p, ls, (st->run_backward & 2) ? 2 : 3)) return e;
     if (st->device_grad_pose && (!p->grad_pose_R || !p->grad_pose_t)) return fail("render_step: pose-gradient buffers are null");
     // the kernel's finalising block writes the [n,12] layout itself: no packing launch
     if (int e = backward_meshes_impl(p, ls, st->device_grad_pose, st->grad_pose_sum)) return e;
@@ -843,7 +852,7 @@ int dibr_render_step(const DibrStep* st, void* stream) {
     ForkJoin fj(both ? (Overlap*)st->overlap : nullptr, (cudaStream_t)stream);
     if (fj.err) return cuda_fail("render_step fork", fj.err);
     if (int e = render_forward_on(st, stream, fj)) return e;
-    if (st->run_backward) return render_backward_on(st, fj.side(stream));       // the student chain's stream
+    if (st->run_backward & 1) return render_backward_on(st, fj.side(stream));   // the student chain's stream
     return 0;
 }
 

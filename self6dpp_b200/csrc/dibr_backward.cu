@@ -431,13 +431,17 @@ __global__ void __launch_bounds__(PREP_THREADS) prepare_backward_kernel(const Bw
     }
 }
 
-int launch_backward_faces(const BwdParams& P, cudaStream_t stream)
+int launch_backward_faces(const BwdParams& P, cudaStream_t stream, int parts)
 {
     if (P.total_faces <= 0) return 0;
     if (P.total_faces > (1 << 28)) return (int)cudaErrorInvalidValue;       // 6 * total_faces is indexed with int
-    prepare_backward_kernel<<<min((P.total_faces + PREP_FACES - 1) / PREP_FACES, 148 * 8), PREP_THREADS, 0, stream>>>(P);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
+    cudaError_t e = cudaSuccess;
+    if (parts & 1) {
+        prepare_backward_kernel<<<min((P.total_faces + PREP_FACES - 1) / PREP_FACES, 148 * 8), PREP_THREADS, 0, stream>>>(P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (!(parts & 2)) return 0;
     const int do_color = P.any_grad_im ? 1 : 0, do_soft = (P.grad_improb && P.knum > 0) ? 1 : 0;
     if (!do_color && !do_soft) {                     // no upstream gradient at all: everything is zero
         if (P.attr_compact) return 0;                // (the prepare kernel has zeroed the compact column)

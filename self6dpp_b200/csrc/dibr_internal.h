@@ -384,7 +384,8 @@ int launch_nnd_backward(const NndParams& P, cudaStream_t stream);
 int launch_setup_faces(const SetupParams& P, cudaStream_t stream);
 int launch_setup_meshes(const SetupParams& P, cudaStream_t stream);
 int launch_forward(const FwdParams& P, cudaStream_t stream);
-int launch_backward_faces(const BwdParams& P, cudaStream_t stream);
+// parts: bit 0 = prepare (zero the gradients, build the work lists from the forward's flags), bit 1 = the face kernel
+int launch_backward_faces(const BwdParams& P, cudaStream_t stream, int parts = 3);
 int launch_backward_meshes(const MeshBwdParams& P, cudaStream_t stream);
 int launch_normal_map_tiles(int batch, int height, int width, const int* order_cnt, const int* order_seg, const float* n, const float* mask,
                             const unsigned int* min_ordered, float* out, cudaStream_t stream);

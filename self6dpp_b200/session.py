@@ -167,6 +167,7 @@ class RenderSession(object):
         # is owned by the session (or, for the backward, is the caller's gradient tensor: another tensor -> another graph).
         self.cuda_graphs = bool(cuda_graphs)
         self._graphs = {}          # key -> [calls seen, CUDAGraph or None, kernels launched per replay]
+        self._bwd_prepared = False # the last forward() prepared the backward and no backward has consumed that yet
         self._last_slots, self._last_total, self._last_ids = None, 0, None
         self._views = {name: self._h_f32[o:o + n].reshape(B, -1) for name, (o, n) in self.off.items() if name in ("sR", "st", "K", "tR", "tt")}
 
@@ -259,7 +260,11 @@ class RenderSession(object):
         st = self.st
         upload = self._stage_inputs(Rs, ts, Ks, models, teacher_Rs, teacher_ts, upload)
         st.staging_bytes = 4 * self.stage_words if upload else 0       # upload=False: inputs already resident
+        # run_backward bit 1: the forward call also prepares the backward (zeroed gradient slots, work lists from the flags the
+        # rasterisation sets) in the shadow of the teacher pass; the first backward after it starts with the face kernel
+        st.run_backward = 2
         self._run(("forward", bool(upload)), self.lib.dibr_render_forward, "dibr_render_forward")
+        self._bwd_prepared = True
         return self.outputs()
 
     def _run(self, key, fn, what):
@@ -306,7 +311,9 @@ class RenderSession(object):
         st = self.st
         ptrs = self._set_grads(grad_color, grad_prob, grad_depth)
         st.host_grad_pose = self.g_pose_host.data_ptr() if download else None
-        self._run(("backward", bool(download)) + ptrs, self.lib.dibr_render_backward, "dibr_render_backward")
+        prepared, self._bwd_prepared = self._bwd_prepared, False        # a second backward over the same forward prepares itself
+        st.run_backward = 2 if prepared else 0
+        self._run(("backward", bool(download), prepared) + ptrs, self.lib.dibr_render_backward, "dibr_render_backward")
         return self.g_pose_dev
 
     def step(self, Rs, ts, Ks, models, teacher_Rs=None, teacher_ts=None, grad_color=None, grad_prob=None,
@@ -316,7 +323,8 @@ class RenderSession(object):
         st = self.st
         upload = self._stage_inputs(Rs, ts, Ks, models, teacher_Rs, teacher_ts, upload)
         self._set_grads(grad_color, grad_prob, grad_depth)
-        st.run_backward = 1 if backward else 0
+        st.run_backward = 3 if backward else 0                         # bit 0: backward in this call; bit 1: prepared inside the forward half
+        self._bwd_prepared = False
         st.staging_bytes = 4 * self.stage_words if upload else 0       # upload=False: inputs already resident
         st.host_grad_pose = self.g_pose_host.data_ptr() if download else None
         with torch.cuda.device(self.device):
