@@ -354,5 +354,22 @@ class NormalMap(Function):
         return gn, gm, None
 
 
+class _NoGradCtx(object):
+    """stands in for the autograd context when nothing can ask for a gradient (torch.no_grad(), or no input requires one):
+    the forward runs as a plain call, without an autograd node (~20 us of host time per render)"""
+
+    def save_for_backward(self, *tensors):
+        pass
+
+    def mark_non_differentiable(self, *tensors):
+        pass
+
+    def set_materialize_grads(self, value):
+        pass
+
+
 def render_meshes(verts_packed, vattr_packed, cam_rot, cam_pos, cam_proj, meta):
+    if not torch.is_grad_enabled() or not (verts_packed.requires_grad or vattr_packed.requires_grad or cam_rot.requires_grad
+                                           or cam_pos.requires_grad or cam_proj.requires_grad):
+        return RenderMeshes.forward(_NoGradCtx(), verts_packed, vattr_packed, cam_rot, cam_pos, cam_proj, meta)
     return RenderMeshes.apply(verts_packed, vattr_packed, cam_rot, cam_pos, cam_proj, meta)
