@@ -196,7 +196,11 @@ int dibr_normal_map_pass(const DibrPass *pass, const float *normals_nx3, const f
  *   5. one D2H copy of dL/dR, dL/dt (num_instances x 12 floats) into pinned host memory.
  * Both passes are ordinary pose-mode DibrPass structs whose DEVICE pointers for pose_R / pose_t / pose_K /
  * inst_desc / face_offsets point INTO `staging_device`, laid out exactly like `staging_host`.
- * Nothing is synchronised: the caller waits on the stream before reading host_grad_pose. */
+ * Nothing is synchronised: the caller waits on the stream before reading host_grad_pose.
+ * The two host transfers are a few KB each.  When staging_host / host_grad_pose are pinned AND mapped (any cudaHostAlloc'd
+ * buffer under unified addressing) they cross the bus without a copy-engine node: a small kernel reads the staging block, and
+ * the kernel that finalises the pose gradients stores them into host_grad_pose itself (e2e 0.296 -> 0.281 ms per step);
+ * any other host pointer goes through cudaMemcpyAsync. */
 typedef struct DibrStep {
     DibrPass student;
     DibrPass teacher;

@@ -416,7 +416,7 @@ static int backward_faces_impl(const DibrPass* p, void* stream, int parts) {
 
 int dibr_backward_faces(const DibrPass* p, void* stream) { return backward_faces_impl(p, stream, 3); }
 
-static int backward_meshes_impl(const DibrPass* p, void* stream, float* packed, int pose_sum = 0) {
+static int backward_meshes_impl(const DibrPass* p, void* stream, float* packed, int pose_sum = 0, float* host_view = nullptr) {
     if (int e = check_common(p, true)) return e;
     if (p->num_instances <= 0 || !p->inst_desc || !p->verts) return fail("backward_meshes: instances and verts required");
     if (!p->pose_R && (!p->cam_rot || !p->cam_pos || !p->cam_proj)) return fail("backward_meshes: cameras required");
@@ -437,6 +437,7 @@ static int backward_meshes_impl(const DibrPass* p, void* stream, float* packed, 
     m.grad_verts = p->grad_verts; m.grad_vert_attr = p->grad_vert_attr;
     m.grad_cam_rot = p->grad_cam_rot; m.grad_cam_pos = p->grad_cam_pos; m.pose_part = w.pose_part; m.pose_done = w.pose_done;
     m.grad_pose_packed = p->pose_R ? packed : nullptr;
+    m.host_pose_packed = (p->pose_R && packed) ? host_view : nullptr;
     m.pose_sum = pose_sum;
     g_launches += 1;
     return cuda_fail("dibr_backward_meshes", dibr::launch_backward_meshes(m, (cudaStream_t)stream));
@@ -732,6 +733,38 @@ int dibr_chamfer_reduce_backward(const DibrChamferReduce* p, void* stream) {
     return cuda_fail("dibr_chamfer_reduce_backward", dibr::launch_chamfer_reduce_backward(q, (cudaStream_t)stream));
 }
 
+// The step's two host transfers are a few KB each (5.9 KB of poses / intrinsics / instance table in, 1.5 KB of pose gradients
+// out).  When the host buffer is pinned and mapped (every cudaHostAlloc'd buffer under unified addressing, torch's pinned
+// tensors included) a tiny kernel moves the words over the bus itself: the copy-engine hand-over of a cudaMemcpyAsync node
+// costs more than the transfer.  Anything else (pageable memory, unregistered pointers) goes through cudaMemcpyAsync.
+__global__ void copy_words_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+static bool device_visible_host(const void* host, const void** dev_view) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    *dev_view = a.devicePointer;
+    return true;
+}
+
+// bytes: multiple of 4, both pointers 4-byte aligned (the staging block and the gradient rows are arrays of 32-bit words)
+static int small_transfer(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+    const void* view = nullptr;
+    const bool words = (bytes & 3) == 0 && bytes <= (1u << 20) && (((uintptr_t)dst | (uintptr_t)src) & 3) == 0;
+    if (words && device_visible_host(kind == cudaMemcpyHostToDevice ? src : dst, &view)) {
+        const int n = (int)(bytes >> 2);
+        const uint32_t* sp = (const uint32_t*)(kind == cudaMemcpyHostToDevice ? view : src);
+        uint32_t* dp = (uint32_t*)(kind == cudaMemcpyHostToDevice ? dst : const_cast<void*>(view));
+        copy_words_kernel<<<(n + 255) / 256, 256, 0, s>>>(sp, dp, n);
+        g_launches += 1;
+        return (int)cudaGetLastError();
+    }
+    return (int)cudaMemcpyAsync(dst, src, bytes, kind, s);
+}
+
 // side stream + fork/join events of one session (dibr_overlap_create): owned by the caller, nothing process-global
 struct Overlap { cudaStream_t stream; cudaEvent_t fork, join; };
 
@@ -806,12 +839,16 @@ int render_backward_on(const DibrStep* st, void* ls) {
     const DibrPass* p = &st->student;
     if (int e = backward_faces_impl(p, ls, (st->run_backward & 2) ? 2 : 3)) return e;
     if (st->device_grad_pose && (!p->grad_pose_R || !p->grad_pose_t)) return fail("render_step: pose-gradient buffers are null");
-    // the kernel's finalising block writes the [n,12] layout itself: no packing launch
-    if (int e = backward_meshes_impl(p, ls, st->device_grad_pose, st->grad_pose_sum)) return e;
-    if (st->device_grad_pose && st->host_grad_pose) {
-        cudaError_t e = cudaMemcpyAsync(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)p->num_instances,
-                                        cudaMemcpyDeviceToHost, (cudaStream_t)ls);
-        if (e != cudaSuccess) return cuda_fail("render_step pose gradients", (int)e);
+    // the kernel's finalising block writes the [n,12] layout itself: no packing launch -- and, when the host buffer is pinned
+    // and mapped, straight into it: no copy behind the kernel either
+    const void* hv = nullptr;
+    const bool direct = st->device_grad_pose && st->host_grad_pose && p->pose_R && ((uintptr_t)st->host_grad_pose & 3) == 0 &&
+                        device_visible_host(st->host_grad_pose, &hv);
+    if (int e = backward_meshes_impl(p, ls, st->device_grad_pose, st->grad_pose_sum, direct ? (float*)const_cast<void*>(hv) : nullptr)) return e;
+    if (st->device_grad_pose && st->host_grad_pose && !direct) {
+        const int e = small_transfer(st->host_grad_pose, st->device_grad_pose, sizeof(float) * 12 * (size_t)p->num_instances,
+                                     cudaMemcpyDeviceToHost, (cudaStream_t)ls);
+        if (e != 0) return cuda_fail("render_step pose gradients", e);
     }
     return 0;
 }
@@ -819,8 +856,8 @@ int render_backward_on(const DibrStep* st, void* ls) {
 int render_upload(const DibrStep* st, cudaStream_t cs) {
     if (st->staging_bytes > 0) {
         if (!st->staging_host || !st->staging_device) return fail("render_step: staging buffers are null");
-        cudaError_t e = cudaMemcpyAsync(st->staging_device, st->staging_host, st->staging_bytes, cudaMemcpyHostToDevice, cs);
-        if (e != cudaSuccess) return cuda_fail("render_step H2D", (int)e);
+        const int e = small_transfer(st->staging_device, st->staging_host, st->staging_bytes, cudaMemcpyHostToDevice, cs);
+        if (e != 0) return cuda_fail("render_step H2D", e);
     }
     return 0;
 }

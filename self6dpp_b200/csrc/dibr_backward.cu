@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(MV_T) mesh_vertex_grad_kernel(MeshBwdParams P)
             const float v = sgn * tot[j * 3 + k] - Tp[j] * tot[9 + k];
             P.grad_pose_R[(size_t)inst * 9 + threadIdx.x] = v;
             if (P.grad_pose_packed) P.grad_pose_packed[(size_t)inst * 12 + threadIdx.x] = v;
+            if (P.host_pose_packed) P.host_pose_packed[(size_t)inst * 12 + threadIdx.x] = v;
         } else {
             const int j = threadIdx.x - 9;
             float gt = 0.f;
@@ -617,6 +618,7 @@ __global__ void __launch_bounds__(MV_T) mesh_vertex_grad_kernel(MeshBwdParams P)
             for (int k = 0; k < 3; k++) gt -= Rp[j * 3 + k] * tot[9 + k];
             P.grad_pose_t[(size_t)inst * 3 + j] = gt;
             if (P.grad_pose_packed) P.grad_pose_packed[(size_t)inst * 12 + 9 + j] = gt;
+            if (P.host_pose_packed) P.host_pose_packed[(size_t)inst * 12 + 9 + j] = gt;
         }
     }
     // ---- optional row num_instances of the packed gradients: their column sums, added in instance order by the block that

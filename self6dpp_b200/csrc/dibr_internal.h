@@ -178,6 +178,8 @@ struct MeshBwdParams {
     float* grad_pose_R;
     float* grad_pose_t;
     float* grad_pose_packed;   // optional [num_instances, 12]: dL/dR then dL/dt, the layout dibr_render_step copies back to the host
+    float* host_pose_packed;   // optional device view of the caller's pinned, mapped [num_instances, 12] buffer: the finalising blocks
+                               // write the rows there as well (no device-to-host copy behind the kernel)
     int pose_sum;              // the packed buffer has one more row that receives the column sums
     int attr_compact;          // grad_face_attr holds the depth channel alone, [total_faces, 3] (see BwdParams)
 };

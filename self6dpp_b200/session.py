@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib, fused
-from .rasterizer import _stream
+from .rasterizer import _on_device, _stream
 from .renderer_dibr import _ModelRegistry
 
 _MODE_ATTR = (("color", "colors"), ("norm", "normals"), ("xyz", "vertices"))
@@ -271,7 +271,7 @@ class RenderSession(object):
         """call ``fn(step, stream)`` eagerly the first time ``key`` is seen, capture it into a CUDA graph the second time,
         replay the graph afterwards"""
         st = self.st
-        with torch.cuda.device(self.device):
+        with _on_device(self.device):
             if torch.cuda.is_current_stream_capturing():                # the caller is capturing a graph of its own: plain launches
                 _lib.check(fn(ctypes.byref(st), _stream(self.device)), what)
                 return
@@ -327,7 +327,7 @@ class RenderSession(object):
         self._bwd_prepared = False
         st.staging_bytes = 4 * self.stage_words if upload else 0       # upload=False: inputs already resident
         st.host_grad_pose = self.g_pose_host.data_ptr() if download else None
-        with torch.cuda.device(self.device):
+        with _on_device(self.device):
             stream = _stream(self.device)
             _lib.check(self.lib.dibr_render_step(ctypes.byref(st), stream), "dibr_render_step")
         return self.outputs()
