@@ -317,6 +317,48 @@ def test_render_session_matches_renderer_dibr():
     assert torch.equal(out2["color"], ret2["color"]) and torch.equal(out2["prob"], ret2["prob"])
 
 
+def test_render_session_pageable_host_buffers_take_the_memcpy_path():
+    """The step's two small host transfers are moved by kernels when the host buffers are pinned and mapped (the session's own
+    are); a caller of the C ABI may hand over pageable memory, which must go through cudaMemcpyAsync and give the same bits."""
+    import ctypes
+    import numpy as np
+    from self6dpp_b200 import synth
+    from self6dpp_b200.session import RenderSession
+    from tests.golden.make_golden import small_meshes
+    meshes = small_meshes()
+    H = W = 64
+    B = 4
+    models = to_dev_models(meshes)
+    for m in models:
+        m["faces"] = m["faces"].to(torch.int32)
+    ids = [0, 2, 1, 1]
+    batch = synth.roi_batch([meshes[i] for i in ids], B, res=W, seed=51, fill=(0.45, 0.7))
+    tea = synth.roi_batch([meshes[i] for i in ids], B, res=W, seed=52, fill=(0.45, 0.7))
+    g = torch.Generator().manual_seed(6)
+    gc, gp, gd = torch.randn(B, H, W, 3, generator=g).to(DEV), torch.randn(B, H, W, generator=g).to(DEV), torch.randn(B, H, W, generator=g).to(DEV)
+    cur = [models[i] for i in ids]
+    ref = RenderSession(models, B, H, W, cuda_graphs=False)
+    ref.forward(batch["Rs"], batch["ts"], batch["Ks"], cur, tea["Rs"], tea["ts"])
+    ref.backward(gc, gp, gd)
+    ref.synchronize()
+    sess = RenderSession(models, B, H, W, cuda_graphs=False)
+    pageable_out = np.full((B, 12), np.nan, dtype=np.float32)
+    sess._stage_inputs(batch["Rs"], batch["ts"], batch["Ks"], cur, tea["Rs"], tea["ts"], True)
+    pageable_in = np.array(sess._h_i32, copy=True)              # the staging block, in ordinary host memory
+    st = sess.st
+    st.staging_host = pageable_in.ctypes.data
+    st.staging_bytes = 4 * sess.stage_words
+    st.run_backward = 0
+    stream = ctypes.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
+    assert sess.lib.dibr_render_forward(ctypes.byref(st), stream) == 0
+    sess._set_grads(gc, gp, gd)
+    st.host_grad_pose = pageable_out.ctypes.data
+    assert sess.lib.dibr_render_backward(ctypes.byref(st), stream) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(torch.from_numpy(pageable_out), ref.grad_pose)
+    assert torch.equal(sess.g_pose_dev.cpu(), ref.grad_pose)
+
+
 def test_render_session_composition_change_and_lean_teacher():
     """(1) a step that says its inputs are resident (upload=False) after the batch composition changed must still get the
     new instance table to the device; (2) RenderSession(teacher_soft_mask=False) returns the same teacher normal map and
