@@ -80,3 +80,26 @@ def test_product_refuses_cpu_tensors():
     z = torch.zeros(1, 2, 9)
     with pytest.raises(Exception):
         linear_rasterizer(8, 8, z, torch.zeros(1, 2, 6), torch.ones(1, 2, 1), torch.zeros(1, 2, 9))
+
+
+def test_pass_templates_copy_the_filled_struct():
+    """fused._pass_from_template: the size / option fields are filled once per configuration, later calls get a COPY (their
+    pointer fields must not leak into the template) and the cached workspace size (host arithmetic, no GPU)."""
+    from self6dpp_b200 import fused
+    from self6dpp_b200.rasterizer import _base_pass
+    calls = []
+
+    def build():
+        calls.append(1)
+        q = _base_pass(2, 32, 48, 5, 30, 1000, 7000, 0.02, 100, 0)
+        q.num_instances = 2
+        q.num_outputs = 2
+        q.out_channels[0], q.out_channels[1] = 3, 2
+        return q
+    key = ("test_pass_templates", 2, 32, 48)
+    p1, n1 = fused._pass_from_template(key, build)
+    p1.improb = 0x1234                                  # a pointer set by one call ...
+    p2, n2 = fused._pass_from_template(key, build)
+    assert len(calls) == 1 and n1 == n2 == _lib.workspace_bytes(build())
+    assert p2.improb is None and p1 is not p2           # ... is not in the next call's struct
+    assert (p2.batch, p2.height, p2.width, p2.num_attr, p2.total_faces, p2.num_outputs, p2.out_channels[1]) == (2, 32, 48, 5, 100, 2, 2)
