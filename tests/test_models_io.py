@@ -142,3 +142,27 @@ def test_get_dibr_models_renderer(gold, tmp_path):
     with pytest.raises(KeyError):
         M.get_dibr_models_renderer(str(tmp_path), ["duck"], {1: "ape", 5: "can"}, height=8, width=8,
                                    mode="VertexColorBatch", device="cpu")
+
+
+def test_model_registry_fast_path_still_sees_changed_tensors():
+    """_ModelRegistry.slots answers an unchanged list of model dicts from its last result (one identity + version look per
+    distinct model), and must still notice a geometry tensor modified in place, replaced, or switched to requires_grad."""
+    import torch
+    from self6dpp_b200.renderer_dibr import _ModelRegistry
+
+    def mk(n):
+        return {"vertices": torch.rand(n, 3), "faces": torch.randint(0, n, (2 * n, 3), dtype=torch.int32), "colors": torch.rand(n, 3)}
+    ms = [mk(10), mk(12), mk(8)]
+    reg = _ModelRegistry()
+    batch = [ms[0], ms[2], ms[0], ms[1]]
+    a = reg.slots(batch)
+    g0 = reg.generation
+    assert a.tolist() == [0, 1, 0, 2]
+    assert reg.slots(batch) is a and reg.slots(list(batch)) is a and reg.generation == g0      # nothing changed: cached answer
+    ms[2]["vertices"].add_(1.0)                                                                  # in place: version counter
+    assert reg.slots(batch).tolist() == [0, 1, 0, 2] and reg.generation == g0 + 1
+    ms[1]["faces"] = ms[1]["faces"].clone()                                                      # replaced: another object
+    reg.slots(batch)
+    assert reg.generation == g0 + 2
+    ms[0]["vertices"].requires_grad_(True)                                                       # cannot be cached any more
+    assert reg.slots(batch) is None
